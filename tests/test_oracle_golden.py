@@ -107,3 +107,58 @@ def test_kat_expectations():
     assert np.abs(g["ref_npBonds"][6:9]).max() >= 5.0   # midpoint left outside the box
     _, g = load_golden("kat_zero_length")
     assert np.isnan(g["ref_S"])
+
+
+# --------------------------------------------------------------------------- C oracle + RDF
+from oracle import c_oracle, rdf_oracle  # noqa: E402
+from tests.util import RDF_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", P2_CASES)
+def test_c_oracle_p2_against_golden(name):
+    melt, g = load_golden(name)
+    vec, ctr = c_oracle.bond_build(melt.positions, melt.bond_atoms, melt.box)
+    vec_np, ctr_np = po.bond_build(melt.positions, melt.bond_atoms, melt.box)
+    assert np.array_equal(vec, vec_np) and np.array_equal(ctr, ctr_np)
+    nbr, ref = p2_masks(melt, g)
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    r = c_oracle.p2(vec, ctr, molb, melt.box, float(g["case_rcut"]), bool(g["case_same_molecule"]),
+                    ref_mask=ref, nbr_mask=nbr, want_lists=True)
+    mean, count, ptr, idx = reference_dense(g, melt.n_bonds)
+    assert np.array_equal(r["count"], count)
+    if not np.isnan(mean[count > 0]).any():
+        assert np.array_equal(r["nbr_ptr"], ptr)
+        assert np.array_equal(r["nbr_idx"], idx)
+    ok = count > 0
+    np.testing.assert_allclose(r["mean"][ok], mean[ok], rtol=1e-13, atol=0, equal_nan=True)
+
+
+def _rdf_inputs(melt, g):
+    names = np.array([melt.atom_type_names[t] for t in melt.atom_type])
+    atomtypes = [str(s) for s in g["case_atomtypes"]]
+    return names, atomtypes, float(g["case_rmin"]), float(g["case_rmax"]), int(g["case_nbin"]), \
+        bool(g["case_same_molecule"])
+
+
+@pytest.mark.parametrize("name", RDF_CASES)
+def test_rdf_numpy_restatement_bit_exact(name):
+    melt, g = load_golden(name)
+    names, atomtypes, rmin, rmax, nbin, same = _rdf_inputs(melt, g)
+    types, data = rdf_oracle.pair_correlation_counts(melt.positions, names, melt.mol, melt.box, atomtypes,
+                                                     rmin, rmax, nbin, same)
+    assert types == [str(s) for s in g["ref_types"]]
+    assert sorted(data) == [str(s) for s in g["ref_keys"]]
+    for k, row in zip(g["ref_keys"], g["ref_counts"]):
+        assert np.array_equal(data[str(k)], row), k
+
+
+@pytest.mark.parametrize("name", RDF_CASES)
+def test_c_oracle_rdf_against_golden(name):
+    melt, g = load_golden(name)
+    names, atomtypes, rmin, rmax, nbin, same = _rdf_inputs(melt, g)
+    types = [str(s) for s in g["ref_types"]]
+    code = np.array([types.index(t) if (not atomtypes or t in atomtypes) else -1 for t in names], np.int32)
+    hist, _ = c_oracle.rdf(melt.positions, code, melt.mol, len(types), melt.box, rmin, rmax, nbin, same)
+    keys = [types[a] + "_" + types[b] for a in range(len(types)) for b in range(a, len(types))]
+    for k, row in zip(g["ref_keys"], g["ref_counts"]):
+        assert np.array_equal(hist[keys.index(str(k))], row), k
