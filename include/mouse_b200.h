@@ -1,0 +1,151 @@
+/* mouse_b200 - C-ABI of the B200-native local-ordering hot path.
+ *
+ * This is the drop-in boundary.  The reference (mglagolev/mouse) has no
+ * FFI of its own: its seam is the set of plain Python functions in ordering_functions.py that
+ * calculate_local_ordering.py / calculate_rdfs.py star-import.  Each entry point below names
+ * the reference lines it replaces; the Python mirror (mouse_b200/ordering_functions.py) binds
+ * them with ctypes and INTEGRATION.md shows the stub a maintainer would add upstream.
+ *
+ * Conventions: plain pointers and sizes only (no torch / C++ types); pointers marked DEV are
+ * device pointers (e.g. tensor.data_ptr()), HOST are host pointers; `stream` is a cudaStream_t
+ * passed as void*; every function returns 0 on success or a negative MOUSE_E* code and never
+ * throws; nothing allocates behind the caller's back: scratch memory is a caller-provided
+ * workspace sized by the *_workspace_bytes() queries.  All launches are asynchronous on
+ * `stream`; entry points keep no static state besides the thread-local last-error string.
+ */
+#ifndef MOUSE_B200_H
+#define MOUSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOUSE_OK 0
+#define MOUSE_EINVAL (-1)     /* bad argument */
+#define MOUSE_ECUDA (-2)      /* CUDA runtime error (see mouse_last_error) */
+#define MOUSE_EWORKSPACE (-3) /* workspace too small */
+
+/* flags for the P2 / RDF sweeps */
+#define MOUSE_SAME_MOLECULE 1u /* include pairs within one molecule (reference: sameMolecule=True) */
+#define MOUSE_FORCE_EXACT 2u   /* use the all-FP64 sweep even when the FP32-filter sweep applies */
+#define MOUSE_NO_CUTOFF 4u     /* reference: rcut < 0 (ordering_functions.py:102-103) */
+
+/* Cell grid chosen on the host for one frame (box, cutoff). */
+typedef struct mouse_grid {
+  double box[3];      /* orthorhombic edge lengths (reference Config.box(), lammpack_types.py:154) */
+  double rcut;        /* cutoff; < 0 = none */
+  double rc2;         /* the caller's Python `rcut**2` - threshold bits equal the reference's (:102) */
+  double cell_w[3];   /* cell edge per axis, >= rcut*(1+1e-6) whenever ncell_axis >= 2 */
+  int32_t ncell_axis[3];
+  int32_t ncell;      /* product */
+  int32_t fast;       /* 1: >= 3 cells on every axis and guard band small -> FP32-filter sweep valid */
+  float guard;        /* relative half-width of the FP32 guard band around rc2 */
+} mouse_grid_t;
+
+/* Totals written by the fused reductions (device or host memory, see each function). */
+typedef struct mouse_p2_totals {
+  double sum_mean;       /* sum_i m_i over references with >= 1 counted neighbour (:205) */
+  int64_t n_refs;        /* i_s (:206) */
+  int64_t n_pairs;       /* sum_i count_i = ordered in-cutoff pairs the reference counts */
+  int64_t n_zero_len;    /* zero-length bonds in the neighbour set (NaN poisoning, :112) */
+  int64_t n_hist_over;   /* values with bin index >= nbins (reference raises IndexError) */
+  int64_t n_band;        /* candidate pairs that needed the FP64 cutoff re-check (diagnostic) */
+} mouse_p2_totals_t;
+
+const char *mouse_version(void);
+const char *mouse_last_error(void);
+
+/* HOST only.  Chooses the cell grid for `n_items` points.  Returns MOUSE_OK. */
+int mouse_grid_plan(const double *box /*HOST[3]*/, double rcut, double rc2, int64_t n_items,
+                    mouse_grid_t *grid /*HOST out*/);
+
+/* K1.  Replaces vector_and_center_pbc_trim method 1 (lammpack_types.py:587-599) as called per
+ * bond by createNumpyBondsArrayFromConfig (ordering_functions.py:29) and again per reference
+ * bond (:92).  vec/ctr are the rows 3-5 / 6-8 of the reference's (9,N_b) npBonds array:
+ * SoA, vec[a*n_bonds + b]. */
+int mouse_bond_build(const double *pos /*DEV [n_atoms][3]*/, const int32_t *bond_atoms /*DEV [n_bonds][2]*/,
+                     int64_t n_bonds, const double *box /*HOST[3]*/, double *vec /*DEV [3][n_bonds]*/,
+                     double *ctr /*DEV [3][n_bonds]*/, void *stream);
+
+/* Workspace for cell list + sweep on `n_items` bonds (or atoms) with `grid`. */
+size_t mouse_workspace_bytes(int64_t n_items, const mouse_grid_t *grid);
+
+/* K2.  No reference counterpart (the reference is all-pairs, ordering_functions.py:94-115);
+ * builds the cell list over the bonds selected by nbr_mask (createNumpyBondsArrayFromConfig's
+ * allowedBondTypes filter, :25-28): single-digit radix (counting) sort by cell id, per-cell
+ * offsets, canonical (ascending bond index) order inside each cell, payload gathered into
+ * sorted float4 / double4 arrays inside the workspace.
+ * mol: per-bond molecule code (hash8(atom1.mol_id), :31,39), ref_mask: bonds that act as
+ * references (:198-199).  Masks may be NULL (= all ones). */
+int mouse_cell_build(const double *vec, const double *ctr, const int32_t *mol /*DEV [n]*/,
+                     const uint8_t *nbr_mask /*DEV [n] or NULL*/, const uint8_t *ref_mask /*DEV [n] or NULL*/,
+                     int64_t n_bonds, const mouse_grid_t *grid /*HOST*/, void *ws /*DEV*/, size_t ws_bytes,
+                     void *stream);
+
+/* K3.  Replaces calculateAveCosSqForReference (ordering_functions.py:91-119) for every
+ * reference bond at once: out_sum[b] = sum of cos^2 over the counted neighbours of bond b,
+ * out_cnt[b] = their number (0 = the reference raised NameError / bond is not a reference).
+ * Outputs are indexed by ORIGINAL bond index and fully overwritten. */
+int mouse_p2_sweep(const double *vec, const double *ctr, int64_t n_bonds, const mouse_grid_t *grid,
+                   uint32_t flags, const void *ws, double *out_sum /*DEV [n]*/, int32_t *out_cnt /*DEV [n]*/,
+                   void *stream);
+
+/* Optional second pass: the counted neighbour lists themselves (CSR over original bond index,
+ * rows ascending).  row_ptr = exclusive scan of out_cnt (n+1 entries, int64), computed here. */
+int mouse_p2_pair_lists(const double *vec, const double *ctr, int64_t n_bonds, const mouse_grid_t *grid,
+                        uint32_t flags, const void *ws, const int32_t *cnt /*DEV [n]*/,
+                        int64_t *row_ptr /*DEV [n+1] out*/, int32_t *nbr_idx /*DEV [capacity] out*/,
+                        int64_t capacity, void *stream);
+
+/* K4.  Replaces the tail of CalculateOrientationOrderParameter (ordering_functions.py:202-206,
+ * 221-224) and updateHistogram (lammpack_misc.py:185-189): per-vector mean cos^2 (NaN when
+ * count == 0), totals, optional histogram of 1.5*m-0.5 with the reference's bin rule.
+ * hist may be NULL.  totals is DEV memory. */
+int mouse_p2_reduce(const double *sum /*DEV [n]*/, const int32_t *cnt /*DEV [n]*/, int64_t n_bonds,
+                    const mouse_grid_t *grid, const void *ws, double *out_mean /*DEV [n]*/, mouse_p2_totals_t *totals /*DEV*/,
+                    int64_t *hist /*DEV [nbins] or NULL*/, double smin, double smax, int32_t nbins,
+                    void *stream);
+
+/* K1..K4 in one call, device buffers (the timed hot path of bench.py `value`). */
+int mouse_p2_frame(const double *pos, const int32_t *bond_atoms, const int32_t *mol, const uint8_t *nbr_mask,
+                   const uint8_t *ref_mask, int64_t n_bonds, const mouse_grid_t *grid, uint32_t flags,
+                   void *ws, size_t ws_bytes, double *vec, double *ctr, double *sum, int32_t *cnt,
+                   double *mean, mouse_p2_totals_t *totals, void *stream);
+
+/* K5.  Replaces calculateRdfForReference (ordering_functions.py:66-88) summed over all atoms as
+ * in CalculatePairCorrelationFunctions (:162-173), accumulating onto zeros.
+ * type: per-atom type code in [0,ntypes) or < 0 (not selected); edges: NumPy's bin edges
+ * (nbin+1 doubles, HOST); hist: int64 [ntypes*(ntypes+1)/2][nbin], overwritten. */
+int mouse_rdf_frame(const double *pos /*DEV [n][3]*/, const int32_t *type /*DEV [n]*/, const int32_t *mol /*DEV [n]*/,
+                    int64_t n_atoms, int32_t ntypes, const mouse_grid_t *grid, uint32_t flags,
+                    const double *edges /*HOST [nbin+1]*/, int32_t nbin, void *ws, size_t ws_bytes,
+                    int64_t *hist /*DEV*/, void *stream);
+
+/* One reference against a caller-built array: the reference's per-call granularity.
+ * mouse_p2_single_ref replaces calculateAveCosSqForReference (ordering_functions.py:91-119):
+ *   np_bonds DEV (9,n) f64 row-major = createNumpyBondsArrayFromConfig's array (:41);
+ *   ref HOST[8] = {bRef.x,y,z, bRefCenter.x,y,z, refBond.num, hash8(refBond.atom1.mol_id)};
+ *   rcut < 0 = no cutoff; flags: MOUSE_SAME_MOLECULE, MOUSE_INCLUDE_SELF (excludeSelf=False);
+ *   out DEV[2] = {sum of unmasked cos^2, unmasked count} (count == 0 -> the reference raises
+ *   NameError("No values to calculate"), :117).  A zero-length bRef is the caller's check (:93,119).
+ * mouse_rdf_single_ref replaces calculateRdfForReference (:66-88):
+ *   np_atoms DEV (6,n) f64 = createNumpyAtomsArrayFromConfig's array (:63);
+ *   ref HOST[5] = {x, y, z, refAtom.num, hash8(refAtom.mol_id)}; edges HOST[nbin+1] (NumPy's);
+ *   hist DEV[nbin+1]: bins, then the number of unmasked distances (0 -> NameError, :88). */
+#define MOUSE_INCLUDE_SELF 8u
+size_t mouse_single_ref_workspace_bytes(void);
+int mouse_p2_single_ref(const double *np_bonds, int64_t n, const double *ref, const double *box, double rcut,
+                        double rc2, uint32_t flags, void *ws, double *out, void *stream);
+int mouse_rdf_single_ref(const double *np_atoms, int64_t n, const double *ref, const double *box, uint32_t flags,
+                         const double *edges, int32_t nbin, void *ws, int64_t *hist, void *stream);
+
+/* Test / tuning hook: "fast_slots" (register-resident candidate slots per lane, 0 = auto). */
+int mouse_set_tuning(const char *key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOUSE_B200_H */

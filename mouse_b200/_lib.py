@@ -1,0 +1,102 @@
+"""ctypes binding of ``libmouse_b200.so`` (the C-ABI declared in ``include/mouse_b200.h``).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails the
+import / call raises.  PyTorch is only used by the callers for device memory and streams;
+this module passes raw pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmouse_b200.so")
+
+MOUSE_SAME_MOLECULE = 1
+MOUSE_FORCE_EXACT = 2
+MOUSE_NO_CUTOFF = 4
+MOUSE_INCLUDE_SELF = 8
+
+
+class Grid(C.Structure):
+    """``mouse_grid_t``"""
+    _fields_ = [("box", C.c_double * 3), ("rcut", C.c_double), ("rc2", C.c_double),
+                ("cell_w", C.c_double * 3), ("ncell_axis", C.c_int32 * 3), ("ncell", C.c_int32),
+                ("fast", C.c_int32), ("guard", C.c_float)]
+
+
+class P2Totals(C.Structure):
+    """``mouse_p2_totals_t``"""
+    _fields_ = [("sum_mean", C.c_double), ("n_refs", C.c_int64), ("n_pairs", C.c_int64),
+                ("n_zero_len", C.c_int64), ("n_hist_over", C.c_int64), ("n_band", C.c_int64)]
+
+
+EXPORTS = [
+    "mouse_version", "mouse_last_error", "mouse_set_tuning", "mouse_grid_plan", "mouse_bond_build",
+    "mouse_workspace_bytes", "mouse_cell_build", "mouse_p2_sweep", "mouse_p2_pair_lists", "mouse_p2_reduce",
+    "mouse_p2_frame", "mouse_rdf_frame", "mouse_single_ref_workspace_bytes", "mouse_p2_single_ref",
+    "mouse_rdf_single_ref",
+]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA sources in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_PKG, "csrc")]
+    if not verbose:
+        cmd.insert(1, "-s")
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("mouse_b200: %s is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, u32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_double
+    gp = C.POINTER(Grid)
+    L.mouse_version.restype = C.c_char_p
+    L.mouse_last_error.restype = C.c_char_p
+    L.mouse_set_tuning.argtypes = [C.c_char_p, C.c_int]
+    L.mouse_grid_plan.argtypes = [C.POINTER(C.c_double), dbl, dbl, i64, gp]
+    L.mouse_bond_build.argtypes = [vp, vp, i64, C.POINTER(C.c_double), vp, vp, vp]
+    L.mouse_workspace_bytes.argtypes = [i64, gp]
+    L.mouse_workspace_bytes.restype = C.c_size_t
+    L.mouse_cell_build.argtypes = [vp, vp, vp, vp, vp, i64, gp, vp, C.c_size_t, vp]
+    L.mouse_p2_sweep.argtypes = [vp, vp, i64, gp, u32, vp, vp, vp, vp]
+    L.mouse_p2_pair_lists.argtypes = [vp, vp, i64, gp, u32, vp, vp, vp, vp, i64, vp]
+    L.mouse_p2_reduce.argtypes = [vp, vp, i64, gp, vp, vp, vp, vp, dbl, dbl, i32, vp]
+    L.mouse_p2_frame.argtypes = [vp, vp, vp, vp, vp, i64, gp, u32, vp, C.c_size_t, vp, vp, vp, vp, vp, vp, vp]
+    L.mouse_rdf_frame.argtypes = [vp, vp, vp, i64, i32, gp, u32, C.POINTER(C.c_double), i32, vp, C.c_size_t, vp, vp]
+    L.mouse_single_ref_workspace_bytes.restype = C.c_size_t
+    L.mouse_p2_single_ref.argtypes = [vp, i64, C.POINTER(C.c_double), C.POINTER(C.c_double), dbl, dbl, u32, vp, vp, vp]
+    L.mouse_rdf_single_ref.argtypes = [vp, i64, C.POINTER(C.c_double), C.POINTER(C.c_double), u32,
+                                       C.POINTER(C.c_double), i32, vp, vp, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int:
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, lib().mouse_last_error().decode()))
+
+
+def grid_plan(box, rcut: float, n_items: int, rc2: float | None = None) -> Grid:
+    """Host-side cell grid.  ``rc2`` defaults to the Python expression ``rcut**2`` so that the
+    threshold bits equal the reference's (``ordering_functions.py:102``)."""
+    g = Grid()
+    b = (C.c_double * 3)(float(box[0]), float(box[1]), float(box[2]))
+    check(lib().mouse_grid_plan(b, float(rcut), float(rcut)**2 if rc2 is None else float(rc2), int(n_items),
+                                C.byref(g)), "mouse_grid_plan")
+    return g

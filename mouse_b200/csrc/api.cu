@@ -1,0 +1,218 @@
+// C-ABI entry points of libmouse_b200 (see include/mouse_b200.h for the contract).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+// launchers implemented next to their kernels
+int mouse_launch_bond_build(const double *pos, const int32_t *bond_atoms, int64_t n, const double *box,
+                            double *vec, double *ctr, cudaStream_t st);
+int mouse_launch_cell_build(int mode, const double *xyz, const double *vec, const int32_t *code,
+                            const int32_t *code2, const uint8_t *nbr_mask, const uint8_t *ref_mask, int64_t n,
+                            const mouse_grid_t *grid, const Workspace &w, cudaStream_t st);
+int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const mouse_grid_t *grid, uint32_t flags,
+                          const Workspace &w, double *out_sum, int32_t *out_cnt, const int64_t *row_ptr,
+                          int32_t *nbr_idx, cudaStream_t st);
+int mouse_launch_row_ptr(const int32_t *cnt, int64_t n, int64_t *row_ptr, cudaStream_t st);
+int mouse_launch_p2_reduce(const double *sum, const int32_t *cnt, int64_t n, const Workspace &w, double *out_mean,
+                           mouse_p2_totals_t *totals, int64_t *hist, double smin, double smax, int32_t nbins,
+                           cudaStream_t st);
+int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, int32_t ntypes, const double *edges_dev,
+                           int32_t nbin, const Workspace &w, int64_t *hist, cudaStream_t st);
+extern int mouse_fast_slots_override;
+extern int mouse_fast_variant;
+
+static thread_local char g_err[512] = "";
+
+void mouse_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" {
+
+const char *mouse_version(void) { return "mouse_b200 0.1 (sm_100a)"; }
+const char *mouse_last_error(void) { return g_err; }
+
+int mouse_set_tuning(const char *key, int value) {
+  if (!strcmp(key, "fast_slots")) mouse_fast_slots_override = value;
+  else if (!strcmp(key, "fast_variant")) mouse_fast_variant = value;
+  else {
+    mouse_set_error("unknown tuning key %s", key);
+    return MOUSE_EINVAL;
+  }
+  return MOUSE_OK;
+}
+
+int mouse_grid_plan(const double *box, double rcut, double rc2, int64_t n_items, mouse_grid_t *grid) {
+  if (!box || !grid) {
+    mouse_set_error("mouse_grid_plan: NULL argument");
+    return MOUSE_EINVAL;
+  }
+  memset(grid, 0, sizeof(*grid));
+  double cells = 1.0;
+  int nax[3];
+  for (int a = 0; a < 3; ++a) {
+    if (!(box[a] > 0.0)) {
+      mouse_set_error("mouse_grid_plan: box[%d]=%g must be positive", a, box[a]);
+      return MOUSE_EINVAL;
+    }
+    int k = 1;
+    if (rcut > 0.0) {
+      double q = box[a] / (rcut * (1.0 + 1e-6));
+      k = q >= 1.0 ? (q > 1024.0 ? 1024 : (int)q) : 1;
+    }
+    nax[a] = k;
+    cells *= k;
+  }
+  // dilute systems: do not allocate many more cells than items
+  double cap = 4.0 * (double)(n_items > 16 ? n_items : 16);
+  if (cap > 2.0e8) cap = 2.0e8;
+  if (cells > cap) {
+    double f = cbrt(cap / cells);
+    for (int a = 0; a < 3; ++a) {
+      int k = (int)(nax[a] * f);
+      nax[a] = k < 1 ? 1 : k;
+    }
+  }
+  double ratio = 0.0;
+  int fast = rcut > 0.0;
+  for (int a = 0; a < 3; ++a) {
+    grid->box[a] = box[a];
+    grid->ncell_axis[a] = nax[a];
+    grid->cell_w[a] = box[a] / nax[a];
+    if (nax[a] < 3) fast = 0;
+    if (rcut > 0.0 && grid->cell_w[a] / rcut > ratio) ratio = grid->cell_w[a] / rcut;
+  }
+  grid->ncell = nax[0] * nax[1] * nax[2];
+  grid->rcut = rcut;
+  grid->rc2 = rc2;
+  // FP32 error budget of the fast sweep (DESIGN.md "guard band"): relative error of d2 at the cutoff
+  // <= 1.45e-6 * (cell_w / rcut) + 1.8e-7; keep a 16x margin, never below 2^-14.
+  double guard = 16.0 * (1.5e-6 * ratio + 2.0e-7);
+  if (guard < 6.103515625e-05) guard = 6.103515625e-05;
+  if (guard > 1.0e-2) fast = 0;
+  grid->guard = (float)guard;
+  grid->fast = fast;
+  return MOUSE_OK;
+}
+
+size_t mouse_workspace_bytes(int64_t n_items, const mouse_grid_t *grid) {
+  if (!grid || n_items < 0) return 0;
+  return mouse_carve(nullptr, n_items, grid->ncell).bytes;
+}
+
+static int check_ws(const char *who, int64_t n, const mouse_grid_t *grid, void *ws, size_t ws_bytes, Workspace *w) {
+  if (!grid || !ws) {
+    mouse_set_error("%s: NULL grid/workspace", who);
+    return MOUSE_EINVAL;
+  }
+  if (n < 0 || n >= 2147483647LL) {
+    mouse_set_error("%s: n=%lld out of range", who, (long long)n);
+    return MOUSE_EINVAL;
+  }
+  *w = mouse_carve(ws, n, grid->ncell);
+  if (ws_bytes < w->bytes) {
+    mouse_set_error("%s: workspace %zu < required %zu bytes", who, ws_bytes, w->bytes);
+    return MOUSE_EWORKSPACE;
+  }
+  if (((uintptr_t)ws & 255u) != 0) {
+    mouse_set_error("%s: workspace must be 256-byte aligned", who);
+    return MOUSE_EINVAL;
+  }
+  return MOUSE_OK;
+}
+
+int mouse_bond_build(const double *pos, const int32_t *bond_atoms, int64_t n_bonds, const double *box, double *vec,
+                     double *ctr, void *stream) {
+  if (!pos || !bond_atoms || !box || !vec || !ctr) {
+    if (n_bonds == 0) return MOUSE_OK;
+    mouse_set_error("mouse_bond_build: NULL argument");
+    return MOUSE_EINVAL;
+  }
+  return mouse_launch_bond_build(pos, bond_atoms, n_bonds, box, vec, ctr, (cudaStream_t)stream);
+}
+
+int mouse_cell_build(const double *vec, const double *ctr, const int32_t *mol, const uint8_t *nbr_mask,
+                     const uint8_t *ref_mask, int64_t n_bonds, const mouse_grid_t *grid, void *ws, size_t ws_bytes,
+                     void *stream) {
+  Workspace w;
+  int rc = check_ws("mouse_cell_build", n_bonds, grid, ws, ws_bytes, &w);
+  if (rc) return rc;
+  return mouse_launch_cell_build(0, ctr, vec, mol, nullptr, nbr_mask, ref_mask, n_bonds, grid, w,
+                                 (cudaStream_t)stream);
+}
+
+int mouse_p2_sweep(const double *vec, const double *ctr, int64_t n_bonds, const mouse_grid_t *grid, uint32_t flags,
+                   const void *ws, double *out_sum, int32_t *out_cnt, void *stream) {
+  if (!grid || !ws || !out_sum || !out_cnt) {
+    mouse_set_error("mouse_p2_sweep: NULL argument");
+    return MOUSE_EINVAL;
+  }
+  Workspace w = mouse_carve((void *)ws, n_bonds, grid->ncell);
+  return mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, out_sum, out_cnt, nullptr, nullptr,
+                               (cudaStream_t)stream);
+}
+
+int mouse_p2_pair_lists(const double *vec, const double *ctr, int64_t n_bonds, const mouse_grid_t *grid,
+                        uint32_t flags, const void *ws, const int32_t *cnt, int64_t *row_ptr, int32_t *nbr_idx,
+                        int64_t capacity, void *stream) {
+  if (!grid || !ws || !cnt || !row_ptr || !nbr_idx) {
+    mouse_set_error("mouse_p2_pair_lists: NULL argument");
+    return MOUSE_EINVAL;
+  }
+  (void)capacity;  // the caller sizes nbr_idx from sum(cnt); rows are written strictly inside row_ptr
+  Workspace w = mouse_carve((void *)ws, n_bonds, grid->ncell);
+  int rc = mouse_launch_row_ptr(cnt, n_bonds, row_ptr, (cudaStream_t)stream);
+  if (rc) return rc;
+  // rank_of is free after the cell build: scratch "entries written so far" per row
+  return mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, nullptr, w.rank_of, row_ptr, nbr_idx,
+                               (cudaStream_t)stream);
+}
+
+int mouse_p2_reduce(const double *sum, const int32_t *cnt, int64_t n_bonds, const mouse_grid_t *grid,
+                       const void *ws, double *out_mean, mouse_p2_totals_t *totals, int64_t *hist, double smin,
+                       double smax, int32_t nbins, void *stream) {
+  if (!sum || !cnt || !ws || !out_mean || !totals || !grid) {
+    mouse_set_error("mouse_p2_reduce: NULL argument");
+    return MOUSE_EINVAL;
+  }
+  Workspace w = mouse_carve((void *)ws, n_bonds, grid->ncell);
+  return mouse_launch_p2_reduce(sum, cnt, n_bonds, w, out_mean, totals, hist, smin, smax, nbins,
+                                (cudaStream_t)stream);
+}
+
+int mouse_p2_frame(const double *pos, const int32_t *bond_atoms, const int32_t *mol, const uint8_t *nbr_mask,
+                   const uint8_t *ref_mask, int64_t n_bonds, const mouse_grid_t *grid, uint32_t flags, void *ws,
+                   size_t ws_bytes, double *vec, double *ctr, double *sum, int32_t *cnt, double *mean,
+                   mouse_p2_totals_t *totals, void *stream) {
+  Workspace w;
+  int rc = check_ws("mouse_p2_frame", n_bonds, grid, ws, ws_bytes, &w);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = mouse_bond_build(pos, bond_atoms, n_bonds, grid->box, vec, ctr, stream))) return rc;
+  if ((rc = mouse_launch_cell_build(0, ctr, vec, mol, nullptr, nbr_mask, ref_mask, n_bonds, grid, w, st))) return rc;
+  if ((rc = mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, sum, cnt, nullptr, nullptr, st))) return rc;
+  return mouse_launch_p2_reduce(sum, cnt, n_bonds, w, mean, totals, nullptr, 0.0, 0.0, 0, st);
+}
+
+int mouse_rdf_frame(const double *pos, const int32_t *type, const int32_t *mol, int64_t n_atoms, int32_t ntypes,
+                    const mouse_grid_t *grid, uint32_t flags, const double *edges, int32_t nbin, void *ws,
+                    size_t ws_bytes, int64_t *hist, void *stream) {
+  Workspace w;
+  int rc = check_ws("mouse_rdf_frame", n_atoms, grid, ws, ws_bytes, &w);
+  if (rc) return rc;
+  if (!pos || !type || !edges || !hist || ntypes < 1 || nbin < 1 || nbin > MOUSE_MAX_BINS) {
+    mouse_set_error("mouse_rdf_frame: bad argument (ntypes=%d nbin=%d)", ntypes, nbin);
+    return MOUSE_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  MOUSE_CUDA_CHECK(cudaMemcpyAsync(w.edges, edges, sizeof(double) * (size_t)(nbin + 1), cudaMemcpyHostToDevice, st));
+  if ((rc = mouse_launch_cell_build(1, pos, nullptr, type, mol, nullptr, nullptr, n_atoms, grid, w, st))) return rc;
+  return mouse_launch_rdf_sweep(grid, flags, n_atoms, ntypes, w.edges, nbin, w, hist, st);
+}
+
+}  // extern "C"

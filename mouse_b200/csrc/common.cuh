@@ -1,0 +1,157 @@
+// Internal helpers shared by the kernels of libmouse_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mouse_b200.h"
+
+#define MOUSE_FULL_MASK 0xffffffffu
+
+// ------------------------------------------------------------------ error plumbing
+void mouse_set_error(const char *fmt, ...);
+
+#define MOUSE_CUDA_CHECK(expr)                                                            \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      mouse_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                      __LINE__);                                                          \
+      return MOUSE_ECUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+#define MOUSE_LAUNCH_CHECK(name)                                                          \
+  do {                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      mouse_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));           \
+      return MOUSE_ECUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+// ------------------------------------------------------------------ workspace layout
+// Everything the cell list and the sweeps need, carved out of one caller-provided buffer.
+struct Workspace {
+  // per cell
+  int32_t *cell_count;   // [ncell+1]   items per cell (atomic histogram), last entry unused
+  int32_t *cell_start;   // [ncell+1]   exclusive scan; cell_start[ncell] = items in the list
+  int32_t *scan_blocks;  // [scan_nblocks+1]
+  // per item, original order
+  int32_t *cell_of;      // [n] cell id or -1 (not in the list)
+  int32_t *rank_of;      // [n] arrival rank inside the cell (atomic order, canonicalised later)
+  // per item, cell-sorted (tmp = arrival order, final = ascending original index inside a cell)
+  float4 *p_tmp;         // [n] cell-local x,y,z (FP32) + molecule/type code bits
+  double4 *u_tmp;        // [n] unit bond vector (FP64) + |b|^2   (P2)  /  absolute position (RDF)
+  int32_t *idx_tmp;      // [n] original index
+  float4 *p_sorted;
+  double4 *u_sorted;
+  int32_t *idx_sorted;
+  int32_t *cell_sorted;  // [n] cell id of each sorted slot
+  uint8_t *flag_sorted;  // [n] bit0 = acts as reference
+  // scalars
+  int64_t *counters;     // [8]: 0 = zero-length bonds in the neighbour set, 1 = band re-checks,
+                         //      2 = reduce ticket, 3.. scratch
+  double *partials;      // [3 * MOUSE_REDUCE_BLOCKS] block partials of the fused reduction
+  double *edges;         // [MOUSE_MAX_BINS + 1] device copy of the RDF bin edges
+  size_t bytes;
+};
+
+#define MOUSE_REDUCE_BLOCKS 1024
+#define MOUSE_SCAN_TILE 2048
+#define MOUSE_MAX_BINS 8192
+
+static inline size_t mouse_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Carves `ws` (may be NULL to only compute the size).  Identical on the query and on the use.
+static inline Workspace mouse_carve(void *ws, int64_t n, int32_t ncell) {
+  Workspace w;
+  size_t off = 0;
+  char *base = (char *)ws;
+  size_t nn = (size_t)(n > 0 ? n : 1);
+  size_t nc = (size_t)ncell + 1;
+  size_t nsb = (nc + MOUSE_SCAN_TILE - 1) / MOUSE_SCAN_TILE + 1;
+#define CARVE(field, type, count)                     \
+  w.field = (type *)(base ? base + off : nullptr);    \
+  off = mouse_align_up(off + sizeof(type) * (count), 256);
+  CARVE(cell_count, int32_t, nc)
+  CARVE(cell_start, int32_t, nc)
+  CARVE(scan_blocks, int32_t, nsb)
+  CARVE(cell_of, int32_t, nn)
+  CARVE(rank_of, int32_t, nn)
+  CARVE(p_tmp, float4, nn)
+  CARVE(u_tmp, double4, nn)
+  CARVE(idx_tmp, int32_t, nn)
+  CARVE(p_sorted, float4, nn)
+  CARVE(u_sorted, double4, nn)
+  CARVE(idx_sorted, int32_t, nn)
+  CARVE(cell_sorted, int32_t, nn)
+  CARVE(flag_sorted, uint8_t, nn)
+  CARVE(counters, int64_t, 8)
+  CARVE(partials, double, 3 * MOUSE_REDUCE_BLOCKS)
+  CARVE(edges, double, MOUSE_MAX_BINS + 1)
+#undef CARVE
+  w.bytes = off;
+  return w;
+}
+
+// ------------------------------------------------------------------ grid passed by value to kernels
+struct GridDev {
+  double box[3];
+  double cw[3];
+  double rc2;
+  int nc[3];
+  int ncell;
+  float cwf[3];
+  float rc2_lo, rc2_hi;  // FP32 guard band: d2 < lo sure hit, d2 > hi sure miss
+};
+
+static inline GridDev mouse_grid_dev(const mouse_grid_t *g) {
+  GridDev d;
+  for (int a = 0; a < 3; ++a) {
+    d.box[a] = g->box[a];
+    d.cw[a] = g->cell_w[a];
+    d.nc[a] = g->ncell_axis[a];
+    d.cwf[a] = (float)g->cell_w[a];
+  }
+  d.rc2 = g->rc2;
+  d.ncell = g->ncell;
+  double lo = g->rc2 * (1.0 - (double)g->guard), hi = g->rc2 * (1.0 + (double)g->guard);
+  d.rc2_lo = nextafterf((float)lo, 0.0f);
+  d.rc2_hi = nextafterf((float)hi, 3.0e38f);
+  return d;
+}
+
+// ------------------------------------------------------------------ exact (reference-order) arithmetic
+// np.around(x) == rint (half to even); `dr - L * around(dr / L)` un-fused, true division
+// (ordering_functions.py:98-100).
+__device__ __forceinline__ double mouse_trim(double dr, double L) {
+  return __dsub_rn(dr, __dmul_rn(L, rint(__ddiv_rn(dr, L))));
+}
+
+// rsq of ordering_functions.py:95-101 for centres (cix..) and (cjx..): (x^2 + y^2) + z^2
+__device__ __forceinline__ double mouse_rsq_exact(double cix, double ciy, double ciz, double cjx,
+                                                  double cjy, double cjz, const double *box) {
+  double tx = mouse_trim(__dsub_rn(cjx, cix), box[0]);
+  double ty = mouse_trim(__dsub_rn(cjy, ciy), box[1]);
+  double tz = mouse_trim(__dsub_rn(cjz, ciz), box[2]);
+  return __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
+}
+
+// un-fused dot product of ordering_functions.py:112: (bx*bx' + by*by') + bz*bz'
+__device__ __forceinline__ double mouse_dot_exact(double ax, double ay, double az, double bx,
+                                                  double by, double bz) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by)), __dmul_rn(az, bz));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MOUSE_FULL_MASK, v, o);
+  return v;
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MOUSE_FULL_MASK, v, o);
+  return v;
+}

@@ -1,0 +1,399 @@
+// K3: the pair sweep.  Replaces calculateAveCosSqForReference (ordering_functions.py:91-119)
+// for all reference bonds of a frame at once.
+//
+// Two kernels:
+//  * p2_sweep_fast_kernel - one warp per home cell.  The candidates of the 27 neighbour cells
+//    are concatenated and held in REGISTERS (SLOTS x 32 lanes, cell-local FP32 coordinates
+//    pre-shifted by the periodic cell offset), the home cell's reference bonds are looped
+//    warp-uniformly, every lane tests its candidates with 3 FADD + FMUL + 2 FFMA + compare.
+//    Sure hits (d2 < rc2*(1-g)) go straight to the FP64 cos^2; candidates inside the FP32
+//    guard band are re-decided by the reference's exact FP64 expression (mouse_rsq_exact).
+//    cos^2 = (u_i . u_j)^2 on FP64 unit vectors; |u_i . u_j| < 1e-9 falls back to the exact
+//    un-fused raw dot so that the reference's "cos^2 == 0 is masked" rule (:113) is bit-exact.
+//    Per-reference sums are reduced with warp shuffles in a fixed order (deterministic).
+//  * p2_sweep_exact_kernel - one thread per reference, all FP64, literally the reference's
+//    expression per candidate.  Valid for ANY grid (fewer than 3 cells on an axis, rcut < 0,
+//    rmax == 0 -> half diagonal); also the on-device cross-check of the fast kernel.
+#include "common.cuh"
+
+struct SweepArgs {
+  GridDev g;
+  const float4 *P;
+  const double4 *U;
+  const int32_t *idx;
+  const int32_t *cell_start;
+  const int32_t *cell_sorted;
+  const uint8_t *flag;
+  const double *vec;  // SoA [3][n], original order
+  const double *ctr;
+  int n;
+  double *out_sum;
+  int32_t *out_cnt;
+  int64_t *counters;
+  const int64_t *row_ptr;  // lists only
+  int32_t *nbr_idx;
+  int same_molecule;
+  int no_cutoff;
+};
+
+// ------------------------------------------------------------------ rare exact paths (fast kernel)
+__device__ __noinline__ bool band_recheck(const SweepArgs &a, int si, int sj) {
+  const size_t n = (size_t)a.n;
+  const int bi = a.idx[si], bj = a.idx[sj];
+  double rsq = mouse_rsq_exact(a.ctr[bi], a.ctr[n + bi], a.ctr[2 * n + bi], a.ctr[bj], a.ctr[n + bj],
+                               a.ctr[2 * n + bj], a.g.box);
+  atomicAdd((unsigned long long *)&a.counters[1], 1ULL);
+  return rsq <= a.g.rc2;
+}
+
+// exact value of the reference's cos^2 expression (:112) for sorted slots si, sj
+__device__ __noinline__ double cos2_exact(const SweepArgs &a, int si, int sj) {
+  const size_t n = (size_t)a.n;
+  const int bi = a.idx[si], bj = a.idx[sj];
+  double ax = a.vec[bi], ay = a.vec[n + bi], az = a.vec[2 * n + bi];
+  double bx = a.vec[bj], by = a.vec[n + bj], bz = a.vec[2 * n + bj];
+  double dot = mouse_dot_exact(ax, ay, az, bx, by, bz);
+  double nr = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+  double nj = __dadd_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)), __dmul_rn(bz, bz));
+  return __ddiv_rn(__ddiv_rn(__dmul_rn(dot, dot), nr), nj);
+}
+
+#define FAST_WARPS 4
+
+template <int SLOTS, bool EXCL_MOL, bool LISTS>
+__global__ void __launch_bounds__(FAST_WARPS * 32) p2_sweep_fast_kernel(const SweepArgs a) {
+  __shared__ int s_start[FAST_WARPS][32];
+  __shared__ int s_pref[FAST_WARPS][32];
+  __shared__ float s_off[FAST_WARPS][3][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
+  int *my_start = s_start[wib];
+  int *my_pref = s_pref[wib];
+  const float rc2_lo = a.g.rc2_lo, rc2_hi = a.g.rc2_hi;
+  // zero-length bonds in the neighbour set turn every mean into NaN and add to every count
+  // (0/0 in ordering_functions.py:112)
+  const long long nzero = LISTS ? 0 : a.counters[0];
+
+  for (int home = blockIdx.x * FAST_WARPS + wib; home < a.g.ncell; home += gridDim.x * FAST_WARPS) {
+    const int hs = a.cell_start[home], he = a.cell_start[home + 1];
+    if (hs == he) continue;
+    const int cx = home % nx, cy = (home / nx) % ny, cz = home / (nx * ny);
+    int st = 0, cn = 0;
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    if (lane < 27) {
+      const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+      int mx = cx + dx, my = cy + dy, mz = cz + dz;
+      mx += (mx < 0) ? nx : 0;
+      mx -= (mx >= nx) ? nx : 0;
+      my += (my < 0) ? ny : 0;
+      my -= (my >= ny) ? ny : 0;
+      mz += (mz < 0) ? nz : 0;
+      mz -= (mz >= nz) ? nz : 0;
+      const int cid = (mz * ny + my) * nx + mx;
+      st = a.cell_start[cid];
+      cn = a.cell_start[cid + 1] - st;
+      ox = (float)dx * a.g.cwf[0];
+      oy = (float)dy * a.g.cwf[1];
+      oz = (float)dz * a.g.cwf[2];
+    }
+    int incl = cn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(MOUSE_FULL_MASK, incl, o);
+      if (lane >= o) incl += y;
+    }
+    const int T = __shfl_sync(MOUSE_FULL_MASK, incl, 31);
+    __syncwarp();
+    my_start[lane] = st;
+    my_pref[lane] = incl - cn;
+    s_off[wib][0][lane] = ox;
+    s_off[wib][1][lane] = oy;
+    s_off[wib][2][lane] = oz;
+    __syncwarp();
+
+    for (int base = 0; base < T; base += 32 * SLOTS) {
+      float xr[SLOTS], yr[SLOTS], zr[SLOTS];
+      int jr[SLOTS], mr[SLOTS];
+#pragma unroll
+      for (int c = 0; c < SLOTS; ++c) {
+        const int t = base + 32 * c + lane;
+        xr[c] = 1e30f;
+        yr[c] = 0.f;
+        zr[c] = 0.f;
+        jr[c] = -1;
+        mr[c] = 0;
+        if (t < T) {
+          int k = 0;  // largest k < 27 with pref[k] <= t
+#pragma unroll
+          for (int step = 16; step > 0; step >>= 1) {
+            const int k2 = k + step;
+            if (k2 < 27 && my_pref[k2] <= t) k = k2;
+          }
+          const int j = my_start[k] + (t - my_pref[k]);
+          const float4 p = __ldg(a.P + j);
+          xr[c] = p.x + s_off[wib][0][k];
+          yr[c] = p.y + s_off[wib][1][k];
+          zr[c] = p.z + s_off[wib][2][k];
+          jr[c] = j;
+          mr[c] = __float_as_int(p.w);
+        }
+      }
+      const int nslots = min(SLOTS, (T - base + 31) >> 5);
+
+      for (int i = hs; i < he; ++i) {
+        if (!(a.flag[i] & 1)) continue;
+        const float4 pi = __ldg(a.P + i);
+        const double4 ui = a.U[i];
+        const int moli = __float_as_int(pi.w);
+        double acc = 0.0;
+        int cnt = 0;
+        int64_t row = 0;
+        if (LISTS) row = a.row_ptr[a.idx[i]] + a.out_cnt[a.idx[i]];  // out_cnt = entries written so far
+#pragma unroll
+        for (int c = 0; c < SLOTS; ++c) {
+          if (c < nslots) {
+            const float dx = xr[c] - pi.x, dy = yr[c] - pi.y, dz = zr[c] - pi.z;
+            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            bool hit = (d2 <= rc2_hi) && (EXCL_MOL ? (mr[c] != moli) : (jr[c] != i));
+            bool counted = false;
+            if (hit) {
+              if (d2 >= rc2_lo) hit = band_recheck(a, i, jr[c]);
+              if (hit) {
+                const double4 uj = a.U[jr[c]];
+                const double d = fma(ui.x, uj.x, fma(ui.y, uj.y, ui.z * uj.z));
+                double q = d * d;
+                counted = true;
+                if (fabs(d) < 1e-9) {  // near-perpendicular: decide the ==0 mask exactly
+                  q = cos2_exact(a, i, jr[c]);
+                  counted = (q != 0.0);
+                }
+                if (counted) {
+                  acc += q;
+                  cnt += 1;
+                }
+              }
+            }
+            if (LISTS) {
+              const unsigned m = __ballot_sync(MOUSE_FULL_MASK, counted);
+              if (counted) a.nbr_idx[row + __popc(m & ((1u << lane) - 1u))] = a.idx[jr[c]];
+              row += __popc(m);
+            }
+          }
+        }
+        acc = warp_sum(acc);
+        cnt = warp_sum(cnt);
+        if (lane == 0) {
+          const int o = a.idx[i];
+          if (LISTS) {
+            a.out_cnt[o] += cnt;
+          } else if (base == 0) {
+            if (nzero) {
+              acc = __longlong_as_double(0x7ff8000000000000LL);
+              cnt += (int)nzero;
+            }
+            a.out_sum[o] = acc;
+            a.out_cnt[o] = cnt;
+          } else {
+            a.out_sum[o] += acc;
+            a.out_cnt[o] += cnt;
+          }
+        }
+        if (LISTS) __syncwarp();
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ exact all-FP64 sweep
+template <bool LISTS>
+__global__ void __launch_bounds__(128) p2_sweep_exact_kernel(const SweepArgs a) {
+  const int n_list = a.cell_start[a.g.ncell];
+  const size_t n = (size_t)a.n;
+  const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_list; s += gridDim.x * blockDim.x) {
+    if (!(a.flag[s] & 1)) continue;
+    const int bi = a.idx[s];
+    const double cix = a.ctr[bi], ciy = a.ctr[n + bi], ciz = a.ctr[2 * n + bi];
+    const double bix = a.vec[bi], biy = a.vec[n + bi], biz = a.vec[2 * n + bi];
+    const double nr = __dadd_rn(__dadd_rn(__dmul_rn(bix, bix), __dmul_rn(biy, biy)), __dmul_rn(biz, biz));
+    const int moli = __float_as_int(a.P[s].w);
+    const int home = a.cell_sorted[s];
+    const int cx = home % nx, cy = (home / nx) % ny, cz = home / (nx * ny);
+    // neighbour cells per axis: {c-1, c, c+1} wrapped when the axis has >= 3 cells, else all cells
+    const int mx = nx >= 3 ? 3 : nx, my = ny >= 3 ? 3 : ny, mz = nz >= 3 ? 3 : nz;
+    double sum = 0.0;
+    int cnt = 0;
+    int64_t row = 0;
+    if (LISTS) row = a.row_ptr[bi];
+    for (int kz = 0; kz < mz; ++kz) {
+      const int zc = nz >= 3 ? (cz + kz - 1 + nz) % nz : kz;
+      for (int ky = 0; ky < my; ++ky) {
+        const int yc = ny >= 3 ? (cy + ky - 1 + ny) % ny : ky;
+        for (int kx = 0; kx < mx; ++kx) {
+          const int xc = nx >= 3 ? (cx + kx - 1 + nx) % nx : kx;
+          const int cid = (zc * ny + yc) * nx + xc;
+          const int ts = a.cell_start[cid], te = a.cell_start[cid + 1];
+          for (int t = ts; t < te; ++t) {
+            if (t == s) continue;
+            if (!a.same_molecule && __float_as_int(a.P[t].w) == moli) continue;
+            const int bj = a.idx[t];
+            if (!a.no_cutoff) {
+              double rsq = mouse_rsq_exact(cix, ciy, ciz, a.ctr[bj], a.ctr[n + bj], a.ctr[2 * n + bj], a.g.box);
+              if (!(rsq <= a.g.rc2)) continue;
+            }
+            const double dot = mouse_dot_exact(bix, biy, biz, a.vec[bj], a.vec[n + bj], a.vec[2 * n + bj]);
+            const double nj = a.U[t].w;
+            const double cs = __ddiv_rn(__ddiv_rn(__dmul_rn(dot, dot), nr), nj);
+            if (cs != 0.0) {
+              if (LISTS) a.nbr_idx[row + cnt] = bj;
+              sum += cs;
+              cnt += 1;
+            }
+          }
+        }
+      }
+    }
+    if (!LISTS) {
+      const long long nzero = a.counters[0];
+      if (nzero) {
+        sum = __longlong_as_double(0x7ff8000000000000LL);
+        cnt += (int)nzero;
+      }
+      a.out_sum[bi] = sum;
+      a.out_cnt[bi] = cnt;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ row_ptr = exclusive scan of cnt (lists)
+__global__ void __launch_bounds__(1024) row_ptr_kernel(const int32_t *__restrict__ cnt, int n,
+                                                       int64_t *__restrict__ row_ptr) {
+  // single block, sequential chunks; only used on the (non-hot) pair-list extraction path
+  __shared__ long long s_warp[32];
+  __shared__ long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    int k = base + threadIdx.x;
+    long long v = k < n ? cnt[k] : 0;
+    long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long y = __shfl_up_sync(MOUSE_FULL_MASK, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      long long w = s_warp[threadIdx.x], xs = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        long long y = __shfl_up_sync(MOUSE_FULL_MASK, xs, o);
+        if (threadIdx.x >= o) xs += y;
+      }
+      s_warp[threadIdx.x] = xs - w;
+    }
+    __syncthreads();
+    long long carry = s_carry;
+    long long incl = x + s_warp[threadIdx.x >> 5];
+    if (k < n) row_ptr[k] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) row_ptr[n] = s_carry;
+}
+
+// ------------------------------------------------------------------ launchers
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int SLOTS>
+static void launch_fast(const SweepArgs &a, bool excl_mol, bool lists, int blocks, cudaStream_t st) {
+  if (lists) {
+    if (excl_mol)
+      p2_sweep_fast_kernel<SLOTS, true, true><<<blocks, FAST_WARPS * 32, 0, st>>>(a);
+    else
+      p2_sweep_fast_kernel<SLOTS, false, true><<<blocks, FAST_WARPS * 32, 0, st>>>(a);
+  } else {
+    if (excl_mol)
+      p2_sweep_fast_kernel<SLOTS, true, false><<<blocks, FAST_WARPS * 32, 0, st>>>(a);
+    else
+      p2_sweep_fast_kernel<SLOTS, false, false><<<blocks, FAST_WARPS * 32, 0, st>>>(a);
+  }
+}
+
+int mouse_fast_slots_override = 0;  // test / tuning hooks (set through mouse_set_tuning)
+int mouse_fast_variant = 0;
+
+int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const mouse_grid_t *grid, uint32_t flags,
+                          const Workspace &w, double *out_sum, int32_t *out_cnt, const int64_t *row_ptr,
+                          int32_t *nbr_idx, cudaStream_t st) {
+  SweepArgs a;
+  a.g = mouse_grid_dev(grid);
+  a.P = w.p_sorted;
+  a.U = w.u_sorted;
+  a.idx = w.idx_sorted;
+  a.cell_start = w.cell_start;
+  a.cell_sorted = w.cell_sorted;
+  a.flag = w.flag_sorted;
+  a.vec = vec;
+  a.ctr = ctr;
+  a.n = (int)n;
+  a.out_sum = out_sum;
+  a.out_cnt = out_cnt;
+  a.counters = w.counters;
+  a.row_ptr = row_ptr;
+  a.nbr_idx = nbr_idx;
+  a.same_molecule = (flags & MOUSE_SAME_MOLECULE) ? 1 : 0;
+  a.no_cutoff = (flags & MOUSE_NO_CUTOFF) ? 1 : 0;
+  const bool lists = nbr_idx != nullptr;
+  if (n == 0) return MOUSE_OK;
+  if (!lists) {
+    MOUSE_CUDA_CHECK(cudaMemsetAsync(out_sum, 0, sizeof(double) * (size_t)n, st));
+  }
+  MOUSE_CUDA_CHECK(cudaMemsetAsync(out_cnt, 0, sizeof(int32_t) * (size_t)n, st));
+  const bool fast = grid->fast && !(flags & (MOUSE_FORCE_EXACT | MOUSE_NO_CUTOFF));
+  if (fast) {
+    // SLOTS*32 registers-resident candidates per pass: size for mean + ~3 sigma of 27 cells
+    double mean = 27.0 * (double)n / (double)grid->ncell;
+    int need = (int)((mean + 3.0 * sqrt(mean) + 31.0) / 32.0);
+    int slots = need <= 4 ? 4 : need <= 8 ? 8 : need <= 12 ? 12 : 16;
+    if (mouse_fast_slots_override) slots = mouse_fast_slots_override;
+    int blocks = (grid->ncell + FAST_WARPS - 1) / FAST_WARPS;
+    int maxb = num_sms() * 16;
+    if (blocks > maxb) blocks = maxb;
+    const bool excl = !a.same_molecule;
+    switch (slots) {
+      case 4: launch_fast<4>(a, excl, lists, blocks, st); break;
+      case 8: launch_fast<8>(a, excl, lists, blocks, st); break;
+      case 12: launch_fast<12>(a, excl, lists, blocks, st); break;
+      default: launch_fast<16>(a, excl, lists, blocks, st); break;
+    }
+    MOUSE_LAUNCH_CHECK("p2_sweep_fast_kernel");
+  } else {
+    int blocks = (int)((n + 127) / 128);
+    int maxb = num_sms() * 32;
+    if (blocks > maxb) blocks = maxb;
+    if (lists)
+      p2_sweep_exact_kernel<true><<<blocks, 128, 0, st>>>(a);
+    else
+      p2_sweep_exact_kernel<false><<<blocks, 128, 0, st>>>(a);
+    MOUSE_LAUNCH_CHECK("p2_sweep_exact_kernel");
+  }
+  return MOUSE_OK;
+}
+
+int mouse_launch_row_ptr(const int32_t *cnt, int64_t n, int64_t *row_ptr, cudaStream_t st) {
+  row_ptr_kernel<<<1, 1024, 0, st>>>(cnt, (int)n, row_ptr);
+  MOUSE_LAUNCH_CHECK("row_ptr_kernel");
+  return MOUSE_OK;
+}

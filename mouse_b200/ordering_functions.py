@@ -1,0 +1,299 @@
+"""Drop-in mirror of the reference's ``ordering_functions.py`` call surface.
+
+Same function names, argument meaning, return types and error behaviour as the reference
+(mglagolev/mouse), but every array computation runs in hand-written sm_100a kernels reached
+through the C-ABI of ``libmouse_b200.so``.  ``config`` may be a reference-style ``Config``
+(duck-typed: ``atoms() / bonds() / box()``) or a ``mouse_b200.frames.FrameArrays``.
+
+There is no CPU fallback: without the CUDA extension or a device these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+from .frames import FrameArrays, hash8
+from .lammpack_misc import createHistogram, normHistogram
+
+__all__ = ["hash8", "createNumpyBondsArrayFromConfig", "createNumpyAtomsArrayFromConfig",
+           "calculateRdfForReference", "calculateAveCosSqForReference", "CalculatePairCorrelationFunctions",
+           "CalculateOrientationOrderParameter"]
+
+
+def _arrays(config) -> FrameArrays:
+    return config if isinstance(config, FrameArrays) else FrameArrays.from_config(config)
+
+
+class DeviceBackedArray(np.ndarray):
+    """NumPy array (what the reference returns) that remembers its device copy, so that the
+    per-reference functions do not re-upload it on every call."""
+    _dev = None
+
+    def device_tensor(self):
+        if self._dev is None or self._dev.shape != self.shape:
+            self._dev = torch.as_tensor(np.ascontiguousarray(self), dtype=torch.float64).cuda()
+        return self._dev
+
+
+def _device_copy(a):
+    if isinstance(a, DeviceBackedArray):
+        return a.device_tensor()
+    if isinstance(a, torch.Tensor):
+        return a.to(device="cuda", dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+# --------------------------------------------------------------------------------------- a3 / a8
+def createNumpyBondsArrayFromConfig(config, allowedBondTypes=[], allowedResTypes=[], allowedMolIds=[],
+                                    allowedBondNums=[]):
+    """(9, N_b) float64 array ``[num, hash8(res_type), hash8(mol_id), bx, by, bz, rx, ry, rz]`` of the
+    bonds passing the filters - reference ``ordering_functions.py:14-41``.  The bond vectors and
+    midpoints (rows 3-8, ``lammpack_types.py:587-599``) come from the ``bond_build`` kernel."""
+    fa = _arrays(config)
+    mask = fa.bond_mask(allowedBondTypes, allowedResTypes, allowedMolIds, allowedBondNums)
+    sel = np.flatnonzero(mask)
+    engine.require_cuda()
+    vec, ctr = engine.bond_build(fa.positions, fa.bond_atoms[sel], fa.box)
+    dev = torch.empty((9, len(sel)), dtype=torch.float64, device=vec.device)
+    dev[0] = torch.as_tensor(fa.bond_num[sel].astype(np.float64)).to(vec.device)
+    dev[1] = torch.as_tensor(fa.bond_res_hash()[sel].astype(np.float64)).to(vec.device)
+    dev[2] = torch.as_tensor(fa.bond_mol_hash()[sel].astype(np.float64)).to(vec.device)
+    dev[3:6] = vec
+    dev[6:9] = ctr
+    out = dev.cpu().numpy().view(DeviceBackedArray)
+    out._dev = dev
+    return out
+
+
+def createNumpyAtomsArrayFromConfig(config, allowedAtomTypes=[], allowedResTypes=[], allowedMolIds=[],
+                                    allowedAtomNums=[]):
+    """(6, N) float64 array ``[num, hash8(res_type), hash8(mol_id), x, y, z]`` - reference
+    ``ordering_functions.py:44-63`` (its py3 ``map`` bug is not reproduced: the intended array is
+    returned).  Pure selection, no arithmetic."""
+    fa = _arrays(config)
+    m = np.ones(fa.n_atoms, bool)
+    for values, allowed in ((fa.atom_type, allowedAtomTypes), (fa.atom_res, allowedResTypes),
+                            (fa.atom_mol, allowedMolIds), (fa.atom_num.tolist(), allowedAtomNums)):
+        if len(allowed) != 0:
+            s = set(allowed)
+            m &= np.fromiter((v in s for v in values), bool, fa.n_atoms)
+    sel = np.flatnonzero(m)
+    out = np.empty((6, len(sel)), np.float64)
+    out[0] = fa.atom_num[sel]
+    out[1] = fa.atom_res_hash()[sel]
+    out[2] = fa.atom_mol_hash()[sel]
+    out[3:6] = fa.positions[sel].T
+    return out.view(DeviceBackedArray)
+
+
+# --------------------------------------------------------------------------------------- a1 on the host
+def _bond_vector(p1, p2, box):
+    """``vector_and_center_pbc_trim`` (``lammpack_types.py:587-599``) for ONE bond, scalar host
+    arithmetic in the reference's operation order (used for the reference bond of the
+    per-reference call, ``ordering_functions.py:92``)."""
+    vec, ctr = [], []
+    for a in range(3):
+        L = float(box[a])
+        x = p2[a] - p1[a]
+        xc = (p2[a] + p1[a]) / 2.
+        xt = np.remainder(x + L / 2., L) - L / 2.
+        vec.append(np.float64(xt))
+        ctr.append(np.float64(xc + (xt - x) / 2.))
+    return vec, ctr
+
+
+def _box3(config):
+    if isinstance(config, FrameArrays):
+        return [float(v) for v in config.box]
+    b = config.box()
+    return [float(b.x), float(b.y), float(b.z)]
+
+
+_sr_ws = {}
+
+
+def _single_ref_ws(device):
+    key = str(device)
+    if key not in _sr_ws:
+        n = _lib.lib().mouse_single_ref_workspace_bytes()
+        _sr_ws[key] = (torch.zeros(n + 256, dtype=torch.uint8, device=device),
+                       torch.zeros(2, dtype=torch.float64, device=device))
+    return _sr_ws[key]
+
+
+# --------------------------------------------------------------------------------------- a4
+def calculateAveCosSqForReference(config, refBond, npBonds, rcut, excludeSelf=True, sameMolecule=True):
+    """Mean cos^2 between ``refBond`` and every column of ``npBonds`` within ``rcut`` -
+    reference ``ordering_functions.py:91-119``; raises ``NameError`` exactly where it does."""
+    box = _box3(config)
+    p1 = (refBond.atom1.pos.x, refBond.atom1.pos.y, refBond.atom1.pos.z)
+    p2 = (refBond.atom2.pos.x, refBond.atom2.pos.y, refBond.atom2.pos.z)
+    b, c = _bond_vector(p1, p2, box)
+    if b[0] != 0. or b[1] != 0. or b[2] != 0.:
+        if rcut >= 0.:
+            rc2 = rcut**2
+        else:
+            rc2 = 0.
+        dev = _device_copy(npBonds)
+        n = int(dev.shape[1])
+        mol_hash = hash8(refBond.atom1.mol_id)
+        if not sameMolecule:
+            if n and bool((dev[2] == float(hash8(''))).any().item()):
+                raise NameError("We should omit the atoms belonging to the same molecules, but some mol_ids are empty")
+        ws, out = _single_ref_ws(dev.device)
+        ref = (C.c_double * 8)(float(b[0]), float(b[1]), float(b[2]), float(c[0]), float(c[1]), float(c[2]),
+                               float(refBond.num), float(mol_hash))
+        flags = (_lib.MOUSE_SAME_MOLECULE if sameMolecule else 0) | (0 if excludeSelf else _lib.MOUSE_INCLUDE_SELF)
+        _lib.check(_lib.lib().mouse_p2_single_ref(C.c_void_p(dev.data_ptr()), n, ref, (C.c_double * 3)(*box),
+                                                  float(rcut), float(rc2), flags, C.c_void_p(ws.data_ptr()),
+                                                  C.c_void_p(out.data_ptr()),
+                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "mouse_p2_single_ref")
+        s, cnt = out.cpu().tolist()
+        if cnt > 0:
+            return np.float64(s) / np.float64(cnt)
+        raise NameError("No values to calculate")
+    raise NameError("Zero length of reference bond " + str(refBond.num))
+
+
+# --------------------------------------------------------------------------------------- a6
+def calculateRdfForReference(config, refAtom, npAtoms, rmin=0., rmax=-1., nbin=100, excludeSelf=True,
+                             sameMolecule=True):
+    """``np.histogram`` of the distances between ``refAtom`` and the columns of ``npAtoms`` -
+    reference ``ordering_functions.py:66-88``.  Returns ``(counts int64[nbin], edges float64[nbin+1])``."""
+    box = _box3(config)
+    if rmax < 0.:
+        rmax = min(box) / 2.
+    dev = _device_copy(npAtoms)
+    n = int(dev.shape[1]) if dev.dim() == 2 else 0
+    if not sameMolecule and n and bool((dev[2] == float(hash8(''))).any().item()):
+        raise NameError("We should omit the atoms belonging to the same molecules, but some mol_ids are empty")
+    edges = np.ascontiguousarray(np.histogram_bin_edges(np.zeros(0), bins=nbin, range=(rmin, rmax)), np.float64)
+    nbin = len(edges) - 1
+    ws, _ = _single_ref_ws(dev.device if n else torch.device("cuda"))
+    hist = torch.zeros(nbin + 1, dtype=torch.int64, device=ws.device)
+    if n:
+        ref = (C.c_double * 5)(float(refAtom.pos.x), float(refAtom.pos.y), float(refAtom.pos.z), float(refAtom.num),
+                               float(hash8(refAtom.mol_id)))
+        flags = (_lib.MOUSE_SAME_MOLECULE if sameMolecule else 0) | (0 if excludeSelf else _lib.MOUSE_INCLUDE_SELF)
+        _lib.check(_lib.lib().mouse_rdf_single_ref(C.c_void_p(dev.data_ptr()), n, ref, (C.c_double * 3)(*box), flags,
+                                                   edges.ctypes.data_as(C.POINTER(C.c_double)), nbin,
+                                                   C.c_void_p(ws.data_ptr()), C.c_void_p(hist.data_ptr()),
+                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "mouse_rdf_single_ref")
+    h = hist.cpu().numpy()
+    if h[nbin] > 0:
+        return h[:nbin].copy(), edges
+    raise NameError("No values to calculate")
+
+
+# --------------------------------------------------------------------------------------- a7
+def CalculatePairCorrelationFunctions(config, atomtypes=[], rmin=0., rmax=0., nbin=100, sameMolecule=True,
+                                      verbose=True):
+    """All-pairs RDF histograms per atom-type pair - reference ``ordering_functions.py:122-177``
+    with the counts accumulated onto zeros (the reference starts from uninitialised memory,
+    ``:155``).  Returns ``{'r', 'v', 'data': {"ti_tj": float64[nbin]}, 'norm': {"ti_tj": float}}``."""
+    fa = _arrays(config)
+    box = _box3(config)
+    if rmax < 0.:
+        rmax = min(box) / 2.
+    types = []
+    for t in fa.atom_type:
+        if atomtypes is None or len(atomtypes) == 0 or (t in atomtypes):
+            if t not in types:
+                types.append(t)
+    types.append('AAAAA')
+    types.sort()
+    rdfs = {}
+    rdfs['r'] = [rmin + (rmax - rmin) * (i + 0.5) / nbin for i in range(nbin)]
+    volumes = []
+    for i in range(nbin):
+        r1 = rmin + (rmax - rmin) * i / nbin
+        r2 = rmin + (rmax - rmin) * (i + 1) / nbin
+        volumes.append(4. / 3. * np.pi * (r2**3 - r1**3))
+    rdfs['v'] = volumes
+    code_of = {t: k for k, t in enumerate(types)}
+    tcode = np.fromiter((code_of.get(t, -1) for t in fa.atom_type), np.int32, fa.n_atoms)
+    if not sameMolecule and bool(np.any((fa.atom_mol_hash() == hash8('')) & (tcode >= 0))):
+        hist = np.zeros((len(types) * (len(types) + 1) // 2, nbin), np.int64)   # every reference raises NameError
+    else:
+        h, _ = engine.rdf_frame(fa.positions, tcode, fa.atom_mol_hash().astype(np.int32), len(types), box, rmin,
+                                rmax, nbin, same_molecule=sameMolecule)
+        hist = h.cpu().numpy()
+    rdfdata, norm = {}, {}
+    slot = 0
+    volume = box[0] * box[1] * box[2]
+    for i in range(len(types)):
+        for j in range(i, len(types)):
+            key = str(types[i]) + '_' + str(types[j])
+            rdfdata[key] = hist[slot].astype(np.float64)
+            norm[key] = float(np.sum(hist[slot])) / 2. / box[0] / box[1] / box[2]
+            slot += 1
+    del volume
+    rdfs['data'] = rdfdata
+    rdfs['norm'] = norm
+    if verbose:
+        sys.stderr.write(str(rdfs))
+    return rdfs
+
+
+# --------------------------------------------------------------------------------------- a5
+def CalculateOrientationOrderParameter(config, bondtypes, rmin=0., rmax=0., storeAsAtomtypes=False, mode='average',
+                                       smin=-0.5, smax=1.0, sbins=75, referenceResTypes=[], sameMolecule=True):
+    """Local orientational order parameter S = <3cos^2(theta)-1>/2 over neighbouring bond pairs -
+    reference ``ordering_functions.py:180-227``.  ``rmin`` is accepted and ignored, as in the
+    reference.  ``mode='average'`` returns ``np.float64``; ``mode='histo'`` returns the
+    reference's histogram dict; ``storeAsAtomtypes`` rewrites ``atom.type`` to ``CXX``/``CmXX``."""
+    fa = _arrays(config)
+    box = _box3(config)
+    if rmax == 0.:
+        rmax = engine.half_diagonal(box)
+    if rmax is None:
+        raise TypeError("'>=' not supported between instances of 'NoneType' and 'float'")
+    if mode == 'histo':
+        s_hist = createHistogram(smin, smax, sbins)
+        for i in range(sbins):
+            sleft, sright = smin + i * s_hist["step"], smin + (i + 1) * s_hist["step"]
+            costhetaleft, costhetaright = (2. / 3. * (sleft + 0.5))**0.5, (2. / 3. * (sright + 0.5))**0.5
+            s_hist["norm"][i] = 1. / (costhetaleft + costhetaright)
+    nbr_mask = fa.bond_mask(bond_types=bondtypes)
+    ref_mask = fa.bond_mask(bond_types=bondtypes, res_types=referenceResTypes)
+    mol = fa.bond_mol_hash().astype(np.int32)
+    all_skipped = False
+    if not sameMolecule and bool(np.any(nbr_mask & (fa.bond_mol_hash() == hash8('')))):
+        all_skipped = True   # every reference raises NameError (:107-109) and is skipped (:214)
+        ref_mask = np.zeros_like(ref_mask)
+    res = engine.p2_frame(fa.positions, fa.bond_atoms, mol, box, rmax, same_molecule=sameMolecule,
+                          nbr_mask=nbr_mask, ref_mask=ref_mask,
+                          hist_args=(smin, smax, sbins) if mode == 'histo' else None)
+    if storeAsAtomtypes and not isinstance(config, FrameArrays):
+        _store_as_atomtypes(config, fa, res)
+    if mode == 'average':
+        return res.order_parameter()
+    elif mode == 'histo':
+        t = res.totals_dict()
+        if t["n_hist_over"] > 0:
+            raise IndexError("list index out of range")
+        s_hist["values"] = [float(v) for v in res.hist.cpu().tolist()]
+        normHistogram(s_hist)
+        return s_hist
+
+
+def _store_as_atomtypes(config, fa, res):
+    """``ordering_functions.py:207-220``: per atom, mean P2 of its reference bonds that produced
+    a value; the per-bond values come from the device, the (tiny) per-atom mean is host logic."""
+    mean = res.mean.cpu().numpy()
+    count = res.count.cpu().numpy()
+    per_atom = {}
+    for b in np.flatnonzero(count > 0):
+        p2 = 1.5 * mean[b] - 0.5
+        for a in fa.bond_atoms[b]:
+            per_atom.setdefault(int(a), []).append(p2)
+    atoms = config.atoms()
+    for a, vals in per_atom.items():
+        m = np.mean(vals)
+        atoms[a].type = ("C" + "%02d" % int(m * 100)) if m >= 0. else ("Cm" + "%02d" % int(m * -100))

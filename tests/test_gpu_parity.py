@@ -1,0 +1,270 @@
+"""Parity of the CUDA path (through the C-ABI) against the golden vectors of the real reference
+and against the oracle.  Bit-exact: bond vectors/midpoints, neighbour counts, pair lists, RDF
+histograms.  Tolerance 1e-5 relative (north_star) on P2 / S - in practice ~1e-13."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from tests.util import (P2_CASES, RDF_CASES, config_from_melt, load_golden, p2_masks,  # noqa: E402
+                        reference_dense)
+
+RTOL = 1e-5       # north_star tolerance for floating-point results
+ATOL_MEAN = 1e-14  # rounding-noise floor of an FP64 mean of O(100) terms in [0,1]
+
+
+def _engine():
+    from mouse_b200 import engine
+    engine.require_cuda()
+    return engine
+
+
+def _run(melt, g, exact):
+    eng = _engine()
+    nbr, ref = p2_masks(melt, g)
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    res = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, float(g["case_rcut"]),
+                       same_molecule=bool(g["case_same_molecule"]), nbr_mask=nbr, ref_mask=ref, exact=exact)
+    return eng, res
+
+
+@pytest.mark.parametrize("name", P2_CASES)
+def test_bond_build_bit_exact(name):
+    melt, g = load_golden(name)
+    eng = _engine()
+    vec, ctr = eng.bond_build(melt.positions, melt.bond_atoms, melt.box)
+    nbr, _ = p2_masks(melt, g)
+    assert np.array_equal(vec.cpu().numpy()[:, nbr], g["ref_npBonds"][3:6])
+    assert np.array_equal(ctr.cpu().numpy()[:, nbr], g["ref_npBonds"][6:9])
+
+
+@pytest.mark.parametrize("exact", [False, True], ids=["fast", "exact"])
+@pytest.mark.parametrize("name", P2_CASES)
+def test_p2_against_golden(name, exact):
+    melt, g = load_golden(name)
+    eng, res = _run(melt, g, exact)
+    mean, count, ptr, idx = reference_dense(g, melt.n_bonds)
+    got_cnt = res.count.cpu().numpy().astype(np.int64)
+    assert np.array_equal(got_cnt, count)                                   # bit-exact counts
+    ok = count > 0
+    got_mean = res.mean.cpu().numpy()
+    np.testing.assert_allclose(got_mean[ok], mean[ok], rtol=1e-12, atol=ATOL_MEAN, equal_nan=True)
+    assert np.isnan(got_mean[~ok]).all()
+    p2_ref, p2_got = 1.5 * mean[ok] - 0.5, 1.5 * got_mean[ok] - 0.5
+    np.testing.assert_allclose(p2_got, p2_ref, rtol=RTOL, atol=1e-13, equal_nan=True)
+    t = res.totals_dict()
+    assert t["n_refs"] == int(ok.sum()) and t["n_pairs"] == int(count.sum())
+    if "ref_S_unbound" in g:
+        with pytest.raises(UnboundLocalError):
+            res.order_parameter()
+    elif np.isnan(g["ref_S"]):
+        assert np.isnan(res.order_parameter())
+    else:
+        assert abs(res.order_parameter() - g["ref_S"]) <= RTOL * abs(g["ref_S"])
+    if not np.isnan(mean[ok]).any():                                        # bit-exact pair lists
+        row_ptr, nbr_idx = eng.p2_pair_lists(res, same_molecule=bool(g["case_same_molecule"]), exact=exact)
+        assert np.array_equal(row_ptr.cpu().numpy(), ptr)
+        assert np.array_equal(nbr_idx.cpu().numpy().astype(np.int64), idx)
+
+
+def test_fast_path_is_used_on_config1():
+    melt, g = load_golden("config1_9900_rc15")
+    _, res = _run(melt, g, False)
+    assert res.grid.fast == 1 and min(res.grid.ncell_axis) >= 3
+
+
+@pytest.mark.parametrize("same", [True, False])
+@pytest.mark.parametrize("shape,rc", [((40, 51), 1.5), ((200, 101), 2.5), ((500, 41), 3.0)])
+def test_p2_against_c_oracle(shape, rc, same):
+    from mouse_b200.melt import make_melt
+    from oracle import c_oracle
+    melt = make_melt(shape[0], shape[1], seed=11, aspect=(1.0, 1.2, 0.9))
+    eng = _engine()
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    res = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, rc, same_molecule=same)
+    vec, ctr = c_oracle.bond_build(melt.positions, melt.bond_atoms, melt.box)
+    assert np.array_equal(res.vec.cpu().numpy().T, vec) and np.array_equal(res.ctr.cpu().numpy().T, ctr)
+    ora = c_oracle.p2(vec, ctr, molb, melt.box, rc, same, want_lists=True)
+    assert np.array_equal(res.count.cpu().numpy().astype(np.int64), ora["count"])
+    ok = ora["count"] > 0
+    np.testing.assert_allclose(res.mean.cpu().numpy()[ok], ora["mean"][ok], rtol=1e-12, atol=ATOL_MEAN)
+    row_ptr, nbr_idx = eng.p2_pair_lists(res, same_molecule=same)
+    assert np.array_equal(row_ptr.cpu().numpy(), ora["nbr_ptr"])
+    assert np.array_equal(nbr_idx.cpu().numpy().astype(np.int64), ora["nbr_idx"])
+    # the exact (all-FP64) kernel agrees with the fast one bit-for-bit on counts
+    res2 = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, rc, same_molecule=same, exact=True)
+    assert np.array_equal(res2.count.cpu().numpy().astype(np.int64), ora["count"])
+    np.testing.assert_allclose(res2.mean.cpu().numpy()[ok], ora["mean"][ok], rtol=1e-12, atol=ATOL_MEAN)
+
+
+def test_p2_full_size_config2():
+    """BASELINE config 2: 1M bonds, rc = 2.5 - counts bit-exact against the C oracle."""
+    from mouse_b200.melt import make_melt
+    from oracle import c_oracle
+    melt = make_melt(10000, 101, seed=0)
+    eng = _engine()
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    vec, ctr = c_oracle.bond_build(melt.positions, melt.bond_atoms, melt.box)
+    for same in (True, False):
+        res = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, 2.5, same_molecule=same)
+        ora = c_oracle.p2(vec, ctr, molb, melt.box, 2.5, same)
+        assert np.array_equal(res.count.cpu().numpy().astype(np.int64), ora["count"])
+        ok = ora["count"] > 0
+        np.testing.assert_allclose(res.mean.cpu().numpy()[ok], ora["mean"][ok], rtol=1e-12, atol=ATOL_MEAN)
+        s_ref = 1.5 * ora["mean"][ok].sum() / ok.sum() - 0.5
+        assert abs(res.order_parameter() - s_ref) <= RTOL * abs(s_ref)
+        assert res.totals_dict()["n_pairs"] == int(ora["count"].sum())
+
+
+def test_deterministic_and_slot_variants():
+    from mouse_b200 import _lib
+    from mouse_b200.melt import make_melt
+    melt = make_melt(100, 101, seed=2)
+    eng = _engine()
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    base = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, 2.5)
+    s0, c0 = base.sum.clone(), base.count.clone()
+    for slots in (0, 4, 8, 12, 16):
+        _lib.lib().mouse_set_tuning(b"fast_slots", slots)
+        try:
+            r = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, 2.5)
+            assert torch.equal(r.count, c0)
+            if slots == 0:
+                assert torch.equal(r.sum, s0)            # run-to-run bit-identical
+            else:
+                torch.testing.assert_close(r.sum, s0, rtol=1e-13, atol=1e-13)
+        finally:
+            _lib.lib().mouse_set_tuning(b"fast_slots", 0)
+
+
+def test_edge_cases():
+    eng = _engine()
+    box = [10., 10., 10.]
+    # empty frame
+    res = eng.p2_frame(np.zeros((0, 3)), np.zeros((0, 2), np.int32), np.zeros(0, np.int32), box, 2.0)
+    assert res.totals_dict()["n_refs"] == 0
+    with pytest.raises(UnboundLocalError):
+        res.order_parameter()
+    # a single bond has no neighbours
+    res = eng.p2_frame(np.array([[0., 0, 0], [1., 0, 0]]), np.array([[0, 1]], np.int32), np.zeros(1, np.int32), box, 2.0)
+    assert res.count.cpu().tolist() == [0]
+    # no cutoff (rcut < 0): every other bond is a neighbour
+    from mouse_b200.melt import make_melt
+    from oracle import p2_oracle as po
+    melt = make_melt(3, 9, seed=4)
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    res = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, -1.0)
+    assert set(res.count.cpu().tolist()) == {melt.n_bonds - 1}
+    vec, ctr = po.bond_build(melt.positions, melt.bond_atoms, melt.box)
+    lit = po.p2_literal(vec, ctr, np.arange(1, melt.n_bonds + 1), molb, melt.box, -1.0)
+    np.testing.assert_allclose(res.mean.cpu().numpy(), lit["mean"], rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------- mirror API
+def test_mirror_api_order_parameter_and_histogram():
+    from mouse_b200 import ordering_functions as of
+    melt, g = load_golden("melt_290_rc15_same")
+    cfg = config_from_melt(melt)
+    s = of.CalculateOrientationOrderParameter(cfg, ["1"], 0., 1.5, mode="average", sameMolecule=True)
+    assert isinstance(s, np.float64) and abs(s - g["ref_S"]) <= RTOL * abs(g["ref_S"])
+    smin, smax, sbins = g["histo_args"]
+    h = of.CalculateOrientationOrderParameter(cfg, ["1"], 0., 1.5, mode="histo", smin=float(smin), smax=float(smax),
+                                              sbins=int(sbins), sameMolecule=True)
+    assert np.array_equal(np.array(h["values"]), g["ref_histo_values"])
+    assert np.array_equal(np.array(h["norm"]), g["ref_histo_norm"]) and h["step"] == g["ref_histo_step"]
+    from mouse_b200.lammpack_misc import printHistogram
+    assert printHistogram(h, norm=False) == str(g["ref_histo_print"])
+    of.CalculateOrientationOrderParameter(cfg, ["1"], 0., 1.5, storeAsAtomtypes=True, sameMolecule=True)
+    assert np.array_equal(np.array([a.type for a in cfg.atoms()]), g["ref_atom_types_after"])
+
+
+def test_mirror_api_selection_and_errors():
+    from mouse_b200 import ordering_functions as of
+    melt, g = load_golden("ortho_960_types_sel")
+    cfg = config_from_melt(melt)
+    s = of.CalculateOrientationOrderParameter(cfg, ["1"], 0., 1.8, referenceResTypes=["R0", "R2"], sameMolecule=False)
+    assert abs(s - g["ref_S"]) <= RTOL * abs(g["ref_S"])
+    melt, g = load_golden("kat_rmax_default")
+    s = of.CalculateOrientationOrderParameter(config_from_melt(melt), ["1"])       # rmax == 0 -> half diagonal
+    assert abs(s - g["ref_S"]) <= RTOL * abs(g["ref_S"])
+    melt, g = load_golden("kat_parallel")
+    cfg = config_from_melt(melt)
+    assert of.CalculateOrientationOrderParameter(cfg, ["1"], 0., 2.5) == 1.0
+    with pytest.raises(IndexError):
+        of.CalculateOrientationOrderParameter(cfg, ["1"], 0., 2.5, mode="histo")
+    melt, g = load_golden("kat_no_neighbours")
+    with pytest.raises(UnboundLocalError):
+        of.CalculateOrientationOrderParameter(config_from_melt(melt), ["1"], 0., 1.0)
+    melt, g = load_golden("kat_zero_length")
+    assert np.isnan(of.CalculateOrientationOrderParameter(config_from_melt(melt), ["1"], 0., 2.0))
+
+
+def test_mirror_api_per_reference_functions():
+    from mouse_b200 import ordering_functions as of
+    melt, g = load_golden("melt_980_rc25_diffmol")
+    cfg = config_from_melt(melt)
+    npb = of.createNumpyBondsArrayFromConfig(cfg, allowedBondTypes=["1"])
+    assert npb.shape == g["ref_npBonds"].shape
+    assert np.array_equal(npb[0], g["ref_npBonds"][0]) and np.array_equal(npb[3:], g["ref_npBonds"][3:])
+    mean, count, _, _ = reference_dense(g, melt.n_bonds)
+    for b in (0, 1, 17, 400, 979):
+        v = of.calculateAveCosSqForReference(cfg, cfg.bonds()[b], npb, 2.5, sameMolecule=False)
+        assert abs(v - mean[b]) <= 1e-12 * abs(mean[b])
+    melt, g = load_golden("kat_zero_length")
+    cfg = config_from_melt(melt)
+    npb = of.createNumpyBondsArrayFromConfig(cfg, allowedBondTypes=["1"])
+    with pytest.raises(NameError, match="Zero length"):
+        of.calculateAveCosSqForReference(cfg, cfg.bonds()[1], npb, 2.0)
+    assert np.isnan(of.calculateAveCosSqForReference(cfg, cfg.bonds()[0], npb, 2.0))
+    melt, g = load_golden("kat_no_neighbours")
+    cfg = config_from_melt(melt)
+    npb = of.createNumpyBondsArrayFromConfig(cfg, allowedBondTypes=["1"])
+    with pytest.raises(NameError, match="No values"):
+        of.calculateAveCosSqForReference(cfg, cfg.bonds()[0], npb, 1.0)
+
+
+# ------------------------------------------------------------------------------- RDF
+@pytest.mark.parametrize("name", RDF_CASES)
+def test_rdf_against_golden(name):
+    from mouse_b200 import ordering_functions as of
+    melt, g = load_golden(name)
+    cfg = config_from_melt(melt)
+    atomtypes = [str(s) for s in g["case_atomtypes"]]
+    rdfs = of.CalculatePairCorrelationFunctions(cfg, atomtypes, float(g["case_rmin"]), float(g["case_rmax"]),
+                                                int(g["case_nbin"]), bool(g["case_same_molecule"]), verbose=False)
+    assert sorted(rdfs["data"]) == [str(s) for s in g["ref_keys"]]
+    vol = float(np.prod(melt.box))
+    for k, row in zip(g["ref_keys"], g["ref_counts"]):
+        assert np.array_equal(rdfs["data"][str(k)], row.astype(np.float64)), k       # bit-exact histogram
+        assert rdfs["norm"][str(k)] == float(row.sum()) / 2. / melt.box[0] / melt.box[1] / melt.box[2]
+    del vol
+    from oracle import rdf_oracle
+    r, v = rdf_oracle.rdf_tables(float(g["case_rmin"]), float(g["case_rmax"]), int(g["case_nbin"]))
+    assert rdfs["r"] == r and rdfs["v"] == v
+
+
+def test_rdf_single_reference_against_oracle():
+    from mouse_b200 import ordering_functions as of
+    from oracle import rdf_oracle
+    melt, g = load_golden("rdf_1000_2types_5s_1000")
+    cfg = config_from_melt(melt)
+    npa = of.createNumpyAtomsArrayFromConfig(cfg, allowedAtomTypes=["1"])
+    sel = np.flatnonzero(melt.atom_type == 0)
+    for a in (0, 5, 999):
+        atom = cfg.atoms()[a]
+        h, edges = of.calculateRdfForReference(cfg, atom, npa, rmin=0., rmax=5., nbin=1000, sameMolecule=False)
+        exp = rdf_oracle.rdf_for_reference(melt.box, melt.positions[a], a + 1, melt.mol[a], sel + 1, melt.mol[sel],
+                                           melt.positions[sel], 0., 5., 1000, same_molecule=False)
+        assert np.array_equal(h, exp)
+
+
+def test_rdf_against_c_oracle_larger():
+    from mouse_b200.melt import make_melt
+    from oracle import c_oracle
+    melt = make_melt(200, 100, seed=5, n_atom_types=2)
+    eng = _engine()
+    for same in (True, False):
+        h, edges = eng.rdf_frame(melt.positions, melt.atom_type, melt.mol, 2, melt.box, 0., 5., 1000, same_molecule=same)
+        exp, e2 = c_oracle.rdf(melt.positions, melt.atom_type, melt.mol, 2, melt.box, 0., 5., 1000, same)
+        assert np.array_equal(edges, e2) and np.array_equal(h.cpu().numpy(), exp)

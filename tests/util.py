@@ -63,3 +63,27 @@ def reference_dense(g, n_bonds):
     ptr[1:] = np.cumsum([len(l) for l in lists])
     idx = np.concatenate(lists) if n_bonds else np.zeros(0, np.int64)
     return mean, count, ptr, idx
+
+
+def config_from_melt(melt, positions=None):
+    """Reference-style Config (mouse_b200's own object model) built like read_lmp_data would."""
+    from mouse_b200.lammpack_types import Atom, Bond, Config, Vector3d
+    pos = melt.positions if positions is None else positions
+    cfg = Config()
+    cfg.set_box(Vector3d(float(melt.box[0]), float(melt.box[1]), float(melt.box[2])))
+    names = melt.mol_id_strings()
+    for i in range(melt.n_atoms):
+        a = Atom()
+        a.id, a.num, a.mol_id = str(i + 1), i + 1, names[i]
+        a.type = melt.atom_type_names[melt.atom_type[i]]
+        a.res_type = melt.res_type_names[melt.res[i]]
+        a.pos = Vector3d(float(pos[i, 0]), float(pos[i, 1]), float(pos[i, 2]))
+        cfg.insert_atom(a)
+    for b in range(melt.n_bonds):
+        bond = Bond()
+        lo, hi = sorted((int(melt.bond_atoms[b, 0]) + 1, int(melt.bond_atoms[b, 1]) + 1))
+        bond.atom1, bond.atom2 = cfg.atom_by_num(lo), cfg.atom_by_num(hi)
+        bond.type = melt.bond_type_names[melt.bond_type[b]]
+        bond.num = cfg.n_bond() + 1
+        cfg.insert_bond(bond)
+    return cfg
