@@ -36,46 +36,80 @@ struct SweepArgs {
   int no_cutoff;
 };
 
-// ------------------------------------------------------------------ rare exact paths (fast kernel)
-__device__ __noinline__ bool band_recheck(const SweepArgs &a, int si, int sj) {
-  const size_t n = (size_t)a.n;
-  const int bi = a.idx[si], bj = a.idx[sj];
-  double rsq = mouse_rsq_exact(a.ctr[bi], a.ctr[n + bi], a.ctr[2 * n + bi], a.ctr[bj], a.ctr[n + bj],
-                               a.ctr[2 * n + bj], a.g.box);
-  atomicAdd((unsigned long long *)&a.counters[1], 1ULL);
-  return rsq <= a.g.rc2;
-}
-
-// exact value of the reference's cos^2 expression (:112) for sorted slots si, sj
-__device__ __noinline__ double cos2_exact(const SweepArgs &a, int si, int sj) {
-  const size_t n = (size_t)a.n;
-  const int bi = a.idx[si], bj = a.idx[sj];
-  double ax = a.vec[bi], ay = a.vec[n + bi], az = a.vec[2 * n + bi];
-  double bx = a.vec[bj], by = a.vec[n + bj], bz = a.vec[2 * n + bj];
-  double dot = mouse_dot_exact(ax, ay, az, bx, by, bz);
-  double nr = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
-  double nj = __dadd_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)), __dmul_rn(bz, bz));
-  return __ddiv_rn(__ddiv_rn(__dmul_rn(dot, dot), nr), nj);
+// ------------------------------------------------------------------ rare exact path (fast kernel)
+// Re-decides ALL candidates of one lane with the reference's FP64 expressions.  Called only for
+// lanes that saw a candidate inside the FP32 guard band around rc^2 or a near-zero dot product.
+// Returns the exact hit mask over the lane's slots and the exact sum of cos^2.
+__device__ __noinline__ unsigned exact_redo(const int32_t *__restrict__ idx, const double *__restrict__ ctr,
+                                            const double *__restrict__ vec, const float4 *__restrict__ P, size_t n,
+                                            const double *box, double rc2, int si, const int *sj_lane,
+                                            int nslots, bool excl_mol, double *acc_out,
+                                            unsigned long long *band_counter) {
+  const int bi = idx[si];
+  const double cix = ctr[bi], ciy = ctr[n + bi], ciz = ctr[2 * n + bi];
+  const double ax = vec[bi], ay = vec[n + bi], az = vec[2 * n + bi];
+  const double nr = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+  const int moli = __float_as_int(P[si].w);
+  unsigned mask = 0;
+  double acc = 0.0;
+  for (int c = 0; c < nslots; ++c) {
+    const int sjv = sj_lane[c * 32];
+    if (sjv < 0 || sjv == si) continue;
+    if (excl_mol && __float_as_int(P[sjv].w) == moli) continue;
+    const int bj = idx[sjv];
+    const double rsq = mouse_rsq_exact(cix, ciy, ciz, ctr[bj], ctr[n + bj], ctr[2 * n + bj], box);
+    if (!(rsq <= rc2)) continue;
+    const double bx = vec[bj], by = vec[n + bj], bz = vec[2 * n + bj];
+    const double dot = mouse_dot_exact(ax, ay, az, bx, by, bz);
+    const double nj = __dadd_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)), __dmul_rn(bz, bz));
+    const double cs = __ddiv_rn(__ddiv_rn(__dmul_rn(dot, dot), nr), nj);
+    if (cs != 0.0) {
+      mask |= 1u << c;
+      acc += cs;
+    }
+  }
+  atomicAdd(band_counter, 1ULL);
+  *acc_out = acc;
+  return mask;
 }
 
 #define FAST_WARPS 4
 
+// One warp per home cell.
+//   load  : the candidates of the 27 neighbour cells are concatenated; lane l / slot c holds
+//           candidate t = base + 32 c + l: cell-local FP32 coordinates (shifted by the periodic
+//           cell offset) in REGISTERS, FP64 unit vector + sorted index in the warp's SHARED memory.
+//   per reference bond i of the home cell (warp-uniform loop):
+//     A   : every lane tests its SLOTS candidates in FP32 (3 FADD, FMUL, 2 FFMA, compare) and
+//           collects a hit bit mask; min |d2 - rc2| is tracked for the guard band.
+//     B   : lanes walk their hit bits: cos^2 = (u_i . u_j)^2 in FP64 from shared memory.
+//     fix : lanes that saw a guard-band candidate or a near-zero dot redo their slots exactly.
+//     sum : warp-shuffle reduction in a fixed order, lane 0 writes.
 template <int SLOTS, bool EXCL_MOL, bool LISTS>
 __global__ void __launch_bounds__(FAST_WARPS * 32) p2_sweep_fast_kernel(const SweepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_start[FAST_WARPS][32];
   __shared__ int s_pref[FAST_WARPS][32];
   __shared__ float s_off[FAST_WARPS][3][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  constexpr int NC = SLOTS * 32;
+  double *su = reinterpret_cast<double *>(smem_raw) + (size_t)wib * (3 * NC);            // [3][NC]
+  int *sj = reinterpret_cast<int *>(smem_raw + sizeof(double) * 3 * NC * FAST_WARPS) + wib * NC;  // [NC]
+  const float4 *__restrict__ P = a.P;
+  const double4 *__restrict__ U = a.U;
+  const int32_t *__restrict__ cell_start = a.cell_start;
   const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
   int *my_start = s_start[wib];
   int *my_pref = s_pref[wib];
-  const float rc2_lo = a.g.rc2_lo, rc2_hi = a.g.rc2_hi;
+  // guard band [rc2_lo, rc2_hi] around rc^2: centre / half width in FP32
+  const float rc2_c = 0.5f * (a.g.rc2_lo + a.g.rc2_hi);
+  const float rc2_w = 0.5f * (a.g.rc2_hi - a.g.rc2_lo) * 1.0001f;
   // zero-length bonds in the neighbour set turn every mean into NaN and add to every count
   // (0/0 in ordering_functions.py:112)
   const long long nzero = LISTS ? 0 : a.counters[0];
 
   for (int home = blockIdx.x * FAST_WARPS + wib; home < a.g.ncell; home += gridDim.x * FAST_WARPS) {
-    const int hs = a.cell_start[home], he = a.cell_start[home + 1];
+    const int hs = cell_start[home], he = cell_start[home + 1];
     if (hs == he) continue;
     const int cx = home % nx, cy = (home / nx) % ny, cz = home / (nx * ny);
     int st = 0, cn = 0;
@@ -90,8 +124,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) p2_sweep_fast_kernel(const Sw
       mz += (mz < 0) ? nz : 0;
       mz -= (mz >= nz) ? nz : 0;
       const int cid = (mz * ny + my) * nx + mx;
-      st = a.cell_start[cid];
-      cn = a.cell_start[cid + 1] - st;
+      st = cell_start[cid];
+      cn = cell_start[cid + 1] - st;
       ox = (float)dx * a.g.cwf[0];
       oy = (float)dy * a.g.cwf[1];
       oz = (float)dz * a.g.cwf[2];
@@ -103,6 +137,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) p2_sweep_fast_kernel(const Sw
       if (lane >= o) incl += y;
     }
     const int T = __shfl_sync(MOUSE_FULL_MASK, incl, 31);
+    const int home_pref = __shfl_sync(MOUSE_FULL_MASK, incl - cn, 13);  // neighbour 13 = the home cell itself
     __syncwarp();
     my_start[lane] = st;
     my_pref[lane] = incl - cn;
@@ -111,17 +146,18 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) p2_sweep_fast_kernel(const Sw
     s_off[wib][2][lane] = oz;
     __syncwarp();
 
-    for (int base = 0; base < T; base += 32 * SLOTS) {
+    for (int base = 0; base < T; base += NC) {
       float xr[SLOTS], yr[SLOTS], zr[SLOTS];
-      int jr[SLOTS], mr[SLOTS];
+      int mr[EXCL_MOL ? SLOTS : 1];
+      __syncwarp();
 #pragma unroll
       for (int c = 0; c < SLOTS; ++c) {
         const int t = base + 32 * c + lane;
         xr[c] = 1e30f;
         yr[c] = 0.f;
         zr[c] = 0.f;
-        jr[c] = -1;
-        mr[c] = 0;
+        if (EXCL_MOL) mr[c] = 0;
+        int j = -1;
         if (t < T) {
           int k = 0;  // largest k < 27 with pref[k] <= t
 #pragma unroll
@@ -129,59 +165,94 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) p2_sweep_fast_kernel(const Sw
             const int k2 = k + step;
             if (k2 < 27 && my_pref[k2] <= t) k = k2;
           }
-          const int j = my_start[k] + (t - my_pref[k]);
-          const float4 p = __ldg(a.P + j);
+          j = my_start[k] + (t - my_pref[k]);
+          const float4 p = __ldg(P + j);
+          const double4 u = U[j];
           xr[c] = p.x + s_off[wib][0][k];
           yr[c] = p.y + s_off[wib][1][k];
           zr[c] = p.z + s_off[wib][2][k];
-          jr[c] = j;
-          mr[c] = __float_as_int(p.w);
+          if (EXCL_MOL) mr[c] = __float_as_int(p.w);
+          su[c * 32 + lane] = u.x;
+          su[NC + c * 32 + lane] = u.y;
+          su[2 * NC + c * 32 + lane] = u.z;
         }
+        sj[c * 32 + lane] = j;
       }
+      __syncwarp();
       const int nslots = min(SLOTS, (T - base + 31) >> 5);
 
       for (int i = hs; i < he; ++i) {
         if (!(a.flag[i] & 1)) continue;
-        const float4 pi = __ldg(a.P + i);
-        const double4 ui = a.U[i];
+        const float4 pi = __ldg(P + i);
         const int moli = __float_as_int(pi.w);
-        double acc = 0.0;
-        int cnt = 0;
-        int64_t row = 0;
-        if (LISTS) row = a.row_ptr[a.idx[i]] + a.out_cnt[a.idx[i]];  // out_cnt = entries written so far
+        // the reference bond is itself a candidate (home cell = neighbour 13): its slot
+        const int tself = home_pref + (i - hs) - base;
+        const bool self_here = (tself >= 0) && (tself < NC);
+        double uix, uiy, uiz;
+        if (self_here) {
+          uix = su[tself];
+          uiy = su[NC + tself];
+          uiz = su[2 * NC + tself];
+        } else {
+          const double4 ui = U[i];
+          uix = ui.x;
+          uiy = ui.y;
+          uiz = ui.z;
+        }
+        // ---- A: FP32 filter
+        unsigned mask = 0;
+        float band = 1e30f;
 #pragma unroll
         for (int c = 0; c < SLOTS; ++c) {
-          if (c < nslots) {
-            const float dx = xr[c] - pi.x, dy = yr[c] - pi.y, dz = zr[c] - pi.z;
-            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            bool hit = (d2 <= rc2_hi) && (EXCL_MOL ? (mr[c] != moli) : (jr[c] != i));
-            bool counted = false;
-            if (hit) {
-              if (d2 >= rc2_lo) hit = band_recheck(a, i, jr[c]);
-              if (hit) {
-                const double4 uj = a.U[jr[c]];
-                const double d = fma(ui.x, uj.x, fma(ui.y, uj.y, ui.z * uj.z));
-                double q = d * d;
-                counted = true;
-                if (fabs(d) < 1e-9) {  // near-perpendicular: decide the ==0 mask exactly
-                  q = cos2_exact(a, i, jr[c]);
-                  counted = (q != 0.0);
-                }
-                if (counted) {
-                  acc += q;
-                  cnt += 1;
-                }
-              }
-            }
-            if (LISTS) {
-              const unsigned m = __ballot_sync(MOUSE_FULL_MASK, counted);
-              if (counted) a.nbr_idx[row + __popc(m & ((1u << lane) - 1u))] = a.idx[jr[c]];
-              row += __popc(m);
-            }
+          if ((c & 3) == 0 && c >= nslots) break;
+          const float dx = xr[c] - pi.x, dy = yr[c] - pi.y, dz = zr[c] - pi.z;
+          const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          bool hit = d2 < rc2_c;
+          if (EXCL_MOL) hit = hit && (mr[c] != moli);
+          if (hit) mask |= 1u << c;
+          band = fminf(band, fabsf(d2 - rc2_c));
+        }
+        if (!EXCL_MOL && self_here && lane == (tself & 31)) mask &= ~(1u << (tself >> 5));
+        // ---- B: FP64 cos^2 of the hits
+        double acc = 0.0;
+        bool redo = band <= rc2_w;
+        unsigned m = mask;
+        while (__any_sync(MOUSE_FULL_MASK, m != 0)) {
+          if (m) {
+            const int c = __ffs(m) - 1;
+            m &= m - 1;
+            const int o = c * 32 + lane;
+            const double d = fma(uix, su[o], fma(uiy, su[NC + o], uiz * su[2 * NC + o]));
+            acc = fma(d, d, acc);
+            redo |= fabs(d) < 1e-9;   // the reference masks cos^2 == 0 exactly (:113)
+          }
+        }
+        // ---- fix: exact re-decision for the (rare) flagged lanes
+        if (__any_sync(MOUSE_FULL_MASK, redo)) {
+          if (redo)
+            mask = exact_redo(a.idx, a.ctr, a.vec, P, (size_t)a.n, a.g.box, a.g.rc2, i, sj + lane, nslots, EXCL_MOL,
+                              &acc, (unsigned long long *)&a.counters[1]);
+        }
+        int cnt = __popc(mask);
+        if (LISTS) {
+          const int o = a.idx[i];
+          int64_t row = a.row_ptr[o] + a.out_cnt[o];  // out_cnt = entries written by earlier passes
+          int incl_c = cnt;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            int y = __shfl_up_sync(MOUSE_FULL_MASK, incl_c, off);
+            if (lane >= off) incl_c += y;
+          }
+          row += incl_c - cnt;
+          unsigned mm = mask;
+          while (mm) {
+            const int c = __ffs(mm) - 1;
+            mm &= mm - 1;
+            a.nbr_idx[row++] = a.idx[sj[c * 32 + lane]];
           }
         }
         acc = warp_sum(acc);
-        cnt = warp_sum(cnt);
+        cnt = __reduce_add_sync(MOUSE_FULL_MASK, cnt);
         if (lane == 0) {
           const int o = a.idx[i];
           if (LISTS) {
@@ -316,18 +387,26 @@ static int num_sms() {
   return g_num_sms;
 }
 
+template <int SLOTS, bool EXCL, bool LISTS>
+static void launch_fast_one(const SweepArgs &a, int blocks, cudaStream_t st) {
+  const size_t smem = (size_t)FAST_WARPS * SLOTS * 32 * (3 * sizeof(double) + sizeof(int));
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(p2_sweep_fast_kernel<SLOTS, EXCL, LISTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    configured = true;
+  }
+  p2_sweep_fast_kernel<SLOTS, EXCL, LISTS><<<blocks, FAST_WARPS * 32, smem, st>>>(a);
+}
+
 template <int SLOTS>
 static void launch_fast(const SweepArgs &a, bool excl_mol, bool lists, int blocks, cudaStream_t st) {
   if (lists) {
-    if (excl_mol)
-      p2_sweep_fast_kernel<SLOTS, true, true><<<blocks, FAST_WARPS * 32, 0, st>>>(a);
-    else
-      p2_sweep_fast_kernel<SLOTS, false, true><<<blocks, FAST_WARPS * 32, 0, st>>>(a);
+    if (excl_mol) launch_fast_one<SLOTS, true, true>(a, blocks, st);
+    else launch_fast_one<SLOTS, false, true>(a, blocks, st);
   } else {
-    if (excl_mol)
-      p2_sweep_fast_kernel<SLOTS, true, false><<<blocks, FAST_WARPS * 32, 0, st>>>(a);
-    else
-      p2_sweep_fast_kernel<SLOTS, false, false><<<blocks, FAST_WARPS * 32, 0, st>>>(a);
+    if (excl_mol) launch_fast_one<SLOTS, true, false>(a, blocks, st);
+    else launch_fast_one<SLOTS, false, false>(a, blocks, st);
   }
 }
 

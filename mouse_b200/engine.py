@@ -31,7 +31,8 @@ _ws_cache: dict = {}
 
 def workspace(nbytes: int, device) -> torch.Tensor:
     """256-byte aligned scratch buffer, grown on demand and reused per device."""
-    key = str(device)
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=device)
