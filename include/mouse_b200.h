@@ -144,6 +144,9 @@ int mouse_rdf_single_ref(const double *np_atoms, int64_t n, const double *ref, c
 
 /* Test / tuning hook: "fast_slots" (register-resident candidate slots per lane, 0 = auto). */
 int mouse_set_tuning(const char *key, int value);
+/* Debug: the 8 int64 workspace counters (0 zero-length, 1 guard-band redos, 4-7 phase cycle timers when built
+ * with -DMOUSE_PHASE_TIMERS); synchronises `stream`. */
+int mouse_debug_counters(const mouse_grid_t *grid, int64_t n_items, const void *ws, int64_t *out8 /*HOST*/, void *stream);
 
 #ifdef __cplusplus
 }

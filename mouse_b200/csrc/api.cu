@@ -215,4 +215,12 @@ int mouse_rdf_frame(const double *pos, const int32_t *type, const int32_t *mol, 
   return mouse_launch_rdf_sweep(grid, flags, n_atoms, ntypes, w.edges, nbin, w, hist, st);
 }
 
+// Debug / tuning: copies the 8 workspace counters to host (synchronises the stream).
+int mouse_debug_counters(const mouse_grid_t *grid, int64_t n_items, const void *ws, int64_t *out8, void *stream) {
+  Workspace w = mouse_carve((void *)ws, n_items, grid->ncell);
+  MOUSE_CUDA_CHECK(cudaMemcpyAsync(out8, w.counters, sizeof(int64_t) * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  MOUSE_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  return MOUSE_OK;
+}
+
 }  // extern "C"

@@ -39,22 +39,36 @@ struct SweepArgs {
 // ------------------------------------------------------------------ rare exact path (fast kernel)
 // Re-decides ALL candidates of one lane with the reference's FP64 expressions.  Called only for
 // lanes that saw a candidate inside the FP32 guard band around rc^2 or a near-zero dot product.
-// Returns the exact hit mask over the lane's slots and the exact sum of cos^2.
-__device__ __noinline__ unsigned exact_redo(const int32_t *__restrict__ idx, const double *__restrict__ ctr,
-                                            const double *__restrict__ vec, const float4 *__restrict__ P, size_t n,
-                                            const double *box, double rc2, int si, const int *sj_lane,
-                                            int nslots, bool excl_mol, double *acc_out,
-                                            unsigned long long *band_counter) {
+// Returns the exact hit mask over the lane's slots (slot c -> bit c) and the exact sum of cos^2.
+struct RedoOut {
+  unsigned mask;
+  double acc;
+};
+
+__device__ __noinline__ RedoOut exact_redo(const int32_t *__restrict__ idx, const double *__restrict__ ctr,
+                                           const double *__restrict__ vec, const float4 *__restrict__ P, size_t n,
+                                           const double *box, double rc2, int si, const int *pref, const int *start,
+                                           int tbase, int nslots, bool excl_mol,
+                                           unsigned long long *band_counter) {
   const int bi = idx[si];
   const double cix = ctr[bi], ciy = ctr[n + bi], ciz = ctr[2 * n + bi];
   const double ax = vec[bi], ay = vec[n + bi], az = vec[2 * n + bi];
   const double nr = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
   const int moli = __float_as_int(P[si].w);
-  unsigned mask = 0;
-  double acc = 0.0;
+  const int T = pref[27];
+  RedoOut out;
+  out.mask = 0;
+  out.acc = 0.0;
   for (int c = 0; c < nslots; ++c) {
-    const int sjv = sj_lane[c * 32];
-    if (sjv < 0 || sjv == si) continue;
+    const int t = tbase + 32 * c;   // this lane's candidate in slot c
+    if (t >= T) break;
+    int k = 0;
+    for (int step = 16; step > 0; step >>= 1) {
+      const int k2 = k + step;
+      if (k2 < 27 && pref[k2] <= t) k = k2;
+    }
+    const int sjv = start[k] + (t - pref[k]);
+    if (sjv == si) continue;
     if (excl_mol && __float_as_int(P[sjv].w) == moli) continue;
     const int bj = idx[sjv];
     const double rsq = mouse_rsq_exact(cix, ciy, ciz, ctr[bj], ctr[n + bj], ctr[2 * n + bj], box);
@@ -64,37 +78,45 @@ __device__ __noinline__ unsigned exact_redo(const int32_t *__restrict__ idx, con
     const double nj = __dadd_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)), __dmul_rn(bz, bz));
     const double cs = __ddiv_rn(__ddiv_rn(__dmul_rn(dot, dot), nr), nj);
     if (cs != 0.0) {
-      mask |= 1u << c;
-      acc += cs;
+      out.mask |= 1u << c;
+      out.acc += cs;
     }
   }
   atomicAdd(band_counter, 1ULL);
-  *acc_out = acc;
-  return mask;
+  return out;
 }
 
+#ifndef FAST_WARPS
 #define FAST_WARPS 4
+#endif
+#ifndef FAST_MIN_BLOCKS
+#define FAST_MIN_BLOCKS 4
+#endif
 
 // One warp per home cell.
 //   load  : the candidates of the 27 neighbour cells are concatenated; lane l / slot c holds
 //           candidate t = base + 32 c + l: cell-local FP32 coordinates (shifted by the periodic
-//           cell offset) in REGISTERS, FP64 unit vector + sorted index in the warp's SHARED memory.
+//           cell offset) in REGISTERS, FP64 unit vector (+ molecule code) in the warp's SHARED memory.
 //   per reference bond i of the home cell (warp-uniform loop):
-//     A   : every lane tests its SLOTS candidates in FP32 (3 FADD, FMUL, 2 FFMA, compare) and
-//           collects a hit bit mask; min |d2 - rc2| is tracked for the guard band.
-//     B   : lanes walk their hit bits: cos^2 = (u_i . u_j)^2 in FP64 from shared memory.
+//     A   : every lane tests its candidates in FP32 (3 FADD, FMUL, 2 FFMA, FADD) and shifts the sign
+//           of d2 - rc2 into a hit mask (one funnel shift); min |d2 - rc2| is tracked for the guard band.
+//     B   : lanes walk their hit bits (warp-uniform trip count): cos^2 = (u_i . u_j)^2 in FP64
+//           from shared memory.
 //     fix : lanes that saw a guard-band candidate or a near-zero dot redo their slots exactly.
 //     sum : warp-shuffle reduction in a fixed order, lane 0 writes.
-template <int SLOTS, bool EXCL_MOL, bool LISTS>
-__global__ void __launch_bounds__(FAST_WARPS * 32) p2_sweep_fast_kernel(const SweepArgs a) {
+template <int SLOTS, int R, bool EXCL_MOL, bool LISTS>
+__global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) p2_sweep_fast_kernel(const SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_start[FAST_WARPS][32];
   __shared__ int s_pref[FAST_WARPS][32];
   __shared__ float s_off[FAST_WARPS][3][32];
+  __shared__ float4 s_home[FAST_WARPS][32];     // the chunk's reference bonds: cell-local xyz + molecule code
+  __shared__ double s_hu[FAST_WARPS][3][32];    //                             FP64 unit vectors
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   constexpr int NC = SLOTS * 32;
-  double *su = reinterpret_cast<double *>(smem_raw) + (size_t)wib * (3 * NC);            // [3][NC]
-  int *sj = reinterpret_cast<int *>(smem_raw + sizeof(double) * 3 * NC * FAST_WARPS) + wib * NC;  // [NC]
+  constexpr int GROUPS = SLOTS / 4;
+  double *su = reinterpret_cast<double *>(smem_raw) + (size_t)wib * (3 * NC) + lane;      // [3][NC], lane column
+  int *smol = reinterpret_cast<int *>(smem_raw + sizeof(double) * 3 * NC * FAST_WARPS) + wib * NC + lane;
   const float4 *__restrict__ P = a.P;
   const double4 *__restrict__ U = a.U;
   const int32_t *__restrict__ cell_start = a.cell_start;
@@ -108,9 +130,18 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) p2_sweep_fast_kernel(const Sw
   // (0/0 in ordering_functions.py:112)
   const long long nzero = LISTS ? 0 : a.counters[0];
 
+#ifdef MOUSE_PHASE_TIMERS
+  long long tm_load = 0, tm_a = 0, tm_b = 0, tm_e = 0, tm0;
+#define TM_START() tm0 = clock64()
+#define TM_ADD(x) do { long long t1_ = clock64(); x += t1_ - tm0; tm0 = t1_; } while (0)
+#else
+#define TM_START()
+#define TM_ADD(x)
+#endif
   for (int home = blockIdx.x * FAST_WARPS + wib; home < a.g.ncell; home += gridDim.x * FAST_WARPS) {
     const int hs = cell_start[home], he = cell_start[home + 1];
     if (hs == he) continue;
+    TM_START();
     const int cx = home % nx, cy = (home / nx) % ny, cz = home / (nx * ny);
     int st = 0, cn = 0;
     float ox = 0.f, oy = 0.f, oz = 0.f;
@@ -140,7 +171,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) p2_sweep_fast_kernel(const Sw
     const int home_pref = __shfl_sync(MOUSE_FULL_MASK, incl - cn, 13);  // neighbour 13 = the home cell itself
     __syncwarp();
     my_start[lane] = st;
-    my_pref[lane] = incl - cn;
+    my_pref[lane] = incl - cn;   // lanes >= 27 hold T (sentinel, read by exact_redo as pref[27])
     s_off[wib][0][lane] = ox;
     s_off[wib][1][lane] = oy;
     s_off[wib][2][lane] = oz;
@@ -148,7 +179,6 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) p2_sweep_fast_kernel(const Sw
 
     for (int base = 0; base < T; base += NC) {
       float xr[SLOTS], yr[SLOTS], zr[SLOTS];
-      int mr[EXCL_MOL ? SLOTS : 1];
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < SLOTS; ++c) {
@@ -156,8 +186,6 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) p2_sweep_fast_kernel(const Sw
         xr[c] = 1e30f;
         yr[c] = 0.f;
         zr[c] = 0.f;
-        if (EXCL_MOL) mr[c] = 0;
-        int j = -1;
         if (t < T) {
           int k = 0;  // largest k < 27 with pref[k] <= t
 #pragma unroll
@@ -165,114 +193,218 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) p2_sweep_fast_kernel(const Sw
             const int k2 = k + step;
             if (k2 < 27 && my_pref[k2] <= t) k = k2;
           }
-          j = my_start[k] + (t - my_pref[k]);
+          const int j = my_start[k] + (t - my_pref[k]);
           const float4 p = __ldg(P + j);
           const double4 u = U[j];
           xr[c] = p.x + s_off[wib][0][k];
           yr[c] = p.y + s_off[wib][1][k];
           zr[c] = p.z + s_off[wib][2][k];
-          if (EXCL_MOL) mr[c] = __float_as_int(p.w);
-          su[c * 32 + lane] = u.x;
-          su[NC + c * 32 + lane] = u.y;
-          su[2 * NC + c * 32 + lane] = u.z;
+          su[c * 32] = u.x;
+          su[NC + c * 32] = u.y;
+          su[2 * NC + c * 32] = u.z;
+          if (EXCL_MOL) smol[c * 32] = __float_as_int(p.w);
         }
-        sj[c * 32 + lane] = j;
       }
       __syncwarp();
       const int nslots = min(SLOTS, (T - base + 31) >> 5);
+      const int ngroups = (nslots + 3) >> 2;
 
-      for (int i = hs; i < he; ++i) {
-        if (!(a.flag[i] & 1)) continue;
-        const float4 pi = __ldg(P + i);
-        const int moli = __float_as_int(pi.w);
-        // the reference bond is itself a candidate (home cell = neighbour 13): its slot
-        const int tself = home_pref + (i - hs) - base;
-        const bool self_here = (tself >= 0) && (tself < NC);
-        double uix, uiy, uiz;
-        if (self_here) {
-          uix = su[tself];
-          uiy = su[NC + tself];
-          uiz = su[2 * NC + tself];
-        } else {
-          const double4 ui = U[i];
-          uix = ui.x;
-          uiy = ui.y;
-          uiz = ui.z;
+      // Reference bonds of the home cell in chunks of 32: lane l owns reference chunk0 + l (its inputs
+      // are staged in shared memory, its result stays in registers) so that the per-reference loop
+      // below touches no global memory at all.
+      for (int chunk0 = hs; chunk0 < he; chunk0 += 32) {
+        const int nchunk = min(32, he - chunk0);
+        int my_idx = 0;
+        bool my_ref = false;
+        __syncwarp();
+        if (lane < nchunk) {
+          const int ic = chunk0 + lane;
+          my_idx = a.idx[ic];
+          my_ref = (a.flag[ic] & 1) != 0;
+          s_home[wib][lane] = __ldg(P + ic);
+          const double4 u = U[ic];
+          s_hu[wib][0][lane] = u.x;
+          s_hu[wib][1][lane] = u.y;
+          s_hu[wib][2][lane] = u.z;
         }
-        // ---- A: FP32 filter
-        unsigned mask = 0;
-        float band = 1e30f;
+        const unsigned refmask = __ballot_sync(MOUSE_FULL_MASK, my_ref);
+        double racc = 0.0;   // result of reference chunk0 + lane
+        int rcnt = 0;
+        __syncwarp();
+        TM_ADD(tm_load);
+
+        // R reference bonds per iteration: R independent dependency chains per lane (ILP)
+        for (int l0 = 0; l0 < nchunk; l0 += R) {
+          if (((refmask >> l0) & ((1u << R) - 1u)) == 0) continue;
+          float pix[R], piy[R], piz[R];
+          double uix[R], uiy[R], uiz[R];
+          int moli[R], tself[R];
+          bool valid[R];
 #pragma unroll
-        for (int c = 0; c < SLOTS; ++c) {
-          if ((c & 3) == 0 && c >= nslots) break;
-          const float dx = xr[c] - pi.x, dy = yr[c] - pi.y, dz = zr[c] - pi.z;
-          const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-          bool hit = d2 < rc2_c;
-          if (EXCL_MOL) hit = hit && (mr[c] != moli);
-          if (hit) mask |= 1u << c;
-          band = fminf(band, fabsf(d2 - rc2_c));
-        }
-        if (!EXCL_MOL && self_here && lane == (tself & 31)) mask &= ~(1u << (tself >> 5));
-        // ---- B: FP64 cos^2 of the hits
-        double acc = 0.0;
-        bool redo = band <= rc2_w;
-        unsigned m = mask;
-        while (__any_sync(MOUSE_FULL_MASK, m != 0)) {
-          if (m) {
-            const int c = __ffs(m) - 1;
-            m &= m - 1;
-            const int o = c * 32 + lane;
-            const double d = fma(uix, su[o], fma(uiy, su[NC + o], uiz * su[2 * NC + o]));
-            acc = fma(d, d, acc);
-            redo |= fabs(d) < 1e-9;   // the reference masks cos^2 == 0 exactly (:113)
+          for (int r = 0; r < R; ++r) {
+            const int il = min(l0 + r, nchunk - 1);
+            valid[r] = (l0 + r < nchunk) && ((refmask >> il) & 1u);
+            const float4 pi = s_home[wib][il];
+            pix[r] = valid[r] ? pi.x : 1e30f;
+            piy[r] = pi.y;
+            piz[r] = pi.z;
+            moli[r] = __float_as_int(pi.w);
+            uix[r] = s_hu[wib][0][il];
+            uiy[r] = s_hu[wib][1][il];
+            uiz[r] = s_hu[wib][2][il];
+            // the reference bond is itself a candidate (home cell = neighbour 13): its slot
+            tself[r] = home_pref + (chunk0 + il - hs) - base;
           }
-        }
-        // ---- fix: exact re-decision for the (rare) flagged lanes
-        if (__any_sync(MOUSE_FULL_MASK, redo)) {
-          if (redo)
-            mask = exact_redo(a.idx, a.ctr, a.vec, P, (size_t)a.n, a.g.box, a.g.rc2, i, sj + lane, nslots, EXCL_MOL,
-                              &acc, (unsigned long long *)&a.counters[1]);
-        }
-        int cnt = __popc(mask);
-        if (LISTS) {
-          const int o = a.idx[i];
-          int64_t row = a.row_ptr[o] + a.out_cnt[o];  // out_cnt = entries written by earlier passes
-          int incl_c = cnt;
+          // ---- A: FP32 filter; slot c ends up in bit c (groups are walked from the last slot down)
+          unsigned mask[R];
+          float band[R];
 #pragma unroll
-          for (int off = 1; off < 32; off <<= 1) {
-            int y = __shfl_up_sync(MOUSE_FULL_MASK, incl_c, off);
-            if (lane >= off) incl_c += y;
+          for (int r = 0; r < R; ++r) {
+            mask[r] = 0;
+            band[r] = 1e30f;
           }
-          row += incl_c - cnt;
-          unsigned mm = mask;
-          while (mm) {
-            const int c = __ffs(mm) - 1;
-            mm &= mm - 1;
-            a.nbr_idx[row++] = a.idx[sj[c * 32 + lane]];
+#pragma unroll
+          for (int g = GROUPS - 1; g >= 0; --g) {
+            if (g < ngroups) {
+#pragma unroll
+              for (int c = 4 * g + 3; c >= 4 * g; --c) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                  const float dx = xr[c] - pix[r], dy = yr[c] - piy[r], dz = zr[c] - piz[r];
+                  const float t = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) - rc2_c;   // < 0: inside
+                  mask[r] = __funnelshift_l(__float_as_uint(t), mask[r], 1);
+                  band[r] = fminf(band[r], fabsf(t));
+                }
+              }
+            }
           }
-        }
-        acc = warp_sum(acc);
-        cnt = __reduce_add_sync(MOUSE_FULL_MASK, cnt);
-        if (lane == 0) {
-          const int o = a.idx[i];
+          TM_ADD(tm_a);
+          int pmax = 0;
+          bool redo[R];
+          double acc[R];
+          unsigned m[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if (tself[r] >= 0 && tself[r] < NC && lane == (tself[r] & 31)) mask[r] &= ~(1u << (tself[r] >> 5));
+            if (!valid[r]) mask[r] = 0;
+            redo[r] = valid[r] && (band[r] <= rc2_w);
+            acc[r] = 0.0;
+            m[r] = mask[r];
+            pmax = max(pmax, __popc(mask[r]));
+          }
+          // ---- B: FP64 cos^2 of the hits
+          const int iters = __reduce_max_sync(MOUSE_FULL_MASK, pmax);
+          unsigned nearz[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) nearz[r] = 0xffffffffu;
+          for (int it = 0; it < iters; ++it) {
+            // branch-free body: R independent chains; idle lanes read slot 0 and contribute d * 0
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const bool act = m[r] != 0;
+              const int c = act ? (__ffs(m[r]) - 1) : 0;
+              m[r] &= m[r] - 1;
+              const double *q = su + c * 32;
+              const double d = fma(uix[r], q[0], fma(uiy[r], q[NC], uiz[r] * q[2 * NC]));
+              bool use = act;
+              if (EXCL_MOL) {
+                const bool same = smol[c * 32] == moli[r];
+                mask[r] &= ~((act && same) ? (1u << c) : 0u);
+                use = act && !same;
+              }
+              const double w = use ? d : 0.0;
+              acc[r] = fma(d, w, acc[r]);
+              // smallest |d| (as its high word) over the used hits: |d| < 1e-9 must be decided exactly (:113)
+              const unsigned h = use ? ((unsigned)__double2hiint(d) & 0x7fffffffu) : 0xffffffffu;
+              nearz[r] = min(nearz[r], h);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r) redo[r] |= nearz[r] < 0x3e112e0bu;
+          TM_ADD(tm_b);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            // ---- fix: exact re-decision for the (rare) flagged lanes
+            if (__any_sync(MOUSE_FULL_MASK, redo[r])) {
+              if (redo[r]) {
+                const RedoOut ro = exact_redo(a.idx, a.ctr, a.vec, P, (size_t)a.n, a.g.box, a.g.rc2, chunk0 + l0 + r,
+                                              my_pref, my_start, base + lane, nslots, EXCL_MOL,
+                                              (unsigned long long *)&a.counters[1]);
+                mask[r] = ro.mask;
+                acc[r] = ro.acc;
+              }
+            }
+          }
+          int cnt[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) cnt[r] = __popc(mask[r]);
           if (LISTS) {
-            a.out_cnt[o] += cnt;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              if (!valid[r]) continue;
+              const int o = __shfl_sync(MOUSE_FULL_MASK, my_idx, l0 + r);
+              int64_t row = a.row_ptr[o] + a.out_cnt[o];  // out_cnt = entries written by earlier passes
+              int incl_c = cnt[r];
+#pragma unroll
+              for (int off = 1; off < 32; off <<= 1) {
+                int y = __shfl_up_sync(MOUSE_FULL_MASK, incl_c, off);
+                if (lane >= off) incl_c += y;
+              }
+              row += incl_c - cnt[r];
+              unsigned mm = mask[r];
+              while (mm) {
+                const int c = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const int t = base + 32 * c + lane;
+                int k = 0;
+                for (int step = 16; step > 0; step >>= 1) {
+                  const int k2 = k + step;
+                  if (k2 < 27 && my_pref[k2] <= t) k = k2;
+                }
+                a.nbr_idx[row++] = a.idx[my_start[k] + (t - my_pref[k])];
+              }
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            acc[r] = warp_sum(acc[r]);
+            cnt[r] = __reduce_add_sync(MOUSE_FULL_MASK, cnt[r]);
+            if (valid[r] && lane == l0 + r) {
+              racc = acc[r];
+              rcnt = cnt[r];
+            }
+          }
+          TM_ADD(tm_e);
+        }
+        // flush the chunk: one store per reference, no global read unless a second pass is running
+        if (my_ref) {
+          if (LISTS) {
+            a.out_cnt[my_idx] += rcnt;
           } else if (base == 0) {
             if (nzero) {
-              acc = __longlong_as_double(0x7ff8000000000000LL);
-              cnt += (int)nzero;
+              racc = __longlong_as_double(0x7ff8000000000000LL);
+              rcnt += (int)nzero;
             }
-            a.out_sum[o] = acc;
-            a.out_cnt[o] = cnt;
+            a.out_sum[my_idx] = racc;
+            a.out_cnt[my_idx] = rcnt;
           } else {
-            a.out_sum[o] += acc;
-            a.out_cnt[o] += cnt;
+            a.out_sum[my_idx] += racc;
+            a.out_cnt[my_idx] += rcnt;
           }
         }
         if (LISTS) __syncwarp();
+        TM_ADD(tm_e);
       }
     }
   }
+#ifdef MOUSE_PHASE_TIMERS
+  if (lane == 0) {
+    atomicAdd((unsigned long long *)&a.counters[4], (unsigned long long)tm_load);
+    atomicAdd((unsigned long long *)&a.counters[5], (unsigned long long)tm_a);
+    atomicAdd((unsigned long long *)&a.counters[6], (unsigned long long)tm_b);
+    atomicAdd((unsigned long long *)&a.counters[7], (unsigned long long)tm_e);
+  }
+#endif
 }
 
 // ------------------------------------------------------------------ exact all-FP64 sweep
@@ -387,31 +519,39 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int SLOTS, bool EXCL, bool LISTS>
+template <int SLOTS, int R, bool EXCL, bool LISTS>
 static void launch_fast_one(const SweepArgs &a, int blocks, cudaStream_t st) {
   const size_t smem = (size_t)FAST_WARPS * SLOTS * 32 * (3 * sizeof(double) + sizeof(int));
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(p2_sweep_fast_kernel<SLOTS, EXCL, LISTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(p2_sweep_fast_kernel<SLOTS, R, EXCL, LISTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
     configured = true;
   }
-  p2_sweep_fast_kernel<SLOTS, EXCL, LISTS><<<blocks, FAST_WARPS * 32, smem, st>>>(a);
+  p2_sweep_fast_kernel<SLOTS, R, EXCL, LISTS><<<blocks, FAST_WARPS * 32, smem, st>>>(a);
 }
 
-template <int SLOTS>
-static void launch_fast(const SweepArgs &a, bool excl_mol, bool lists, int blocks, cudaStream_t st) {
+template <int SLOTS, int R>
+static void launch_fast_r(const SweepArgs &a, bool excl_mol, bool lists, int blocks, cudaStream_t st) {
   if (lists) {
-    if (excl_mol) launch_fast_one<SLOTS, true, true>(a, blocks, st);
-    else launch_fast_one<SLOTS, false, true>(a, blocks, st);
+    if (excl_mol) launch_fast_one<SLOTS, 1, true, true>(a, blocks, st);
+    else launch_fast_one<SLOTS, 1, false, true>(a, blocks, st);
   } else {
-    if (excl_mol) launch_fast_one<SLOTS, true, false>(a, blocks, st);
-    else launch_fast_one<SLOTS, false, false>(a, blocks, st);
+    if (excl_mol) launch_fast_one<SLOTS, R, true, false>(a, blocks, st);
+    else launch_fast_one<SLOTS, R, false, false>(a, blocks, st);
   }
 }
 
+int mouse_fast_variant = 2;  // reference bonds per iteration (ILP): 1, 2 or 4
+
+template <int SLOTS>
+static void launch_fast(const SweepArgs &a, bool excl_mol, bool lists, int blocks, cudaStream_t st) {
+  if (mouse_fast_variant >= 4) launch_fast_r<SLOTS, 4>(a, excl_mol, lists, blocks, st);
+  else if (mouse_fast_variant >= 2) launch_fast_r<SLOTS, 2>(a, excl_mol, lists, blocks, st);
+  else launch_fast_r<SLOTS, 1>(a, excl_mol, lists, blocks, st);
+}
+
 int mouse_fast_slots_override = 0;  // test / tuning hooks (set through mouse_set_tuning)
-int mouse_fast_variant = 0;
 
 int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const mouse_grid_t *grid, uint32_t flags,
                           const Workspace &w, double *out_sum, int32_t *out_cnt, const int64_t *row_ptr,
@@ -444,8 +584,9 @@ int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const
   if (fast) {
     // SLOTS*32 registers-resident candidates per pass: size for mean + ~3 sigma of 27 cells
     double mean = 27.0 * (double)n / (double)grid->ncell;
-    int need = (int)((mean + 3.0 * sqrt(mean) + 31.0) / 32.0);
+    int need = (int)((1.15 * mean + 2.0 * sqrt(mean) + 31.0) / 32.0);
     int slots = need <= 4 ? 4 : need <= 8 ? 8 : need <= 12 ? 12 : 16;
+    (void)need;
     if (mouse_fast_slots_override) slots = mouse_fast_slots_override;
     int blocks = (grid->ncell + FAST_WARPS - 1) / FAST_WARPS;
     int maxb = num_sms() * 16;
