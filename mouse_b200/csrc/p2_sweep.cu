@@ -48,7 +48,7 @@ struct RedoOut {
 __device__ __noinline__ RedoOut exact_redo(const int32_t *__restrict__ idx, const double *__restrict__ ctr,
                                            const double *__restrict__ vec, const float4 *__restrict__ P, size_t n,
                                            const double *box, double rc2, int si, const int *pref, const int *start,
-                                           int tbase, int nslots, bool excl_mol,
+                                           int tbase, int tstride, int nslots, bool excl_mol,
                                            unsigned long long *band_counter) {
   const int bi = idx[si];
   const double cix = ctr[bi], ciy = ctr[n + bi], ciz = ctr[2 * n + bi];
@@ -60,7 +60,7 @@ __device__ __noinline__ RedoOut exact_redo(const int32_t *__restrict__ idx, cons
   out.mask = 0;
   out.acc = 0.0;
   for (int c = 0; c < nslots; ++c) {
-    const int t = tbase + 32 * c;   // this lane's candidate in slot c
+    const int t = tbase + tstride * c;   // this lane's candidate in slot c
     if (t >= T) break;
     int k = 0;
     for (int step = 16; step > 0; step >>= 1) {
@@ -86,50 +86,51 @@ __device__ __noinline__ RedoOut exact_redo(const int32_t *__restrict__ idx, cons
   return out;
 }
 
-#ifndef FAST_WARPS
-#define FAST_WARPS 4
-#endif
-#ifndef FAST_MIN_BLOCKS
-#define FAST_MIN_BLOCKS 4
+#ifndef FAST_TARGET_WARPS
+#define FAST_TARGET_WARPS 16   // resident warps per SM the register allocation is sized for
 #endif
 
-// One warp per home cell.
-//   load  : the candidates of the 27 neighbour cells are concatenated; lane l / slot c holds
-//           candidate t = base + 32 c + l: cell-local FP32 coordinates (shifted by the periodic
-//           cell offset) in REGISTERS, FP64 unit vector (+ molecule code) in the warp's SHARED memory.
-//   per reference bond i of the home cell (warp-uniform loop):
-//     A   : every lane tests its candidates in FP32 (3 FADD, FMUL, 2 FFMA, FADD) and shifts the sign
-//           of d2 - rc2 into a hit mask (one funnel shift); min |d2 - rc2| is tracked for the guard band.
-//     B   : lanes walk their hit bits (warp-uniform trip count): cos^2 = (u_i . u_j)^2 in FP64
-//           from shared memory.
+// One CTA of K warps per home cell (grid-stride over home cells).
+//   load  : the candidates of the 27 neighbour cells are concatenated into t = 0..T-1 and dealt out in
+//           chunks of 32: chunk g belongs to warp g % K, slot g / K, lane t % 32.  Each lane keeps its
+//           candidates' cell-local FP32 coordinates (shifted by the periodic cell offset) in REGISTERS and
+//           their FP64 unit vectors (+ molecule codes) in SHARED memory.  The home cell's reference bonds
+//           are staged in shared memory in chunks of 32 (lane l of every warp owns reference chunk0 + l).
+//   per reference bond (warp-uniform loop, no global memory traffic):
+//     A   : every lane tests its candidates in FP32 (3 FADD, FMUL, 2 FFMA, FADD) and shifts the sign of
+//           d2 - rc2 into a hit mask (one funnel shift); min |d2 - rc2| is tracked for the guard band.
+//     B   : lanes walk their hit bits (warp-uniform trip count, branch-free body):
+//           cos^2 = (u_i . u_j)^2 in FP64 from shared memory.
 //     fix : lanes that saw a guard-band candidate or a near-zero dot redo their slots exactly.
-//     sum : warp-shuffle reduction in a fixed order, lane 0 writes.
-template <int SLOTS, int R, bool EXCL_MOL, bool LISTS>
-__global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) p2_sweep_fast_kernel(const SweepArgs a) {
+//     sum : warp-shuffle reduction in a fixed order; the result stays in the owning lane's registers.
+//   flush : the K warps' partial results are combined in warp order through shared memory (deterministic)
+//           and stored with one write per reference.
+template <int SLOTS, int K, bool EXCL_MOL, bool LISTS>
+__global__ void __launch_bounds__(K * 32, (FAST_TARGET_WARPS / K > 32 ? 32 : FAST_TARGET_WARPS / K)) p2_sweep_fast_kernel(const SweepArgs a) {
+  static_assert(!LISTS || K == 1, "pair lists use the single-warp variant");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_start[FAST_WARPS][32];
-  __shared__ int s_pref[FAST_WARPS][32];
-  __shared__ float s_off[FAST_WARPS][3][32];
-  __shared__ float4 s_home[FAST_WARPS][32];     // the chunk's reference bonds: cell-local xyz + molecule code
-  __shared__ double s_hu[FAST_WARPS][3][32];    //                             FP64 unit vectors
+  __shared__ int s_start[32];
+  __shared__ int s_pref[32];
+  __shared__ float s_off[3][32];
+  __shared__ float4 s_home[32];          // the chunk's reference bonds: cell-local xyz + molecule code
+  __shared__ double s_hu[3][32];         //                             FP64 unit vectors
+  __shared__ double s_pacc[K][32];       // partial results of warps 1..K-1
+  __shared__ int s_pcnt[K][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  constexpr int NC = SLOTS * 32;
-  constexpr int GROUPS = SLOTS / 4;
+  constexpr int NC = SLOTS * 32;         // candidates per warp and pass
+  constexpr int GROUPS = (SLOTS + 3) / 4;
   double *su = reinterpret_cast<double *>(smem_raw) + (size_t)wib * (3 * NC) + lane;      // [3][NC], lane column
-  int *smol = reinterpret_cast<int *>(smem_raw + sizeof(double) * 3 * NC * FAST_WARPS) + wib * NC + lane;
+  int *smol = reinterpret_cast<int *>(smem_raw + sizeof(double) * 3 * NC * K) + wib * NC + lane;
   const float4 *__restrict__ P = a.P;
   const double4 *__restrict__ U = a.U;
   const int32_t *__restrict__ cell_start = a.cell_start;
   const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
-  int *my_start = s_start[wib];
-  int *my_pref = s_pref[wib];
   // guard band [rc2_lo, rc2_hi] around rc^2: centre / half width in FP32
   const float rc2_c = 0.5f * (a.g.rc2_lo + a.g.rc2_hi);
   const float rc2_w = 0.5f * (a.g.rc2_hi - a.g.rc2_lo) * 1.0001f;
   // zero-length bonds in the neighbour set turn every mean into NaN and add to every count
   // (0/0 in ordering_functions.py:112)
   const long long nzero = LISTS ? 0 : a.counters[0];
-
 #ifdef MOUSE_PHASE_TIMERS
   long long tm_load = 0, tm_a = 0, tm_b = 0, tm_e = 0, tm0;
 #define TM_START() tm0 = clock64()
@@ -138,11 +139,13 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) p2_sweep_fas
 #define TM_START()
 #define TM_ADD(x)
 #endif
-  for (int home = blockIdx.x * FAST_WARPS + wib; home < a.g.ncell; home += gridDim.x * FAST_WARPS) {
+
+  for (int home = blockIdx.x; home < a.g.ncell; home += gridDim.x) {
     const int hs = cell_start[home], he = cell_start[home + 1];
-    if (hs == he) continue;
+    if (hs == he) continue;          // CTA-uniform
     TM_START();
     const int cx = home % nx, cy = (home / nx) % ny, cz = home / (nx * ny);
+    // neighbour table (every warp computes it redundantly in registers; warp 0 publishes it)
     int st = 0, cn = 0;
     float ox = 0.f, oy = 0.f, oz = 0.f;
     if (lane < 27) {
@@ -169,20 +172,21 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) p2_sweep_fas
     }
     const int T = __shfl_sync(MOUSE_FULL_MASK, incl, 31);
     const int home_pref = __shfl_sync(MOUSE_FULL_MASK, incl - cn, 13);  // neighbour 13 = the home cell itself
-    __syncwarp();
-    my_start[lane] = st;
-    my_pref[lane] = incl - cn;   // lanes >= 27 hold T (sentinel, read by exact_redo as pref[27])
-    s_off[wib][0][lane] = ox;
-    s_off[wib][1][lane] = oy;
-    s_off[wib][2][lane] = oz;
-    __syncwarp();
+    __syncthreads();                 // previous home cell fully consumed
+    if (wib == 0) {
+      s_start[lane] = st;
+      s_pref[lane] = incl - cn;      // lanes >= 27 hold T (sentinel, read by exact_redo as pref[27])
+      s_off[0][lane] = ox;
+      s_off[1][lane] = oy;
+      s_off[2][lane] = oz;
+    }
+    __syncthreads();
 
-    for (int base = 0; base < T; base += NC) {
+    for (int base = 0; base < T; base += NC * K) {
       float xr[SLOTS], yr[SLOTS], zr[SLOTS];
-      __syncwarp();
 #pragma unroll
       for (int c = 0; c < SLOTS; ++c) {
-        const int t = base + 32 * c + lane;
+        const int t = base + 32 * (c * K + wib) + lane;
         xr[c] = 1e30f;
         yr[c] = 0.f;
         zr[c] = 0.f;
@@ -191,193 +195,163 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) p2_sweep_fas
 #pragma unroll
           for (int step = 16; step > 0; step >>= 1) {
             const int k2 = k + step;
-            if (k2 < 27 && my_pref[k2] <= t) k = k2;
+            if (k2 < 27 && s_pref[k2] <= t) k = k2;
           }
-          const int j = my_start[k] + (t - my_pref[k]);
+          const int j = s_start[k] + (t - s_pref[k]);
           const float4 p = __ldg(P + j);
           const double4 u = U[j];
-          xr[c] = p.x + s_off[wib][0][k];
-          yr[c] = p.y + s_off[wib][1][k];
-          zr[c] = p.z + s_off[wib][2][k];
+          xr[c] = p.x + s_off[0][k];
+          yr[c] = p.y + s_off[1][k];
+          zr[c] = p.z + s_off[2][k];
           su[c * 32] = u.x;
           su[NC + c * 32] = u.y;
           su[2 * NC + c * 32] = u.z;
           if (EXCL_MOL) smol[c * 32] = __float_as_int(p.w);
         }
       }
-      __syncwarp();
-      const int nslots = min(SLOTS, (T - base + 31) >> 5);
+      // slots of this warp that hold candidates in this pass
+      const int nchunks = min(SLOTS * K, (T - base + 31) >> 5);
+      const int nslots = (nchunks - wib + K - 1) / K;
       const int ngroups = (nslots + 3) >> 2;
 
-      // Reference bonds of the home cell in chunks of 32: lane l owns reference chunk0 + l (its inputs
-      // are staged in shared memory, its result stays in registers) so that the per-reference loop
-      // below touches no global memory at all.
       for (int chunk0 = hs; chunk0 < he; chunk0 += 32) {
         const int nchunk = min(32, he - chunk0);
         int my_idx = 0;
         bool my_ref = false;
-        __syncwarp();
+        __syncthreads();             // staging buffers free (and, first time, su complete per warp)
         if (lane < nchunk) {
           const int ic = chunk0 + lane;
           my_idx = a.idx[ic];
           my_ref = (a.flag[ic] & 1) != 0;
-          s_home[wib][lane] = __ldg(P + ic);
-          const double4 u = U[ic];
-          s_hu[wib][0][lane] = u.x;
-          s_hu[wib][1][lane] = u.y;
-          s_hu[wib][2][lane] = u.z;
+          if (wib == 0) {
+            s_home[lane] = __ldg(P + ic);
+            const double4 u = U[ic];
+            s_hu[0][lane] = u.x;
+            s_hu[1][lane] = u.y;
+            s_hu[2][lane] = u.z;
+          }
         }
         const unsigned refmask = __ballot_sync(MOUSE_FULL_MASK, my_ref);
-        double racc = 0.0;   // result of reference chunk0 + lane
+        double racc = 0.0;   // this warp's partial result of reference chunk0 + lane
         int rcnt = 0;
-        __syncwarp();
+        __syncthreads();
         TM_ADD(tm_load);
 
-        // R reference bonds per iteration: R independent dependency chains per lane (ILP)
-        for (int l0 = 0; l0 < nchunk; l0 += R) {
-          if (((refmask >> l0) & ((1u << R) - 1u)) == 0) continue;
-          float pix[R], piy[R], piz[R];
-          double uix[R], uiy[R], uiz[R];
-          int moli[R], tself[R];
-          bool valid[R];
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int il = min(l0 + r, nchunk - 1);
-            valid[r] = (l0 + r < nchunk) && ((refmask >> il) & 1u);
-            const float4 pi = s_home[wib][il];
-            pix[r] = valid[r] ? pi.x : 1e30f;
-            piy[r] = pi.y;
-            piz[r] = pi.z;
-            moli[r] = __float_as_int(pi.w);
-            uix[r] = s_hu[wib][0][il];
-            uiy[r] = s_hu[wib][1][il];
-            uiz[r] = s_hu[wib][2][il];
-            // the reference bond is itself a candidate (home cell = neighbour 13): its slot
-            tself[r] = home_pref + (chunk0 + il - hs) - base;
-          }
+        for (int il = 0; il < nchunk; ++il) {
+          if (!((refmask >> il) & 1u)) continue;
+          const float4 pi = s_home[il];
+          const int moli = __float_as_int(pi.w);
+          const double uix = s_hu[0][il], uiy = s_hu[1][il], uiz = s_hu[2][il];
+          // the reference bond is itself a candidate (home cell = neighbour 13): chunk / lane of its slot
+          const int tself = home_pref + (chunk0 + il - hs) - base;
           // ---- A: FP32 filter; slot c ends up in bit c (groups are walked from the last slot down)
-          unsigned mask[R];
-          float band[R];
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            mask[r] = 0;
-            band[r] = 1e30f;
-          }
+          unsigned mask = 0;
+          float band = 1e30f;
 #pragma unroll
           for (int g = GROUPS - 1; g >= 0; --g) {
             if (g < ngroups) {
 #pragma unroll
-              for (int c = 4 * g + 3; c >= 4 * g; --c) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                  const float dx = xr[c] - pix[r], dy = yr[c] - piy[r], dz = zr[c] - piz[r];
-                  const float t = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) - rc2_c;   // < 0: inside
-                  mask[r] = __funnelshift_l(__float_as_uint(t), mask[r], 1);
-                  band[r] = fminf(band[r], fabsf(t));
-                }
+              for (int c = min(4 * g + 3, SLOTS - 1); c >= 4 * g; --c) {
+                const float dx = xr[c] - pi.x, dy = yr[c] - pi.y, dz = zr[c] - pi.z;
+                const float t = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) - rc2_c;   // < 0: inside
+                mask = __funnelshift_l(__float_as_uint(t), mask, 1);
+                band = fminf(band, fabsf(t));
               }
             }
+          }
+          if (SLOTS % 4 != 0) mask >>= 0;   // (slot numbering is unaffected by the partial last group)
+          {
+            const int gself = tself >> 5;   // chunk that holds the reference itself
+            if (tself >= 0 && gself < SLOTS * K && (gself % K) == wib && lane == (tself & 31))
+              mask &= ~(1u << (gself / K));
           }
           TM_ADD(tm_a);
-          int pmax = 0;
-          bool redo[R];
-          double acc[R];
-          unsigned m[R];
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            if (tself[r] >= 0 && tself[r] < NC && lane == (tself[r] & 31)) mask[r] &= ~(1u << (tself[r] >> 5));
-            if (!valid[r]) mask[r] = 0;
-            redo[r] = valid[r] && (band[r] <= rc2_w);
-            acc[r] = 0.0;
-            m[r] = mask[r];
-            pmax = max(pmax, __popc(mask[r]));
-          }
           // ---- B: FP64 cos^2 of the hits
-          const int iters = __reduce_max_sync(MOUSE_FULL_MASK, pmax);
-          unsigned nearz[R];
-#pragma unroll
-          for (int r = 0; r < R; ++r) nearz[r] = 0xffffffffu;
+          bool redo = band <= rc2_w;
+          double acc = 0.0;
+          unsigned m = mask;
+          unsigned nearz = 0xffffffffu;
+          const int iters = __reduce_max_sync(MOUSE_FULL_MASK, __popc(mask));
           for (int it = 0; it < iters; ++it) {
-            // branch-free body: R independent chains; idle lanes read slot 0 and contribute d * 0
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              const bool act = m[r] != 0;
-              const int c = act ? (__ffs(m[r]) - 1) : 0;
-              m[r] &= m[r] - 1;
-              const double *q = su + c * 32;
-              const double d = fma(uix[r], q[0], fma(uiy[r], q[NC], uiz[r] * q[2 * NC]));
-              bool use = act;
-              if (EXCL_MOL) {
-                const bool same = smol[c * 32] == moli[r];
-                mask[r] &= ~((act && same) ? (1u << c) : 0u);
-                use = act && !same;
-              }
-              const double w = use ? d : 0.0;
-              acc[r] = fma(d, w, acc[r]);
-              // smallest |d| (as its high word) over the used hits: |d| < 1e-9 must be decided exactly (:113)
-              const unsigned h = use ? ((unsigned)__double2hiint(d) & 0x7fffffffu) : 0xffffffffu;
-              nearz[r] = min(nearz[r], h);
+            // branch-free body: idle lanes read slot 0 and contribute d * 0
+            const bool act = m != 0;
+            const int c = act ? (__ffs(m) - 1) : 0;
+            m &= m - 1;
+            const double *q = su + c * 32;
+            const double d = fma(uix, q[0], fma(uiy, q[NC], uiz * q[2 * NC]));
+            bool use = act;
+            if (EXCL_MOL) {
+              const bool same = smol[c * 32] == moli;
+              mask &= ~((act && same) ? (1u << c) : 0u);
+              use = act && !same;
             }
+            const double w = use ? d : 0.0;
+            acc = fma(d, w, acc);
+            // smallest |d| (as its high word) over the used hits: |d| < 1e-9 must be decided exactly (:113)
+            const unsigned h = use ? ((unsigned)__double2hiint(d) & 0x7fffffffu) : 0xffffffffu;
+            nearz = min(nearz, h);
           }
-#pragma unroll
-          for (int r = 0; r < R; ++r) redo[r] |= nearz[r] < 0x3e112e0bu;
+          redo |= nearz < 0x3e112e0bu;
           TM_ADD(tm_b);
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            // ---- fix: exact re-decision for the (rare) flagged lanes
-            if (__any_sync(MOUSE_FULL_MASK, redo[r])) {
-              if (redo[r]) {
-                const RedoOut ro = exact_redo(a.idx, a.ctr, a.vec, P, (size_t)a.n, a.g.box, a.g.rc2, chunk0 + l0 + r,
-                                              my_pref, my_start, base + lane, nslots, EXCL_MOL,
-                                              (unsigned long long *)&a.counters[1]);
-                mask[r] = ro.mask;
-                acc[r] = ro.acc;
-              }
+          // ---- fix: exact re-decision for the (rare) flagged lanes
+          if (__any_sync(MOUSE_FULL_MASK, redo)) {
+            if (redo) {
+              const RedoOut ro = exact_redo(a.idx, a.ctr, a.vec, P, (size_t)a.n, a.g.box, a.g.rc2, chunk0 + il, s_pref,
+                                            s_start, base + 32 * wib + lane, 32 * K, nslots, EXCL_MOL,
+                                            (unsigned long long *)&a.counters[1]);
+              mask = ro.mask;
+              acc = ro.acc;
             }
           }
-          int cnt[R];
-#pragma unroll
-          for (int r = 0; r < R; ++r) cnt[r] = __popc(mask[r]);
+          int cnt = __popc(mask);
           if (LISTS) {
+            const int o = __shfl_sync(MOUSE_FULL_MASK, my_idx, il);
+            int64_t row = a.row_ptr[o] + a.out_cnt[o];  // out_cnt = entries written by earlier passes
+            int incl_c = cnt;
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-              if (!valid[r]) continue;
-              const int o = __shfl_sync(MOUSE_FULL_MASK, my_idx, l0 + r);
-              int64_t row = a.row_ptr[o] + a.out_cnt[o];  // out_cnt = entries written by earlier passes
-              int incl_c = cnt[r];
-#pragma unroll
-              for (int off = 1; off < 32; off <<= 1) {
-                int y = __shfl_up_sync(MOUSE_FULL_MASK, incl_c, off);
-                if (lane >= off) incl_c += y;
-              }
-              row += incl_c - cnt[r];
-              unsigned mm = mask[r];
-              while (mm) {
-                const int c = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const int t = base + 32 * c + lane;
-                int k = 0;
-                for (int step = 16; step > 0; step >>= 1) {
-                  const int k2 = k + step;
-                  if (k2 < 27 && my_pref[k2] <= t) k = k2;
-                }
-                a.nbr_idx[row++] = a.idx[my_start[k] + (t - my_pref[k])];
-              }
+            for (int off = 1; off < 32; off <<= 1) {
+              int y = __shfl_up_sync(MOUSE_FULL_MASK, incl_c, off);
+              if (lane >= off) incl_c += y;
             }
+            row += incl_c - cnt;
+            unsigned mm = mask;
+            while (mm) {
+              const int c = __ffs(mm) - 1;
+              mm &= mm - 1;
+              const int t = base + 32 * (c * K + wib) + lane;
+              int k = 0;
+              for (int step = 16; step > 0; step >>= 1) {
+                const int k2 = k + step;
+                if (k2 < 27 && s_pref[k2] <= t) k = k2;
+              }
+              a.nbr_idx[row++] = a.idx[s_start[k] + (t - s_pref[k])];
+            }
+            __syncwarp();
           }
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            acc[r] = warp_sum(acc[r]);
-            cnt[r] = __reduce_add_sync(MOUSE_FULL_MASK, cnt[r]);
-            if (valid[r] && lane == l0 + r) {
-              racc = acc[r];
-              rcnt = cnt[r];
-            }
+          acc = warp_sum(acc);
+          cnt = __reduce_add_sync(MOUSE_FULL_MASK, cnt);
+          if (lane == il) {
+            racc = acc;
+            rcnt = cnt;
           }
           TM_ADD(tm_e);
         }
-        // flush the chunk: one store per reference, no global read unless a second pass is running
-        if (my_ref) {
+        // flush the chunk: combine the K warps' partials in warp order, one store per reference
+        if (K > 1) {
+          if (wib > 0) {
+            s_pacc[wib][lane] = racc;
+            s_pcnt[wib][lane] = rcnt;
+          }
+          __syncthreads();
+          if (wib == 0) {
+#pragma unroll
+            for (int w = 1; w < K; ++w) {
+              racc += s_pacc[w][lane];
+              rcnt += s_pcnt[w][lane];
+            }
+          }
+        }
+        if (wib == 0 && my_ref) {
           if (LISTS) {
             a.out_cnt[my_idx] += rcnt;
           } else if (base == 0) {
@@ -392,7 +366,6 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) p2_sweep_fas
             a.out_cnt[my_idx] += rcnt;
           }
         }
-        if (LISTS) __syncwarp();
         TM_ADD(tm_e);
       }
     }
@@ -519,36 +492,46 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int SLOTS, int R, bool EXCL, bool LISTS>
-static void launch_fast_one(const SweepArgs &a, int blocks, cudaStream_t st) {
-  const size_t smem = (size_t)FAST_WARPS * SLOTS * 32 * (3 * sizeof(double) + sizeof(int));
+template <int SLOTS, int K, bool EXCL, bool LISTS>
+static void launch_fast_one(const SweepArgs &a, cudaStream_t st) {
+  const size_t smem = (size_t)K * SLOTS * 32 * (3 * sizeof(double) + sizeof(int));
   static bool configured = false;
+  static int blocks_per_sm = 1;
   if (!configured) {
-    cudaFuncSetAttribute(p2_sweep_fast_kernel<SLOTS, R, EXCL, LISTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(p2_sweep_fast_kernel<SLOTS, K, EXCL, LISTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, p2_sweep_fast_kernel<SLOTS, K, EXCL, LISTS>, K * 32,
+                                                  smem);
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
     configured = true;
   }
-  p2_sweep_fast_kernel<SLOTS, R, EXCL, LISTS><<<blocks, FAST_WARPS * 32, smem, st>>>(a);
+  // persistent-style grid: a few waves of resident CTAs, each striding over home cells
+  int blocks = num_sms() * blocks_per_sm * 4;
+  if (blocks > a.g.ncell) blocks = a.g.ncell;
+  p2_sweep_fast_kernel<SLOTS, K, EXCL, LISTS><<<blocks, K * 32, smem, st>>>(a);
 }
 
-template <int SLOTS, int R>
-static void launch_fast_r(const SweepArgs &a, bool excl_mol, bool lists, int blocks, cudaStream_t st) {
+int mouse_fast_variant = 1;  // K = warps per home cell (1, 2 or 4); 1 measured fastest on B200
+
+// total candidate slots per lane over the CTA = SLOTS * K
+template <int TOTAL>
+static void launch_fast(const SweepArgs &a, bool excl_mol, bool lists, cudaStream_t st) {
   if (lists) {
-    if (excl_mol) launch_fast_one<SLOTS, 1, true, true>(a, blocks, st);
-    else launch_fast_one<SLOTS, 1, false, true>(a, blocks, st);
-  } else {
-    if (excl_mol) launch_fast_one<SLOTS, R, true, false>(a, blocks, st);
-    else launch_fast_one<SLOTS, R, false, false>(a, blocks, st);
+    if (excl_mol) launch_fast_one<TOTAL, 1, true, true>(a, st);
+    else launch_fast_one<TOTAL, 1, false, true>(a, st);
+    return;
   }
-}
-
-int mouse_fast_variant = 2;  // reference bonds per iteration (ILP): 1, 2 or 4
-
-template <int SLOTS>
-static void launch_fast(const SweepArgs &a, bool excl_mol, bool lists, int blocks, cudaStream_t st) {
-  if (mouse_fast_variant >= 4) launch_fast_r<SLOTS, 4>(a, excl_mol, lists, blocks, st);
-  else if (mouse_fast_variant >= 2) launch_fast_r<SLOTS, 2>(a, excl_mol, lists, blocks, st);
-  else launch_fast_r<SLOTS, 1>(a, excl_mol, lists, blocks, st);
+  const int k = mouse_fast_variant;
+  if (k >= 4) {
+    if (excl_mol) launch_fast_one<TOTAL / 4, 4, true, false>(a, st);
+    else launch_fast_one<TOTAL / 4, 4, false, false>(a, st);
+  } else if (k >= 2) {
+    if (excl_mol) launch_fast_one<TOTAL / 2, 2, true, false>(a, st);
+    else launch_fast_one<TOTAL / 2, 2, false, false>(a, st);
+  } else {
+    if (excl_mol) launch_fast_one<TOTAL, 1, true, false>(a, st);
+    else launch_fast_one<TOTAL, 1, false, false>(a, st);
+  }
 }
 
 int mouse_fast_slots_override = 0;  // test / tuning hooks (set through mouse_set_tuning)
@@ -584,19 +567,16 @@ int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const
   if (fast) {
     // SLOTS*32 registers-resident candidates per pass: size for mean + ~3 sigma of 27 cells
     double mean = 27.0 * (double)n / (double)grid->ncell;
-    int need = (int)((1.15 * mean + 2.0 * sqrt(mean) + 31.0) / 32.0);
+    int need = (int)((mean + 1.0 * sqrt(mean) + 31.0) / 32.0);
     int slots = need <= 4 ? 4 : need <= 8 ? 8 : need <= 12 ? 12 : 16;
     (void)need;
     if (mouse_fast_slots_override) slots = mouse_fast_slots_override;
-    int blocks = (grid->ncell + FAST_WARPS - 1) / FAST_WARPS;
-    int maxb = num_sms() * 16;
-    if (blocks > maxb) blocks = maxb;
     const bool excl = !a.same_molecule;
     switch (slots) {
-      case 4: launch_fast<4>(a, excl, lists, blocks, st); break;
-      case 8: launch_fast<8>(a, excl, lists, blocks, st); break;
-      case 12: launch_fast<12>(a, excl, lists, blocks, st); break;
-      default: launch_fast<16>(a, excl, lists, blocks, st); break;
+      case 4: launch_fast<4>(a, excl, lists, st); break;
+      case 8: launch_fast<8>(a, excl, lists, st); break;
+      case 12: launch_fast<12>(a, excl, lists, st); break;
+      default: launch_fast<16>(a, excl, lists, st); break;
     }
     MOUSE_LAUNCH_CHECK("p2_sweep_fast_kernel");
   } else {

@@ -1,0 +1,174 @@
+"""Trajectory driver: frames are independent units (the reference loops over frame files with no
+carried state, ``calculate_local_ordering.py:39-76``), so they are block-sharded over the ranks of
+one node - one process per GPU - and the only communication is ONE final all-reduce of a packed
+buffer of order-parameter sums and counts.  ``torch.distributed`` is the
+plumbing (NCCL on GPUs, gloo in the CPU tests of the sharding / reduction logic)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+
+
+def shard_range(n_frames: int, rank: int, world: int):
+    """Contiguous block of frames of ``rank``: [r*F/G, (r+1)*F/G)."""
+    return (rank * n_frames) // world, ((rank + 1) * n_frames) // world
+
+
+@dataclass
+class TrajectoryTotals:
+    """What the final all-reduce carries (exactly reducible integers + f64 sums)."""
+    sum_s: float = 0.0        # sum over frames of S_frame
+    n_frames: int = 0         # frames that produced an S
+    sum_mean: float = 0.0     # sum over frames of sum_i m_i
+    n_refs: int = 0           # sum over frames of i_s
+    n_pairs: int = 0          # ordered in-cutoff pairs counted
+    n_skipped_frames: int = 0  # frames without any reference that has neighbours
+
+    def pack(self, device):
+        f = torch.tensor([self.sum_s, self.sum_mean], dtype=torch.float64, device=device)
+        i = torch.tensor([self.n_frames, self.n_refs, self.n_pairs, self.n_skipped_frames], dtype=torch.int64,
+                         device=device)
+        return f, i
+
+    @classmethod
+    def unpack(cls, f, i):
+        f, i = f.cpu().tolist(), i.cpu().tolist()
+        return cls(sum_s=f[0], sum_mean=f[1], n_frames=int(i[0]), n_refs=int(i[1]), n_pairs=int(i[2]),
+                   n_skipped_frames=int(i[3]))
+
+    def add_frame(self, sum_mean, n_refs, n_pairs):
+        if n_refs > 0:
+            self.sum_s += 1.5 * sum_mean / n_refs - 0.5
+            self.n_frames += 1
+        else:
+            self.n_skipped_frames += 1
+        self.sum_mean += sum_mean
+        self.n_refs += int(n_refs)
+        self.n_pairs += int(n_pairs)
+
+    @property
+    def mean_s(self):
+        return self.sum_s / self.n_frames if self.n_frames else float("nan")
+
+
+def all_reduce_totals(t: TrajectoryTotals, device) -> TrajectoryTotals:
+    """The single collective of the path: sum-all-reduce of the packed totals (two tiny tensors:
+    f64 sums and i64 counts; the integers reduce exactly)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return t
+    f, i = t.pack(device)
+    dist.all_reduce(f, op=dist.ReduceOp.SUM)
+    dist.all_reduce(i, op=dist.ReduceOp.SUM)
+    return TrajectoryTotals.unpack(f, i)
+
+
+class FramePipeline:
+    """Host-buffer entry point of the hot path for one topology: ``submit(positions_host)`` copies a
+    frame's positions from pinned host memory, runs K1-K4 and reads back the 48-byte totals.  Two
+    buffers / two streams: the copy of frame k+1 overlaps the kernels of frame k."""
+
+    def __init__(self, bond_atoms, mol, box, rcut, n_atoms, same_molecule=True, nbr_mask=None, ref_mask=None,
+                 device=None, depth=2):
+        engine.require_cuda()
+        self.device = torch.device(device or "cuda")
+        self.n_atoms = int(n_atoms)
+        self.bonds = engine.as_dev(bond_atoms, torch.int32, self.device)
+        self.n = int(self.bonds.shape[0])
+        self.mol = engine.as_dev(mol, torch.int32, self.device) if mol is not None else \
+            torch.zeros(self.n, dtype=torch.int32, device=self.device)
+        self.nbr = engine.as_dev(nbr_mask, torch.uint8, self.device)
+        self.ref = engine.as_dev(ref_mask, torch.uint8, self.device)
+        self.box = [float(b) for b in box]
+        self.rcut = float(rcut)
+        self.grid = _lib.grid_plan(self.box, self.rcut, self.n)
+        self.flags = (_lib.MOUSE_SAME_MOLECULE if same_molecule else 0) | (_lib.MOUSE_NO_CUTOFF if rcut < 0 else 0)
+        L = _lib.lib()
+        self.L = L
+        nbytes = L.mouse_workspace_bytes(self.n, C.byref(self.grid))
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.compute_stream = torch.cuda.Stream(device=self.device)
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append(dict(
+                pos=torch.empty((self.n_atoms, 3), dtype=torch.float64, device=self.device),
+                totals=torch.zeros(6, dtype=torch.int64, device=self.device),
+                totals_host=torch.zeros(6, dtype=torch.int64).pin_memory(),
+                copied=torch.cuda.Event(), done=torch.cuda.Event(), busy=False))
+        # one workspace and one set of per-bond outputs: frames are serialised on the compute stream
+        self.ws = torch.empty(int(nbytes) + 4096, dtype=torch.uint8, device=self.device)
+        self.vec = torch.empty((3, self.n), dtype=torch.float64, device=self.device)
+        self.ctr = torch.empty((3, self.n), dtype=torch.float64, device=self.device)
+        self.sum = torch.empty(self.n, dtype=torch.float64, device=self.device)
+        self.cnt = torch.empty(self.n, dtype=torch.int32, device=self.device)
+        self.mean = torch.empty(self.n, dtype=torch.float64, device=self.device)
+        self._next = 0
+        self._pending = []
+        self.h2d_bytes_per_frame = self.n_atoms * 3 * 8
+        self.d2h_bytes_per_frame = 48
+        self.kernels_per_frame = 9   # bond_build, cell_assign, 3 x scan, scatter, canon, sweep, reduce
+
+    def submit(self, positions_host: torch.Tensor):
+        """Enqueue one frame (``positions_host``: pinned (N_a,3) f64 CPU tensor).  Returns finished
+        results (list of totals dicts) that had to be drained to free a slot."""
+        out = []
+        s = self.slots[self._next]
+        if s["busy"]:
+            out.append(self._collect(s))
+        p = engine._ptr
+        with torch.cuda.stream(self.copy_stream):
+            s["pos"].copy_(positions_host, non_blocking=True)
+            s["copied"].record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(s["copied"])
+            st = C.c_void_p(self.compute_stream.cuda_stream)
+            _lib.check(self.L.mouse_p2_frame(p(s["pos"]), p(self.bonds), p(self.mol), p(self.nbr), p(self.ref), self.n,
+                                             C.byref(self.grid), self.flags, p(self.ws), self.ws.numel(), p(self.vec),
+                                             p(self.ctr), p(self.sum), p(self.cnt), p(self.mean), p(s["totals"]), st),
+                       "mouse_p2_frame")
+            s["totals_host"].copy_(s["totals"], non_blocking=True)
+            s["done"].record(self.compute_stream)
+        s["busy"] = True
+        self._pending.append(s)
+        self._next = (self._next + 1) % self.depth
+        return out
+
+    def _collect(self, s):
+        s["done"].synchronize()
+        s["busy"] = False
+        if s in self._pending:
+            self._pending.remove(s)
+        t = s["totals_host"]
+        return dict(sum_mean=float(t.view(torch.float64)[0]), n_refs=int(t[1]), n_pairs=int(t[2]),
+                    n_zero_len=int(t[3]))
+
+    def drain(self):
+        return [self._collect(s) for s in list(self._pending)]
+
+
+def local_ordering_trajectory(frames_positions, bond_atoms, mol, box, rcut, same_molecule=True, nbr_mask=None,
+                              ref_mask=None, device=None):
+    """Per-frame S of this rank's shard plus the trajectory totals reduced over all ranks.
+    ``frames_positions``: sequence of (N_a,3) float64 arrays / tensors (the WHOLE trajectory, every
+    rank indexes its own block).  Returns (list of (frame_index, S) for this rank, TrajectoryTotals)."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    lo, hi = shard_range(len(frames_positions), rank, world)
+    device = torch.device(device or "cuda")
+    totals = TrajectoryTotals()
+    per_frame = []
+    res = None
+    for f in range(lo, hi):
+        res = engine.p2_frame(frames_positions[f], bond_atoms, mol, box, rcut, same_molecule=same_molecule,
+                              nbr_mask=nbr_mask, ref_mask=ref_mask, device=device, out=res)
+        t = res.totals_dict()
+        totals.add_frame(t["sum_mean"], t["n_refs"], t["n_pairs"])
+        per_frame.append((f, np.float64(1.5 * t["sum_mean"] / t["n_refs"] - 0.5) if t["n_refs"] else np.float64("nan")))
+    return per_frame, all_reduce_totals(totals, device)
