@@ -80,21 +80,41 @@ __global__ void __launch_bounds__(RED_THREADS) p2_reduce_kernel(
     s_last = (ticket == (unsigned long long)gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (s_last) {
+    // the last block sums the block partials: fixed assignment and fixed tree -> deterministic
     __threadfence();
     double t = 0.0, r = 0.0, p = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) {  // ascending block order: deterministic
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += RED_THREADS) {
       t += ((volatile double *)partials)[3 * b];
       r += ((volatile double *)partials)[3 * b + 1];
       p += ((volatile double *)partials)[3 * b + 2];
     }
-    totals->sum_mean = t;
-    totals->n_refs = (int64_t)r;
-    totals->n_pairs = (int64_t)p;
-    totals->n_zero_len = ((volatile int64_t *)counters)[0];
-    totals->n_band = ((volatile int64_t *)counters)[1];
-    totals->n_hist_over = ((volatile int64_t *)counters)[3];
-    counters[2] = 0;
+    t = warp_sum(t);
+    r = warp_sum(r);
+    p = warp_sum(p);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+      s_sum[threadIdx.x >> 5] = t;
+      s_refs[threadIdx.x >> 5] = (long long)r;
+      s_pairs[threadIdx.x >> 5] = (long long)p;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tt = 0.0;
+      long long rr = 0, pp = 0;
+      for (int w = 0; w < RED_THREADS / 32; ++w) {
+        tt += s_sum[w];
+        rr += s_refs[w];
+        pp += s_pairs[w];
+      }
+      totals->sum_mean = tt;
+      totals->n_refs = rr;
+      totals->n_pairs = pp;
+      totals->n_zero_len = ((volatile int64_t *)counters)[0];
+      totals->n_band = ((volatile int64_t *)counters)[1];
+      totals->n_hist_over = ((volatile int64_t *)counters)[3];
+      counters[2] = 0;
+    }
   }
 }
 
