@@ -268,3 +268,19 @@ def test_rdf_against_c_oracle_larger():
         h, edges = eng.rdf_frame(melt.positions, melt.atom_type, melt.mol, 2, melt.box, 0., 5., 1000, same_molecule=same)
         exp, e2 = c_oracle.rdf(melt.positions, melt.atom_type, melt.mol, 2, melt.box, 0., 5., 1000, same)
         assert np.array_equal(edges, e2) and np.array_equal(h.cpu().numpy(), exp)
+
+
+def test_cli_matches_reference_output(capsys):
+    """calculate_local_ordering.py <golden data file> --bondtypes 1 --max 1.5 --same-molecule prints the
+    reference's S for that file (the golden S came from the reference's own Config of the same arrays)."""
+    import os
+    import calculate_local_ordering as cli
+    from tests.util import GOLDEN_DIR
+    _, g = load_golden("melt_290_rc15_same")
+    cli.main([os.path.join(GOLDEN_DIR, "melt_290.data"), "--bondtypes", "1", "--max", "1.5", "--same-molecule"])
+    out = capsys.readouterr().out.strip()
+    assert abs(float(out) - float(g["ref_S"])) <= RTOL * abs(float(g["ref_S"]))
+    _, g = load_golden("melt_290_rc15_diffmol")
+    cli.main([os.path.join(GOLDEN_DIR, "melt_290.data"), "--bondtypes", "1", "--max", "1.5"])
+    out = capsys.readouterr().out.strip()
+    assert abs(float(out) - float(g["ref_S"])) <= RTOL * abs(float(g["ref_S"]))
