@@ -32,99 +32,128 @@ struct SweepArgs {
   int64_t *counters;
   const int64_t *row_ptr;  // lists only
   int32_t *nbr_idx;
+  int32_t *fix_list;       // home cells queued for p2_fixup_kernel (length in counters[3])
+  unsigned *redo_mask;     // [FAST_MAX_PASSES][n] per sorted slot: lanes to re-decide exactly (fast sweep -> fixup)
   int same_molecule;
   int no_cutoff;
 };
 
 // ------------------------------------------------------------------ rare exact path (fast kernel)
-// Re-decides ALL candidates of one lane with the reference's FP64 expressions.  Called only for
-// lanes that saw a candidate inside the FP32 guard band around rc^2 or a near-zero dot product.
-// Returns the exact hit mask over the lane's slots (slot c -> bit c) and the exact sum of cos^2.
-struct RedoOut {
-  unsigned mask;
-  double acc;
-};
-
-__device__ __noinline__ RedoOut exact_redo(const int32_t *__restrict__ idx, const double *__restrict__ ctr,
-                                           const double *__restrict__ vec, const float4 *__restrict__ P, size_t n,
-                                           const double *box, double rc2, int si, const int *pref, const int *start,
-                                           int tbase, int tstride, int nslots, bool excl_mol,
-                                           unsigned long long *band_counter) {
-  const int bi = idx[si];
-  const double cix = ctr[bi], ciy = ctr[n + bi], ciz = ctr[2 * n + bi];
+// The reference's decision for ONE pair of sorted slots (si = reference, sj = candidate): returns
+// cos^2 exactly as ordering_functions.py:95-113 evaluates it, or 0.0 when the pair is not counted
+// (out of range, or cos^2 == 0 which the reference masks).
+__device__ __forceinline__ double exact_pair(const int32_t *__restrict__ idx, const double *__restrict__ ctr,
+                                             const double *__restrict__ vec, size_t n, const double *box, double rc2,
+                                             int si, int sj) {
+  const int bi = idx[si], bj = idx[sj];
+  const double rsq = mouse_rsq_exact(ctr[bi], ctr[n + bi], ctr[2 * n + bi], ctr[bj], ctr[n + bj], ctr[2 * n + bj], box);
+  if (!(rsq <= rc2)) return 0.0;
   const double ax = vec[bi], ay = vec[n + bi], az = vec[2 * n + bi];
+  const double bx = vec[bj], by = vec[n + bj], bz = vec[2 * n + bj];
+  const double dot = mouse_dot_exact(ax, ay, az, bx, by, bz);
   const double nr = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
-  const int moli = __float_as_int(P[si].w);
-  const int T = pref[27];
-  RedoOut out;
-  out.mask = 0;
-  out.acc = 0.0;
-  for (int c = 0; c < nslots; ++c) {
-    const int t = tbase + tstride * c;   // this lane's candidate in slot c
-    if (t >= T) break;
-    int k = 0;
-    for (int step = 16; step > 0; step >>= 1) {
-      const int k2 = k + step;
-      if (k2 < 27 && pref[k2] <= t) k = k2;
-    }
-    const int sjv = start[k] + (t - pref[k]);
-    if (sjv == si) continue;
-    if (excl_mol && __float_as_int(P[sjv].w) == moli) continue;
-    const int bj = idx[sjv];
-    const double rsq = mouse_rsq_exact(cix, ciy, ciz, ctr[bj], ctr[n + bj], ctr[2 * n + bj], box);
-    if (!(rsq <= rc2)) continue;
-    const double bx = vec[bj], by = vec[n + bj], bz = vec[2 * n + bj];
-    const double dot = mouse_dot_exact(ax, ay, az, bx, by, bz);
-    const double nj = __dadd_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)), __dmul_rn(bz, bz));
-    const double cs = __ddiv_rn(__ddiv_rn(__dmul_rn(dot, dot), nr), nj);
-    if (cs != 0.0) {
-      out.mask |= 1u << c;
-      out.acc += cs;
-    }
-  }
-  atomicAdd(band_counter, 1ULL);
-  return out;
+  const double nj = __dadd_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)), __dmul_rn(bz, bz));
+  return __ddiv_rn(__ddiv_rn(__dmul_rn(dot, dot), nr), nj);
 }
 
+// candidate t of the concatenated 27-cell list -> sorted slot (largest k < 27 with pref[k] <= t)
+__device__ __forceinline__ int cand_slot(const int *pref, const int *start, int t) {
+  int k = 0;
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1) {
+    const int k2 = k + step;
+    if (k2 < 27 && pref[k2] <= t) k = k2;
+  }
+  return start[k] + (t - pref[k]);
+}
+
+#define FAST_MAX_PASSES 4   // redo masks are kept for this many candidate passes per home cell
 #ifndef FAST_TARGET_WARPS
 #define FAST_TARGET_WARPS 16   // resident warps per SM the register allocation is sized for
 #endif
+#ifndef FAST_BU
+#define FAST_BU 2             // hits per phase-B trip (independent FP64 chains per lane)
+#endif
+#ifndef FAST_RUN
+#define FAST_RUN 1             // consecutive home cells per CTA visit (L1 reuse of shared neighbour cells)
+#endif
 
-// One CTA of K warps per home cell (grid-stride over home cells).
-//   load  : the candidates of the 27 neighbour cells are concatenated into t = 0..T-1 and dealt out in
-//           chunks of 32: chunk g belongs to warp g % K, slot g / K, lane t % 32.  Each lane keeps its
-//           candidates' cell-local FP32 coordinates (shifted by the periodic cell offset) in REGISTERS and
-//           their FP64 unit vectors (+ molecule codes) in SHARED memory.  The home cell's reference bonds
-//           are staged in shared memory in chunks of 32 (lane l of every warp owns reference chunk0 + l).
-//   per reference bond (warp-uniform loop, no global memory traffic):
+// neighbour table of a home cell: per neighbour k (lane k < 27) first sorted slot, exclusive prefix of the
+// counts, periodic cell shift.  Returns T (all lanes) and the home cell's own prefix.
+__device__ __forceinline__ int neighbour_table(const SweepArgs &a, int home, int lane, int *s_start, int *s_pref,
+                                               float (*s_off)[32], int &home_pref) {
+  const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
+  const int cx = home % nx, cy = (home / nx) % ny, cz = home / (nx * ny);
+  int st = 0, cn = 0;
+  float ox = 0.f, oy = 0.f, oz = 0.f;
+  if (lane < 27) {
+    const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+    int mx = cx + dx, my = cy + dy, mz = cz + dz;
+    mx += (mx < 0) ? nx : 0;
+    mx -= (mx >= nx) ? nx : 0;
+    my += (my < 0) ? ny : 0;
+    my -= (my >= ny) ? ny : 0;
+    mz += (mz < 0) ? nz : 0;
+    mz -= (mz >= nz) ? nz : 0;
+    const int cid = (mz * ny + my) * nx + mx;
+    st = a.cell_start[cid];
+    cn = a.cell_start[cid + 1] - st;
+    ox = (float)dx * a.g.cwf[0];
+    oy = (float)dy * a.g.cwf[1];
+    oz = (float)dz * a.g.cwf[2];
+  }
+  int incl = cn;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(MOUSE_FULL_MASK, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const int T = __shfl_sync(MOUSE_FULL_MASK, incl, 31);
+  home_pref = __shfl_sync(MOUSE_FULL_MASK, incl - cn, 13);  // neighbour 13 = the home cell itself
+  __syncwarp();
+  s_start[lane] = st;
+  s_pref[lane] = incl - cn;      // lanes >= 27 hold T
+  if (s_off) {
+    s_off[0][lane] = ox;
+    s_off[1][lane] = oy;
+    s_off[2][lane] = oz;
+  }
+  __syncwarp();
+  return T;
+}
+
+// One warp per home cell (CTA = 1 warp; CTAs visit runs of FAST_RUN consecutive home cells).
+//   load  : the candidates of the 27 neighbour cells are concatenated into t = 0..T-1; lane t % 32 keeps
+//           candidate t's cell-local FP32 coordinates (shifted by the periodic cell offset) in REGISTERS
+//           (slot t / 32) and its FP64 unit vector (+ molecule code) in SHARED memory.  The home cell's
+//           reference bonds are staged in shared memory in chunks of 32 (lane l owns reference chunk0 + l).
+//   per reference bond (warp-uniform loop, no global memory traffic, no calls):
 //     A   : every lane tests its candidates in FP32 (3 FADD, FMUL, 2 FFMA, FADD) and shifts the sign of
 //           d2 - rc2 into a hit mask (one funnel shift); min |d2 - rc2| is tracked for the guard band.
 //     B   : lanes walk their hit bits (warp-uniform trip count, branch-free body):
 //           cos^2 = (u_i . u_j)^2 in FP64 from shared memory.
-//     fix : lanes that saw a guard-band candidate or a near-zero dot redo their slots exactly.
+//     flag: a lane that saw a guard-band candidate or a near-zero dot drops its contribution for this
+//           reference and sets its bit in the reference's redo mask (decided exactly by p2_fixup_kernel).
 //     sum : warp-shuffle reduction in a fixed order; the result stays in the owning lane's registers.
-//   flush : the K warps' partial results are combined in warp order through shared memory (deterministic)
-//           and stored with one write per reference.
-template <int SLOTS, int K, bool EXCL_MOL, bool LISTS>
-__global__ void __launch_bounds__(K * 32, (FAST_TARGET_WARPS / K > 32 ? 32 : FAST_TARGET_WARPS / K)) p2_sweep_fast_kernel(const SweepArgs a) {
-  static_assert(!LISTS || K == 1, "pair lists use the single-warp variant");
+//   flush : one store per reference (sum, count, redo mask).
+template <int SLOTS, bool EXCL_MOL, bool LISTS>
+__global__ void __launch_bounds__(32, (FAST_TARGET_WARPS > 32 ? 32 : FAST_TARGET_WARPS))
+    p2_sweep_fast_kernel(const SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_start[32];
   __shared__ int s_pref[32];
   __shared__ float s_off[3][32];
   __shared__ float4 s_home[32];          // the chunk's reference bonds: cell-local xyz + molecule code
   __shared__ double s_hu[3][32];         //                             FP64 unit vectors
-  __shared__ double s_pacc[K][32];       // partial results of warps 1..K-1
-  __shared__ int s_pcnt[K][32];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  constexpr int NC = SLOTS * 32;         // candidates per warp and pass
+  const int lane = threadIdx.x;
+  constexpr int NC = SLOTS * 32;         // candidates per pass
   constexpr int GROUPS = (SLOTS + 3) / 4;
-  double *su = reinterpret_cast<double *>(smem_raw) + (size_t)wib * (3 * NC) + lane;      // [3][NC], lane column
-  int *smol = reinterpret_cast<int *>(smem_raw + sizeof(double) * 3 * NC * K) + wib * NC + lane;
+  constexpr int BU = FAST_BU;
+  double *su = reinterpret_cast<double *>(smem_raw) + lane;      // [3][NC], lane column
+  int *smol = reinterpret_cast<int *>(smem_raw + sizeof(double) * 3 * NC) + lane;
   const float4 *__restrict__ P = a.P;
   const double4 *__restrict__ U = a.U;
   const int32_t *__restrict__ cell_start = a.cell_start;
-  const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
   // guard band [rc2_lo, rc2_hi] around rc^2: centre / half width in FP32
   const float rc2_c = 0.5f * (a.g.rc2_lo + a.g.rc2_hi);
   const float rc2_w = 0.5f * (a.g.rc2_hi - a.g.rc2_lo) * 1.0001f;
@@ -140,234 +169,217 @@ __global__ void __launch_bounds__(K * 32, (FAST_TARGET_WARPS / K > 32 ? 32 : FAS
 #define TM_ADD(x)
 #endif
 
-  for (int home = blockIdx.x; home < a.g.ncell; home += gridDim.x) {
-    const int hs = cell_start[home], he = cell_start[home + 1];
-    if (hs == he) continue;          // CTA-uniform
-    TM_START();
-    const int cx = home % nx, cy = (home / nx) % ny, cz = home / (nx * ny);
-    // neighbour table (every warp computes it redundantly in registers; warp 0 publishes it)
-    int st = 0, cn = 0;
-    float ox = 0.f, oy = 0.f, oz = 0.f;
-    if (lane < 27) {
-      const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
-      int mx = cx + dx, my = cy + dy, mz = cz + dz;
-      mx += (mx < 0) ? nx : 0;
-      mx -= (mx >= nx) ? nx : 0;
-      my += (my < 0) ? ny : 0;
-      my -= (my >= ny) ? ny : 0;
-      mz += (mz < 0) ? nz : 0;
-      mz -= (mz >= nz) ? nz : 0;
-      const int cid = (mz * ny + my) * nx + mx;
-      st = cell_start[cid];
-      cn = cell_start[cid + 1] - st;
-      ox = (float)dx * a.g.cwf[0];
-      oy = (float)dy * a.g.cwf[1];
-      oz = (float)dz * a.g.cwf[2];
-    }
-    int incl = cn;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(MOUSE_FULL_MASK, incl, o);
-      if (lane >= o) incl += y;
-    }
-    const int T = __shfl_sync(MOUSE_FULL_MASK, incl, 31);
-    const int home_pref = __shfl_sync(MOUSE_FULL_MASK, incl - cn, 13);  // neighbour 13 = the home cell itself
-    __syncthreads();                 // previous home cell fully consumed
-    if (wib == 0) {
-      s_start[lane] = st;
-      s_pref[lane] = incl - cn;      // lanes >= 27 hold T (sentinel, read by exact_redo as pref[27])
-      s_off[0][lane] = ox;
-      s_off[1][lane] = oy;
-      s_off[2][lane] = oz;
-    }
-    __syncthreads();
+  // persistent warps fetch runs of FAST_RUN consecutive home cells from a global ticket counter
+  // (dynamic load balance; consecutive cells share 18 of their 27 neighbour cells -> L1/L2 reuse)
+  const int nruns = (a.g.ncell + FAST_RUN - 1) / FAST_RUN;
+  for (;;) {
+    int run = 0;
+    if (lane == 0) run = (int)atomicAdd((unsigned long long *)&a.counters[2], 1ULL);
+    run = __shfl_sync(MOUSE_FULL_MASK, run, 0);
+    if (run >= nruns) break;
+    for (int home = run * FAST_RUN; home < min(a.g.ncell, (run + 1) * FAST_RUN); ++home) {
+      const int hs = cell_start[home], he = cell_start[home + 1];
+      if (hs == he) continue;
+      TM_START();
+      int home_pref;
+      const int T = neighbour_table(a, home, lane, s_start, s_pref, s_off, home_pref);
+      unsigned home_any = (!LISTS && T > FAST_MAX_PASSES * NC) ? 1u : 0u;   // needs p2_fixup_kernel?
 
-    for (int base = 0; base < T; base += NC * K) {
-      float xr[SLOTS], yr[SLOTS], zr[SLOTS];
+      // (candidate passes beyond FAST_MAX_PASSES are left entirely to p2_fixup_kernel)
+      for (int base = 0, pass = 0; base < T && (LISTS || pass < FAST_MAX_PASSES); base += NC, ++pass) {
+        float xr[SLOTS], yr[SLOTS], zr[SLOTS];
+        __syncwarp();
 #pragma unroll
-      for (int c = 0; c < SLOTS; ++c) {
-        const int t = base + 32 * (c * K + wib) + lane;
-        xr[c] = 1e30f;
-        yr[c] = 0.f;
-        zr[c] = 0.f;
-        if (t < T) {
-          int k = 0;  // largest k < 27 with pref[k] <= t
+        for (int c = 0; c < SLOTS; ++c) {
+          const int t = base + 32 * c + lane;
+          xr[c] = 1e30f;
+          yr[c] = 0.f;
+          zr[c] = 0.f;
+          if (t < T) {
+            int k = 0;  // largest k < 27 with pref[k] <= t
 #pragma unroll
-          for (int step = 16; step > 0; step >>= 1) {
-            const int k2 = k + step;
-            if (k2 < 27 && s_pref[k2] <= t) k = k2;
+            for (int step = 16; step > 0; step >>= 1) {
+              const int k2 = k + step;
+              if (k2 < 27 && s_pref[k2] <= t) k = k2;
+            }
+            const int j = s_start[k] + (t - s_pref[k]);
+            const float4 p = __ldg(P + j);
+            const double4 u = U[j];
+            xr[c] = p.x + s_off[0][k];
+            yr[c] = p.y + s_off[1][k];
+            zr[c] = p.z + s_off[2][k];
+            su[c * 32] = u.x;
+            su[NC + c * 32] = u.y;
+            su[2 * NC + c * 32] = u.z;
+            if (EXCL_MOL) smol[c * 32] = __float_as_int(p.w);
+          } else {   // padded slot: finite data for the branch-free walk
+            su[c * 32] = 0.0;
+            su[NC + c * 32] = 0.0;
+            su[2 * NC + c * 32] = 0.0;
+            if (EXCL_MOL) smol[c * 32] = 0;
           }
-          const int j = s_start[k] + (t - s_pref[k]);
-          const float4 p = __ldg(P + j);
-          const double4 u = U[j];
-          xr[c] = p.x + s_off[0][k];
-          yr[c] = p.y + s_off[1][k];
-          zr[c] = p.z + s_off[2][k];
-          su[c * 32] = u.x;
-          su[NC + c * 32] = u.y;
-          su[2 * NC + c * 32] = u.z;
-          if (EXCL_MOL) smol[c * 32] = __float_as_int(p.w);
         }
-      }
-      // slots of this warp that hold candidates in this pass
-      const int nchunks = min(SLOTS * K, (T - base + 31) >> 5);
-      const int nslots = (nchunks - wib + K - 1) / K;
-      const int ngroups = (nslots + 3) >> 2;
+        const int nslots = min(SLOTS, (T - base + 31) >> 5);
+        const int ngroups = (nslots + 3) >> 2;
 
-      for (int chunk0 = hs; chunk0 < he; chunk0 += 32) {
-        const int nchunk = min(32, he - chunk0);
-        int my_idx = 0;
-        bool my_ref = false;
-        __syncthreads();             // staging buffers free (and, first time, su complete per warp)
-        if (lane < nchunk) {
-          const int ic = chunk0 + lane;
-          my_idx = a.idx[ic];
-          my_ref = (a.flag[ic] & 1) != 0;
-          if (wib == 0) {
+        for (int chunk0 = hs; chunk0 < he; chunk0 += 32) {
+          const int nchunk = min(32, he - chunk0);
+          int my_idx = 0;
+          bool my_ref = false;
+          __syncwarp();
+          if (lane < nchunk) {
+            const int ic = chunk0 + lane;
+            my_idx = a.idx[ic];
+            my_ref = (a.flag[ic] & 1) != 0;
             s_home[lane] = __ldg(P + ic);
             const double4 u = U[ic];
             s_hu[0][lane] = u.x;
             s_hu[1][lane] = u.y;
             s_hu[2][lane] = u.z;
           }
-        }
-        const unsigned refmask = __ballot_sync(MOUSE_FULL_MASK, my_ref);
-        double racc = 0.0;   // this warp's partial result of reference chunk0 + lane
-        int rcnt = 0;
-        __syncthreads();
-        TM_ADD(tm_load);
+          const unsigned refmask = __ballot_sync(MOUSE_FULL_MASK, my_ref);
+          double racc = 0.0;      // result of reference chunk0 + lane
+          int rcnt = 0;
+          unsigned rredo = 0;     // lanes whose contribution to reference chunk0 + lane must be decided exactly
+          __syncwarp();
+          TM_ADD(tm_load);
 
-        for (int il = 0; il < nchunk; ++il) {
-          if (!((refmask >> il) & 1u)) continue;
-          const float4 pi = s_home[il];
-          const int moli = __float_as_int(pi.w);
-          const double uix = s_hu[0][il], uiy = s_hu[1][il], uiz = s_hu[2][il];
-          // the reference bond is itself a candidate (home cell = neighbour 13): chunk / lane of its slot
-          const int tself = home_pref + (chunk0 + il - hs) - base;
-          // ---- A: FP32 filter; slot c ends up in bit c (groups are walked from the last slot down)
-          unsigned mask = 0;
-          float band = 1e30f;
+          for (int il = 0; il < nchunk; ++il) {
+            if (!((refmask >> il) & 1u)) continue;
+            const float4 pi = s_home[il];
+            const int moli = __float_as_int(pi.w);
+            const double uix = s_hu[0][il], uiy = s_hu[1][il], uiz = s_hu[2][il];
+            // the reference bond is itself a candidate (home cell = neighbour 13): slot / lane of it
+            const int tself = home_pref + (chunk0 + il - hs) - base;
+            // ---- A: FP32 filter; slot c ends up in bit c (groups are walked from the last slot down)
+            unsigned mask = 0;
+            float band = 1e30f;
 #pragma unroll
-          for (int g = GROUPS - 1; g >= 0; --g) {
-            if (g < ngroups) {
+            for (int g = GROUPS - 1; g >= 0; --g) {
+              if (g < ngroups) {
 #pragma unroll
-              for (int c = min(4 * g + 3, SLOTS - 1); c >= 4 * g; --c) {
-                const float dx = xr[c] - pi.x, dy = yr[c] - pi.y, dz = zr[c] - pi.z;
-                const float t = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) - rc2_c;   // < 0: inside
-                mask = __funnelshift_l(__float_as_uint(t), mask, 1);
-                band = fminf(band, fabsf(t));
+                for (int c = min(4 * g + 3, SLOTS - 1); c >= 4 * g; --c) {
+                  const float dx = xr[c] - pi.x, dy = yr[c] - pi.y, dz = zr[c] - pi.z;
+                  const float t = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) - rc2_c;   // < 0: inside
+                  mask = __funnelshift_l(__float_as_uint(t), mask, 1);
+                  band = fminf(band, fabsf(t));
+                }
               }
             }
-          }
-          if (SLOTS % 4 != 0) mask >>= 0;   // (slot numbering is unaffected by the partial last group)
-          {
-            const int gself = tself >> 5;   // chunk that holds the reference itself
-            if (tself >= 0 && gself < SLOTS * K && (gself % K) == wib && lane == (tself & 31))
-              mask &= ~(1u << (gself / K));
-          }
-          TM_ADD(tm_a);
-          // ---- B: FP64 cos^2 of the hits
-          bool redo = band <= rc2_w;
-          double acc = 0.0;
-          unsigned m = mask;
-          unsigned nearz = 0xffffffffu;
-          const int iters = __reduce_max_sync(MOUSE_FULL_MASK, __popc(mask));
-          for (int it = 0; it < iters; ++it) {
-            // branch-free body: idle lanes read slot 0 and contribute d * 0
-            const bool act = m != 0;
-            const int c = act ? (__ffs(m) - 1) : 0;
-            m &= m - 1;
-            const double *q = su + c * 32;
-            const double d = fma(uix, q[0], fma(uiy, q[NC], uiz * q[2 * NC]));
-            bool use = act;
-            if (EXCL_MOL) {
-              const bool same = smol[c * 32] == moli;
-              mask &= ~((act && same) ? (1u << c) : 0u);
-              use = act && !same;
+            if (tself >= 0 && tself < NC && lane == (tself & 31)) mask &= ~(1u << (tself >> 5));
+            TM_ADD(tm_a);
+            // ---- B: FP64 cos^2 of the hits
+            double acc = 0.0;
+            unsigned m = mask;
+            unsigned nearz = 0xffffffffu;
+            const int iters = __reduce_max_sync(MOUSE_FULL_MASK, __popc(mask));
+            // BU hits per trip: BU independent load -> FMA chains per lane (ILP); branch-free bodies,
+            // idle lanes read slot 0 and contribute d * 0
+            double acc2[BU];
+#pragma unroll
+            for (int u = 0; u < BU; ++u) acc2[u] = 0.0;
+            for (int it = 0; it < iters; it += BU) {
+#pragma unroll
+              for (int u = 0; u < BU; ++u) {
+                // highest hit bit first; an exhausted lane (m == 0) clamps to the last slot (finite data,
+                // contributes d * 0): no branch, one bit scan
+                const bool act = m != 0;
+                const int c = (int)min((unsigned)(31 - __clz((int)m)), (unsigned)(SLOTS - 1));
+                m &= ~(1u << c);
+                const double *q = su + c * 32;
+                const double d = fma(uix, q[0], fma(uiy, q[NC], uiz * q[2 * NC]));
+                bool use = act;
+                if (EXCL_MOL) {
+                  const bool same = smol[c * 32] == moli;
+                  mask &= ~((act && same) ? (1u << c) : 0u);
+                  use = act && !same;
+                }
+                const double w = use ? d : 0.0;
+                acc2[u] = fma(d, w, acc2[u]);
+                // smallest |d| (as its high word) over the used hits: |d| < 1e-9 must be decided exactly (:113)
+                const unsigned h = use ? ((unsigned)__double2hiint(d) & 0x7fffffffu) : 0xffffffffu;
+                nearz = min(nearz, h);
+              }
             }
-            const double w = use ? d : 0.0;
-            acc = fma(d, w, acc);
-            // smallest |d| (as its high word) over the used hits: |d| < 1e-9 must be decided exactly (:113)
-            const unsigned h = use ? ((unsigned)__double2hiint(d) & 0x7fffffffu) : 0xffffffffu;
-            nearz = min(nearz, h);
-          }
-          redo |= nearz < 0x3e112e0bu;
-          TM_ADD(tm_b);
-          // ---- fix: exact re-decision for the (rare) flagged lanes
-          if (__any_sync(MOUSE_FULL_MASK, redo)) {
+#pragma unroll
+            for (int u = 0; u < BU; ++u) acc += acc2[u];
+            bool redo = (band <= rc2_w) || (nearz < 0x3e112e0bu);
+            TM_ADD(tm_b);
+            if (LISTS) {
+              // pair lists are extracted with every decision made in place (not on the timed path)
+              if (redo) {
+                mask = 0;
+                for (int c = 0; c < nslots; ++c) {
+                  const int t = base + 32 * c + lane;
+                  if (t >= T) break;
+                  const int sj = cand_slot(s_pref, s_start, t);
+                  if (sj == chunk0 + il) continue;
+                  if (EXCL_MOL && __float_as_int(P[sj].w) == moli) continue;
+                  if (exact_pair(a.idx, a.ctr, a.vec, (size_t)a.n, a.g.box, a.g.rc2, chunk0 + il, sj) != 0.0)
+                    mask |= 1u << c;
+                }
+              }
+              __syncwarp();
+              int cntl = __popc(mask);
+              const int o = __shfl_sync(MOUSE_FULL_MASK, my_idx, il);
+              int64_t row = a.row_ptr[o] + a.out_cnt[o];  // out_cnt = entries written by earlier passes
+              int incl_c = cntl;
+#pragma unroll
+              for (int off = 1; off < 32; off <<= 1) {
+                int y = __shfl_up_sync(MOUSE_FULL_MASK, incl_c, off);
+                if (lane >= off) incl_c += y;
+              }
+              row += incl_c - cntl;
+              unsigned mm = mask;
+              while (mm) {
+                const int c = __ffs(mm) - 1;
+                mm &= mm - 1;
+                a.nbr_idx[row++] = a.idx[cand_slot(s_pref, s_start, base + 32 * c + lane)];
+              }
+              cntl = __reduce_add_sync(MOUSE_FULL_MASK, cntl);
+              if (lane == 0) a.out_cnt[o] += cntl;
+              __syncwarp();
+              continue;
+            }
+            // ---- flag: flagged lanes drop their contribution; p2_fixup_kernel adds the exact one
+            const unsigned fm = __ballot_sync(MOUSE_FULL_MASK, redo);
+            home_any |= fm;
             if (redo) {
-              const RedoOut ro = exact_redo(a.idx, a.ctr, a.vec, P, (size_t)a.n, a.g.box, a.g.rc2, chunk0 + il, s_pref,
-                                            s_start, base + 32 * wib + lane, 32 * K, nslots, EXCL_MOL,
-                                            (unsigned long long *)&a.counters[1]);
-              mask = ro.mask;
-              acc = ro.acc;
+              acc = 0.0;
+              mask = 0;
             }
+            acc = warp_sum(acc);
+            const int cnt = __reduce_add_sync(MOUSE_FULL_MASK, __popc(mask));
+            if (lane == il) {
+              racc = acc;
+              rcnt = cnt;
+              rredo = fm;
+            }
+            TM_ADD(tm_e);
           }
-          int cnt = __popc(mask);
-          if (LISTS) {
-            const int o = __shfl_sync(MOUSE_FULL_MASK, my_idx, il);
-            int64_t row = a.row_ptr[o] + a.out_cnt[o];  // out_cnt = entries written by earlier passes
-            int incl_c = cnt;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-              int y = __shfl_up_sync(MOUSE_FULL_MASK, incl_c, off);
-              if (lane >= off) incl_c += y;
-            }
-            row += incl_c - cnt;
-            unsigned mm = mask;
-            while (mm) {
-              const int c = __ffs(mm) - 1;
-              mm &= mm - 1;
-              const int t = base + 32 * (c * K + wib) + lane;
-              int k = 0;
-              for (int step = 16; step > 0; step >>= 1) {
-                const int k2 = k + step;
-                if (k2 < 27 && s_pref[k2] <= t) k = k2;
+          // flush the chunk: one store per reference, no global read unless a second pass is running
+          if (!LISTS && lane < nchunk) {
+            if (my_ref) {
+              if (base == 0) {
+                if (nzero) {
+                  racc = __longlong_as_double(0x7ff8000000000000LL);
+                  rcnt += (int)nzero;
+                }
+                a.out_sum[my_idx] = racc;
+                a.out_cnt[my_idx] = rcnt;
+              } else {
+                a.out_sum[my_idx] += racc;
+                a.out_cnt[my_idx] += rcnt;
               }
-              a.nbr_idx[row++] = a.idx[s_start[k] + (t - s_pref[k])];
             }
-            __syncwarp();
-          }
-          acc = warp_sum(acc);
-          cnt = __reduce_add_sync(MOUSE_FULL_MASK, cnt);
-          if (lane == il) {
-            racc = acc;
-            rcnt = cnt;
+            a.redo_mask[(size_t)pass * a.n + chunk0 + lane] = rredo;
           }
           TM_ADD(tm_e);
         }
-        // flush the chunk: combine the K warps' partials in warp order, one store per reference
-        if (K > 1) {
-          if (wib > 0) {
-            s_pacc[wib][lane] = racc;
-            s_pcnt[wib][lane] = rcnt;
-          }
-          __syncthreads();
-          if (wib == 0) {
-#pragma unroll
-            for (int w = 1; w < K; ++w) {
-              racc += s_pacc[w][lane];
-              rcnt += s_pcnt[w][lane];
-            }
-          }
-        }
-        if (wib == 0 && my_ref) {
-          if (LISTS) {
-            a.out_cnt[my_idx] += rcnt;
-          } else if (base == 0) {
-            if (nzero) {
-              racc = __longlong_as_double(0x7ff8000000000000LL);
-              rcnt += (int)nzero;
-            }
-            a.out_sum[my_idx] = racc;
-            a.out_cnt[my_idx] = rcnt;
-          } else {
-            a.out_sum[my_idx] += racc;
-            a.out_cnt[my_idx] += rcnt;
-          }
-        }
-        TM_ADD(tm_e);
       }
+      // home cells with dropped contributions (or skipped passes) are queued for p2_fixup_kernel
+      if (!LISTS && home_any && lane == 0)
+        a.fix_list[atomicAdd((unsigned long long *)&a.counters[3], 1ULL)] = home;
     }
   }
 #ifdef MOUSE_PHASE_TIMERS
@@ -378,6 +390,76 @@ __global__ void __launch_bounds__(K * 32, (FAST_TARGET_WARPS / K > 32 ? 32 : FAS
     atomicAdd((unsigned long long *)&a.counters[7], (unsigned long long)tm_e);
   }
 #endif
+}
+
+// Exact re-decision of the contributions the fast sweep dropped: one warp per home cell; for every reference
+// with a non-zero redo mask, every flagged lane's candidates (slots 0..SLOTS-1 of that pass) are evaluated with
+// the reference's FP64 expressions - lane s takes slot s - and added to the reference's sum / count in a fixed
+// order (pass, lane, slot tree), so the result stays deterministic.  Candidate passes beyond FAST_MAX_PASSES
+// (more than FAST_MAX_PASSES * SLOTS * 32 candidates around one cell) are recomputed exactly as a whole.
+template <int SLOTS, bool EXCL_MOL>
+__global__ void __launch_bounds__(32) p2_fixup_kernel(const SweepArgs a) {
+  __shared__ int s_start[32];
+  __shared__ int s_pref[32];
+  const int lane = threadIdx.x;
+  constexpr int NC = SLOTS * 32;
+  const size_t n = (size_t)a.n;
+  const int nfix = (int)((volatile int64_t *)a.counters)[3];
+  for (int e = blockIdx.x; e < nfix; e += gridDim.x) {
+    const int home = a.fix_list[e];
+    const int hs = a.cell_start[home], he = a.cell_start[home + 1];
+    int home_pref = 0;
+    const int T = neighbour_table(a, home, lane, s_start, s_pref, nullptr, home_pref);
+    const int npass = (T + NC - 1) / NC;
+    for (int chunk0 = hs; chunk0 < he; chunk0 += 32) {
+      // lane l reads the redo masks of reference chunk0 + l (coalesced), flagged references are then
+      // visited one at a time
+      const int i_l = chunk0 + lane;
+      unsigned mk[FAST_MAX_PASSES];
+      bool want = false;
+#pragma unroll
+      for (int pass = 0; pass < FAST_MAX_PASSES; ++pass) {
+        mk[pass] = (i_l < he && pass < npass) ? a.redo_mask[(size_t)pass * n + i_l] : 0u;
+        want |= mk[pass] != 0;
+      }
+      want = (i_l < he) && (a.flag[min(i_l, he - 1)] & 1) && (want || npass > FAST_MAX_PASSES);
+      unsigned todo = __ballot_sync(MOUSE_FULL_MASK, want);
+      while (todo) {
+        const int il = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int i = chunk0 + il;
+        const int moli = __float_as_int(a.P[i].w);
+        double add = 0.0;
+        int addc = 0;
+        for (int pass = 0; pass < npass; ++pass) {
+          // passes the fast sweep skipped are evaluated for every lane
+          unsigned lanes = 0xffffffffu;
+#pragma unroll
+          for (int q = 0; q < FAST_MAX_PASSES; ++q)
+            if (q == pass) lanes = __shfl_sync(MOUSE_FULL_MASK, mk[q], il);
+          while (lanes) {
+            const int L = __ffs(lanes) - 1;
+            lanes &= lanes - 1;
+            const int t = pass * NC + 32 * lane + L;          // lane s handles slot s of flagged lane L
+            double cs = 0.0;
+            if (lane < SLOTS && t < T) {
+              const int sj = cand_slot(s_pref, s_start, t);
+              if (sj != i && !(EXCL_MOL && __float_as_int(a.P[sj].w) == moli))
+                cs = exact_pair(a.idx, a.ctr, a.vec, n, a.g.box, a.g.rc2, i, sj);
+            }
+            add += warp_sum(cs);
+            addc += __reduce_add_sync(MOUSE_FULL_MASK, cs != 0.0 ? 1 : 0);
+            if (lane == 0) atomicAdd((unsigned long long *)&a.counters[1], 1ULL);
+          }
+        }
+        if (lane == 0 && (add != 0.0 || addc != 0)) {
+          const int o = a.idx[i];
+          a.out_sum[o] += add;
+          a.out_cnt[o] += addc;
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------ exact all-FP64 sweep
@@ -492,45 +574,41 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int SLOTS, int K, bool EXCL, bool LISTS>
+int mouse_fast_variant = 1;  // tuning / debug knob (2 = skip the fixup kernel)
+
+template <int SLOTS, bool EXCL, bool LISTS>
 static void launch_fast_one(const SweepArgs &a, cudaStream_t st) {
-  const size_t smem = (size_t)K * SLOTS * 32 * (3 * sizeof(double) + sizeof(int));
+  const size_t smem = (size_t)SLOTS * 32 * (3 * sizeof(double) + sizeof(int));
   static bool configured = false;
   static int blocks_per_sm = 1;
   if (!configured) {
-    cudaFuncSetAttribute(p2_sweep_fast_kernel<SLOTS, K, EXCL, LISTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(p2_sweep_fast_kernel<SLOTS, EXCL, LISTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, p2_sweep_fast_kernel<SLOTS, K, EXCL, LISTS>, K * 32,
-                                                  smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, p2_sweep_fast_kernel<SLOTS, EXCL, LISTS>, 32, smem);
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     configured = true;
   }
-  // persistent-style grid: a few waves of resident CTAs, each striding over home cells
-  int blocks = num_sms() * blocks_per_sm * 4;
-  if (blocks > a.g.ncell) blocks = a.g.ncell;
-  p2_sweep_fast_kernel<SLOTS, K, EXCL, LISTS><<<blocks, K * 32, smem, st>>>(a);
+  // persistent-style grid: a few waves of resident warps, each striding over runs of home cells
+  const int nruns = (a.g.ncell + FAST_RUN - 1) / FAST_RUN;
+  int blocks = num_sms() * blocks_per_sm;
+  if (blocks > nruns) blocks = nruns;
+  p2_sweep_fast_kernel<SLOTS, EXCL, LISTS><<<blocks, 32, smem, st>>>(a);
+  if (!LISTS && mouse_fast_variant != 2) {   // variant 2 (debug): leave the dropped contributions out
+    int fb = num_sms() * 32;
+    if (fb > a.g.ncell) fb = a.g.ncell;
+    p2_fixup_kernel<SLOTS, EXCL><<<fb, 32, 0, st>>>(a);
+  }
 }
 
-int mouse_fast_variant = 1;  // K = warps per home cell (1, 2 or 4); 1 measured fastest on B200
 
-// total candidate slots per lane over the CTA = SLOTS * K
-template <int TOTAL>
+template <int SLOTS>
 static void launch_fast(const SweepArgs &a, bool excl_mol, bool lists, cudaStream_t st) {
   if (lists) {
-    if (excl_mol) launch_fast_one<TOTAL, 1, true, true>(a, st);
-    else launch_fast_one<TOTAL, 1, false, true>(a, st);
-    return;
-  }
-  const int k = mouse_fast_variant;
-  if (k >= 4) {
-    if (excl_mol) launch_fast_one<TOTAL / 4, 4, true, false>(a, st);
-    else launch_fast_one<TOTAL / 4, 4, false, false>(a, st);
-  } else if (k >= 2) {
-    if (excl_mol) launch_fast_one<TOTAL / 2, 2, true, false>(a, st);
-    else launch_fast_one<TOTAL / 2, 2, false, false>(a, st);
+    if (excl_mol) launch_fast_one<SLOTS, true, true>(a, st);
+    else launch_fast_one<SLOTS, false, true>(a, st);
   } else {
-    if (excl_mol) launch_fast_one<TOTAL, 1, true, false>(a, st);
-    else launch_fast_one<TOTAL, 1, false, false>(a, st);
+    if (excl_mol) launch_fast_one<SLOTS, true, false>(a, st);
+    else launch_fast_one<SLOTS, false, false>(a, st);
   }
 }
 
@@ -555,6 +633,8 @@ int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const
   a.counters = w.counters;
   a.row_ptr = row_ptr;
   a.nbr_idx = nbr_idx;
+  a.fix_list = w.cell_count;           // cell_count is free once cell_start exists
+  a.redo_mask = (unsigned *)w.p_tmp;   // p_tmp (16 B per item) is free after the cell build: 4 x u32 per item
   a.same_molecule = (flags & MOUSE_SAME_MOLECULE) ? 1 : 0;
   a.no_cutoff = (flags & MOUSE_NO_CUTOFF) ? 1 : 0;
   const bool lists = nbr_idx != nullptr;
@@ -563,11 +643,14 @@ int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const
     MOUSE_CUDA_CHECK(cudaMemsetAsync(out_sum, 0, sizeof(double) * (size_t)n, st));
   }
   MOUSE_CUDA_CHECK(cudaMemsetAsync(out_cnt, 0, sizeof(int32_t) * (size_t)n, st));
+  // counters[1] = exact re-decisions (diagnostic), counters[3] = length of the fixup list: per sweep
+  // counters[2] = run ticket of the persistent fast sweep (the reduce kernel resets it before using it)
+  MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters + 1, 0, 3 * sizeof(int64_t), st));
   const bool fast = grid->fast && !(flags & (MOUSE_FORCE_EXACT | MOUSE_NO_CUTOFF));
   if (fast) {
     // SLOTS*32 registers-resident candidates per pass: size for mean + ~3 sigma of 27 cells
     double mean = 27.0 * (double)n / (double)grid->ncell;
-    int need = (int)((mean + 1.0 * sqrt(mean) + 31.0) / 32.0);
+    int need = (int)((1.15 * mean + 2.0 * sqrt(mean) + 31.0) / 32.0);
     int slots = need <= 4 ? 4 : need <= 8 ? 8 : need <= 12 ? 12 : 16;
     (void)need;
     if (mouse_fast_slots_override) slots = mouse_fast_slots_override;

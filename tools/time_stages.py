@@ -62,7 +62,7 @@ def main():
         med, mn = timeit(fn)
         print("%-12s median %.3f ms  min %.3f ms" % (name, med, mn))
     pairs = int(tot.cpu()[2])
-    for R in (1, 2, 4):  # K = warps per home cell
+    for R in (1,):
         L.mouse_set_tuning(b"fast_variant", R)
         for slots in (12, 16):
             L.mouse_set_tuning(b"fast_slots", slots)
@@ -71,7 +71,7 @@ def main():
     L.mouse_set_tuning(b"fast_slots", 0)
     L.mouse_set_tuning(b"fast_variant", 1)
     if os.environ.get("MOUSE_TIMERS"):
-        for R, slots in ((1, 12), (2, 12), (1, 16), (2, 16)):
+        for R, slots in ((1, 12), (1, 16)):
             L.mouse_set_tuning(b"fast_variant", R); L.mouse_set_tuning(b"fast_slots", slots)
             L.mouse_cell_build(p(vec), p(ctr), p(mol), None, None, n, C.byref(grid), p(ws), ws.numel(), st)
             stages["p2_sweep"]()
