@@ -146,11 +146,17 @@ __global__ void __launch_bounds__(32, (FAST_TARGET_WARPS > 32 ? 32 : FAST_TARGET
   __shared__ float4 s_home[32];          // the chunk's reference bonds: cell-local xyz + molecule code
   __shared__ double s_hu[3][32];         //                             FP64 unit vectors
   const int lane = threadIdx.x;
+  static_assert(SLOTS % 4 == 0, "slots come in groups of 4");
   constexpr int NC = SLOTS * 32;         // candidates per pass
-  constexpr int GROUPS = (SLOTS + 3) / 4;
+  constexpr int NCZ = NC + 32;           // + one all-zero row for exhausted lanes
+  constexpr int GROUPS = SLOTS / 4;
   constexpr int BU = FAST_BU;
   double *su = reinterpret_cast<double *>(smem_raw) + lane;      // [3][NC], lane column
-  int *smol = reinterpret_cast<int *>(smem_raw + sizeof(double) * 3 * NC) + lane;
+  int *smol = reinterpret_cast<int *>(smem_raw + sizeof(double) * 3 * NCZ) + lane;   // [NCZ]
+  su[NC] = 0.0;
+  su[NCZ + NC] = 0.0;
+  su[2 * NCZ + NC] = 0.0;
+  smol[NC] = 0;
   const float4 *__restrict__ P = a.P;
   const double4 *__restrict__ U = a.U;
   const int32_t *__restrict__ cell_start = a.cell_start;
@@ -187,14 +193,13 @@ __global__ void __launch_bounds__(32, (FAST_TARGET_WARPS > 32 ? 32 : FAST_TARGET
 
       // (candidate passes beyond FAST_MAX_PASSES are left entirely to p2_fixup_kernel)
       for (int base = 0, pass = 0; base < T && (LISTS || pass < FAST_MAX_PASSES); base += NC, ++pass) {
-        float xr[SLOTS], yr[SLOTS], zr[SLOTS];
+        // candidate coordinates as FP32 pairs (slots 2p, 2p+1): phase A runs on packed f32x2 instructions
+        float2 xr2[SLOTS / 2], yr2[SLOTS / 2], zr2[SLOTS / 2];
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < SLOTS; ++c) {
           const int t = base + 32 * c + lane;
-          xr[c] = 1e30f;
-          yr[c] = 0.f;
-          zr[c] = 0.f;
+          float px = 1e30f, py = 0.f, pz = 0.f;
           if (t < T) {
             int k = 0;  // largest k < 27 with pref[k] <= t
 #pragma unroll
@@ -205,18 +210,24 @@ __global__ void __launch_bounds__(32, (FAST_TARGET_WARPS > 32 ? 32 : FAST_TARGET
             const int j = s_start[k] + (t - s_pref[k]);
             const float4 p = __ldg(P + j);
             const double4 u = U[j];
-            xr[c] = p.x + s_off[0][k];
-            yr[c] = p.y + s_off[1][k];
-            zr[c] = p.z + s_off[2][k];
+            px = p.x + s_off[0][k];
+            py = p.y + s_off[1][k];
+            pz = p.z + s_off[2][k];
             su[c * 32] = u.x;
-            su[NC + c * 32] = u.y;
-            su[2 * NC + c * 32] = u.z;
+            su[NCZ + c * 32] = u.y;
+            su[2 * NCZ + c * 32] = u.z;
             if (EXCL_MOL) smol[c * 32] = __float_as_int(p.w);
-          } else {   // padded slot: finite data for the branch-free walk
-            su[c * 32] = 0.0;
-            su[NC + c * 32] = 0.0;
-            su[2 * NC + c * 32] = 0.0;
-            if (EXCL_MOL) smol[c * 32] = 0;
+          } else if (EXCL_MOL) {
+            smol[c * 32] = 0;
+          }
+          if (c & 1) {
+            xr2[c >> 1].y = px;
+            yr2[c >> 1].y = py;
+            zr2[c >> 1].y = pz;
+          } else {
+            xr2[c >> 1].x = px;
+            yr2[c >> 1].x = py;
+            zr2[c >> 1].x = pz;
           }
         }
         const int nslots = min(SLOTS, (T - base + 31) >> 5);
@@ -254,15 +265,18 @@ __global__ void __launch_bounds__(32, (FAST_TARGET_WARPS > 32 ? 32 : FAST_TARGET
             // ---- A: FP32 filter; slot c ends up in bit c (groups are walked from the last slot down)
             unsigned mask = 0;
             float band = 1e30f;
+            const float2 npx = make_float2(-pi.x, -pi.x), npy = make_float2(-pi.y, -pi.y), npz = make_float2(-pi.z, -pi.z);
+            const float2 nrc = make_float2(-rc2_c, -rc2_c);
 #pragma unroll
             for (int g = GROUPS - 1; g >= 0; --g) {
               if (g < ngroups) {
 #pragma unroll
-                for (int c = min(4 * g + 3, SLOTS - 1); c >= 4 * g; --c) {
-                  const float dx = xr[c] - pi.x, dy = yr[c] - pi.y, dz = zr[c] - pi.z;
-                  const float t = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) - rc2_c;   // < 0: inside
-                  mask = __funnelshift_l(__float_as_uint(t), mask, 1);
-                  band = fminf(band, fabsf(t));
+                for (int pp = 2 * g + 1; pp >= 2 * g; --pp) {
+                  const float2 dx = __fadd2_rn(xr2[pp], npx), dy = __fadd2_rn(yr2[pp], npy), dz = __fadd2_rn(zr2[pp], npz);
+                  const float2 t = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), nrc);  // < 0: inside
+                  mask = __funnelshift_l(__float_as_uint(t.y), mask, 1);   // slot 2pp+1
+                  mask = __funnelshift_l(__float_as_uint(t.x), mask, 1);   // slot 2pp
+                  band = fminf(band, fminf(fabsf(t.x), fabsf(t.y)));
                 }
               }
             }
@@ -283,22 +297,24 @@ __global__ void __launch_bounds__(32, (FAST_TARGET_WARPS > 32 ? 32 : FAST_TARGET
               for (int u = 0; u < BU; ++u) {
                 // highest hit bit first; an exhausted lane (m == 0) clamps to the last slot (finite data,
                 // contributes d * 0): no branch, one bit scan
+                // highest hit bit first; an exhausted lane (m == 0) is sent to the all-zero row SLOTS of the
+                // table (d == 0 exactly): no branch, no select, one bit scan
                 const bool act = m != 0;
-                const int c = (int)min((unsigned)(31 - __clz((int)m)), (unsigned)(SLOTS - 1));
+                const int c = (int)min((unsigned)(31 - __clz((int)m)), (unsigned)SLOTS);
                 m &= ~(1u << c);
                 const double *q = su + c * 32;
-                const double d = fma(uix, q[0], fma(uiy, q[NC], uiz * q[2 * NC]));
+                const double d = fma(uix, q[0], fma(uiy, q[NCZ], uiz * q[2 * NCZ]));
                 bool use = act;
+                double w = d;
                 if (EXCL_MOL) {
                   const bool same = smol[c * 32] == moli;
                   mask &= ~((act && same) ? (1u << c) : 0u);
                   use = act && !same;
+                  w = same ? 0.0 : d;
                 }
-                const double w = use ? d : 0.0;
                 acc2[u] = fma(d, w, acc2[u]);
                 // smallest |d| (as its high word) over the used hits: |d| < 1e-9 must be decided exactly (:113)
-                const unsigned h = use ? ((unsigned)__double2hiint(d) & 0x7fffffffu) : 0xffffffffu;
-                nearz = min(nearz, h);
+                if (use) nearz = min(nearz, (unsigned)__double2hiint(d) & 0x7fffffffu);
               }
             }
 #pragma unroll
@@ -578,7 +594,7 @@ int mouse_fast_variant = 1;  // tuning / debug knob (2 = skip the fixup kernel)
 
 template <int SLOTS, bool EXCL, bool LISTS>
 static void launch_fast_one(const SweepArgs &a, cudaStream_t st) {
-  const size_t smem = (size_t)SLOTS * 32 * (3 * sizeof(double) + sizeof(int));
+  const size_t smem = (size_t)(SLOTS + 1) * 32 * (3 * sizeof(double) + sizeof(int));
   static bool configured = false;
   static int blocks_per_sm = 1;
   if (!configured) {
