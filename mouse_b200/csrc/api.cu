@@ -90,10 +90,13 @@ int mouse_grid_plan(const double *box, double rcut, double rc2, int64_t n_items,
   grid->ncell = nax[0] * nax[1] * nax[2];
   grid->rcut = rcut;
   grid->rc2 = rc2;
-  // FP32 error budget of the fast sweep (DESIGN.md "guard band"): relative error of d2 at the cutoff
-  // <= 1.45e-6 * (cell_w / rcut) + 1.8e-7; keep a 16x margin, never below 2^-14.
-  double guard = 16.0 * (1.5e-6 * ratio + 2.0e-7);
-  if (guard < 6.103515625e-05) guard = 6.103515625e-05;
+  // FP32 error budget of the fast sweep (DESIGN.md "guard band"): coordinates are stored as FP32 of
+  // (wrapped - L/2), one rounded periodic shift, one subtraction: |delta dx| <= 2.5 * 2^-24 * L, so the
+  // relative error of d2 at the cutoff is <= 5.2e-7 * (Lmax / rcut) + 1.8e-7; keep a 4x margin, never below 2^-15.
+  (void)ratio;
+  double lmax = box[0] > box[1] ? (box[0] > box[2] ? box[0] : box[2]) : (box[1] > box[2] ? box[1] : box[2]);
+  double guard = rcut > 0.0 ? 4.0 * (5.2e-7 * (lmax / rcut) + 2.0e-7) : 1.0;
+  if (guard < 3.0517578125e-05) guard = 3.0517578125e-05;
   if (guard > 1.0e-2) fast = 0;
   grid->guard = (float)guard;
   grid->fast = fast;

@@ -48,13 +48,13 @@ __global__ void __launch_bounds__(256) bond_build_kernel(const double *__restric
 
 // Wrapped copy of a coordinate into [0, L) and its cell index / in-cell offset.  The reference
 // never wraps midpoints (lammpack_types.py:590-591); this copy is used for binning only.
-__device__ __forceinline__ void cell_axis(double c, double L, double cw, int nc, int &k, double &xi) {
+__device__ __forceinline__ void cell_axis(double c, double L, double cw, int nc, int &k, double &xw) {
   double x = c - L * floor(c / L);
   if (x >= L) x -= L;
   if (!(x >= 0.0)) x = 0.0;
   k = (int)(x / cw);
   if (k >= nc) k = nc - 1;
-  xi = x - (double)k * cw;
+  xw = x;
 }
 
 // One thread per item (bond midpoint or atom).  MODE 0: P2 (items = bonds, payload needs vec);
@@ -225,10 +225,11 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(const double *__restr
   cell_axis(cx, g.box[0], g.cw[0], g.nc[0], k, xi);
   cell_axis(cy, g.box[1], g.cw[1], g.nc[1], k, yi);
   cell_axis(cz, g.box[2], g.cw[2], g.nc[2], k, zi);
+  // FP32 copy of the wrapped coordinate, centred on the box (|x| <= L/2 keeps one more mantissa bit)
   float4 p;
-  p.x = (float)xi;
-  p.y = (float)yi;
-  p.z = (float)zi;
+  p.x = (float)(xi - 0.5 * g.box[0]);
+  p.y = (float)(yi - 0.5 * g.box[1]);
+  p.z = (float)(zi - 0.5 * g.box[2]);
   p.w = __int_as_float(code ? code[b] : 0);
   double4 u;
   if (MODE == 0) {
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, const int32_
                                                          double4 *__restrict__ u_sorted,
                                                          int32_t *__restrict__ idx_sorted,
                                                          int32_t *__restrict__ cell_sorted,
-                                                         uint8_t *__restrict__ flag_sorted) {
+                                                         uint8_t *__restrict__ flag_sorted, int pack_index) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < ncell; c += warps) {
@@ -272,7 +273,9 @@ __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, const int32_
       if (lane < nc) {
         int d = s + rank;
         p_sorted[d] = p_tmp[s + lane];
-        u_sorted[d] = u_tmp[s + lane];
+        double4 u = u_tmp[s + lane];
+        if (pack_index) u.w = __hiloint2double(0, d);   // the sweep's candidate registers carry their own slot
+        u_sorted[d] = u;
         idx_sorted[d] = mine;
         cell_sorted[d] = c;
         flag_sorted[d] = (uint8_t)((unsigned)raw >> 31);
@@ -285,7 +288,9 @@ __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, const int32_
         for (int k = 0; k < nc; ++k) rank += (idx_tmp[s + k] & 0x7fffffff) < mine;
         int d = s + rank;
         p_sorted[d] = p_tmp[s + m];
-        u_sorted[d] = u_tmp[s + m];
+        double4 u = u_tmp[s + m];
+        if (pack_index) u.w = __hiloint2double(0, d);
+        u_sorted[d] = u;
         idx_sorted[d] = mine;
         cell_sorted[d] = c;
         flag_sorted[d] = (uint8_t)((unsigned)raw >> 31);
@@ -341,7 +346,7 @@ int mouse_launch_cell_build(int mode, const double *xyz, const double *vec, cons
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
     cell_canon_kernel<<<blocks, 256, 0, st>>>(grid->ncell, w.cell_start, w.p_tmp, w.u_tmp, w.idx_tmp, w.p_sorted,
-                                              w.u_sorted, w.idx_sorted, w.cell_sorted, w.flag_sorted);
+                                              w.u_sorted, w.idx_sorted, w.cell_sorted, w.flag_sorted, mode == 0);
     MOUSE_LAUNCH_CHECK("cell_canon_kernel");
   }
   return MOUSE_OK;

@@ -41,14 +41,17 @@ struct Workspace {
   int32_t *cell_of;      // [n] cell id or -1 (not in the list)
   int32_t *rank_of;      // [n] arrival rank inside the cell (atomic order, canonicalised later)
   // per item, cell-sorted (tmp = arrival order, final = ascending original index inside a cell)
-  float4 *p_tmp;         // [n] cell-local x,y,z (FP32) + molecule/type code bits
-  double4 *u_tmp;        // [n] unit bond vector (FP64) + |b|^2   (P2)  /  absolute position (RDF)
+  float4 *p_tmp;         // [n] FP32 (wrapped coordinate - L/2) x,y,z + molecule/type code bits
+  double4 *u_tmp;        // [n] unit bond vector (FP64), .w = sorted slot index bits (P2)  /  absolute position + molecule code (RDF)
   int32_t *idx_tmp;      // [n] original index
   float4 *p_sorted;
   double4 *u_sorted;
   int32_t *idx_sorted;
   int32_t *cell_sorted;  // [n] cell id of each sorted slot
   uint8_t *flag_sorted;  // [n] bit0 = acts as reference
+  // half-shell sweep accumulators per sorted slot (adjacent: zeroed with one memset)
+  long long *acc_fix;    // [n] sum of cos^2, 2^-47 fixed point (integer atomics: exact, order independent)
+  int32_t *acc_cnt;      // [n] counted neighbours
   // scalars
   int64_t *counters;     // [8]: 0 = zero-length bonds in the neighbour set, 1 = band re-checks,
                          //      2 = reduce ticket, 3.. scratch
@@ -87,6 +90,8 @@ static inline Workspace mouse_carve(void *ws, int64_t n, int32_t ncell) {
   CARVE(idx_sorted, int32_t, nn)
   CARVE(cell_sorted, int32_t, nn)
   CARVE(flag_sorted, uint8_t, nn)
+  CARVE(acc_fix, long long, nn)
+  CARVE(acc_cnt, int32_t, nn)
   CARVE(counters, int64_t, 8)
   CARVE(partials, double, 3 * MOUSE_REDUCE_BLOCKS)
   CARVE(edges, double, MOUSE_MAX_BINS + 1)
@@ -103,6 +108,7 @@ struct GridDev {
   int nc[3];
   int ncell;
   float cwf[3];
+  float boxf[3], inv_boxf[3];
   float rc2_lo, rc2_hi;  // FP32 guard band: d2 < lo sure hit, d2 > hi sure miss
 };
 
@@ -113,6 +119,8 @@ static inline GridDev mouse_grid_dev(const mouse_grid_t *g) {
     d.cw[a] = g->cell_w[a];
     d.nc[a] = g->ncell_axis[a];
     d.cwf[a] = (float)g->cell_w[a];
+    d.boxf[a] = (float)g->box[a];
+    d.inv_boxf[a] = (float)(1.0 / g->box[a]);
   }
   d.rc2 = g->rc2;
   d.ncell = g->ncell;

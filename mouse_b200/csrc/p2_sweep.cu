@@ -1,44 +1,59 @@
 // K3: the pair sweep.  Replaces calculateAveCosSqForReference (ordering_functions.py:91-119)
 // for all reference bonds of a frame at once.
 //
-// Two kernels:
-//  * p2_sweep_fast_kernel - one warp per home cell.  The candidates of the 27 neighbour cells
-//    are concatenated and held in REGISTERS (SLOTS x 32 lanes, cell-local FP32 coordinates
-//    pre-shifted by the periodic cell offset), the home cell's reference bonds are looped
-//    warp-uniformly, every lane tests its candidates with 3 FADD + FMUL + 2 FFMA + compare.
-//    Sure hits (d2 < rc2*(1-g)) go straight to the FP64 cos^2; candidates inside the FP32
-//    guard band are re-decided by the reference's exact FP64 expression (mouse_rsq_exact).
-//    cos^2 = (u_i . u_j)^2 on FP64 unit vectors; |u_i . u_j| < 1e-9 falls back to the exact
-//    un-fused raw dot so that the reference's "cos^2 == 0 is masked" rule (:113) is bit-exact.
-//    Per-reference sums are reduced with warp shuffles in a fixed order (deterministic).
+//  * p2_sweep_half_kernel - the fast path.  Half shell (Newton's third law): every unordered pair of
+//    bonds is decided ONCE - home cell against itself (j > i) and against its 13 "forward" neighbour
+//    cells - and its cos^2 is added to both partners.  One warp per home cell, persistent warps with a
+//    ticket counter.  The candidates of the 14 cells are up to 10 contiguous ranges of the cell-sorted
+//    arrays: they are fetched with 1-D TMA bulk copies (cp.async.bulk + mbarrier) into a shared-memory
+//    landing zone, moved into REGISTERS (lane t % 32, slot t / 32: FP32 wrapped coordinates as packed
+//    pairs, FP64 unit vectors) and the landing zone is immediately re-armed with the NEXT home cell's
+//    copies, which then overlap the arithmetic.  Per reference bond (warp-uniform loop, broadcast LDS):
+//    packed f32x2 distance test against the guard band, dense FP64 cos^2 = (u_i . u_j)^2 for every
+//    slot, predicated accumulation into the reference's and the candidate's registers.  Candidates
+//    inside the FP32 guard band around rc^2, and sure hits with |u_i . u_j| < 1e-9 (the reference masks
+//    cos^2 == 0, :113), are NOT decided here: they are appended to a pair list and decided with the
+//    reference's exact un-fused FP64 expressions by p2_fixup_kernel.  Sums are merged across home cells
+//    as 2^-47 fixed point with integer atomics: exact, order independent -> run-to-run bit-identical.
 //  * p2_sweep_exact_kernel - one thread per reference, all FP64, literally the reference's
 //    expression per candidate.  Valid for ANY grid (fewer than 3 cells on an axis, rcut < 0,
-//    rmax == 0 -> half diagonal); also the on-device cross-check of the fast kernel.
+//    rmax == 0 -> half diagonal); it also extracts the pair lists and is the automatic fallback when
+//    the pair list of the fast path overflows.
 #include "common.cuh"
 
 struct SweepArgs {
   GridDev g;
-  const float4 *P;
-  const double4 *U;
+  const float4 *P;         // sorted: FP32 (wrapped midpoint - L/2), molecule code bits in .w
+  const double4 *U;        // sorted: FP64 unit bond vector, .w = bit pattern of the sorted slot index
   const int32_t *idx;
   const int32_t *cell_start;
   const int32_t *cell_sorted;
   const uint8_t *flag;
-  const double *vec;  // SoA [3][n], original order
+  const double *vec;       // SoA [3][n], original order
   const double *ctr;
   int n;
   double *out_sum;
   int32_t *out_cnt;
-  int64_t *counters;
+  int64_t *counters;       // 0 zero-length bonds, 1 exact re-decisions (diagnostic), 2 home-cell ticket,
+                           // 3 length of the pair list, 4 pair list overflowed
   const int64_t *row_ptr;  // lists only
   int32_t *nbr_idx;
-  int32_t *fix_list;       // home cells queued for p2_fixup_kernel (length in counters[3])
-  unsigned *redo_mask;     // [FAST_MAX_PASSES][n] per sorted slot: lanes to re-decide exactly (fast sweep -> fixup)
+  long long *acc_fix;      // [n] per sorted slot: sum of cos^2 as 2^-47 fixed point
+  int32_t *acc_cnt;        // [n] per sorted slot: counted neighbours
+  int2 *fix_list;          // pairs of sorted slots left to p2_fixup_kernel: x = i | kind << 31, y = j
+  long long fix_cap;
   int same_molecule;
   int no_cutoff;
+  int only_if_overflow;    // exact kernel: run only when the pair list overflowed
 };
 
-// ------------------------------------------------------------------ rare exact path (fast kernel)
+#define C_NZERO 0
+#define C_NFIX_DONE 1
+#define C_TICKET 2
+#define C_NFIX 3
+#define C_OVERFLOW 4
+
+// ------------------------------------------------------------------ rare exact path
 // The reference's decision for ONE pair of sorted slots (si = reference, sj = candidate): returns
 // cos^2 exactly as ordering_functions.py:95-113 evaluates it, or 0.0 when the pair is not counted
 // (out of range, or cos^2 == 0 which the reference masks).
@@ -56,431 +71,408 @@ __device__ __forceinline__ double exact_pair(const int32_t *__restrict__ idx, co
   return __ddiv_rn(__ddiv_rn(__dmul_rn(dot, dot), nr), nj);
 }
 
-// candidate t of the concatenated 27-cell list -> sorted slot (largest k < 27 with pref[k] <= t)
-__device__ __forceinline__ int cand_slot(const int *pref, const int *start, int t) {
-  int k = 0;
-#pragma unroll
-  for (int step = 16; step > 0; step >>= 1) {
-    const int k2 = k + step;
-    if (k2 < 27 && pref[k2] <= t) k = k2;
-  }
-  return start[k] + (t - pref[k]);
+// ------------------------------------------------------------------ PTX: mbarrier + 1-D TMA bulk copy
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MB_DONE;\n"
+      "bra MB_WAIT;\n"
+      "MB_DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA unit), completion counted in bytes on `bar`; 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ------------------------------------------------------------------ half-shell fast sweep
+#define HS_MAXHOME 64      // home cells with more bonds are decided pair by pair by p2_fixup_kernel
+#define HS_MAXPASS 8       // ... and home cells with more than HS_MAXPASS * SLOTS * 32 candidates
+#ifndef HS_WARPS
+#define HS_WARPS 12        // resident warps (= CTAs) per SM the register allocation is sized for
+#endif
+#define HS_FIX_SCALE 140737488355328.0     // 2^47
+#define HS_FIX_INV 7.105427357601002e-15   // 2^-47
+#define HS_NEARZ 1e-9                      // |u_i . u_j| below this is decided exactly (:113)
+#define HS_NEARZ_HI 0x3e112e0b             // high word of 1e-9
+#define HS_PAD 1.0e18f                     // coordinate of an empty slot
+
+struct HsItem {
+  int home, hs, nhome, T;   // home cell, its first sorted slot, its bonds, candidates of the 14 cells
+  int rsrc, rlen, rt;       // lane L < 10: range L of the candidate concatenation (first slot, length, offset t)
+  float hx, hy, hz;         // home cell centre (frame of the stored FP32 coordinates)
+  int boundary;             // some neighbour cell is a periodic image
+};
+
+__device__ __forceinline__ void fix_append(int64_t *counters, int2 *fix_list, long long fix_cap, int si, int sj,
+                                           int kind) {
+  const unsigned long long pos = atomicAdd((unsigned long long *)&counters[C_NFIX], 1ULL);
+  if (pos < (unsigned long long)fix_cap) fix_list[pos] = make_int2(si | (kind << 31), sj);
+  else counters[C_OVERFLOW] = 1;   // the exact sweep recomputes the whole frame
 }
 
-#define FAST_MAX_PASSES 4   // redo masks are kept for this many candidate passes per home cell
-#ifndef FAST_TARGET_WARPS
-#define FAST_TARGET_WARPS 16   // resident warps per SM the register allocation is sized for
-#endif
-#ifndef FAST_BU
-#define FAST_BU 2             // hits per phase-B trip (independent FP64 chains per lane)
-#endif
-#ifndef FAST_RUN
-#define FAST_RUN 1             // consecutive home cells per CTA visit (L1 reuse of shared neighbour cells)
-#endif
+// every pair of an oversized home cell goes to the pair list
+__device__ __noinline__ void hs_oversize(const float4 *__restrict__ P, int64_t *counters, int2 *fix_list,
+                                         long long fix_cap, int same_molecule, int lane, int hs, int nhome, int rsrc,
+                                         int rlen, int rt0) {
+  for (int r = 0; r < 10; ++r) {
+    const int src = __shfl_sync(MOUSE_FULL_MASK, rsrc, r), len = __shfl_sync(MOUSE_FULL_MASK, rlen, r);
+    const int rt = __shfl_sync(MOUSE_FULL_MASK, rt0, r);
+    for (int k = lane; k < len; k += 32) {
+      const int sj = src + k, tj = rt + k;
+      const int molj = __float_as_int(P[sj].w);
+      for (int il = 0; il < nhome; ++il) {
+        if (tj <= il) continue;                                   // home-home pairs once (j > i)
+        if (!same_molecule && __float_as_int(P[hs + il].w) == molj) continue;
+        fix_append(counters, fix_list, fix_cap, hs + il, sj, 0);
+      }
+    }
+  }
+}
 
-// neighbour table of a home cell: per neighbour k (lane k < 27) first sorted slot, exclusive prefix of the
-// counts, periodic cell shift.  Returns T (all lanes) and the home cell's own prefix.
-__device__ __forceinline__ int neighbour_table(const SweepArgs &a, int home, int lane, int *s_start, int *s_pref,
-                                               float (*s_off)[32], int &home_pref) {
+// next non-empty home cell from the ticket counter + its range table; false when the grid is exhausted
+__device__ __forceinline__ bool hs_fetch_item(const SweepArgs &a, int lane, int nc_pass, HsItem &it) {
   const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
-  const int cx = home % nx, cy = (home / nx) % ny, cz = home / (nx * ny);
-  int st = 0, cn = 0;
-  float ox = 0.f, oy = 0.f, oz = 0.f;
-  if (lane < 27) {
-    const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
-    int mx = cx + dx, my = cy + dy, mz = cz + dz;
-    mx += (mx < 0) ? nx : 0;
-    mx -= (mx >= nx) ? nx : 0;
-    my += (my < 0) ? ny : 0;
-    my -= (my >= ny) ? ny : 0;
-    mz += (mz < 0) ? nz : 0;
-    mz -= (mz >= nz) ? nz : 0;
-    const int cid = (mz * ny + my) * nx + mx;
-    st = a.cell_start[cid];
-    cn = a.cell_start[cid + 1] - st;
-    ox = (float)dx * a.g.cwf[0];
-    oy = (float)dy * a.g.cwf[1];
-    oz = (float)dz * a.g.cwf[2];
-  }
-  int incl = cn;
+  for (;;) {
+    int tk = 0;
+    if (lane == 0) tk = (int)atomicAdd((unsigned long long *)&a.counters[C_TICKET], 1ULL);
+    tk = __shfl_sync(MOUSE_FULL_MASK, tk, 0);
+    if (tk >= a.g.ncell) return false;
+    const int hs = a.cell_start[tk], he = a.cell_start[tk + 1];
+    if (hs == he) continue;
+    const int cx = tk % nx, cy = (tk / nx) % ny, cz = tk / (nx * ny);
+    // rows of the forward half shell: (dy,dz) = (0,0) cells x..x+1 (home first), (1,0), (-1,1), (0,1), (1,1) cells
+    // x-1..x+1; a row that crosses the periodic boundary in x splits into two ranges (part 0 / part 1)
+    int src = 0, len = 0;
+    if (lane < 10) {
+      const int row = lane >> 1, part = lane & 1;
+      const int dy = (row == 1 || row == 4) ? 1 : (row == 2 ? -1 : 0);
+      const int dz = row >= 2 ? 1 : 0;
+      int yc = cy + dy, zc = cz + dz;
+      yc += yc < 0 ? ny : 0;
+      yc -= yc >= ny ? ny : 0;
+      zc -= zc >= nz ? nz : 0;
+      const int rb = (zc * ny + yc) * nx;
+      const int xa = row == 0 ? cx : cx - 1, xb = cx + 1;
+      int lo, hi;  // inclusive cell range of this part, empty when lo > hi
+      if (xa < 0) {
+        lo = part ? 0 : nx - 1;
+        hi = part ? xb : nx - 1;
+      } else if (xb >= nx) {
+        lo = part ? 0 : xa;
+        hi = part ? xb - nx : nx - 1;
+      } else {
+        lo = part ? 1 : xa;
+        hi = part ? 0 : xb;
+      }
+      if (lo <= hi) {
+        src = a.cell_start[rb + lo];
+        len = a.cell_start[rb + hi + 1] - src;
+      }
+    }
+    int incl = len;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int y = __shfl_up_sync(MOUSE_FULL_MASK, incl, o);
-    if (lane >= o) incl += y;
+    for (int o = 1; o < 16; o <<= 1) {
+      const int y = __shfl_up_sync(MOUSE_FULL_MASK, incl, o);
+      if (lane >= o) incl += y;
+    }
+    it.home = tk;
+    it.hs = hs;
+    it.nhome = he - hs;
+    it.T = __shfl_sync(MOUSE_FULL_MASK, incl, 15);
+    it.rsrc = src;
+    it.rlen = len;
+    it.rt = incl - len;
+    it.hx = ((float)cx + 0.5f) * a.g.cwf[0] - 0.5f * a.g.boxf[0];
+    it.hy = ((float)cy + 0.5f) * a.g.cwf[1] - 0.5f * a.g.boxf[1];
+    it.hz = ((float)cz + 0.5f) * a.g.cwf[2] - 0.5f * a.g.boxf[2];
+    it.boundary = (cx == 0) | (cx == nx - 1) | (cy == 0) | (cy == ny - 1) | (cz == nz - 1);
+    if (it.nhome > HS_MAXHOME || it.T > HS_MAXPASS * nc_pass) {
+      hs_oversize(a.P, a.counters, a.fix_list, a.fix_cap, a.same_molecule, lane, it.hs, it.nhome, it.rsrc, it.rlen, it.rt);
+      continue;
+    }
+    return true;
   }
-  const int T = __shfl_sync(MOUSE_FULL_MASK, incl, 31);
-  home_pref = __shfl_sync(MOUSE_FULL_MASK, incl - cn, 13);  // neighbour 13 = the home cell itself
-  __syncwarp();
-  s_start[lane] = st;
-  s_pref[lane] = incl - cn;      // lanes >= 27 hold T
-  if (s_off) {
-    s_off[0][lane] = ox;
-    s_off[1][lane] = oy;
-    s_off[2][lane] = oz;
-  }
-  __syncwarp();
-  return T;
 }
 
-// One warp per home cell (CTA = 1 warp; CTAs visit runs of FAST_RUN consecutive home cells).
-//   load  : the candidates of the 27 neighbour cells are concatenated into t = 0..T-1; lane t % 32 keeps
-//           candidate t's cell-local FP32 coordinates (shifted by the periodic cell offset) in REGISTERS
-//           (slot t / 32) and its FP64 unit vector (+ molecule code) in SHARED memory.  The home cell's
-//           reference bonds are staged in shared memory in chunks of 32 (lane l owns reference chunk0 + l).
-//   per reference bond (warp-uniform loop, no global memory traffic, no calls):
-//     A   : every lane tests its candidates in FP32 (3 FADD, FMUL, 2 FFMA, FADD) and shifts the sign of
-//           d2 - rc2 into a hit mask (one funnel shift); min |d2 - rc2| is tracked for the guard band.
-//     B   : lanes walk their hit bits (warp-uniform trip count, branch-free body):
-//           cos^2 = (u_i . u_j)^2 in FP64 from shared memory.
-//     flag: a lane that saw a guard-band candidate or a near-zero dot drops its contribution for this
-//           reference and sets its bit in the reference's redo mask (decided exactly by p2_fixup_kernel).
-//     sum : warp-shuffle reduction in a fixed order; the result stays in the owning lane's registers.
-//   flush : one store per reference (sum, count, redo mask).
-template <int SLOTS, bool EXCL_MOL, bool LISTS>
-__global__ void __launch_bounds__(32, (FAST_TARGET_WARPS > 32 ? 32 : FAST_TARGET_WARPS))
-    p2_sweep_fast_kernel(const SweepArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_start[32];
-  __shared__ int s_pref[32];
-  __shared__ float s_off[3][32];
-  __shared__ float4 s_home[32];          // the chunk's reference bonds: cell-local xyz + molecule code
-  __shared__ double s_hu[3][32];         //                             FP64 unit vectors
+template <int SLOTS, bool EXCL_MOL>
+__global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const SweepArgs a) {
+  constexpr int NC = SLOTS * 32;   // candidates per pass
+  constexpr int NPAIR = SLOTS / 2;
+  static_assert(SLOTS % 2 == 0 && NC >= HS_MAXHOME, "slots come in pairs; the home cell lives in pass 0");
+  __shared__ __align__(128) float4 s_landP[NC];     // TMA landing zone
+  __shared__ __align__(128) double4 s_landU[NC];
+  __shared__ float4 s_homeP[HS_MAXHOME];            // the home cell's bonds: the references of this item
+  __shared__ double s_homeU[3][HS_MAXHOME];
+  __shared__ double s_acc[8][33];                   // per-lane partial sums of 8 references (transposed reduce)
+  __shared__ __align__(8) uint64_t s_bar;
   const int lane = threadIdx.x;
-  static_assert(SLOTS % 4 == 0, "slots come in groups of 4");
-  constexpr int NC = SLOTS * 32;         // candidates per pass
-  constexpr int NCZ = NC + 32;           // + one all-zero row for exhausted lanes
-  constexpr int GROUPS = SLOTS / 4;
-  constexpr int BU = FAST_BU;
-  double *su = reinterpret_cast<double *>(smem_raw) + lane;      // [3][NC], lane column
-  int *smol = reinterpret_cast<int *>(smem_raw + sizeof(double) * 3 * NCZ) + lane;   // [NCZ]
-  su[NC] = 0.0;
-  su[NCZ + NC] = 0.0;
-  su[2 * NCZ + NC] = 0.0;
-  smol[NC] = 0;
-  const float4 *__restrict__ P = a.P;
-  const double4 *__restrict__ U = a.U;
-  const int32_t *__restrict__ cell_start = a.cell_start;
-  // guard band [rc2_lo, rc2_hi] around rc^2: centre / half width in FP32
-  const float rc2_c = 0.5f * (a.g.rc2_lo + a.g.rc2_hi);
+  const float rc2_c = 0.5f * (a.g.rc2_lo + a.g.rc2_hi);             // guard band [c - w, c + w] around rc^2
   const float rc2_w = 0.5f * (a.g.rc2_hi - a.g.rc2_lo) * 1.0001f;
-  // zero-length bonds in the neighbour set turn every mean into NaN and add to every count
-  // (0/0 in ordering_functions.py:112)
-  const long long nzero = LISTS ? 0 : a.counters[0];
-#ifdef MOUSE_PHASE_TIMERS
-  long long tm_load = 0, tm_a = 0, tm_b = 0, tm_e = 0, tm0;
-#define TM_START() tm0 = clock64()
-#define TM_ADD(x) do { long long t1_ = clock64(); x += t1_ - tm0; tm0 = t1_; } while (0)
-#else
-#define TM_START()
-#define TM_ADD(x)
-#endif
+  const float negw = -rc2_w;
+  const float nearz_thr = __int_as_float(HS_NEARZ_HI);
+  const float2 nrc = make_float2(-rc2_c, -rc2_c);
 
-  // persistent warps fetch runs of FAST_RUN consecutive home cells from a global ticket counter
-  // (dynamic load balance; consecutive cells share 18 of their 27 neighbour cells -> L1/L2 reuse)
-  const int nruns = (a.g.ncell + FAST_RUN - 1) / FAST_RUN;
+  if (lane == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  uint32_t phase = 0;
+
+  // arm the landing zone with pass `pass` of item `it`: candidates [pass * NC, min(T, pass * NC + NC))
+  auto issue = [&](const HsItem &it, int pass) {
+    const int w0 = pass * NC, w1 = min(it.T, w0 + NC);
+    fence_proxy_async();     // the generic-proxy reads of the previous contents are done (WAR across proxies)
+    if (lane == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)(w1 - w0) * 48u);
+    __syncwarp();
+    const int a0 = max(it.rt, w0), b0 = min(it.rt + it.rlen, w1);
+    if (b0 > a0) {
+      const int src = it.rsrc + (a0 - it.rt), cnt = b0 - a0, dst = a0 - w0;
+      tma_load_1d(&s_landP[dst], a.P + src, (uint32_t)cnt * 16u, &s_bar);
+      tma_load_1d(&s_landU[dst], a.U + src, (uint32_t)cnt * 32u, &s_bar);
+    }
+  };
+
+  HsItem cur;
+  if (!hs_fetch_item(a, lane, NC, cur)) return;
+  int pass = 0;
+  issue(cur, pass);
+
   for (;;) {
-    int run = 0;
-    if (lane == 0) run = (int)atomicAdd((unsigned long long *)&a.counters[2], 1ULL);
-    run = __shfl_sync(MOUSE_FULL_MASK, run, 0);
-    if (run >= nruns) break;
-    for (int home = run * FAST_RUN; home < min(a.g.ncell, (run + 1) * FAST_RUN); ++home) {
-      const int hs = cell_start[home], he = cell_start[home + 1];
-      if (hs == he) continue;
-      TM_START();
-      int home_pref;
-      const int T = neighbour_table(a, home, lane, s_start, s_pref, s_off, home_pref);
-      unsigned home_any = (!LISTS && T > FAST_MAX_PASSES * NC) ? 1u : 0u;   // needs p2_fixup_kernel?
+    // ---- landing zone -> registers
+    const int w0 = pass * NC;
+    const int nvalid = min(cur.T, w0 + NC) - w0;
+    const int npp = (nvalid + 63) >> 6;             // slot pairs in use
+    float2 xr2[NPAIR], yr2[NPAIR], zr2[NPAIR];
+    double ux[SLOTS], uy[SLOTS], uz[SLOTS];
+    double accj[SLOTS];
+    int cntj[SLOTS], gid[SLOTS], molr[SLOTS];
+    mbar_wait(&s_bar, phase);
+    phase ^= 1u;
+    const float Lx = a.g.boxf[0], Ly = a.g.boxf[1], Lz = a.g.boxf[2];
+#pragma unroll
+    for (int c = 0; c < SLOTS; ++c) {
+      const int tl = 32 * c + lane;
+      const bool valid = tl < nvalid;
+      const float4 p = s_landP[tl];
+      const double4 u = s_landU[tl];
+      float px = p.x, py = p.y, pz = p.z;
+      if (cur.boundary) {     // nearest periodic image to the home cell centre
+        px -= Lx * rintf((px - cur.hx) * a.g.inv_boxf[0]);
+        py -= Ly * rintf((py - cur.hy) * a.g.inv_boxf[1]);
+        pz -= Lz * rintf((pz - cur.hz) * a.g.inv_boxf[2]);
+      }
+      px = valid ? px : HS_PAD;
+      py = valid ? py : HS_PAD;
+      pz = valid ? pz : HS_PAD;
+      ux[c] = valid ? u.x : 1.0;
+      uy[c] = valid ? u.y : 1.0;
+      uz[c] = valid ? u.z : 1.0;
+      gid[c] = valid ? __double2loint(u.w) : -1;
+      molr[c] = __float_as_int(p.w);
+      accj[c] = 0.0;
+      cntj[c] = 0;
+      if (c & 1) {
+        xr2[c >> 1].y = px;
+        yr2[c >> 1].y = py;
+        zr2[c >> 1].y = pz;
+      } else {
+        xr2[c >> 1].x = px;
+        yr2[c >> 1].x = py;
+        zr2[c >> 1].x = pz;
+      }
+      if (c < HS_MAXHOME / 32 && pass == 0 && tl < cur.nhome) {   // the home cell leads the concatenation
+        s_homeP[tl] = make_float4(px, py, pz, p.w);
+        s_homeU[0][tl] = u.x;
+        s_homeU[1][tl] = u.y;
+        s_homeU[2][tl] = u.z;
+      }
+    }
+    __syncwarp();
 
-      // (candidate passes beyond FAST_MAX_PASSES are left entirely to p2_fixup_kernel)
-      for (int base = 0, pass = 0; base < T && (LISTS || pass < FAST_MAX_PASSES); base += NC, ++pass) {
-        // candidate coordinates as FP32 pairs (slots 2p, 2p+1): phase A runs on packed f32x2 instructions
-        float2 xr2[SLOTS / 2], yr2[SLOTS / 2], zr2[SLOTS / 2];
-        __syncwarp();
+    // ---- re-arm the landing zone: next pass of this home cell, or pass 0 of the next one
+    HsItem nxt = cur;
+    int npass = pass + 1;
+    bool have_next = true;
+    if (npass * NC >= cur.T) {
+      npass = 0;
+      have_next = hs_fetch_item(a, lane, NC, nxt);
+    }
+    if (have_next) issue(nxt, npass);
+
+    // ---- the references of the home cell against the register-resident candidates
+    int mycnt = 0;
+    for (int il = 0; il < cur.nhome; ++il) {
+      const float4 pi = s_homeP[il];
+      const double uix = s_homeU[0][il], uiy = s_homeU[1][il], uiz = s_homeU[2][il];
+      const int moli = __float_as_int(pi.w);
+      const float2 npx = make_float2(-pi.x, -pi.x), npy = make_float2(-pi.y, -pi.y), npz = make_float2(-pi.z, -pi.z);
+      // home-home pairs are decided once: candidate t (pass 0: slot 0 holds t = lane, slot 1 t = 32 + lane) > il
+      const bool ps0 = pass != 0 || lane > il;
+      const bool ps1 = pass != 0 || lane + 32 > il;
+      double acci0 = 0.0, acci1 = 0.0;
+      int cnti = 0;
+      float band = 3.0e38f, nearz = 3.0e38f;
+#pragma unroll
+      for (int pp = NPAIR - 1; pp >= 0; --pp) {
+        if (pp < npp) {
+          const float2 dx = __fadd2_rn(xr2[pp], npx), dy = __fadd2_rn(yr2[pp], npy), dz = __fadd2_rn(zr2[pp], npz);
+          const float2 t = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), nrc);   // d2 - rc2
+          band = fminf(band, fminf(fabsf(t.x), fabsf(t.y)));
+          const double d0 = fma(uix, ux[2 * pp], fma(uiy, uy[2 * pp], uiz * uz[2 * pp]));
+          const double d1 = fma(uix, ux[2 * pp + 1], fma(uiy, uy[2 * pp + 1], uiz * uz[2 * pp + 1]));
+          // smallest |d| over ALL slots (as the high word, compared as a float): a false alarm only costs time
+          nearz = fminf(nearz, fminf(fabsf(__int_as_float(__double2hiint(d0))), fabsf(__int_as_float(__double2hiint(d1)))));
+          bool h0 = t.x < negw, h1 = t.y < negw;
+          if (pp == 0) {
+            h0 = h0 && ps0;
+            h1 = h1 && ps1;
+          }
+          if (EXCL_MOL) {
+            h0 = h0 && molr[2 * pp] != moli;
+            h1 = h1 && molr[2 * pp + 1] != moli;
+          }
+          if (h0) {
+            accj[2 * pp] = fma(d0, d0, accj[2 * pp]);
+            cntj[2 * pp] += 1;
+            acci0 = fma(d0, d0, acci0);
+            cnti += 1;
+          }
+          if (h1) {
+            accj[2 * pp + 1] = fma(d1, d1, accj[2 * pp + 1]);
+            cntj[2 * pp + 1] += 1;
+            acci1 = fma(d1, d1, acci1);
+            cnti += 1;
+          }
+        }
+      }
+      // ---- rare: candidates inside the guard band / near-zero dots are handed to p2_fixup_kernel
+      if (band <= rc2_w || nearz <= nearz_thr) {
 #pragma unroll
         for (int c = 0; c < SLOTS; ++c) {
-          const int t = base + 32 * c + lane;
-          float px = 1e30f, py = 0.f, pz = 0.f;
-          if (t < T) {
-            int k = 0;  // largest k < 27 with pref[k] <= t
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-              const int k2 = k + step;
-              if (k2 < 27 && s_pref[k2] <= t) k = k2;
+          if (c < 2 * npp && gid[c] >= 0) {
+            bool ps = c == 0 ? ps0 : (c == 1 ? ps1 : true);
+            if (EXCL_MOL) ps = ps && molr[c] != moli;
+            if (ps) {
+              const float px = (c & 1) ? xr2[c >> 1].y : xr2[c >> 1].x;
+              const float py = (c & 1) ? yr2[c >> 1].y : yr2[c >> 1].x;
+              const float pz = (c & 1) ? zr2[c >> 1].y : zr2[c >> 1].x;
+              const float dx = __fadd_rn(px, -pi.x), dy = __fadd_rn(py, -pi.y), dz = __fadd_rn(pz, -pi.z);
+              const float t = __fadd_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))), -rc2_c);
+              if (fabsf(t) <= rc2_w) {
+                fix_append(a.counters, a.fix_list, a.fix_cap, cur.hs + il, gid[c], 0);          // undecided: nothing was added
+              } else if (t < negw) {
+                const double d = fma(uix, ux[c], fma(uiy, uy[c], uiz * uz[c]));
+                if (fabs(d) < HS_NEARZ) fix_append(a.counters, a.fix_list, a.fix_cap, cur.hs + il, gid[c], 1);   // added as a hit; cos^2 == 0 ?
+              }
             }
-            const int j = s_start[k] + (t - s_pref[k]);
-            const float4 p = __ldg(P + j);
-            const double4 u = U[j];
-            px = p.x + s_off[0][k];
-            py = p.y + s_off[1][k];
-            pz = p.z + s_off[2][k];
-            su[c * 32] = u.x;
-            su[NCZ + c * 32] = u.y;
-            su[2 * NCZ + c * 32] = u.z;
-            if (EXCL_MOL) smol[c * 32] = __float_as_int(p.w);
-          } else if (EXCL_MOL) {
-            smol[c * 32] = 0;
           }
-          if (c & 1) {
-            xr2[c >> 1].y = px;
-            yr2[c >> 1].y = py;
-            zr2[c >> 1].y = pz;
-          } else {
-            xr2[c >> 1].x = px;
-            yr2[c >> 1].x = py;
-            zr2[c >> 1].x = pz;
-          }
-        }
-        const int nslots = min(SLOTS, (T - base + 31) >> 5);
-        const int ngroups = (nslots + 3) >> 2;
-
-        for (int chunk0 = hs; chunk0 < he; chunk0 += 32) {
-          const int nchunk = min(32, he - chunk0);
-          int my_idx = 0;
-          bool my_ref = false;
-          __syncwarp();
-          if (lane < nchunk) {
-            const int ic = chunk0 + lane;
-            my_idx = a.idx[ic];
-            my_ref = (a.flag[ic] & 1) != 0;
-            s_home[lane] = __ldg(P + ic);
-            const double4 u = U[ic];
-            s_hu[0][lane] = u.x;
-            s_hu[1][lane] = u.y;
-            s_hu[2][lane] = u.z;
-          }
-          const unsigned refmask = __ballot_sync(MOUSE_FULL_MASK, my_ref);
-          double racc = 0.0;      // result of reference chunk0 + lane
-          int rcnt = 0;
-          unsigned rredo = 0;     // lanes whose contribution to reference chunk0 + lane must be decided exactly
-          __syncwarp();
-          TM_ADD(tm_load);
-
-          for (int il = 0; il < nchunk; ++il) {
-            if (!((refmask >> il) & 1u)) continue;
-            const float4 pi = s_home[il];
-            const int moli = __float_as_int(pi.w);
-            const double uix = s_hu[0][il], uiy = s_hu[1][il], uiz = s_hu[2][il];
-            // the reference bond is itself a candidate (home cell = neighbour 13): slot / lane of it
-            const int tself = home_pref + (chunk0 + il - hs) - base;
-            // ---- A: FP32 filter; slot c ends up in bit c (groups are walked from the last slot down)
-            unsigned mask = 0;
-            float band = 1e30f;
-            const float2 npx = make_float2(-pi.x, -pi.x), npy = make_float2(-pi.y, -pi.y), npz = make_float2(-pi.z, -pi.z);
-            const float2 nrc = make_float2(-rc2_c, -rc2_c);
-#pragma unroll
-            for (int g = GROUPS - 1; g >= 0; --g) {
-              if (g < ngroups) {
-#pragma unroll
-                for (int pp = 2 * g + 1; pp >= 2 * g; --pp) {
-                  const float2 dx = __fadd2_rn(xr2[pp], npx), dy = __fadd2_rn(yr2[pp], npy), dz = __fadd2_rn(zr2[pp], npz);
-                  const float2 t = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), nrc);  // < 0: inside
-                  mask = __funnelshift_l(__float_as_uint(t.y), mask, 1);   // slot 2pp+1
-                  mask = __funnelshift_l(__float_as_uint(t.x), mask, 1);   // slot 2pp
-                  band = fminf(band, fminf(fabsf(t.x), fabsf(t.y)));
-                }
-              }
-            }
-            if (tself >= 0 && tself < NC && lane == (tself & 31)) mask &= ~(1u << (tself >> 5));
-            TM_ADD(tm_a);
-            // ---- B: FP64 cos^2 of the hits
-            double acc = 0.0;
-            unsigned m = mask;
-            unsigned nearz = 0xffffffffu;
-            const int iters = __reduce_max_sync(MOUSE_FULL_MASK, __popc(mask));
-            // BU hits per trip: BU independent load -> FMA chains per lane (ILP); branch-free bodies,
-            // idle lanes read slot 0 and contribute d * 0
-            double acc2[BU];
-#pragma unroll
-            for (int u = 0; u < BU; ++u) acc2[u] = 0.0;
-            for (int it = 0; it < iters; it += BU) {
-#pragma unroll
-              for (int u = 0; u < BU; ++u) {
-                // highest hit bit first; an exhausted lane (m == 0) clamps to the last slot (finite data,
-                // contributes d * 0): no branch, one bit scan
-                // highest hit bit first; an exhausted lane (m == 0) is sent to the all-zero row SLOTS of the
-                // table (d == 0 exactly): no branch, no select, one bit scan
-                const bool act = m != 0;
-                const int c = (int)min((unsigned)(31 - __clz((int)m)), (unsigned)SLOTS);
-                m &= ~(1u << c);
-                const double *q = su + c * 32;
-                const double d = fma(uix, q[0], fma(uiy, q[NCZ], uiz * q[2 * NCZ]));
-                bool use = act;
-                double w = d;
-                if (EXCL_MOL) {
-                  const bool same = smol[c * 32] == moli;
-                  mask &= ~((act && same) ? (1u << c) : 0u);
-                  use = act && !same;
-                  w = same ? 0.0 : d;
-                }
-                acc2[u] = fma(d, w, acc2[u]);
-                // smallest |d| (as its high word) over the used hits: |d| < 1e-9 must be decided exactly (:113)
-                if (use) nearz = min(nearz, (unsigned)__double2hiint(d) & 0x7fffffffu);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < BU; ++u) acc += acc2[u];
-            bool redo = (band <= rc2_w) || (nearz < 0x3e112e0bu);
-            TM_ADD(tm_b);
-            if (LISTS) {
-              // pair lists are extracted with every decision made in place (not on the timed path)
-              if (redo) {
-                mask = 0;
-                for (int c = 0; c < nslots; ++c) {
-                  const int t = base + 32 * c + lane;
-                  if (t >= T) break;
-                  const int sj = cand_slot(s_pref, s_start, t);
-                  if (sj == chunk0 + il) continue;
-                  if (EXCL_MOL && __float_as_int(P[sj].w) == moli) continue;
-                  if (exact_pair(a.idx, a.ctr, a.vec, (size_t)a.n, a.g.box, a.g.rc2, chunk0 + il, sj) != 0.0)
-                    mask |= 1u << c;
-                }
-              }
-              __syncwarp();
-              int cntl = __popc(mask);
-              const int o = __shfl_sync(MOUSE_FULL_MASK, my_idx, il);
-              int64_t row = a.row_ptr[o] + a.out_cnt[o];  // out_cnt = entries written by earlier passes
-              int incl_c = cntl;
-#pragma unroll
-              for (int off = 1; off < 32; off <<= 1) {
-                int y = __shfl_up_sync(MOUSE_FULL_MASK, incl_c, off);
-                if (lane >= off) incl_c += y;
-              }
-              row += incl_c - cntl;
-              unsigned mm = mask;
-              while (mm) {
-                const int c = __ffs(mm) - 1;
-                mm &= mm - 1;
-                a.nbr_idx[row++] = a.idx[cand_slot(s_pref, s_start, base + 32 * c + lane)];
-              }
-              cntl = __reduce_add_sync(MOUSE_FULL_MASK, cntl);
-              if (lane == 0) a.out_cnt[o] += cntl;
-              __syncwarp();
-              continue;
-            }
-            // ---- flag: flagged lanes drop their contribution; p2_fixup_kernel adds the exact one
-            const unsigned fm = __ballot_sync(MOUSE_FULL_MASK, redo);
-            home_any |= fm;
-            if (redo) {
-              acc = 0.0;
-              mask = 0;
-            }
-            acc = warp_sum(acc);
-            const int cnt = __reduce_add_sync(MOUSE_FULL_MASK, __popc(mask));
-            if (lane == il) {
-              racc = acc;
-              rcnt = cnt;
-              rredo = fm;
-            }
-            TM_ADD(tm_e);
-          }
-          // flush the chunk: one store per reference, no global read unless a second pass is running
-          if (!LISTS && lane < nchunk) {
-            if (my_ref) {
-              if (base == 0) {
-                if (nzero) {
-                  racc = __longlong_as_double(0x7ff8000000000000LL);
-                  rcnt += (int)nzero;
-                }
-                a.out_sum[my_idx] = racc;
-                a.out_cnt[my_idx] = rcnt;
-              } else {
-                a.out_sum[my_idx] += racc;
-                a.out_cnt[my_idx] += rcnt;
-              }
-            }
-            a.redo_mask[(size_t)pass * a.n + chunk0 + lane] = rredo;
-          }
-          TM_ADD(tm_e);
         }
       }
-      // home cells with dropped contributions (or skipped passes) are queued for p2_fixup_kernel
-      if (!LISTS && home_any && lane == 0)
-        a.fix_list[atomicAdd((unsigned long long *)&a.counters[3], 1ULL)] = home;
+      // ---- reference side: per-lane partials -> shared memory, 8 references are reduced together
+      s_acc[il & 7][lane] = acci0 + acci1;
+      const int ctot = __reduce_add_sync(MOUSE_FULL_MASK, cnti);
+      if (lane == (il & 7)) mycnt = ctot;
+      if ((il & 7) == 7 || il == cur.nhome - 1) {
+        __syncwarp();
+        const int row = lane & 7, part = lane >> 3;
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += s_acc[row][part * 8 + k];
+        v += __shfl_xor_sync(MOUSE_FULL_MASK, v, 8);
+        v += __shfl_xor_sync(MOUSE_FULL_MASK, v, 16);
+        const int iref = (il & ~7) + lane;
+        if (lane < 8 && iref <= il && mycnt > 0) {
+          atomicAdd((unsigned long long *)&a.acc_fix[cur.hs + iref], (unsigned long long)__double2ll_rn(v * HS_FIX_SCALE));
+          atomicAdd(&a.acc_cnt[cur.hs + iref], mycnt);
+        }
+        __syncwarp();
+      }
     }
+    // ---- candidate side: one pair of integer atomics per candidate that was hit
+#pragma unroll
+    for (int c = 0; c < SLOTS; ++c) {
+      if (c < 2 * npp && cntj[c] > 0) {
+        atomicAdd((unsigned long long *)&a.acc_fix[gid[c]], (unsigned long long)__double2ll_rn(accj[c] * HS_FIX_SCALE));
+        atomicAdd(&a.acc_cnt[gid[c]], cntj[c]);
+      }
+    }
+    if (!have_next) break;
+    cur = nxt;
+    pass = npass;
   }
-#ifdef MOUSE_PHASE_TIMERS
-  if (lane == 0) {
-    atomicAdd((unsigned long long *)&a.counters[4], (unsigned long long)tm_load);
-    atomicAdd((unsigned long long *)&a.counters[5], (unsigned long long)tm_a);
-    atomicAdd((unsigned long long *)&a.counters[6], (unsigned long long)tm_b);
-    atomicAdd((unsigned long long *)&a.counters[7], (unsigned long long)tm_e);
-  }
-#endif
 }
 
-// Exact re-decision of the contributions the fast sweep dropped: one warp per home cell; for every reference
-// with a non-zero redo mask, every flagged lane's candidates (slots 0..SLOTS-1 of that pass) are evaluated with
-// the reference's FP64 expressions - lane s takes slot s - and added to the reference's sum / count in a fixed
-// order (pass, lane, slot tree), so the result stays deterministic.  Candidate passes beyond FAST_MAX_PASSES
-// (more than FAST_MAX_PASSES * SLOTS * 32 candidates around one cell) are recomputed exactly as a whole.
-template <int SLOTS, bool EXCL_MOL>
-__global__ void __launch_bounds__(32) p2_fixup_kernel(const SweepArgs a) {
-  __shared__ int s_start[32];
-  __shared__ int s_pref[32];
-  const int lane = threadIdx.x;
-  constexpr int NC = SLOTS * 32;
+// Exact decision of the listed pairs (one thread per pair): kind 0 = nothing was added by the fast sweep, add the
+// reference's cos^2 to both partners if the pair is counted; kind 1 = added as a hit with a near-zero dot product,
+// remove it from both counts if the reference's cos^2 is exactly 0.0 (masked, :113).
+__global__ void __launch_bounds__(256) p2_fixup_kernel(const SweepArgs a) {
+  if (((volatile int64_t *)a.counters)[C_OVERFLOW]) return;
+  const long long nfix = ((volatile int64_t *)a.counters)[C_NFIX];
   const size_t n = (size_t)a.n;
-  const int nfix = (int)((volatile int64_t *)a.counters)[3];
-  for (int e = blockIdx.x; e < nfix; e += gridDim.x) {
-    const int home = a.fix_list[e];
-    const int hs = a.cell_start[home], he = a.cell_start[home + 1];
-    int home_pref = 0;
-    const int T = neighbour_table(a, home, lane, s_start, s_pref, nullptr, home_pref);
-    const int npass = (T + NC - 1) / NC;
-    for (int chunk0 = hs; chunk0 < he; chunk0 += 32) {
-      // lane l reads the redo masks of reference chunk0 + l (coalesced), flagged references are then
-      // visited one at a time
-      const int i_l = chunk0 + lane;
-      unsigned mk[FAST_MAX_PASSES];
-      bool want = false;
-#pragma unroll
-      for (int pass = 0; pass < FAST_MAX_PASSES; ++pass) {
-        mk[pass] = (i_l < he && pass < npass) ? a.redo_mask[(size_t)pass * n + i_l] : 0u;
-        want |= mk[pass] != 0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nfix; e += (long long)gridDim.x * blockDim.x) {
+    const int2 pr = a.fix_list[e];
+    const int si = pr.x & 0x7fffffff, sj = pr.y, kind = (unsigned)pr.x >> 31;
+    const double cs = exact_pair(a.idx, a.ctr, a.vec, n, a.g.box, a.g.rc2, si, sj);
+    if (kind == 0) {
+      if (cs != 0.0) {
+        const unsigned long long f = (unsigned long long)__double2ll_rn(cs * HS_FIX_SCALE);
+        atomicAdd((unsigned long long *)&a.acc_fix[si], f);
+        atomicAdd((unsigned long long *)&a.acc_fix[sj], f);
+        atomicAdd(&a.acc_cnt[si], 1);
+        atomicAdd(&a.acc_cnt[sj], 1);
       }
-      want = (i_l < he) && (a.flag[min(i_l, he - 1)] & 1) && (want || npass > FAST_MAX_PASSES);
-      unsigned todo = __ballot_sync(MOUSE_FULL_MASK, want);
-      while (todo) {
-        const int il = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int i = chunk0 + il;
-        const int moli = __float_as_int(a.P[i].w);
-        double add = 0.0;
-        int addc = 0;
-        for (int pass = 0; pass < npass; ++pass) {
-          // passes the fast sweep skipped are evaluated for every lane
-          unsigned lanes = 0xffffffffu;
-#pragma unroll
-          for (int q = 0; q < FAST_MAX_PASSES; ++q)
-            if (q == pass) lanes = __shfl_sync(MOUSE_FULL_MASK, mk[q], il);
-          while (lanes) {
-            const int L = __ffs(lanes) - 1;
-            lanes &= lanes - 1;
-            const int t = pass * NC + 32 * lane + L;          // lane s handles slot s of flagged lane L
-            double cs = 0.0;
-            if (lane < SLOTS && t < T) {
-              const int sj = cand_slot(s_pref, s_start, t);
-              if (sj != i && !(EXCL_MOL && __float_as_int(a.P[sj].w) == moli))
-                cs = exact_pair(a.idx, a.ctr, a.vec, n, a.g.box, a.g.rc2, i, sj);
-            }
-            add += warp_sum(cs);
-            addc += __reduce_add_sync(MOUSE_FULL_MASK, cs != 0.0 ? 1 : 0);
-            if (lane == 0) atomicAdd((unsigned long long *)&a.counters[1], 1ULL);
-          }
-        }
-        if (lane == 0 && (add != 0.0 || addc != 0)) {
-          const int o = a.idx[i];
-          a.out_sum[o] += add;
-          a.out_cnt[o] += addc;
-        }
-      }
+    } else if (cs == 0.0) {
+      atomicAdd(&a.acc_cnt[si], -1);
+      atomicAdd(&a.acc_cnt[sj], -1);
     }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.counters[C_NFIX_DONE] = nfix;
+}
+
+// accumulators (sorted slots, fixed point) -> out_sum / out_cnt (original bond order)
+__global__ void __launch_bounds__(256) p2_finish_kernel(const SweepArgs a) {
+  if (((volatile int64_t *)a.counters)[C_OVERFLOW]) return;
+  const int n_list = a.cell_start[a.g.ncell];
+  const long long nzero = a.counters[C_NZERO];
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_list; s += gridDim.x * blockDim.x) {
+    if (!(a.flag[s] & 1)) continue;                 // not a reference: out stays 0 / 0
+    const int o = a.idx[s];
+    double sum = (double)a.acc_fix[s] * HS_FIX_INV;
+    int cnt = a.acc_cnt[s];
+    // zero-length bonds in the neighbour set turn every mean into NaN and add to every count
+    // (0/0 in ordering_functions.py:112)
+    if (nzero) {
+      sum = __longlong_as_double(0x7ff8000000000000LL);
+      cnt += (int)nzero;
+    }
+    a.out_sum[o] = sum;
+    a.out_cnt[o] = cnt;
   }
 }
 
 // ------------------------------------------------------------------ exact all-FP64 sweep
 template <bool LISTS>
 __global__ void __launch_bounds__(128) p2_sweep_exact_kernel(const SweepArgs a) {
+  if (a.only_if_overflow && !((volatile int64_t *)a.counters)[C_OVERFLOW]) return;
   const int n_list = a.cell_start[a.g.ncell];
   const size_t n = (size_t)a.n;
   const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
@@ -515,8 +507,9 @@ __global__ void __launch_bounds__(128) p2_sweep_exact_kernel(const SweepArgs a) 
               double rsq = mouse_rsq_exact(cix, ciy, ciz, a.ctr[bj], a.ctr[n + bj], a.ctr[2 * n + bj], a.g.box);
               if (!(rsq <= a.g.rc2)) continue;
             }
-            const double dot = mouse_dot_exact(bix, biy, biz, a.vec[bj], a.vec[n + bj], a.vec[2 * n + bj]);
-            const double nj = a.U[t].w;
+            const double bjx = a.vec[bj], bjy = a.vec[n + bj], bjz = a.vec[2 * n + bj];
+            const double dot = mouse_dot_exact(bix, biy, biz, bjx, bjy, bjz);
+            const double nj = __dadd_rn(__dadd_rn(__dmul_rn(bjx, bjx), __dmul_rn(bjy, bjy)), __dmul_rn(bjz, bjz));
             const double cs = __ddiv_rn(__ddiv_rn(__dmul_rn(dot, dot), nr), nj);
             if (cs != 0.0) {
               if (LISTS) a.nbr_idx[row + cnt] = bj;
@@ -528,7 +521,7 @@ __global__ void __launch_bounds__(128) p2_sweep_exact_kernel(const SweepArgs a) 
       }
     }
     if (!LISTS) {
-      const long long nzero = a.counters[0];
+      const long long nzero = a.counters[C_NZERO];
       if (nzero) {
         sum = __longlong_as_double(0x7ff8000000000000LL);
         cnt += (int)nzero;
@@ -590,45 +583,27 @@ static int num_sms() {
   return g_num_sms;
 }
 
-int mouse_fast_variant = 1;  // tuning / debug knob (2 = skip the fixup kernel)
+int mouse_fast_variant = 1;         // tuning / debug knob (2 = skip the fixup kernel)
+int mouse_fast_slots_override = 0;  // test / tuning hook (set through mouse_set_tuning)
 
-template <int SLOTS, bool EXCL, bool LISTS>
-static void launch_fast_one(const SweepArgs &a, cudaStream_t st) {
-  const size_t smem = (size_t)(SLOTS + 1) * 32 * (3 * sizeof(double) + sizeof(int));
-  static bool configured = false;
-  static int blocks_per_sm = 1;
-  if (!configured) {
-    cudaFuncSetAttribute(p2_sweep_fast_kernel<SLOTS, EXCL, LISTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, p2_sweep_fast_kernel<SLOTS, EXCL, LISTS>, 32, smem);
+template <int SLOTS, bool EXCL>
+static void launch_half_one(const SweepArgs &a, cudaStream_t st) {
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, p2_sweep_half_kernel<SLOTS, EXCL>, 32, 0);
     if (blocks_per_sm < 1) blocks_per_sm = 1;
-    configured = true;
   }
-  // persistent-style grid: a few waves of resident warps, each striding over runs of home cells
-  const int nruns = (a.g.ncell + FAST_RUN - 1) / FAST_RUN;
+  // persistent warps: every resident warp (CTA) pulls home cells from the ticket counter
   int blocks = num_sms() * blocks_per_sm;
-  if (blocks > nruns) blocks = nruns;
-  p2_sweep_fast_kernel<SLOTS, EXCL, LISTS><<<blocks, 32, smem, st>>>(a);
-  if (!LISTS && mouse_fast_variant != 2) {   // variant 2 (debug): leave the dropped contributions out
-    int fb = num_sms() * 32;
-    if (fb > a.g.ncell) fb = a.g.ncell;
-    p2_fixup_kernel<SLOTS, EXCL><<<fb, 32, 0, st>>>(a);
-  }
+  if (blocks > a.g.ncell) blocks = a.g.ncell;
+  p2_sweep_half_kernel<SLOTS, EXCL><<<blocks, 32, 0, st>>>(a);
 }
-
 
 template <int SLOTS>
-static void launch_fast(const SweepArgs &a, bool excl_mol, bool lists, cudaStream_t st) {
-  if (lists) {
-    if (excl_mol) launch_fast_one<SLOTS, true, true>(a, st);
-    else launch_fast_one<SLOTS, false, true>(a, st);
-  } else {
-    if (excl_mol) launch_fast_one<SLOTS, true, false>(a, st);
-    else launch_fast_one<SLOTS, false, false>(a, st);
-  }
+static void launch_half(const SweepArgs &a, bool excl_mol, cudaStream_t st) {
+  if (excl_mol) launch_half_one<SLOTS, true>(a, st);
+  else launch_half_one<SLOTS, false>(a, st);
 }
-
-int mouse_fast_slots_override = 0;  // test / tuning hooks (set through mouse_set_tuning)
 
 int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const mouse_grid_t *grid, uint32_t flags,
                           const Workspace &w, double *out_sum, int32_t *out_cnt, const int64_t *row_ptr,
@@ -649,39 +624,52 @@ int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const
   a.counters = w.counters;
   a.row_ptr = row_ptr;
   a.nbr_idx = nbr_idx;
-  a.fix_list = w.cell_count;           // cell_count is free once cell_start exists
-  a.redo_mask = (unsigned *)w.p_tmp;   // p_tmp (16 B per item) is free after the cell build: 4 x u32 per item
+  a.acc_fix = w.acc_fix;
+  a.acc_cnt = w.acc_cnt;
+  // p_tmp / u_tmp (48 B per item, contiguous) are free after the cell build: the pair list of the fast sweep
+  a.fix_list = (int2 *)w.p_tmp;
+  a.fix_cap = (long long)(((char *)w.idx_tmp - (char *)w.p_tmp) / sizeof(int2));
   a.same_molecule = (flags & MOUSE_SAME_MOLECULE) ? 1 : 0;
   a.no_cutoff = (flags & MOUSE_NO_CUTOFF) ? 1 : 0;
+  a.only_if_overflow = 0;
   const bool lists = nbr_idx != nullptr;
   if (n == 0) return MOUSE_OK;
   if (!lists) {
     MOUSE_CUDA_CHECK(cudaMemsetAsync(out_sum, 0, sizeof(double) * (size_t)n, st));
   }
   MOUSE_CUDA_CHECK(cudaMemsetAsync(out_cnt, 0, sizeof(int32_t) * (size_t)n, st));
-  // counters[1] = exact re-decisions (diagnostic), counters[3] = length of the fixup list: per sweep
-  // counters[2] = run ticket of the persistent fast sweep (the reduce kernel resets it before using it)
-  MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters + 1, 0, 3 * sizeof(int64_t), st));
-  const bool fast = grid->fast && !(flags & (MOUSE_FORCE_EXACT | MOUSE_NO_CUTOFF));
+  // counters 1..4: diagnostics, home-cell ticket, pair list length, overflow flag (the reduce kernel resets
+  // the ticket again before using it)
+  MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters + 1, 0, 4 * sizeof(int64_t), st));
+  const bool fast = grid->fast && !lists && !(flags & (MOUSE_FORCE_EXACT | MOUSE_NO_CUTOFF));
+  int blocks = (int)((n + 127) / 128);
+  int maxb = num_sms() * 32;
+  if (blocks > maxb) blocks = maxb;
   if (fast) {
-    // SLOTS*32 registers-resident candidates per pass: size for mean + ~3 sigma of 27 cells
-    double mean = 27.0 * (double)n / (double)grid->ncell;
-    int need = (int)((1.15 * mean + 2.0 * sqrt(mean) + 31.0) / 32.0);
-    int slots = need <= 4 ? 4 : need <= 8 ? 8 : need <= 12 ? 12 : 16;
-    (void)need;
+    // acc_fix and acc_cnt are adjacent in the workspace: one memset
+    MOUSE_CUDA_CHECK(cudaMemsetAsync(w.acc_fix, 0, (size_t)((char *)(w.acc_cnt + n) - (char *)w.acc_fix), st));
+    // SLOTS * 32 register-resident candidates per pass: size for the mean of the 14 half-shell cells + ~2 sigma
+    double mean = 14.0 * (double)n / (double)grid->ncell;
+    int need = (int)((mean + 2.0 * sqrt(mean) + 31.0) / 32.0);
+    int slots = need <= 4 ? 4 : need <= 8 ? 8 : 12;
     if (mouse_fast_slots_override) slots = mouse_fast_slots_override;
     const bool excl = !a.same_molecule;
     switch (slots) {
-      case 4: launch_fast<4>(a, excl, lists, st); break;
-      case 8: launch_fast<8>(a, excl, lists, st); break;
-      case 12: launch_fast<12>(a, excl, lists, st); break;
-      default: launch_fast<16>(a, excl, lists, st); break;
+      case 4: launch_half<4>(a, excl, st); break;
+      case 8: launch_half<8>(a, excl, st); break;
+      default: launch_half<12>(a, excl, st); break;
     }
-    MOUSE_LAUNCH_CHECK("p2_sweep_fast_kernel");
+    MOUSE_LAUNCH_CHECK("p2_sweep_half_kernel");
+    if (mouse_fast_variant != 2) {   // variant 2 (debug): leave the undecided pairs out
+      p2_fixup_kernel<<<num_sms() * 2, 256, 0, st>>>(a);
+      MOUSE_LAUNCH_CHECK("p2_fixup_kernel");
+    }
+    p2_finish_kernel<<<num_sms() * 8, 256, 0, st>>>(a);
+    MOUSE_LAUNCH_CHECK("p2_finish_kernel");
+    a.only_if_overflow = 1;          // pair list overflow (pathological inputs): redo the frame exactly
+    p2_sweep_exact_kernel<false><<<blocks, 128, 0, st>>>(a);
+    MOUSE_LAUNCH_CHECK("p2_sweep_exact_kernel");
   } else {
-    int blocks = (int)((n + 127) / 128);
-    int maxb = num_sms() * 32;
-    if (blocks > maxb) blocks = maxb;
     if (lists)
       p2_sweep_exact_kernel<true><<<blocks, 128, 0, st>>>(a);
     else
