@@ -103,7 +103,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ------------------------------------------------------------------ half-shell fast sweep
-#define HS_MAXHOME 64      // home cells with more bonds are decided pair by pair by p2_fixup_kernel
+#define HS_MAXHOME 128     // home cells with more bonds are decided pair by pair by p2_fixup_kernel
 #define HS_MAXPASS 8       // ... and home cells with more than HS_MAXPASS * SLOTS * 32 candidates
 #ifndef HS_WARPS
 #define HS_WARPS 12        // resident warps (= CTAs) per SM the register allocation is sized for
@@ -212,16 +212,46 @@ __device__ __forceinline__ bool hs_fetch_item(const SweepArgs &a, int lane, int 
   }
 }
 
+// hit = (t < negw) [&& lane > ilc] [&& molj != moli];  accj += hit * d*d; cntj += hit; acci += hit * d*d; cnti += hit.
+// Branch-free: the weight w is d with its high word cleared on a miss (|w| < 1e-300, d * w vanishes in the sums), so
+// the two FP64 FMAs are unconditional and a miss costs one integer select.
+template <bool EXCL>
+__device__ __forceinline__ void hs_hit(const bool SELF, float t, float negw, double d, double &accj, int &cntj,
+                                       double &acci, int &cnti, int lane, int ilc, int molj, int moli) {
+  bool hit = t < negw;
+  if (SELF) hit = hit && lane > ilc;
+  if (EXCL) hit = hit && molj != moli;
+  const double w = __hiloint2double(hit ? __double2hiint(d) : 0, __double2loint(d));
+  accj = fma(d, w, accj);
+  acci = fma(d, w, acci);
+  cntj += hit ? 1 : 0;
+  cnti += hit ? 1 : 0;
+}
+
+// @(cnt > 0): acc_fix[g] += round(acc * 2^47); acc_cnt[g] += cnt   (no return value: RED)
+__device__ __forceinline__ void hs_flush(long long *acc_fix, int32_t *acc_cnt, int g, double acc, int cnt) {
+  const long long v = __double2ll_rn(acc * HS_FIX_SCALE);
+  asm volatile("{\n.reg .pred p;\nsetp.gt.s32 p, %3, 0;\n@p red.global.add.u64 [%0], %2;\n@p red.global.add.s32 [%1], %3;\n}" ::"l"(
+                   acc_fix + g),
+               "l"(acc_cnt + g), "l"(v), "r"(cnt)
+               : "memory");
+}
+
 template <int SLOTS, bool EXCL_MOL>
 __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const SweepArgs a) {
   constexpr int NC = SLOTS * 32;   // candidates per pass
   constexpr int NPAIR = SLOTS / 2;
+  constexpr int HSL = HS_MAXHOME / 32;   // slots of pass 0 that may hold home-cell bonds
   static_assert(SLOTS % 2 == 0 && NC >= HS_MAXHOME, "slots come in pairs; the home cell lives in pass 0");
   __shared__ __align__(128) float4 s_landP[NC];     // TMA landing zone
   __shared__ __align__(128) double4 s_landU[NC];
   __shared__ float4 s_homeP[HS_MAXHOME];            // the home cell's bonds: the references of this item
   __shared__ double s_homeU[3][HS_MAXHOME];
   __shared__ double s_acc[8][33];                   // per-lane partial sums of 8 references (transposed reduce)
+  __shared__ int s_gid[SLOTS][32];                  // sorted slot of every register-resident candidate (-1: empty)
+  __shared__ int s_next[3][32];                     // range table of the prefetched item (kept out of the registers)
+  __shared__ float s_nextf[4];
+  __shared__ int s_nexti[6];
   __shared__ __align__(8) uint64_t s_bar;
   const int lane = threadIdx.x;
   const float rc2_c = 0.5f * (a.g.rc2_lo + a.g.rc2_hi);             // guard band [c - w, c + w] around rc^2
@@ -264,70 +294,90 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     float2 xr2[NPAIR], yr2[NPAIR], zr2[NPAIR];
     double ux[SLOTS], uy[SLOTS], uz[SLOTS];
     double accj[SLOTS];
-    int cntj[SLOTS], gid[SLOTS], molr[SLOTS];
+    int cntj[SLOTS], molr[SLOTS];
     mbar_wait(&s_bar, phase);
     phase ^= 1u;
-    const float Lx = a.g.boxf[0], Ly = a.g.boxf[1], Lz = a.g.boxf[2];
+    {
+      const float Lx = a.g.boxf[0], Ly = a.g.boxf[1], Lz = a.g.boxf[2];
+      const float iLx = a.g.inv_boxf[0], iLy = a.g.inv_boxf[1], iLz = a.g.inv_boxf[2];
+      const bool bnd = cur.boundary != 0;
 #pragma unroll
-    for (int c = 0; c < SLOTS; ++c) {
-      const int tl = 32 * c + lane;
-      const bool valid = tl < nvalid;
-      const float4 p = s_landP[tl];
-      const double4 u = s_landU[tl];
-      float px = p.x, py = p.y, pz = p.z;
-      if (cur.boundary) {     // nearest periodic image to the home cell centre
-        px -= Lx * rintf((px - cur.hx) * a.g.inv_boxf[0]);
-        py -= Ly * rintf((py - cur.hy) * a.g.inv_boxf[1]);
-        pz -= Lz * rintf((pz - cur.hz) * a.g.inv_boxf[2]);
-      }
-      px = valid ? px : HS_PAD;
-      py = valid ? py : HS_PAD;
-      pz = valid ? pz : HS_PAD;
-      ux[c] = valid ? u.x : 1.0;
-      uy[c] = valid ? u.y : 1.0;
-      uz[c] = valid ? u.z : 1.0;
-      gid[c] = valid ? __double2loint(u.w) : -1;
-      molr[c] = __float_as_int(p.w);
-      accj[c] = 0.0;
-      cntj[c] = 0;
-      if (c & 1) {
-        xr2[c >> 1].y = px;
-        yr2[c >> 1].y = py;
-        zr2[c >> 1].y = pz;
-      } else {
-        xr2[c >> 1].x = px;
-        yr2[c >> 1].x = py;
-        zr2[c >> 1].x = pz;
-      }
-      if (c < HS_MAXHOME / 32 && pass == 0 && tl < cur.nhome) {   // the home cell leads the concatenation
-        s_homeP[tl] = make_float4(px, py, pz, p.w);
-        s_homeU[0][tl] = u.x;
-        s_homeU[1][tl] = u.y;
-        s_homeU[2][tl] = u.z;
+      for (int pp = 0; pp < NPAIR; ++pp) {
+        float q[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = 2 * pp + h;
+          const int tl = 32 * c + lane;
+          const bool valid = tl < nvalid;
+          const float4 p = s_landP[tl];
+          const double4 u = s_landU[tl];
+          float px = p.x, py = p.y, pz = p.z;
+          if (bnd) {     // nearest periodic image to the home cell centre
+            px -= Lx * rintf((px - cur.hx) * iLx);
+            py -= Ly * rintf((py - cur.hy) * iLy);
+            pz -= Lz * rintf((pz - cur.hz) * iLz);
+          }
+          q[h][0] = valid ? px : HS_PAD;
+          q[h][1] = valid ? py : HS_PAD;
+          q[h][2] = valid ? pz : HS_PAD;
+          ux[c] = valid ? u.x : 1.0;
+          uy[c] = valid ? u.y : 1.0;
+          uz[c] = valid ? u.z : 1.0;
+          s_gid[c][lane] = valid ? __double2loint(u.w) : -1;
+          molr[c] = __float_as_int(p.w);
+          accj[c] = 0.0;
+          cntj[c] = 0;
+          if (c < HSL && pass == 0 && tl < cur.nhome) {   // the home cell leads the concatenation
+            s_homeP[tl] = make_float4(px, py, pz, p.w);
+            s_homeU[0][tl] = u.x;
+            s_homeU[1][tl] = u.y;
+            s_homeU[2][tl] = u.z;
+          }
+        }
+        xr2[pp] = make_float2(q[0][0], q[1][0]);
+        yr2[pp] = make_float2(q[0][1], q[1][1]);
+        zr2[pp] = make_float2(q[0][2], q[1][2]);
       }
     }
     __syncwarp();
 
     // ---- re-arm the landing zone: next pass of this home cell, or pass 0 of the next one
-    HsItem nxt = cur;
     int npass = pass + 1;
     bool have_next = true;
-    if (npass * NC >= cur.T) {
-      npass = 0;
-      have_next = hs_fetch_item(a, lane, NC, nxt);
+    {
+      HsItem nxt = cur;
+      if (npass * NC >= cur.T) {
+        npass = 0;
+        have_next = hs_fetch_item(a, lane, NC, nxt);
+      }
+      if (have_next) {
+        issue(nxt, npass);
+        s_next[0][lane] = nxt.rsrc;
+        s_next[1][lane] = nxt.rlen;
+        s_next[2][lane] = nxt.rt;
+        if (lane == 0) {
+          s_nexti[0] = nxt.home;
+          s_nexti[1] = nxt.hs;
+          s_nexti[2] = nxt.nhome;
+          s_nexti[3] = nxt.T;
+          s_nexti[4] = nxt.boundary;
+          s_nextf[0] = nxt.hx;
+          s_nextf[1] = nxt.hy;
+          s_nextf[2] = nxt.hz;
+        }
+      }
     }
-    if (have_next) issue(nxt, npass);
+    const int hs = cur.hs, nhome = cur.nhome;
 
     // ---- the references of the home cell against the register-resident candidates
     int mycnt = 0;
-    for (int il = 0; il < cur.nhome; ++il) {
+    for (int il = 0; il < nhome; ++il) {
       const float4 pi = s_homeP[il];
       const double uix = s_homeU[0][il], uiy = s_homeU[1][il], uiz = s_homeU[2][il];
       const int moli = __float_as_int(pi.w);
       const float2 npx = make_float2(-pi.x, -pi.x), npy = make_float2(-pi.y, -pi.y), npz = make_float2(-pi.z, -pi.z);
-      // home-home pairs are decided once: candidate t (pass 0: slot 0 holds t = lane, slot 1 t = 32 + lane) > il
-      const bool ps0 = pass != 0 || lane > il;
-      const bool ps1 = pass != 0 || lane + 32 > il;
+      // home-home pairs are decided once: candidate t > il (pass 0: slot c < HSL holds t = 32 c + lane)
+      const int il_eff = pass == 0 ? il : -1;
       double acci0 = 0.0, acci1 = 0.0;
       int cnti = 0;
       float band = 3.0e38f, nearz = 3.0e38f;
@@ -341,47 +391,32 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
           const double d1 = fma(uix, ux[2 * pp + 1], fma(uiy, uy[2 * pp + 1], uiz * uz[2 * pp + 1]));
           // smallest |d| over ALL slots (as the high word, compared as a float): a false alarm only costs time
           nearz = fminf(nearz, fminf(fabsf(__int_as_float(__double2hiint(d0))), fabsf(__int_as_float(__double2hiint(d1)))));
-          bool h0 = t.x < negw, h1 = t.y < negw;
-          if (pp == 0) {
-            h0 = h0 && ps0;
-            h1 = h1 && ps1;
-          }
-          if (EXCL_MOL) {
-            h0 = h0 && molr[2 * pp] != moli;
-            h1 = h1 && molr[2 * pp + 1] != moli;
-          }
-          if (h0) {
-            accj[2 * pp] = fma(d0, d0, accj[2 * pp]);
-            cntj[2 * pp] += 1;
-            acci0 = fma(d0, d0, acci0);
-            cnti += 1;
-          }
-          if (h1) {
-            accj[2 * pp + 1] = fma(d1, d1, accj[2 * pp + 1]);
-            cntj[2 * pp + 1] += 1;
-            acci1 = fma(d1, d1, acci1);
-            cnti += 1;
-          }
+          hs_hit<EXCL_MOL>(2 * pp < HSL, t.x, negw, d0, accj[2 * pp], cntj[2 * pp], acci0, cnti, lane,
+                                           il_eff - 64 * pp, molr[2 * pp], moli);
+          hs_hit<EXCL_MOL>(2 * pp + 1 < HSL, t.y, negw, d1, accj[2 * pp + 1], cntj[2 * pp + 1], acci1, cnti, lane,
+                                               il_eff - 64 * pp - 32, molr[2 * pp + 1], moli);
         }
       }
       // ---- rare: candidates inside the guard band / near-zero dots are handed to p2_fixup_kernel
       if (band <= rc2_w || nearz <= nearz_thr) {
 #pragma unroll
         for (int c = 0; c < SLOTS; ++c) {
-          if (c < 2 * npp && gid[c] >= 0) {
-            bool ps = c == 0 ? ps0 : (c == 1 ? ps1 : true);
-            if (EXCL_MOL) ps = ps && molr[c] != moli;
-            if (ps) {
+          if (c < 2 * npp) {
+            const int g = s_gid[c][lane];
+            bool pc = g >= 0;
+            if (c < HSL) pc = pc && 32 * c + lane > il_eff;
+            if (EXCL_MOL) pc = pc && molr[c] != moli;
+            if (pc) {
               const float px = (c & 1) ? xr2[c >> 1].y : xr2[c >> 1].x;
               const float py = (c & 1) ? yr2[c >> 1].y : yr2[c >> 1].x;
               const float pz = (c & 1) ? zr2[c >> 1].y : zr2[c >> 1].x;
               const float dx = __fadd_rn(px, -pi.x), dy = __fadd_rn(py, -pi.y), dz = __fadd_rn(pz, -pi.z);
               const float t = __fadd_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))), -rc2_c);
               if (fabsf(t) <= rc2_w) {
-                fix_append(a.counters, a.fix_list, a.fix_cap, cur.hs + il, gid[c], 0);          // undecided: nothing was added
+                fix_append(a.counters, a.fix_list, a.fix_cap, hs + il, g, 0);          // undecided: nothing was added
               } else if (t < negw) {
                 const double d = fma(uix, ux[c], fma(uiy, uy[c], uiz * uz[c]));
-                if (fabs(d) < HS_NEARZ) fix_append(a.counters, a.fix_list, a.fix_cap, cur.hs + il, gid[c], 1);   // added as a hit; cos^2 == 0 ?
+                if (fabs(d) < HS_NEARZ) fix_append(a.counters, a.fix_list, a.fix_cap, hs + il, g, 1);   // counted; cos^2 == 0 ?
               }
             }
           }
@@ -391,7 +426,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
       s_acc[il & 7][lane] = acci0 + acci1;
       const int ctot = __reduce_add_sync(MOUSE_FULL_MASK, cnti);
       if (lane == (il & 7)) mycnt = ctot;
-      if ((il & 7) == 7 || il == cur.nhome - 1) {
+      if ((il & 7) == 7 || il == nhome - 1) {
         __syncwarp();
         const int row = lane & 7, part = lane >> 3;
         double v = 0.0;
@@ -400,24 +435,33 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
         v += __shfl_xor_sync(MOUSE_FULL_MASK, v, 8);
         v += __shfl_xor_sync(MOUSE_FULL_MASK, v, 16);
         const int iref = (il & ~7) + lane;
-        if (lane < 8 && iref <= il && mycnt > 0) {
-          atomicAdd((unsigned long long *)&a.acc_fix[cur.hs + iref], (unsigned long long)__double2ll_rn(v * HS_FIX_SCALE));
-          atomicAdd(&a.acc_cnt[cur.hs + iref], mycnt);
-        }
+        if (lane < 8 && iref <= il) hs_flush(a.acc_fix, a.acc_cnt, hs + iref, v, mycnt);
         __syncwarp();
       }
     }
     // ---- candidate side: one pair of integer atomics per candidate that was hit
 #pragma unroll
     for (int c = 0; c < SLOTS; ++c) {
-      if (c < 2 * npp && cntj[c] > 0) {
-        atomicAdd((unsigned long long *)&a.acc_fix[gid[c]], (unsigned long long)__double2ll_rn(accj[c] * HS_FIX_SCALE));
-        atomicAdd(&a.acc_cnt[gid[c]], cntj[c]);
+      if (c < 2 * npp) {
+        const int g = s_gid[c][lane];
+        hs_flush(a.acc_fix, a.acc_cnt, g < 0 ? 0 : g, accj[c], cntj[c]);
       }
     }
     if (!have_next) break;
-    cur = nxt;
+    __syncwarp();
+    cur.rsrc = s_next[0][lane];
+    cur.rlen = s_next[1][lane];
+    cur.rt = s_next[2][lane];
+    cur.home = s_nexti[0];
+    cur.hs = s_nexti[1];
+    cur.nhome = s_nexti[2];
+    cur.T = s_nexti[3];
+    cur.boundary = s_nexti[4];
+    cur.hx = s_nextf[0];
+    cur.hy = s_nextf[1];
+    cur.hz = s_nextf[2];
     pass = npass;
+    __syncwarp();
   }
 }
 

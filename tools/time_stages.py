@@ -62,26 +62,14 @@ def main():
         med, mn = timeit(fn)
         print("%-12s median %.3f ms  min %.3f ms" % (name, med, mn))
     pairs = int(tot.cpu()[2])
-    for R in (1,):
+    for R in (1, 2):      # 2 = without the fixup kernel
         L.mouse_set_tuning(b"fast_variant", R)
-        for slots in (12, 16):
+        for slots in (4, 8, 12):
             L.mouse_set_tuning(b"fast_slots", slots)
             med, mn = timeit(stages["p2_sweep"])
-            print("sweep K=%d slots=%-2d median %.3f ms  min %.3f ms  -> %.3e pairs/s" % (R, slots, med, mn, pairs / (mn * 1e-3)))
+            print("sweep variant=%d slots=%-2d median %.3f ms  min %.3f ms  -> %.3e pairs/s" % (R, slots, med, mn, pairs / (mn * 1e-3)))
     L.mouse_set_tuning(b"fast_slots", 0)
     L.mouse_set_tuning(b"fast_variant", 1)
-    if os.environ.get("MOUSE_TIMERS"):
-        for R, slots in ((1, 12), (1, 16)):
-            L.mouse_set_tuning(b"fast_variant", R); L.mouse_set_tuning(b"fast_slots", slots)
-            L.mouse_cell_build(p(vec), p(ctr), p(mol), None, None, n, C.byref(grid), p(ws), ws.numel(), st)
-            stages["p2_sweep"]()
-            out8 = (C.c_int64 * 8)()
-            L.mouse_debug_counters(C.byref(grid), n, p(ws), out8, st)
-            t = [out8[k] for k in range(4, 8)]
-            tot_c = sum(t) or 1
-            print("R=%d slots=%d warp-cycles: load %.1f%% A %.1f%% B %.1f%% epi %.1f%%  total %.3e (per ref %.0f)" % (
-                R, slots, 100 * t[0] / tot_c, 100 * t[1] / tot_c, 100 * t[2] / tot_c, 100 * t[3] / tot_c, tot_c, tot_c / n))
-        L.mouse_set_tuning(b"fast_slots", 0); L.mouse_set_tuning(b"fast_variant", 1)
     med, mn = timeit(lambda: L.mouse_p2_sweep(p(vec), p(ctr), n, C.byref(grid), flags | _lib.MOUSE_FORCE_EXACT, p(ws),
                                               p(ssum), p(cnt), st), reps=3, warm=1)
     print("sweep exact   median %.3f ms  min %.3f ms" % (med, mn))
