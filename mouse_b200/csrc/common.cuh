@@ -109,6 +109,7 @@ struct GridDev {
   int ncell;
   float cwf[3];
   float boxf[3], inv_boxf[3];
+  unsigned magic_x, magic_xy;   // floor(2^32 / nx), floor(2^32 / (nx * ny)): division-free cell index decoding
   float rc2_lo, rc2_hi;  // FP32 guard band: d2 < lo sure hit, d2 > hi sure miss
 };
 
@@ -124,6 +125,8 @@ static inline GridDev mouse_grid_dev(const mouse_grid_t *g) {
   }
   d.rc2 = g->rc2;
   d.ncell = g->ncell;
+  d.magic_x = (unsigned)(4294967296ULL / (unsigned long long)(d.nc[0] > 1 ? d.nc[0] : 2));
+  d.magic_xy = (unsigned)(4294967296ULL / (unsigned long long)(d.nc[0] * d.nc[1] > 1 ? d.nc[0] * d.nc[1] : 2));
   double lo = g->rc2 * (1.0 - (double)g->guard), hi = g->rc2 * (1.0 + (double)g->guard);
   d.rc2_lo = nextafterf((float)lo, 0.0f);
   d.rc2_hi = nextafterf((float)hi, 3.0e38f);

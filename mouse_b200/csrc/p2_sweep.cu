@@ -103,7 +103,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ------------------------------------------------------------------ half-shell fast sweep
-#define HS_MAXHOME 128     // home cells with more bonds are decided pair by pair by p2_fixup_kernel
+#define HS_MAXHOME 96      // home cells with more bonds are decided pair by pair by p2_fixup_kernel
 #define HS_MAXPASS 8       // ... and home cells with more than HS_MAXPASS * SLOTS * 32 candidates
 #ifndef HS_WARPS
 #define HS_WARPS 12        // resident warps (= CTAs) per SM the register allocation is sized for
@@ -147,85 +147,129 @@ __device__ __noinline__ void hs_oversize(const float4 *__restrict__ P, int64_t *
   }
 }
 
-// next non-empty home cell from the ticket counter + its range table; false when the grid is exhausted
-__device__ __forceinline__ bool hs_fetch_item(const SweepArgs &a, int lane, int nc_pass, HsItem &it) {
-  const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
-  for (;;) {
-    int tk = 0;
-    if (lane == 0) tk = (int)atomicAdd((unsigned long long *)&a.counters[C_TICKET], 1ULL);
-    tk = __shfl_sync(MOUSE_FULL_MASK, tk, 0);
-    if (tk >= a.g.ncell) return false;
-    const int hs = a.cell_start[tk], he = a.cell_start[tk + 1];
-    if (hs == he) continue;
-    const int cx = tk % nx, cy = (tk / nx) % ny, cz = tk / (nx * ny);
-    // rows of the forward half shell: (dy,dz) = (0,0) cells x..x+1 (home first), (1,0), (-1,1), (0,1), (1,1) cells
-    // x-1..x+1; a row that crosses the periodic boundary in x splits into two ranges (part 0 / part 1)
-    int src = 0, len = 0;
-    if (lane < 10) {
-      const int row = lane >> 1, part = lane & 1;
-      const int dy = (row == 1 || row == 4) ? 1 : (row == 2 ? -1 : 0);
-      const int dz = row >= 2 ? 1 : 0;
-      int yc = cy + dy, zc = cz + dz;
-      yc += yc < 0 ? ny : 0;
-      yc -= yc >= ny ? ny : 0;
-      zc -= zc >= nz ? nz : 0;
-      const int rb = (zc * ny + yc) * nx;
-      const int xa = row == 0 ? cx : cx - 1, xb = cx + 1;
-      int lo, hi;  // inclusive cell range of this part, empty when lo > hi
-      if (xa < 0) {
-        lo = part ? 0 : nx - 1;
-        hi = part ? xb : nx - 1;
-      } else if (xb >= nx) {
-        lo = part ? 0 : xa;
-        hi = part ? xb - nx : nx - 1;
-      } else {
-        lo = part ? 1 : xa;
-        hi = part ? 0 : xb;
-      }
-      if (lo <= hi) {
-        src = a.cell_start[rb + lo];
-        len = a.cell_start[rb + hi + 1] - src;
-      }
-    }
-    int incl = len;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-      const int y = __shfl_up_sync(MOUSE_FULL_MASK, incl, o);
-      if (lane >= o) incl += y;
-    }
-    it.home = tk;
-    it.hs = hs;
-    it.nhome = he - hs;
-    it.T = __shfl_sync(MOUSE_FULL_MASK, incl, 15);
-    it.rsrc = src;
-    it.rlen = len;
-    it.rt = incl - len;
-    it.hx = ((float)cx + 0.5f) * a.g.cwf[0] - 0.5f * a.g.boxf[0];
-    it.hy = ((float)cy + 0.5f) * a.g.cwf[1] - 0.5f * a.g.boxf[1];
-    it.hz = ((float)cz + 0.5f) * a.g.cwf[2] - 0.5f * a.g.boxf[2];
-    it.boundary = (cx == 0) | (cx == nx - 1) | (cy == 0) | (cy == ny - 1) | (cz == nz - 1);
-    if (it.nhome > HS_MAXHOME || it.T > HS_MAXPASS * nc_pass) {
-      hs_oversize(a.P, a.counters, a.fix_list, a.fix_cap, a.same_molecule, lane, it.hs, it.nhome, it.rsrc, it.rlen, it.rt);
-      continue;
-    }
-    return true;
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Range table of home cell tk.  Rows of the forward half shell: (dy,dz) = (0,0) cells x..x+1 (home first), (1,0),
+// (-1,1), (0,1), (1,1) cells x-1..x+1; a row that crosses the periodic boundary in x splits into two ranges
+// (part 0 / part 1).  Lane L < 10 owns range L = 2 * row + part: cells [lo, hi] of row base rb (empty when lo > hi).
+// tk -> (cx, cy, cz) without integer division: multiply-high by floor(2^32 / d), then at most two corrections
+__device__ __forceinline__ void hs_divmod(unsigned n, unsigned d, unsigned magic, int &q, int &r) {
+  unsigned qq = __umulhi(n, magic);
+  unsigned rr = n - qq * d;
+  if (rr >= d) {
+    rr -= d;
+    qq += 1;
+  }
+  if (rr >= d) {
+    rr -= d;
+    qq += 1;
+  }
+  q = (int)qq;
+  r = (int)rr;
+}
+__device__ __forceinline__ void hs_cell_coords(const GridDev &g, int tk, int &cx, int &cy, int &cz) {
+  int rem;
+  hs_divmod((unsigned)tk, (unsigned)(g.nc[0] * g.nc[1]), g.magic_xy, cz, rem);
+  hs_divmod((unsigned)rem, (unsigned)g.nc[0], g.magic_x, cy, cx);
+}
+
+__device__ __forceinline__ void hs_range_cells(const GridDev &g, int cx, int cy, int cz, int lane, int &rb, int &lo,
+                                               int &hi) {
+  const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
+  const int row = lane >> 1, part = lane & 1;
+  const int dy = (row == 1 || row == 4) ? 1 : (row == 2 ? -1 : 0);
+  const int dz = row >= 2 ? 1 : 0;
+  int yc = cy + dy, zc = cz + dz;
+  yc += yc < 0 ? ny : 0;
+  yc -= yc >= ny ? ny : 0;
+  zc -= zc >= nz ? nz : 0;
+  rb = (zc * ny + yc) * nx;
+  const int xa = row == 0 ? cx : cx - 1, xb = cx + 1;
+  if (xa < 0) {
+    lo = part ? 0 : nx - 1;
+    hi = part ? xb : nx - 1;
+  } else if (xb >= nx) {
+    lo = part ? 0 : xa;
+    hi = part ? xb - nx : nx - 1;
+  } else {
+    lo = part ? 1 : xa;
+    hi = part ? 0 : xb;
   }
 }
 
-// hit = (t < negw) [&& lane > ilc] [&& molj != moli];  accj += hit * d*d; cntj += hit; acci += hit * d*d; cnti += hit.
-// Branch-free: the weight w is d with its high word cleared on a miss (|w| < 1e-300, d * w vanishes in the sums), so
-// the two FP64 FMAs are unconditional and a miss costs one integer select.
-template <bool EXCL>
-__device__ __forceinline__ void hs_hit(const bool SELF, float t, float negw, double d, double &accj, int &cntj,
-                                       double &acci, int &cnti, int lane, int ilc, int molj, int moli) {
-  bool hit = t < negw;
-  if (SELF) hit = hit && lane > ilc;
-  if (EXCL) hit = hit && molj != moli;
-  const double w = __hiloint2double(hit ? __double2hiint(d) : 0, __double2loint(d));
-  accj = fma(d, w, accj);
-  acci = fma(d, w, acci);
-  cntj += hit ? 1 : 0;
-  cnti += hit ? 1 : 0;
+// fetch stage 2: start the loads of home cell tk's range table (cell_start entries) into s_raw, asynchronously
+__device__ __forceinline__ void hs_raw_issue(const SweepArgs &a, int lane, int tk, int (*s_raw)[32]) {
+  int cx, cy, cz;
+  hs_cell_coords(a.g, tk, cx, cy, cz);
+  if (lane == 12) {
+    s_raw[2][12] = cx;
+    s_raw[2][13] = cy;
+    s_raw[2][14] = cz;
+  }
+  if (lane < 10) {
+    int rb, lo, hi;
+    hs_range_cells(a.g, cx, cy, cz, lane, rb, lo, hi);
+    if (lo <= hi) {
+      cp_async4(&s_raw[0][lane], a.cell_start + rb + lo);
+      cp_async4(&s_raw[1][lane], a.cell_start + rb + hi + 1);
+    }
+    s_raw[2][lane] = lo <= hi;
+  } else if (lane < 12) {
+    cp_async4(&s_raw[0][lane], a.cell_start + tk + (lane - 10));   // lanes 10, 11: the home cell itself
+  }
+  cp_async_commit();
+}
+
+// fetch stage 3: the table of home cell tk has landed in s_raw; false when the cell is empty
+__device__ __forceinline__ bool hs_finalize(const SweepArgs &a, int lane, int tk, int (*s_raw)[32], HsItem &it) {
+  cp_async_wait_all();
+  __syncwarp();
+  const int hs = s_raw[0][10], he = s_raw[0][11];
+  const bool has = lane < 10 && s_raw[2][lane] != 0;
+  const int src = has ? s_raw[0][lane] : 0;
+  const int len = has ? s_raw[1][lane] - src : 0;
+  const int cx = s_raw[2][12], cy = s_raw[2][13], cz = s_raw[2][14];
+  __syncwarp();
+  int incl = len;
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) {
+    const int y = __shfl_up_sync(MOUSE_FULL_MASK, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
+  it.home = tk;
+  it.hs = hs;
+  it.nhome = he - hs;
+  it.T = __shfl_sync(MOUSE_FULL_MASK, incl, 15);
+  it.rsrc = src;
+  it.rlen = len;
+  it.rt = incl - len;
+  it.hx = ((float)cx + 0.5f) * a.g.cwf[0] - 0.5f * a.g.boxf[0];
+  it.hy = ((float)cy + 0.5f) * a.g.cwf[1] - 0.5f * a.g.boxf[1];
+  it.hz = ((float)cz + 0.5f) * a.g.cwf[2] - 0.5f * a.g.boxf[2];
+  it.boundary = (cx == 0) | (cx == nx - 1) | (cy == 0) | (cy == ny - 1) | (cz == nz - 1);
+  return he > hs;
+}
+
+// all-ones when x < y (FSET: one instruction, no predicate register)
+__device__ __forceinline__ int mask_lt(float x, float y) {
+  int m;
+  asm("set.lt.s32.f32 %0, %1, %2;" : "=r"(m) : "f"(x), "f"(y));
+  return m;
+}
+__device__ __forceinline__ int mask_gt(int x, int y) {
+  int m;
+  asm("set.gt.s32.s32 %0, %1, %2;" : "=r"(m) : "r"(x), "r"(y));
+  return m;
+}
+__device__ __forceinline__ int mask_ne(int x, int y) {
+  int m;
+  asm("set.ne.s32.s32 %0, %1, %2;" : "=r"(m) : "r"(x), "r"(y));
+  return m;
 }
 
 // @(cnt > 0): acc_fix[g] += round(acc * 2^47); acc_cnt[g] += cnt   (no return value: RED)
@@ -237,28 +281,142 @@ __device__ __forceinline__ void hs_flush(long long *acc_fix, int32_t *acc_cnt, i
                : "memory");
 }
 
+struct HsConst {
+  float rc2_c, rc2_w, negw, nearz_thr;
+};
+
+// The references of one home cell against NPP register-resident slot pairs (specialised on NPP: no guards inside the
+// reference loop, the slot pairs interleave freely).
+template <int SLOTS, int NPP, bool EXCL_MOL>
+__device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k, const int lane, const int pass,
+                                            const int hs, const int nhome, const float2 (&xr2)[SLOTS / 2],
+                                            const float2 (&yr2)[SLOTS / 2], const float2 (&zr2)[SLOTS / 2],
+                                            const double (&ux)[SLOTS], const double (&uy)[SLOTS],
+                                            const double (&uz)[SLOTS], double (&accj)[SLOTS], int (&cntj)[SLOTS],
+                                            const int (&molr)[SLOTS], const float4 *s_homeP,
+                                            const double (*s_homeU)[HS_MAXHOME], double (*s_acc)[33],
+                                            int (*s_cnt)[33], const int (*s_gid)[32]) {
+  constexpr int HSL = HS_MAXHOME / 32;   // slots of pass 0 that may hold home-cell bonds
+  const float2 nrc = make_float2(-k.rc2_c, -k.rc2_c);
+  // reference il + 1 is fetched from shared memory while reference il is processed
+  float4 pi_n = s_homeP[0];
+  double uix_n = s_homeU[0][0], uiy_n = s_homeU[1][0], uiz_n = s_homeU[2][0];
+  for (int il = 0; il < nhome; ++il) {
+    const float4 pi = pi_n;
+    const double uix = uix_n, uiy = uiy_n, uiz = uiz_n;
+    {
+      const int in = min(il + 1, HS_MAXHOME - 1);
+      pi_n = s_homeP[in];
+      uix_n = s_homeU[0][in];
+      uiy_n = s_homeU[1][in];
+      uiz_n = s_homeU[2][in];
+    }
+    const int moli = __float_as_int(pi.w);
+    const float2 npx = make_float2(-pi.x, -pi.x), npy = make_float2(-pi.y, -pi.y), npz = make_float2(-pi.z, -pi.z);
+    // home-home pairs are decided once: candidate t > il (pass 0: slot c < HSL holds t = 32 c + lane)
+    const int il_eff = pass == 0 ? il : -1;
+    double acci0 = 0.0, acci1 = 0.0;
+    int cnti = 0;
+    float band = 3.0e38f, nearz = 3.0e38f;
+#pragma unroll
+    for (int pp = 0; pp < NPP; ++pp) {
+      const float2 dx = __fadd2_rn(xr2[pp], npx), dy = __fadd2_rn(yr2[pp], npy), dz = __fadd2_rn(zr2[pp], npz);
+      const float2 t = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), nrc);   // d2 - rc2
+      band = fminf(band, fminf(fabsf(t.x), fabsf(t.y)));
+      const double d0 = fma(uix, ux[2 * pp], fma(uiy, uy[2 * pp], uiz * uz[2 * pp]));
+      const double d1 = fma(uix, ux[2 * pp + 1], fma(uiy, uy[2 * pp + 1], uiz * uz[2 * pp + 1]));
+      // smallest |d| over ALL slots (as the high word, compared as a float): a false alarm only costs time
+      nearz = fminf(nearz, fminf(fabsf(__int_as_float(__double2hiint(d0))), fabsf(__int_as_float(__double2hiint(d1)))));
+      // hit masks (all ones / zero).  Branch-free: the weight w is d with its high word cleared on a miss
+      // (|w| < 1e-300, w * w vanishes in the sums), so the FP64 FMAs are unconditional
+      int m0 = mask_lt(t.x, k.negw), m1 = mask_lt(t.y, k.negw);
+      if (2 * pp < HSL) m0 &= mask_gt(lane, il_eff - 64 * pp);
+      if (2 * pp + 1 < HSL) m1 &= mask_gt(lane, il_eff - 64 * pp - 32);
+      if (EXCL_MOL) {
+        m0 &= mask_ne(molr[2 * pp], moli);
+        m1 &= mask_ne(molr[2 * pp + 1], moli);
+      }
+      const double w0 = __hiloint2double(__double2hiint(d0) & m0, __double2loint(d0));
+      const double w1 = __hiloint2double(__double2hiint(d1) & m1, __double2loint(d1));
+      accj[2 * pp] = fma(w0, w0, accj[2 * pp]);
+      accj[2 * pp + 1] = fma(w1, w1, accj[2 * pp + 1]);
+      acci0 = fma(w0, w0, acci0);
+      acci1 = fma(w1, w1, acci1);
+      cntj[2 * pp] -= m0;
+      cntj[2 * pp + 1] -= m1;
+      cnti -= m0 + m1;
+    }
+    // ---- rare: candidates inside the guard band / near-zero dots are handed to p2_fixup_kernel
+    if (band <= k.rc2_w || nearz <= k.nearz_thr) {
+#pragma unroll
+      for (int c = 0; c < 2 * NPP; ++c) {
+        const int g = s_gid[c][lane];
+        bool pc = g >= 0;
+        if (c < HSL) pc = pc && 32 * c + lane > il_eff;
+        if (EXCL_MOL) pc = pc && molr[c] != moli;
+        if (pc) {
+          const float px = (c & 1) ? xr2[c >> 1].y : xr2[c >> 1].x;
+          const float py = (c & 1) ? yr2[c >> 1].y : yr2[c >> 1].x;
+          const float pz = (c & 1) ? zr2[c >> 1].y : zr2[c >> 1].x;
+          const float dx = __fadd_rn(px, -pi.x), dy = __fadd_rn(py, -pi.y), dz = __fadd_rn(pz, -pi.z);
+          const float t = __fadd_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))), -k.rc2_c);
+          if (fabsf(t) <= k.rc2_w) {
+            fix_append(a.counters, a.fix_list, a.fix_cap, hs + il, g, 0);          // undecided: nothing was added
+          } else if (t < k.negw) {
+            const double d = fma(uix, ux[c], fma(uiy, uy[c], uiz * uz[c]));
+            if (fabs(d) < HS_NEARZ) fix_append(a.counters, a.fix_list, a.fix_cap, hs + il, g, 1);   // counted; cos^2 == 0 ?
+          }
+        }
+      }
+    }
+    // ---- reference side: per-lane partials -> shared memory, 8 references are reduced together
+    s_acc[il & 7][lane] = acci0 + acci1;
+    s_cnt[il & 7][lane] = cnti;
+    if ((il & 7) == 7 || il == nhome - 1) {
+      __syncwarp();
+      const int row = lane & 7, part = lane >> 3;
+      double v = 0.0;
+      int nv = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        v += s_acc[row][part * 8 + q];
+        nv += s_cnt[row][part * 8 + q];
+      }
+      v += __shfl_xor_sync(MOUSE_FULL_MASK, v, 8);
+      nv += __shfl_xor_sync(MOUSE_FULL_MASK, nv, 8);
+      v += __shfl_xor_sync(MOUSE_FULL_MASK, v, 16);
+      nv += __shfl_xor_sync(MOUSE_FULL_MASK, nv, 16);
+      const int iref = (il & ~7) + lane;
+      if (lane < 8 && iref <= il) hs_flush(a.acc_fix, a.acc_cnt, hs + iref, v, nv);
+      __syncwarp();
+    }
+  }
+}
+
 template <int SLOTS, bool EXCL_MOL>
 __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const SweepArgs a) {
   constexpr int NC = SLOTS * 32;   // candidates per pass
   constexpr int NPAIR = SLOTS / 2;
-  constexpr int HSL = HS_MAXHOME / 32;   // slots of pass 0 that may hold home-cell bonds
-  static_assert(SLOTS % 2 == 0 && NC >= HS_MAXHOME, "slots come in pairs; the home cell lives in pass 0");
+  constexpr int HSL = HS_MAXHOME / 32;
+  static_assert(SLOTS % 2 == 0 && NC >= HS_MAXHOME && NPAIR <= 6, "slots come in pairs; the home cell lives in pass 0");
   __shared__ __align__(128) float4 s_landP[NC];     // TMA landing zone
   __shared__ __align__(128) double4 s_landU[NC];
   __shared__ float4 s_homeP[HS_MAXHOME];            // the home cell's bonds: the references of this item
   __shared__ double s_homeU[3][HS_MAXHOME];
   __shared__ double s_acc[8][33];                   // per-lane partial sums of 8 references (transposed reduce)
+  __shared__ int s_cnt[8][33];                      // ... and partial counts
   __shared__ int s_gid[SLOTS][32];                  // sorted slot of every register-resident candidate (-1: empty)
+  __shared__ int s_raw[3][32];                      // range table in flight (fetch stage 2 -> 3)
   __shared__ int s_next[3][32];                     // range table of the prefetched item (kept out of the registers)
   __shared__ float s_nextf[4];
   __shared__ int s_nexti[6];
   __shared__ __align__(8) uint64_t s_bar;
   const int lane = threadIdx.x;
-  const float rc2_c = 0.5f * (a.g.rc2_lo + a.g.rc2_hi);             // guard band [c - w, c + w] around rc^2
-  const float rc2_w = 0.5f * (a.g.rc2_hi - a.g.rc2_lo) * 1.0001f;
-  const float negw = -rc2_w;
-  const float nearz_thr = __int_as_float(HS_NEARZ_HI);
-  const float2 nrc = make_float2(-rc2_c, -rc2_c);
+  HsConst k;
+  k.rc2_c = 0.5f * (a.g.rc2_lo + a.g.rc2_hi);             // guard band [c - w, c + w] around rc^2
+  k.rc2_w = 0.5f * (a.g.rc2_hi - a.g.rc2_lo) * 1.0001f;
+  k.negw = -k.rc2_w;
+  k.nearz_thr = __int_as_float(HS_NEARZ_HI);
 
   if (lane == 0) {
     mbar_init(&s_bar, 1);
@@ -281,8 +439,39 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     }
   };
 
+  // Three-stage fetch pipeline, one stage per loop iteration so that no global latency is exposed:
+  //   stage 1  ticket  = atomicAdd(home-cell counter)           (tkP: issued one iteration before it is used)
+  //   stage 2  range table of the ticket's home cell -> s_raw   (tkA: cp.async issued one iteration before stage 3)
+  //   stage 3  finalize the table, arm the landing zone (TMA)   (one iteration before the data is consumed)
+  int tkA, tkP = 0;
+  {
+    int t0 = 0;
+    if (lane == 0) {
+      t0 = (int)atomicAdd((unsigned int *)&a.counters[C_TICKET], 1u);    // low word of the 64-bit counter
+      tkP = (int)atomicAdd((unsigned int *)&a.counters[C_TICKET], 1u);
+    }
+    tkA = __shfl_sync(MOUSE_FULL_MASK, t0, 0);
+    if (tkA < a.g.ncell) hs_raw_issue(a, lane, tkA, s_raw);
+  }
+  // next non-empty, regular home cell; false when the grid is exhausted
+  auto advance = [&](HsItem &it) -> bool {
+    for (;;) {
+      if (tkA >= a.g.ncell) return false;
+      const bool nonempty = hs_finalize(a, lane, tkA, s_raw, it);
+      tkA = __shfl_sync(MOUSE_FULL_MASK, tkP, 0);
+      if (lane == 0) tkP = (int)atomicAdd((unsigned int *)&a.counters[C_TICKET], 1u);
+      if (tkA < a.g.ncell) hs_raw_issue(a, lane, tkA, s_raw);
+      if (!nonempty) continue;
+      if (it.nhome > HS_MAXHOME || it.T > HS_MAXPASS * NC) {
+        hs_oversize(a.P, a.counters, a.fix_list, a.fix_cap, a.same_molecule, lane, it.hs, it.nhome, it.rsrc, it.rlen, it.rt);
+        continue;
+      }
+      return true;
+    }
+  };
+
   HsItem cur;
-  if (!hs_fetch_item(a, lane, NC, cur)) return;
+  if (!advance(cur)) return;
   int pass = 0;
   issue(cur, pass);
 
@@ -348,7 +537,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
       HsItem nxt = cur;
       if (npass * NC >= cur.T) {
         npass = 0;
-        have_next = hs_fetch_item(a, lane, NC, nxt);
+        have_next = advance(nxt);
       }
       if (have_next) {
         issue(nxt, npass);
@@ -370,75 +559,18 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     const int hs = cur.hs, nhome = cur.nhome;
 
     // ---- the references of the home cell against the register-resident candidates
-    int mycnt = 0;
-    for (int il = 0; il < nhome; ++il) {
-      const float4 pi = s_homeP[il];
-      const double uix = s_homeU[0][il], uiy = s_homeU[1][il], uiz = s_homeU[2][il];
-      const int moli = __float_as_int(pi.w);
-      const float2 npx = make_float2(-pi.x, -pi.x), npy = make_float2(-pi.y, -pi.y), npz = make_float2(-pi.z, -pi.z);
-      // home-home pairs are decided once: candidate t > il (pass 0: slot c < HSL holds t = 32 c + lane)
-      const int il_eff = pass == 0 ? il : -1;
-      double acci0 = 0.0, acci1 = 0.0;
-      int cnti = 0;
-      float band = 3.0e38f, nearz = 3.0e38f;
-#pragma unroll
-      for (int pp = NPAIR - 1; pp >= 0; --pp) {
-        if (pp < npp) {
-          const float2 dx = __fadd2_rn(xr2[pp], npx), dy = __fadd2_rn(yr2[pp], npy), dz = __fadd2_rn(zr2[pp], npz);
-          const float2 t = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), nrc);   // d2 - rc2
-          band = fminf(band, fminf(fabsf(t.x), fabsf(t.y)));
-          const double d0 = fma(uix, ux[2 * pp], fma(uiy, uy[2 * pp], uiz * uz[2 * pp]));
-          const double d1 = fma(uix, ux[2 * pp + 1], fma(uiy, uy[2 * pp + 1], uiz * uz[2 * pp + 1]));
-          // smallest |d| over ALL slots (as the high word, compared as a float): a false alarm only costs time
-          nearz = fminf(nearz, fminf(fabsf(__int_as_float(__double2hiint(d0))), fabsf(__int_as_float(__double2hiint(d1)))));
-          hs_hit<EXCL_MOL>(2 * pp < HSL, t.x, negw, d0, accj[2 * pp], cntj[2 * pp], acci0, cnti, lane,
-                                           il_eff - 64 * pp, molr[2 * pp], moli);
-          hs_hit<EXCL_MOL>(2 * pp + 1 < HSL, t.y, negw, d1, accj[2 * pp + 1], cntj[2 * pp + 1], acci1, cnti, lane,
-                                               il_eff - 64 * pp - 32, molr[2 * pp + 1], moli);
-        }
-      }
-      // ---- rare: candidates inside the guard band / near-zero dots are handed to p2_fixup_kernel
-      if (band <= rc2_w || nearz <= nearz_thr) {
-#pragma unroll
-        for (int c = 0; c < SLOTS; ++c) {
-          if (c < 2 * npp) {
-            const int g = s_gid[c][lane];
-            bool pc = g >= 0;
-            if (c < HSL) pc = pc && 32 * c + lane > il_eff;
-            if (EXCL_MOL) pc = pc && molr[c] != moli;
-            if (pc) {
-              const float px = (c & 1) ? xr2[c >> 1].y : xr2[c >> 1].x;
-              const float py = (c & 1) ? yr2[c >> 1].y : yr2[c >> 1].x;
-              const float pz = (c & 1) ? zr2[c >> 1].y : zr2[c >> 1].x;
-              const float dx = __fadd_rn(px, -pi.x), dy = __fadd_rn(py, -pi.y), dz = __fadd_rn(pz, -pi.z);
-              const float t = __fadd_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))), -rc2_c);
-              if (fabsf(t) <= rc2_w) {
-                fix_append(a.counters, a.fix_list, a.fix_cap, hs + il, g, 0);          // undecided: nothing was added
-              } else if (t < negw) {
-                const double d = fma(uix, ux[c], fma(uiy, uy[c], uiz * uz[c]));
-                if (fabs(d) < HS_NEARZ) fix_append(a.counters, a.fix_list, a.fix_cap, hs + il, g, 1);   // counted; cos^2 == 0 ?
-              }
-            }
-          }
-        }
-      }
-      // ---- reference side: per-lane partials -> shared memory, 8 references are reduced together
-      s_acc[il & 7][lane] = acci0 + acci1;
-      const int ctot = __reduce_add_sync(MOUSE_FULL_MASK, cnti);
-      if (lane == (il & 7)) mycnt = ctot;
-      if ((il & 7) == 7 || il == nhome - 1) {
-        __syncwarp();
-        const int row = lane & 7, part = lane >> 3;
-        double v = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v += s_acc[row][part * 8 + k];
-        v += __shfl_xor_sync(MOUSE_FULL_MASK, v, 8);
-        v += __shfl_xor_sync(MOUSE_FULL_MASK, v, 16);
-        const int iref = (il & ~7) + lane;
-        if (lane < 8 && iref <= il) hs_flush(a.acc_fix, a.acc_cnt, hs + iref, v, mycnt);
-        __syncwarp();
-      }
+#define HS_RUN(N)                                                                                                  \
+  hs_ref_loop<SLOTS, (N <= NPAIR ? N : NPAIR), EXCL_MOL>(a, k, lane, pass, hs, nhome, xr2, yr2, zr2, ux, uy, uz, accj, cntj, \
+                                                          molr, s_homeP, s_homeU, s_acc, s_cnt, s_gid)
+    switch (npp) {
+      case 1: HS_RUN(1); break;
+      case 2: HS_RUN(2); break;
+      case 3: HS_RUN(3); break;
+      case 4: HS_RUN(4); break;
+      case 5: HS_RUN(5); break;
+      default: HS_RUN(6); break;
     }
+#undef HS_RUN
     // ---- candidate side: one pair of integer atomics per candidate that was hit
 #pragma unroll
     for (int c = 0; c < SLOTS; ++c) {
