@@ -115,6 +115,14 @@ int mouse_p2_frame(const double *pos, const int32_t *bond_atoms, const int32_t *
                    void *ws, size_t ws_bytes, double *vec, double *ctr, double *sum, int32_t *cnt,
                    double *mean, mouse_p2_totals_t *totals, void *stream);
 
+/* mouse_p2_frame with two optional cudaEvent_t handles (NULL = none) recorded on `stream` right before and right
+ * after the K3 launches: lets a caller time the pair sweep inside a frame (bench.py's roofline line). */
+int mouse_p2_frame_timed(const double *pos, const int32_t *bond_atoms, const int32_t *mol, const uint8_t *nbr_mask,
+                         const uint8_t *ref_mask, int64_t n_bonds, const mouse_grid_t *grid, uint32_t flags,
+                         void *ws, size_t ws_bytes, double *vec, double *ctr, double *sum, int32_t *cnt,
+                         double *mean, mouse_p2_totals_t *totals, void *ev_sweep_begin, void *ev_sweep_end,
+                         void *stream);
+
 /* K5.  Replaces calculateRdfForReference (ordering_functions.py:66-88) summed over all atoms as
  * in CalculatePairCorrelationFunctions (:162-173), accumulating onto zeros.
  * type: per-atom type code in [0,ntypes) or < 0 (not selected); edges: NumPy's bin edges

@@ -35,7 +35,7 @@ class P2Totals(C.Structure):
 EXPORTS = [
     "mouse_version", "mouse_last_error", "mouse_set_tuning", "mouse_grid_plan", "mouse_bond_build",
     "mouse_workspace_bytes", "mouse_cell_build", "mouse_p2_sweep", "mouse_p2_pair_lists", "mouse_p2_reduce",
-    "mouse_p2_frame", "mouse_rdf_frame", "mouse_single_ref_workspace_bytes", "mouse_p2_single_ref",
+    "mouse_p2_frame", "mouse_p2_frame_timed", "mouse_rdf_frame", "mouse_single_ref_workspace_bytes", "mouse_p2_single_ref",
     "mouse_rdf_single_ref", "mouse_debug_counters",
 ]
 
@@ -74,6 +74,7 @@ def lib():
     L.mouse_p2_pair_lists.argtypes = [vp, vp, i64, gp, u32, vp, vp, vp, vp, i64, vp]
     L.mouse_p2_reduce.argtypes = [vp, vp, i64, gp, vp, vp, vp, vp, dbl, dbl, i32, vp]
     L.mouse_p2_frame.argtypes = [vp, vp, vp, vp, vp, i64, gp, u32, vp, C.c_size_t, vp, vp, vp, vp, vp, vp, vp]
+    L.mouse_p2_frame_timed.argtypes = [vp, vp, vp, vp, vp, i64, gp, u32, vp, C.c_size_t, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.mouse_rdf_frame.argtypes = [vp, vp, vp, i64, i32, gp, u32, C.POINTER(C.c_double), i32, vp, C.c_size_t, vp, vp]
     L.mouse_single_ref_workspace_bytes.restype = C.c_size_t
     L.mouse_p2_single_ref.argtypes = [vp, i64, C.POINTER(C.c_double), C.POINTER(C.c_double), dbl, dbl, u32, vp, vp, vp]

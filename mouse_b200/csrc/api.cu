@@ -11,9 +11,15 @@ int mouse_launch_bond_build(const double *pos, const int32_t *bond_atoms, int64_
 int mouse_launch_cell_build(int mode, const double *xyz, const double *vec, const int32_t *code,
                             const int32_t *code2, const uint8_t *nbr_mask, const uint8_t *ref_mask, int64_t n,
                             const mouse_grid_t *grid, const Workspace &w, cudaStream_t st);
+int mouse_launch_frame_build(const double *pos, const int32_t *bond_atoms, const int32_t *mol, const uint8_t *nbr_mask,
+                             const uint8_t *ref_mask, int64_t n, const mouse_grid_t *grid, const Workspace &w,
+                             double *vec, double *ctr, double *out_sum, int32_t *out_cnt, double *out_mean,
+                             cudaStream_t st);
 int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const mouse_grid_t *grid, uint32_t flags,
                           const Workspace &w, double *out_sum, int32_t *out_cnt, const int64_t *row_ptr,
-                          int32_t *nbr_idx, cudaStream_t st);
+                          int32_t *nbr_idx, int frame_mode, int *used_fast, cudaStream_t st);
+int mouse_launch_p2_finish_reduce(int64_t n, const mouse_grid_t *grid, const Workspace &w, double *out_sum,
+                                  int32_t *out_cnt, double *out_mean, mouse_p2_totals_t *totals, cudaStream_t st);
 int mouse_launch_row_ptr(const int32_t *cnt, int64_t n, int64_t *row_ptr, cudaStream_t st);
 int mouse_launch_p2_reduce(const double *sum, const int32_t *cnt, int64_t n, const Workspace &w, double *out_mean,
                            mouse_p2_totals_t *totals, int64_t *hist, double smin, double smax, int32_t nbins,
@@ -156,7 +162,7 @@ int mouse_p2_sweep(const double *vec, const double *ctr, int64_t n_bonds, const 
     return MOUSE_EINVAL;
   }
   Workspace w = mouse_carve((void *)ws, n_bonds, grid->ncell);
-  return mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, out_sum, out_cnt, nullptr, nullptr,
+  return mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, out_sum, out_cnt, nullptr, nullptr, 0, nullptr,
                                (cudaStream_t)stream);
 }
 
@@ -172,7 +178,7 @@ int mouse_p2_pair_lists(const double *vec, const double *ctr, int64_t n_bonds, c
   int rc = mouse_launch_row_ptr(cnt, n_bonds, row_ptr, (cudaStream_t)stream);
   if (rc) return rc;
   // rank_of is free after the cell build: scratch "entries written so far" per row
-  return mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, nullptr, w.rank_of, row_ptr, nbr_idx,
+  return mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, nullptr, w.rank_of, row_ptr, nbr_idx, 0, nullptr,
                                (cudaStream_t)stream);
 }
 
@@ -188,18 +194,39 @@ int mouse_p2_reduce(const double *sum, const int32_t *cnt, int64_t n_bonds, cons
                                 (cudaStream_t)stream);
 }
 
-int mouse_p2_frame(const double *pos, const int32_t *bond_atoms, const int32_t *mol, const uint8_t *nbr_mask,
-                   const uint8_t *ref_mask, int64_t n_bonds, const mouse_grid_t *grid, uint32_t flags, void *ws,
-                   size_t ws_bytes, double *vec, double *ctr, double *sum, int32_t *cnt, double *mean,
-                   mouse_p2_totals_t *totals, void *stream) {
+int mouse_p2_frame_timed(const double *pos, const int32_t *bond_atoms, const int32_t *mol, const uint8_t *nbr_mask,
+                         const uint8_t *ref_mask, int64_t n_bonds, const mouse_grid_t *grid, uint32_t flags, void *ws,
+                         size_t ws_bytes, double *vec, double *ctr, double *sum, int32_t *cnt, double *mean,
+                         mouse_p2_totals_t *totals, void *ev_sweep_begin, void *ev_sweep_end, void *stream) {
   Workspace w;
   int rc = check_ws("mouse_p2_frame", n_bonds, grid, ws, ws_bytes, &w);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = mouse_bond_build(pos, bond_atoms, n_bonds, grid->box, vec, ctr, stream))) return rc;
-  if ((rc = mouse_launch_cell_build(0, ctr, vec, mol, nullptr, nbr_mask, ref_mask, n_bonds, grid, w, st))) return rc;
-  if ((rc = mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, sum, cnt, nullptr, nullptr, st))) return rc;
+  if (!pos || !bond_atoms || !vec || !ctr || !sum || !cnt || !mean || !totals) {
+    if (n_bonds > 0) {
+      mouse_set_error("mouse_p2_frame: NULL argument");
+      return MOUSE_EINVAL;
+    }
+  }
+  // K1 + K2 fused (bond vectors, cell list, outputs initialised) -> K3 -> K4 fused with the accumulator conversion
+  if ((rc = mouse_launch_frame_build(pos, bond_atoms, mol, nbr_mask, ref_mask, n_bonds, grid, w, vec, ctr, sum, cnt,
+                                     mean, st)))
+    return rc;
+  int used_fast = 0;
+  if (ev_sweep_begin) MOUSE_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev_sweep_begin, st));
+  if ((rc = mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, sum, cnt, nullptr, nullptr, 1, &used_fast, st)))
+    return rc;
+  if (ev_sweep_end) MOUSE_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev_sweep_end, st));
+  if (used_fast) return mouse_launch_p2_finish_reduce(n_bonds, grid, w, sum, cnt, mean, totals, st);
   return mouse_launch_p2_reduce(sum, cnt, n_bonds, w, mean, totals, nullptr, 0.0, 0.0, 0, st);
+}
+
+int mouse_p2_frame(const double *pos, const int32_t *bond_atoms, const int32_t *mol, const uint8_t *nbr_mask,
+                   const uint8_t *ref_mask, int64_t n_bonds, const mouse_grid_t *grid, uint32_t flags, void *ws,
+                   size_t ws_bytes, double *vec, double *ctr, double *sum, int32_t *cnt, double *mean,
+                   mouse_p2_totals_t *totals, void *stream) {
+  return mouse_p2_frame_timed(pos, bond_atoms, mol, nbr_mask, ref_mask, n_bonds, grid, flags, ws, ws_bytes, vec, ctr, sum,
+                              cnt, mean, totals, nullptr, nullptr, stream);
 }
 
 int mouse_rdf_frame(const double *pos, const int32_t *type, const int32_t *mol, int64_t n_atoms, int32_t ntypes,

@@ -57,24 +57,44 @@ __device__ __forceinline__ void cell_axis(double c, double L, double cw, int nc,
   xw = x;
 }
 
+// payload of an item, written once in ORIGINAL order (16 + 32 contiguous bytes: the canonical gather then costs two
+// sectors per item).  P = FP32 copy of the wrapped coordinate, centred on the box (|x| <= L/2 keeps one more
+// mantissa bit) + code bits; U = FP64 unit bond vector (P2) / absolute position + molecule code (RDF).
+__device__ __forceinline__ float4 payload_p(double xw, double yw, double zw, const GridDev &g, int code) {
+  float4 p;
+  p.x = (float)(xw - 0.5 * g.box[0]);
+  p.y = (float)(yw - 0.5 * g.box[1]);
+  p.z = (float)(zw - 0.5 * g.box[2]);
+  p.w = __int_as_float(code);
+  return p;
+}
+__device__ __forceinline__ double4 payload_u_bond(double vx, double vy, double vz) {
+  double n2 = vx * vx + vy * vy + vz * vz;
+  double inv = 1.0 / sqrt(n2);
+  return make_double4(vx * inv, vy * inv, vz * inv, 0.0);
+}
+
 // One thread per item (bond midpoint or atom).  MODE 0: P2 (items = bonds, payload needs vec);
 // MODE 1: RDF (items = atoms, xyz AoS [n][3], sel = type code < 0 means not selected).
 template <int MODE>
 __global__ void __launch_bounds__(256) cell_assign_kernel(const double *__restrict__ xyz,
                                                           const double *__restrict__ vec,
                                                           const uint8_t *__restrict__ nbr_mask,
-                                                          const int32_t *__restrict__ type, int n, GridDev g,
+                                                          const int32_t *__restrict__ type,
+                                                          const int32_t *__restrict__ code2, int n, GridDev g,
                                                           int32_t *__restrict__ cell_of,
                                                           int32_t *__restrict__ rank_of,
                                                           int32_t *__restrict__ cell_count,
-                                                          int64_t *__restrict__ counters) {
+                                                          int64_t *__restrict__ counters,
+                                                          float4 *__restrict__ p_tmp, double4 *__restrict__ u_tmp) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
   bool in_list;
   double cx, cy, cz;
+  double vx = 0.0, vy = 0.0, vz = 0.0;
   if (MODE == 0) {
     in_list = nbr_mask ? (nbr_mask[b] != 0) : true;
-    double vx = vec[b], vy = vec[(size_t)n + b], vz = vec[2 * (size_t)n + b];
+    vx = vec[b], vy = vec[(size_t)n + b], vz = vec[2 * (size_t)n + b];
     if (in_list && vx == 0.0 && vy == 0.0 && vz == 0.0) {   // zero-length bond: never a reference
       atomicAdd((unsigned long long *)&counters[0], 1ULL);  // (:93,119), poisons as neighbour (:112)
       in_list = false;
@@ -93,13 +113,15 @@ __global__ void __launch_bounds__(256) cell_assign_kernel(const double *__restri
     return;
   }
   int kx, ky, kz;
-  double t;
-  cell_axis(cx, g.box[0], g.cw[0], g.nc[0], kx, t);
-  cell_axis(cy, g.box[1], g.cw[1], g.nc[1], ky, t);
-  cell_axis(cz, g.box[2], g.cw[2], g.nc[2], kz, t);
+  double xw, yw, zw;
+  cell_axis(cx, g.box[0], g.cw[0], g.nc[0], kx, xw);
+  cell_axis(cy, g.box[1], g.cw[1], g.nc[1], ky, yw);
+  cell_axis(cz, g.box[2], g.cw[2], g.nc[2], kz, zw);
   int cid = (kz * g.nc[1] + ky) * g.nc[0] + kx;
   cell_of[b] = cid;
   rank_of[b] = atomicAdd(&cell_count[cid], 1);
+  p_tmp[b] = payload_p(xw, yw, zw, g, type ? type[b] : 0);
+  u_tmp[b] = MODE == 0 ? payload_u_bond(vx, vy, vz) : make_double4(cx, cy, cz, code2 ? (double)code2[b] : 0.0);
 }
 
 // ---- exclusive scan of cell_count[0..nc) -> cell_start, three small kernels ----------------
@@ -192,111 +214,168 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(const int32_t *__restri
   }
 }
 
-// ---- scatter payload into arrival order ------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(256) cell_scatter_kernel(const double *__restrict__ xyz,
-                                                           const double *__restrict__ vec,
-                                                           const int32_t *__restrict__ code,
-                                                           const int32_t *__restrict__ code2,
-                                                           const uint8_t *__restrict__ ref_mask, int n,
-                                                           GridDev g, const int32_t *__restrict__ cell_of,
-                                                           const int32_t *__restrict__ rank_of,
-                                                           const int32_t *__restrict__ cell_start,
-                                                           float4 *__restrict__ p_tmp,
-                                                           double4 *__restrict__ u_tmp,
-                                                           int32_t *__restrict__ idx_tmp) {
+// ---- exclusive scan, second kernel of two: every block sums the tile totals in front of it (a few dozen values)
+// and scans its own tile
+__global__ void __launch_bounds__(256) scan_apply2_kernel(const int32_t *__restrict__ in, int nc,
+                                                          const int32_t *__restrict__ tile_sums,
+                                                          int32_t *__restrict__ out) {
+  __shared__ int s_warp[8];
+  __shared__ int s_off;
+  // offset of this tile = sum of the totals of all tiles before it
+  int part = 0;
+  for (int k = threadIdx.x; k < (int)blockIdx.x; k += 256) part += tile_sums[k];
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += s_warp[w];
+    s_off = t;
+  }
+  __syncthreads();
+  const int off = s_off;
+  __syncthreads();
+  int base = blockIdx.x * MOUSE_SCAN_TILE + threadIdx.x * 8;
+  int v[8];
+  int tsum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int c = base + k;
+    v[k] = c < nc ? in[c] : 0;
+    tsum += v[k];
+  }
+  int x = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(MOUSE_FULL_MASK, x, o);
+    if ((threadIdx.x & 31) >= o) x += y;
+  }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += s_warp[w];
+  int run = off + woff + x - tsum;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int c = base + k;
+    if (c < nc) out[c] = run;
+    run += v[k];
+  }
+}
+
+// ---- scatter the item index into its cell (arrival order); the payload moves once, in cell_canon_kernel -----
+__global__ void __launch_bounds__(256) cell_scatter_idx_kernel(const uint8_t *__restrict__ ref_mask, int n,
+                                                               const int32_t *__restrict__ cell_of,
+                                                               const int32_t *__restrict__ rank_of,
+                                                               const int32_t *__restrict__ cell_start,
+                                                               int32_t *__restrict__ idx_tmp) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
   int cid = cell_of[b];
   if (cid < 0) return;
-  int dst = cell_start[cid] + rank_of[b];
-  double cx, cy, cz;
-  if (MODE == 0) {
-    cx = xyz[b];
-    cy = xyz[(size_t)n + b];
-    cz = xyz[2 * (size_t)n + b];
-  } else {
-    cx = xyz[3 * (size_t)b];
-    cy = xyz[3 * (size_t)b + 1];
-    cz = xyz[3 * (size_t)b + 2];
-  }
-  int k;
-  double xi, yi, zi;
-  cell_axis(cx, g.box[0], g.cw[0], g.nc[0], k, xi);
-  cell_axis(cy, g.box[1], g.cw[1], g.nc[1], k, yi);
-  cell_axis(cz, g.box[2], g.cw[2], g.nc[2], k, zi);
-  // FP32 copy of the wrapped coordinate, centred on the box (|x| <= L/2 keeps one more mantissa bit)
-  float4 p;
-  p.x = (float)(xi - 0.5 * g.box[0]);
-  p.y = (float)(yi - 0.5 * g.box[1]);
-  p.z = (float)(zi - 0.5 * g.box[2]);
-  p.w = __int_as_float(code ? code[b] : 0);
-  double4 u;
-  if (MODE == 0) {
-    double vx = vec[b], vy = vec[(size_t)n + b], vz = vec[2 * (size_t)n + b];
-    double n2 = vx * vx + vy * vy + vz * vz;
-    double inv = 1.0 / sqrt(n2);
-    u = make_double4(vx * inv, vy * inv, vz * inv, n2);
-  } else {
-    u = make_double4(cx, cy, cz, code2 ? (double)code2[b] : 0.0);
-  }
-  p_tmp[dst] = p;
-  u_tmp[dst] = u;
   bool is_ref = ref_mask ? (ref_mask[b] != 0) : true;
-  idx_tmp[dst] = b | (is_ref ? (int32_t)0x80000000 : 0);
+  idx_tmp[cell_start[cid] + rank_of[b]] = b | (is_ref ? (int32_t)0x80000000 : 0);
 }
 
-// ---- canonical order inside each cell: ascending original index (one warp per cell) ----------
-__global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, const int32_t *__restrict__ cell_start,
+// ---- canonical order inside each cell (ascending original index, one warp per cell) + payload gather ---------
+// The items of a cell arrive in atomic order; ranking them by original index makes the sorted arrays - and with
+// them every floating-point sum of the sweeps - a deterministic function of the input.
+template <int MODE>
+__global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, int n, GridDev g,
+                                                         const int32_t *__restrict__ cell_start,
+                                                         const int32_t *__restrict__ idx_tmp,
                                                          const float4 *__restrict__ p_tmp,
                                                          const double4 *__restrict__ u_tmp,
-                                                         const int32_t *__restrict__ idx_tmp,
                                                          float4 *__restrict__ p_sorted,
                                                          double4 *__restrict__ u_sorted,
                                                          int32_t *__restrict__ idx_sorted,
                                                          int32_t *__restrict__ cell_sorted,
-                                                         uint8_t *__restrict__ flag_sorted, int pack_index) {
+                                                         uint8_t *__restrict__ flag_sorted,
+                                                         long long *__restrict__ acc_fix,
+                                                         int32_t *__restrict__ acc_cnt) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < ncell; c += warps) {
-    int s = cell_start[c], e = cell_start[c + 1];
-    int nc = e - s;
+    const int s = cell_start[c], e = cell_start[c + 1];
+    const int nc = e - s;
     if (nc <= 0) continue;
-    if (nc <= 32) {
-      int raw = lane < nc ? idx_tmp[s + lane] : 0x7fffffff;
-      int mine = raw & 0x7fffffff;
+    for (int m0 = 0; m0 < nc; m0 += 32) {
+      const int m = m0 + lane;
+      const int raw = m < nc ? idx_tmp[s + m] : 0x7fffffff;
+      const int mine = raw & 0x7fffffff;
       int rank = 0;
-      for (int k = 0; k < nc; ++k) {
-        int other = __shfl_sync(MOUSE_FULL_MASK, mine, k);
-        rank += other < mine;
-      }
-      if (lane < nc) {
-        int d = s + rank;
-        p_sorted[d] = p_tmp[s + lane];
-        double4 u = u_tmp[s + lane];
-        if (pack_index) u.w = __hiloint2double(0, d);   // the sweep's candidate registers carry their own slot
-        u_sorted[d] = u;
-        idx_sorted[d] = mine;
-        cell_sorted[d] = c;
-        flag_sorted[d] = (uint8_t)((unsigned)raw >> 31);
-      }
-    } else {
-      for (int m = lane; m < nc; m += 32) {
-        int raw = idx_tmp[s + m];
-        int mine = raw & 0x7fffffff;
-        int rank = 0;
+      if (nc <= 32) {
+        for (int k = 0; k < nc; ++k) {
+          const int other = __shfl_sync(MOUSE_FULL_MASK, mine, k);
+          rank += other < mine;
+        }
+      } else {
         for (int k = 0; k < nc; ++k) rank += (idx_tmp[s + k] & 0x7fffffff) < mine;
-        int d = s + rank;
-        p_sorted[d] = p_tmp[s + m];
-        double4 u = u_tmp[s + m];
-        if (pack_index) u.w = __hiloint2double(0, d);
+      }
+      if (m < nc) {
+        const int d = s + rank;
+        p_sorted[d] = p_tmp[mine];
+        double4 u = u_tmp[mine];
+        // .w carries the sorted slot itself: the sweep's register-resident candidates know where they live
+        if (MODE == 0) u.w = __hiloint2double(0, d);
         u_sorted[d] = u;
         idx_sorted[d] = mine;
         cell_sorted[d] = c;
         flag_sorted[d] = (uint8_t)((unsigned)raw >> 31);
+        acc_fix[d] = 0;      // the half-shell sweep's accumulators start (and are left) at zero
+        acc_cnt[d] = 0;
       }
     }
   }
+}
+
+// ---- K1 + cell assignment + output initialisation in one pass (mouse_p2_frame) -------------------------------
+__global__ void __launch_bounds__(256) bond_assign_kernel(const double *__restrict__ pos, const int2 *__restrict__ bonds,
+                                                          const int32_t *__restrict__ mol,
+                                                          const uint8_t *__restrict__ nbr_mask, int n, GridDev g,
+                                                          double *__restrict__ vec, double *__restrict__ ctr,
+                                                          int32_t *__restrict__ cell_of, int32_t *__restrict__ rank_of,
+                                                          int32_t *__restrict__ cell_count,
+                                                          int64_t *__restrict__ counters, float4 *__restrict__ p_tmp,
+                                                          double4 *__restrict__ u_tmp, double *__restrict__ out_sum,
+                                                          int32_t *__restrict__ out_cnt, double *__restrict__ out_mean) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  int2 ab = __ldg(bonds + b);
+  const double *p1 = pos + 3 * (size_t)ab.x;
+  const double *p2 = pos + 3 * (size_t)ab.y;
+  double vx, vy, vz, cx, cy, cz;
+  bond_axis(__ldg(p1), __ldg(p2), g.box[0], vx, cx);
+  bond_axis(__ldg(p1 + 1), __ldg(p2 + 1), g.box[1], vy, cy);
+  bond_axis(__ldg(p1 + 2), __ldg(p2 + 2), g.box[2], vz, cz);
+  vec[b] = vx;
+  vec[(size_t)n + b] = vy;
+  vec[2 * (size_t)n + b] = vz;
+  ctr[b] = cx;
+  ctr[(size_t)n + b] = cy;
+  ctr[2 * (size_t)n + b] = cz;
+  out_sum[b] = 0.0;
+  out_cnt[b] = 0;
+  out_mean[b] = __longlong_as_double(0x7ff8000000000000LL);
+  bool in_list = nbr_mask ? (nbr_mask[b] != 0) : true;
+  if (in_list && vx == 0.0 && vy == 0.0 && vz == 0.0) {   // zero-length bond: never a reference
+    atomicAdd((unsigned long long *)&counters[0], 1ULL);  // (:93,119), poisons as neighbour (:112)
+    in_list = false;
+  }
+  if (!in_list) {
+    cell_of[b] = -1;
+    return;
+  }
+  int kx, ky, kz;
+  double xw, yw, zw;
+  cell_axis(cx, g.box[0], g.cw[0], g.nc[0], kx, xw);
+  cell_axis(cy, g.box[1], g.cw[1], g.nc[1], ky, yw);
+  cell_axis(cz, g.box[2], g.cw[2], g.nc[2], kz, zw);
+  int cid = (kz * g.nc[1] + ky) * g.nc[0] + kx;
+  cell_of[b] = cid;
+  rank_of[b] = atomicAdd(&cell_count[cid], 1);
+  p_tmp[b] = payload_p(xw, yw, zw, g, mol ? mol[b] : 0);
+  u_tmp[b] = payload_u_bond(vx, vy, vz);
 }
 
 // ---- host-side launchers ------------------------------------------------------------------------
@@ -309,45 +388,75 @@ int mouse_launch_bond_build(const double *pos, const int32_t *bond_atoms, int64_
   return MOUSE_OK;
 }
 
+// exclusive scan of cell_count -> cell_start, then index scatter and canonical gather (shared by all cell builds)
+static int cell_build_tail(int mode, const uint8_t *ref_mask, int64_t n, const mouse_grid_t *grid, const GridDev &g,
+                           const Workspace &w, cudaStream_t st) {
+  int nc = grid->ncell + 1;
+  int tiles = (nc + MOUSE_SCAN_TILE - 1) / MOUSE_SCAN_TILE;
+  scan_reduce_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks);
+  MOUSE_LAUNCH_CHECK("scan_reduce_kernel");
+  if (tiles <= 4096) {   // the apply kernel sums the tile totals in front of its tile itself
+    scan_apply2_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start);
+    MOUSE_LAUNCH_CHECK("scan_apply2_kernel");
+  } else {
+    scan_top_kernel<<<1, 1024, 0, st>>>(w.scan_blocks, tiles);
+    MOUSE_LAUNCH_CHECK("scan_top_kernel");
+    scan_apply_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start);
+    MOUSE_LAUNCH_CHECK("scan_apply_kernel");
+  }
+  if (n > 0) {
+    unsigned nb = (unsigned)((n + 255) / 256);
+    cell_scatter_idx_kernel<<<nb, 256, 0, st>>>(ref_mask, (int)n, w.cell_of, w.rank_of, w.cell_start, w.idx_tmp);
+    MOUSE_LAUNCH_CHECK("cell_scatter_idx_kernel");
+    int blocks = (int)((((int64_t)grid->ncell * 32) + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    if (mode == 0)
+      cell_canon_kernel<0><<<blocks, 256, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.p_tmp, w.u_tmp,
+                                                   w.p_sorted, w.u_sorted, w.idx_sorted, w.cell_sorted,
+                                                   w.flag_sorted, w.acc_fix, w.acc_cnt);
+    else
+      cell_canon_kernel<1><<<blocks, 256, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.p_tmp, w.u_tmp,
+                                                   w.p_sorted, w.u_sorted, w.idx_sorted, w.cell_sorted,
+                                                   w.flag_sorted, w.acc_fix, w.acc_cnt);
+    MOUSE_LAUNCH_CHECK("cell_canon_kernel");
+  }
+  return MOUSE_OK;
+}
+
 // mode 0: xyz = ctr SoA [3][n], vec SoA, code = mol; mode 1: xyz = pos AoS [n][3], code = type, code2 = mol
 int mouse_launch_cell_build(int mode, const double *xyz, const double *vec, const int32_t *code,
                             const int32_t *code2, const uint8_t *nbr_mask, const uint8_t *ref_mask, int64_t n, const mouse_grid_t *grid,
                             const Workspace &w, cudaStream_t st) {
   GridDev g = mouse_grid_dev(grid);
-  int nc = grid->ncell + 1;
-  MOUSE_CUDA_CHECK(cudaMemsetAsync(w.cell_count, 0, sizeof(int32_t) * (size_t)nc, st));
-  MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, sizeof(int64_t) * 8, st));
+  // counters sit right in front of cell_count: one memset clears both
+  MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, (size_t)((char *)(w.cell_count + grid->ncell + 1) - (char *)w.counters), st));
   unsigned nb = (unsigned)((n + 255) / 256);
   if (n > 0) {
     if (mode == 0)
-      cell_assign_kernel<0><<<nb, 256, 0, st>>>(xyz, vec, nbr_mask, nullptr, (int)n, g, w.cell_of, w.rank_of,
-                                                w.cell_count, w.counters);
+      cell_assign_kernel<0><<<nb, 256, 0, st>>>(xyz, vec, nbr_mask, code, nullptr, (int)n, g, w.cell_of, w.rank_of,
+                                                w.cell_count, w.counters, w.p_tmp, w.u_tmp);
     else
-      cell_assign_kernel<1><<<nb, 256, 0, st>>>(xyz, nullptr, nullptr, code, (int)n, g, w.cell_of, w.rank_of,
-                                                w.cell_count, w.counters);
+      cell_assign_kernel<1><<<nb, 256, 0, st>>>(xyz, nullptr, nullptr, code, code2, (int)n, g, w.cell_of, w.rank_of,
+                                                w.cell_count, w.counters, w.p_tmp, w.u_tmp);
     MOUSE_LAUNCH_CHECK("cell_assign_kernel");
   }
-  int tiles = (nc + MOUSE_SCAN_TILE - 1) / MOUSE_SCAN_TILE;
-  scan_reduce_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks);
-  MOUSE_LAUNCH_CHECK("scan_reduce_kernel");
-  scan_top_kernel<<<1, 1024, 0, st>>>(w.scan_blocks, tiles);
-  MOUSE_LAUNCH_CHECK("scan_top_kernel");
-  scan_apply_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start);
-  MOUSE_LAUNCH_CHECK("scan_apply_kernel");
+  return cell_build_tail(mode, ref_mask, n, grid, g, w, st);
+}
+
+// K1 + K2 of mouse_p2_frame: bond vectors / midpoints, cell list, outputs initialised (sum 0, count 0, mean NaN)
+int mouse_launch_frame_build(const double *pos, const int32_t *bond_atoms, const int32_t *mol, const uint8_t *nbr_mask,
+                             const uint8_t *ref_mask, int64_t n, const mouse_grid_t *grid, const Workspace &w,
+                             double *vec, double *ctr, double *out_sum, int32_t *out_cnt, double *out_mean,
+                             cudaStream_t st) {
+  GridDev g = mouse_grid_dev(grid);
+  MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, (size_t)((char *)(w.cell_count + grid->ncell + 1) - (char *)w.counters), st));
   if (n > 0) {
-    if (mode == 0)
-      cell_scatter_kernel<0><<<nb, 256, 0, st>>>(xyz, vec, code, nullptr, ref_mask, (int)n, g, w.cell_of, w.rank_of,
-                                                 w.cell_start, w.p_tmp, w.u_tmp, w.idx_tmp);
-    else
-      cell_scatter_kernel<1><<<nb, 256, 0, st>>>(xyz, nullptr, code, code2, nullptr, (int)n, g, w.cell_of, w.rank_of,
-                                                 w.cell_start, w.p_tmp, w.u_tmp, w.idx_tmp);
-    MOUSE_LAUNCH_CHECK("cell_scatter_kernel");
-    int blocks = (int)((((int64_t)grid->ncell * 32) + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    if (blocks < 1) blocks = 1;
-    cell_canon_kernel<<<blocks, 256, 0, st>>>(grid->ncell, w.cell_start, w.p_tmp, w.u_tmp, w.idx_tmp, w.p_sorted,
-                                              w.u_sorted, w.idx_sorted, w.cell_sorted, w.flag_sorted, mode == 0);
-    MOUSE_LAUNCH_CHECK("cell_canon_kernel");
+    bond_assign_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pos, (const int2 *)bond_atoms, mol, nbr_mask, (int)n,
+                                                                     g, vec, ctr, w.cell_of, w.rank_of, w.cell_count,
+                                                                     w.counters, w.p_tmp, w.u_tmp, out_sum, out_cnt,
+                                                                     out_mean);
+    MOUSE_LAUNCH_CHECK("bond_assign_kernel");
   }
-  return MOUSE_OK;
+  return cell_build_tail(0, ref_mask, n, grid, g, w, st);
 }

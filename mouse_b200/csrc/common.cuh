@@ -40,12 +40,13 @@ struct Workspace {
   // per item, original order
   int32_t *cell_of;      // [n] cell id or -1 (not in the list)
   int32_t *rank_of;      // [n] arrival rank inside the cell (atomic order, canonicalised later)
-  // per item, cell-sorted (tmp = arrival order, final = ascending original index inside a cell)
-  float4 *p_tmp;         // [n] FP32 (wrapped coordinate - L/2) x,y,z + molecule/type code bits
-  double4 *u_tmp;        // [n] unit bond vector (FP64), .w = sorted slot index bits (P2)  /  absolute position + molecule code (RDF)
-  int32_t *idx_tmp;      // [n] original index
-  float4 *p_sorted;
-  double4 *u_sorted;
+  // per item, cell-sorted (ascending original index inside a cell)
+  float4 *p_tmp;         // [n] payload in ORIGINAL order (built by the assign kernel, gathered by the canon kernel)
+  double4 *u_tmp;        // [n]   ... p_tmp + u_tmp (48 B per item, contiguous) are reused after the build as the
+                         //       fast sweep's pair list (int2 entries) for the exact fixup kernel
+  int32_t *idx_tmp;      // [n] original index (| ref bit), arrival order
+  float4 *p_sorted;      // [n] FP32 (wrapped coordinate - L/2) x,y,z + molecule/type code bits
+  double4 *u_sorted;     // [n] unit bond vector (FP64), .w = sorted slot index bits (P2)  /  absolute position + molecule code (RDF)
   int32_t *idx_sorted;
   int32_t *cell_sorted;  // [n] cell id of each sorted slot
   uint8_t *flag_sorted;  // [n] bit0 = acts as reference
@@ -53,8 +54,9 @@ struct Workspace {
   long long *acc_fix;    // [n] sum of cos^2, 2^-47 fixed point (integer atomics: exact, order independent)
   int32_t *acc_cnt;      // [n] counted neighbours
   // scalars
-  int64_t *counters;     // [8]: 0 = zero-length bonds in the neighbour set, 1 = band re-checks,
-                         //      2 = reduce ticket, 3.. scratch
+  int64_t *counters;     // [32]: 0 zero-length bonds in the neighbour set, 1 exact re-decisions, 2 home-cell ticket /
+                         //       reduce ticket, 3 pair-list length / histogram overflow, 4 pair-list overflow flag,
+                         //       5 ticket and 6 histogram overflow of the fused finish + reduce
   double *partials;      // [3 * MOUSE_REDUCE_BLOCKS] block partials of the fused reduction
   double *edges;         // [MOUSE_MAX_BINS + 1] device copy of the RDF bin edges
   size_t bytes;
@@ -77,6 +79,7 @@ static inline Workspace mouse_carve(void *ws, int64_t n, int32_t ncell) {
 #define CARVE(field, type, count)                     \
   w.field = (type *)(base ? base + off : nullptr);    \
   off = mouse_align_up(off + sizeof(type) * (count), 256);
+  CARVE(counters, int64_t, 32)     // directly in front of cell_count: both are cleared by one memset
   CARVE(cell_count, int32_t, nc)
   CARVE(cell_start, int32_t, nc)
   CARVE(scan_blocks, int32_t, nsb)
@@ -92,7 +95,6 @@ static inline Workspace mouse_carve(void *ws, int64_t n, int32_t ncell) {
   CARVE(flag_sorted, uint8_t, nn)
   CARVE(acc_fix, long long, nn)
   CARVE(acc_cnt, int32_t, nn)
-  CARVE(counters, int64_t, 8)
   CARVE(partials, double, 3 * MOUSE_REDUCE_BLOCKS)
   CARVE(edges, double, MOUSE_MAX_BINS + 1)
 #undef CARVE

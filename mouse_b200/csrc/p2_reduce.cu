@@ -118,6 +118,179 @@ __global__ void __launch_bounds__(RED_THREADS) p2_reduce_kernel(
   }
 }
 
+// ---- fused finish + reduce (mouse_p2_frame, fast sweep): the half-shell sweep's fixed-point accumulators (per
+// sorted slot) are converted, written to out_sum / out_cnt / out_mean in original bond order, handed back zeroed,
+// and reduced to the totals in the same pass.  Deterministic: fixed slot ranges per block, fixed trees.
+struct FinishArgs {
+  long long *acc_fix;
+  int32_t *acc_cnt;
+  const int32_t *idx;
+  const uint8_t *flag;
+  const int32_t *cell_start;
+  int ncell;
+  int chunk;
+  double *out_sum;
+  int32_t *out_cnt;
+  double *out_mean;
+  double *partials;
+  int64_t *counters;
+  mouse_p2_totals_t *totals;
+};
+
+__global__ void __launch_bounds__(RED_THREADS) p2_finish_reduce_kernel(const FinishArgs a) {
+  __shared__ double s_sum[RED_THREADS / 32];
+  __shared__ long long s_refs[RED_THREADS / 32], s_pairs[RED_THREADS / 32];
+  __shared__ bool s_last;
+  const bool overflow = ((volatile int64_t *)a.counters)[4] != 0;   // the exact sweep wrote out_sum / out_cnt
+  const long long nzero = a.counters[0];
+  const int n_list = a.cell_start[a.ncell];
+  const int lo = blockIdx.x * a.chunk;
+  const int hi = min(n_list, lo + a.chunk);
+  long long *__restrict__ acc_fix = a.acc_fix;
+  int32_t *__restrict__ acc_cnt = a.acc_cnt;
+  const int32_t *__restrict__ idx = a.idx;
+  const uint8_t *__restrict__ flag = a.flag;
+  double acc = 0.0;
+  long long refs = 0, pairs = 0;
+  // four slots per thread and trip, all loads up front (memory-level parallelism)
+  for (int s0 = lo + threadIdx.x; s0 < hi; s0 += 4 * RED_THREADS) {
+    long long fix[4];
+    int c[4], o[4];
+    bool isref[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int s = s0 + q * RED_THREADS;
+      const bool in = s < hi;
+      fix[q] = in ? acc_fix[s] : 0;
+      c[q] = in ? acc_cnt[s] : 0;
+      o[q] = in ? idx[s] : 0;
+      isref[q] = in && (flag[s] & 1);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int s = s0 + q * RED_THREADS;
+      if (s < hi) {
+        acc_fix[s] = 0;
+        acc_cnt[s] = 0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (!isref[q]) continue;             // not a reference: outputs keep their initial 0 / 0 / NaN
+      double sum;
+      int cc = c[q];
+      if (overflow) {
+        sum = a.out_sum[o[q]];
+        cc = a.out_cnt[o[q]];
+      } else {
+        sum = (double)fix[q] * 7.105427357601002e-15;   // 2^-47
+        if (nzero) {   // zero-length bonds poison every mean and add to every count (ordering_functions.py:112)
+          sum = __longlong_as_double(0x7ff8000000000000LL);
+          cc += (int)nzero;
+        }
+        a.out_sum[o[q]] = sum;
+        a.out_cnt[o[q]] = cc;
+      }
+      if (cc > 0) {
+        const double m = __ddiv_rn(sum, (double)cc);
+        a.out_mean[o[q]] = m;
+        acc += m;
+        refs += 1;
+        pairs += cc;
+      }
+    }
+  }
+  acc = warp_sum(acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    refs += __shfl_xor_sync(MOUSE_FULL_MASK, refs, o);
+    pairs += __shfl_xor_sync(MOUSE_FULL_MASK, pairs, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_sum[threadIdx.x >> 5] = acc;
+    s_refs[threadIdx.x >> 5] = refs;
+    s_pairs[threadIdx.x >> 5] = pairs;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    long long r = 0, p = 0;
+    for (int w = 0; w < RED_THREADS / 32; ++w) {
+      t += s_sum[w];
+      r += s_refs[w];
+      p += s_pairs[w];
+    }
+    a.partials[3 * blockIdx.x] = t;
+    a.partials[3 * blockIdx.x + 1] = (double)r;   // exact: < 2^53
+    a.partials[3 * blockIdx.x + 2] = (double)p;
+    __threadfence();
+    unsigned long long ticket = atomicAdd((unsigned long long *)&a.counters[5], 1ULL);
+    s_last = (ticket == (unsigned long long)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double t = 0.0, r = 0.0, p = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += RED_THREADS) {
+      t += ((volatile double *)a.partials)[3 * b];
+      r += ((volatile double *)a.partials)[3 * b + 1];
+      p += ((volatile double *)a.partials)[3 * b + 2];
+    }
+    t = warp_sum(t);
+    r = warp_sum(r);
+    p = warp_sum(p);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+      s_sum[threadIdx.x >> 5] = t;
+      s_refs[threadIdx.x >> 5] = (long long)r;
+      s_pairs[threadIdx.x >> 5] = (long long)p;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tt = 0.0;
+      long long rr = 0, pp = 0;
+      for (int w = 0; w < RED_THREADS / 32; ++w) {
+        tt += s_sum[w];
+        rr += s_refs[w];
+        pp += s_pairs[w];
+      }
+      a.totals->sum_mean = tt;
+      a.totals->n_refs = rr;
+      a.totals->n_pairs = pp;
+      a.totals->n_zero_len = ((volatile int64_t *)a.counters)[0];
+      a.totals->n_band = ((volatile int64_t *)a.counters)[1];
+      a.totals->n_hist_over = 0;
+    }
+  }
+}
+
+int mouse_launch_p2_finish_reduce(int64_t n, const mouse_grid_t *grid, const Workspace &w, double *out_sum,
+                                  int32_t *out_cnt, double *out_mean, mouse_p2_totals_t *totals, cudaStream_t st) {
+  FinishArgs a;
+  a.acc_fix = w.acc_fix;
+  a.acc_cnt = w.acc_cnt;
+  a.idx = w.idx_sorted;
+  a.flag = w.flag_sorted;
+  a.cell_start = w.cell_start;
+  a.ncell = grid->ncell;
+  int blocks = (int)((n + RED_THREADS - 1) / RED_THREADS);
+  if (blocks > MOUSE_REDUCE_BLOCKS) blocks = MOUSE_REDUCE_BLOCKS;
+  if (blocks < 1) blocks = 1;
+  int chunk = (int)((n + blocks - 1) / blocks);
+  chunk = (chunk + RED_THREADS - 1) / RED_THREADS * RED_THREADS;
+  if (chunk < RED_THREADS) chunk = RED_THREADS;
+  a.chunk = chunk;
+  a.out_sum = out_sum;
+  a.out_cnt = out_cnt;
+  a.out_mean = out_mean;
+  a.partials = w.partials;
+  a.counters = w.counters;
+  a.totals = totals;
+  p2_finish_reduce_kernel<<<blocks, RED_THREADS, 0, st>>>(a);
+  MOUSE_LAUNCH_CHECK("p2_finish_reduce_kernel");
+  return MOUSE_OK;
+}
+
 int mouse_launch_p2_reduce(const double *sum, const int32_t *cnt, int64_t n, const Workspace &w, double *out_mean,
                            mouse_p2_totals_t *totals, int64_t *hist, double smin, double smax, int32_t nbins,
                            cudaStream_t st) {

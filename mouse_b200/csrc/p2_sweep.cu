@@ -624,16 +624,20 @@ __global__ void __launch_bounds__(256) p2_fixup_kernel(const SweepArgs a) {
   if (blockIdx.x == 0 && threadIdx.x == 0) a.counters[C_NFIX_DONE] = nfix;
 }
 
-// accumulators (sorted slots, fixed point) -> out_sum / out_cnt (original bond order)
+// accumulators (sorted slots, fixed point) -> out_sum / out_cnt (original bond order).  The accumulators are
+// handed back zeroed: the cell build zeroes them once, every sweep leaves them as it found them.
 __global__ void __launch_bounds__(256) p2_finish_kernel(const SweepArgs a) {
-  if (((volatile int64_t *)a.counters)[C_OVERFLOW]) return;
+  const bool overflow = ((volatile int64_t *)a.counters)[C_OVERFLOW] != 0;   // the exact sweep writes the outputs
   const int n_list = a.cell_start[a.g.ncell];
   const long long nzero = a.counters[C_NZERO];
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_list; s += gridDim.x * blockDim.x) {
-    if (!(a.flag[s] & 1)) continue;                 // not a reference: out stays 0 / 0
-    const int o = a.idx[s];
-    double sum = (double)a.acc_fix[s] * HS_FIX_INV;
+    const long long fix = a.acc_fix[s];
     int cnt = a.acc_cnt[s];
+    a.acc_fix[s] = 0;
+    a.acc_cnt[s] = 0;
+    if (overflow || !(a.flag[s] & 1)) continue;     // not a reference: out stays 0 / 0
+    const int o = a.idx[s];
+    double sum = (double)fix * HS_FIX_INV;
     // zero-length bonds in the neighbour set turn every mean into NaN and add to every count
     // (0/0 in ordering_functions.py:112)
     if (nzero) {
@@ -781,9 +785,12 @@ static void launch_half(const SweepArgs &a, bool excl_mol, cudaStream_t st) {
   else launch_half_one<SLOTS, false>(a, st);
 }
 
+// frame_mode 0: stand-alone sweep (outputs zeroed here, accumulators converted by p2_finish_kernel);
+// frame_mode 1: called from mouse_p2_frame - the outputs were initialised by the build and the caller converts the
+// accumulators in the fused finish + reduce kernel.  *used_fast tells the caller which path ran.
 int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const mouse_grid_t *grid, uint32_t flags,
                           const Workspace &w, double *out_sum, int32_t *out_cnt, const int64_t *row_ptr,
-                          int32_t *nbr_idx, cudaStream_t st) {
+                          int32_t *nbr_idx, int frame_mode, int *used_fast, cudaStream_t st) {
   SweepArgs a;
   a.g = mouse_grid_dev(grid);
   a.P = w.p_sorted;
@@ -802,48 +809,48 @@ int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const
   a.nbr_idx = nbr_idx;
   a.acc_fix = w.acc_fix;
   a.acc_cnt = w.acc_cnt;
-  // p_tmp / u_tmp (48 B per item, contiguous) are free after the cell build: the pair list of the fast sweep
-  a.fix_list = (int2 *)w.p_tmp;
+  a.fix_list = (int2 *)w.p_tmp;      // p_tmp / u_tmp are free once the cell list is built
   a.fix_cap = (long long)(((char *)w.idx_tmp - (char *)w.p_tmp) / sizeof(int2));
   a.same_molecule = (flags & MOUSE_SAME_MOLECULE) ? 1 : 0;
   a.no_cutoff = (flags & MOUSE_NO_CUTOFF) ? 1 : 0;
   a.only_if_overflow = 0;
   const bool lists = nbr_idx != nullptr;
-  if (n == 0) return MOUSE_OK;
-  if (!lists) {
-    MOUSE_CUDA_CHECK(cudaMemsetAsync(out_sum, 0, sizeof(double) * (size_t)n, st));
-  }
-  MOUSE_CUDA_CHECK(cudaMemsetAsync(out_cnt, 0, sizeof(int32_t) * (size_t)n, st));
-  // counters 1..4: diagnostics, home-cell ticket, pair list length, overflow flag (the reduce kernel resets
-  // the ticket again before using it)
-  MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters + 1, 0, 4 * sizeof(int64_t), st));
   const bool fast = grid->fast && !lists && !(flags & (MOUSE_FORCE_EXACT | MOUSE_NO_CUTOFF));
+  if (used_fast) *used_fast = fast ? 1 : 0;
+  if (n == 0) return MOUSE_OK;
+  if (!frame_mode) {
+    if (!lists) MOUSE_CUDA_CHECK(cudaMemsetAsync(out_sum, 0, sizeof(double) * (size_t)n, st));
+    MOUSE_CUDA_CHECK(cudaMemsetAsync(out_cnt, 0, sizeof(int32_t) * (size_t)n, st));
+    // counters 1..4: diagnostics, home-cell ticket, pair list length, overflow flag (the reduce kernel resets
+    // the ticket again before using it); a frame build has just cleared all of them
+    MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters + 1, 0, 4 * sizeof(int64_t), st));
+  }
   int blocks = (int)((n + 127) / 128);
   int maxb = num_sms() * 32;
   if (blocks > maxb) blocks = maxb;
   if (fast) {
-    // acc_fix and acc_cnt are adjacent in the workspace: one memset
-    MOUSE_CUDA_CHECK(cudaMemsetAsync(w.acc_fix, 0, (size_t)((char *)(w.acc_cnt + n) - (char *)w.acc_fix), st));
-    // SLOTS * 32 register-resident candidates per pass: size for the mean of the 14 half-shell cells + ~2 sigma
+    // SLOTS * 32 register-resident candidates per pass, sized from the mean of the 14 half-shell cells
     double mean = 14.0 * (double)n / (double)grid->ncell;
-    int need = (int)((mean + 2.0 * sqrt(mean) + 31.0) / 32.0);
-    int slots = need <= 4 ? 4 : need <= 8 ? 8 : 12;
+    int slots = mean <= 110.0 ? 4 : 6;
     if (mouse_fast_slots_override) slots = mouse_fast_slots_override;
     const bool excl = !a.same_molecule;
     switch (slots) {
       case 4: launch_half<4>(a, excl, st); break;
+      case 6: launch_half<6>(a, excl, st); break;
       case 8: launch_half<8>(a, excl, st); break;
       default: launch_half<12>(a, excl, st); break;
     }
     MOUSE_LAUNCH_CHECK("p2_sweep_half_kernel");
     if (mouse_fast_variant != 2) {   // variant 2 (debug): leave the undecided pairs out
-      p2_fixup_kernel<<<num_sms() * 2, 256, 0, st>>>(a);
+      p2_fixup_kernel<<<num_sms(), 256, 0, st>>>(a);
       MOUSE_LAUNCH_CHECK("p2_fixup_kernel");
     }
-    p2_finish_kernel<<<num_sms() * 8, 256, 0, st>>>(a);
-    MOUSE_LAUNCH_CHECK("p2_finish_kernel");
+    if (!frame_mode) {
+      p2_finish_kernel<<<num_sms() * 8, 256, 0, st>>>(a);
+      MOUSE_LAUNCH_CHECK("p2_finish_kernel");
+    }
     a.only_if_overflow = 1;          // pair list overflow (pathological inputs): redo the frame exactly
-    p2_sweep_exact_kernel<false><<<blocks, 128, 0, st>>>(a);
+    p2_sweep_exact_kernel<false><<<num_sms() * 4, 128, 0, st>>>(a);
     MOUSE_LAUNCH_CHECK("p2_sweep_exact_kernel");
   } else {
     if (lists)

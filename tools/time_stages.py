@@ -62,9 +62,9 @@ def main():
         med, mn = timeit(fn)
         print("%-12s median %.3f ms  min %.3f ms" % (name, med, mn))
     pairs = int(tot.cpu()[2])
-    for R in (1, 2):      # 2 = without the fixup kernel
+    for R in (1,):
         L.mouse_set_tuning(b"fast_variant", R)
-        for slots in (4, 8, 12):
+        for slots in (4, 6, 8):
             L.mouse_set_tuning(b"fast_slots", slots)
             med, mn = timeit(stages["p2_sweep"])
             print("sweep variant=%d slots=%-2d median %.3f ms  min %.3f ms  -> %.3e pairs/s" % (R, slots, med, mn, pairs / (mn * 1e-3)))
