@@ -36,19 +36,53 @@ N_FRAME_VARIANTS = 4              # distinct frames cycled (working set per fram
 
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  In-process NVML (nvidia_ml_py) on a thread:
+    a query costs microseconds and does not stall kernel launches the way a polling `nvidia-smi -lms` child does
+    (observed: tens of ms of blocked submission per query); falls back to nvidia-smi when NVML is unavailable."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.samples, self.proc = index, [], None
+    def __init__(self, index, period=0.01):
+        self.index, self.samples, self.proc, self.period = index, [], None, period
+        self._stop = threading.Event()
+        self._thread = None
+        self.how = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        r = int(reasons_fn(h))
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        act = lambda k: "Active" if r & bits[k] else "Not Active"  # noqa: E731
+                        self.samples.append([str(sm), str(mx), "%.1f" % pw, act("hw_slowdown"), act("hw_thermal_slowdown"),
+                                             act("sw_thermal_slowdown"), act("sw_power_cap")])
+                    except Exception:
+                        pass
+                    self._stop.wait(self.period)
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+            self.how = "nvml"
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            self.how = "nvidia-smi"
         except OSError:
             self.proc = None
 
@@ -59,6 +93,9 @@ class ClockSampler:
                 self.samples.append(p)
 
     def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=1.0)
         if self.proc:
             self.proc.terminate()
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
@@ -68,7 +105,7 @@ class ClockSampler:
             if any(s[k].lower().startswith("active") for s in self.samples):
                 reasons.append(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "how": self.how}
 
 
 # ------------------------------------------------------------------------------------------- reference arm
@@ -227,12 +264,27 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timed region (value)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(local_rank, period=float(os.environ.get("MOUSE_BENCH_CLOCK_PERIOD", "0.01")))
+    if rank == 0 and not os.environ.get("MOUSE_BENCH_NOSAMPLER"):
         sampler.start()          # NVML start-up perturbs the GPU for a few ms: start well before timing
         time.sleep(1.0)
-    for k in range(warm):
-        frame(k)
+    # warm-up: at least `warm` frames AND at least 0.3 s of back-to-back frames, so that the timed region measures the
+    # steady state of a trajectory run (clocks / power state settled), not the first milliseconds after idle
+    t_spin = time.perf_counter() + 0.3
+    k = 0
+    while k < warm or time.perf_counter() < t_spin:
+        frame(k % warm)
+        k += 1
+        if k % 16 == 0:
+            torch.cuda.synchronize()
+    warm_done = k
+    # the tail of the timed region (sum of the per-frame totals + the path's only collective) is warmed up too:
+    # the first call of a torch kernel / NCCL collective pays one-off module loading and communicator set-up
+    _w = tot[:warm].sum(dim=0)
+    if world > 1:
+        _wf = tot[:warm, 0].view(torch.float64).sum().reshape(1)
+        dist.all_reduce(_wf)
+        dist.all_reduce(_w)
     barrier()
     n_before = len(sampler.samples)
     e0, e1 = ev(), ev()
@@ -254,6 +306,11 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
     sweep_ms = float(np.mean([a.elapsed_time(b) for a, b in sweep_ev]))
+    if os.environ.get("MOUSE_BENCH_DIAG"):
+        gaps = [sweep_ev[i][0].elapsed_time(sweep_ev[i + 1][0]) for i in range(steps - 1)]
+        sys.stderr.write("frame-to-frame ms: " + " ".join("%.2f" % g for g in gaps) + "\n")
+        sys.stderr.write("first sweep start after e0: %.3f ms; last sweep end to e1: %.3f ms\n" % (
+            e0.elapsed_time(sweep_ev[0][0]), sweep_ev[-1][1].elapsed_time(e1)))
     tl = tot[warm:].cpu()
     pairs_local = int(tl[:, 2].sum())
     pairs_all = int(tsum[2].item()) if world > 1 else pairs_local
@@ -306,7 +363,7 @@ def run_ours(args):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         build_ms = ms / steps - sweep_ms
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm_done,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 (packed FP32 cutoff filter with exact FP64 re-check, FP64 cos^2, 2^-47 fixed-point sums)", "data": "synthetic",
             "config": {"workload": WORKLOAD["name"], "bonds_per_frame": n, "frames_per_step_per_gpu": 1,
