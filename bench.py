@@ -358,6 +358,13 @@ def run_ours(args):
         except OSError:
             pass
         f_clk = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        traffic, traffic_src = None, None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the sweep kernel (ncu --set full capture)
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_sweep_half_v2.json")))
+            traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
+            traffic_src = prof["source"]
+        except (OSError, KeyError, ValueError):
+            pass
         peak_issue = sms * 128 * f_clk * 1e6                       # lane-instructions / s
         sweep_pairs_s = (pairs_local / steps) / (sweep_ms * 1e-3)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -384,7 +391,7 @@ def run_ours(args):
                 "achieved": sweep_pairs_s * W_LANE_INSTR_PER_PAIR / 1e12,
                 "peak": peak_issue / 1e12, "unit": "Tlane-instr/s",
                 "frac": sweep_pairs_s * W_LANE_INSTR_PER_PAIR / peak_issue,
-                "traffic": None,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "how": "SURVEY 8(d): ordered pairs/s x 55.2 lane-instr/pair (full-shell bound; the kernel is half-shell: "
                        "every unordered pair is decided once and counted for both partners) over SMs x 128 lanes x f_clk "
                        "(%d SMs, %.0f MHz %s); sweep %.3f ms/launch (CUDA events, in the timed region)"
