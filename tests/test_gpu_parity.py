@@ -284,3 +284,107 @@ def test_cli_matches_reference_output(capsys):
     cli.main([os.path.join(GOLDEN_DIR, "melt_290.data"), "--bondtypes", "1", "--max", "1.5"])
     out = capsys.readouterr().out.strip()
     assert abs(float(out) - float(g["ref_S"])) <= RTOL * abs(float(g["ref_S"]))
+
+
+# ------------------------------------------------------------------------------- half-shell sweep corner cases
+def _bonds_from_midpoints(ctr, vec):
+    """Positions / bond table for bonds given by midpoint and vector (two private atoms per bond)."""
+    n = len(ctr)
+    pos = np.empty((2 * n, 3))
+    pos[0::2] = ctr - 0.5 * vec
+    pos[1::2] = ctr + 0.5 * vec
+    bonds = np.stack([np.arange(0, 2 * n, 2), np.arange(1, 2 * n, 2)], axis=1).astype(np.int32)
+    return pos, bonds
+
+
+def _sweep_counters(res, n):
+    """The workspace counters left behind by the last frame (0 zero-length, 1 exact re-decisions, 3 pair-list
+    length, 4 pair-list overflow flag)."""
+    import ctypes as C
+    from mouse_b200 import _lib, engine
+    L = _lib.lib()
+    ws = engine.workspace(L.mouse_workspace_bytes(n, C.byref(res.grid)), res.sum.device)
+    out = (C.c_int64 * 8)()
+    _lib.check(L.mouse_debug_counters(C.byref(res.grid), n, engine._ptr(ws), out, engine._stream()), "debug_counters")
+    return list(out)
+
+
+def _check_against_c_oracle(pos, bonds, mol, box, rc, same=True, nbr=None, ref=None):
+    from oracle import c_oracle
+    eng = _engine()
+    res = eng.p2_frame(pos, bonds, mol, box, rc, same_molecule=same, nbr_mask=nbr, ref_mask=ref)
+    assert res.grid.fast == 1
+    vec, ctr = c_oracle.bond_build(pos, bonds, box)
+    ora = c_oracle.p2(vec, ctr, mol, box, rc, same, ref_mask=ref, nbr_mask=nbr)
+    assert np.array_equal(res.count.cpu().numpy().astype(np.int64), ora["count"])
+    ok = ora["count"] > 0
+    np.testing.assert_allclose(res.mean.cpu().numpy()[ok], ora["mean"][ok], rtol=1e-12, atol=ATOL_MEAN)
+    assert res.totals_dict()["n_pairs"] == int(ora["count"].sum())
+    return res, ora
+
+
+def test_dense_cluster_oversize_home_cells_and_many_passes():
+    """One cell holds far more bonds than the fast sweep keeps in shared memory / registers: those home cells are
+    decided pair by pair through the pair list, their neighbours take several candidate passes."""
+    rng = np.random.default_rng(5)
+    box = np.array([24.0, 24.0, 24.0])
+    n_bg, n_cl = 20000, 150          # 15^3 cells of edge 1.6; the cluster sits in the middle of one of them
+    ctr = np.concatenate([rng.uniform(-12, 12, (n_bg, 3)), rng.normal(0.8, 0.2, (n_cl, 3))])
+    vec = rng.normal(size=(len(ctr), 3))
+    vec *= 0.97 / np.linalg.norm(vec, axis=1)[:, None]
+    pos, bonds = _bonds_from_midpoints(ctr, vec)
+    mol = (np.arange(len(ctr)) // 7).astype(np.int32)
+    for same in (True, False):
+        res, ora = _check_against_c_oracle(pos, bonds, mol, box, 1.5, same)
+        assert ora["count"].max() > 140        # the cluster really is dense
+        c = _sweep_counters(res, len(bonds))
+        assert c[4] == 0 and c[3] > 5000       # the oversized home cell went through the pair list, no overflow
+
+
+def test_pair_list_overflow_falls_back_to_the_exact_sweep():
+    """Four bonds on every site of a cubic lattice, cutoff exactly the lattice constant: 24 neighbours of every bond
+    sit exactly on the cutoff, the fast sweep's pair list overflows and the frame is recomputed in FP64.
+    Perpendicular bonds exercise the cos^2 == 0 mask at the same time."""
+    m, a = 6, 1.0
+    g = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3) * a - 0.5 * m * a + 0.25
+    dirs = np.array([[1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0], [1.0, 1.0, 0]]) * 0.5
+    ctr = np.repeat(g, 4, axis=0)
+    vec = np.tile(dirs, (len(g), 1))
+    pos, bonds = _bonds_from_midpoints(ctr, vec)
+    box = np.array([m * a] * 3)
+    mol = np.arange(len(ctr), dtype=np.int32)
+    res, ora = _check_against_c_oracle(pos, bonds, mol, box, a, True)
+    assert ora["count"].min() >= 1
+    assert _sweep_counters(res, len(bonds))[4] == 1     # the pair list did overflow
+
+
+@pytest.mark.parametrize("same", [True, False])
+def test_three_cells_per_axis_and_masks(same):
+    """Smallest grid the fast sweep accepts (3 x 3 x 3 cells: every neighbour cell is a periodic image of another)
+    combined with neighbour / reference selections."""
+    from mouse_b200.melt import make_melt
+    melt = make_melt(12, 40, seed=9)
+    rc = float(melt.box[0]) / 3.3
+    rng = np.random.default_rng(1)
+    nbr = (rng.random(melt.n_bonds) < 0.8).astype(np.uint8)
+    ref = (rng.random(melt.n_bonds) < 0.5).astype(np.uint8) & nbr
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    res, _ = _check_against_c_oracle(melt.positions, melt.bond_atoms, molb, melt.box, rc, same, nbr=nbr, ref=ref)
+    assert list(res.grid.ncell_axis) == [3, 3, 3]
+
+
+def test_frame_and_staged_paths_agree():
+    """mouse_p2_frame (fused build / finish) and the staged entry points give the same per-bond results."""
+    import ctypes as C
+    from mouse_b200 import _lib
+    from mouse_b200.melt import make_melt
+    melt = make_melt(60, 51, seed=3)
+    eng = _engine()
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    a = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, 2.0)
+    b = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, 2.0, hist_args=(-0.5, 1.0, 75))   # staged calls
+    assert torch.equal(a.count, b.count) and torch.equal(a.sum, b.sum)
+    assert torch.equal(a.vec, b.vec) and torch.equal(a.ctr, b.ctr)
+    assert a.totals_dict()["n_pairs"] == b.totals_dict()["n_pairs"] and a.totals_dict()["n_refs"] == b.totals_dict()["n_refs"]
+    assert abs(a.order_parameter() - b.order_parameter()) < 1e-13
+    assert int(b.hist.sum()) == b.totals_dict()["n_refs"]
