@@ -242,6 +242,9 @@ int mouse_rdf_frame(const double *pos, const int32_t *type, const int32_t *mol, 
   cudaStream_t st = (cudaStream_t)stream;
   MOUSE_CUDA_CHECK(cudaMemcpyAsync(w.edges, edges, sizeof(double) * (size_t)(nbin + 1), cudaMemcpyHostToDevice, st));
   if ((rc = mouse_launch_cell_build(1, pos, nullptr, type, mol, nullptr, nullptr, n_atoms, grid, w, st))) return rc;
+  w.rdf_first = edges[0];
+  // the fast sweep's cutoff is the last edge: it needs a grid planned for exactly that cutoff
+  if (!(grid->rcut == edges[nbin]) || !(edges[nbin] > edges[0])) flags |= MOUSE_FORCE_EXACT;
   return mouse_launch_rdf_sweep(grid, flags, n_atoms, ntypes, w.edges, nbin, w, hist, st);
 }
 

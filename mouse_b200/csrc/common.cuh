@@ -59,6 +59,8 @@ struct Workspace {
                          //       5 ticket and 6 histogram overflow of the fused finish + reduce
   double *partials;      // [3 * MOUSE_REDUCE_BLOCKS] block partials of the fused reduction
   double *edges;         // [MOUSE_MAX_BINS + 1] device copy of the RDF bin edges
+  double *thr;           // [MOUSE_MAX_BINS + 2] the edges as exact thresholds on d^2 (fast RDF sweep)
+  double rdf_first;      // (host value, not a buffer) first bin edge of the current RDF call
   size_t bytes;
 };
 
@@ -97,6 +99,8 @@ static inline Workspace mouse_carve(void *ws, int64_t n, int32_t ncell) {
   CARVE(acc_cnt, int32_t, nn)
   CARVE(partials, double, 3 * MOUSE_REDUCE_BLOCKS)
   CARVE(edges, double, MOUSE_MAX_BINS + 1)
+  CARVE(thr, double, MOUSE_MAX_BINS + 2)
+  w.rdf_first = 0.0;
 #undef CARVE
   w.bytes = off;
   return w;

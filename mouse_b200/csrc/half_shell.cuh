@@ -1,0 +1,153 @@
+// Shared machinery of the half-shell sweeps (P2: p2_sweep.cu, RDF: rdf_sweep.cu): one warp per home cell, the
+// candidates of the home cell and its 13 forward neighbour cells are contiguous ranges of the cell-sorted arrays,
+// fetched with 1-D TMA bulk copies; the range table itself comes through a cp.async software pipeline.
+#pragma once
+#include "common.cuh"
+
+// ------------------------------------------------------------------ PTX: mbarrier + 1-D TMA bulk copy
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MB_DONE;\n"
+      "bra MB_WAIT;\n"
+      "MB_DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA unit), completion counted in bytes on `bar`; 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+struct HsItem {
+  int home, hs, nhome, T;   // home cell, its first sorted slot, its bonds, candidates of the 14 cells
+  int rsrc, rlen, rt;       // lane L < 10: range L of the candidate concatenation (first slot, length, offset t)
+  float hx, hy, hz;         // home cell centre (frame of the stored FP32 coordinates)
+  int boundary;             // some neighbour cell is a periodic image
+};
+
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Range table of home cell tk.  Rows of the forward half shell: (dy,dz) = (0,0) cells x..x+1 (home first), (1,0),
+// (-1,1), (0,1), (1,1) cells x-1..x+1; a row that crosses the periodic boundary in x splits into two ranges
+// (part 0 / part 1).  Lane L < 10 owns range L = 2 * row + part: cells [lo, hi] of row base rb (empty when lo > hi).
+// tk -> (cx, cy, cz) without integer division: multiply-high by floor(2^32 / d), then at most two corrections
+__device__ __forceinline__ void hs_divmod(unsigned n, unsigned d, unsigned magic, int &q, int &r) {
+  unsigned qq = __umulhi(n, magic);
+  unsigned rr = n - qq * d;
+  if (rr >= d) {
+    rr -= d;
+    qq += 1;
+  }
+  if (rr >= d) {
+    rr -= d;
+    qq += 1;
+  }
+  q = (int)qq;
+  r = (int)rr;
+}
+__device__ __forceinline__ void hs_cell_coords(const GridDev &g, int tk, int &cx, int &cy, int &cz) {
+  int rem;
+  hs_divmod((unsigned)tk, (unsigned)(g.nc[0] * g.nc[1]), g.magic_xy, cz, rem);
+  hs_divmod((unsigned)rem, (unsigned)g.nc[0], g.magic_x, cy, cx);
+}
+
+__device__ __forceinline__ void hs_range_cells(const GridDev &g, int cx, int cy, int cz, int lane, int &rb, int &lo,
+                                               int &hi) {
+  const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
+  const int row = lane >> 1, part = lane & 1;
+  const int dy = (row == 1 || row == 4) ? 1 : (row == 2 ? -1 : 0);
+  const int dz = row >= 2 ? 1 : 0;
+  int yc = cy + dy, zc = cz + dz;
+  yc += yc < 0 ? ny : 0;
+  yc -= yc >= ny ? ny : 0;
+  zc -= zc >= nz ? nz : 0;
+  rb = (zc * ny + yc) * nx;
+  const int xa = row == 0 ? cx : cx - 1, xb = cx + 1;
+  if (xa < 0) {
+    lo = part ? 0 : nx - 1;
+    hi = part ? xb : nx - 1;
+  } else if (xb >= nx) {
+    lo = part ? 0 : xa;
+    hi = part ? xb - nx : nx - 1;
+  } else {
+    lo = part ? 1 : xa;
+    hi = part ? 0 : xb;
+  }
+}
+
+// fetch stage 2: start the loads of home cell tk's range table (cell_start entries) into s_raw, asynchronously
+__device__ __forceinline__ void hs_raw_issue(const GridDev &g, const int32_t *__restrict__ cell_start, int lane,
+                                             int tk, int (*s_raw)[32]) {
+  int cx, cy, cz;
+  hs_cell_coords(g, tk, cx, cy, cz);
+  if (lane == 12) {
+    s_raw[2][12] = cx;
+    s_raw[2][13] = cy;
+    s_raw[2][14] = cz;
+  }
+  if (lane < 10) {
+    int rb, lo, hi;
+    hs_range_cells(g, cx, cy, cz, lane, rb, lo, hi);
+    if (lo <= hi) {
+      cp_async4(&s_raw[0][lane], cell_start + rb + lo);
+      cp_async4(&s_raw[1][lane], cell_start + rb + hi + 1);
+    }
+    s_raw[2][lane] = lo <= hi;
+  } else if (lane < 12) {
+    cp_async4(&s_raw[0][lane], cell_start + tk + (lane - 10));   // lanes 10, 11: the home cell itself
+  }
+  cp_async_commit();
+}
+
+// fetch stage 3: the table of home cell tk has landed in s_raw; false when the cell is empty
+__device__ __forceinline__ bool hs_finalize(const GridDev &g, int lane, int tk, int (*s_raw)[32], HsItem &it) {
+  cp_async_wait_all();
+  __syncwarp();
+  const int hs = s_raw[0][10], he = s_raw[0][11];
+  const bool has = lane < 10 && s_raw[2][lane] != 0;
+  const int src = has ? s_raw[0][lane] : 0;
+  const int len = has ? s_raw[1][lane] - src : 0;
+  const int cx = s_raw[2][12], cy = s_raw[2][13], cz = s_raw[2][14];
+  __syncwarp();
+  int incl = len;
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) {
+    const int y = __shfl_up_sync(MOUSE_FULL_MASK, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
+  it.home = tk;
+  it.hs = hs;
+  it.nhome = he - hs;
+  it.T = __shfl_sync(MOUSE_FULL_MASK, incl, 15);
+  it.rsrc = src;
+  it.rlen = len;
+  it.rt = incl - len;
+  it.hx = ((float)cx + 0.5f) * g.cwf[0] - 0.5f * g.boxf[0];
+  it.hy = ((float)cy + 0.5f) * g.cwf[1] - 0.5f * g.boxf[1];
+  it.hz = ((float)cz + 0.5f) * g.cwf[2] - 0.5f * g.boxf[2];
+  it.boundary = (cx == 0) | (cx == nx - 1) | (cy == 0) | (cy == ny - 1) | (cz == nz - 1);
+  return he > hs;
+}
+

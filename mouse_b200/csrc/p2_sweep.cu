@@ -19,7 +19,7 @@
 //    expression per candidate.  Valid for ANY grid (fewer than 3 cells on an axis, rcut < 0,
 //    rmax == 0 -> half diagonal); it also extracts the pair lists and is the automatic fallback when
 //    the pair list of the fast path overflows.
-#include "common.cuh"
+#include "half_shell.cuh"
 
 struct SweepArgs {
   GridDev g;
@@ -71,37 +71,6 @@ __device__ __forceinline__ double exact_pair(const int32_t *__restrict__ idx, co
   return __ddiv_rn(__ddiv_rn(__dmul_rn(dot, dot), nr), nj);
 }
 
-// ------------------------------------------------------------------ PTX: mbarrier + 1-D TMA bulk copy
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "MB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra MB_DONE;\n"
-      "bra MB_WAIT;\n"
-      "MB_DONE:\n"
-      "}\n" ::"r"(smem_addr(bar)),
-      "r"(parity)
-      : "memory");
-}
-// global -> shared bulk copy (TMA unit), completion counted in bytes on `bar`; 16-byte aligned, size % 16 == 0
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_addr(dst)),
-               "l"(src), "r"(bytes), "r"(smem_addr(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
 // ------------------------------------------------------------------ half-shell fast sweep
 #define HS_MAXHOME 96      // home cells with more bonds are decided pair by pair by p2_fixup_kernel
 #define HS_MAXPASS 8       // ... and home cells with more than HS_MAXPASS * SLOTS * 32 candidates
@@ -113,13 +82,6 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 #define HS_NEARZ 1e-9                      // |u_i . u_j| below this is decided exactly (:113)
 #define HS_NEARZ_HI 0x3e112e0b             // high word of 1e-9
 #define HS_PAD 1.0e18f                     // coordinate of an empty slot
-
-struct HsItem {
-  int home, hs, nhome, T;   // home cell, its first sorted slot, its bonds, candidates of the 14 cells
-  int rsrc, rlen, rt;       // lane L < 10: range L of the candidate concatenation (first slot, length, offset t)
-  float hx, hy, hz;         // home cell centre (frame of the stored FP32 coordinates)
-  int boundary;             // some neighbour cell is a periodic image
-};
 
 __device__ __forceinline__ void fix_append(int64_t *counters, int2 *fix_list, long long fix_cap, int si, int sj,
                                            int kind) {
@@ -145,114 +107,6 @@ __device__ __noinline__ void hs_oversize(const float4 *__restrict__ P, int64_t *
       }
     }
   }
-}
-
-__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// Range table of home cell tk.  Rows of the forward half shell: (dy,dz) = (0,0) cells x..x+1 (home first), (1,0),
-// (-1,1), (0,1), (1,1) cells x-1..x+1; a row that crosses the periodic boundary in x splits into two ranges
-// (part 0 / part 1).  Lane L < 10 owns range L = 2 * row + part: cells [lo, hi] of row base rb (empty when lo > hi).
-// tk -> (cx, cy, cz) without integer division: multiply-high by floor(2^32 / d), then at most two corrections
-__device__ __forceinline__ void hs_divmod(unsigned n, unsigned d, unsigned magic, int &q, int &r) {
-  unsigned qq = __umulhi(n, magic);
-  unsigned rr = n - qq * d;
-  if (rr >= d) {
-    rr -= d;
-    qq += 1;
-  }
-  if (rr >= d) {
-    rr -= d;
-    qq += 1;
-  }
-  q = (int)qq;
-  r = (int)rr;
-}
-__device__ __forceinline__ void hs_cell_coords(const GridDev &g, int tk, int &cx, int &cy, int &cz) {
-  int rem;
-  hs_divmod((unsigned)tk, (unsigned)(g.nc[0] * g.nc[1]), g.magic_xy, cz, rem);
-  hs_divmod((unsigned)rem, (unsigned)g.nc[0], g.magic_x, cy, cx);
-}
-
-__device__ __forceinline__ void hs_range_cells(const GridDev &g, int cx, int cy, int cz, int lane, int &rb, int &lo,
-                                               int &hi) {
-  const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
-  const int row = lane >> 1, part = lane & 1;
-  const int dy = (row == 1 || row == 4) ? 1 : (row == 2 ? -1 : 0);
-  const int dz = row >= 2 ? 1 : 0;
-  int yc = cy + dy, zc = cz + dz;
-  yc += yc < 0 ? ny : 0;
-  yc -= yc >= ny ? ny : 0;
-  zc -= zc >= nz ? nz : 0;
-  rb = (zc * ny + yc) * nx;
-  const int xa = row == 0 ? cx : cx - 1, xb = cx + 1;
-  if (xa < 0) {
-    lo = part ? 0 : nx - 1;
-    hi = part ? xb : nx - 1;
-  } else if (xb >= nx) {
-    lo = part ? 0 : xa;
-    hi = part ? xb - nx : nx - 1;
-  } else {
-    lo = part ? 1 : xa;
-    hi = part ? 0 : xb;
-  }
-}
-
-// fetch stage 2: start the loads of home cell tk's range table (cell_start entries) into s_raw, asynchronously
-__device__ __forceinline__ void hs_raw_issue(const SweepArgs &a, int lane, int tk, int (*s_raw)[32]) {
-  int cx, cy, cz;
-  hs_cell_coords(a.g, tk, cx, cy, cz);
-  if (lane == 12) {
-    s_raw[2][12] = cx;
-    s_raw[2][13] = cy;
-    s_raw[2][14] = cz;
-  }
-  if (lane < 10) {
-    int rb, lo, hi;
-    hs_range_cells(a.g, cx, cy, cz, lane, rb, lo, hi);
-    if (lo <= hi) {
-      cp_async4(&s_raw[0][lane], a.cell_start + rb + lo);
-      cp_async4(&s_raw[1][lane], a.cell_start + rb + hi + 1);
-    }
-    s_raw[2][lane] = lo <= hi;
-  } else if (lane < 12) {
-    cp_async4(&s_raw[0][lane], a.cell_start + tk + (lane - 10));   // lanes 10, 11: the home cell itself
-  }
-  cp_async_commit();
-}
-
-// fetch stage 3: the table of home cell tk has landed in s_raw; false when the cell is empty
-__device__ __forceinline__ bool hs_finalize(const SweepArgs &a, int lane, int tk, int (*s_raw)[32], HsItem &it) {
-  cp_async_wait_all();
-  __syncwarp();
-  const int hs = s_raw[0][10], he = s_raw[0][11];
-  const bool has = lane < 10 && s_raw[2][lane] != 0;
-  const int src = has ? s_raw[0][lane] : 0;
-  const int len = has ? s_raw[1][lane] - src : 0;
-  const int cx = s_raw[2][12], cy = s_raw[2][13], cz = s_raw[2][14];
-  __syncwarp();
-  int incl = len;
-#pragma unroll
-  for (int o = 1; o < 16; o <<= 1) {
-    const int y = __shfl_up_sync(MOUSE_FULL_MASK, incl, o);
-    if (lane >= o) incl += y;
-  }
-  const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
-  it.home = tk;
-  it.hs = hs;
-  it.nhome = he - hs;
-  it.T = __shfl_sync(MOUSE_FULL_MASK, incl, 15);
-  it.rsrc = src;
-  it.rlen = len;
-  it.rt = incl - len;
-  it.hx = ((float)cx + 0.5f) * a.g.cwf[0] - 0.5f * a.g.boxf[0];
-  it.hy = ((float)cy + 0.5f) * a.g.cwf[1] - 0.5f * a.g.boxf[1];
-  it.hz = ((float)cz + 0.5f) * a.g.cwf[2] - 0.5f * a.g.boxf[2];
-  it.boundary = (cx == 0) | (cx == nx - 1) | (cy == 0) | (cy == ny - 1) | (cz == nz - 1);
-  return he > hs;
 }
 
 // all-ones when x < y (FSET: one instruction, no predicate register)
@@ -428,7 +282,9 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
   // arm the landing zone with pass `pass` of item `it`: candidates [pass * NC, min(T, pass * NC + NC))
   auto issue = [&](const HsItem &it, int pass) {
     const int w0 = pass * NC, w1 = min(it.T, w0 + NC);
-    fence_proxy_async();     // the generic-proxy reads of the previous contents are done (WAR across proxies)
+    // WAR on the landing zone: every lane's shared-memory reads of the previous contents were issued before the
+    // __syncwarp() that precedes this call (consumer-release ordering, as in TMA producer / consumer pipelines; a
+    // proxy fence is only required after generic-proxy WRITES, which never touch the landing zone)
     if (lane == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)(w1 - w0) * 48u);
     __syncwarp();
     const int a0 = max(it.rt, w0), b0 = min(it.rt + it.rlen, w1);
@@ -451,16 +307,16 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
       tkP = (int)atomicAdd((unsigned int *)&a.counters[C_TICKET], 1u);
     }
     tkA = __shfl_sync(MOUSE_FULL_MASK, t0, 0);
-    if (tkA < a.g.ncell) hs_raw_issue(a, lane, tkA, s_raw);
+    if (tkA < a.g.ncell) hs_raw_issue(a.g, a.cell_start, lane, tkA, s_raw);
   }
   // next non-empty, regular home cell; false when the grid is exhausted
   auto advance = [&](HsItem &it) -> bool {
     for (;;) {
       if (tkA >= a.g.ncell) return false;
-      const bool nonempty = hs_finalize(a, lane, tkA, s_raw, it);
+      const bool nonempty = hs_finalize(a.g, lane, tkA, s_raw, it);
       tkA = __shfl_sync(MOUSE_FULL_MASK, tkP, 0);
       if (lane == 0) tkP = (int)atomicAdd((unsigned int *)&a.counters[C_TICKET], 1u);
-      if (tkA < a.g.ncell) hs_raw_issue(a, lane, tkA, s_raw);
+      if (tkA < a.g.ncell) hs_raw_issue(a.g, a.cell_start, lane, tkA, s_raw);
       if (!nonempty) continue;
       if (it.nhome > HS_MAXHOME || it.T > HS_MAXPASS * NC) {
         hs_oversize(a.P, a.counters, a.fix_list, a.fix_cap, a.same_molecule, lane, it.hs, it.nhome, it.rsrc, it.rlen, it.rt);

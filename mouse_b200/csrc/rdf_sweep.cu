@@ -6,7 +6,7 @@
 // (np.add(x, -1.*x_ref); dr + -1.*L*around(dr/L); sqrt(x^2+y^2+z^2)), NumPy's uniform-bin index
 // rule (truncate, then +-1 correction against the edges table), shared-memory privatised
 // histogram per block flushed with integer atomics (deterministic result).
-#include "common.cuh"
+#include "half_shell.cuh"
 
 struct RdfArgs {
   GridDev g;
@@ -87,9 +87,283 @@ __global__ void __launch_bounds__(128) rdf_sweep_exact_kernel(const RdfArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ fast RDF sweep (half shell)
+// Same decomposition as the P2 sweep (half_shell.cuh): one warp per home cell, every unordered pair of atoms is
+// decided once and counted twice (the reference counts both orderings into the same sorted type-pair key,
+// ordering_functions.py:162-173).  Candidates come through TMA into shared memory; their FP32 coordinates are held
+// in registers for a packed f32x2 distance filter against a slightly inflated rmax^2; the lanes then walk their
+// filter hits and evaluate the reference's FP64 expression exactly (un-fused dr, minimum image, (x^2+y^2)+z^2).
+// The bin is found WITHOUT sqrt / division in FP64: thr[k] is the smallest double s whose correctly rounded
+// sqrt(s) is >= edges[k] (rdf_thresholds_kernel), so "edges[k] <= sqrt(s) < edges[k+1]" is decided by comparing s
+// itself - bit-exact with numpy.histogram's rule, including range ends and the closed last bin.
+#define RH_WARPS 12
+
+struct RdfHalfArgs {
+  GridDev g;
+  const float4 *P;       // sorted: FP32 (wrapped - L/2), .w = type code
+  const double4 *U;      // sorted: FP64 absolute position, .w = molecule code
+  const int32_t *cell_start;
+  const double *thr;     // [nbin + 2]: thr[0..nbin] lower thresholds in s = d^2, thr[nbin + 1] = largest s with sqrt(s) <= last
+  int nbin, ntypes, same_molecule, use_smem;
+  float first, scale;    // bin estimate (sqrtf(s) - first) * scale
+  float r2hi;            // loose FP32 filter: d2 < r2hi may be in range
+  unsigned long long *hist;
+  int64_t *counters;
+};
+
+__global__ void rdf_thresholds_kernel(const double *__restrict__ edges, int nbin, double *__restrict__ thr) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > nbin + 1) return;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  if (k <= nbin) {       // smallest s >= 0 with sqrt(s) >= edges[k]
+    const double e = edges[k];
+    double s = e > 0.0 ? e * e : 0.0;
+    if (e > 0.0) {
+      while (s > 0.0 && sqrt(nextafter(s, -inf)) >= e) s = nextafter(s, -inf);
+      while (sqrt(s) < e) s = nextafter(s, inf);
+    }
+    thr[k] = s;
+  } else {               // largest s with sqrt(s) <= edges[nbin]
+    const double e = edges[nbin];
+    double s = e * e;
+    if (e < 0.0) {
+      s = -1.0;
+    } else {
+      while (sqrt(nextafter(s, inf)) <= e) s = nextafter(s, inf);
+      while (s > 0.0 && sqrt(s) > e) s = nextafter(s, -inf);
+    }
+    thr[k] = s;
+  }
+}
+
+template <int SLOTS>
+__global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfHalfArgs a) {
+  constexpr int NC = SLOTS * 32;
+  constexpr int NPAIR = SLOTS / 2;
+  extern __shared__ unsigned int s_hist[];            // [npairs * nbin] when use_smem
+  __shared__ __align__(128) float4 s_landP[NC];       // TMA landing zone; stays valid for the whole pass
+  __shared__ __align__(128) double4 s_landU[NC];
+  __shared__ float4 s_homeP[2][32];                   // reference atoms of the home cell, 32 at a time, double buffered
+  __shared__ double4 s_homeU[2][32];
+  __shared__ int s_raw[3][32];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int lane = threadIdx.x;
+  const int nbin = a.nbin;
+  const int hsize = a.ntypes * (a.ntypes + 1) / 2 * nbin;
+  if (a.use_smem)
+    for (int k = lane; k < hsize; k += 32) s_hist[k] = 0;
+  if (lane == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  uint32_t phase = 0;
+  const double thr0 = a.thr[0], shi = a.thr[nbin + 1];
+  const double Lx = a.g.box[0], Ly = a.g.box[1], Lz = a.g.box[2];
+  const double hLx = 0.5 * Lx, hLy = 0.5 * Ly, hLz = 0.5 * Lz;
+  const float2 nr2 = make_float2(-a.r2hi, -a.r2hi);
+
+  // fetch pipeline (see p2_sweep_half_kernel): ticket one item ahead, range table one item ahead
+  int tkA, tkP = 0;
+  {
+    int t0 = 0;
+    if (lane == 0) {
+      t0 = (int)atomicAdd((unsigned int *)&a.counters[2], 1u);
+      tkP = (int)atomicAdd((unsigned int *)&a.counters[2], 1u);
+    }
+    tkA = __shfl_sync(MOUSE_FULL_MASK, t0, 0);
+    if (tkA < a.g.ncell) hs_raw_issue(a.g, a.cell_start, lane, tkA, s_raw);
+  }
+  for (;;) {
+    HsItem cur;
+    bool have = false;
+    while (tkA < a.g.ncell) {
+      const bool nonempty = hs_finalize(a.g, lane, tkA, s_raw, cur);
+      tkA = __shfl_sync(MOUSE_FULL_MASK, tkP, 0);
+      if (lane == 0) tkP = (int)atomicAdd((unsigned int *)&a.counters[2], 1u);
+      if (tkA < a.g.ncell) hs_raw_issue(a.g, a.cell_start, lane, tkA, s_raw);
+      if (nonempty) {
+        have = true;
+        break;
+      }
+    }
+    if (!have) break;
+    const int hs = cur.hs, nhome = cur.nhome, T = cur.T;
+    const bool bnd = cur.boundary != 0;
+
+    for (int w0 = 0; w0 < T; w0 += NC) {
+      // ---- candidates [w0, w1) of the concatenation -> landing zone (TMA) -> FP32 coordinates in registers
+      const int w1 = min(T, w0 + NC), nvalid = w1 - w0;
+      const int npp = (nvalid + 63) >> 6;
+      __syncwarp();          // every lane is done with the previous contents
+      if (lane == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)nvalid * 48u);
+      __syncwarp();
+      {
+        const int a0 = max(cur.rt, w0), b0 = min(cur.rt + cur.rlen, w1);
+        if (b0 > a0) {
+          const int src = cur.rsrc + (a0 - cur.rt), cnt = b0 - a0, dst = a0 - w0;
+          tma_load_1d(&s_landP[dst], a.P + src, (uint32_t)cnt * 16u, &s_bar);
+          tma_load_1d(&s_landU[dst], a.U + src, (uint32_t)cnt * 32u, &s_bar);
+        }
+      }
+      // the first chunk of reference atoms is fetched while the bulk copies fly
+      float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
+      double4 hu = make_double4(0.0, 0.0, 0.0, 0.0);
+      if (lane < nhome) {
+        hp = a.P[hs + lane];
+        hu = a.U[hs + lane];
+      }
+      mbar_wait(&s_bar, phase);
+      phase ^= 1u;
+      float2 xr2[NPAIR], yr2[NPAIR], zr2[NPAIR];
+      {
+        const float Lxf = a.g.boxf[0], Lyf = a.g.boxf[1], Lzf = a.g.boxf[2];
+#pragma unroll
+        for (int pp = 0; pp < NPAIR; ++pp) {
+          float q[2][3];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int tl = 32 * (2 * pp + h) + lane;
+            const float4 p = s_landP[tl];
+            float px = p.x, py = p.y, pz = p.z;
+            if (bnd) {     // nearest periodic image to the home cell centre
+              px -= Lxf * rintf((px - cur.hx) * a.g.inv_boxf[0]);
+              py -= Lyf * rintf((py - cur.hy) * a.g.inv_boxf[1]);
+              pz -= Lzf * rintf((pz - cur.hz) * a.g.inv_boxf[2]);
+            }
+            const bool valid = tl < nvalid;
+            q[h][0] = valid ? px : 1.0e18f;
+            q[h][1] = valid ? py : 1.0e18f;
+            q[h][2] = valid ? pz : 1.0e18f;
+          }
+          xr2[pp] = make_float2(q[0][0], q[1][0]);
+          yr2[pp] = make_float2(q[0][1], q[1][1]);
+          zr2[pp] = make_float2(q[0][2], q[1][2]);
+        }
+      }
+      s_homeP[0][lane] = hp;
+      s_homeU[0][lane] = hu;
+      __syncwarp();
+
+      for (int chunk0 = 0, buf = 0; chunk0 < nhome; chunk0 += 32, buf ^= 1) {
+        const int nchunk = min(32, nhome - chunk0);
+        // next chunk of reference atoms: loaded now, stored after this chunk has been processed
+        if (chunk0 + 32 + lane < nhome) {
+          hp = a.P[hs + chunk0 + 32 + lane];
+          hu = a.U[hs + chunk0 + 32 + lane];
+        }
+        for (int il = 0; il < nchunk; ++il) {
+          const float4 pi = s_homeP[buf][il];
+          const double4 ui = s_homeU[buf][il];
+          const int ti = __float_as_int(pi.w);
+          // ---- FP32 filter: slot c -> bit c of the mask (slots are walked from the last one down)
+          const float2 npx = make_float2(-pi.x, -pi.x), npy = make_float2(-pi.y, -pi.y), npz = make_float2(-pi.z, -pi.z);
+          unsigned mask = 0;
+#pragma unroll
+          for (int pp = NPAIR - 1; pp >= 0; --pp) {
+            if (pp < npp) {
+              const float2 dx = __fadd2_rn(xr2[pp], npx), dy = __fadd2_rn(yr2[pp], npy), dz = __fadd2_rn(zr2[pp], npz);
+              const float2 t = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), nr2);   // < 0: maybe in range
+              mask = __funnelshift_l(__float_as_uint(t.y), mask, 1);
+              mask = __funnelshift_l(__float_as_uint(t.x), mask, 1);
+            }
+          }
+          if (w0 < nhome) {       // home-cell candidates lead the concatenation: count home-home pairs once (t > i)
+            const int lim = chunk0 + il - w0 - lane;        // slot c allowed iff 32 c > lim
+            const int cmin = min(max((lim + 32) >> 5, 0), 32);
+            mask &= cmin >= 32 ? 0u : ~((1u << cmin) - 1u);
+          }
+          // ---- the lanes walk their filter hits: exact FP64 distance, exact bin
+          const int iters = __reduce_max_sync(MOUSE_FULL_MASK, __popc(mask));
+          for (int it = 0; it < iters; ++it) {
+            const bool act = mask != 0;
+            const int c = act ? (__ffs(mask) - 1) : 0;
+            mask &= mask - 1;
+            const double4 uj = s_landU[c * 32 + lane];
+            double tx = __dsub_rn(uj.x, ui.x), ty = __dsub_rn(uj.y, ui.y), tz = __dsub_rn(uj.z, ui.z);
+            // dr - L * around(dr / L): around() is 0 whenever |dr| <= L / 2 (ordering_functions.py:72-74)
+            if (!(fabs(tx) <= hLx)) tx = mouse_trim(tx, Lx);
+            if (!(fabs(ty) <= hLy)) ty = mouse_trim(ty, Ly);
+            if (!(fabs(tz) <= hLz)) tz = mouse_trim(tz, Lz);
+            const double s = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
+            // np.ma.masked_equal(d, 0.) drops coincident atoms (:84); values outside [first, last] are dropped (:86)
+            bool keep = act && s != 0.0 && s >= thr0 && s <= shi;
+            if (!a.same_molecule) keep = keep && uj.w != ui.w;
+            if (keep) {
+              int k = (int)((sqrtf((float)s) - a.first) * a.scale);
+              k = min(max(k, 0), nbin - 1);
+              if (s < __ldg(a.thr + k)) {
+                k -= 1;
+                if (s < __ldg(a.thr + k)) k -= 1;
+              } else if (k < nbin - 1 && s >= __ldg(a.thr + k + 1)) {
+                k += 1;
+                if (k < nbin - 1 && s >= __ldg(a.thr + k + 1)) k += 1;
+              }
+              const int tj = __float_as_int(s_landP[c * 32 + lane].w);
+              const int ta = min(ti, tj), tb = max(ti, tj);
+              const int slot = ta * a.ntypes - ta * (ta - 1) / 2 + (tb - ta);
+              if (a.use_smem) atomicAdd(&s_hist[slot * nbin + k], 2u);
+              else atomicAdd(&a.hist[(size_t)slot * nbin + k], 2ULL);
+            }
+          }
+        }
+        __syncwarp();
+        s_homeP[buf ^ 1][lane] = hp;
+        s_homeU[buf ^ 1][lane] = hu;
+        __syncwarp();
+      }
+    }
+  }
+  if (a.use_smem) {
+    __syncwarp();
+    for (int k = lane; k < hsize; k += 32)
+      if (s_hist[k]) atomicAdd(&a.hist[k], (unsigned long long)s_hist[k]);
+  }
+}
+
 int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, int32_t ntypes,
                            const double *edges_dev, int32_t nbin, const Workspace &w, int64_t *hist,
                            cudaStream_t st) {
+  const size_t hsize = (size_t)ntypes * (ntypes + 1) / 2 * (size_t)nbin;
+  MOUSE_CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(int64_t) * hsize, st));
+  if (n == 0) return MOUSE_OK;
+  const bool fast = grid->fast && !(flags & MOUSE_FORCE_EXACT);
+  if (fast) {
+    RdfHalfArgs h;
+    h.g = mouse_grid_dev(grid);
+    h.P = w.p_sorted;
+    h.U = w.u_sorted;
+    h.cell_start = w.cell_start;
+    h.thr = w.thr;
+    h.nbin = nbin;
+    h.ntypes = ntypes;
+    h.same_molecule = (flags & MOUSE_SAME_MOLECULE) ? 1 : 0;
+    h.hist = (unsigned long long *)hist;
+    h.counters = w.counters;
+    // bin estimate and loose filter need the range on the host: grid->rcut is the last edge (engine.rdf_frame),
+    // the first edge rides in through rdf_first
+    h.first = (float)w.rdf_first;
+    h.scale = (float)((double)nbin / (grid->rcut - w.rdf_first));
+    h.r2hi = nextafterf((float)(grid->rc2 * (1.0 + (double)grid->guard)), 3.0e38f);
+    size_t smem = hsize * sizeof(unsigned int);
+    h.use_smem = smem <= 16 * 1024;
+    if (!h.use_smem) smem = 0;
+    rdf_thresholds_kernel<<<(nbin + 2 + 127) / 128, 128, 0, st>>>(edges_dev, nbin, w.thr);
+    MOUSE_LAUNCH_CHECK("rdf_thresholds_kernel");
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rdf_sweep_half_kernel<8>, 32, 4096);
+      if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int blocks = sms * blocks_per_sm;
+    if (blocks > grid->ncell) blocks = grid->ncell;
+    rdf_sweep_half_kernel<8><<<blocks, 32, smem, st>>>(h);
+    MOUSE_LAUNCH_CHECK("rdf_sweep_half_kernel");
+    return MOUSE_OK;
+  }
   RdfArgs a;
   a.g = mouse_grid_dev(grid);
   a.P = w.p_sorted;
@@ -101,9 +375,6 @@ int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, 
   a.ntypes = ntypes;
   a.same_molecule = (flags & MOUSE_SAME_MOLECULE) ? 1 : 0;
   a.hist = (unsigned long long *)hist;
-  const size_t hsize = (size_t)ntypes * (ntypes + 1) / 2 * (size_t)nbin;
-  MOUSE_CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(int64_t) * hsize, st));
-  if (n == 0) return MOUSE_OK;
   size_t smem = hsize * sizeof(unsigned int);
   a.use_smem = smem <= 96 * 1024;
   if (!a.use_smem) smem = 0;

@@ -169,8 +169,9 @@ def bond_build(positions, bond_atoms, box, device=None):
     return vec, ctr
 
 
-def rdf_frame(positions, type_code, mol, ntypes, box, rmin, rmax, nbin, same_molecule=True, device=None):
-    """K5: int64 histogram [ntypes*(ntypes+1)/2, nbin] over ordered pairs, NumPy bin edges."""
+def rdf_frame(positions, type_code, mol, ntypes, box, rmin, rmax, nbin, same_molecule=True, device=None, exact=False):
+    """K5: int64 histogram [ntypes*(ntypes+1)/2, nbin] over ordered pairs, NumPy bin edges.  ``exact`` forces the
+    all-FP64 one-thread-per-atom kernel (the default picks the half-shell sweep whenever the grid allows it)."""
     require_cuda()
     device = torch.device(device or "cuda")
     pos = as_dev(positions, torch.float64, device)
@@ -185,7 +186,7 @@ def rdf_frame(positions, type_code, mol, ntypes, box, rmin, rmax, nbin, same_mol
     ws = workspace(L.mouse_workspace_bytes(n, C.byref(grid)), device)
     npairs = ntypes * (ntypes + 1) // 2
     hist = torch.empty((npairs, int(nbin)), dtype=torch.int64, device=device)
-    flags = _lib.MOUSE_SAME_MOLECULE if same_molecule else 0
+    flags = (_lib.MOUSE_SAME_MOLECULE if same_molecule else 0) | (_lib.MOUSE_FORCE_EXACT if exact else 0)
     _lib.check(L.mouse_rdf_frame(_ptr(pos), _ptr(tcode), _ptr(molc), n, int(ntypes), C.byref(grid), flags,
                                  edges.ctypes.data_as(C.POINTER(C.c_double)), int(nbin), _ptr(ws), ws.numel(),
                                  _ptr(hist), _stream()), "mouse_rdf_frame")

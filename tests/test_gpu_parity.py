@@ -270,6 +270,39 @@ def test_rdf_against_c_oracle_larger():
         assert np.array_equal(edges, e2) and np.array_equal(h.cpu().numpy(), exp)
 
 
+@pytest.mark.parametrize("rmin,rmax,nbin", [(0., 2.5, 250), (0.9, 3.0, 77), (0., 5., 1000)])
+def test_rdf_fast_sweep_variants(rmin, rmax, nbin):
+    """Half-shell RDF sweep: bit-exact against the C oracle and against the all-FP64 kernel; un-wrapped input
+    coordinates (atoms several box lengths away) and a lower range bound exercise the exact minimum image / bin rule."""
+    from mouse_b200.melt import make_melt
+    from oracle import c_oracle
+    melt = make_melt(150, 100, seed=8, n_atom_types=3)
+    eng = _engine()
+    pos = melt.positions + melt.images * melt.box        # un-wrapped coordinates
+    pos[::7] += 3.0 * melt.box                            # and some atoms far outside the box
+    for same in (True, False):
+        h, edges = eng.rdf_frame(pos, melt.atom_type, melt.mol, 3, melt.box, rmin, rmax, nbin, same_molecule=same)
+        hx, _ = eng.rdf_frame(pos, melt.atom_type, melt.mol, 3, melt.box, rmin, rmax, nbin, same_molecule=same, exact=True)
+        exp, e2 = c_oracle.rdf(pos, melt.atom_type, melt.mol, 3, melt.box, rmin, rmax, nbin, same)
+        assert np.array_equal(edges, e2)
+        assert np.array_equal(hx.cpu().numpy(), exp)
+        assert np.array_equal(h.cpu().numpy(), exp)
+
+
+def test_rdf_fast_sweep_lattice_on_bin_edges():
+    """Simple cubic lattice, bin edges placed on lattice distances: every pair sits exactly on an edge."""
+    from oracle import c_oracle
+    m, a0 = 12, 1.0
+    g = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3) * a0 - 0.5 * m * a0
+    box = np.array([m * a0] * 3)
+    typ = np.zeros(len(g), np.int32)
+    mol = np.arange(len(g), dtype=np.int32)
+    eng = _engine()
+    h, edges = eng.rdf_frame(g, typ, mol, 1, box, 0., 3.0, 30)
+    exp, _ = c_oracle.rdf(g, typ, mol, 1, box, 0., 3.0, 30, True)
+    assert np.array_equal(h.cpu().numpy(), exp) and int(exp.sum()) > 0
+
+
 def test_cli_matches_reference_output(capsys):
     """calculate_local_ordering.py <golden data file> --bondtypes 1 --max 1.5 --same-molecule prints the
     reference's S for that file (the golden S came from the reference's own Config of the same arrays)."""
