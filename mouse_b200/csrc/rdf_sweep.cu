@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
   const double Lx = a.g.box[0], Ly = a.g.box[1], Lz = a.g.box[2];
   const double hLx = 0.5 * Lx, hLy = 0.5 * Ly, hLz = 0.5 * Lz;
   const float2 nr2 = make_float2(-a.r2hi, -a.r2hi);
+  const double4 *landU_lane = s_landU + lane;    // candidate (slot c, this lane) = element c * 32
+  const float4 *landP_lane = s_landP + lane;
 
   // fetch pipeline (see p2_sweep_half_kernel): ticket one item ahead, range table one item ahead
   int tkA, tkP = 0;
@@ -273,37 +275,42 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
             const int cmin = min(max((lim + 32) >> 5, 0), 32);
             mask &= cmin >= 32 ? 0u : ~((1u << cmin) - 1u);
           }
-          // ---- the lanes walk their filter hits: exact FP64 distance, exact bin
+          // ---- the lanes walk their filter hits (highest slot first): exact FP64 distance, exact bin.
+          // Branch-free body; exhausted lanes re-read slot 0 and are masked out by `act`.
           const int iters = __reduce_max_sync(MOUSE_FULL_MASK, __popc(mask));
           for (int it = 0; it < iters; ++it) {
             const bool act = mask != 0;
-            const int c = act ? (__ffs(mask) - 1) : 0;
-            mask &= mask - 1;
-            const double4 uj = s_landU[c * 32 + lane];
+            const int c = (int)min((unsigned)(31 - __clz((int)mask)), (unsigned)(SLOTS - 1));   // mask == 0 -> clamped
+            mask &= ~(1u << c);
+            const double4 uj = landU_lane[c * 32];
             double tx = __dsub_rn(uj.x, ui.x), ty = __dsub_rn(uj.y, ui.y), tz = __dsub_rn(uj.z, ui.z);
-            // dr - L * around(dr / L): around() is 0 whenever |dr| <= L / 2 (ordering_functions.py:72-74)
-            if (!(fabs(tx) <= hLx)) tx = mouse_trim(tx, Lx);
-            if (!(fabs(ty) <= hLy)) ty = mouse_trim(ty, Ly);
-            if (!(fabs(tz) <= hLz)) tz = mouse_trim(tz, Lz);
+            // dr - L * around(dr / L): around() is 0 whenever |dr| <= L / 2 (ordering_functions.py:72-74); one
+            // rare branch for coordinates that were not wrapped into the box
+            if (!(fabs(tx) <= hLx && fabs(ty) <= hLy && fabs(tz) <= hLz)) {
+              tx = mouse_trim(tx, Lx);
+              ty = mouse_trim(ty, Ly);
+              tz = mouse_trim(tz, Lz);
+            }
             const double s = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
             // np.ma.masked_equal(d, 0.) drops coincident atoms (:84); values outside [first, last] are dropped (:86)
             bool keep = act && s != 0.0 && s >= thr0 && s <= shi;
             if (!a.same_molecule) keep = keep && uj.w != ui.w;
-            if (keep) {
-              int k = (int)((sqrtf((float)s) - a.first) * a.scale);
-              k = min(max(k, 0), nbin - 1);
-              if (s < __ldg(a.thr + k)) {
-                k -= 1;
-                if (s < __ldg(a.thr + k)) k -= 1;
-              } else if (k < nbin - 1 && s >= __ldg(a.thr + k + 1)) {
-                k += 1;
-                if (k < nbin - 1 && s >= __ldg(a.thr + k + 1)) k += 1;
-              }
-              const int tj = __float_as_int(s_landP[c * 32 + lane].w);
+            // bin estimate from an FP32 square root (error << one bin), made exact with the two thresholds around it
+            const float sf = fmaxf((float)s, 1.0e-30f);
+            int k = (int)((sf * __frsqrt_rn(sf) - a.first) * a.scale);
+            k = min(max(k, 0), nbin - 1);
+            const double tlo = __ldg(a.thr + k), thi = __ldg(a.thr + k + 1);
+            k += (s >= thi && k < nbin - 1) ? 1 : 0;
+            k -= (s < tlo && k > 0) ? 1 : 0;
+            int slot = 0;
+            if (a.ntypes > 1) {     // warp-uniform
+              const int tj = __float_as_int(landP_lane[c * 32].w);
               const int ta = min(ti, tj), tb = max(ti, tj);
-              const int slot = ta * a.ntypes - ta * (ta - 1) / 2 + (tb - ta);
-              if (a.use_smem) atomicAdd(&s_hist[slot * nbin + k], 2u);
-              else atomicAdd(&a.hist[(size_t)slot * nbin + k], 2ULL);
+              slot = (ta * a.ntypes - ta * (ta - 1) / 2 + (tb - ta)) * nbin;
+            }
+            if (keep) {
+              if (a.use_smem) atomicAdd(&s_hist[slot + k], 2u);
+              else atomicAdd(&a.hist[(size_t)(slot + k)], 2ULL);
             }
           }
         }
