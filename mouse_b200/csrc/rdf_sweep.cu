@@ -297,7 +297,9 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
             if (!a.same_molecule) keep = keep && uj.w != ui.w;
             // bin estimate from an FP32 square root (error << one bin), made exact with the two thresholds around it
             const float sf = fmaxf((float)s, 1.0e-30f);
-            int k = (int)((sf * __frsqrt_rn(sf) - a.first) * a.scale);
+            float rs;
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(sf));      // one MUFU.RSQ; 2 ulp is plenty here
+            int k = (int)((sf * rs - a.first) * a.scale);
             k = min(max(k, 0), nbin - 1);
             const double tlo = __ldg(a.thr + k), thi = __ldg(a.thr + k + 1);
             k += (s >= thi && k < nbin - 1) ? 1 : 0;
