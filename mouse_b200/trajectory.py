@@ -172,3 +172,35 @@ def local_ordering_trajectory(frames_positions, bond_atoms, mol, box, rcut, same
         totals.add_frame(t["sum_mean"], t["n_refs"], t["n_pairs"])
         per_frame.append((f, np.float64(1.5 * t["sum_mean"] / t["n_refs"] - 0.5) if t["n_refs"] else np.float64("nan")))
     return per_frame, all_reduce_totals(totals, device)
+
+
+def local_ordering_from_dump(topology, dump_path, bondtypes=None, rcut=0., coords_type="scaled",
+                             reference_res_types=None, same_molecule=True, device=None):
+    """Trajectory driver over files: ``topology`` is a ``FrameArrays`` (e.g.
+    ``ingest.read_lmp_data_arrays(data_file)``), the frames come from a LAMMPS dump.  Every frame carries its own
+    box, so the cell grid is re-planned per frame; frames are block-sharded over the ranks exactly like
+    ``local_ordering_trajectory`` and reduced with the same single all-reduce.  Selections follow the reference:
+    neighbour set = bonds passing ``bondtypes``, reference set = those also passing ``reference_res_types``
+    (``ordering_functions.py:196-199``); ``rcut == 0`` means half the box diagonal (``:185-186``)."""
+    import torch.distributed as dist
+    from . import ingest
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    device = torch.device(device or "cuda")
+    timesteps, boxes, positions = ingest.read_lmp_dump_arrays(dump_path, topology.atom_num, coords_type)
+    lo, hi = shard_range(len(timesteps), rank, world)
+    nbr_mask = topology.bond_mask(bond_types=bondtypes)
+    ref_mask = topology.bond_mask(bond_types=bondtypes, res_types=reference_res_types)
+    mol = topology.bond_mol_hash().astype(np.int32)
+    totals = TrajectoryTotals()
+    per_frame = []
+    res = None
+    for f in range(lo, hi):
+        rc = float(rcut) if rcut != 0. else engine.half_diagonal(boxes[f])
+        res = engine.p2_frame(positions[f], topology.bond_atoms, mol, boxes[f], rc, same_molecule=same_molecule,
+                              nbr_mask=nbr_mask, ref_mask=ref_mask, device=device, out=res)
+        t = res.totals_dict()
+        totals.add_frame(t["sum_mean"], t["n_refs"], t["n_pairs"])
+        s = np.float64(1.5 * t["sum_mean"] / t["n_refs"] - 0.5) if t["n_refs"] else np.float64("nan")
+        per_frame.append((int(timesteps[f]), s))
+    return per_frame, all_reduce_totals(totals, device)

@@ -421,3 +421,24 @@ def test_frame_and_staged_paths_agree():
     assert a.totals_dict()["n_pairs"] == b.totals_dict()["n_pairs"] and a.totals_dict()["n_refs"] == b.totals_dict()["n_refs"]
     assert abs(a.order_parameter() - b.order_parameter()) < 1e-13
     assert int(b.hist.sum()) == b.totals_dict()["n_refs"]
+
+
+def test_dump_trajectory_matches_the_oracle_frame_by_frame():
+    """File ingestion row: LAMMPS data + dump -> arrays -> hot path, against the NumPy restatement of the reference
+    on the same frames (per-frame box, scaled coordinates)."""
+    import os
+    from mouse_b200 import ingest
+    from mouse_b200.trajectory import local_ordering_from_dump
+    from oracle import p2_oracle as po
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    top = ingest.read_lmp_data_arrays(os.path.join(here, "melt_290.data"))
+    dump = os.path.join(here, "melt_290.dump")
+    per_frame, totals = local_ordering_from_dump(top, dump, ["1"], 1.5, "scaled", same_molecule=True)
+    ts, boxes, pos = ingest.read_lmp_dump_arrays(dump, top.atom_num, "scaled")
+    assert [t for t, _ in per_frame] == ts.tolist() and totals.n_frames == 3
+    for f in range(3):
+        vec, ctr = po.bond_build(pos[f], top.bond_atoms, boxes[f])
+        lit = po.p2_literal(vec, ctr, top.bond_num, top.bond_mol_hash(), boxes[f], 1.5)
+        ok = lit["count"] > 0
+        s_ref = 1.5 * lit["mean"][ok].sum() / ok.sum() - 0.5
+        assert abs(per_frame[f][1] - s_ref) <= RTOL * abs(s_ref)
