@@ -72,7 +72,12 @@ __device__ __forceinline__ double exact_pair(const int32_t *__restrict__ idx, co
 }
 
 // ------------------------------------------------------------------ half-shell fast sweep
+#ifndef HS_MAXHOME
 #define HS_MAXHOME 96      // home cells with more bonds are decided pair by pair by p2_fixup_kernel
+#endif
+#ifndef HS_GRP
+#define HS_GRP 8           // references reduced together (transposed reduction through shared memory)
+#endif
 #define HS_MAXPASS 8       // ... and home cells with more than HS_MAXPASS * SLOTS * 32 candidates
 #ifndef HS_WARPS
 #define HS_WARPS 12        // resident warps (= CTAs) per SM the register allocation is sized for
@@ -150,6 +155,7 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
                                             const int (&molr)[SLOTS], const float4 *s_homeP,
                                             const double (*s_homeU)[HS_MAXHOME], double (*s_acc)[33],
                                             int (*s_cnt)[33], const int (*s_gid)[32]) {
+  static_assert(HS_GRP == 8 || HS_GRP == 4, "reference groups of 4 or 8");
   constexpr int HSL = HS_MAXHOME / 32;   // slots of pass 0 that may hold home-cell bonds
   const float2 nrc = make_float2(-k.rc2_c, -k.rc2_c);
   // reference il + 1 is fetched from shared memory while reference il is processed
@@ -224,24 +230,27 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
       }
     }
     // ---- reference side: per-lane partials -> shared memory, 8 references are reduced together
-    s_acc[il & 7][lane] = acci0 + acci1;
-    s_cnt[il & 7][lane] = cnti;
-    if ((il & 7) == 7 || il == nhome - 1) {
+    s_acc[il & (HS_GRP - 1)][lane] = acci0 + acci1;
+    s_cnt[il & (HS_GRP - 1)][lane] = cnti;
+    if ((il & (HS_GRP - 1)) == HS_GRP - 1 || il == nhome - 1) {
       __syncwarp();
-      const int row = lane & 7, part = lane >> 3;
+      constexpr int PER = 32 / HS_GRP * 2;            // 32 / HS_GRP lanes share a reference, PER partials each
+      const int row = lane & (HS_GRP - 1), part = lane / HS_GRP;
       double v = 0.0;
       int nv = 0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        v += s_acc[row][part * 8 + q];
-        nv += s_cnt[row][part * 8 + q];
+      for (int q = 0; q < HS_GRP; ++q) {
+        v += s_acc[row][part * HS_GRP + q];
+        nv += s_cnt[row][part * HS_GRP + q];
       }
-      v += __shfl_xor_sync(MOUSE_FULL_MASK, v, 8);
-      nv += __shfl_xor_sync(MOUSE_FULL_MASK, nv, 8);
-      v += __shfl_xor_sync(MOUSE_FULL_MASK, v, 16);
-      nv += __shfl_xor_sync(MOUSE_FULL_MASK, nv, 16);
-      const int iref = (il & ~7) + lane;
-      if (lane < 8 && iref <= il) hs_flush(a.acc_fix, a.acc_cnt, hs + iref, v, nv);
+      (void)PER;
+#pragma unroll
+      for (int o = HS_GRP; o < 32; o <<= 1) {
+        v += __shfl_xor_sync(MOUSE_FULL_MASK, v, o);
+        nv += __shfl_xor_sync(MOUSE_FULL_MASK, nv, o);
+      }
+      const int iref = (il & ~(HS_GRP - 1)) + lane;
+      if (lane < HS_GRP && iref <= il) hs_flush(a.acc_fix, a.acc_cnt, hs + iref, v, nv);
       __syncwarp();
     }
   }
@@ -257,8 +266,8 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
   __shared__ __align__(128) double4 s_landU[NC];
   __shared__ float4 s_homeP[HS_MAXHOME];            // the home cell's bonds: the references of this item
   __shared__ double s_homeU[3][HS_MAXHOME];
-  __shared__ double s_acc[8][33];                   // per-lane partial sums of 8 references (transposed reduce)
-  __shared__ int s_cnt[8][33];                      // ... and partial counts
+  __shared__ double s_acc[HS_GRP][33];                   // per-lane partial sums of 8 references (transposed reduce)
+  __shared__ int s_cnt[HS_GRP][33];                      // ... and partial counts
   __shared__ int s_gid[SLOTS][32];                  // sorted slot of every register-resident candidate (-1: empty)
   __shared__ int s_raw[3][32];                      // range table in flight (fetch stage 2 -> 3)
   __shared__ int s_next[3][32];                     // range table of the prefetched item (kept out of the registers)
