@@ -5,7 +5,9 @@ The arithmetic runs in the sm_100a kernels behind ``mouse_b200.ordering_function
 import argparse
 import sys
 
-from mouse_b200.lammpack_misc import printHistogram, read_data_typeselect, select_chains, select_rectangular
+from mouse_b200 import ingest
+from mouse_b200.lammpack_misc import (determine_data_type, printHistogram, read_data_typeselect, select_chains,
+                                      select_rectangular)
 from mouse_b200.ordering_functions import CalculateOrientationOrderParameter
 
 
@@ -31,19 +33,24 @@ def main(argv=None):
     args = build_parser().parse_args(argv)
     for path in args.frames:
         sys.stderr.write("\r")
-        frame = read_data_typeselect(path)
-        sys.stderr.write("Read frame (natom): " + str(frame.n_atom()) + "\n")
+        store = bool(args.out_pdb)
+        # LAMMPS data files go straight into arrays (no per-atom objects); the object model is only built when the
+        # atoms have to be recoloured for --out-pdb
+        as_arrays = not store and determine_data_type(path) == "lammps_data"
+        frame = ingest.read_lmp_data_arrays(path) if as_arrays else read_data_typeselect(path)
+        natom = (lambda fr: fr.n_atoms) if as_arrays else (lambda fr: fr.n_atom())
+        sys.stderr.write("Read frame (natom): " + str(natom(frame)) + "\n")
         if args.chains:
-            frame = select_chains(frame, args.chains)
-        sys.stderr.write("After molecules selection: " + str(frame.n_atom()) + "\n")
+            frame = frame.select_chains(args.chains) if as_arrays else select_chains(frame, args.chains)
+        sys.stderr.write("After molecules selection: " + str(natom(frame)) + "\n")
         if args.subcell is not None:
             lim = [0., 1., 0., 1., 0., 1.]
             cut = [False, False, False]
             for k in range(min(len(args.subcell) // 2, 3)):
                 lim[2 * k], lim[2 * k + 1], cut[k] = args.subcell[2 * k], args.subcell[2 * k + 1], True
-            frame = select_rectangular(frame, cut[0], lim[0], lim[1], cut[1], lim[2], lim[3], cut[2], lim[4], lim[5])
-        sys.stderr.write("After region selection: " + str(frame.n_atom()) + "\n")
-        store = bool(args.out_pdb)
+            sel = (cut[0], lim[0], lim[1], cut[1], lim[2], lim[3], cut[2], lim[4], lim[5])
+            frame = frame.select_rectangular(*sel) if as_arrays else select_rectangular(frame, *sel)
+        sys.stderr.write("After region selection: " + str(natom(frame)) + "\n")
         s = CalculateOrientationOrderParameter(frame, args.bondtypes, args.min, args.max, mode=args.mode,
                                                storeAsAtomtypes=store, smin=args.histo_min, smax=args.histo_max,
                                                sbins=args.histo_bins, referenceResTypes=args.reference_residue,

@@ -127,3 +127,35 @@ class FrameArrays:
         if b is not None:
             m &= b
         return m
+
+    # ---------------------------------------------------------------- selections on arrays
+    def subset(self, atom_keep) -> "FrameArrays":
+        """Atoms with ``atom_keep`` true plus the bonds whose BOTH atoms survive - what the reference's
+        ``selectByAtomFields`` / ``select_rectangular`` build as a new ``Config`` (``lammpack_misc.py:96-144``).
+        Atom and bond numbers are kept (the reference re-inserts the same objects)."""
+        keep = np.asarray(atom_keep, bool)
+        new_index = np.cumsum(keep) - 1
+        bk = keep[self.bond_atoms[:, 0]] & keep[self.bond_atoms[:, 1]] if self.n_bonds else np.zeros(0, bool)
+        ai = np.flatnonzero(keep)
+        bi = np.flatnonzero(bk)
+        return FrameArrays(positions=self.positions[ai], box=self.box.copy(), atom_num=self.atom_num[ai],
+                           atom_type=[self.atom_type[k] for k in ai], atom_res=[self.atom_res[k] for k in ai],
+                           atom_mol=[self.atom_mol[k] for k in ai],
+                           bond_atoms=new_index[self.bond_atoms[bi]].astype(np.int32).reshape(len(bi), 2),
+                           bond_num=self.bond_num[bi], bond_type=[self.bond_type[k] for k in bi])
+
+    def select_chains(self, chain_list) -> "FrameArrays":
+        """``select_chains`` (``lammpack_misc.py:120-121``): atoms whose ``mol_id`` is in ``chain_list``."""
+        allowed = set(chain_list)
+        return self.subset(np.fromiter((m in allowed for m in self.atom_mol), bool, self.n_atoms))
+
+    def select_rectangular(self, cutx=False, xrelmin=0., xrelmax=1., cuty=False, yrelmin=0., yrelmax=1.,
+                           cutz=False, zrelmin=0., zrelmax=1.) -> "FrameArrays":
+        """``select_rectangular`` (``lammpack_misc.py:124-144``): box-relative coordinate ``pos / box`` inside
+        ``[min, max]`` (both ends included) on every axis that is cut."""
+        rel = self.positions / self.box
+        keep = np.ones(self.n_atoms, bool)
+        for a, (cut, lo, hi) in enumerate(((cutx, xrelmin, xrelmax), (cuty, yrelmin, yrelmax), (cutz, zrelmin, zrelmax))):
+            if cut:
+                keep &= (rel[:, a] >= lo) & (rel[:, a] <= hi)
+        return self.subset(keep)

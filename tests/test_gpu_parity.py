@@ -319,6 +319,24 @@ def test_cli_matches_reference_output(capsys):
     assert abs(float(out) - float(g["ref_S"])) <= RTOL * abs(float(g["ref_S"]))
 
 
+def test_cli_selections_on_arrays_match_the_object_path(capsys):
+    """--chains / --subcell: the CLI's array path (ingest + FrameArrays selections) against the same selections made
+    on the object model with the mirrors of the reference's select_chains / select_rectangular."""
+    import os
+    import calculate_local_ordering as cli
+    from mouse_b200 import ordering_functions as of
+    from mouse_b200.lammpack_misc import read_data_typeselect, select_chains, select_rectangular
+    from tests.util import GOLDEN_DIR
+    path = os.path.join(GOLDEN_DIR, "melt_290.data")
+    cli.main([path, "--bondtypes", "1", "--max", "2.0", "--same-molecule", "--chains", "1", "2", "3",
+              "--subcell", "-0.5", "0.35"])
+    out = float(capsys.readouterr().out.strip())
+    cfg = select_chains(read_data_typeselect(path), ["1", "2", "3"])
+    cfg = select_rectangular(cfg, True, -0.5, 0.35)
+    ref = of.CalculateOrientationOrderParameter(cfg, ["1"], None, 2.0, sameMolecule=True)
+    assert out == float(ref)
+
+
 # ------------------------------------------------------------------------------- half-shell sweep corner cases
 def _bonds_from_midpoints(ctr, vec):
     """Positions / bond table for bonds given by midpoint and vector (two private atoms per bond)."""

@@ -53,3 +53,19 @@ def test_dump_atom_count_mismatch_raises_like_the_reference():
         list(ingest.iter_lmp_dump_frames(DUMP, np.arange(1, 10), "scaled"))
     with pytest.raises(ValueError):
         list(ingest.iter_lmp_dump_frames(DUMP, np.arange(1, 301), "fractional"))
+
+
+def test_array_selections_equal_the_object_selections():
+    """--chains / --subcell on arrays vs the Config-rebuilding mirrors of the reference's selectByAtomFields /
+    select_rectangular."""
+    from mouse_b200.lammpack_misc import select_chains, select_rectangular
+    cfg = read_data_typeselect(DATA)
+    fa = ingest.read_lmp_data_arrays(DATA)
+    for got, exp in ((fa.select_chains(["1", "3"]), select_chains(cfg, ["1", "3"])),
+                     (fa.select_rectangular(True, -0.2, 0.3, False, 0., 1., True, -0.5, 0.1),
+                      select_rectangular(cfg, True, -0.2, 0.3, False, 0., 1., True, -0.5, 0.1))):
+        ref = FrameArrays.from_config(exp)
+        assert got.n_atoms == ref.n_atoms and got.n_bonds == ref.n_bonds and got.n_bonds > 0
+        assert np.array_equal(got.positions, ref.positions) and np.array_equal(got.atom_num, ref.atom_num)
+        assert np.array_equal(got.bond_atoms, ref.bond_atoms) and np.array_equal(got.bond_num, ref.bond_num)
+        assert got.atom_mol == ref.atom_mol and got.bond_type == ref.bond_type
