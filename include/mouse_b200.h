@@ -150,6 +150,13 @@ int mouse_p2_single_ref(const double *np_bonds, int64_t n, const double *ref, co
 int mouse_rdf_single_ref(const double *np_atoms, int64_t n, const double *ref, const double *box, uint32_t flags,
                          const double *edges, int32_t nbin, void *ws, int64_t *hist, void *stream);
 
+/* P2 of every bond against one director: replaces the per-bond loop of CalculateCrystallinityParameter's histo branch
+ * (ordering_functions.py:263-273).  vec = K1's SoA [3][n]; mask NULL = all bonds; director HOST[3] (ave_b, :242-251);
+ * out_s DEV[n] = 1.5*cos^2-0.5 per bond (NaN where masked out); hist DEV[nbins+1]: bins filled with the rule of
+ * updateHistogram (lammpack_misc.py:185-189), hist[nbins] = values the reference would raise IndexError on. */
+int mouse_director_p2(const double *vec, const uint8_t *mask, int64_t n_bonds, const double *director, double *out_s,
+                      int64_t *hist, double smin, double smax, int32_t nbins, void *stream);
+
 /* Test / tuning hook: "fast_slots" (register-resident candidate slots per lane, 0 = auto). */
 int mouse_set_tuning(const char *key, int value);
 /* Debug: the 8 int64 workspace counters (0 zero-length, 1 guard-band redos, 4-7 phase cycle timers when built

@@ -26,6 +26,8 @@ int mouse_launch_p2_reduce(const double *sum, const int32_t *cnt, int64_t n, con
                            cudaStream_t st);
 int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, int32_t ntypes, const double *edges_dev,
                            int32_t nbin, const Workspace &w, int64_t *hist, cudaStream_t st);
+int mouse_launch_director_p2(const double *vec, const uint8_t *mask, int64_t n, const double *director, double *out_s,
+                             int64_t *hist, double smin, double smax, int32_t nbins, cudaStream_t st);
 extern int mouse_fast_slots_override;
 extern int mouse_fast_variant;
 
@@ -246,6 +248,17 @@ int mouse_rdf_frame(const double *pos, const int32_t *type, const int32_t *mol, 
   // the fast sweep's cutoff is the last edge: it needs a grid planned for exactly that cutoff
   if (!(grid->rcut == edges[nbin]) || !(edges[nbin] > edges[0])) flags |= MOUSE_FORCE_EXACT;
   return mouse_launch_rdf_sweep(grid, flags, n_atoms, ntypes, w.edges, nbin, w, hist, st);
+}
+
+int mouse_director_p2(const double *vec, const uint8_t *mask, int64_t n_bonds, const double *director, double *out_s,
+                      int64_t *hist, double smin, double smax, int32_t nbins, void *stream) {
+  if (!vec || !director || !out_s || !hist || nbins < 1 || nbins > MOUSE_MAX_BINS) {
+    if (n_bonds == 0 && hist && nbins >= 1 && nbins <= MOUSE_MAX_BINS)
+      return mouse_launch_director_p2(vec, mask, 0, director, out_s, hist, smin, smax, nbins, (cudaStream_t)stream);
+    mouse_set_error("mouse_director_p2: bad argument (nbins=%d)", nbins);
+    return MOUSE_EINVAL;
+  }
+  return mouse_launch_director_p2(vec, mask, n_bonds, director, out_s, hist, smin, smax, nbins, (cudaStream_t)stream);
 }
 
 // Debug / tuning: copies the 8 workspace counters to host (synchronises the stream).

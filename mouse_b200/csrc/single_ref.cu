@@ -179,3 +179,55 @@ int mouse_rdf_single_ref(const double *np_atoms, int64_t n, const double *ref, c
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// P2 of every bond against ONE director (CalculateCrystallinityParameter, histo branch, ordering_functions.py:263-267):
+//   s = 1.5 * (b.x*d.x + b.y*d.y + b.z*d.z)**2 / b.length_sq() / d.length_sq() - 0.5     (left to right, un-fused)
+// vec is the SoA [3][n] output of K1; bonds with mask == 0 get NaN and are not histogrammed.  The histogram uses the
+// reference's updateHistogram rule (lammpack_misc.py:185-189): int(nbins*(v-min)/(max-min)), negative wraps, >= nbins
+// is counted in *over (the reference raises IndexError).
+__global__ void __launch_bounds__(256) director_p2_kernel(const double *__restrict__ vec, const uint8_t *__restrict__ mask,
+                                                          int n, double dx, double dy, double dz,
+                                                          double *__restrict__ out_s, unsigned long long *__restrict__ hist,
+                                                          unsigned long long *__restrict__ over, double smin, double smax,
+                                                          int nbins) {
+  extern __shared__ unsigned int s_hist[];   // nbins + 1
+  for (int k = threadIdx.x; k <= nbins; k += blockDim.x) s_hist[k] = 0;
+  __syncthreads();
+  const size_t N = (size_t)n;
+  const double ld = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
+    double s = __longlong_as_double(0x7ff8000000000000LL);
+    if (!mask || mask[b]) {
+      const double bx = vec[b], by = vec[N + b], bz = vec[2 * N + b];
+      const double dot = __dadd_rn(__dadd_rn(__dmul_rn(bx, dx), __dmul_rn(by, dy)), __dmul_rn(bz, dz));
+      const double lb = __dadd_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)), __dmul_rn(bz, bz));
+      s = __dsub_rn(__ddiv_rn(__ddiv_rn(__dmul_rn(1.5, __dmul_rn(dot, dot)), lb), ld), 0.5);
+      const double f = __ddiv_rn(__dmul_rn((double)nbins, __dsub_rn(s, smin)), __dsub_rn(smax, smin));
+      int bin = nbins;
+      if (f == f && fabs(f) < 2.0e9) {
+        const int t = (int)f;   // truncation toward zero, like Python int()
+        if (t >= 0 && t < nbins) bin = t;
+        else if (t < 0 && t >= -nbins) bin = nbins + t;
+      }
+      atomicAdd(&s_hist[bin], 1u);
+    }
+    out_s[b] = s;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k <= nbins; k += blockDim.x)
+    if (s_hist[k]) atomicAdd(k < nbins ? &hist[k] : over, (unsigned long long)s_hist[k]);
+}
+
+int mouse_launch_director_p2(const double *vec, const uint8_t *mask, int64_t n, const double *director, double *out_s,
+                             int64_t *hist, double smin, double smax, int32_t nbins, cudaStream_t st) {
+  MOUSE_CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(int64_t) * (size_t)(nbins + 1), st));
+  if (n == 0) return MOUSE_OK;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  director_p2_kernel<<<blocks, 256, sizeof(unsigned int) * (size_t)(nbins + 1), st>>>(
+      vec, mask, (int)n, director[0], director[1], director[2], out_s, (unsigned long long *)hist,
+      (unsigned long long *)hist + nbins, smin, smax, nbins);
+  MOUSE_LAUNCH_CHECK("director_p2_kernel");
+  return MOUSE_OK;
+}

@@ -21,7 +21,7 @@ from .lammpack_misc import createHistogram, normHistogram
 
 __all__ = ["hash8", "createNumpyBondsArrayFromConfig", "createNumpyAtomsArrayFromConfig",
            "calculateRdfForReference", "calculateAveCosSqForReference", "CalculatePairCorrelationFunctions",
-           "CalculateOrientationOrderParameter"]
+           "CalculateOrientationOrderParameter", "CalculateCrystallinityParameter", "CalculateComRdfs"]
 
 
 def _arrays(config) -> FrameArrays:
@@ -177,7 +177,8 @@ def calculateRdfForReference(config, refAtom, npAtoms, rmin=0., rmax=-1., nbin=1
     ws, _ = _single_ref_ws(dev.device if n else torch.device("cuda"))
     hist = torch.zeros(nbin + 1, dtype=torch.int64, device=ws.device)
     if n:
-        ref = (C.c_double * 5)(float(refAtom.pos.x), float(refAtom.pos.y), float(refAtom.pos.z), float(refAtom.num),
+        ref = (C.c_double * 5)(float(refAtom.pos.x), float(refAtom.pos.y), float(refAtom.pos.z),
+                               float(refAtom.num) if refAtom.num is not None else -1.,
                                float(hash8(refAtom.mol_id)))
         flags = (_lib.MOUSE_SAME_MOLECULE if sameMolecule else 0) | (0 if excludeSelf else _lib.MOUSE_INCLUDE_SELF)
         _lib.check(_lib.lib().mouse_rdf_single_ref(C.c_void_p(dev.data_ptr()), n, ref, (C.c_double * 3)(*box), flags,
@@ -297,3 +298,99 @@ def _store_as_atomtypes(config, fa, res):
     for a, vals in per_atom.items():
         m = np.mean(vals)
         atoms[a].type = ("C" + "%02d" % int(m * 100)) if m >= 0. else ("Cm" + "%02d" % int(m * -100))
+
+
+# --------------------------------------------------------------------------------------- next rows
+def CalculateCrystallinityParameter(config, bondtypes, reference_vector=None, storeAsAtomtypes=False, mode='average',
+                                    smin=-0.5, smax=1.0, sbins=75):
+    """P2 of every selected bond against one director - reference ``ordering_functions.py:230-282``.
+    ``reference_vector`` (anything with ``.x .y .z``; ``None`` or zero length = the mean bond vector, ``:242-251``).
+    ``mode='histo'`` returns the reference's histogram dict (``normHistogram(..., normInternalNorm=True)``) and, with
+    ``storeAsAtomtypes``, rewrites ``atom.type`` to ``CXX`` / ``CmXX``.  ``mode='average'`` raises ``KeyError(0)``
+    exactly like the reference does (it fabricates a ``Bond`` with ``num == 0`` that ``bond_vector_by_num`` cannot find,
+    ``:257-261`` - SURVEY.md section 2)."""
+    fa = _arrays(config)
+    box = _box3(config)
+    if mode == 'histo':
+        s_hist = createHistogram(smin, smax, sbins)
+        for i in range(sbins):
+            sleft, sright = smin + i * s_hist["step"], smin + (i + 1) * s_hist["step"]
+            costhetaleft, costhetaright = (2. / 3. * (sleft + 0.5))**0.5, (2. / 3. * (sright + 0.5))**0.5
+            s_hist["norm"][i] = 1. / (costhetaleft + costhetaright)
+    mask = np.ones(fa.n_bonds, bool) if bondtypes is None else np.fromiter(
+        (t in bondtypes for t in fa.bond_type), bool, fa.n_bonds)              # `bond.type in bondtypes` (:241)
+    vec, _ = engine.bond_build(fa.positions, fa.bond_atoms, box)                # K1 on the device, (3, N_b)
+    rv = (0., 0., 0.) if reference_vector is None else (float(reference_vector.x), float(reference_vector.y),
+                                                        float(reference_vector.z))
+    if rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2] == 0.:
+        # ave_b = ((b_1 + b_2) + b_3) + ... scaled by 1/i_b (:243-249): a running sum in bond order
+        sel = vec[:, torch.as_tensor(mask, device=vec.device)].cpu().numpy()
+        if sel.shape[1] > 0:
+            tot = np.cumsum(sel, axis=1)[:, -1]
+            k = 1. / float(sel.shape[1])
+            rv = (float(tot[0] * k), float(tot[1] * k), float(tot[2] * k))
+    if mode == 'average':
+        raise KeyError(0)
+    elif mode == 'histo':
+        dev = vec.device
+        out_s = torch.empty(fa.n_bonds, dtype=torch.float64, device=dev)
+        hist = torch.zeros(int(sbins) + 1, dtype=torch.int64, device=dev)
+        m = torch.as_tensor(mask.astype(np.uint8), device=dev)
+        _lib.check(_lib.lib().mouse_director_p2(engine._ptr(vec), engine._ptr(m), fa.n_bonds, (C.c_double * 3)(*rv),
+                                                engine._ptr(out_s), engine._ptr(hist), float(smin), float(smax),
+                                                int(sbins), engine._stream()), "mouse_director_p2")
+        h = hist.cpu().numpy()
+        if h[int(sbins)] > 0:
+            raise IndexError("list index out of range")
+        s_hist["values"] = [float(v) for v in h[:int(sbins)]]
+        if storeAsAtomtypes and not isinstance(config, FrameArrays):
+            s = out_s.cpu().numpy()
+            per_atom = {}
+            for b in np.flatnonzero(mask):
+                for a in fa.bond_atoms[b]:
+                    per_atom.setdefault(int(a), []).append(s[b])
+            atoms = config.atoms()
+            for a, vals in per_atom.items():
+                mval = np.mean(vals)
+                atoms[a].type = ("C" + "%02d" % int(mval * 100)) if mval >= 0. else ("Cm" + "%02d" % int(mval * -100))
+        normHistogram(s_hist, normInternalNorm=True)
+        return s_hist
+
+
+def CalculateComRdfs(config, rmin, rmax, nbin):
+    """Radial distribution of every atom type around the centre of mass - reference ``ordering_functions.py:284-313``:
+    coordinates un-cut with the image flags (``convertCoordsCutToUncut``, ``lammpack_types.py:228-232``), centre =
+    ``Config.com()`` (``:234-248``: masses are used when any atom has one, but the sum is divided by the NUMBER of
+    atoms with mass), one ``calculateRdfForReference(..., excludeSelf=False)`` per type.  Needs the object model
+    (image flags and masses live on the atoms)."""
+    from .lammpack_types import Atom, Vector3d
+    atoms = config.atoms()
+    box = _box3(config)
+    n = len(atoms)
+    pos = np.array([[a.pos.x + box[0] * a.pbc.x, a.pos.y + box[1] * a.pbc.y, a.pos.z + box[2] * a.pbc.z] for a in atoms],
+                   np.float64).reshape(n, 3)
+    masses = np.array([a.mass for a in atoms], np.float64)
+    with_mass = int((masses > 0.).sum())
+    w = masses if with_mass > 0 else np.ones(n)
+    denom = with_mass if with_mass > 0 else n
+    com = np.cumsum(pos * w[:, None], axis=0)[-1] * (1. / float(denom)) if n else np.zeros(3)   # running sum, atom order
+    center = Atom()
+    center.pos = Vector3d(float(com[0]), float(com[1]), float(com[2]))
+    center.num = None
+    types = [a.type for a in atoms]
+    rdfs = {'r': [rmin + (rmax - rmin) * (i + 0.5) / nbin for i in range(nbin)],
+            'v': [4. / 3. * np.pi * ((rmin + (rmax - rmin) * (i + 1) / nbin)**3 - (rmin + (rmax - rmin) * i / nbin)**3)
+                  for i in range(nbin)]}
+    nums = np.array([float(a.num) for a in atoms])
+    resh = np.array([float(hash8(a.res_type)) for a in atoms])
+    molh = np.array([float(hash8(a.mol_id)) for a in atoms])
+    data, norm = {}, {}
+    for atype in set(types):
+        sel = np.fromiter((t == atype for t in types), bool, n)
+        np_atoms = np.array([nums[sel], resh[sel], molh[sel], pos[sel, 0], pos[sel, 1], pos[sel, 2]])
+        rdf = calculateRdfForReference(config, center, np_atoms, rmin=rmin, rmax=rmax, nbin=nbin, excludeSelf=False,
+                                       sameMolecule=True)
+        data[atype] = rdf[0]
+        norm[atype] = np.sum(rdf[0])
+    rdfs['data'], rdfs['norm'] = data, norm
+    return rdfs

@@ -460,3 +460,45 @@ def test_dump_trajectory_matches_the_oracle_frame_by_frame():
         ok = lit["count"] > 0
         s_ref = 1.5 * lit["mean"][ok].sum() / ok.sum() - 0.5
         assert abs(per_frame[f][1] - s_ref) <= RTOL * abs(s_ref)
+
+
+# ------------------------------------------------------------------------------- next rows: director P2, COM RDF
+def test_crystallinity_parameter_against_the_reference():
+    """CalculateCrystallinityParameter (ordering_functions.py:230-282): histogram, labels and recoloured atom types
+    against golden vectors produced by the reference (tests/golden/make_golden_next.py); 'average' crashes with
+    KeyError(0) in the reference and here."""
+    import os
+    from mouse_b200 import ordering_functions as of
+    from mouse_b200.lammpack_misc import read_data_typeselect
+    from mouse_b200.lammpack_types import Vector3d
+    from tests.util import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "next_290.npz"))
+    path = os.path.join(GOLDEN_DIR, "melt_290.data")
+    for tag, rv in (("mean", Vector3d(0., 0., 0.)), ("z", Vector3d(0., 0., 1.)), ("tilt", Vector3d(0.3, -1.2, 0.5))):
+        cfg = read_data_typeselect(path)
+        h = of.CalculateCrystallinityParameter(cfg, ['1'], reference_vector=rv, storeAsAtomtypes=True, mode='histo',
+                                               smin=-0.5, smax=1.0, sbins=40)
+        assert np.array_equal(np.array(h["values"]), g["cryst_%s_values" % tag]), tag
+        assert np.array_equal(np.array(h["norm"]), g["cryst_%s_norm" % tag]) and h["step"] == float(g["cryst_%s_step" % tag])
+        assert [a.type for a in cfg.atoms()] == [str(s) for s in g["cryst_%s_types" % tag]], tag
+    assert str(g["cryst_average_error"]).startswith("KeyError")
+    with pytest.raises(KeyError):
+        of.CalculateCrystallinityParameter(read_data_typeselect(path), ['1'], mode='average')
+
+
+def test_com_rdfs_against_the_reference():
+    """CalculateComRdfs (ordering_functions.py:284-313) with and without masses."""
+    import os
+    from mouse_b200 import ordering_functions as of
+    from mouse_b200.lammpack_misc import read_data_typeselect
+    from tests.util import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "next_290.npz"))
+    path = os.path.join(GOLDEN_DIR, "melt_290.data")
+    for tag in ("nomass", "mass"):
+        cfg = read_data_typeselect(path)
+        if tag == "mass":
+            for k, a in enumerate(cfg.atoms()):
+                a.mass = 1.0 + (k % 3) if k % 2 == 0 else 0.0
+        r = of.CalculateComRdfs(cfg, 0., 4., 32)
+        assert np.array_equal(r["data"]["1"], g["com_%s_data_1" % tag]) and r["norm"]["1"] == g["com_%s_norm_1" % tag]
+        assert np.array_equal(np.array(r["r"]), g["com_%s_r" % tag]) and np.array_equal(np.array(r["v"]), g["com_%s_v" % tag])

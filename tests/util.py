@@ -15,7 +15,7 @@ def golden_names(prefix=""):
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, prefix + "*.npz")))
 
 
-P2_CASES = [n for n in golden_names() if not n.startswith(("rdf_", "ingest_"))]
+P2_CASES = [n for n in golden_names() if not n.startswith(("rdf_", "ingest_", "next_"))]
 RDF_CASES = golden_names("rdf_")
 # the Theta(N^2) literal restatement takes ~5 s on the 9 900-bond case; keep it out of the quick lists
 P2_SMALL_CASES = [n for n in P2_CASES if not n.startswith("config1")]
