@@ -292,8 +292,9 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
   auto issue = [&](const HsItem &it, int pass) {
     const int w0 = pass * NC, w1 = min(it.T, w0 + NC);
     // WAR on the landing zone: every lane's shared-memory reads of the previous contents were issued before the
-    // __syncwarp() that precedes this call (consumer-release ordering, as in TMA producer / consumer pipelines; a
-    // proxy fence is only required after generic-proxy WRITES, which never touch the landing zone)
+    // __syncwarp() that precedes this call; the proxy fence orders them against the async-proxy writes (measured
+    // cost: none)
+    fence_proxy_async();
     if (lane == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)(w1 - w0) * 48u);
     __syncwarp();
     const int a0 = max(it.rt, w0), b0 = min(it.rt + it.rlen, w1);

@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
       const int w1 = min(T, w0 + NC), nvalid = w1 - w0;
       const int npp = (nvalid + 63) >> 6;
       __syncwarp();          // every lane is done with the previous contents
+      fence_proxy_async();
       if (lane == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)nvalid * 48u);
       __syncwarp();
       {
