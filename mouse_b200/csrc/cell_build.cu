@@ -3,7 +3,7 @@
 //
 // K1 restates lammpack_types.py:587-599 (np.remainder form) in un-fused FP64.  K2 has no
 // reference counterpart - the reference is all-pairs (ordering_functions.py:94-115).
-#include "common.cuh"
+#include "half_shell.cuh"
 
 // np.remainder(a, b), b > 0: fmod then shift negatives by +b (NumPy npy_divmod); fmod is exact.
 __device__ __forceinline__ double np_remainder_pos(double a, double b) {
@@ -329,6 +329,18 @@ __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, int n, GridD
   }
 }
 
+// ---- item table of the half-shell sweeps: one thread per home cell (needs >= 3 cells on every axis) -----------------
+__global__ void __launch_bounds__(128) cell_items_kernel(GridDev g, const int32_t *__restrict__ cell_start,
+                                                         int32_t *__restrict__ items) {
+  const int tk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tk >= g.ncell) return;
+  int32_t row[HS_ITEM_INTS];
+  hs_item_row(g, cell_start, tk, row);
+  int4 *dst = reinterpret_cast<int4 *>(items + (size_t)tk * HS_ITEM_INTS);
+#pragma unroll
+  for (int k = 0; k < HS_ITEM_INTS / 4; ++k) dst[k] = make_int4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]);
+}
+
 // ---- K1 + cell assignment + output initialisation in one pass (mouse_p2_frame) -------------------------------
 __global__ void __launch_bounds__(256) bond_assign_kernel(const double *__restrict__ pos, const int2 *__restrict__ bonds,
                                                           const int32_t *__restrict__ mol,
@@ -403,6 +415,10 @@ static int cell_build_tail(int mode, const uint8_t *ref_mask, int64_t n, const m
     MOUSE_LAUNCH_CHECK("scan_top_kernel");
     scan_apply_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start);
     MOUSE_LAUNCH_CHECK("scan_apply_kernel");
+  }
+  if (grid->fast) {
+    cell_items_kernel<<<(grid->ncell + 127) / 128, 128, 0, st>>>(g, w.cell_start, w.items);
+    MOUSE_LAUNCH_CHECK("cell_items_kernel");
   }
   if (n > 0) {
     unsigned nb = (unsigned)((n + 255) / 256);

@@ -96,58 +96,65 @@ __device__ __forceinline__ void hs_range_cells(const GridDev &g, int cx, int cy,
   }
 }
 
-// fetch stage 2: start the loads of home cell tk's range table (cell_start entries) into s_raw, asynchronously
-__device__ __forceinline__ void hs_raw_issue(const GridDev &g, const int32_t *__restrict__ cell_start, int lane,
-                                             int tk, int (*s_raw)[32]) {
+// Per-cell item table (32 ints per cell, written by cell_items_kernel right after the scan, read by the sweeps):
+//   [0..9] first sorted slot of range L, [10..19] its length, [20..29] its offset t in the candidate concatenation,
+//   [30] bonds / atoms in the home cell, [31] cx | cy << 10 | cz << 20 | boundary << 30.
+#define HS_ITEM_INTS 32
+
+__device__ __forceinline__ void hs_item_row(const GridDev &g, const int32_t *__restrict__ cell_start, int tk,
+                                            int32_t *__restrict__ row) {
   int cx, cy, cz;
   hs_cell_coords(g, tk, cx, cy, cz);
-  if (lane == 12) {
-    s_raw[2][12] = cx;
-    s_raw[2][13] = cy;
-    s_raw[2][14] = cz;
-  }
-  if (lane < 10) {
-    int rb, lo, hi;
-    hs_range_cells(g, cx, cy, cz, lane, rb, lo, hi);
+  int t = 0;
+#pragma unroll
+  for (int L = 0; L < 10; ++L) {
+    int rb, lo, hi, src = 0, len = 0;
+    hs_range_cells(g, cx, cy, cz, L, rb, lo, hi);
     if (lo <= hi) {
-      cp_async4(&s_raw[0][lane], cell_start + rb + lo);
-      cp_async4(&s_raw[1][lane], cell_start + rb + hi + 1);
+      src = cell_start[rb + lo];
+      len = cell_start[rb + hi + 1] - src;
     }
-    s_raw[2][lane] = lo <= hi;
-  } else if (lane < 12) {
-    cp_async4(&s_raw[0][lane], cell_start + tk + (lane - 10));   // lanes 10, 11: the home cell itself
+    row[L] = src;
+    row[10 + L] = len;
+    row[20 + L] = t;
+    t += len;
   }
+  const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
+  const int boundary = (cx == 0) | (cx == nx - 1) | (cy == 0) | (cy == ny - 1) | (cz == nz - 1);
+  row[30] = cell_start[tk + 1] - cell_start[tk];
+  row[31] = cx | (cy << 10) | (cz << 20) | (boundary << 30);
+}
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+
+// fetch stage 2: start the (asynchronous) copy of home cell tk's item row into s_raw
+__device__ __forceinline__ void hs_raw_issue(const int32_t *__restrict__ items, int lane, int tk, int *s_raw) {
+  if (lane < HS_ITEM_INTS / 4) cp_async16(s_raw + 4 * lane, items + (size_t)tk * HS_ITEM_INTS + 4 * lane);
   cp_async_commit();
 }
 
-// fetch stage 3: the table of home cell tk has landed in s_raw; false when the cell is empty
-__device__ __forceinline__ bool hs_finalize(const GridDev &g, int lane, int tk, int (*s_raw)[32], HsItem &it) {
+// fetch stage 3: the item row of home cell tk has landed in s_raw; false when the cell is empty
+__device__ __forceinline__ bool hs_finalize(const GridDev &g, int lane, int tk, const int *s_raw, HsItem &it) {
   cp_async_wait_all();
   __syncwarp();
-  const int hs = s_raw[0][10], he = s_raw[0][11];
-  const bool has = lane < 10 && s_raw[2][lane] != 0;
-  const int src = has ? s_raw[0][lane] : 0;
-  const int len = has ? s_raw[1][lane] - src : 0;
-  const int cx = s_raw[2][12], cy = s_raw[2][13], cz = s_raw[2][14];
+  const int l = lane < 10 ? lane : 0;
+  const int src = s_raw[l], len = lane < 10 ? s_raw[10 + l] : 0, rt = s_raw[20 + l];
+  const int T = s_raw[29] + s_raw[19];
+  const int nhome = s_raw[30], packed = s_raw[31];
   __syncwarp();
-  int incl = len;
-#pragma unroll
-  for (int o = 1; o < 16; o <<= 1) {
-    const int y = __shfl_up_sync(MOUSE_FULL_MASK, incl, o);
-    if (lane >= o) incl += y;
-  }
-  const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
+  const int cx = packed & 1023, cy = (packed >> 10) & 1023, cz = (packed >> 20) & 1023;
   it.home = tk;
-  it.hs = hs;
-  it.nhome = he - hs;
-  it.T = __shfl_sync(MOUSE_FULL_MASK, incl, 15);
+  it.hs = __shfl_sync(MOUSE_FULL_MASK, src, 0);      // range 0 starts with the home cell
+  it.nhome = nhome;
+  it.T = T;
   it.rsrc = src;
   it.rlen = len;
-  it.rt = incl - len;
+  it.rt = rt;
   it.hx = ((float)cx + 0.5f) * g.cwf[0] - 0.5f * g.boxf[0];
   it.hy = ((float)cy + 0.5f) * g.cwf[1] - 0.5f * g.boxf[1];
   it.hz = ((float)cz + 0.5f) * g.cwf[2] - 0.5f * g.boxf[2];
-  it.boundary = (cx == 0) | (cx == nx - 1) | (cy == 0) | (cy == ny - 1) | (cz == nz - 1);
-  return he > hs;
+  it.boundary = (packed >> 30) & 1;
+  return nhome > 0;
 }
-

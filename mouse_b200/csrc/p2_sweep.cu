@@ -27,6 +27,7 @@ struct SweepArgs {
   const double4 *U;        // sorted: FP64 unit bond vector, .w = bit pattern of the sorted slot index
   const int32_t *idx;
   const int32_t *cell_start;
+  const int32_t *items;    // per-cell item table of the half-shell sweep (half_shell.cuh)
   const int32_t *cell_sorted;
   const uint8_t *flag;
   const double *vec;       // SoA [3][n], original order
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
   __shared__ double s_acc[HS_GRP][33];                   // per-lane partial sums of 8 references (transposed reduce)
   __shared__ int s_cnt[HS_GRP][33];                      // ... and partial counts
   __shared__ int s_gid[SLOTS][32];                  // sorted slot of every register-resident candidate (-1: empty)
-  __shared__ int s_raw[3][32];                      // range table in flight (fetch stage 2 -> 3)
+  __shared__ __align__(16) int s_raw[HS_ITEM_INTS];                      // range table in flight (fetch stage 2 -> 3)
   __shared__ int s_next[3][32];                     // range table of the prefetched item (kept out of the registers)
   __shared__ float s_nextf[4];
   __shared__ int s_nexti[6];
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
       tkP = (int)atomicAdd((unsigned int *)&a.counters[C_TICKET], 1u);
     }
     tkA = __shfl_sync(MOUSE_FULL_MASK, t0, 0);
-    if (tkA < a.g.ncell) hs_raw_issue(a.g, a.cell_start, lane, tkA, s_raw);
+    if (tkA < a.g.ncell) hs_raw_issue(a.items, lane, tkA, s_raw);
   }
   // next non-empty, regular home cell; false when the grid is exhausted
   auto advance = [&](HsItem &it) -> bool {
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
       const bool nonempty = hs_finalize(a.g, lane, tkA, s_raw, it);
       tkA = __shfl_sync(MOUSE_FULL_MASK, tkP, 0);
       if (lane == 0) tkP = (int)atomicAdd((unsigned int *)&a.counters[C_TICKET], 1u);
-      if (tkA < a.g.ncell) hs_raw_issue(a.g, a.cell_start, lane, tkA, s_raw);
+      if (tkA < a.g.ncell) hs_raw_issue(a.items, lane, tkA, s_raw);
       if (!nonempty) continue;
       if (it.nhome > HS_MAXHOME || it.T > HS_MAXPASS * NC) {
         hs_oversize(a.P, a.counters, a.fix_list, a.fix_cap, a.same_molecule, lane, it.hs, it.nhome, it.rsrc, it.rlen, it.rt);
@@ -663,6 +664,7 @@ int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const
   a.U = w.u_sorted;
   a.idx = w.idx_sorted;
   a.cell_start = w.cell_start;
+  a.items = w.items;
   a.cell_sorted = w.cell_sorted;
   a.flag = w.flag_sorted;
   a.vec = vec;

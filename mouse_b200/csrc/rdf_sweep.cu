@@ -103,6 +103,7 @@ struct RdfHalfArgs {
   const float4 *P;       // sorted: FP32 (wrapped - L/2), .w = type code
   const double4 *U;      // sorted: FP64 absolute position, .w = molecule code
   const int32_t *cell_start;
+  const int32_t *items;
   const double *thr;     // [nbin + 2]: thr[0..nbin] lower thresholds in s = d^2, thr[nbin + 1] = largest s with sqrt(s) <= last
   int nbin, ntypes, same_molecule, use_smem;
   float first, scale;    // bin estimate (sqrtf(s) - first) * scale
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
   __shared__ __align__(128) double4 s_landU[NC];
   __shared__ float4 s_homeP[2][32];                   // reference atoms of the home cell, 32 at a time, double buffered
   __shared__ double4 s_homeU[2][32];
-  __shared__ int s_raw[3][32];
+  __shared__ __align__(16) int s_raw[HS_ITEM_INTS];
   __shared__ __align__(8) uint64_t s_bar;
   const int lane = threadIdx.x;
   const int nbin = a.nbin;
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
       tkP = (int)atomicAdd((unsigned int *)&a.counters[2], 1u);
     }
     tkA = __shfl_sync(MOUSE_FULL_MASK, t0, 0);
-    if (tkA < a.g.ncell) hs_raw_issue(a.g, a.cell_start, lane, tkA, s_raw);
+    if (tkA < a.g.ncell) hs_raw_issue(a.items, lane, tkA, s_raw);
   }
   for (;;) {
     HsItem cur;
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
       const bool nonempty = hs_finalize(a.g, lane, tkA, s_raw, cur);
       tkA = __shfl_sync(MOUSE_FULL_MASK, tkP, 0);
       if (lane == 0) tkP = (int)atomicAdd((unsigned int *)&a.counters[2], 1u);
-      if (tkA < a.g.ncell) hs_raw_issue(a.g, a.cell_start, lane, tkA, s_raw);
+      if (tkA < a.g.ncell) hs_raw_issue(a.items, lane, tkA, s_raw);
       if (nonempty) {
         have = true;
         break;
@@ -344,6 +345,7 @@ int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, 
     h.P = w.p_sorted;
     h.U = w.u_sorted;
     h.cell_start = w.cell_start;
+    h.items = w.items;
     h.thr = w.thr;
     h.nbin = nbin;
     h.ntypes = ntypes;
