@@ -19,6 +19,8 @@
 //    expression per candidate.  Valid for ANY grid (fewer than 3 cells on an axis, rcut < 0,
 //    rmax == 0 -> half diagonal); it also extracts the pair lists and is the automatic fallback when
 //    the pair list of the fast path overflows.
+#include <type_traits>
+
 #include "half_shell.cuh"
 
 struct SweepArgs {
@@ -353,10 +355,11 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     int cntj[SLOTS], molr[SLOTS];
     mbar_wait(&s_bar, phase);
     phase ^= 1u;
-    {
+    // (two copies of the loop, boundary / interior: no branch inside, so all the shared-memory loads batch up)
+    auto load_regs = [&](auto bnd_tag) {
+      constexpr bool BND = decltype(bnd_tag)::value;
       const float Lx = a.g.boxf[0], Ly = a.g.boxf[1], Lz = a.g.boxf[2];
       const float iLx = a.g.inv_boxf[0], iLy = a.g.inv_boxf[1], iLz = a.g.inv_boxf[2];
-      const bool bnd = cur.boundary != 0;
 #pragma unroll
       for (int pp = 0; pp < NPAIR; ++pp) {
         float q[2][3];
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
           const float4 p = s_landP[tl];
           const double4 u = s_landU[tl];
           float px = p.x, py = p.y, pz = p.z;
-          if (bnd) {     // nearest periodic image to the home cell centre
+          if (BND) {     // nearest periodic image to the home cell centre
             px -= Lx * rintf((px - cur.hx) * iLx);
             py -= Ly * rintf((py - cur.hy) * iLy);
             pz -= Lz * rintf((pz - cur.hz) * iLz);
@@ -394,7 +397,9 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
         yr2[pp] = make_float2(q[0][1], q[1][1]);
         zr2[pp] = make_float2(q[0][2], q[1][2]);
       }
-    }
+    };
+    if (cur.boundary) load_regs(std::true_type{});
+    else load_regs(std::false_type{});
     __syncwarp();
 
     // ---- re-arm the landing zone: next pass of this home cell, or pass 0 of the next one
