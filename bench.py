@@ -375,7 +375,7 @@ def run_ours(args):
             "dtype": "f64 (packed FP32 cutoff filter with exact FP64 re-check, FP64 cos^2, 2^-47 fixed-point sums)", "data": "synthetic",
             "config": {"workload": WORKLOAD["name"], "bonds_per_frame": n, "frames_per_step_per_gpu": 1,
                        "pairs_per_frame": pairs_local // steps, "cell_grid": list(grid.ncell_axis),
-                       "l2": "inputs larger than L2: ~210 MB touched per frame (> 126 MB L2), %d distinct frames cycled"
+                       "l2": "working set larger than L2: ~230 MB touched per frame (> 126 MB L2), %d distinct frames cycled"
                              % N_FRAME_VARIANTS,
                        "parallelism": "frames sharded, %d rank(s), one NCCL all-reduce of packed sums" % world,
                        "S_mean": totals.mean_s},
