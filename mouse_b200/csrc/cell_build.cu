@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) cell_assign_kernel(const double *__restri
                                                           int32_t *__restrict__ rank_of,
                                                           int32_t *__restrict__ cell_count,
                                                           int64_t *__restrict__ counters,
-                                                          float4 *__restrict__ p_tmp, double4 *__restrict__ u_tmp) {
+                                                          Rec *__restrict__ rec_tmp) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
   bool in_list;
@@ -120,8 +120,10 @@ __global__ void __launch_bounds__(256) cell_assign_kernel(const double *__restri
   int cid = (kz * g.nc[1] + ky) * g.nc[0] + kx;
   cell_of[b] = cid;
   rank_of[b] = atomicAdd(&cell_count[cid], 1);
-  p_tmp[b] = payload_p(xw, yw, zw, g, type ? type[b] : 0);
-  u_tmp[b] = MODE == 0 ? payload_u_bond(vx, vy, vz) : make_double4(cx, cy, cz, code2 ? (double)code2[b] : 0.0);
+  Rec r;
+  r.p = payload_p(xw, yw, zw, g, type ? type[b] : 0);
+  r.u = MODE == 0 ? payload_u_bond(vx, vy, vz) : make_double4(cx, cy, cz, code2 ? (double)code2[b] : 0.0);
+  rec_tmp[b] = r;
 }
 
 // ---- exclusive scan of cell_count[0..nc) -> cell_start, three small kernels ----------------
@@ -284,10 +286,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, int n, GridDev g,
                                                          const int32_t *__restrict__ cell_start,
                                                          const int32_t *__restrict__ idx_tmp,
-                                                         const float4 *__restrict__ p_tmp,
-                                                         const double4 *__restrict__ u_tmp,
-                                                         float4 *__restrict__ p_sorted,
-                                                         double4 *__restrict__ u_sorted,
+                                                         const Rec *__restrict__ rec_tmp,
+                                                         Rec *__restrict__ rec_sorted,
                                                          int32_t *__restrict__ idx_sorted,
                                                          int32_t *__restrict__ cell_sorted,
                                                          uint8_t *__restrict__ flag_sorted,
@@ -314,11 +314,10 @@ __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, int n, GridD
       }
       if (m < nc) {
         const int d = s + rank;
-        p_sorted[d] = p_tmp[mine];
-        double4 u = u_tmp[mine];
+        Rec r = rec_tmp[mine];
         // .w carries the sorted slot itself: the sweep's register-resident candidates know where they live
-        if (MODE == 0) u.w = __hiloint2double(0, d);
-        u_sorted[d] = u;
+        if (MODE == 0) r.u.w = __hiloint2double(0, d);
+        rec_sorted[d] = r;
         idx_sorted[d] = mine;
         cell_sorted[d] = c;
         flag_sorted[d] = (uint8_t)((unsigned)raw >> 31);
@@ -348,8 +347,8 @@ __global__ void __launch_bounds__(256) bond_assign_kernel(const double *__restri
                                                           double *__restrict__ vec, double *__restrict__ ctr,
                                                           int32_t *__restrict__ cell_of, int32_t *__restrict__ rank_of,
                                                           int32_t *__restrict__ cell_count,
-                                                          int64_t *__restrict__ counters, float4 *__restrict__ p_tmp,
-                                                          double4 *__restrict__ u_tmp, double *__restrict__ out_sum,
+                                                          int64_t *__restrict__ counters, Rec *__restrict__ rec_tmp,
+                                                          double *__restrict__ out_sum,
                                                           int32_t *__restrict__ out_cnt, double *__restrict__ out_mean) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
@@ -386,8 +385,10 @@ __global__ void __launch_bounds__(256) bond_assign_kernel(const double *__restri
   int cid = (kz * g.nc[1] + ky) * g.nc[0] + kx;
   cell_of[b] = cid;
   rank_of[b] = atomicAdd(&cell_count[cid], 1);
-  p_tmp[b] = payload_p(xw, yw, zw, g, mol ? mol[b] : 0);
-  u_tmp[b] = payload_u_bond(vx, vy, vz);
+  Rec r;
+  r.p = payload_p(xw, yw, zw, g, mol ? mol[b] : 0);
+  r.u = payload_u_bond(vx, vy, vz);
+  rec_tmp[b] = r;
 }
 
 // ---- host-side launchers ------------------------------------------------------------------------
@@ -428,12 +429,12 @@ static int cell_build_tail(int mode, const uint8_t *ref_mask, int64_t n, const m
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
     if (mode == 0)
-      cell_canon_kernel<0><<<blocks, 256, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.p_tmp, w.u_tmp,
-                                                   w.p_sorted, w.u_sorted, w.idx_sorted, w.cell_sorted,
+      cell_canon_kernel<0><<<blocks, 256, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.rec_sorted,
+                                                   w.idx_sorted, w.cell_sorted,
                                                    w.flag_sorted, w.acc_fix, w.acc_cnt);
     else
-      cell_canon_kernel<1><<<blocks, 256, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.p_tmp, w.u_tmp,
-                                                   w.p_sorted, w.u_sorted, w.idx_sorted, w.cell_sorted,
+      cell_canon_kernel<1><<<blocks, 256, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.rec_sorted,
+                                                   w.idx_sorted, w.cell_sorted,
                                                    w.flag_sorted, w.acc_fix, w.acc_cnt);
     MOUSE_LAUNCH_CHECK("cell_canon_kernel");
   }
@@ -451,10 +452,10 @@ int mouse_launch_cell_build(int mode, const double *xyz, const double *vec, cons
   if (n > 0) {
     if (mode == 0)
       cell_assign_kernel<0><<<nb, 256, 0, st>>>(xyz, vec, nbr_mask, code, nullptr, (int)n, g, w.cell_of, w.rank_of,
-                                                w.cell_count, w.counters, w.p_tmp, w.u_tmp);
+                                                w.cell_count, w.counters, w.rec_tmp);
     else
       cell_assign_kernel<1><<<nb, 256, 0, st>>>(xyz, nullptr, nullptr, code, code2, (int)n, g, w.cell_of, w.rank_of,
-                                                w.cell_count, w.counters, w.p_tmp, w.u_tmp);
+                                                w.cell_count, w.counters, w.rec_tmp);
     MOUSE_LAUNCH_CHECK("cell_assign_kernel");
   }
   return cell_build_tail(mode, ref_mask, n, grid, g, w, st);
@@ -470,7 +471,7 @@ int mouse_launch_frame_build(const double *pos, const int32_t *bond_atoms, const
   if (n > 0) {
     bond_assign_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pos, (const int2 *)bond_atoms, mol, nbr_mask, (int)n,
                                                                      g, vec, ctr, w.cell_of, w.rank_of, w.cell_count,
-                                                                     w.counters, w.p_tmp, w.u_tmp, out_sum, out_cnt,
+                                                                     w.counters, w.rec_tmp, out_sum, out_cnt,
                                                                      out_mean);
     MOUSE_LAUNCH_CHECK("bond_assign_kernel");
   }

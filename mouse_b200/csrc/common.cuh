@@ -30,6 +30,16 @@ void mouse_set_error(const char *fmt, ...);
     }                                                                                     \
   } while (0)
 
+// One item of a cell list as the sweeps consume it: 48 bytes, 16-byte aligned, so that one 1-D TMA bulk copy moves a
+// whole range of items and a 48-byte stride is conflict-free for 128-bit shared-memory loads.
+//   p = FP32 (wrapped coordinate - L/2) x, y, z + molecule (P2) / type (RDF) code bits in .w
+//   u = P2: FP64 unit bond vector, .w = bit pattern of the item's own sorted slot;  RDF: absolute position, .w = molecule code
+struct __align__(16) Rec {
+  float4 p;
+  double4 u;
+};
+static_assert(sizeof(Rec) == 48, "Rec must be 48 bytes");
+
 // ------------------------------------------------------------------ workspace layout
 // Everything the cell list and the sweeps need, carved out of one caller-provided buffer.
 struct Workspace {
@@ -42,12 +52,10 @@ struct Workspace {
   int32_t *cell_of;      // [n] cell id or -1 (not in the list)
   int32_t *rank_of;      // [n] arrival rank inside the cell (atomic order, canonicalised later)
   // per item, cell-sorted (ascending original index inside a cell)
-  float4 *p_tmp;         // [n] payload in ORIGINAL order (built by the assign kernel, gathered by the canon kernel)
-  double4 *u_tmp;        // [n]   ... p_tmp + u_tmp (48 B per item, contiguous) are reused after the build as the
-                         //       fast sweep's pair list (int2 entries) for the exact fixup kernel
+  Rec *rec_tmp;          // [n] payload in ORIGINAL order (built by the assign kernel, gathered by the canon kernel);
+                         //     reused after the build as the fast sweep's pair list (6 int2 entries per item)
   int32_t *idx_tmp;      // [n] original index (| ref bit), arrival order
-  float4 *p_sorted;      // [n] FP32 (wrapped coordinate - L/2) x,y,z + molecule/type code bits
-  double4 *u_sorted;     // [n] unit bond vector (FP64), .w = sorted slot index bits (P2)  /  absolute position + molecule code (RDF)
+  Rec *rec_sorted;       // [n] the payload in cell-sorted order
   int32_t *idx_sorted;
   int32_t *cell_sorted;  // [n] cell id of each sorted slot
   uint8_t *flag_sorted;  // [n] bit0 = acts as reference
@@ -89,11 +97,9 @@ static inline Workspace mouse_carve(void *ws, int64_t n, int32_t ncell) {
   CARVE(items, int32_t, 32 * nc)
   CARVE(cell_of, int32_t, nn)
   CARVE(rank_of, int32_t, nn)
-  CARVE(p_tmp, float4, nn)
-  CARVE(u_tmp, double4, nn)
+  CARVE(rec_tmp, Rec, nn)
   CARVE(idx_tmp, int32_t, nn)
-  CARVE(p_sorted, float4, nn)
-  CARVE(u_sorted, double4, nn)
+  CARVE(rec_sorted, Rec, nn)
   CARVE(idx_sorted, int32_t, nn)
   CARVE(cell_sorted, int32_t, nn)
   CARVE(flag_sorted, uint8_t, nn)

@@ -25,8 +25,8 @@
 
 struct SweepArgs {
   GridDev g;
-  const float4 *P;         // sorted: FP32 (wrapped midpoint - L/2), molecule code bits in .w
-  const double4 *U;        // sorted: FP64 unit bond vector, .w = bit pattern of the sorted slot index
+  const Rec *R;            // sorted items: .p FP32 (wrapped midpoint - L/2) + molecule code bits, .u FP64 unit bond
+                           // vector with .w = bit pattern of the sorted slot index
   const int32_t *idx;
   const int32_t *cell_start;
   const int32_t *items;    // per-cell item table of the half-shell sweep (half_shell.cuh)
@@ -99,7 +99,7 @@ __device__ __forceinline__ void fix_append(int64_t *counters, int2 *fix_list, lo
 }
 
 // every pair of an oversized home cell goes to the pair list
-__device__ __noinline__ void hs_oversize(const float4 *__restrict__ P, int64_t *counters, int2 *fix_list,
+__device__ __noinline__ void hs_oversize(const Rec *__restrict__ R, int64_t *counters, int2 *fix_list,
                                          long long fix_cap, int same_molecule, int lane, int hs, int nhome, int rsrc,
                                          int rlen, int rt0) {
   for (int r = 0; r < 10; ++r) {
@@ -107,10 +107,10 @@ __device__ __noinline__ void hs_oversize(const float4 *__restrict__ P, int64_t *
     const int rt = __shfl_sync(MOUSE_FULL_MASK, rt0, r);
     for (int k = lane; k < len; k += 32) {
       const int sj = src + k, tj = rt + k;
-      const int molj = __float_as_int(P[sj].w);
+      const int molj = __float_as_int(R[sj].p.w);
       for (int il = 0; il < nhome; ++il) {
         if (tj <= il) continue;                                   // home-home pairs once (j > i)
-        if (!same_molecule && __float_as_int(P[hs + il].w) == molj) continue;
+        if (!same_molecule && __float_as_int(R[hs + il].p.w) == molj) continue;
         fix_append(counters, fix_list, fix_cap, hs + il, sj, 0);
       }
     }
@@ -265,8 +265,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
   constexpr int NPAIR = SLOTS / 2;
   constexpr int HSL = HS_MAXHOME / 32;
   static_assert(SLOTS % 2 == 0 && NC >= HS_MAXHOME && NPAIR <= 6, "slots come in pairs; the home cell lives in pass 0");
-  __shared__ __align__(128) float4 s_landP[NC];     // TMA landing zone
-  __shared__ __align__(128) double4 s_landU[NC];
+  __shared__ __align__(128) Rec s_land[NC];         // TMA landing zone
   __shared__ float4 s_homeP[HS_MAXHOME];            // the home cell's bonds: the references of this item
   __shared__ double s_homeU[3][HS_MAXHOME];
   __shared__ double s_acc[HS_GRP][33];                   // per-lane partial sums of 8 references (transposed reduce)
@@ -303,8 +302,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     const int a0 = max(it.rt, w0), b0 = min(it.rt + it.rlen, w1);
     if (b0 > a0) {
       const int src = it.rsrc + (a0 - it.rt), cnt = b0 - a0, dst = a0 - w0;
-      tma_load_1d(&s_landP[dst], a.P + src, (uint32_t)cnt * 16u, &s_bar);
-      tma_load_1d(&s_landU[dst], a.U + src, (uint32_t)cnt * 32u, &s_bar);
+      tma_load_1d(&s_land[dst], a.R + src, (uint32_t)cnt * 48u, &s_bar);
     }
   };
 
@@ -332,7 +330,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
       if (tkA < a.g.ncell) hs_raw_issue(a.items, lane, tkA, s_raw);
       if (!nonempty) continue;
       if (it.nhome > HS_MAXHOME || it.T > HS_MAXPASS * NC) {
-        hs_oversize(a.P, a.counters, a.fix_list, a.fix_cap, a.same_molecule, lane, it.hs, it.nhome, it.rsrc, it.rlen, it.rt);
+        hs_oversize(a.R, a.counters, a.fix_list, a.fix_cap, a.same_molecule, lane, it.hs, it.nhome, it.rsrc, it.rlen, it.rt);
         continue;
       }
       return true;
@@ -368,8 +366,8 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
           const int c = 2 * pp + h;
           const int tl = 32 * c + lane;
           const bool valid = tl < nvalid;
-          const float4 p = s_landP[tl];
-          const double4 u = s_landU[tl];
+          const float4 p = s_land[tl].p;
+          const double4 u = s_land[tl].u;
           float px = p.x, py = p.y, pz = p.z;
           if (BND) {     // nearest periodic image to the home cell centre
             px -= Lx * rintf((px - cur.hx) * iLx);
@@ -534,7 +532,7 @@ __global__ void __launch_bounds__(128) p2_sweep_exact_kernel(const SweepArgs a) 
     const double cix = a.ctr[bi], ciy = a.ctr[n + bi], ciz = a.ctr[2 * n + bi];
     const double bix = a.vec[bi], biy = a.vec[n + bi], biz = a.vec[2 * n + bi];
     const double nr = __dadd_rn(__dadd_rn(__dmul_rn(bix, bix), __dmul_rn(biy, biy)), __dmul_rn(biz, biz));
-    const int moli = __float_as_int(a.P[s].w);
+    const int moli = __float_as_int(a.R[s].p.w);
     const int home = a.cell_sorted[s];
     const int cx = home % nx, cy = (home / nx) % ny, cz = home / (nx * ny);
     // neighbour cells per axis: {c-1, c, c+1} wrapped when the axis has >= 3 cells, else all cells
@@ -553,7 +551,7 @@ __global__ void __launch_bounds__(128) p2_sweep_exact_kernel(const SweepArgs a) 
           const int ts = a.cell_start[cid], te = a.cell_start[cid + 1];
           for (int t = ts; t < te; ++t) {
             if (t == s) continue;
-            if (!a.same_molecule && __float_as_int(a.P[t].w) == moli) continue;
+            if (!a.same_molecule && __float_as_int(a.R[t].p.w) == moli) continue;
             const int bj = a.idx[t];
             if (!a.no_cutoff) {
               double rsq = mouse_rsq_exact(cix, ciy, ciz, a.ctr[bj], a.ctr[n + bj], a.ctr[2 * n + bj], a.g.box);
@@ -665,8 +663,7 @@ int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const
                           int32_t *nbr_idx, int frame_mode, int *used_fast, cudaStream_t st) {
   SweepArgs a;
   a.g = mouse_grid_dev(grid);
-  a.P = w.p_sorted;
-  a.U = w.u_sorted;
+  a.R = w.rec_sorted;
   a.idx = w.idx_sorted;
   a.cell_start = w.cell_start;
   a.items = w.items;
@@ -682,8 +679,8 @@ int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const
   a.nbr_idx = nbr_idx;
   a.acc_fix = w.acc_fix;
   a.acc_cnt = w.acc_cnt;
-  a.fix_list = (int2 *)w.p_tmp;      // p_tmp / u_tmp are free once the cell list is built
-  a.fix_cap = (long long)(((char *)w.idx_tmp - (char *)w.p_tmp) / sizeof(int2));
+  a.fix_list = (int2 *)w.rec_tmp;    // the original-order payload is dead once the cell list is built
+  a.fix_cap = 6LL * (n > 0 ? n : 1);
   a.same_molecule = (flags & MOUSE_SAME_MOLECULE) ? 1 : 0;
   a.no_cutoff = (flags & MOUSE_NO_CUTOFF) ? 1 : 0;
   a.only_if_overflow = 0;

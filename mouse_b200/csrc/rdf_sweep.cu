@@ -10,8 +10,7 @@
 
 struct RdfArgs {
   GridDev g;
-  const float4 *P;       // .w = type code
-  const double4 *U;      // absolute position (FP64) + molecule code in .w
+  const Rec *R;          // .p.w = type code; .u = absolute position (FP64) + molecule code in .w
   const int32_t *cell_start;
   const int32_t *cell_sorted;
   const double *edges;   // [nbin+1] device
@@ -46,8 +45,8 @@ __global__ void __launch_bounds__(128) rdf_sweep_exact_kernel(const RdfArgs a) {
   const double first = a.edges[0], last = a.edges[a.nbin];
   const double Lx = a.g.box[0], Ly = a.g.box[1], Lz = a.g.box[2];
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_list; s += gridDim.x * blockDim.x) {
-    const double4 pi = a.U[s];
-    const int ti = __float_as_int(a.P[s].w);
+    const double4 pi = a.R[s].u;
+    const int ti = __float_as_int(a.R[s].p.w);
     const int home = a.cell_sorted[s];
     const int cx = home % nx, cy = (home / nx) % ny, cz = home / (nx * ny);
     const int mx = nx >= 3 ? 3 : nx, my = ny >= 3 ? 3 : ny, mz = nz >= 3 ? 3 : nz;
@@ -61,7 +60,7 @@ __global__ void __launch_bounds__(128) rdf_sweep_exact_kernel(const RdfArgs a) {
           const int ts = a.cell_start[cid], te = a.cell_start[cid + 1];
           for (int t = ts; t < te; ++t) {
             if (t == s) continue;
-            const double4 pj = a.U[t];
+            const double4 pj = a.R[t].u;
             if (!a.same_molecule && pj.w == pi.w) continue;
             const double tx = mouse_trim(__dsub_rn(pj.x, pi.x), Lx);
             const double ty = mouse_trim(__dsub_rn(pj.y, pi.y), Ly);
@@ -70,7 +69,7 @@ __global__ void __launch_bounds__(128) rdf_sweep_exact_kernel(const RdfArgs a) {
             if (d == 0.0) continue;  // np.ma.masked_equal(d, 0.) also drops coincident atoms (:84)
             const int k = np_bin(d, first, last, a.nbin, a.edges);
             if (k < 0) continue;
-            const int tj = __float_as_int(a.P[t].w);
+            const int tj = __float_as_int(a.R[t].p.w);
             const int ta = min(ti, tj), tb = max(ti, tj);
             const int slot = ta * a.ntypes - ta * (ta - 1) / 2 + (tb - ta);
             if (a.use_smem) atomicAdd(&s_hist[slot * a.nbin + k], 1u);
@@ -100,8 +99,7 @@ __global__ void __launch_bounds__(128) rdf_sweep_exact_kernel(const RdfArgs a) {
 
 struct RdfHalfArgs {
   GridDev g;
-  const float4 *P;       // sorted: FP32 (wrapped - L/2), .w = type code
-  const double4 *U;      // sorted: FP64 absolute position, .w = molecule code
+  const Rec *R;          // sorted items: .p FP32 (wrapped - L/2) + type code, .u FP64 absolute position + molecule code
   const int32_t *cell_start;
   const int32_t *items;
   const double *thr;     // [nbin + 2]: thr[0..nbin] lower thresholds in s = d^2, thr[nbin + 1] = largest s with sqrt(s) <= last
@@ -142,8 +140,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
   constexpr int NC = SLOTS * 32;
   constexpr int NPAIR = SLOTS / 2;
   extern __shared__ unsigned int s_hist[];            // [npairs * nbin] when use_smem
-  __shared__ __align__(128) float4 s_landP[NC];       // TMA landing zone; stays valid for the whole pass
-  __shared__ __align__(128) double4 s_landU[NC];
+  __shared__ __align__(128) Rec s_land[NC];           // TMA landing zone; stays valid for the whole pass
   __shared__ float4 s_homeP[2][32];                   // reference atoms of the home cell, 32 at a time, double buffered
   __shared__ double4 s_homeU[2][32];
   __shared__ __align__(16) int s_raw[HS_ITEM_INTS];
@@ -163,8 +160,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
   const double Lx = a.g.box[0], Ly = a.g.box[1], Lz = a.g.box[2];
   const double hLx = 0.5 * Lx, hLy = 0.5 * Ly, hLz = 0.5 * Lz;
   const float2 nr2 = make_float2(-a.r2hi, -a.r2hi);
-  const double4 *landU_lane = s_landU + lane;    // candidate (slot c, this lane) = element c * 32
-  const float4 *landP_lane = s_landP + lane;
+  const Rec *land_lane = s_land + lane;          // candidate (slot c, this lane) = element c * 32
 
   // fetch pipeline (see p2_sweep_half_kernel): ticket one item ahead, range table one item ahead
   int tkA, tkP = 0;
@@ -206,16 +202,15 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
         const int a0 = max(cur.rt, w0), b0 = min(cur.rt + cur.rlen, w1);
         if (b0 > a0) {
           const int src = cur.rsrc + (a0 - cur.rt), cnt = b0 - a0, dst = a0 - w0;
-          tma_load_1d(&s_landP[dst], a.P + src, (uint32_t)cnt * 16u, &s_bar);
-          tma_load_1d(&s_landU[dst], a.U + src, (uint32_t)cnt * 32u, &s_bar);
+          tma_load_1d(&s_land[dst], a.R + src, (uint32_t)cnt * 48u, &s_bar);
         }
       }
       // the first chunk of reference atoms is fetched while the bulk copies fly
       float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
       double4 hu = make_double4(0.0, 0.0, 0.0, 0.0);
       if (lane < nhome) {
-        hp = a.P[hs + lane];
-        hu = a.U[hs + lane];
+        hp = a.R[hs + lane].p;
+        hu = a.R[hs + lane].u;
       }
       mbar_wait(&s_bar, phase);
       phase ^= 1u;
@@ -228,7 +223,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int tl = 32 * (2 * pp + h) + lane;
-            const float4 p = s_landP[tl];
+            const float4 p = s_land[tl].p;
             float px = p.x, py = p.y, pz = p.z;
             if (bnd) {     // nearest periodic image to the home cell centre
               px -= Lxf * rintf((px - cur.hx) * a.g.inv_boxf[0]);
@@ -253,8 +248,8 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
         const int nchunk = min(32, nhome - chunk0);
         // next chunk of reference atoms: loaded now, stored after this chunk has been processed
         if (chunk0 + 32 + lane < nhome) {
-          hp = a.P[hs + chunk0 + 32 + lane];
-          hu = a.U[hs + chunk0 + 32 + lane];
+          hp = a.R[hs + chunk0 + 32 + lane].p;
+          hu = a.R[hs + chunk0 + 32 + lane].u;
         }
         for (int il = 0; il < nchunk; ++il) {
           const float4 pi = s_homeP[buf][il];
@@ -284,7 +279,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
             const bool act = mask != 0;
             const int c = (int)min((unsigned)(31 - __clz((int)mask)), (unsigned)(SLOTS - 1));   // mask == 0 -> clamped
             mask &= ~(1u << c);
-            const double4 uj = landU_lane[c * 32];
+            const double4 uj = land_lane[c * 32].u;
             double tx = __dsub_rn(uj.x, ui.x), ty = __dsub_rn(uj.y, ui.y), tz = __dsub_rn(uj.z, ui.z);
             // dr - L * around(dr / L): around() is 0 whenever |dr| <= L / 2 (ordering_functions.py:72-74); one
             // rare branch for coordinates that were not wrapped into the box
@@ -308,7 +303,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
             k -= (s < tlo && k > 0) ? 1 : 0;
             int slot = 0;
             if (a.ntypes > 1) {     // warp-uniform
-              const int tj = __float_as_int(landP_lane[c * 32].w);
+              const int tj = __float_as_int(land_lane[c * 32].p.w);
               const int ta = min(ti, tj), tb = max(ti, tj);
               slot = (ta * a.ntypes - ta * (ta - 1) / 2 + (tb - ta)) * nbin;
             }
@@ -342,8 +337,7 @@ int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, 
   if (fast) {
     RdfHalfArgs h;
     h.g = mouse_grid_dev(grid);
-    h.P = w.p_sorted;
-    h.U = w.u_sorted;
+    h.R = w.rec_sorted;
     h.cell_start = w.cell_start;
     h.items = w.items;
     h.thr = w.thr;
@@ -378,8 +372,7 @@ int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, 
   }
   RdfArgs a;
   a.g = mouse_grid_dev(grid);
-  a.P = w.p_sorted;
-  a.U = w.u_sorted;
+  a.R = w.rec_sorted;
   a.cell_start = w.cell_start;
   a.cell_sorted = w.cell_sorted;
   a.edges = edges_dev;
