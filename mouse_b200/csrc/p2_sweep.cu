@@ -239,13 +239,19 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
       __syncwarp();
       constexpr int PER = 32 / HS_GRP * 2;            // 32 / HS_GRP lanes share a reference, PER partials each
       const int row = lane & (HS_GRP - 1), part = lane / HS_GRP;
-      double v = 0.0;
+      // fixed pairwise tree (deterministic, log-depth dependency chain)
+      double pv[HS_GRP];
       int nv = 0;
 #pragma unroll
       for (int q = 0; q < HS_GRP; ++q) {
-        v += s_acc[row][part * HS_GRP + q];
+        pv[q] = s_acc[row][part * HS_GRP + q];
         nv += s_cnt[row][part * HS_GRP + q];
       }
+#pragma unroll
+      for (int w = 1; w < HS_GRP; w <<= 1)
+#pragma unroll
+        for (int q = 0; q + w < HS_GRP; q += 2 * w) pv[q] += pv[q + w];
+      double v = pv[0];
       (void)PER;
 #pragma unroll
       for (int o = HS_GRP; o < 32; o <<= 1) {
