@@ -135,7 +135,27 @@ __global__ void rdf_thresholds_kernel(const double *__restrict__ edges, int nbin
   }
 }
 
-template <int SLOTS>
+// explicit shared-memory accesses with a 32-bit address held in a register (the compiler otherwise rebuilds the
+// shared window base with uniform-datapath instructions at every use inside the hit walk)
+__device__ __forceinline__ double4 lds_double4(uint32_t addr) {
+  double4 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%4];\nld.shared.v2.f64 {%2, %3}, [%4+16];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
+               : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int lds_int(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void reds_add(uint32_t addr, unsigned v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// SAME_MOL: pairs inside one molecule count (reference sameMolecule=True); ONE_TYPE: a single type-pair key;
+// SMEM_HIST: the histogram fits the per-warp shared-memory copy
+template <int SLOTS, bool SAME_MOL, bool ONE_TYPE, bool SMEM_HIST>
 __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfHalfArgs a) {
   constexpr int NC = SLOTS * 32;
   constexpr int NPAIR = SLOTS / 2;
@@ -148,7 +168,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
   const int lane = threadIdx.x;
   const int nbin = a.nbin;
   const int hsize = a.ntypes * (a.ntypes + 1) / 2 * nbin;
-  if (a.use_smem)
+  if (SMEM_HIST)
     for (int k = lane; k < hsize; k += 32) s_hist[k] = 0;
   if (lane == 0) {
     mbar_init(&s_bar, 1);
@@ -160,7 +180,8 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
   const double Lx = a.g.box[0], Ly = a.g.box[1], Lz = a.g.box[2];
   const double hLx = 0.5 * Lx, hLy = 0.5 * Ly, hLz = 0.5 * Lz;
   const float2 nr2 = make_float2(-a.r2hi, -a.r2hi);
-  const Rec *land_lane = s_land + lane;          // candidate (slot c, this lane) = element c * 32
+  const uint32_t land_lane = smem_addr(s_land + lane);   // candidate (slot c, this lane) = element c * 32
+  const uint32_t hist_base = smem_addr(s_hist);
 
   // fetch pipeline (see p2_sweep_half_kernel): ticket one item ahead, range table one item ahead
   int tkA, tkP = 0;
@@ -279,7 +300,8 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
             const bool act = mask != 0;
             const int c = (int)min((unsigned)(31 - __clz((int)mask)), (unsigned)(SLOTS - 1));   // mask == 0 -> clamped
             mask &= ~(1u << c);
-            const double4 uj = land_lane[c * 32].u;
+            const uint32_t cand = land_lane + (uint32_t)c * (32u * 48u);
+            const double4 uj = lds_double4(cand + 16u);
             double tx = __dsub_rn(uj.x, ui.x), ty = __dsub_rn(uj.y, ui.y), tz = __dsub_rn(uj.z, ui.z);
             // dr - L * around(dr / L): around() is 0 whenever |dr| <= L / 2 (ordering_functions.py:72-74); one
             // rare branch for coordinates that were not wrapped into the box
@@ -291,7 +313,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
             const double s = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
             // np.ma.masked_equal(d, 0.) drops coincident atoms (:84); values outside [first, last] are dropped (:86)
             bool keep = act && s != 0.0 && s >= thr0 && s <= shi;
-            if (!a.same_molecule) keep = keep && uj.w != ui.w;
+            if (!SAME_MOL) keep = keep && uj.w != ui.w;
             // bin estimate from an FP32 square root (error << one bin), made exact with the two thresholds around it
             const float sf = fmaxf((float)s, 1.0e-30f);
             float rs;
@@ -302,13 +324,13 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
             k += (s >= thi && k < nbin - 1) ? 1 : 0;
             k -= (s < tlo && k > 0) ? 1 : 0;
             int slot = 0;
-            if (a.ntypes > 1) {     // warp-uniform
-              const int tj = __float_as_int(land_lane[c * 32].p.w);
+            if (!ONE_TYPE) {
+              const int tj = lds_int(cand + 12u);
               const int ta = min(ti, tj), tb = max(ti, tj);
               slot = (ta * a.ntypes - ta * (ta - 1) / 2 + (tb - ta)) * nbin;
             }
             if (keep) {
-              if (a.use_smem) atomicAdd(&s_hist[slot + k], 2u);
+              if (SMEM_HIST) reds_add(hist_base + 4u * (uint32_t)(slot + k), 2u);
               else atomicAdd(&a.hist[(size_t)(slot + k)], 2ULL);
             }
           }
@@ -320,11 +342,27 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
       }
     }
   }
-  if (a.use_smem) {
+  if (SMEM_HIST) {
     __syncwarp();
     for (int k = lane; k < hsize; k += 32)
       if (s_hist[k]) atomicAdd(&a.hist[k], (unsigned long long)s_hist[k]);
   }
+}
+
+template <bool SAME_MOL, bool ONE_TYPE, bool SMEM_HIST>
+static void launch_rdf_half(const RdfHalfArgs &h, int ncell, size_t smem, cudaStream_t st) {
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rdf_sweep_half_kernel<8, SAME_MOL, ONE_TYPE, SMEM_HIST>,
+                                                  32, SMEM_HIST ? 4096 : 0);
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int blocks = sms * blocks_per_sm;
+  if (blocks > ncell) blocks = ncell;
+  rdf_sweep_half_kernel<8, SAME_MOL, ONE_TYPE, SMEM_HIST><<<blocks, 32, smem, st>>>(h);
 }
 
 int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, int32_t ntypes,
@@ -356,17 +394,17 @@ int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, 
     if (!h.use_smem) smem = 0;
     rdf_thresholds_kernel<<<(nbin + 2 + 127) / 128, 128, 0, st>>>(edges_dev, nbin, w.thr);
     MOUSE_LAUNCH_CHECK("rdf_thresholds_kernel");
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rdf_sweep_half_kernel<8>, 32, 4096);
-      if (blocks_per_sm < 1) blocks_per_sm = 1;
+    const int key = (h.same_molecule ? 4 : 0) | (ntypes == 1 ? 2 : 0) | (h.use_smem ? 1 : 0);
+    switch (key) {
+      case 0: launch_rdf_half<false, false, false>(h, grid->ncell, smem, st); break;
+      case 1: launch_rdf_half<false, false, true>(h, grid->ncell, smem, st); break;
+      case 2: launch_rdf_half<false, true, false>(h, grid->ncell, smem, st); break;
+      case 3: launch_rdf_half<false, true, true>(h, grid->ncell, smem, st); break;
+      case 4: launch_rdf_half<true, false, false>(h, grid->ncell, smem, st); break;
+      case 5: launch_rdf_half<true, false, true>(h, grid->ncell, smem, st); break;
+      case 6: launch_rdf_half<true, true, false>(h, grid->ncell, smem, st); break;
+      default: launch_rdf_half<true, true, true>(h, grid->ncell, smem, st); break;
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int blocks = sms * blocks_per_sm;
-    if (blocks > grid->ncell) blocks = grid->ncell;
-    rdf_sweep_half_kernel<8><<<blocks, 32, smem, st>>>(h);
     MOUSE_LAUNCH_CHECK("rdf_sweep_half_kernel");
     return MOUSE_OK;
   }
