@@ -384,7 +384,7 @@ def run_ours(args):
                     "ms_per_step": 1e3 * float(e2e_t.item()) / steps,
                     "note": "FramePipeline.submit(): pinned host positions -> H2D -> K1-K4 -> 48-byte totals -> D2H, "
                             "copy of frame k+1 overlapped with kernels of frame k; topology resident"},
-            "gpu_launches": steps * 10 + (2 if world > 1 else 0),
+            "gpu_launches": steps * 9 + (2 if world > 1 else 0),
             "clocks": clocks,
             "roofline": {
                 "bound": "fp_issue", "kernel": "p2_sweep_half_kernel (+ p2_fixup_kernel)",

@@ -292,12 +292,46 @@ __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, int n, GridD
                                                          int32_t *__restrict__ cell_sorted,
                                                          uint8_t *__restrict__ flag_sorted,
                                                          long long *__restrict__ acc_fix,
-                                                         int32_t *__restrict__ acc_cnt) {
+                                                         int32_t *__restrict__ acc_cnt,
+                                                         int32_t *__restrict__ items) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < ncell; c += warps) {
     const int s = cell_start[c], e = cell_start[c + 1];
     const int nc = e - s;
+    if (items) {
+      // the cell's item row for the half-shell sweeps (half_shell.cuh): lane L < 10 owns range L; an empty cell
+      // only needs its size (the sweeps skip it)
+      int32_t val = 0;
+      if (nc > 0) {
+        int cx, cy, cz;
+        hs_cell_coords(g, c, cx, cy, cz);
+        int src = 0, len = 0;
+        if (lane < 10) {
+          int rb, lo, hi;
+          hs_range_cells(g, cx, cy, cz, lane, rb, lo, hi);
+          if (lo <= hi) {
+            src = cell_start[rb + lo];
+            len = cell_start[rb + hi + 1] - src;
+          }
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+          const int y = __shfl_up_sync(MOUSE_FULL_MASK, incl, o);
+          if (lane >= o) incl += y;
+        }
+        // row layout: [0..9] src, [10..19] len, [20..29] offset, [30] size, [31] packed coordinates + boundary bit
+        const int src_k = __shfl_sync(MOUSE_FULL_MASK, src, lane % 10);
+        const int len_k = __shfl_sync(MOUSE_FULL_MASK, len, lane % 10);
+        const int off_k = __shfl_sync(MOUSE_FULL_MASK, incl - len, lane % 10);
+        const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
+        const int boundary = (cx == 0) | (cx == nx - 1) | (cy == 0) | (cy == ny - 1) | (cz == nz - 1);
+        val = lane < 10 ? src_k : lane < 20 ? len_k : lane < 30 ? off_k : lane == 30 ? nc
+                                                                   : (cx | (cy << 10) | (cz << 20) | (boundary << 30));
+      }
+      items[(size_t)c * HS_ITEM_INTS + lane] = val;
+    }
     if (nc <= 0) continue;
     for (int m0 = 0; m0 < nc; m0 += 32) {
       const int m = m0 + lane;
@@ -326,18 +360,6 @@ __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, int n, GridD
       }
     }
   }
-}
-
-// ---- item table of the half-shell sweeps: one thread per home cell (needs >= 3 cells on every axis) -----------------
-__global__ void __launch_bounds__(128) cell_items_kernel(GridDev g, const int32_t *__restrict__ cell_start,
-                                                         int32_t *__restrict__ items) {
-  const int tk = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tk >= g.ncell) return;
-  int32_t row[HS_ITEM_INTS];
-  hs_item_row(g, cell_start, tk, row);
-  int4 *dst = reinterpret_cast<int4 *>(items + (size_t)tk * HS_ITEM_INTS);
-#pragma unroll
-  for (int k = 0; k < HS_ITEM_INTS / 4; ++k) dst[k] = make_int4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]);
 }
 
 // ---- K1 + cell assignment + output initialisation in one pass (mouse_p2_frame) -------------------------------
@@ -417,10 +439,6 @@ static int cell_build_tail(int mode, const uint8_t *ref_mask, int64_t n, const m
     scan_apply_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start);
     MOUSE_LAUNCH_CHECK("scan_apply_kernel");
   }
-  if (grid->fast) {
-    cell_items_kernel<<<(grid->ncell + 127) / 128, 128, 0, st>>>(g, w.cell_start, w.items);
-    MOUSE_LAUNCH_CHECK("cell_items_kernel");
-  }
   if (n > 0) {
     unsigned nb = (unsigned)((n + 255) / 256);
     cell_scatter_idx_kernel<<<nb, 256, 0, st>>>(ref_mask, (int)n, w.cell_of, w.rank_of, w.cell_start, w.idx_tmp);
@@ -431,11 +449,11 @@ static int cell_build_tail(int mode, const uint8_t *ref_mask, int64_t n, const m
     if (mode == 0)
       cell_canon_kernel<0><<<blocks, 256, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.rec_sorted,
                                                    w.idx_sorted, w.cell_sorted,
-                                                   w.flag_sorted, w.acc_fix, w.acc_cnt);
+                                                   w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr);
     else
       cell_canon_kernel<1><<<blocks, 256, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.rec_sorted,
                                                    w.idx_sorted, w.cell_sorted,
-                                                   w.flag_sorted, w.acc_fix, w.acc_cnt);
+                                                   w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr);
     MOUSE_LAUNCH_CHECK("cell_canon_kernel");
   }
   return MOUSE_OK;

@@ -96,34 +96,10 @@ __device__ __forceinline__ void hs_range_cells(const GridDev &g, int cx, int cy,
   }
 }
 
-// Per-cell item table (32 ints per cell, written by cell_items_kernel right after the scan, read by the sweeps):
+// Per-cell item table (32 ints per cell, written by cell_canon_kernel, one warp per cell, read by the sweeps):
 //   [0..9] first sorted slot of range L, [10..19] its length, [20..29] its offset t in the candidate concatenation,
 //   [30] bonds / atoms in the home cell, [31] cx | cy << 10 | cz << 20 | boundary << 30.
 #define HS_ITEM_INTS 32
-
-__device__ __forceinline__ void hs_item_row(const GridDev &g, const int32_t *__restrict__ cell_start, int tk,
-                                            int32_t *__restrict__ row) {
-  int cx, cy, cz;
-  hs_cell_coords(g, tk, cx, cy, cz);
-  int t = 0;
-#pragma unroll
-  for (int L = 0; L < 10; ++L) {
-    int rb, lo, hi, src = 0, len = 0;
-    hs_range_cells(g, cx, cy, cz, L, rb, lo, hi);
-    if (lo <= hi) {
-      src = cell_start[rb + lo];
-      len = cell_start[rb + hi + 1] - src;
-    }
-    row[L] = src;
-    row[10 + L] = len;
-    row[20 + L] = t;
-    t += len;
-  }
-  const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
-  const int boundary = (cx == 0) | (cx == nx - 1) | (cy == 0) | (cy == ny - 1) | (cz == nz - 1);
-  row[30] = cell_start[tk + 1] - cell_start[tk];
-  row[31] = cx | (cy << 10) | (cz << 20) | (boundary << 30);
-}
 
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");

@@ -112,7 +112,7 @@ class FramePipeline:
         self._pending = []
         self.h2d_bytes_per_frame = self.n_atoms * 3 * 8
         self.d2h_bytes_per_frame = 48
-        self.kernels_per_frame = 10  # bond_assign, 2 x scan, items, scatter_idx, canon, sweep, fixup, exact check, finish+reduce
+        self.kernels_per_frame = 9   # bond_assign, 2 x scan, scatter_idx, canon, sweep, fixup, exact check, finish+reduce
 
     def submit(self, positions_host: torch.Tensor):
         """Enqueue one frame (``positions_host``: pinned (N_a,3) f64 CPU tensor).  Returns finished
