@@ -14,7 +14,7 @@ int mouse_launch_cell_build(int mode, const double *xyz, const double *vec, cons
 int mouse_launch_frame_build(const double *pos, const int32_t *bond_atoms, const int32_t *mol, const uint8_t *nbr_mask,
                              const uint8_t *ref_mask, int64_t n, const mouse_grid_t *grid, const Workspace &w,
                              double *vec, double *ctr, double *out_sum, int32_t *out_cnt, double *out_mean,
-                             cudaStream_t st);
+                             int init_listed, cudaStream_t st);
 int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const mouse_grid_t *grid, uint32_t flags,
                           const Workspace &w, double *out_sum, int32_t *out_cnt, const int64_t *row_ptr,
                           int32_t *nbr_idx, int frame_mode, int *used_fast, cudaStream_t st);
@@ -211,8 +211,10 @@ int mouse_p2_frame_timed(const double *pos, const int32_t *bond_atoms, const int
     }
   }
   // K1 + K2 fused (bond vectors, cell list, outputs initialised) -> K3 -> K4 fused with the accumulator conversion
+  // (the fast sweep's K4 writes every listed bond itself; the all-FP64 path needs all outputs initialised)
+  const int fast_path = grid->fast && !(flags & (MOUSE_FORCE_EXACT | MOUSE_NO_CUTOFF));
   if ((rc = mouse_launch_frame_build(pos, bond_atoms, mol, nbr_mask, ref_mask, n_bonds, grid, w, vec, ctr, sum, cnt,
-                                     mean, st)))
+                                     mean, !fast_path, st)))
     return rc;
   int used_fast = 0;
   if (ev_sweep_begin) MOUSE_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev_sweep_begin, st));

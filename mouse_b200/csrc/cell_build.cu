@@ -371,7 +371,8 @@ __global__ void __launch_bounds__(256) bond_assign_kernel(const double *__restri
                                                           int32_t *__restrict__ cell_count,
                                                           int64_t *__restrict__ counters, Rec *__restrict__ rec_tmp,
                                                           double *__restrict__ out_sum,
-                                                          int32_t *__restrict__ out_cnt, double *__restrict__ out_mean) {
+                                                          int32_t *__restrict__ out_cnt, double *__restrict__ out_mean,
+                                                          int init_listed) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
   int2 ab = __ldg(bonds + b);
@@ -387,13 +388,17 @@ __global__ void __launch_bounds__(256) bond_assign_kernel(const double *__restri
   ctr[b] = cx;
   ctr[(size_t)n + b] = cy;
   ctr[2 * (size_t)n + b] = cz;
-  out_sum[b] = 0.0;
-  out_cnt[b] = 0;
-  out_mean[b] = __longlong_as_double(0x7ff8000000000000LL);
   bool in_list = nbr_mask ? (nbr_mask[b] != 0) : true;
   if (in_list && vx == 0.0 && vy == 0.0 && vz == 0.0) {   // zero-length bond: never a reference
     atomicAdd((unsigned long long *)&counters[0], 1ULL);  // (:93,119), poisons as neighbour (:112)
     in_list = false;
+  }
+  if (!in_list || init_listed) {
+    // bonds outside the cell list never reach the fused K4: their outputs are final here (listed bonds are written
+    // by p2_finish_reduce_kernel; the all-FP64 sweep + plain reduce path needs every output initialised)
+    out_sum[b] = 0.0;
+    out_cnt[b] = 0;
+    out_mean[b] = __longlong_as_double(0x7ff8000000000000LL);
   }
   if (!in_list) {
     cell_of[b] = -1;
@@ -483,14 +488,14 @@ int mouse_launch_cell_build(int mode, const double *xyz, const double *vec, cons
 int mouse_launch_frame_build(const double *pos, const int32_t *bond_atoms, const int32_t *mol, const uint8_t *nbr_mask,
                              const uint8_t *ref_mask, int64_t n, const mouse_grid_t *grid, const Workspace &w,
                              double *vec, double *ctr, double *out_sum, int32_t *out_cnt, double *out_mean,
-                             cudaStream_t st) {
+                             int init_listed, cudaStream_t st) {
   GridDev g = mouse_grid_dev(grid);
   MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, (size_t)((char *)(w.cell_count + grid->ncell + 1) - (char *)w.counters), st));
   if (n > 0) {
     bond_assign_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pos, (const int2 *)bond_atoms, mol, nbr_mask, (int)n,
                                                                      g, vec, ctr, w.cell_of, w.rank_of, w.cell_count,
                                                                      w.counters, w.rec_tmp, out_sum, out_cnt,
-                                                                     out_mean);
+                                                                     out_mean, init_listed);
     MOUSE_LAUNCH_CHECK("bond_assign_kernel");
   }
   return cell_build_tail(0, ref_mask, n, grid, g, w, st);

@@ -176,7 +176,15 @@ __global__ void __launch_bounds__(RED_THREADS) p2_finish_reduce_kernel(const Fin
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (!isref[q]) continue;             // not a reference: outputs keep their initial 0 / 0 / NaN
+      const int s = s0 + q * RED_THREADS;
+      if (s >= hi) continue;
+      const double nan = __longlong_as_double(0x7ff8000000000000LL);
+      if (!isref[q]) {                     // listed, but not a reference: 0 / 0 / NaN
+        a.out_sum[o[q]] = 0.0;
+        a.out_cnt[o[q]] = 0;
+        a.out_mean[o[q]] = nan;
+        continue;
+      }
       double sum;
       int cc = c[q];
       if (overflow) {
@@ -191,13 +199,14 @@ __global__ void __launch_bounds__(RED_THREADS) p2_finish_reduce_kernel(const Fin
         a.out_sum[o[q]] = sum;
         a.out_cnt[o[q]] = cc;
       }
+      double m = nan;
       if (cc > 0) {
-        const double m = __ddiv_rn(sum, (double)cc);
-        a.out_mean[o[q]] = m;
+        m = __ddiv_rn(sum, (double)cc);
         acc += m;
         refs += 1;
         pairs += cc;
       }
+      a.out_mean[o[q]] = m;
     }
   }
   acc = warp_sum(acc);

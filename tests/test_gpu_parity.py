@@ -502,3 +502,27 @@ def test_com_rdfs_against_the_reference():
         r = of.CalculateComRdfs(cfg, 0., 4., 32)
         assert np.array_equal(r["data"]["1"], g["com_%s_data_1" % tag]) and r["norm"]["1"] == g["com_%s_norm_1" % tag]
         assert np.array_equal(np.array(r["r"]), g["com_%s_r" % tag]) and np.array_equal(np.array(r["v"]), g["com_%s_v" % tag])
+
+
+@pytest.mark.parametrize("exact", [False, True], ids=["fast", "exact"])
+def test_outputs_do_not_depend_on_previous_contents(exact):
+    """Every per-bond output is (re)written by a frame: reusing the output tensors of an unrelated frame (different
+    selections, garbage in the unselected bonds) gives the same bits as fresh tensors."""
+    from mouse_b200.melt import make_melt
+    melt = make_melt(40, 60, seed=12)
+    eng = _engine()
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    rng = np.random.default_rng(3)
+    nbr = (rng.random(melt.n_bonds) < 0.7).astype(np.uint8)
+    ref = ((rng.random(melt.n_bonds) < 0.5) & nbr.astype(bool)).astype(np.uint8)
+    fresh = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, 1.8, nbr_mask=nbr, ref_mask=ref, exact=exact)
+    f_sum, f_cnt, f_mean = fresh.sum.clone(), fresh.count.clone(), fresh.mean.clone()
+    dirty = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, 2.4, exact=exact)        # everything non-zero
+    dirty.sum.fill_(123.0)
+    dirty.count.fill_(77)
+    dirty.mean.fill_(-5.0)
+    again = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, 1.8, nbr_mask=nbr, ref_mask=ref, exact=exact,
+                         out=dirty)
+    assert torch.equal(again.count, f_cnt) and torch.equal(again.sum, f_sum)
+    assert torch.equal(torch.nan_to_num(again.mean, nan=-1.0), torch.nan_to_num(f_mean, nan=-1.0))
+    assert int((again.count[torch.as_tensor(ref == 0, device=again.count.device)] != 0).sum()) == 0
