@@ -526,3 +526,22 @@ def test_outputs_do_not_depend_on_previous_contents(exact):
     assert torch.equal(again.count, f_cnt) and torch.equal(again.sum, f_sum)
     assert torch.equal(torch.nan_to_num(again.mean, nan=-1.0), torch.nan_to_num(f_mean, nan=-1.0))
     assert int((again.count[torch.as_tensor(ref == 0, device=again.count.device)] != 0).sum()) == 0
+
+
+def test_rdf_cli_prints_the_reference_table(capsys):
+    """calculate_rdfs.py (same flags as the reference's script): the printed table equals printRdfs of the mirror's
+    CalculatePairCorrelationFunctions on the object model, and the histogram behind it is the golden one."""
+    import io
+    import os
+    import calculate_rdfs as cli
+    from mouse_b200 import ordering_functions as of
+    from mouse_b200.lammpack_misc import printRdfs, read_data_typeselect
+    from tests.util import GOLDEN_DIR
+    path = os.path.join(GOLDEN_DIR, "melt_290.data")
+    cli.main([path, "--rmin", "0.", "--rmax", "3.0", "--nbin", "30", "--same-molecule", "--no-norm"])
+    out = capsys.readouterr().out
+    rdfs = of.CalculatePairCorrelationFunctions(read_data_typeselect(path), None, 0., 3.0, 30, True, verbose=False)
+    buf = io.StringIO()
+    printRdfs(rdfs, False, out=buf)
+    assert out == buf.getvalue() and out.startswith("#r\tvol\t1_1\t1_AAAAA\tAAAAA_AAAAA\n")
+    assert sum(float(line.split("\t")[2]) for line in out.splitlines()[1:]) > 0
