@@ -159,58 +159,96 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
                                             const double (*s_homeU)[HS_MAXHOME], double (*s_acc)[33],
                                             int (*s_cnt)[33], const int (*s_gid)[32]) {
   static_assert(HS_GRP == 8 || HS_GRP == 4, "reference groups of 4 or 8");
+  static_assert(HS_MAXHOME % 2 == 0, "references are processed two at a time");
   constexpr int HSL = HS_MAXHOME / 32;   // slots of pass 0 that may hold home-cell bonds
   const float2 nrc = make_float2(-k.rc2_c, -k.rc2_c);
-  // reference il + 1 is fetched from shared memory while reference il is processed
-  float4 pi_n = s_homeP[0];
-  double uix_n = s_homeU[0][0], uiy_n = s_homeU[1][0], uiz_n = s_homeU[2][0];
-  for (int il = 0; il < nhome; ++il) {
-    const float4 pi = pi_n;
-    const double uix = uix_n, uiy = uiy_n, uiz = uiz_n;
-    {
-      const int in = min(il + 1, HS_MAXHOME - 1);
-      pi_n = s_homeP[in];
-      uix_n = s_homeU[0][in];
-      uiy_n = s_homeU[1][in];
-      uiz_n = s_homeU[2][in];
-    }
-    const int moli = __float_as_int(pi.w);
-    const float2 npx = make_float2(-pi.x, -pi.x), npy = make_float2(-pi.y, -pi.y), npz = make_float2(-pi.z, -pi.z);
-    // home-home pairs are decided once: candidate t > il (pass 0: slot c < HSL holds t = 32 c + lane)
-    const int il_eff = pass == 0 ? il : -1;
-    double acci0 = 0.0, acci1 = 0.0;
-    int cnti = 0;
-    float band = 3.0e38f, nearz = 3.0e38f;
+  // References are processed in groups of HS_GRP.  The inner loop is one basic block: the rare-candidate
+  // decision is only recorded (one bit per reference) and the reference-side partial of reference il is
+  // stored while reference il + 1 is computed, so no iteration ends by draining its own FP64 chain.
+  for (int base = 0; base < nhome; base += HS_GRP) {
+    const int nref = min(HS_GRP, nhome - base);
+    unsigned rare = 0u;
+    // two references per iteration: two independent dependency chains per warp.  The second one of an odd
+    // tail is switched off through its threshold
+#pragma unroll 1
+    for (int r = 0; r < nref; r += 2) {
+      const int il = base + r;
+      const float4 pa = s_homeP[il], pb = s_homeP[il + 1];
+      const double uax = s_homeU[0][il], uay = s_homeU[1][il], uaz = s_homeU[2][il];
+      const double ubx = s_homeU[0][il + 1], uby = s_homeU[1][il + 1], ubz = s_homeU[2][il + 1];
+      const float negwb = r + 1 < nref ? k.negw : -3.0e38f;
+      const int mola = __float_as_int(pa.w), molb = __float_as_int(pb.w);
+      const float2 nax = make_float2(-pa.x, -pa.x), nay = make_float2(-pa.y, -pa.y), naz = make_float2(-pa.z, -pa.z);
+      const float2 nbx = make_float2(-pb.x, -pb.x), nby = make_float2(-pb.y, -pb.y), nbz = make_float2(-pb.z, -pb.z);
+      // home-home pairs are decided once: candidate t > il (pass 0: slot c < HSL holds t = 32 c + lane)
+      const int ea = pass == 0 ? il : -1, eb = pass == 0 ? il + 1 : -1;
+      double acca0 = 0.0, acca1 = 0.0, accb0 = 0.0, accb1 = 0.0;
+      int cnta = 0, cntb = 0;
+      float banda = 3.0e38f, nza = 3.0e38f, bandb = 3.0e38f, nzb = 3.0e38f;
 #pragma unroll
-    for (int pp = 0; pp < NPP; ++pp) {
-      const float2 dx = __fadd2_rn(xr2[pp], npx), dy = __fadd2_rn(yr2[pp], npy), dz = __fadd2_rn(zr2[pp], npz);
-      const float2 t = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), nrc);   // d2 - rc2
-      band = fminf(band, fminf(fabsf(t.x), fabsf(t.y)));
-      const double d0 = fma(uix, ux[2 * pp], fma(uiy, uy[2 * pp], uiz * uz[2 * pp]));
-      const double d1 = fma(uix, ux[2 * pp + 1], fma(uiy, uy[2 * pp + 1], uiz * uz[2 * pp + 1]));
-      // smallest |d| over ALL slots (as the high word, compared as a float): a false alarm only costs time
-      nearz = fminf(nearz, fminf(fabsf(__int_as_float(__double2hiint(d0))), fabsf(__int_as_float(__double2hiint(d1)))));
-      // hit masks (all ones / zero).  Branch-free: the weight w is d with its high word cleared on a miss
-      // (|w| < 1e-300, w * w vanishes in the sums), so the FP64 FMAs are unconditional
-      int m0 = mask_lt(t.x, k.negw), m1 = mask_lt(t.y, k.negw);
-      if (2 * pp < HSL) m0 &= mask_gt(lane, il_eff - 64 * pp);
-      if (2 * pp + 1 < HSL) m1 &= mask_gt(lane, il_eff - 64 * pp - 32);
-      if (EXCL_MOL) {
-        m0 &= mask_ne(molr[2 * pp], moli);
-        m1 &= mask_ne(molr[2 * pp + 1], moli);
+      for (int pp = 0; pp < NPP; ++pp) {
+        const float2 dxa = __fadd2_rn(xr2[pp], nax), dya = __fadd2_rn(yr2[pp], nay), dza = __fadd2_rn(zr2[pp], naz);
+        const float2 dxb = __fadd2_rn(xr2[pp], nbx), dyb = __fadd2_rn(yr2[pp], nby), dzb = __fadd2_rn(zr2[pp], nbz);
+        const float2 ta = __fadd2_rn(__ffma2_rn(dza, dza, __ffma2_rn(dya, dya, __fmul2_rn(dxa, dxa))), nrc);   // d2 - rc2
+        const float2 tb = __fadd2_rn(__ffma2_rn(dzb, dzb, __ffma2_rn(dyb, dyb, __fmul2_rn(dxb, dxb))), nrc);
+        banda = fminf(banda, fminf(fabsf(ta.x), fabsf(ta.y)));
+        bandb = fminf(bandb, fminf(fabsf(tb.x), fabsf(tb.y)));
+        const double da0 = fma(uax, ux[2 * pp], fma(uay, uy[2 * pp], uaz * uz[2 * pp]));
+        const double da1 = fma(uax, ux[2 * pp + 1], fma(uay, uy[2 * pp + 1], uaz * uz[2 * pp + 1]));
+        const double db0 = fma(ubx, ux[2 * pp], fma(uby, uy[2 * pp], ubz * uz[2 * pp]));
+        const double db1 = fma(ubx, ux[2 * pp + 1], fma(uby, uy[2 * pp + 1], ubz * uz[2 * pp + 1]));
+        // smallest |d| over ALL slots (as the high word, compared as a float): a false alarm only costs time
+        nza = fminf(nza, fminf(fabsf(__int_as_float(__double2hiint(da0))), fabsf(__int_as_float(__double2hiint(da1)))));
+        nzb = fminf(nzb, fminf(fabsf(__int_as_float(__double2hiint(db0))), fabsf(__int_as_float(__double2hiint(db1)))));
+        // Branch-free: the weight w is d with its high word cleared on a miss (|w| < 1e-300, w * w vanishes
+        // in the sums), so the FP64 FMAs are unconditional
+        bool pa0 = ta.x < k.negw, pa1 = ta.y < k.negw, pb0 = tb.x < negwb, pb1 = tb.y < negwb;
+        // (bitwise & on purpose: && makes ptxas emit divergent branches here)
+        if (2 * pp < HSL) {
+          pa0 = pa0 & (lane > ea - 64 * pp);
+          pb0 = pb0 & (lane > eb - 64 * pp);
+        }
+        if (2 * pp + 1 < HSL) {
+          pa1 = pa1 & (lane > ea - 64 * pp - 32);
+          pb1 = pb1 & (lane > eb - 64 * pp - 32);
+        }
+        if (EXCL_MOL) {
+          pa0 = pa0 & (molr[2 * pp] != mola);
+          pa1 = pa1 & (molr[2 * pp + 1] != mola);
+          pb0 = pb0 & (molr[2 * pp] != molb);
+          pb1 = pb1 & (molr[2 * pp + 1] != molb);
+        }
+        const double wa0 = __hiloint2double(pa0 ? __double2hiint(da0) : 0, __double2loint(da0));
+        const double wa1 = __hiloint2double(pa1 ? __double2hiint(da1) : 0, __double2loint(da1));
+        const double wb0 = __hiloint2double(pb0 ? __double2hiint(db0) : 0, __double2loint(db0));
+        const double wb1 = __hiloint2double(pb1 ? __double2hiint(db1) : 0, __double2loint(db1));
+        accj[2 * pp] = fma(wb0, wb0, fma(wa0, wa0, accj[2 * pp]));
+        accj[2 * pp + 1] = fma(wb1, wb1, fma(wa1, wa1, accj[2 * pp + 1]));
+        acca0 = fma(wa0, wa0, acca0);
+        acca1 = fma(wa1, wa1, acca1);
+        accb0 = fma(wb0, wb0, accb0);
+        accb1 = fma(wb1, wb1, accb1);
+        cntj[2 * pp] += (pa0 ? 1 : 0) + (pb0 ? 1 : 0);
+        cntj[2 * pp + 1] += (pa1 ? 1 : 0) + (pb1 ? 1 : 0);
+        cnta += (pa0 ? 1 : 0) + (pa1 ? 1 : 0);
+        cntb += (pb0 ? 1 : 0) + (pb1 ? 1 : 0);
       }
-      const double w0 = __hiloint2double(__double2hiint(d0) & m0, __double2loint(d0));
-      const double w1 = __hiloint2double(__double2hiint(d1) & m1, __double2loint(d1));
-      accj[2 * pp] = fma(w0, w0, accj[2 * pp]);
-      accj[2 * pp + 1] = fma(w1, w1, accj[2 * pp + 1]);
-      acci0 = fma(w0, w0, acci0);
-      acci1 = fma(w1, w1, acci1);
-      cntj[2 * pp] -= m0;
-      cntj[2 * pp + 1] -= m1;
-      cnti -= m0 + m1;
+      rare |= (unsigned)(banda <= k.rc2_w || nza <= k.nearz_thr) << r;
+      rare |= (unsigned)(r + 1 < nref && (bandb <= k.rc2_w || nzb <= k.nearz_thr)) << (r + 1);
+      s_acc[r][lane] = acca0 + acca1;
+      s_cnt[r][lane] = cnta;
+      s_acc[r + 1][lane] = accb0 + accb1;
+      s_cnt[r + 1][lane] = cntb;
     }
     // ---- rare: candidates inside the guard band / near-zero dots are handed to p2_fixup_kernel
-    if (band <= k.rc2_w || nearz <= k.nearz_thr) {
+    while (rare) {
+      const int r = __ffs(rare) - 1;
+      rare &= rare - 1;
+      const int il = base + r;
+      const float4 pi = s_homeP[il];
+      const double uix = s_homeU[0][il], uiy = s_homeU[1][il], uiz = s_homeU[2][il];
+      const int moli = __float_as_int(pi.w);
+      const int il_eff = pass == 0 ? il : -1;
 #pragma unroll
       for (int c = 0; c < 2 * NPP; ++c) {
         const int g = s_gid[c][lane];
@@ -232,12 +270,9 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
         }
       }
     }
-    // ---- reference side: per-lane partials -> shared memory, 8 references are reduced together
-    s_acc[il & (HS_GRP - 1)][lane] = acci0 + acci1;
-    s_cnt[il & (HS_GRP - 1)][lane] = cnti;
-    if ((il & (HS_GRP - 1)) == HS_GRP - 1 || il == nhome - 1) {
+    // ---- reference side: per-lane partials of the group's references are reduced together
+    {
       __syncwarp();
-      constexpr int PER = 32 / HS_GRP * 2;            // 32 / HS_GRP lanes share a reference, PER partials each
       const int row = lane & (HS_GRP - 1), part = lane / HS_GRP;
       // fixed pairwise tree (deterministic, log-depth dependency chain)
       double pv[HS_GRP];
@@ -252,14 +287,12 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
 #pragma unroll
         for (int q = 0; q + w < HS_GRP; q += 2 * w) pv[q] += pv[q + w];
       double v = pv[0];
-      (void)PER;
 #pragma unroll
       for (int o = HS_GRP; o < 32; o <<= 1) {
         v += __shfl_xor_sync(MOUSE_FULL_MASK, v, o);
         nv += __shfl_xor_sync(MOUSE_FULL_MASK, nv, o);
       }
-      const int iref = (il & ~(HS_GRP - 1)) + lane;
-      if (lane < HS_GRP && iref <= il) hs_flush(a.acc_fix, a.acc_cnt, hs + iref, v, nv);
+      if (lane < nref) hs_flush(a.acc_fix, a.acc_cnt, hs + base + lane, v, nv);
       __syncwarp();
     }
   }
