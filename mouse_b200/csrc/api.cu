@@ -86,6 +86,21 @@ int mouse_grid_plan(const double *box, double rcut, double rc2, int64_t n_items,
       nax[a] = k < 1 ? 1 : k;
     }
   }
+  // sparse cells: the half-shell sweeps pay a fixed cost per home cell (fetch, TMA, register load, flush), which
+  // is amortised best at ~10 items per cell (one pass of 6 slots); any cell edge >= rcut is a valid cell list.
+  // Small systems keep the fine grid: they need the home cells for parallelism, not for amortisation.
+  {
+    const double target = 9.5;
+    double now = (double)nax[0] * nax[1] * nax[2];
+    if (rcut > 0.0 && n_items >= 65536 && now * target > (double)n_items) {
+      double f = cbrt((double)n_items / target / now);
+      for (int a = 0; a < 3; ++a) {
+        int k = (int)(nax[a] * f);
+        int lo = nax[a] < 3 ? nax[a] : 3;
+        nax[a] = k < lo ? lo : k;
+      }
+    }
+  }
   double ratio = 0.0;
   int fast = rcut > 0.0;
   for (int a = 0; a < 3; ++a) {

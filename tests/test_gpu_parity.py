@@ -117,6 +117,28 @@ def test_p2_full_size_config2():
         assert res.totals_dict()["n_pairs"] == int(ora["count"].sum())
 
 
+@pytest.mark.parametrize("same", [True, False])
+def test_sparse_cells_use_a_coarser_grid(same):
+    """>= 65 536 bonds with few bonds per rc-sized cell: the planner widens the cells to ~10 bonds each
+    (mouse_grid_plan); counts, pair sums and S stay those of the reference's cutoff."""
+    from mouse_b200.melt import make_melt
+    from oracle import c_oracle
+    melt = make_melt(1500, 81, seed=4)
+    rc = 1.2
+    eng = _engine()
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    res = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, rc, same_molecule=same)
+    assert res.grid.fast == 1 and min(res.grid.cell_w) > 1.5 * rc
+    assert 8.0 < melt.n_bonds / res.grid.ncell < 14.0
+    vec, ctr = c_oracle.bond_build(melt.positions, melt.bond_atoms, melt.box)
+    ora = c_oracle.p2(vec, ctr, molb, melt.box, rc, same)
+    assert np.array_equal(res.count.cpu().numpy().astype(np.int64), ora["count"])
+    ok = ora["count"] > 0
+    np.testing.assert_allclose(res.mean.cpu().numpy()[ok], ora["mean"][ok], rtol=1e-12, atol=ATOL_MEAN)
+    s_ref = 1.5 * ora["mean"][ok].sum() / ok.sum() - 0.5
+    assert abs(res.order_parameter() - s_ref) <= RTOL * abs(s_ref)
+
+
 def test_deterministic_and_slot_variants():
     from mouse_b200 import _lib
     from mouse_b200.melt import make_melt

@@ -34,6 +34,11 @@ def test_grid_plan_host():
     assert g.ncell == 1 and g.fast == 0
     g = _lib.grid_plan([1000., 1000., 1000.], 1.0, 100)      # dilute: cells capped near 4 * n
     assert g.ncell <= 4 * 100 + 64 and all(w >= 1.0 for w in g.cell_w)
+    # sparse cells (large system, few items per rc-sized cell): cells widened to ~10 items each
+    g = _lib.grid_plan([105.57, 105.57, 105.57], 1.5, 999_999)
+    assert list(g.ncell_axis) == [47, 47, 47] and g.fast == 1 and 9.0 < 999_999 / g.ncell < 11.0
+    g = _lib.grid_plan([22.7, 22.7, 22.7], 1.5, 9_900)       # small system: the fine grid stays
+    assert list(g.ncell_axis) == [15, 15, 15]
     with pytest.raises(RuntimeError):
         _lib.grid_plan([0., 1., 1.], 1.0, 10)
 
