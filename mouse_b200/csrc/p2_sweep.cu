@@ -286,13 +286,9 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
       for (int w = 1; w < HS_GRP; w <<= 1)
 #pragma unroll
         for (int q = 0; q + w < HS_GRP; q += 2 * w) pv[q] += pv[q + w];
-      double v = pv[0];
-#pragma unroll
-      for (int o = HS_GRP; o < 32; o <<= 1) {
-        v += __shfl_xor_sync(MOUSE_FULL_MASK, v, o);
-        nv += __shfl_xor_sync(MOUSE_FULL_MASK, nv, o);
-      }
-      if (lane < nref) hs_flush(a.acc_fix, a.acc_cnt, hs + base + lane, v, nv);
+      // the 32 / HS_GRP partials of a reference go straight to the integer accumulators (no shuffle stages:
+      // their latency would be exposed here, the extra atomics are not)
+      if (row < nref) hs_flush(a.acc_fix, a.acc_cnt, hs + base + row, pv[0], nv);
       __syncwarp();
     }
   }

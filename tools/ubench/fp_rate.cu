@@ -16,7 +16,13 @@ __global__ void __launch_bounds__(32) rate_kernel(double *out, long long *cyc, i
     f[i] = make_float2((float)(seed + i), (float)(seed - i));
     q[i] = (int)seed + i;
   }
-  const double m = seed * 0.5, c = seed * 0.25;
+  double b[8], cc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    b[i] = seed * (i + 2) + threadIdx.x;
+    cc[i] = seed / (i + 3) - threadIdx.x;
+  }
+  const double m = seed * 0.5, c = seed * 0.25, e = seed * 0.125;
   const float2 mf = make_float2((float)m, (float)m), cf = make_float2((float)c, (float)c);
   const long long t0 = clock64();
 #pragma unroll 1
@@ -66,6 +72,18 @@ __global__ void __launch_bounds__(32) rate_kernel(double *out, long long *cyc, i
       for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int i = 0; i < 8; ++i) q[i] = (q[i] ^ it) + i;
+    } else if (MODE == 8) {   // 16 DFMA, three distinct register operands each (no operand reuse)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fma(b[i], cc[i], a[i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fma(cc[i], b[(i + 3) & 7], a[i]);
+    } else if (MODE == 9) {   // the sweep's FP64 pattern for 4 candidates: 3-term dot, then two accumulations
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double d = fma(m, b[i], fma(c, cc[i], e * b[i + 4]));
+        a[i] = fma(d, d, a[i]);
+        a[i + 4] = fma(d, d, a[i + 4]);
+      }
     } else if (MODE == 7) {   // 8 FFMA2 + 8 integer
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -77,7 +95,7 @@ __global__ void __launch_bounds__(32) rate_kernel(double *out, long long *cyc, i
   const long long t1 = clock64();
   double s = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s += a[i] + f[i].x + f[i].y + q[i];
+  for (int i = 0; i < 8; ++i) s += a[i] + f[i].x + f[i].y + q[i] + b[i] + cc[i];
   out[blockIdx.x * 32 + threadIdx.x] = s;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -110,6 +128,8 @@ int main() {
   cudaMalloc(&out, 148 * 24 * 32 * 8); cudaMalloc(&cyc, 148 * 24 * 8);
   long long *h = new long long[148 * 24];
   run<0>("DFMA", 16, out, cyc, h);
+  run<8>("DFMA 3 distinct operands", 16, out, cyc, h);
+  run<9>("DFMA dot+2 acc pattern", 20, out, cyc, h);
   run<1>("FFMA2 (packed)", 16, out, cyc, h);
   run<2>("FFMA (scalar)", 16, out, cyc, h);
   run<6>("integer LOP+IADD", 32, out, cyc, h);
