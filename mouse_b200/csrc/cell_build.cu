@@ -6,8 +6,14 @@
 #include "half_shell.cuh"
 
 // np.remainder(a, b), b > 0: fmod then shift negatives by +b (NumPy npy_divmod); fmod is exact.
+// For |a| < 2 b (every bond of a wrapped or mildly unwrapped configuration) fmod needs no library call:
+// fmod(a, b) = a for |a| < b, and a -+ b for b <= |a| < 2 b, where the subtraction is exact (Sterbenz).
 __device__ __forceinline__ double np_remainder_pos(double a, double b) {
-  double m = fmod(a, b);
+  double m;
+  const double aa = fabs(a);
+  if (aa < b) m = a;
+  else if (aa < __dadd_rn(b, b)) m = a < 0.0 ? __dadd_rn(a, b) : __dsub_rn(a, b);
+  else m = fmod(a, b);
   if (m != 0.0) {
     if (m < 0.0) m = __dadd_rn(m, b);
   } else {
@@ -49,7 +55,12 @@ __global__ void __launch_bounds__(256) bond_build_kernel(const double *__restric
 // Wrapped copy of a coordinate into [0, L) and its cell index / in-cell offset.  The reference
 // never wraps midpoints (lammpack_types.py:590-591); this copy is used for binning only.
 __device__ __forceinline__ void cell_axis(double c, double L, double cw, int nc, int &k, double &xw) {
-  double x = c - L * floor(c / L);
+  // c - L * floor(c / L); the division is only needed outside [-L, 2 L)
+  double x;
+  if (c >= 0.0 && c < L) x = c;
+  else if (c >= -L && c < 0.0) x = c + L;
+  else if (c >= L && c < L + L) x = c - L;
+  else x = c - L * floor(c / L);
   if (x >= L) x -= L;
   if (!(x >= 0.0)) x = 0.0;
   k = (int)(x / cw);
