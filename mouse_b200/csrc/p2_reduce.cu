@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(RED_THREADS) p2_reduce_kernel(
 }
 
 // ---- fused finish + reduce (mouse_p2_frame, fast sweep): the half-shell sweep's fixed-point accumulators (per
-// sorted slot) are converted, written to out_sum / out_cnt / out_mean in original bond order, handed back zeroed,
+// sorted slot) are converted, written to out_sum / out_cnt / out_mean in original bond order (the next frame build zeroes them again),
 // and reduced to the totals in the same pass.  Deterministic: fixed slot ranges per block, fixed trees.
 struct FinishArgs {
   long long *acc_fix;
@@ -166,14 +166,7 @@ __global__ void __launch_bounds__(RED_THREADS) p2_finish_reduce_kernel(const Fin
       o[q] = in ? idx[s] : 0;
       isref[q] = in && (flag[s] & 1);
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int s = s0 + q * RED_THREADS;
-      if (s < hi) {
-        acc_fix[s] = 0;
-        acc_cnt[s] = 0;
-      }
-    }
+    // (the accumulators are NOT re-zeroed here: every frame build zeroes them in cell_canon_kernel)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int s = s0 + q * RED_THREADS;

@@ -729,6 +729,10 @@ int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const
     // counters 1..4: diagnostics, home-cell ticket, pair list length, overflow flag (the reduce kernel resets
     // the ticket again before using it); a frame build has just cleared all of them
     MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters + 1, 0, 4 * sizeof(int64_t), st));
+    if (grid->fast) {   // a fused frame on the same cell list leaves its sums in the accumulators
+      MOUSE_CUDA_CHECK(cudaMemsetAsync(w.acc_fix, 0, sizeof(long long) * (size_t)n, st));
+      MOUSE_CUDA_CHECK(cudaMemsetAsync(w.acc_cnt, 0, sizeof(int32_t) * (size_t)n, st));
+    }
   }
   int blocks = (int)((n + 127) / 128);
   int maxb = num_sms() * 32;

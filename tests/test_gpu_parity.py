@@ -463,6 +463,45 @@ def test_frame_and_staged_paths_agree():
     assert int(b.hist.sum()) == b.totals_dict()["n_refs"]
 
 
+def test_staged_sweep_after_a_fused_frame_on_the_same_cell_list():
+    """The fused frame leaves its sums in the workspace accumulators; a staged mouse_p2_sweep on the same cell
+    list (no rebuild) must start from zero again - twice in a row, for both molecule modes."""
+    import ctypes as C
+    from mouse_b200 import _lib, engine
+    from mouse_b200.melt import make_melt
+    melt = make_melt(80, 61, seed=9)
+    dev = torch.device("cuda")
+    n = melt.n_bonds
+    L = _lib.lib()
+    grid = _lib.grid_plan(melt.box, 2.0, n)
+    assert grid.fast == 1
+    pos = torch.as_tensor(melt.positions).to(dev)
+    bonds = torch.as_tensor(melt.bond_atoms).to(dev)
+    mol = torch.as_tensor(melt.mol[melt.bond_atoms[:, 0]].astype(np.int32)).to(dev)
+    ws = engine.workspace(L.mouse_workspace_bytes(n, C.byref(grid)), dev)
+    vec = torch.empty((3, n), dtype=torch.float64, device=dev)
+    ctr = torch.empty_like(vec)
+    mean = torch.empty(n, dtype=torch.float64, device=dev)
+    tot = torch.zeros(6, dtype=torch.int64, device=dev)
+    p, st = engine._ptr, engine._stream()
+    out = {}
+    for flags in (_lib.MOUSE_SAME_MOLECULE, 0):
+        ssum = torch.empty(n, dtype=torch.float64, device=dev)
+        cnt = torch.empty(n, dtype=torch.int32, device=dev)
+        rc = L.mouse_p2_frame(p(pos), p(bonds), p(mol), None, None, n, C.byref(grid), flags, p(ws), ws.numel(),
+                              p(vec), p(ctr), p(ssum), p(cnt), p(mean), p(tot), st)
+        assert rc == 0
+        out[flags] = (ssum.clone(), cnt.clone())
+    for _ in range(2):
+        for flags in (_lib.MOUSE_SAME_MOLECULE, 0):
+            s2 = torch.full((n,), -1.0, dtype=torch.float64, device=dev)
+            c2 = torch.full((n,), -1, dtype=torch.int32, device=dev)
+            rc = L.mouse_p2_sweep(p(vec), p(ctr), n, C.byref(grid), flags, p(ws), p(s2), p(c2), st)
+            assert rc == 0
+            torch.cuda.synchronize()
+            assert torch.equal(c2, out[flags][1]) and torch.equal(s2, out[flags][0])
+
+
 def test_dump_trajectory_matches_the_oracle_frame_by_frame():
     """File ingestion row: LAMMPS data + dump -> arrays -> hot path, against the NumPy restatement of the reference
     on the same frames (per-frame box, scaled coordinates)."""
