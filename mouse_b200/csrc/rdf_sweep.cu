@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(128) rdf_sweep_exact_kernel(const RdfArgs a) {
 // sqrt(s) is >= edges[k] (rdf_thresholds_kernel), so "edges[k] <= sqrt(s) < edges[k+1]" is decided by comparing s
 // itself - bit-exact with numpy.histogram's rule, including range ends and the closed last bin.
 #define RH_WARPS 12
+#define RH_QUEUE 256      // ring capacity (power of two); one reference adds at most SLOTS * 32 = 256 entries
 
 struct RdfHalfArgs {
   GridDev g;
@@ -164,6 +165,8 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
   __shared__ float4 s_homeP[2][32];                   // reference atoms of the home cell, 32 at a time, double buffered
   __shared__ double4 s_homeU[2][32];
   __shared__ __align__(16) int s_raw[HS_ITEM_INTS];
+  __shared__ unsigned short s_q[RH_QUEUE];            // hit queue: reference (5 bits) | slot << 5 | lane << 9
+  __shared__ unsigned s_qt;                           // ... its tail (running counter, advanced with one atomic per lane)
   __shared__ __align__(8) uint64_t s_bar;
   const int lane = threadIdx.x;
   const int nbin = a.nbin;
@@ -173,6 +176,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
   if (lane == 0) {
     mbar_init(&s_bar, 1);
     fence_mbar_init();
+    s_qt = 0u;
   }
   __syncwarp();
   uint32_t phase = 0;
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
   const double Lx = a.g.box[0], Ly = a.g.box[1], Lz = a.g.box[2];
   const double hLx = 0.5 * Lx, hLy = 0.5 * Ly, hLz = 0.5 * Lz;
   const float2 nr2 = make_float2(-a.r2hi, -a.r2hi);
-  const uint32_t land_lane = smem_addr(s_land + lane);   // candidate (slot c, this lane) = element c * 32
+  const uint32_t land_base = smem_addr(s_land);          // candidate (slot c, lane l) = element c * 32 + l
   const uint32_t hist_base = smem_addr(s_hist);
 
   // fetch pipeline (see p2_sweep_half_kernel): ticket one item ahead, range table one item ahead
@@ -265,6 +269,62 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
       s_homeU[0][lane] = hu;
       __syncwarp();
 
+      unsigned qh = s_qt;     // hit queue (ring in shared memory): head (running counter), length - warp-uniform
+      int qn = 0;
+      // up to two queued hits per lane (entries lane and lane + 32; those >= navail idle): the reference's FP64
+      // expression and the exact bin.  The two chains are independent and interleave (the single chain is a long
+      // sequence of dependent shared loads, FP64 and conversion instructions)
+      auto walk = [&](const int navail, const int buf) {
+        bool act[2];
+        double4 ui[2], uj[2];
+        uint32_t cand[2];
+        int ilr[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          act[r] = lane + 32 * r < navail;
+          const unsigned e = act[r] ? (unsigned)s_q[(qh + (unsigned)(lane + 32 * r)) & (RH_QUEUE - 1)] : 0u;
+          const int c = (e >> 5) & 15u, lj = e >> 9;
+          ilr[r] = e & 31u;
+          ui[r] = s_homeU[buf][ilr[r]];
+          cand[r] = land_base + (uint32_t)(c * 32 + lj) * 48u;
+          uj[r] = lds_double4(cand[r] + 16u);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          double tx = __dsub_rn(uj[r].x, ui[r].x), ty = __dsub_rn(uj[r].y, ui[r].y), tz = __dsub_rn(uj[r].z, ui[r].z);
+          // dr - L * around(dr / L): around() is 0 whenever |dr| <= L / 2 (ordering_functions.py:72-74); one
+          // rare branch for coordinates that were not wrapped into the box
+          if (!(fabs(tx) <= hLx && fabs(ty) <= hLy && fabs(tz) <= hLz)) {
+            tx = mouse_trim(tx, Lx);
+            ty = mouse_trim(ty, Ly);
+            tz = mouse_trim(tz, Lz);
+          }
+          const double s = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
+          // np.ma.masked_equal(d, 0.) drops coincident atoms (:84); values outside [first, last] are dropped (:86)
+          bool keep = act[r] && s != 0.0 && s >= thr0 && s <= shi;
+          if (!SAME_MOL) keep = keep && uj[r].w != ui[r].w;
+          // bin estimate from an FP32 square root (error << one bin), made exact with the two thresholds around it
+          const float sf = fmaxf((float)s, 1.0e-30f);
+          float rs;
+          asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(sf));      // one MUFU.RSQ; 2 ulp is plenty here
+          int k = (int)((sf * rs - a.first) * a.scale);
+          k = min(max(k, 0), nbin - 1);
+          const double tlo = __ldg(a.thr + k), thi = __ldg(a.thr + k + 1);
+          k += (s >= thi && k < nbin - 1) ? 1 : 0;
+          k -= (s < tlo && k > 0) ? 1 : 0;
+          int slot = 0;
+          if (!ONE_TYPE) {
+            const int ti = __float_as_int(s_homeP[buf][ilr[r]].w);
+            const int tj = lds_int(cand[r] + 12u);
+            const int ta = min(ti, tj), tb = max(ti, tj);
+            slot = (ta * a.ntypes - ta * (ta - 1) / 2 + (tb - ta)) * nbin;
+          }
+          if (keep) {
+            if (SMEM_HIST) reds_add(hist_base + 4u * (uint32_t)(slot + k), 2u);
+            else atomicAdd(&a.hist[(size_t)(slot + k)], 2ULL);
+          }
+        }
+      };
       for (int chunk0 = 0, buf = 0; chunk0 < nhome; chunk0 += 32, buf ^= 1) {
         const int nchunk = min(32, nhome - chunk0);
         // next chunk of reference atoms: loaded now, stored after this chunk has been processed
@@ -272,68 +332,94 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
           hp = a.R[hs + chunk0 + 32 + lane].p;
           hu = a.R[hs + chunk0 + 32 + lane].u;
         }
-        for (int il = 0; il < nchunk; ++il) {
-          const float4 pi = s_homeP[buf][il];
-          const double4 ui = s_homeU[buf][il];
-          const int ti = __float_as_int(pi.w);
-          // ---- FP32 filter: slot c -> bit c of the mask (slots are walked from the last one down)
-          const float2 npx = make_float2(-pi.x, -pi.x), npy = make_float2(-pi.y, -pi.y), npz = make_float2(-pi.z, -pi.z);
-          unsigned mask = 0;
+        for (int il = 0; il < nchunk; il += 2) {
+          // two reference atoms per iteration (two independent filter chains, one queue update); the second one
+          // of an odd tail is switched off
+          const float4 pa = s_homeP[buf][il], pb = s_homeP[buf][(il + 1) & 31];
+          const bool two = il + 1 < nchunk;
+          // ---- FP32 filter: slot c -> bit c of the lane's mask
+          const float2 nax = make_float2(-pa.x, -pa.x), nay = make_float2(-pa.y, -pa.y), naz = make_float2(-pa.z, -pa.z);
+          const float2 nbx = make_float2(-pb.x, -pb.x), nby = make_float2(-pb.y, -pb.y), nbz = make_float2(-pb.z, -pb.z);
+          unsigned maska = 0, maskb = 0;
 #pragma unroll
           for (int pp = NPAIR - 1; pp >= 0; --pp) {
             if (pp < npp) {
-              const float2 dx = __fadd2_rn(xr2[pp], npx), dy = __fadd2_rn(yr2[pp], npy), dz = __fadd2_rn(zr2[pp], npz);
-              const float2 t = __fadd2_rn(__ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx))), nr2);   // < 0: maybe in range
-              mask = __funnelshift_l(__float_as_uint(t.y), mask, 1);
-              mask = __funnelshift_l(__float_as_uint(t.x), mask, 1);
+              const float2 dxa = __fadd2_rn(xr2[pp], nax), dya = __fadd2_rn(yr2[pp], nay), dza = __fadd2_rn(zr2[pp], naz);
+              const float2 dxb = __fadd2_rn(xr2[pp], nbx), dyb = __fadd2_rn(yr2[pp], nby), dzb = __fadd2_rn(zr2[pp], nbz);
+              const float2 ta = __fadd2_rn(__ffma2_rn(dza, dza, __ffma2_rn(dya, dya, __fmul2_rn(dxa, dxa))), nr2);   // < 0: maybe in range
+              const float2 tb = __fadd2_rn(__ffma2_rn(dzb, dzb, __ffma2_rn(dyb, dyb, __fmul2_rn(dxb, dxb))), nr2);
+              maska = __funnelshift_l(__float_as_uint(ta.y), maska, 1);
+              maska = __funnelshift_l(__float_as_uint(ta.x), maska, 1);
+              maskb = __funnelshift_l(__float_as_uint(tb.y), maskb, 1);
+              maskb = __funnelshift_l(__float_as_uint(tb.x), maskb, 1);
             }
           }
           if (w0 < nhome) {       // home-cell candidates lead the concatenation: count home-home pairs once (t > i)
             const int lim = chunk0 + il - w0 - lane;        // slot c allowed iff 32 c > lim
-            const int cmin = min(max((lim + 32) >> 5, 0), 32);
-            mask &= cmin >= 32 ? 0u : ~((1u << cmin) - 1u);
+            const int cmina = min(max((lim + 32) >> 5, 0), 32), cminb = min(max((lim + 33) >> 5, 0), 32);
+            maska &= cmina >= 32 ? 0u : ~((1u << cmina) - 1u);
+            maskb &= cminb >= 32 ? 0u : ~((1u << cminb) - 1u);
           }
-          // ---- the lanes walk their filter hits (highest slot first): exact FP64 distance, exact bin.
-          // Branch-free body; exhausted lanes re-read slot 0 and are masked out by `act`.
-          const int iters = __reduce_max_sync(MOUSE_FULL_MASK, __popc(mask));
-          for (int it = 0; it < iters; ++it) {
-            const bool act = mask != 0;
-            const int c = (int)min((unsigned)(31 - __clz((int)mask)), (unsigned)(SLOTS - 1));   // mask == 0 -> clamped
-            mask &= ~(1u << c);
-            const uint32_t cand = land_lane + (uint32_t)c * (32u * 48u);
-            const double4 uj = lds_double4(cand + 16u);
-            double tx = __dsub_rn(uj.x, ui.x), ty = __dsub_rn(uj.y, ui.y), tz = __dsub_rn(uj.z, ui.z);
-            // dr - L * around(dr / L): around() is 0 whenever |dr| <= L / 2 (ordering_functions.py:72-74); one
-            // rare branch for coordinates that were not wrapped into the box
-            if (!(fabs(tx) <= hLx && fabs(ty) <= hLy && fabs(tz) <= hLz)) {
-              tx = mouse_trim(tx, Lx);
-              ty = mouse_trim(ty, Ly);
-              tz = mouse_trim(tz, Lz);
+          if (!two) maskb = 0u;
+          // ---- the hits go to the warp's queue (reference, slot, lane), so that the exact FP64 part below runs with
+          // two hits per lane whatever their distribution over the lanes (a lane holds 0..SLOTS of them per reference)
+          auto push = [&](unsigned ma, unsigned mb) {
+            const int n2 = __popc(ma) + __popc(mb);
+            if (n2) {
+              unsigned pos = atomicAdd(&s_qt, (unsigned)n2);
+              unsigned ebase = (unsigned)il | ((unsigned)lane << 9);
+              while (ma) {
+                const int c = 31 - __clz((int)ma);
+                ma &= ~(1u << c);
+                s_q[pos & (RH_QUEUE - 1)] = (unsigned short)(ebase | ((unsigned)c << 5));
+                ++pos;
+              }
+              ++ebase;
+              while (mb) {
+                const int c = 31 - __clz((int)mb);
+                mb &= ~(1u << c);
+                s_q[pos & (RH_QUEUE - 1)] = (unsigned short)(ebase | ((unsigned)c << 5));
+                ++pos;
+              }
             }
-            const double s = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
-            // np.ma.masked_equal(d, 0.) drops coincident atoms (:84); values outside [first, last] are dropped (:86)
-            bool keep = act && s != 0.0 && s >= thr0 && s <= shi;
-            if (!SAME_MOL) keep = keep && uj.w != ui.w;
-            // bin estimate from an FP32 square root (error << one bin), made exact with the two thresholds around it
-            const float sf = fmaxf((float)s, 1.0e-30f);
-            float rs;
-            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(sf));      // one MUFU.RSQ; 2 ulp is plenty here
-            int k = (int)((sf * rs - a.first) * a.scale);
-            k = min(max(k, 0), nbin - 1);
-            const double tlo = __ldg(a.thr + k), thi = __ldg(a.thr + k + 1);
-            k += (s >= thi && k < nbin - 1) ? 1 : 0;
-            k -= (s < tlo && k > 0) ? 1 : 0;
-            int slot = 0;
-            if (!ONE_TYPE) {
-              const int tj = lds_int(cand + 12u);
-              const int ta = min(ti, tj), tb = max(ti, tj);
-              slot = (ta * a.ntypes - ta * (ta - 1) / 2 + (tb - ta)) * nbin;
+          };
+          auto drain = [&]() {
+            __syncwarp();
+            while (qn > 0) {
+              const int m = min(qn, 64);
+              walk(m, buf);
+              qh += m;
+              qn -= m;
             }
-            if (keep) {
-              if (SMEM_HIST) reds_add(hist_base + 4u * (uint32_t)(slot + k), 2u);
-              else atomicAdd(&a.hist[(size_t)(slot + k)], 2ULL);
+            __syncwarp();
+          };
+          int tot = __reduce_add_sync(MOUSE_FULL_MASK, __popc(maska) + __popc(maskb));
+          if (qn + tot > RH_QUEUE) {      // cannot happen below ~3 hits per lane and reference
+            drain();
+            if (tot > RH_QUEUE) {         // more than 4 per lane and reference: one reference at a time
+              const int ta = __reduce_add_sync(MOUSE_FULL_MASK, __popc(maska));
+              push(maska, 0u);
+              qn = ta;
+              drain();
+              maska = 0u;
+              tot -= ta;
             }
           }
+          push(maska, maskb);
+          qn += tot;
+          __syncwarp();
+          // ---- full rounds of 64 queued hits: exact FP64 distance, exact bin, two hits per lane
+          while (qn >= 64) {
+            walk(64, buf);
+            qh += 64;
+            qn -= 64;
+          }
+          __syncwarp();
+        }
+        if (qn > 0) {       // the reference chunk (and, after the last chunk, the landing zone) is about to change
+          walk(qn, buf);
+          qh += qn;
+          qn = 0;
         }
         __syncwarp();
         s_homeP[buf ^ 1][lane] = hp;

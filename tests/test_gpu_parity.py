@@ -325,6 +325,26 @@ def test_rdf_fast_sweep_lattice_on_bin_edges():
     assert np.array_equal(h.cpu().numpy(), exp) and int(exp.sum()) > 0
 
 
+@pytest.mark.parametrize("same", [True, False])
+def test_rdf_fast_sweep_dense_blobs_overflow_the_hit_queue(same):
+    """Tight blobs: nearly every candidate of a home cell is in range, so one pair of reference atoms produces
+    more hits than the warp's hit queue holds (the one-reference-at-a-time path), two atom types."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(17)
+    box = np.array([12.0, 12.0, 12.0])
+    centres = np.array([[0.3, 0.2, -0.4], [0.9, 0.3, -0.2], [-4.0, 3.0, 5.9], [5.8, -5.9, 0.0]])
+    pos = np.concatenate([c + 0.35 * rng.normal(size=(k, 3)) for c, k in zip(centres, (700, 500, 400, 300))]
+                         + [rng.uniform(-6, 6, size=(800, 3))])
+    pos = pos - np.floor((pos + 6.0) / 12.0) * 12.0
+    n = len(pos)
+    typ = rng.integers(0, 2, n).astype(np.int32)
+    mol = (np.arange(n) // 7).astype(np.int32)
+    eng = _engine()
+    h, _ = eng.rdf_frame(pos, typ, mol, 2, box, 0., 2.0, 40, same_molecule=same)
+    exp, _ = c_oracle.rdf(pos, typ, mol, 2, box, 0., 2.0, 40, same)
+    assert np.array_equal(h.cpu().numpy(), exp) and int(exp.sum()) > 200000
+
+
 def test_cli_matches_reference_output(capsys):
     """calculate_local_ordering.py <golden data file> --bondtypes 1 --max 1.5 --same-molecule prints the
     reference's S for that file (the golden S came from the reference's own Config of the same arrays)."""
