@@ -96,6 +96,9 @@ __global__ void __launch_bounds__(128) rdf_sweep_exact_kernel(const RdfArgs a) {
 // sqrt(s) is >= edges[k] (rdf_thresholds_kernel), so "edges[k] <= sqrt(s) < edges[k+1]" is decided by comparing s
 // itself - bit-exact with numpy.histogram's rule, including range ends and the closed last bin.
 #define RH_WARPS 12
+#ifndef RH_WALK
+#define RH_WALK 2          // queued hits per lane and walk round
+#endif
 #define RH_QUEUE 256      // ring capacity (power of two); one reference adds at most SLOTS * 32 = 256 entries
 
 struct RdfHalfArgs {
@@ -275,12 +278,12 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
       // expression and the exact bin.  The two chains are independent and interleave (the single chain is a long
       // sequence of dependent shared loads, FP64 and conversion instructions)
       auto walk = [&](const int navail, const int buf) {
-        bool act[2];
-        double4 ui[2], uj[2];
-        uint32_t cand[2];
-        int ilr[2];
+        bool act[RH_WALK];
+        double4 ui[RH_WALK], uj[RH_WALK];
+        uint32_t cand[RH_WALK];
+        int ilr[RH_WALK];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < RH_WALK; ++r) {
           act[r] = lane + 32 * r < navail;
           const unsigned e = act[r] ? (unsigned)s_q[(qh + (unsigned)(lane + 32 * r)) & (RH_QUEUE - 1)] : 0u;
           const int c = (e >> 5) & 15u, lj = e >> 9;
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
           uj[r] = lds_double4(cand[r] + 16u);
         }
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < RH_WALK; ++r) {
           double tx = __dsub_rn(uj[r].x, ui[r].x), ty = __dsub_rn(uj[r].y, ui[r].y), tz = __dsub_rn(uj[r].z, ui[r].z);
           // dr - L * around(dr / L): around() is 0 whenever |dr| <= L / 2 (ordering_functions.py:72-74); one
           // rare branch for coordinates that were not wrapped into the box
@@ -386,7 +389,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
           auto drain = [&]() {
             __syncwarp();
             while (qn > 0) {
-              const int m = min(qn, 64);
+              const int m = min(qn, 32 * RH_WALK);
               walk(m, buf);
               qh += m;
               qn -= m;
@@ -409,10 +412,10 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
           qn += tot;
           __syncwarp();
           // ---- full rounds of 64 queued hits: exact FP64 distance, exact bin, two hits per lane
-          while (qn >= 64) {
-            walk(64, buf);
-            qh += 64;
-            qn -= 64;
+          while (qn >= 32 * RH_WALK) {
+            walk(32 * RH_WALK, buf);
+            qh += 32 * RH_WALK;
+            qn -= 32 * RH_WALK;
           }
           __syncwarp();
         }
