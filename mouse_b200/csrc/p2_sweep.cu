@@ -467,13 +467,13 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
 #define HS_RUN(N)                                                                                                  \
   hs_ref_loop<SLOTS, (N <= NPAIR ? N : NPAIR), EXCL_MOL>(a, k, lane, pass, hs, nhome, xr2, yr2, zr2, ux, uy, uz, accj, cntj, \
                                                           molr, s_homeP, s_homeU, s_acc, s_cnt, s_gid)
-    switch (npp) {
+    switch (npp) {      // npp <= NPAIR: the other cases are not instantiated
       case 1: HS_RUN(1); break;
-      case 2: HS_RUN(2); break;
-      case 3: HS_RUN(3); break;
-      case 4: HS_RUN(4); break;
-      case 5: HS_RUN(5); break;
-      default: HS_RUN(6); break;
+      case 2: if constexpr (NPAIR >= 2) HS_RUN(2); break;
+      case 3: if constexpr (NPAIR >= 3) HS_RUN(3); break;
+      case 4: if constexpr (NPAIR >= 4) HS_RUN(4); break;
+      case 5: if constexpr (NPAIR >= 5) HS_RUN(5); break;
+      default: if constexpr (NPAIR >= 6) HS_RUN(6); break;
     }
 #undef HS_RUN
     // ---- candidate side: one pair of integer atomics per candidate that was hit
