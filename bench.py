@@ -39,6 +39,7 @@ UNIT = "pairs/s"
 W_LANE_INSTR_PER_PAIR = 55.2      # 6.45 x 7 FP32 + 10 FP64 lane-instructions per counted pair
 BYTES_PER_BOND = 72.0             # compulsory HBM bytes per bond per frame
 N_FRAME_VARIANTS = 4              # distinct frames cycled (working set per frame ~210 MB > 126 MB L2)
+LANES = 3                         # frames in flight in the device-resident timed region (own stream + workspace each)
 
 
 # ------------------------------------------------------------------------------------------- clocks
@@ -238,32 +239,43 @@ def run_ours(args):
     mol = torch.as_tensor(melt.mol[melt.bond_atoms[:, 0]].astype(np.int32)).to(dev)
     L = _lib.lib()
     grid = _lib.grid_plan(melt.box, rcut, n)
-    ws = engine.workspace(L.mouse_workspace_bytes(n, C.byref(grid)), dev)
-    vec = torch.empty((3, n), dtype=torch.float64, device=dev)
-    ctr = torch.empty_like(vec)
-    ssum = torch.empty(n, dtype=torch.float64, device=dev)
-    cnt = torch.empty(n, dtype=torch.int32, device=dev)
-    mean = torch.empty(n, dtype=torch.float64, device=dev)
+    # LANES frames in flight, each on its own stream with its own workspace and per-bond outputs (frames are
+    # independent): the HBM-side kernels and the tail of the persistent sweep of one frame overlap the sweep of
+    # the next.  Lane 0 alone (serialised frames) gives the per-kernel durations of the roofline object.
+    nbytes = L.mouse_workspace_bytes(n, C.byref(grid))
+    lanes = []
+    for _ in range(LANES):
+        lanes.append(dict(ws=torch.empty(int(nbytes) + 4096, dtype=torch.uint8, device=dev),
+                          vec=torch.empty((3, n), dtype=torch.float64, device=dev),
+                          ctr=torch.empty((3, n), dtype=torch.float64, device=dev),
+                          ssum=torch.empty(n, dtype=torch.float64, device=dev),
+                          cnt=torch.empty(n, dtype=torch.int32, device=dev),
+                          mean=torch.empty(n, dtype=torch.float64, device=dev),
+                          stream=torch.cuda.Stream(device=dev), done=torch.cuda.Event()))
     tot = torch.zeros((warm + steps, 6), dtype=torch.int64, device=dev)
-    box3 = (C.c_double * 3)(*[float(b) for b in melt.box])
+    tot_serial = torch.zeros((100, 6), dtype=torch.int64, device=dev)
     p, flags = engine._ptr, _lib.MOUSE_SAME_MOLECULE
     stream = torch.cuda.current_stream()
-    st = C.c_void_p(stream.cuda_stream)
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     sweep_ev = [(ev(), ev()) for _ in range(steps)]
+    serial_ev = [(ev(), ev()) for _ in range(min(steps, 100))]
 
-    for e0_, e1_ in sweep_ev:          # create the CUDA events (torch creates them lazily at the first record)
+    for e0_, e1_ in sweep_ev + serial_ev:   # create the CUDA events (torch creates them lazily at the first record)
         e0_.record(stream)
         e1_.record(stream)
 
-    def frame(k, timed_idx=None):
+    def frame(k, timed=None, lane=None, out=None):
         # one C-ABI call per frame: K1+K2 (fused build), K3 (half-shell sweep + exact fixup), K4 (fused finish + reduce);
-        # the two events bracket the K3 launches on the same stream
+        # the two events bracket the K3 launches on the frame's stream
+        ln = lanes[k % LANES if lane is None else lane]
         pos = frames_dev[k % N_FRAME_VARIANTS]
-        ev0 = C.c_void_p(sweep_ev[timed_idx][0].cuda_event) if timed_idx is not None else None
-        ev1 = C.c_void_p(sweep_ev[timed_idx][1].cuda_event) if timed_idx is not None else None
-        _lib.check(L.mouse_p2_frame_timed(p(pos), p(bonds), p(mol), None, None, n, C.byref(grid), flags, p(ws), ws.numel(),
-                                          p(vec), p(ctr), p(ssum), p(cnt), p(mean), p(tot[k]), ev0, ev1, st), "p2_frame")
+        ev0 = C.c_void_p(timed[0].cuda_event) if timed is not None else None
+        ev1 = C.c_void_p(timed[1].cuda_event) if timed is not None else None
+        _lib.check(L.mouse_p2_frame_timed(p(pos), p(bonds), p(mol), None, None, n, C.byref(grid), flags, p(ln["ws"]),
+                                          ln["ws"].numel(), p(ln["vec"]), p(ln["ctr"]), p(ln["ssum"]), p(ln["cnt"]),
+                                          p(ln["mean"]), p(tot[k] if out is None else out[k]), ev0, ev1,
+                                          C.c_void_p(ln["stream"].cuda_stream)),
+                   "p2_frame")
 
     def barrier():
         if world > 1:
@@ -296,8 +308,13 @@ def run_ours(args):
     n_before = len(sampler.samples)
     e0, e1 = ev(), ev()
     e0.record(stream)
+    for ln in lanes:
+        ln["stream"].wait_event(e0)
     for k in range(steps):
-        frame(warm + k, k)
+        frame(warm + k, sweep_ev[k])
+    for ln in lanes:
+        ln["done"].record(ln["stream"])
+        stream.wait_event(ln["done"])
     totals = TrajectoryTotals()
     # the path's only collective: all-reduce of the packed order-parameter sums (device tensors)
     tsum = tot[warm:].sum(dim=0)
@@ -312,12 +329,21 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
-    sweep_ms = float(np.mean([a.elapsed_time(b) for a, b in sweep_ev]))
+    sweep_ms_overlapped = float(np.mean([a.elapsed_time(b) for a, b in sweep_ev]))
+    # per-kernel durations: the same frames once more, serialised on one lane (in the overlapped region above the
+    # kernels of up to LANES frames share the SMs, so an in-stream duration there is not a kernel time)
+    s0, s1 = ev(), ev()
+    ln0 = lanes[0]["stream"]
+    s0.record(ln0)
+    for k, tev in enumerate(serial_ev):
+        frame(k, tev, lane=0, out=tot_serial)
+    s1.record(ln0)
+    torch.cuda.synchronize()
+    serial_ms = s0.elapsed_time(s1) / len(serial_ev)
+    sweep_ms = float(np.mean([a.elapsed_time(b) for a, b in serial_ev]))
     if os.environ.get("MOUSE_BENCH_DIAG"):
-        gaps = [sweep_ev[i][0].elapsed_time(sweep_ev[i + 1][0]) for i in range(steps - 1)]
-        sys.stderr.write("frame-to-frame ms: " + " ".join("%.2f" % g for g in gaps) + "\n")
-        sys.stderr.write("first sweep start after e0: %.3f ms; last sweep end to e1: %.3f ms\n" % (
-            e0.elapsed_time(sweep_ev[0][0]), sweep_ev[-1][1].elapsed_time(e1)))
+        sys.stderr.write("overlapped frame %.4f ms; serial frame %.4f ms, sweep %.4f ms (in-stream, overlapped: %.4f ms)\n" % (
+            ms / steps, serial_ms, sweep_ms, sweep_ms_overlapped))
     tl = tot[warm:].cpu()
     pairs_local = int(tl[:, 2].sum())
     pairs_all = int(tsum[2].item()) if world > 1 else pairs_local
@@ -373,9 +399,10 @@ def run_ours(args):
         except (OSError, KeyError, ValueError):
             pass
         peak_issue = sms * 128 * f_clk * 1e6                       # lane-instructions / s
-        sweep_pairs_s = (pairs_local / steps) / (sweep_ms * 1e-3)
+        pairs_serial = float(tot_serial[:len(serial_ev), 2].sum().item()) / len(serial_ev)
+        sweep_pairs_s = pairs_serial / (sweep_ms * 1e-3)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        build_ms = ms / steps - sweep_ms
+        build_ms = serial_ms - sweep_ms
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm_done,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -385,13 +412,15 @@ def run_ours(args):
                        "l2": "~%d MB touched per frame (L2 is 126 MB), %d distinct frames cycled"
                              % (int(230e-6 * n), N_FRAME_VARIANTS),
                        "frames_per_s": world * steps / (ms * 1e-3),
-                       "parallelism": "frames sharded, %d rank(s), one NCCL all-reduce of packed sums" % world,
+                       "parallelism": "frames sharded, %d rank(s), one NCCL all-reduce of packed sums; %d frames in "
+                                      "flight per GPU (own stream / workspace each)" % (world, LANES),
                        "S_mean": totals.mean_s},
             "e2e": {"value": float(e2e_p.item()) / float(e2e_t.item()), "unit": UNIT,
                     "h2d_bytes_per_step": pipe.h2d_bytes_per_frame, "d2h_bytes_per_step": pipe.d2h_bytes_per_frame,
                     "ms_per_step": 1e3 * float(e2e_t.item()) / steps,
                     "note": "FramePipeline.submit(): pinned host positions -> H2D -> K1-K4 -> 48-byte totals -> D2H, "
-                            "copy of frame k+1 overlapped with kernels of frame k; topology resident"},
+                            "%d frames in flight (copy of frame k+1 and its HBM-side kernels overlap the sweep of frame k); "
+                            "topology resident" % pipe.depth},
             "gpu_launches": steps * 9 + (2 if world > 1 else 0),
             "clocks": clocks,
             "roofline": {
@@ -402,9 +431,13 @@ def run_ours(args):
                 "traffic": traffic, "traffic_source": traffic_src,
                 "how": "SURVEY 8(d): ordered pairs/s x 55.2 lane-instr/pair (full-shell bound; the kernel is half-shell: "
                        "every unordered pair is decided once and counted for both partners) over SMs x 128 lanes x f_clk "
-                       "(%d SMs, %.0f MHz %s); sweep %.3f ms/launch (CUDA events, in the timed region)"
-                       % (sms, f_clk, "sampled under load" if clocks and clocks.get("sm_mhz") else "max clock", sweep_ms),
-                "sweep_ms": sweep_ms, "sweep_pairs_per_s": sweep_pairs_s,
+                       "(%d SMs, %.0f MHz %s); sweep %.3f ms/launch: CUDA events around the K3 launches of %d frames "
+                       "serialised on one stream right after the timed region (in the timed region up to %d frames "
+                       "share the SMs; the in-stream duration there is %.3f ms)"
+                       % (sms, f_clk, "sampled under load" if clocks and clocks.get("sm_mhz") else "max clock", sweep_ms,
+                          len(serial_ev), LANES, sweep_ms_overlapped),
+                "sweep_ms": sweep_ms, "sweep_ms_in_timed_region": sweep_ms_overlapped, "serial_frame_ms": serial_ms,
+                "sweep_pairs_per_s": sweep_pairs_s,
                 "hbm": {"bound": "hbm", "stage": "K1+K2+K4 build/reduce stages", "achieved": BYTES_PER_BOND * n /
                         (max(build_ms, 1e-6) * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": BYTES_PER_BOND * n / (max(build_ms, 1e-6) * 1e-3) / 1e9 / hbm_peak,

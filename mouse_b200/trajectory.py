@@ -70,11 +70,15 @@ def all_reduce_totals(t: TrajectoryTotals, device) -> TrajectoryTotals:
 
 class FramePipeline:
     """Host-buffer entry point of the hot path for one topology: ``submit(positions_host)`` copies a
-    frame's positions from pinned host memory, runs K1-K4 and reads back the 48-byte totals.  Two
-    buffers / two streams: the copy of frame k+1 overlaps the kernels of frame k."""
+    frame's positions from pinned host memory, runs K1-K4 and reads back the 48-byte totals.
+    ``depth`` frames are in flight, each on its own compute stream with its own workspace and per-bond
+    outputs: the copy of frame k+1 overlaps the kernels of frame k, and the HBM-side kernels / the tail of
+    the persistent sweep of one frame overlap the sweep of the next (frames are independent,
+    ``calculate_local_ordering.py:39-76``).  Per-bond results of a frame live in ``slot["sum"/"cnt"/"mean"]``
+    until the slot is reused."""
 
     def __init__(self, bond_atoms, mol, box, rcut, n_atoms, same_molecule=True, nbr_mask=None, ref_mask=None,
-                 device=None, depth=2):
+                 device=None, depth=3):
         engine.require_cuda()
         self.device = torch.device(device or "cuda")
         self.n_atoms = int(n_atoms)
@@ -93,47 +97,58 @@ class FramePipeline:
         nbytes = L.mouse_workspace_bytes(self.n, C.byref(self.grid))
         self.depth = depth
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        self.compute_stream = torch.cuda.Stream(device=self.device)
         self.slots = []
         for _ in range(depth):
             self.slots.append(dict(
                 pos=torch.empty((self.n_atoms, 3), dtype=torch.float64, device=self.device),
                 totals=torch.zeros(6, dtype=torch.int64, device=self.device),
                 totals_host=torch.zeros(6, dtype=torch.int64).pin_memory(),
-                copied=torch.cuda.Event(), done=torch.cuda.Event(), busy=False))
-        # one workspace and one set of per-bond outputs: frames are serialised on the compute stream
-        self.ws = torch.empty(int(nbytes) + 4096, dtype=torch.uint8, device=self.device)
-        self.vec = torch.empty((3, self.n), dtype=torch.float64, device=self.device)
-        self.ctr = torch.empty((3, self.n), dtype=torch.float64, device=self.device)
-        self.sum = torch.empty(self.n, dtype=torch.float64, device=self.device)
-        self.cnt = torch.empty(self.n, dtype=torch.int32, device=self.device)
-        self.mean = torch.empty(self.n, dtype=torch.float64, device=self.device)
+                copied=torch.cuda.Event(), done=torch.cuda.Event(), busy=False,
+                stream=torch.cuda.Stream(device=self.device),
+                ws=torch.empty(int(nbytes) + 4096, dtype=torch.uint8, device=self.device),
+                vec=torch.empty((3, self.n), dtype=torch.float64, device=self.device),
+                ctr=torch.empty((3, self.n), dtype=torch.float64, device=self.device),
+                sum=torch.empty(self.n, dtype=torch.float64, device=self.device),
+                cnt=torch.empty(self.n, dtype=torch.int32, device=self.device),
+                mean=torch.empty(self.n, dtype=torch.float64, device=self.device)))
+            assert self.slots[-1]["ws"].data_ptr() % 256 == 0
         self._next = 0
         self._pending = []
         self.h2d_bytes_per_frame = self.n_atoms * 3 * 8
         self.d2h_bytes_per_frame = 48
         self.kernels_per_frame = 9   # bond_assign, 2 x scan, scatter_idx, canon, sweep, fixup, exact check, finish+reduce
 
-    def submit(self, positions_host: torch.Tensor):
-        """Enqueue one frame (``positions_host``: pinned (N_a,3) f64 CPU tensor).  Returns finished
-        results (list of totals dicts) that had to be drained to free a slot."""
+    def submit(self, positions_host, tag=None):
+        """Enqueue one frame.  ``positions_host``: (N_a,3) f64 - a pinned CPU tensor is copied asynchronously as it
+        is; a NumPy array / pageable tensor is staged through the slot's own pinned buffer; a CUDA tensor is
+        copied on the device.  Returns the finished results (list of totals dicts, submission order, each with
+        the ``tag`` it was submitted with) that had to be collected to free a slot."""
         out = []
         s = self.slots[self._next]
         if s["busy"]:
             out.append(self._collect(s))
+        s["tag"] = tag
         p = engine._ptr
+        src = positions_host
+        if not isinstance(src, torch.Tensor):
+            src = torch.from_numpy(np.ascontiguousarray(src, dtype=np.float64))
+        if src.device.type == "cpu" and not src.is_pinned():
+            if "stage" not in s:
+                s["stage"] = torch.empty((self.n_atoms, 3), dtype=torch.float64).pin_memory()
+            s["stage"].copy_(src.reshape(self.n_atoms, 3))
+            src = s["stage"]
         with torch.cuda.stream(self.copy_stream):
-            s["pos"].copy_(positions_host, non_blocking=True)
+            s["pos"].copy_(src.reshape(self.n_atoms, 3), non_blocking=True)
             s["copied"].record(self.copy_stream)
-        with torch.cuda.stream(self.compute_stream):
-            self.compute_stream.wait_event(s["copied"])
-            st = C.c_void_p(self.compute_stream.cuda_stream)
+        with torch.cuda.stream(s["stream"]):
+            s["stream"].wait_event(s["copied"])
+            st = C.c_void_p(s["stream"].cuda_stream)
             _lib.check(self.L.mouse_p2_frame(p(s["pos"]), p(self.bonds), p(self.mol), p(self.nbr), p(self.ref), self.n,
-                                             C.byref(self.grid), self.flags, p(self.ws), self.ws.numel(), p(self.vec),
-                                             p(self.ctr), p(self.sum), p(self.cnt), p(self.mean), p(s["totals"]), st),
+                                             C.byref(self.grid), self.flags, p(s["ws"]), s["ws"].numel(), p(s["vec"]),
+                                             p(s["ctr"]), p(s["sum"]), p(s["cnt"]), p(s["mean"]), p(s["totals"]), st),
                        "mouse_p2_frame")
             s["totals_host"].copy_(s["totals"], non_blocking=True)
-            s["done"].record(self.compute_stream)
+            s["done"].record(s["stream"])
         s["busy"] = True
         self._pending.append(s)
         self._next = (self._next + 1) % self.depth
@@ -146,7 +161,7 @@ class FramePipeline:
             self._pending.remove(s)
         t = s["totals_host"]
         return dict(sum_mean=float(t.view(torch.float64)[0]), n_refs=int(t[1]), n_pairs=int(t[2]),
-                    n_zero_len=int(t[3]))
+                    n_zero_len=int(t[3]), tag=s.get("tag"))
 
     def drain(self):
         return [self._collect(s) for s in list(self._pending)]
@@ -164,13 +179,20 @@ def local_ordering_trajectory(frames_positions, bond_atoms, mol, box, rcut, same
     device = torch.device(device or "cuda")
     totals = TrajectoryTotals()
     per_frame = []
-    res = None
-    for f in range(lo, hi):
-        res = engine.p2_frame(frames_positions[f], bond_atoms, mol, box, rcut, same_molecule=same_molecule,
-                              nbr_mask=nbr_mask, ref_mask=ref_mask, device=device, out=res)
-        t = res.totals_dict()
-        totals.add_frame(t["sum_mean"], t["n_refs"], t["n_pairs"])
-        per_frame.append((f, np.float64(1.5 * t["sum_mean"] / t["n_refs"] - 0.5) if t["n_refs"] else np.float64("nan")))
+    if hi > lo:
+        # fixed topology and box: the frames go through the pipeline (several frames in flight, no per-frame sync)
+        n_atoms = int(np.asarray(frames_positions[lo].shape)[0]) if hasattr(frames_positions[lo], "shape") \
+            else len(frames_positions[lo])
+        pipe = FramePipeline(bond_atoms, mol, box, rcut, n_atoms, same_molecule=same_molecule, nbr_mask=nbr_mask,
+                             ref_mask=ref_mask, device=device)
+        done = []
+        for f in range(lo, hi):
+            done += pipe.submit(frames_positions[f], tag=f)
+        done += pipe.drain()
+        for t in done:
+            totals.add_frame(t["sum_mean"], t["n_refs"], t["n_pairs"])
+            per_frame.append((t["tag"], np.float64(1.5 * t["sum_mean"] / t["n_refs"] - 0.5) if t["n_refs"]
+                              else np.float64("nan")))
     return per_frame, all_reduce_totals(totals, device)
 
 

@@ -522,6 +522,34 @@ def test_staged_sweep_after_a_fused_frame_on_the_same_cell_list():
             assert torch.equal(c2, out[flags][1]) and torch.equal(s2, out[flags][0])
 
 
+def test_trajectory_pipeline_matches_frame_by_frame_calls():
+    """local_ordering_trajectory (several frames in flight, own stream / workspace each) gives, frame by frame
+    and bit for bit, what separate p2_frame calls give; results come back in submission order."""
+    from mouse_b200.melt import jitter, make_melt
+    from mouse_b200.trajectory import FramePipeline, local_ordering_trajectory
+    melt = make_melt(50, 41, seed=2)
+    eng = _engine()
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    frames = [melt.positions] + [jitter(melt, f, 0.05) for f in range(1, 8)]
+    per_frame, totals = local_ordering_trajectory(frames, melt.bond_atoms, molb, melt.box, 2.0, same_molecule=False)
+    assert [f for f, _ in per_frame] == list(range(8))
+    n_pairs = 0
+    for f, s in per_frame:
+        res = eng.p2_frame(frames[f], melt.bond_atoms, molb, melt.box, 2.0, same_molecule=False)
+        assert s == res.order_parameter()
+        n_pairs += res.totals_dict()["n_pairs"]
+    assert totals.n_frames == 8 and totals.n_pairs == n_pairs
+    # per-bond outputs of the last submitted frame stay in its slot; pinned, pageable and device inputs agree
+    pipe = FramePipeline(melt.bond_atoms, molb, melt.box, 2.0, melt.n_atoms, same_molecule=False, depth=2)
+    pinned = torch.from_numpy(frames[3]).pin_memory()
+    done = pipe.submit(pinned, tag="a") + pipe.submit(frames[3], tag="b") + pipe.submit(torch.from_numpy(frames[3]).cuda(), tag="c")
+    done += pipe.drain()
+    assert [d["tag"] for d in done] == ["a", "b", "c"]
+    assert len({(d["sum_mean"], d["n_refs"], d["n_pairs"]) for d in done}) == 1
+    ref = eng.p2_frame(frames[3], melt.bond_atoms, molb, melt.box, 2.0, same_molecule=False)
+    assert torch.equal(pipe.slots[0]["cnt"], ref.count) and torch.equal(pipe.slots[0]["sum"], ref.sum)
+
+
 def test_dump_trajectory_matches_the_oracle_frame_by_frame():
     """File ingestion row: LAMMPS data + dump -> arrays -> hot path, against the NumPy restatement of the reference
     on the same frames (per-frame box, scaled coordinates)."""
