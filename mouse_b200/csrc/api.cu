@@ -29,6 +29,7 @@ int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, 
 int mouse_launch_director_p2(const double *vec, const uint8_t *mask, int64_t n, const double *director, double *out_s,
                              int64_t *hist, double smin, double smax, int32_t nbins, cudaStream_t st);
 extern int mouse_fast_slots_override;
+extern int mouse_fast_warps_override;
 extern int mouse_fast_variant;
 
 static thread_local char g_err[512] = "";
@@ -48,6 +49,7 @@ const char *mouse_last_error(void) { return g_err; }
 int mouse_set_tuning(const char *key, int value) {
   if (!strcmp(key, "fast_slots")) mouse_fast_slots_override = value;
   else if (!strcmp(key, "fast_variant")) mouse_fast_variant = value;
+  else if (!strcmp(key, "fast_warps")) mouse_fast_warps_override = value;
   else {
     mouse_set_error("unknown tuning key %s", key);
     return MOUSE_EINVAL;

@@ -670,6 +670,7 @@ static int num_sms() {
 
 int mouse_fast_variant = 1;         // tuning / debug knob (2 = skip the fixup kernel)
 int mouse_fast_slots_override = 0;  // test / tuning hook (set through mouse_set_tuning)
+int mouse_fast_warps_override = 0;  // tuning hook: resident sweep warps per SM (0 = as many as fit)
 
 template <int SLOTS, bool EXCL>
 static void launch_half_one(const SweepArgs &a, cudaStream_t st) {
@@ -679,7 +680,9 @@ static void launch_half_one(const SweepArgs &a, cudaStream_t st) {
     if (blocks_per_sm < 1) blocks_per_sm = 1;
   }
   // persistent warps: every resident warp (CTA) pulls home cells from the ticket counter
-  int blocks = num_sms() * blocks_per_sm;
+  int per_sm = blocks_per_sm;
+  if (mouse_fast_warps_override > 0 && mouse_fast_warps_override < per_sm) per_sm = mouse_fast_warps_override;
+  int blocks = num_sms() * per_sm;
   if (blocks > a.g.ncell) blocks = a.g.ncell;
   p2_sweep_half_kernel<SLOTS, EXCL><<<blocks, 32, 0, st>>>(a);
 }

@@ -24,7 +24,10 @@ def lane():
                 c=torch.empty(n, dtype=torch.int32, device=dev), m=torch.empty(n, dtype=torch.float64, device=dev),
                 t=torch.zeros(6, dtype=torch.int64, device=dev), st=torch.cuda.Stream(device=dev))
 
-for S in (1, 2, 3, 1, 2):
+for key in ('fast_slots', 'fast_warps'):
+    if os.environ.get('MOUSE_' + key.upper()):
+        L.mouse_set_tuning(key.encode(), int(os.environ['MOUSE_' + key.upper()]))
+for S in (1, 3, 4):
     lanes = [lane() for _ in range(S)]
     def run(K):
         for k in range(K):
