@@ -393,7 +393,7 @@ def run_ours(args):
         f_clk = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
         traffic, traffic_src = None, None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the sweep kernel (ncu --set full capture)
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_sweep_half_v5.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_sweep_half_v6.json")))
             traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
             traffic_src = prof["source"]
         except (OSError, KeyError, ValueError):
