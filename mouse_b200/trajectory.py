@@ -118,16 +118,28 @@ class FramePipeline:
         self.d2h_bytes_per_frame = 48
         self.kernels_per_frame = 9   # bond_assign, 2 x scan, scatter_idx, canon, sweep, fixup, exact check, finish+reduce
 
-    def submit(self, positions_host, tag=None):
+    def submit(self, positions_host, tag=None, box=None, rcut=None):
         """Enqueue one frame.  ``positions_host``: (N_a,3) f64 - a pinned CPU tensor is copied asynchronously as it
         is; a NumPy array / pageable tensor is staged through the slot's own pinned buffer; a CUDA tensor is
         copied on the device.  Returns the finished results (list of totals dicts, submission order, each with
-        the ``tag`` it was submitted with) that had to be collected to free a slot."""
+        the ``tag`` it was submitted with) that had to be collected to free a slot.  ``box`` / ``rcut``: this
+        frame's own box and cutoff (NPT dumps): the cell grid is re-planned for the frame, the slot's workspace
+        grows if the new grid needs it."""
         out = []
         s = self.slots[self._next]
         if s["busy"]:
             out.append(self._collect(s))
         s["tag"] = tag
+        grid, flags = self.grid, self.flags
+        if box is not None or rcut is not None:
+            rc = self.rcut if rcut is None else float(rcut)
+            grid = _lib.grid_plan(self.box if box is None else [float(b) for b in box], rc, self.n)
+            flags = (self.flags & ~_lib.MOUSE_NO_CUTOFF) | (_lib.MOUSE_NO_CUTOFF if rc < 0 else 0)
+            need = self.L.mouse_workspace_bytes(self.n, C.byref(grid))
+            if s["ws"].numel() < need:
+                s["ws"] = torch.empty(int(need * 1.1) + 4096, dtype=torch.uint8, device=self.device)
+                assert s["ws"].data_ptr() % 256 == 0
+        s["grid"] = grid     # keeps the ctypes struct alive until the call below has returned
         p = engine._ptr
         src = positions_host
         if not isinstance(src, torch.Tensor):
@@ -144,7 +156,7 @@ class FramePipeline:
             s["stream"].wait_event(s["copied"])
             st = C.c_void_p(s["stream"].cuda_stream)
             _lib.check(self.L.mouse_p2_frame(p(s["pos"]), p(self.bonds), p(self.mol), p(self.nbr), p(self.ref), self.n,
-                                             C.byref(self.grid), self.flags, p(s["ws"]), s["ws"].numel(), p(s["vec"]),
+                                             C.byref(grid), flags, p(s["ws"]), s["ws"].numel(), p(s["vec"]),
                                              p(s["ctr"]), p(s["sum"]), p(s["cnt"]), p(s["mean"]), p(s["totals"]), st),
                        "mouse_p2_frame")
             s["totals_host"].copy_(s["totals"], non_blocking=True)
@@ -216,13 +228,17 @@ def local_ordering_from_dump(topology, dump_path, bondtypes=None, rcut=0., coord
     mol = topology.bond_mol_hash().astype(np.int32)
     totals = TrajectoryTotals()
     per_frame = []
-    res = None
-    for f in range(lo, hi):
-        rc = float(rcut) if rcut != 0. else engine.half_diagonal(boxes[f])
-        res = engine.p2_frame(positions[f], topology.bond_atoms, mol, boxes[f], rc, same_molecule=same_molecule,
-                              nbr_mask=nbr_mask, ref_mask=ref_mask, device=device, out=res)
-        t = res.totals_dict()
-        totals.add_frame(t["sum_mean"], t["n_refs"], t["n_pairs"])
-        s = np.float64(1.5 * t["sum_mean"] / t["n_refs"] - 0.5) if t["n_refs"] else np.float64("nan")
-        per_frame.append((int(timesteps[f]), s))
+    if hi > lo:
+        rc0 = float(rcut) if rcut != 0. else engine.half_diagonal(boxes[lo])
+        pipe = FramePipeline(topology.bond_atoms, mol, boxes[lo], rc0, positions[lo].shape[0],
+                             same_molecule=same_molecule, nbr_mask=nbr_mask, ref_mask=ref_mask, device=device)
+        done = []
+        for f in range(lo, hi):
+            rc = float(rcut) if rcut != 0. else engine.half_diagonal(boxes[f])
+            done += pipe.submit(positions[f], tag=int(timesteps[f]), box=boxes[f], rcut=rc)
+        done += pipe.drain()
+        for t in done:
+            totals.add_frame(t["sum_mean"], t["n_refs"], t["n_pairs"])
+            per_frame.append((t["tag"], np.float64(1.5 * t["sum_mean"] / t["n_refs"] - 0.5) if t["n_refs"]
+                              else np.float64("nan")))
     return per_frame, all_reduce_totals(totals, device)
