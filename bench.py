@@ -226,6 +226,7 @@ def run_ours(args):
     # the CPU-baseline leg forks worker processes: run it before this process creates a CUDA context
     cpu_line = cpu_baseline(melt) if (world == 1 and not args.no_cpu_baseline) else None
     torch.cuda.set_device(local_rank)
+    numa_bound = engine.bind_host_to_gpu(local_rank) if (world > 1 and not os.environ.get("MOUSE_BENCH_NOBIND")) else False
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -420,7 +421,7 @@ def run_ours(args):
                     "ms_per_step": 1e3 * float(e2e_t.item()) / steps,
                     "note": "FramePipeline.submit(): pinned host positions -> H2D -> K1-K4 -> 48-byte totals -> D2H, "
                             "%d frames in flight (copy of frame k+1 and its HBM-side kernels overlap the sweep of frame k); "
-                            "topology resident" % pipe.depth},
+                            "topology resident%s" % (pipe.depth, "; host process bound to the GPU's CPU set" if numa_bound else "")},
             "gpu_launches": steps * 9 + (2 if world > 1 else 0),
             "clocks": clocks,
             "roofline": {

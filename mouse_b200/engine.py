@@ -41,6 +41,28 @@ def workspace(nbytes: int, device) -> torch.Tensor:
     return buf
 
 
+def bind_host_to_gpu(device_index: int) -> bool:
+    """Pin this process to the CPUs NVML reports as local to the GPU (same NUMA node / PCIe root), so that the
+    pinned staging buffers allocated afterwards are first-touched next to the device.  Matters when several
+    ranks stream frames over PCIe at the same time; returns False (and changes nothing) when NVML or
+    sched_setaffinity is not available or the mask would be empty."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        have = os.sched_getaffinity(0)
+        cpus &= have
+        if not cpus or cpus == have:     # no topology information (e.g. a VM that reports every CPU for every GPU)
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 def as_dev(x, dtype, device):
     if x is None:
         return None
