@@ -25,7 +25,8 @@ def build_parser():
     ap.add_argument("--subcell", type=float, nargs="+", help="xmin xmax ymin ymax zmin zmax, box-relative")
     ap.add_argument("--reference-residue", type=str, nargs="+", help="residue types of the reference bonds")
     ap.add_argument("--same-molecule", action="store_true", help="also count bonds of the same molecule")
-    ap.add_argument("--out-pdb", type=str, nargs="*", help="(not on the accelerated path) PDB with CXX atom types")
+    ap.add_argument("--out-pdb", type=str, nargs="*", help="output .pdb with atom types encoding the local ordering "
+                                                          "value, e.g. CXX, where XX is the value in %%")
     return ap
 
 
@@ -56,7 +57,7 @@ def main(argv=None):
                                                sbins=args.histo_bins, referenceResTypes=args.reference_residue,
                                                sameMolecule=args.same_molecule)
         if store:
-            sys.stderr.write("--out-pdb: atom types were recoloured in memory; PDB writing is outside the hot path\n")
+            frame.write_pdb(args.out_pdb[0], hide_pbc_bonds=True)     # calculate_local_ordering.py:66,74
         if args.mode == "average":
             sys.stdout.write(str(s) + "\n")
         elif args.mode == "histo":

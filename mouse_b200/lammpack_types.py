@@ -41,6 +41,25 @@ class Atom:
         self.num = 0
         self.charge = 0.
         self.mass = 0.0
+        self.is_hetatm = False
+        self.res_insert = ""
+        self.bfactor = 0.0
+        self.occupancy = 0.0
+
+    def pdb_str(self):
+        """One ATOM / HETATM record, field widths of ``lammpack_types.py:41-53`` (5-column serial; the record
+        name loses its last blank from atom 100 000 on, which PyMol still reads)."""
+        name = "HETATM" if self.is_hetatm else ("ATOM  " if self.num < 100000 else "ATOM ")
+        t = self.type
+        if len(t) == 1:
+            t = " " + t + "  "
+        elif len(t) == 2:
+            t = " " + t + " "
+        elif len(t) == 3:
+            t = t + " " if t[0].isdigit() else " " + t
+        return "%s%5s %4s %4s%1s%4d%1s   %8.3f%8.3f%8.3f%6.2f%6.2f         %2s%2s" % (
+            name, self.num, t, self.res_type, self.mol_id[:1], self.res_num, self.res_insert,
+            self.pos.x, self.pos.y, self.pos.z, self.occupancy, self.bfactor, "  ", "  ")
 
 
 class Bond:
@@ -49,6 +68,11 @@ class Bond:
         self.atom2 = None
         self.type = ""
         self.num = 0
+
+    def pdb_str(self):
+        """CONECT record (``lammpack_types.py:94-99``): 5-column serials, 7 from atom 100 000 on."""
+        w = 7 if (self.atom1.num >= 100000 or self.atom2.num >= 100000) else 5
+        return "CONECT" + str(self.atom1.num).rjust(w) + str(self.atom2.num).rjust(w)
 
 
 class Config:
@@ -72,6 +96,29 @@ class Config:
 
     def set_box_center(self, c):
         self._box_center = c
+
+    def write_pdb(self, pdb, hide_pbc_bonds=False):
+        """PDB file as the reference writes it (``lammpack_types.py:316-339``): TITLE, orthorhombic CRYST1, one
+        MODEL with the atoms, TER / ENDMDL, then the CONECT records; ``hide_pbc_bonds`` drops bonds that span
+        more than half a box edge (they would be drawn across the cell).  The reference orders atoms and
+        bonds with a comparator that only ever answers "less" or "equal"; for files read in ascending order
+        (every LAMMPS data file) that is the stored order, which is what is written here."""
+        box = self.box()
+        with open(pdb, "w") as f:
+            f.write("TITLE     " + self.title + "\n")
+            f.write("%6s%9.3f%9.3f%9.3f%7.2f%7.2f%7.2f\n" % ("CRYST1", box.x, box.y, box.z, 90., 90., 90.))
+            f.write("MODEL     %4i\n" % 1)
+            for atom in self._atoms:
+                f.write(atom.pdb_str() + "\n")
+            f.write("TER\n")
+            f.write("ENDMDL\n")
+            for bond in self._bonds:
+                if hide_pbc_bonds:
+                    a1, a2 = bond.atom1.pos, bond.atom2.pos
+                    if (box.x > 0 and abs(a2.x - a1.x) / box.x > 0.5) or (box.y > 0 and abs(a2.y - a1.y) / box.y > 0.5) \
+                            or (box.z > 0 and abs(a2.z - a1.z) / box.z > 0.5):
+                        continue
+                f.write(bond.pdb_str() + "\n")
 
     def n_atom(self):
         return len(self._atoms)

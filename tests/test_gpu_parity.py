@@ -361,6 +361,20 @@ def test_cli_matches_reference_output(capsys):
     assert abs(float(out) - float(g["ref_S"])) <= RTOL * abs(float(g["ref_S"]))
 
 
+def test_cli_out_pdb_matches_the_reference_file(tmp_path, capsys):
+    """calculate_local_ordering.py ... --out-pdb: the recoloured PDB (CXX / CmXX atom types from the per-atom mean
+    P2, ``ordering_functions.py:207-220``) equals the file the reference wrote, and S is still printed."""
+    import os
+    import calculate_local_ordering as cli
+    from tests.util import GOLDEN_DIR
+    out = tmp_path / "coloured.pdb"
+    cli.main([os.path.join(GOLDEN_DIR, "melt_290.data"), "--bondtypes", "1", "--max", "1.5", "--same-molecule",
+              "--out-pdb", str(out)])
+    assert out.read_text() == open(os.path.join(GOLDEN_DIR, "melt_290_coloured.pdb")).read()
+    _, g = load_golden("melt_290_rc15_same")
+    assert abs(float(capsys.readouterr().out.strip()) - float(g["ref_S"])) <= RTOL * abs(float(g["ref_S"]))
+
+
 def test_cli_selections_on_arrays_match_the_object_path(capsys):
     """--chains / --subcell: the CLI's array path (ingest + FrameArrays selections) against the same selections made
     on the object model with the mirrors of the reference's select_chains / select_rectangular."""

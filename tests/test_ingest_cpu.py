@@ -69,3 +69,18 @@ def test_array_selections_equal_the_object_selections():
         assert np.array_equal(got.positions, ref.positions) and np.array_equal(got.atom_num, ref.atom_num)
         assert np.array_equal(got.bond_atoms, ref.bond_atoms) and np.array_equal(got.bond_num, ref.bond_num)
         assert got.atom_mol == ref.atom_mol and got.bond_type == ref.bond_type
+
+
+def test_write_pdb_matches_the_reference_file(tmp_path):
+    """Config.write_pdb(hide_pbc_bonds=True) of the mirror object model writes, byte for byte, the file the
+    reference writes for the same LAMMPS data file (tests/golden/make_golden_pdb.py)."""
+    import os
+    from mouse_b200.lammpack_misc import read_data_typeselect
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    cfg = read_data_typeselect(os.path.join(gold, "melt_290.data"))
+    out = tmp_path / "plain.pdb"
+    cfg.write_pdb(str(out), hide_pbc_bonds=True)
+    assert out.read_text() == open(os.path.join(gold, "melt_290_plain.pdb")).read()
+    # without hiding, every bond gets its CONECT record
+    cfg.write_pdb(str(out))
+    assert sum(l.startswith("CONECT") for l in out.read_text().splitlines()) == cfg.n_bond()
