@@ -668,3 +668,34 @@ def test_rdf_cli_prints_the_reference_table(capsys):
     printRdfs(rdfs, False, out=buf)
     assert out == buf.getvalue() and out.startswith("#r\tvol\t1_1\t1_AAAAA\tAAAAA_AAAAA\n")
     assert sum(float(line.split("\t")[2]) for line in out.splitlines()[1:]) > 0
+
+
+def test_crystallinity_and_com_rdf_clis(tmp_path, capsys):
+    """calculate_crystallinity.py / calculate_com_rdfs.py (the reference's flags): printed tables equal the
+    reference-format printers applied to the golden histogram / to the mirror function; --out-pdb writes the
+    recoloured atoms; --mode average fails like the reference."""
+    import io
+    import os
+    import calculate_com_rdfs as com_cli
+    import calculate_crystallinity as cli
+    from mouse_b200 import ordering_functions as of
+    from mouse_b200.lammpack_misc import printHistogram, printRdfs, read_data_typeselect
+    from tests.util import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "next_290.npz"))
+    path = os.path.join(GOLDEN_DIR, "melt_290.data")
+    pdb = tmp_path / "c.pdb"
+    cli.main([path, "--mode", "histo", "--bins", "40", "--bondtypes", "1", "--reference", "0", "0", "1", "--out-pdb", str(pdb)])
+    out = capsys.readouterr().out
+    hist = dict(min=-0.5, max=1.0, nbins=40, step=float(g["cryst_z_step"]), values=list(g["cryst_z_values"]),
+                norm=list(g["cryst_z_norm"]))
+    assert out == printHistogram(hist, norm=True)
+    types = [line[12:16].strip() for line in pdb.read_text().splitlines() if line.startswith("ATOM")]
+    assert types == [str(t) for t in g["cryst_z_types"]]
+    with pytest.raises(KeyError):
+        cli.main([path, "--bondtypes", "1"])
+    capsys.readouterr()
+    com_cli.main([path, "--rmin", "0.", "--rmax", "4.0", "--nbin", "32"])
+    out = capsys.readouterr().out
+    buf = io.StringIO()
+    printRdfs(of.CalculateComRdfs(read_data_typeselect(path), 0., 4., 32), True, out=buf)
+    assert out == buf.getvalue() and len(out.splitlines()) == 33
