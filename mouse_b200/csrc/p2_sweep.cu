@@ -8,9 +8,10 @@
 //    arrays: they are fetched with 1-D TMA bulk copies (cp.async.bulk + mbarrier) into a shared-memory
 //    landing zone, moved into REGISTERS (lane t % 32, slot t / 32: FP32 wrapped coordinates as packed
 //    pairs, FP64 unit vectors) and the landing zone is immediately re-armed with the NEXT home cell's
-//    copies, which then overlap the arithmetic.  Per reference bond (warp-uniform loop, broadcast LDS):
-//    packed f32x2 distance test against the guard band, dense FP64 cos^2 = (u_i . u_j)^2 for every
-//    slot, predicated accumulation into the reference's and the candidate's registers.  Candidates
+//    copies, which then overlap the arithmetic.  The references are taken in groups of eight, two per
+//    loop iteration (warp-uniform loop, broadcast LDS): packed f32x2 distance test against the guard
+//    band, dense FP64 cos^2 = (u_i . u_j)^2 for every slot, branch-free accumulation into the
+//    reference's and the candidate's registers (the hit predicate clears the weight).  Candidates
 //    inside the FP32 guard band around rc^2, and sure hits with |u_i . u_j| < 1e-9 (the reference masks
 //    cos^2 == 0, :113), are NOT decided here: they are appended to a pair list and decided with the
 //    reference's exact un-fused FP64 expressions by p2_fixup_kernel.  Sums are merged across home cells
