@@ -18,18 +18,58 @@ The parsing itself is NumPy block conversion (one ``split`` per section instead 
 """
 from __future__ import annotations
 
+import itertools
+
 import numpy as np
 
 from .frames import FrameArrays
 
 
 def _block(lines, ncol_min):
-    """Whitespace-separated numeric block -> list of token rows (ragged widths allowed)."""
+    """Whitespace-separated block of a LAMMPS section -> per-COLUMN token lists ``cols[j][row]``, addressed from
+    the front (``cols[j]``) or from the end of the line (``cols[j - ncol]``).  One ``str.split`` over the whole
+    block when every line has the same number of tokens (every file LAMMPS writes); ragged blocks fall back to
+    one split per line and are addressed per row through ``_RaggedCols``."""
+    if not lines:
+        return _Cols([], 0, 0)
+    ncol = len(lines[0].split())
+    if ncol < ncol_min:
+        raise ValueError("short line in LAMMPS section: %r" % lines[0])
+    tokens = "\n".join(lines).split()
+    if len(tokens) == ncol * len(lines) and all(len(ln.split()) == ncol for ln in lines[::61]) \
+            and len(lines[-1].split()) == ncol:
+        # same total, same width on the first, the last and every 61st line: a block LAMMPS wrote
+        return _Cols(tokens, ncol, len(lines))
     rows = [ln.split() for ln in lines]
     for r in rows:
         if len(r) < ncol_min:
             raise ValueError("short line in LAMMPS section: %r" % " ".join(r))
-    return rows
+    return _RaggedCols(rows)
+
+
+class _Cols:
+    def __init__(self, tokens, ncol, nrow):
+        self.tokens, self.ncol, self.nrow = tokens, ncol, nrow
+
+    def __len__(self):
+        return self.nrow
+
+    def col(self, j):
+        """Column ``j`` (negative: counted from the end of the line) as a list of token strings."""
+        if self.ncol == 0:
+            return []
+        return self.tokens[j % self.ncol::self.ncol]
+
+
+class _RaggedCols:
+    def __init__(self, rows):
+        self.rows, self.nrow = rows, len(rows)
+
+    def __len__(self):
+        return self.nrow
+
+    def col(self, j):
+        return [r[j] for r in self.rows]
 
 
 def read_lmp_data_arrays(path, bonds=True) -> FrameArrays:
@@ -61,22 +101,26 @@ def read_lmp_data_arrays(path, bonds=True) -> FrameArrays:
             natom = int(w[0])
         elif len(w) >= 2 and w[1] == "bonds":
             nbond = int(w[0])
-    atom_rows = atom_rows or []
+    if atom_rows is None:
+        atom_rows = _block([], 9)
     n = len(atom_rows)
-    num = np.fromiter((int(r[0]) for r in atom_rows), np.int64, n)
-    pos = np.array([[r[-6], r[-5], r[-4]] for r in atom_rows], dtype=np.float64).reshape(n, 3)
-    mol = [r[1] for r in atom_rows]
-    typ = [r[2] for r in atom_rows]
-    if bonds and bond_rows:
+    num = np.array(atom_rows.col(0), dtype=np.int64).reshape(n)
+    # coordinates (and image flags) are taken from the END of the line (lammpack_lmp_functions.py:22-27)
+    pos = np.empty((n, 3), np.float64)
+    for a, j in enumerate((-6, -5, -4)):
+        pos[:, a] = np.array(atom_rows.col(j), dtype=np.float64).reshape(n)
+    mol = atom_rows.col(1)
+    typ = atom_rows.col(2)
+    if bonds and bond_rows is not None and len(bond_rows):
         m = len(bond_rows)
-        a = np.array([[r[2], r[3]] for r in bond_rows], dtype=np.int64).reshape(m, 2)
+        a = np.stack([np.array(bond_rows.col(2), dtype=np.int64), np.array(bond_rows.col(3), dtype=np.int64)], 1).reshape(m, 2)
         a.sort(axis=1)                               # atom1 = lower atom number (lammpack_lmp_functions.py:8-11)
         order = np.argsort(num, kind="stable")
         where = np.searchsorted(num[order], a.ravel())
         if np.any(where >= n) or np.any(num[order][np.minimum(where, n - 1)] != a.ravel()):
             raise KeyError("bond refers to an unknown atom number")
         ba = order[where].reshape(m, 2).astype(np.int32)
-        btype = [r[1] for r in bond_rows]
+        btype = bond_rows.col(1)
         bnum = np.arange(1, m + 1, dtype=np.int64)   # renumbered in file order (:12)
     else:
         ba, btype, bnum = np.zeros((0, 2), np.int32), [], np.zeros(0, np.int64)
@@ -116,7 +160,11 @@ def iter_lmp_dump_frames(path, atom_num, coords_type="scaled"):
                     lo[a], hi[a] = float(w[0]), float(w[1])
             elif item.split()[0] == "ATOMS":
                 keys = item.split()[1:]
-                data = np.array([f.readline().split() for _ in range(natom)], dtype=np.float64).reshape(natom, len(keys))
+                block = "".join(itertools.islice(f, natom))
+                data = np.fromstring(block, dtype=np.float64, sep=" ") if block.strip() else np.zeros(0)
+                if data.size != natom * len(keys):      # non-numeric columns or a short block: token by token
+                    data = np.array([ln.split() for ln in block.split("\n") if ln.strip()], dtype=np.float64)
+                data = data.reshape(natom, len(keys))
                 ids = data[:, keys.index("id")].astype(np.int64)
                 where = np.searchsorted(sorted_num, ids)
                 if np.any(where >= n) or np.any(sorted_num[np.minimum(where, n - 1)] != ids):
