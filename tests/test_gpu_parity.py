@@ -137,6 +137,11 @@ def test_sparse_cells_use_a_coarser_grid(same):
     np.testing.assert_allclose(res.mean.cpu().numpy()[ok], ora["mean"][ok], rtol=1e-12, atol=ATOL_MEAN)
     s_ref = 1.5 * ora["mean"][ok].sum() / ok.sum() - 0.5
     assert abs(res.order_parameter() - s_ref) <= RTOL * abs(s_ref)
+    # the RDF sweep runs on the same (widened) cell list
+    typ = np.zeros(melt.n_atoms, np.int32)
+    h, _ = eng.rdf_frame(melt.positions, typ, melt.mol, 1, melt.box, 0., rc, 48, same_molecule=same)
+    exp, _ = c_oracle.rdf(melt.positions, typ, melt.mol, 1, melt.box, 0., rc, 48, same)
+    assert np.array_equal(h.cpu().numpy(), exp) and int(exp.sum()) > 0
 
 
 def test_deterministic_and_slot_variants():
