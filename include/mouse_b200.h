@@ -163,6 +163,14 @@ int mouse_set_tuning(const char *key, int value);
  * with -DMOUSE_PHASE_TIMERS); synchronises `stream`. */
 int mouse_debug_counters(const mouse_grid_t *grid, int64_t n_items, const void *ws, int64_t *out8 /*HOST*/, void *stream);
 
+/* HOST only (file ingestion row).  Parses the whitespace-separated decimal numbers of a text
+ * block (the ATOMS section of a LAMMPS dump, lammpack_types.py:377-395 reads it with one float() per token) into
+ * out[0..cap).  Correctly rounded: numbers with <= 15 significant digits and a decimal exponent within +-22 take the
+ * exact fast path (integer mantissa times / divided by an exactly representable power of ten, one rounding), all
+ * others go through strtod.  Returns the number of values written, or -(offset + 1) of the first token that is not a
+ * number or does not fit. */
+int64_t mouse_parse_doubles(const char *text /*HOST*/, int64_t len, double *out /*HOST*/, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,7 +36,7 @@ EXPORTS = [
     "mouse_version", "mouse_last_error", "mouse_set_tuning", "mouse_grid_plan", "mouse_bond_build",
     "mouse_workspace_bytes", "mouse_cell_build", "mouse_p2_sweep", "mouse_p2_pair_lists", "mouse_p2_reduce",
     "mouse_p2_frame", "mouse_p2_frame_timed", "mouse_rdf_frame", "mouse_single_ref_workspace_bytes", "mouse_p2_single_ref",
-    "mouse_rdf_single_ref", "mouse_director_p2", "mouse_debug_counters",
+    "mouse_rdf_single_ref", "mouse_director_p2", "mouse_debug_counters", "mouse_parse_doubles",
 ]
 
 
@@ -82,6 +82,8 @@ def lib():
                                        C.POINTER(C.c_double), i32, vp, vp, vp]
     L.mouse_director_p2.argtypes = [vp, vp, i64, C.POINTER(C.c_double), vp, vp, dbl, dbl, i32, vp]
     L.mouse_debug_counters.argtypes = [gp, i64, vp, vp, vp]
+    L.mouse_parse_doubles.argtypes = [C.c_char_p, i64, vp, i64]
+    L.mouse_parse_doubles.restype = i64
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:

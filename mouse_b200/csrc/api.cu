@@ -1,6 +1,7 @@
 // C-ABI entry points of libmouse_b200 (see include/mouse_b200.h for the contract).
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -289,3 +290,84 @@ int mouse_debug_counters(const mouse_grid_t *grid, int64_t n_items, const void *
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ host-side ingestion helper
+int64_t mouse_parse_doubles(const char *text, int64_t len, double *out, int64_t cap) {
+  static const double p10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  const char *s = text, *end = text + len;
+  int64_t n = 0;
+  for (;;) {
+    while (s < end && (*s == ' ' || *s == '\n' || *s == '\t' || *s == '\r')) ++s;
+    if (s >= end) break;
+    const char *tok = s;
+    if (n >= cap) return -((int64_t)(tok - text) + 1);
+    bool neg = false;
+    if (*s == '-' || *s == '+') neg = (*s++ == '-');
+    uint64_t m = 0;
+    int digits = 0, frac = 0;
+    bool any = false, lead = true;
+    while (s < end && *s >= '0' && *s <= '9') {
+      any = true;
+      if (!(lead && *s == '0')) {
+        lead = false;
+        if (digits < 19) m = m * 10 + (uint64_t)(*s - '0');
+        ++digits;
+      }
+      ++s;
+    }
+    if (s < end && *s == '.') {
+      ++s;
+      while (s < end && *s >= '0' && *s <= '9') {
+        any = true;
+        if (!(lead && *s == '0')) {
+          lead = false;
+          if (digits < 19) m = m * 10 + (uint64_t)(*s - '0');
+          ++digits;
+        }
+        ++frac;
+        ++s;
+      }
+    }
+    int e10 = 0;
+    bool fast = any;
+    if (any && s < end && (*s == 'e' || *s == 'E')) {
+      const char *save = s++;
+      bool eneg = false;
+      if (s < end && (*s == '-' || *s == '+')) eneg = (*s++ == '-');
+      if (s < end && *s >= '0' && *s <= '9') {
+        int e = 0;
+        while (s < end && *s >= '0' && *s <= '9') {
+          if (e < 10000) e = e * 10 + (*s - '0');
+          ++s;
+        }
+        e10 = eneg ? -e : e;
+      } else {
+        s = save;      // "1e" / "1ex": not an exponent
+        fast = false;
+      }
+    }
+    const bool token_ends = s >= end || *s == ' ' || *s == '\n' || *s == '\t' || *s == '\r';
+    const int e = e10 - frac;
+    if (fast && token_ends && digits <= 15 && e >= -22 && e <= 22) {
+      double v = (double)m;                       // exact: m < 10^15 < 2^53
+      v = e >= 0 ? v * p10[e] : v / p10[-e];      // one correctly rounded operation with an exact power of ten
+      out[n++] = neg ? -v : v;
+      continue;
+    }
+    // everything else (long mantissas, large exponents, nan / inf, malformed tokens): the C library
+    const char *t = tok;
+    while (t < end && !(*t == ' ' || *t == '\n' || *t == '\t' || *t == '\r')) ++t;
+    char buf[128];
+    const size_t tl = (size_t)(t - tok);
+    if (tl == 0 || tl >= sizeof(buf)) return -((int64_t)(tok - text) + 1);
+    memcpy(buf, tok, tl);
+    buf[tl] = 0;
+    char *stop = nullptr;
+    const double v = strtod(buf, &stop);
+    if (stop != buf + tl) return -((int64_t)(tok - text) + 1);
+    out[n++] = v;
+    s = t;
+  }
+  return n;
+}

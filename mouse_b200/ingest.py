@@ -131,6 +131,21 @@ def read_lmp_data_arrays(path, bonds=True) -> FrameArrays:
 _COORD_KEYS = {"scaled": ("xs", "ys", "zs"), "cut": ("xc", "yc", "zc"), "uncut": ("xu", "yu", "zu")}
 
 
+def _parse_numbers(block: bytes, count: int):
+    """``count`` whitespace-separated numbers of a text block as float64 (correctly rounded, the same values
+    ``float()`` gives): the C parser of ``libmouse_b200.so`` (``mouse_parse_doubles``), NumPy's text parser when the
+    library is not built.  ``None`` when the block does not hold exactly ``count`` numbers."""
+    try:
+        import ctypes as C
+        from . import _lib
+        out = np.empty(max(count, 1), np.float64)
+        got = _lib.lib().mouse_parse_doubles(block, len(block), C.c_void_p(out.ctypes.data), count)
+        return out[:count] if got == count else None
+    except (ImportError, OSError):
+        data = np.fromstring(block.decode(), dtype=np.float64, sep=" ") if block.strip() else np.zeros(0)
+        return data if data.size == count else None
+
+
 def iter_lmp_dump_frames(path, atom_num, coords_type="scaled"):
     """Yield ``(timestep, box[3], box_center[3], positions[N,3], images[N,3] or None)`` per frame of a LAMMPS dump,
     with the rows ordered like ``atom_num`` (the topology's atom numbers)."""
@@ -140,10 +155,10 @@ def iter_lmp_dump_frames(path, atom_num, coords_type="scaled"):
     order = np.argsort(atom_num, kind="stable")
     sorted_num = atom_num[order]
     n = len(atom_num)
-    with open(path, "r") as f:
+    with open(path, "rb") as f:
         timestep, natom, lo, hi = 0, n, np.zeros(3), np.zeros(3)
         while True:
-            head = f.readline()
+            head = f.readline().decode()
             item = head[6:-1]
             if len(item) == 0:
                 break
@@ -160,10 +175,10 @@ def iter_lmp_dump_frames(path, atom_num, coords_type="scaled"):
                     lo[a], hi[a] = float(w[0]), float(w[1])
             elif item.split()[0] == "ATOMS":
                 keys = item.split()[1:]
-                block = "".join(itertools.islice(f, natom))
-                data = np.fromstring(block, dtype=np.float64, sep=" ") if block.strip() else np.zeros(0)
-                if data.size != natom * len(keys):      # non-numeric columns or a short block: token by token
-                    data = np.array([ln.split() for ln in block.split("\n") if ln.strip()], dtype=np.float64)
+                block = b"".join(itertools.islice(f, natom))
+                data = _parse_numbers(block, natom * len(keys))
+                if data is None:                        # non-numeric columns or a short block: token by token
+                    data = np.array([ln.split() for ln in block.decode().split("\n") if ln.strip()], dtype=np.float64)
                 data = data.reshape(natom, len(keys))
                 ids = data[:, keys.index("id")].astype(np.int64)
                 where = np.searchsorted(sorted_num, ids)

@@ -84,3 +84,40 @@ def test_write_pdb_matches_the_reference_file(tmp_path):
     # without hiding, every bond gets its CONECT record
     cfg.write_pdb(str(out))
     assert sum(l.startswith("CONECT") for l in out.read_text().splitlines()) == cfg.n_bond()
+
+
+def test_parse_doubles_is_correctly_rounded():
+    """mouse_parse_doubles (the dump reader's number parser): bit-identical to Python float() on fixed, general,
+    exponent, long-mantissa and special tokens; reports the offset of a token that is not a number."""
+    import ctypes as C
+    import random
+    from mouse_b200 import _lib
+    L = _lib.lib()
+    rng = random.Random(7)
+    toks = ["0", "-0", "0.0", "-0.000", "1e5", "1E-5", "+3.5", ".5", "5.", "0.000001234", "123456789012345",
+            "1234567890123456", "1e22", "1e23", "1e-22", "1e-23", "000123.4500", "9007199254740993", "1e308", "4.9e-324",
+            "2.2250738585072014e-308", "0.1", "0.30000000000000004", "nan", "inf", "-inf"]
+    for _ in range(20000):
+        k = rng.random()
+        if k < 0.3:
+            toks.append("%.6f" % rng.uniform(-100, 100))
+        elif k < 0.5:
+            toks.append("%.10g" % rng.uniform(-1e5, 1e5))
+        elif k < 0.65:
+            toks.append(repr(rng.uniform(-1, 1)))
+        elif k < 0.75:
+            toks.append("%d" % rng.randint(-10**9, 10**9))
+        elif k < 0.9:
+            toks.append("%.8e" % (rng.uniform(-1, 1) * 10.0**rng.randint(-30, 30)))
+        else:
+            toks.append("%.15g" % rng.uniform(-1e3, 1e3))
+    text = (" ".join(toks[:5000]) + "\n" + "\t".join(toks[5000:]) + " \r\n").encode()
+    out = np.empty(len(toks))
+    assert L.mouse_parse_doubles(text, len(text), C.c_void_p(out.ctypes.data), out.size) == len(toks)
+    exp = np.array([float(t) for t in toks])
+    assert np.array_equal(out.view(np.int64)[~np.isnan(exp)], exp.view(np.int64)[~np.isnan(exp)])
+    assert np.array_equal(np.isnan(out), np.isnan(exp))
+    bad = b"1.0 2.0 abc 3.0"
+    assert L.mouse_parse_doubles(bad, len(bad), C.c_void_p(out.ctypes.data), out.size) == -(bad.index(b"abc") + 1)
+    assert L.mouse_parse_doubles(b"1 2 3", 5, C.c_void_p(out.ctypes.data), 2) == -(4 + 1)     # does not fit
+    assert L.mouse_parse_doubles(b"  \n", 3, C.c_void_p(out.ctypes.data), 2) == 0
