@@ -11,7 +11,8 @@
  * passed as void*; every function returns 0 on success or a negative MOUSE_E* code and never
  * throws; nothing allocates behind the caller's back: scratch memory is a caller-provided
  * workspace sized by the *_workspace_bytes() queries.  All launches are asynchronous on
- * `stream`; entry points keep no static state besides the thread-local last-error string.
+ * `stream`; entry points keep no mutable static state besides the thread-local last-error string (the
+ * only cache is a table of immutable per-device facts: SM count, resident CTAs per SM).
  */
 #ifndef MOUSE_B200_H
 #define MOUSE_B200_H
@@ -32,6 +33,11 @@ extern "C" {
 #define MOUSE_SAME_MOLECULE 1u /* include pairs within one molecule (reference: sameMolecule=True) */
 #define MOUSE_FORCE_EXACT 2u   /* use the all-FP64 sweep even when the FP32-filter sweep applies */
 #define MOUSE_NO_CUTOFF 4u     /* reference: rcut < 0 (ordering_functions.py:102-103) */
+#define MOUSE_FORCE_FAST 16u   /* P2: keep the FP32-filter sweep even when the cells are crowded (tests) */
+/* Tuning fields inside `flags` (0 = automatic; there is no process-global tuning state): register-resident candidate
+ * slots per lane of the fast P2 sweep (4, 6 or 8) and resident sweep warps per SM. */
+#define MOUSE_SLOTS(n) (((uint32_t)(n) & 0xffu) << 8)
+#define MOUSE_WARPS(n) (((uint32_t)(n) & 0xffu) << 16)
 
 /* Cell grid chosen on the host for one frame (box, cutoff). */
 typedef struct mouse_grid {
@@ -90,13 +96,14 @@ int mouse_cell_build(const double *vec, const double *ctr, const int32_t *mol /*
  * out_cnt[b] = their number (0 = the reference raised NameError / bond is not a reference).
  * Outputs are indexed by ORIGINAL bond index and fully overwritten. */
 int mouse_p2_sweep(const double *vec, const double *ctr, int64_t n_bonds, const mouse_grid_t *grid,
-                   uint32_t flags, const void *ws, double *out_sum /*DEV [n]*/, int32_t *out_cnt /*DEV [n]*/,
-                   void *stream);
+                   uint32_t flags, void *ws /*DEV, holds the cell list*/, size_t ws_bytes,
+                   double *out_sum /*DEV [n]*/, int32_t *out_cnt /*DEV [n]*/, void *stream);
 
 /* Optional second pass: the counted neighbour lists themselves (CSR over original bond index,
- * rows ascending).  row_ptr = exclusive scan of out_cnt (n+1 entries, int64), computed here. */
+ * rows ascending).  row_ptr = exclusive scan of out_cnt (n+1 entries, int64), computed here; entries at or beyond
+ * `capacity` (the allocated length of nbr_idx, normally sum(cnt)) are never written. */
 int mouse_p2_pair_lists(const double *vec, const double *ctr, int64_t n_bonds, const mouse_grid_t *grid,
-                        uint32_t flags, const void *ws, const int32_t *cnt /*DEV [n]*/,
+                        uint32_t flags, void *ws, size_t ws_bytes, const int32_t *cnt /*DEV [n]*/,
                         int64_t *row_ptr /*DEV [n+1] out*/, int32_t *nbr_idx /*DEV [capacity] out*/,
                         int64_t capacity, void *stream);
 
@@ -105,9 +112,9 @@ int mouse_p2_pair_lists(const double *vec, const double *ctr, int64_t n_bonds, c
  * count == 0), totals, optional histogram of 1.5*m-0.5 with the reference's bin rule.
  * hist may be NULL.  totals is DEV memory. */
 int mouse_p2_reduce(const double *sum /*DEV [n]*/, const int32_t *cnt /*DEV [n]*/, int64_t n_bonds,
-                    const mouse_grid_t *grid, const void *ws, double *out_mean /*DEV [n]*/, mouse_p2_totals_t *totals /*DEV*/,
-                    int64_t *hist /*DEV [nbins] or NULL*/, double smin, double smax, int32_t nbins,
-                    void *stream);
+                    const mouse_grid_t *grid, void *ws, size_t ws_bytes, double *out_mean /*DEV [n]*/,
+                    mouse_p2_totals_t *totals /*DEV*/, int64_t *hist /*DEV [nbins] or NULL*/, double smin, double smax,
+                    int32_t nbins, void *stream);
 
 /* K1..K4 in one call, device buffers (the timed hot path of bench.py `value`). */
 int mouse_p2_frame(const double *pos, const int32_t *bond_atoms, const int32_t *mol, const uint8_t *nbr_mask,
@@ -157,8 +164,6 @@ int mouse_rdf_single_ref(const double *np_atoms, int64_t n, const double *ref, c
 int mouse_director_p2(const double *vec, const uint8_t *mask, int64_t n_bonds, const double *director, double *out_s,
                       int64_t *hist, double smin, double smax, int32_t nbins, void *stream);
 
-/* Test / tuning hook: "fast_slots" (register-resident candidate slots per lane, 0 = auto). */
-int mouse_set_tuning(const char *key, int value);
 /* Debug: the 8 int64 workspace counters (0 zero-length, 1 guard-band redos, 4-7 phase cycle timers when built
  * with -DMOUSE_PHASE_TIMERS); synchronises `stream`. */
 int mouse_debug_counters(const mouse_grid_t *grid, int64_t n_items, const void *ws, int64_t *out8 /*HOST*/, void *stream);

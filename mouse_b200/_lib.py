@@ -17,6 +17,17 @@ MOUSE_SAME_MOLECULE = 1
 MOUSE_FORCE_EXACT = 2
 MOUSE_NO_CUTOFF = 4
 MOUSE_INCLUDE_SELF = 8
+MOUSE_FORCE_FAST = 16
+
+
+def MOUSE_SLOTS(n: int) -> int:
+    """Tuning field of ``flags``: register-resident candidate slots per lane of the fast P2 sweep (0 = automatic)."""
+    return (int(n) & 0xff) << 8
+
+
+def MOUSE_WARPS(n: int) -> int:
+    """Tuning field of ``flags``: resident sweep warps per SM (0 = as many as fit)."""
+    return (int(n) & 0xff) << 16
 
 
 class Grid(C.Structure):
@@ -33,7 +44,7 @@ class P2Totals(C.Structure):
 
 
 EXPORTS = [
-    "mouse_version", "mouse_last_error", "mouse_set_tuning", "mouse_grid_plan", "mouse_bond_build",
+    "mouse_version", "mouse_last_error", "mouse_grid_plan", "mouse_bond_build",
     "mouse_workspace_bytes", "mouse_cell_build", "mouse_p2_sweep", "mouse_p2_pair_lists", "mouse_p2_reduce",
     "mouse_p2_frame", "mouse_p2_frame_timed", "mouse_rdf_frame", "mouse_single_ref_workspace_bytes", "mouse_p2_single_ref",
     "mouse_rdf_single_ref", "mouse_director_p2", "mouse_debug_counters", "mouse_parse_doubles",
@@ -64,15 +75,14 @@ def lib():
     gp = C.POINTER(Grid)
     L.mouse_version.restype = C.c_char_p
     L.mouse_last_error.restype = C.c_char_p
-    L.mouse_set_tuning.argtypes = [C.c_char_p, C.c_int]
     L.mouse_grid_plan.argtypes = [C.POINTER(C.c_double), dbl, dbl, i64, gp]
     L.mouse_bond_build.argtypes = [vp, vp, i64, C.POINTER(C.c_double), vp, vp, vp]
     L.mouse_workspace_bytes.argtypes = [i64, gp]
     L.mouse_workspace_bytes.restype = C.c_size_t
     L.mouse_cell_build.argtypes = [vp, vp, vp, vp, vp, i64, gp, vp, C.c_size_t, vp]
-    L.mouse_p2_sweep.argtypes = [vp, vp, i64, gp, u32, vp, vp, vp, vp]
-    L.mouse_p2_pair_lists.argtypes = [vp, vp, i64, gp, u32, vp, vp, vp, vp, i64, vp]
-    L.mouse_p2_reduce.argtypes = [vp, vp, i64, gp, vp, vp, vp, vp, dbl, dbl, i32, vp]
+    L.mouse_p2_sweep.argtypes = [vp, vp, i64, gp, u32, vp, C.c_size_t, vp, vp, vp]
+    L.mouse_p2_pair_lists.argtypes = [vp, vp, i64, gp, u32, vp, C.c_size_t, vp, vp, vp, i64, vp]
+    L.mouse_p2_reduce.argtypes = [vp, vp, i64, gp, vp, C.c_size_t, vp, vp, vp, dbl, dbl, i32, vp]
     L.mouse_p2_frame.argtypes = [vp, vp, vp, vp, vp, i64, gp, u32, vp, C.c_size_t, vp, vp, vp, vp, vp, vp, vp]
     L.mouse_p2_frame_timed.argtypes = [vp, vp, vp, vp, vp, i64, gp, u32, vp, C.c_size_t, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.mouse_rdf_frame.argtypes = [vp, vp, vp, i64, i32, gp, u32, C.POINTER(C.c_double), i32, vp, C.c_size_t, vp, vp]

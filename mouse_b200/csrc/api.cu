@@ -18,7 +18,7 @@ int mouse_launch_frame_build(const double *pos, const int32_t *bond_atoms, const
                              int init_listed, cudaStream_t st);
 int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const mouse_grid_t *grid, uint32_t flags,
                           const Workspace &w, double *out_sum, int32_t *out_cnt, const int64_t *row_ptr,
-                          int32_t *nbr_idx, int frame_mode, int *used_fast, cudaStream_t st);
+                          int32_t *nbr_idx, int64_t list_cap, int frame_mode, int *used_fast, cudaStream_t st);
 int mouse_launch_p2_finish_reduce(int64_t n, const mouse_grid_t *grid, const Workspace &w, double *out_sum,
                                   int32_t *out_cnt, double *out_mean, mouse_p2_totals_t *totals, cudaStream_t st);
 int mouse_launch_row_ptr(const int32_t *cnt, int64_t n, int64_t *row_ptr, cudaStream_t st);
@@ -29,9 +29,7 @@ int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, 
                            int32_t nbin, const Workspace &w, int64_t *hist, cudaStream_t st);
 int mouse_launch_director_p2(const double *vec, const uint8_t *mask, int64_t n, const double *director, double *out_s,
                              int64_t *hist, double smin, double smax, int32_t nbins, cudaStream_t st);
-extern int mouse_fast_slots_override;
-extern int mouse_fast_warps_override;
-extern int mouse_fast_variant;
+int mouse_p2_uses_fast(const mouse_grid_t *grid, int64_t n, uint32_t flags, bool lists);
 
 static thread_local char g_err[512] = "";
 
@@ -46,17 +44,6 @@ extern "C" {
 
 const char *mouse_version(void) { return "mouse_b200 0.1 (sm_100a)"; }
 const char *mouse_last_error(void) { return g_err; }
-
-int mouse_set_tuning(const char *key, int value) {
-  if (!strcmp(key, "fast_slots")) mouse_fast_slots_override = value;
-  else if (!strcmp(key, "fast_variant")) mouse_fast_variant = value;
-  else if (!strcmp(key, "fast_warps")) mouse_fast_warps_override = value;
-  else {
-    mouse_set_error("unknown tuning key %s", key);
-    return MOUSE_EINVAL;
-  }
-  return MOUSE_OK;
-}
 
 int mouse_grid_plan(const double *box, double rcut, double rc2, int64_t n_items, mouse_grid_t *grid) {
   if (!box || !grid) {
@@ -176,40 +163,45 @@ int mouse_cell_build(const double *vec, const double *ctr, const int32_t *mol, c
 }
 
 int mouse_p2_sweep(const double *vec, const double *ctr, int64_t n_bonds, const mouse_grid_t *grid, uint32_t flags,
-                   const void *ws, double *out_sum, int32_t *out_cnt, void *stream) {
-  if (!grid || !ws || !out_sum || !out_cnt) {
+                   void *ws, size_t ws_bytes, double *out_sum, int32_t *out_cnt, void *stream) {
+  if (!out_sum || !out_cnt) {
     mouse_set_error("mouse_p2_sweep: NULL argument");
     return MOUSE_EINVAL;
   }
-  Workspace w = mouse_carve((void *)ws, n_bonds, grid->ncell);
-  return mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, out_sum, out_cnt, nullptr, nullptr, 0, nullptr,
+  Workspace w;
+  int rc = check_ws("mouse_p2_sweep", n_bonds, grid, ws, ws_bytes, &w);
+  if (rc) return rc;
+  return mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, out_sum, out_cnt, nullptr, nullptr, 0, 0, nullptr,
                                (cudaStream_t)stream);
 }
 
 int mouse_p2_pair_lists(const double *vec, const double *ctr, int64_t n_bonds, const mouse_grid_t *grid,
-                        uint32_t flags, const void *ws, const int32_t *cnt, int64_t *row_ptr, int32_t *nbr_idx,
-                        int64_t capacity, void *stream) {
-  if (!grid || !ws || !cnt || !row_ptr || !nbr_idx) {
-    mouse_set_error("mouse_p2_pair_lists: NULL argument");
+                        uint32_t flags, void *ws, size_t ws_bytes, const int32_t *cnt, int64_t *row_ptr,
+                        int32_t *nbr_idx, int64_t capacity, void *stream) {
+  if (!cnt || !row_ptr || !nbr_idx || capacity < 0) {
+    mouse_set_error("mouse_p2_pair_lists: NULL argument / negative capacity");
     return MOUSE_EINVAL;
   }
-  (void)capacity;  // the caller sizes nbr_idx from sum(cnt); rows are written strictly inside row_ptr
-  Workspace w = mouse_carve((void *)ws, n_bonds, grid->ncell);
-  int rc = mouse_launch_row_ptr(cnt, n_bonds, row_ptr, (cudaStream_t)stream);
+  Workspace w;
+  int rc = check_ws("mouse_p2_pair_lists", n_bonds, grid, ws, ws_bytes, &w);
   if (rc) return rc;
-  // rank_of is free after the cell build: scratch "entries written so far" per row
-  return mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, nullptr, w.rank_of, row_ptr, nbr_idx, 0, nullptr,
-                               (cudaStream_t)stream);
+  if ((rc = mouse_launch_row_ptr(cnt, n_bonds, row_ptr, (cudaStream_t)stream))) return rc;
+  // rank_of is free after the cell build: scratch "entries written so far" per row.  Entries at or beyond
+  // `capacity` are not written (the kernel checks every store against it)
+  return mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, nullptr, w.rank_of, row_ptr, nbr_idx, capacity, 0,
+                               nullptr, (cudaStream_t)stream);
 }
 
-int mouse_p2_reduce(const double *sum, const int32_t *cnt, int64_t n_bonds, const mouse_grid_t *grid,
-                       const void *ws, double *out_mean, mouse_p2_totals_t *totals, int64_t *hist, double smin,
-                       double smax, int32_t nbins, void *stream) {
-  if (!sum || !cnt || !ws || !out_mean || !totals || !grid) {
+int mouse_p2_reduce(const double *sum, const int32_t *cnt, int64_t n_bonds, const mouse_grid_t *grid, void *ws,
+                    size_t ws_bytes, double *out_mean, mouse_p2_totals_t *totals, int64_t *hist, double smin,
+                    double smax, int32_t nbins, void *stream) {
+  if (!sum || !cnt || !out_mean || !totals) {
     mouse_set_error("mouse_p2_reduce: NULL argument");
     return MOUSE_EINVAL;
   }
-  Workspace w = mouse_carve((void *)ws, n_bonds, grid->ncell);
+  Workspace w;
+  int rc = check_ws("mouse_p2_reduce", n_bonds, grid, ws, ws_bytes, &w);
+  if (rc) return rc;
   return mouse_launch_p2_reduce(sum, cnt, n_bonds, w, out_mean, totals, hist, smin, smax, nbins,
                                 (cudaStream_t)stream);
 }
@@ -230,13 +222,13 @@ int mouse_p2_frame_timed(const double *pos, const int32_t *bond_atoms, const int
   }
   // K1 + K2 fused (bond vectors, cell list, outputs initialised) -> K3 -> K4 fused with the accumulator conversion
   // (the fast sweep's K4 writes every listed bond itself; the all-FP64 path needs all outputs initialised)
-  const int fast_path = grid->fast && !(flags & (MOUSE_FORCE_EXACT | MOUSE_NO_CUTOFF));
+  const int fast_path = mouse_p2_uses_fast(grid, n_bonds, flags, false);
   if ((rc = mouse_launch_frame_build(pos, bond_atoms, mol, nbr_mask, ref_mask, n_bonds, grid, w, vec, ctr, sum, cnt,
                                      mean, !fast_path, st)))
     return rc;
   int used_fast = 0;
   if (ev_sweep_begin) MOUSE_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev_sweep_begin, st));
-  if ((rc = mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, sum, cnt, nullptr, nullptr, 1, &used_fast, st)))
+  if ((rc = mouse_launch_p2_sweep(vec, ctr, n_bonds, grid, flags, w, sum, cnt, nullptr, nullptr, 0, 1, &used_fast, st)))
     return rc;
   if (ev_sweep_end) MOUSE_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev_sweep_end, st));
   if (used_fast) return mouse_launch_p2_finish_reduce(n_bonds, grid, w, sum, cnt, mean, totals, st);

@@ -332,7 +332,8 @@ __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, int n, GridD
           const int y = __shfl_up_sync(MOUSE_FULL_MASK, incl, o);
           if (lane >= o) incl += y;
         }
-        // row layout: [0..9] src, [10..19] len, [20..29] offset, [30] size, [31] packed coordinates + boundary bit
+        // row layout: [0..9] src, [10..19] len, [20..29] offset, [30] size, [31] packed coordinates + boundary bit,
+        // [32..37] bounding box of the cell's items (written below)
         const int src_k = __shfl_sync(MOUSE_FULL_MASK, src, lane % 10);
         const int len_k = __shfl_sync(MOUSE_FULL_MASK, len, lane % 10);
         const int off_k = __shfl_sync(MOUSE_FULL_MASK, incl - len, lane % 10);
@@ -342,8 +343,10 @@ __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, int n, GridD
                                                                    : (cx | (cy << 10) | (cz << 20) | (boundary << 30));
       }
       items[(size_t)c * HS_ITEM_INTS + lane] = val;
+      if (nc <= 0 && lane < 8) items[(size_t)c * HS_ITEM_INTS + 32 + lane] = 0;
     }
     if (nc <= 0) continue;
+    float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
     for (int m0 = 0; m0 < nc; m0 += 32) {
       const int m = m0 + lane;
       const int raw = m < nc ? idx_tmp[s + m] : 0x7fffffff;
@@ -360,6 +363,8 @@ __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, int n, GridD
       if (m < nc) {
         const int d = s + rank;
         Rec r = rec_tmp[mine];
+        blo[0] = fminf(blo[0], r.p.x), blo[1] = fminf(blo[1], r.p.y), blo[2] = fminf(blo[2], r.p.z);
+        bhi[0] = fmaxf(bhi[0], r.p.x), bhi[1] = fmaxf(bhi[1], r.p.y), bhi[2] = fmaxf(bhi[2], r.p.z);
         // .w carries the sorted slot itself: the sweep's register-resident candidates know where they live
         if (MODE == 0) r.u.w = __hiloint2double(0, d);
         rec_sorted[d] = r;
@@ -368,6 +373,22 @@ __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, int n, GridD
         flag_sorted[d] = (uint8_t)((unsigned)raw >> 31);
         acc_fix[d] = 0;      // the half-shell sweep's accumulators start (and are left) at zero
         acc_cnt[d] = 0;
+      }
+    }
+    if (items) {
+      // bounding box of the cell's items: the P2 sweep drops candidates farther than the cutoff from it
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          blo[ax] = fminf(blo[ax], __shfl_xor_sync(MOUSE_FULL_MASK, blo[ax], o));
+          bhi[ax] = fmaxf(bhi[ax], __shfl_xor_sync(MOUSE_FULL_MASK, bhi[ax], o));
+        }
+      }
+      if (lane < 8) {
+        const float v = lane == 0 ? blo[0] : lane == 1 ? blo[1] : lane == 2 ? blo[2] : lane == 3 ? bhi[0]
+                        : lane == 4 ? bhi[1] : lane == 5 ? bhi[2] : 0.0f;
+        items[(size_t)c * HS_ITEM_INTS + 32 + lane] = __float_as_int(v);
       }
     }
   }

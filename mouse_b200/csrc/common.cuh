@@ -47,7 +47,7 @@ struct Workspace {
   int32_t *cell_count;   // [ncell+1]   items per cell (atomic histogram), last entry unused
   int32_t *cell_start;   // [ncell+1]   exclusive scan; cell_start[ncell] = items in the list
   int32_t *scan_blocks;  // [scan_nblocks+1]
-  int32_t *items;        // [ncell][32] item table of the half-shell sweeps (ranges of the 14 cells, see half_shell.cuh)
+  int32_t *items;        // [ncell][40] item table of the half-shell sweeps (ranges of the 14 cells, see half_shell.cuh)
   // per item, original order
   int32_t *cell_of;      // [n] cell id or -1 (not in the list)
   int32_t *rank_of;      // [n] arrival rank inside the cell (atomic order, canonicalised later)
@@ -94,7 +94,7 @@ static inline Workspace mouse_carve(void *ws, int64_t n, int32_t ncell) {
   CARVE(cell_count, int32_t, nc)
   CARVE(cell_start, int32_t, nc)
   CARVE(scan_blocks, int32_t, nsb)
-  CARVE(items, int32_t, 32 * nc)
+  CARVE(items, int32_t, 40 * nc)
   CARVE(cell_of, int32_t, nn)
   CARVE(rank_of, int32_t, nn)
   CARVE(rec_tmp, Rec, nn)

@@ -96,10 +96,12 @@ __device__ __forceinline__ void hs_range_cells(const GridDev &g, int cx, int cy,
   }
 }
 
-// Per-cell item table (32 ints per cell, written by cell_canon_kernel, one warp per cell, read by the sweeps):
+// Per-cell item table (40 ints per cell, written by cell_canon_kernel, one warp per cell, read by the sweeps):
 //   [0..9] first sorted slot of range L, [10..19] its length, [20..29] its offset t in the candidate concatenation,
-//   [30] bonds / atoms in the home cell, [31] cx | cy << 10 | cz << 20 | boundary << 30.
-#define HS_ITEM_INTS 32
+//   [30] bonds / atoms in the home cell, [31] cx | cy << 10 | cz << 20 | boundary << 30,
+//   [32..34] / [35..37] lower / upper corner of the bounding box of the cell's own items (FP32 bit patterns, frame of
+//   the stored coordinates: wrapped - L/2), [38..39] unused.
+#define HS_ITEM_INTS 40
 
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");

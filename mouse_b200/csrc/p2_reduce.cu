@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(RED_THREADS) p2_reduce_kernel(
         if (k < nbins) atomicAdd((unsigned long long *)&hist[k], (unsigned long long)s_hist[k]);
         else atomicAdd((unsigned long long *)&counters[3], (unsigned long long)s_hist[k]);
       }
+    __syncthreads();   // every thread's out-of-range count is in counters[3] before thread 0 takes the ticket
   }
   if (threadIdx.x == 0) {
     double t = 0.0;

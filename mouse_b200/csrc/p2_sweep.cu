@@ -13,13 +13,15 @@
 //    band, dense FP64 cos^2 = (u_i . u_j)^2 for every slot, branch-free accumulation into the
 //    reference's and the candidate's registers (the hit predicate clears the weight).  Candidates
 //    inside the FP32 guard band around rc^2, and sure hits with |u_i . u_j| < 1e-9 (the reference masks
-//    cos^2 == 0, :113), are NOT decided here: they are appended to a pair list and decided with the
-//    reference's exact un-fused FP64 expressions by p2_fixup_kernel.  Sums are merged across home cells
+//    cos^2 == 0, :113), are NOT decided in FP32: they are appended to a pair list and decided with the
+//    reference's exact un-fused FP64 expressions by p2_fixup_kernel.  Before the reference
+//    loop the candidates farther than the cutoff from the bounding box of the home cell's bonds are dropped
+//    (hs_cull): 220 -> 148 candidates per reference on the 1M-bond melt.  Sums are merged across home cells
 //    as 2^-47 fixed point with integer atomics: exact, order independent -> run-to-run bit-identical.
 //  * p2_sweep_exact_kernel - one thread per reference, all FP64, literally the reference's
 //    expression per candidate.  Valid for ANY grid (fewer than 3 cells on an axis, rcut < 0,
-//    rmax == 0 -> half diagonal); it also extracts the pair lists and is the automatic fallback when
-//    the pair list of the fast path overflows.
+//    rmax == 0 -> half diagonal, crowded cells); it also extracts the pair lists and is the automatic
+//    fallback when the pair list of the fast path overflows.
 #include <type_traits>
 
 #include "half_shell.cuh"
@@ -42,13 +44,14 @@ struct SweepArgs {
                            // 3 length of the pair list, 4 pair list overflowed
   const int64_t *row_ptr;  // lists only
   int32_t *nbr_idx;
-  long long *acc_fix;      // [n] per sorted slot: sum of cos^2 as 2^-47 fixed point
-  int32_t *acc_cnt;        // [n] per sorted slot: counted neighbours
+  int64_t list_cap;        // lists only: entries of nbr_idx the caller allocated
   int2 *fix_list;          // pairs of sorted slots left to p2_fixup_kernel: x = i | kind << 31, y = j
   long long fix_cap;
+  int only_if_overflow;    // exact kernel: run only when the pair list overflowed
+  long long *acc_fix;      // [n] per sorted slot: sum of cos^2 as 2^-47 fixed point
+  int32_t *acc_cnt;        // [n] per sorted slot: counted neighbours
   int same_molecule;
   int no_cutoff;
-  int only_if_overflow;    // exact kernel: run only when the pair list overflowed
 };
 
 #define C_NZERO 0
@@ -77,14 +80,17 @@ __device__ __forceinline__ double exact_pair(const int32_t *__restrict__ idx, co
 
 // ------------------------------------------------------------------ half-shell fast sweep
 #ifndef HS_MAXHOME
-#define HS_MAXHOME 96      // home cells with more bonds are decided pair by pair by p2_fixup_kernel
+#define HS_MAXHOME 64      // home cells with more bonds are decided pair by pair, exactly (hs_oversize)
 #endif
 #ifndef HS_GRP
 #define HS_GRP 8           // references reduced together (transposed reduction through shared memory)
 #endif
-#define HS_MAXPASS 8       // ... and home cells with more than HS_MAXPASS * SLOTS * 32 candidates
+#ifndef HS_LZ
+#define HS_LZ 256          // landing zone of the TMA copies, in records: one chunk of the candidate concatenation
+#endif
+#define HS_MAXT 16384      // more candidates than this per home cell: exact path (keeps the 2^-47 fixed point in range)
 #ifndef HS_WARPS
-#define HS_WARPS 12        // resident warps (= CTAs) per SM the register allocation is sized for
+#define HS_WARPS 10        // resident warps (= CTAs) per SM the register allocation is sized for
 #endif
 #define HS_FIX_SCALE 140737488355328.0     // 2^47
 #define HS_FIX_INV 7.105427357601002e-15   // 2^-47
@@ -92,6 +98,8 @@ __device__ __forceinline__ double exact_pair(const int32_t *__restrict__ idx, co
 #define HS_NEARZ_HI 0x3e112e0b             // high word of 1e-9
 #define HS_PAD 1.0e18f                     // coordinate of an empty slot
 
+// Pairs the sweep does not decide in FP32 are appended to a global pair list and decided by p2_fixup_kernel
+// (no function call and no extra state inside the sweep: its register budget is spent on the candidates).
 __device__ __forceinline__ void fix_append(int64_t *counters, int2 *fix_list, long long fix_cap, int si, int sj,
                                            int kind) {
   const unsigned long long pos = atomicAdd((unsigned long long *)&counters[C_NFIX], 1ULL);
@@ -99,7 +107,7 @@ __device__ __forceinline__ void fix_append(int64_t *counters, int2 *fix_list, lo
   else counters[C_OVERFLOW] = 1;   // the exact sweep recomputes the whole frame
 }
 
-// every pair of an oversized home cell goes to the pair list
+// every pair of an oversized home cell (more bonds than the landing zone holds) goes to the pair list
 __device__ __noinline__ void hs_oversize(const Rec *__restrict__ R, int64_t *counters, int2 *fix_list,
                                          long long fix_cap, int same_molecule, int lane, int hs, int nhome, int rsrc,
                                          int rlen, int rt0) {
@@ -107,6 +115,7 @@ __device__ __noinline__ void hs_oversize(const Rec *__restrict__ R, int64_t *cou
     const int src = __shfl_sync(MOUSE_FULL_MASK, rsrc, r), len = __shfl_sync(MOUSE_FULL_MASK, rlen, r);
     const int rt = __shfl_sync(MOUSE_FULL_MASK, rt0, r);
     for (int k = lane; k < len; k += 32) {
+      if (((volatile int64_t *)counters)[C_OVERFLOW]) return;     // the frame is being redone exactly anyway
       const int sj = src + k, tj = rt + k;
       const int molj = __float_as_int(R[sj].p.w);
       for (int il = 0; il < nhome; ++il) {
@@ -116,23 +125,6 @@ __device__ __noinline__ void hs_oversize(const Rec *__restrict__ R, int64_t *cou
       }
     }
   }
-}
-
-// all-ones when x < y (FSET: one instruction, no predicate register)
-__device__ __forceinline__ int mask_lt(float x, float y) {
-  int m;
-  asm("set.lt.s32.f32 %0, %1, %2;" : "=r"(m) : "f"(x), "f"(y));
-  return m;
-}
-__device__ __forceinline__ int mask_gt(int x, int y) {
-  int m;
-  asm("set.gt.s32.s32 %0, %1, %2;" : "=r"(m) : "r"(x), "r"(y));
-  return m;
-}
-__device__ __forceinline__ int mask_ne(int x, int y) {
-  int m;
-  asm("set.ne.s32.s32 %0, %1, %2;" : "=r"(m) : "r"(x), "r"(y));
-  return m;
 }
 
 // @(cnt > 0): acc_fix[g] += round(acc * 2^47); acc_cnt[g] += cnt   (no return value: RED)
@@ -151,7 +143,7 @@ struct HsConst {
 // The references of one home cell against NPP register-resident slot pairs (specialised on NPP: no guards inside the
 // reference loop, the slot pairs interleave freely).
 template <int SLOTS, int NPP, bool EXCL_MOL>
-__device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k, const int lane, const int pass,
+__device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k, const int lane, const bool pass0,
                                             const int hs, const int nhome, const float2 (&xr2)[SLOTS / 2],
                                             const float2 (&yr2)[SLOTS / 2], const float2 (&zr2)[SLOTS / 2],
                                             const double (&ux)[SLOTS], const double (&uy)[SLOTS],
@@ -182,7 +174,7 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
       const float2 nax = make_float2(-pa.x, -pa.x), nay = make_float2(-pa.y, -pa.y), naz = make_float2(-pa.z, -pa.z);
       const float2 nbx = make_float2(-pb.x, -pb.x), nby = make_float2(-pb.y, -pb.y), nbz = make_float2(-pb.z, -pb.z);
       // home-home pairs are decided once: candidate t > il (pass 0: slot c < HSL holds t = 32 c + lane)
-      const int ea = pass == 0 ? il : -1, eb = pass == 0 ? il + 1 : -1;
+      const int ea = pass0 ? il : -1, eb = pass0 ? il + 1 : -1;
       double acca0 = 0.0, acca1 = 0.0, accb0 = 0.0, accb1 = 0.0;
       int cnta = 0, cntb = 0;
       float banda = 3.0e38f, nza = 3.0e38f, bandb = 3.0e38f, nzb = 3.0e38f;
@@ -190,8 +182,13 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
       for (int pp = 0; pp < NPP; ++pp) {
         const float2 dxa = __fadd2_rn(xr2[pp], nax), dya = __fadd2_rn(yr2[pp], nay), dza = __fadd2_rn(zr2[pp], naz);
         const float2 dxb = __fadd2_rn(xr2[pp], nbx), dyb = __fadd2_rn(yr2[pp], nby), dzb = __fadd2_rn(zr2[pp], nbz);
+#ifdef HS_FOLD_RC
+        const float2 ta = __ffma2_rn(dza, dza, __ffma2_rn(dya, dya, __ffma2_rn(dxa, dxa, nrc)));   // d2 - rc2
+        const float2 tb = __ffma2_rn(dzb, dzb, __ffma2_rn(dyb, dyb, __ffma2_rn(dxb, dxb, nrc)));
+#else
         const float2 ta = __fadd2_rn(__ffma2_rn(dza, dza, __ffma2_rn(dya, dya, __fmul2_rn(dxa, dxa))), nrc);   // d2 - rc2
         const float2 tb = __fadd2_rn(__ffma2_rn(dzb, dzb, __ffma2_rn(dyb, dyb, __fmul2_rn(dxb, dxb))), nrc);
+#endif
         banda = fminf(banda, fminf(fabsf(ta.x), fabsf(ta.y)));
         bandb = fminf(bandb, fminf(fabsf(tb.x), fabsf(tb.y)));
         const double da0 = fma(uax, ux[2 * pp], fma(uay, uy[2 * pp], uaz * uz[2 * pp]));
@@ -249,7 +246,7 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
       const float4 pi = s_homeP[il];
       const double uix = s_homeU[0][il], uiy = s_homeU[1][il], uiz = s_homeU[2][il];
       const int moli = __float_as_int(pi.w);
-      const int il_eff = pass == 0 ? il : -1;
+      const int il_eff = pass0 ? il : -1;
 #pragma unroll
       for (int c = 0; c < 2 * NPP; ++c) {
         const int g = s_gid[c][lane];
@@ -261,7 +258,11 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
           const float py = (c & 1) ? yr2[c >> 1].y : yr2[c >> 1].x;
           const float pz = (c & 1) ? zr2[c >> 1].y : zr2[c >> 1].x;
           const float dx = __fadd_rn(px, -pi.x), dy = __fadd_rn(py, -pi.y), dz = __fadd_rn(pz, -pi.z);
+#ifdef HS_FOLD_RC
+          const float t = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, -k.rc2_c)));
+#else
           const float t = __fadd_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))), -k.rc2_c);
+#endif
           if (fabsf(t) <= k.rc2_w) {
             fix_append(a.counters, a.fix_list, a.fix_cap, hs + il, g, 0);          // undecided: nothing was added
           } else if (t < k.negw) {
@@ -295,21 +296,82 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
   }
 }
 
+// explicit shared-memory accesses with a 32-bit address held in a register
+__device__ __forceinline__ float4 lds_float4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_float4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, int v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+
+// Drops the candidates of the landing zone that are farther than the cutoff from the bounding box of the home cell's
+// bonds (no reference of the home cell can reach them): s_sel[0..M) = landing-zone index of the candidates kept, in
+// order; returns M.  bb (shared memory) = home cell centre, box lower corner, box upper corner.  BND: the home cell
+// sits on the periodic boundary; the candidates are first moved to their image nearest to the home cell centre
+// (written back to the landing zone).  Two candidates per lane and trip (two independent chains).
+template <bool BND>
+__device__ __forceinline__ int hs_cull(uint32_t land, uint32_t sel, const float *bb, const GridDev &g, int lane,
+                                       int nland, float thr) {
+  const float blx = bb[3], bly = bb[4], blz = bb[5], bhx = bb[6], bhy = bb[7], bhz = bb[8];
+  const unsigned lt = (1u << lane) - 1u;
+  int M = 0;
+  uint32_t pa = land + 48u * (uint32_t)lane;
+  for (int t0 = 0; t0 < nland; t0 += 64, pa += 64u * 48u) {
+    float4 p = lds_float4(pa), q = lds_float4(pa + 32u * 48u);
+    if (BND) {
+      const float hx = bb[0], hy = bb[1], hz = bb[2];
+      p.x -= g.boxf[0] * rintf((p.x - hx) * g.inv_boxf[0]);
+      p.y -= g.boxf[1] * rintf((p.y - hy) * g.inv_boxf[1]);
+      p.z -= g.boxf[2] * rintf((p.z - hz) * g.inv_boxf[2]);
+      q.x -= g.boxf[0] * rintf((q.x - hx) * g.inv_boxf[0]);
+      q.y -= g.boxf[1] * rintf((q.y - hy) * g.inv_boxf[1]);
+      q.z -= g.boxf[2] * rintf((q.z - hz) * g.inv_boxf[2]);
+      sts_float4(pa, p);
+      sts_float4(pa + 32u * 48u, q);
+    }
+    const float ex = fmaxf(fmaxf(__fadd_rn(blx, -p.x), __fadd_rn(p.x, -bhx)), 0.0f);
+    const float ey = fmaxf(fmaxf(__fadd_rn(bly, -p.y), __fadd_rn(p.y, -bhy)), 0.0f);
+    const float ez = fmaxf(fmaxf(__fadd_rn(blz, -p.z), __fadd_rn(p.z, -bhz)), 0.0f);
+    const float fx = fmaxf(fmaxf(__fadd_rn(blx, -q.x), __fadd_rn(q.x, -bhx)), 0.0f);
+    const float fy = fmaxf(fmaxf(__fadd_rn(bly, -q.y), __fadd_rn(q.y, -bhy)), 0.0f);
+    const float fz = fmaxf(fmaxf(__fadd_rn(blz, -q.z), __fadd_rn(q.z, -bhz)), 0.0f);
+    const float d2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
+    const float e2 = __fmaf_rn(fz, fz, __fmaf_rn(fy, fy, __fmul_rn(fx, fx)));
+    const int ta = t0 + lane, tb = ta + 32;
+    const bool ka = (ta < nland) & (d2 <= thr), kb = (tb < nland) & (e2 <= thr);
+    const unsigned ba = __ballot_sync(MOUSE_FULL_MASK, ka), bq = __ballot_sync(MOUSE_FULL_MASK, kb);
+    const int na = __popc(ba);
+    if (ka) sts_u16(sel + 2u * (uint32_t)(M + __popc(ba & lt)), ta);
+    if (kb) sts_u16(sel + 2u * (uint32_t)(M + na + __popc(bq & lt)), tb);
+    M += na + __popc(bq);
+  }
+  __syncwarp();
+  return M;
+}
+
 template <int SLOTS, bool EXCL_MOL>
 __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const SweepArgs a) {
-  constexpr int NC = SLOTS * 32;   // candidates per pass
+  constexpr int NC = SLOTS * 32;   // register-resident candidates per sub-pass
   constexpr int NPAIR = SLOTS / 2;
   constexpr int HSL = HS_MAXHOME / 32;
-  static_assert(SLOTS % 2 == 0 && NC >= HS_MAXHOME && NPAIR <= 6, "slots come in pairs; the home cell lives in pass 0");
-  __shared__ __align__(128) Rec s_land[NC];         // TMA landing zone
+  constexpr int LZ = HS_LZ;
+  static_assert(SLOTS % 2 == 0 && NC >= HS_MAXHOME && LZ >= HS_MAXHOME && LZ % 64 == 0 && NPAIR <= 6,
+                "slots come in pairs; the home cell lives in the first sub-pass of the first chunk");
+  __shared__ __align__(128) Rec s_land[LZ];         // TMA landing zone (one chunk of the candidate concatenation)
+  __shared__ uint16_t s_sel[LZ];                    // landing-zone index of the candidates that survived the cull
   __shared__ float4 s_homeP[HS_MAXHOME];            // the home cell's bonds: the references of this item
   __shared__ double s_homeU[3][HS_MAXHOME];
-  __shared__ double s_acc[HS_GRP][33];                   // per-lane partial sums of 8 references (transposed reduce)
-  __shared__ int s_cnt[HS_GRP][33];                      // ... and partial counts
+  __shared__ double s_acc[HS_GRP][33];              // per-lane partial sums of 8 references (transposed reduce)
+  __shared__ int s_cnt[HS_GRP][33];                 // ... and partial counts
   __shared__ int s_gid[SLOTS][32];                  // sorted slot of every register-resident candidate (-1: empty)
-  __shared__ __align__(16) int s_raw[HS_ITEM_INTS];                      // range table in flight (fetch stage 2 -> 3)
+  __shared__ __align__(16) int s_raw[HS_ITEM_INTS]; // item row in flight (fetch stage 2 -> 3)
   __shared__ int s_next[3][32];                     // range table of the prefetched item (kept out of the registers)
-  __shared__ float s_nextf[4];
+  __shared__ float s_bb[9];                         // home cell centre + bounding box of the prefetched / current item
   __shared__ int s_nexti[6];
   __shared__ __align__(8) uint64_t s_bar;
   const int lane = threadIdx.x;
@@ -318,20 +380,22 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
   k.rc2_w = 0.5f * (a.g.rc2_hi - a.g.rc2_lo) * 1.0001f;
   k.negw = -k.rc2_w;
   k.nearz_thr = __int_as_float(HS_NEARZ_HI);
+  const float cull_thr = a.g.rc2_hi * 1.001f;             // box distance test: well outside the guard band
 
   if (lane == 0) {
     mbar_init(&s_bar, 1);
     fence_mbar_init();
   }
+#pragma unroll
+  for (int q = 0; q < LZ / 32; ++q) s_sel[32 * q + lane] = 0;
   __syncwarp();
   uint32_t phase = 0;
 
-  // arm the landing zone with pass `pass` of item `it`: candidates [pass * NC, min(T, pass * NC + NC))
-  auto issue = [&](const HsItem &it, int pass) {
-    const int w0 = pass * NC, w1 = min(it.T, w0 + NC);
-    // WAR on the landing zone: every lane's shared-memory reads of the previous contents were issued before the
-    // __syncwarp() that precedes this call; the proxy fence orders them against the async-proxy writes (measured
-    // cost: none)
+  // arm the landing zone with chunk `ch` of item `it`: candidates [ch * LZ, min(T, ch * LZ + LZ))
+  auto issue = [&](const HsItem &it, int ch) {
+    const int w0 = ch * LZ, w1 = min(it.T, w0 + LZ);
+    // WAR on the landing zone: every lane's shared-memory accesses to the previous contents were issued before the
+    // __syncwarp() that precedes this call; the proxy fence orders them against the async-proxy writes
     fence_proxy_async();
     if (lane == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)(w1 - w0) * 48u);
     __syncwarp();
@@ -344,8 +408,8 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
 
   // Three-stage fetch pipeline, one stage per loop iteration so that no global latency is exposed:
   //   stage 1  ticket  = atomicAdd(home-cell counter)           (tkP: issued one iteration before it is used)
-  //   stage 2  range table of the ticket's home cell -> s_raw   (tkA: cp.async issued one iteration before stage 3)
-  //   stage 3  finalize the table, arm the landing zone (TMA)   (one iteration before the data is consumed)
+  //   stage 2  item row of the ticket's home cell -> s_raw      (tkA: cp.async issued one iteration before stage 3)
+  //   stage 3  finalize the row, arm the landing zone (TMA)     (one iteration before the data is consumed)
   int tkA, tkP = 0;
   {
     int t0 = 0;
@@ -356,97 +420,110 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     tkA = __shfl_sync(MOUSE_FULL_MASK, t0, 0);
     if (tkA < a.g.ncell) hs_raw_issue(a.items, lane, tkA, s_raw);
   }
-  // next non-empty, regular home cell; false when the grid is exhausted
+  // next non-empty, regular home cell (its centre and bounding box go to s_bb); false when the grid is exhausted
   auto advance = [&](HsItem &it) -> bool {
     for (;;) {
       if (tkA >= a.g.ncell) return false;
       const bool nonempty = hs_finalize(a.g, lane, tkA, s_raw, it);
+      const float bbv = lane < 6 ? __int_as_float(s_raw[32 + lane]) : 0.0f;
+      __syncwarp();
       tkA = __shfl_sync(MOUSE_FULL_MASK, tkP, 0);
       if (lane == 0) tkP = (int)atomicAdd((unsigned int *)&a.counters[C_TICKET], 1u);
       if (tkA < a.g.ncell) hs_raw_issue(a.items, lane, tkA, s_raw);
       if (!nonempty) continue;
-      if (it.nhome > HS_MAXHOME || it.T > HS_MAXPASS * NC) {
+      if (it.nhome > LZ || it.T > HS_MAXT) {
         hs_oversize(a.R, a.counters, a.fix_list, a.fix_cap, a.same_molecule, lane, it.hs, it.nhome, it.rsrc, it.rlen, it.rt);
         continue;
+      }
+      if (lane < 6) s_bb[3 + lane] = bbv;
+      if (lane == 0) {
+        s_bb[0] = it.hx;
+        s_bb[1] = it.hy;
+        s_bb[2] = it.hz;
       }
       return true;
     }
   };
 
+  // A home cell with more than HS_MAXHOME bonds is taken in windows of HS_MAXHOME references [rb, rb + HS_MAXHOME):
+  // each window is a pass over the whole candidate concatenation of its own, in which the survivors in front of the
+  // window (home-cell bonds j < rb <= i: those pairs belong to the earlier windows) are skipped.
   HsItem cur;
-  if (!advance(cur)) return;
-  int pass = 0;
-  issue(cur, pass);
+  bool have = advance(cur);
+  int ch = 0, sp = 0, M = 0, rb = 0;
+  bool fresh = true;
+  if (have) issue(cur, 0);
 
-  for (;;) {
-    // ---- landing zone -> registers
-    const int w0 = pass * NC;
-    const int nvalid = min(cur.T, w0 + NC) - w0;
+  while (have) {
+    if (fresh) {
+      // ---- a new chunk has landed: drop the candidates no reference of the home cell can reach
+      const int nland = min(cur.T - ch * LZ, LZ);
+      mbar_wait(&s_bar, phase);
+      phase ^= 1u;
+      M = cur.boundary ? hs_cull<true>(smem_addr(s_land), smem_addr(s_sel), s_bb, a.g, lane, nland, cull_thr)
+                       : hs_cull<false>(smem_addr(s_land), smem_addr(s_sel), s_bb, a.g, lane, nland, cull_thr);
+      sp = 0;
+    }
+    // ---- landing zone -> registers: candidates [k0, k0 + NC) of the survivors (first chunk: behind the window start)
+    const int k0 = sp * NC + (ch == 0 ? rb : 0);
+    const int nvalid = max(min(M - k0, NC), 0);
     const int npp = (nvalid + 63) >> 6;             // slot pairs in use
+    const bool last = k0 + NC >= M;                 // last sub-pass of this chunk
+    const bool pass0 = (ch == 0) & (sp == 0);       // the home cell leads the concatenation and is never dropped
+    const int hs = cur.hs + rb, nhome = min(cur.nhome - rb, HS_MAXHOME);   // this window's references
     float2 xr2[NPAIR], yr2[NPAIR], zr2[NPAIR];
     double ux[SLOTS], uy[SLOTS], uz[SLOTS];
     double accj[SLOTS];
     int cntj[SLOTS], molr[SLOTS];
-    mbar_wait(&s_bar, phase);
-    phase ^= 1u;
-    // (two copies of the loop, boundary / interior: no branch inside, so all the shared-memory loads batch up)
-    auto load_regs = [&](auto bnd_tag) {
-      constexpr bool BND = decltype(bnd_tag)::value;
-      const float Lx = a.g.boxf[0], Ly = a.g.boxf[1], Lz = a.g.boxf[2];
-      const float iLx = a.g.inv_boxf[0], iLy = a.g.inv_boxf[1], iLz = a.g.inv_boxf[2];
 #pragma unroll
-      for (int pp = 0; pp < NPAIR; ++pp) {
-        float q[2][3];
+    for (int pp = 0; pp < NPAIR; ++pp) {
+      float q[2][3];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = 2 * pp + h;
-          const int tl = 32 * c + lane;
-          const bool valid = tl < nvalid;
-          const float4 p = s_land[tl].p;
-          const double4 u = s_land[tl].u;
-          float px = p.x, py = p.y, pz = p.z;
-          if (BND) {     // nearest periodic image to the home cell centre
-            px -= Lx * rintf((px - cur.hx) * iLx);
-            py -= Ly * rintf((py - cur.hy) * iLy);
-            pz -= Lz * rintf((pz - cur.hz) * iLz);
-          }
-          q[h][0] = valid ? px : HS_PAD;
-          q[h][1] = valid ? py : HS_PAD;
-          q[h][2] = valid ? pz : HS_PAD;
-          ux[c] = valid ? u.x : 1.0;
-          uy[c] = valid ? u.y : 1.0;
-          uz[c] = valid ? u.z : 1.0;
-          s_gid[c][lane] = valid ? __double2loint(u.w) : -1;
-          molr[c] = __float_as_int(p.w);
-          accj[c] = 0.0;
-          cntj[c] = 0;
-          if (c < HSL && pass == 0 && tl < cur.nhome) {   // the home cell leads the concatenation
-            s_homeP[tl] = make_float4(px, py, pz, p.w);
-            s_homeU[0][tl] = u.x;
-            s_homeU[1][tl] = u.y;
-            s_homeU[2][tl] = u.z;
-          }
+      for (int h = 0; h < 2; ++h) {
+        const int c = 2 * pp + h;
+        const int tl = 32 * c + lane;
+        const bool valid = tl < nvalid;
+        const int t = s_sel[min(k0 + tl, LZ - 1)];
+        const float4 p = s_land[t].p;
+        const double4 u = s_land[t].u;
+        q[h][0] = valid ? p.x : HS_PAD;
+        q[h][1] = valid ? p.y : HS_PAD;
+        q[h][2] = valid ? p.z : HS_PAD;
+        ux[c] = valid ? u.x : 1.0;
+        uy[c] = valid ? u.y : 1.0;
+        uz[c] = valid ? u.z : 1.0;
+        s_gid[c][lane] = valid ? __double2loint(u.w) : -1;
+        molr[c] = __float_as_int(p.w);
+        accj[c] = 0.0;
+        cntj[c] = 0;
+        if (c < HSL && pass0 && tl < nhome) {   // survivors [0, nhome) of the cell are its own bonds, in order
+          s_homeP[tl] = make_float4(p.x, p.y, p.z, p.w);
+          s_homeU[0][tl] = u.x;
+          s_homeU[1][tl] = u.y;
+          s_homeU[2][tl] = u.z;
         }
-        xr2[pp] = make_float2(q[0][0], q[1][0]);
-        yr2[pp] = make_float2(q[0][1], q[1][1]);
-        zr2[pp] = make_float2(q[0][2], q[1][2]);
       }
-    };
-    if (cur.boundary) load_regs(std::true_type{});
-    else load_regs(std::false_type{});
+      xr2[pp] = make_float2(q[0][0], q[1][0]);
+      yr2[pp] = make_float2(q[0][1], q[1][1]);
+      zr2[pp] = make_float2(q[0][2], q[1][2]);
+    }
     __syncwarp();
 
-    // ---- re-arm the landing zone: next pass of this home cell, or pass 0 of the next one
-    int npass = pass + 1;
-    bool have_next = true;
-    {
+    // ---- after the last sub-pass's register load the landing zone is free: re-arm it with the next chunk of
+    // this home cell, or with the first chunk of the next one (the copy then overlaps the arithmetic below)
+    int nch = ch + 1, nrb = rb;
+    if (last) {
       HsItem nxt = cur;
-      if (npass * NC >= cur.T) {
-        npass = 0;
-        have_next = advance(nxt);
+      if (nch * LZ >= cur.T) {
+        nch = 0;
+        nrb = rb + HS_MAXHOME;               // next window of this home cell, or the next home cell
+        if (nrb >= cur.nhome) {
+          nrb = 0;
+          have = advance(nxt);
+        }
       }
-      if (have_next) {
-        issue(nxt, npass);
+      if (have) {
+        issue(nxt, nch);
         s_next[0][lane] = nxt.rsrc;
         s_next[1][lane] = nxt.rlen;
         s_next[2][lane] = nxt.rt;
@@ -456,19 +533,16 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
           s_nexti[2] = nxt.nhome;
           s_nexti[3] = nxt.T;
           s_nexti[4] = nxt.boundary;
-          s_nextf[0] = nxt.hx;
-          s_nextf[1] = nxt.hy;
-          s_nextf[2] = nxt.hz;
         }
       }
     }
-    const int hs = cur.hs, nhome = cur.nhome;
 
     // ---- the references of the home cell against the register-resident candidates
 #define HS_RUN(N)                                                                                                  \
-  hs_ref_loop<SLOTS, (N <= NPAIR ? N : NPAIR), EXCL_MOL>(a, k, lane, pass, hs, nhome, xr2, yr2, zr2, ux, uy, uz, accj, cntj, \
+  hs_ref_loop<SLOTS, (N <= NPAIR ? N : NPAIR), EXCL_MOL>(a, k, lane, pass0, hs, nhome, xr2, yr2, zr2, ux, uy, uz, accj, cntj, \
                                                           molr, s_homeP, s_homeU, s_acc, s_cnt, s_gid)
     switch (npp) {      // npp <= NPAIR: the other cases are not instantiated
+      case 0: break;    // a later chunk without survivors
       case 1: HS_RUN(1); break;
       case 2: if constexpr (NPAIR >= 2) HS_RUN(2); break;
       case 3: if constexpr (NPAIR >= 3) HS_RUN(3); break;
@@ -485,7 +559,13 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
         hs_flush(a.acc_fix, a.acc_cnt, g < 0 ? 0 : g, accj[c], cntj[c]);
       }
     }
-    if (!have_next) break;
+    if (!last) {
+      sp += 1;
+      fresh = false;
+      __syncwarp();
+      continue;
+    }
+    if (!have) break;
     __syncwarp();
     cur.rsrc = s_next[0][lane];
     cur.rlen = s_next[1][lane];
@@ -495,10 +575,9 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     cur.nhome = s_nexti[2];
     cur.T = s_nexti[3];
     cur.boundary = s_nexti[4];
-    cur.hx = s_nextf[0];
-    cur.hy = s_nextf[1];
-    cur.hz = s_nextf[2];
-    pass = npass;
+    ch = nch;
+    rb = nrb;
+    fresh = true;
     __syncwarp();
   }
 }
@@ -598,7 +677,7 @@ __global__ void __launch_bounds__(128) p2_sweep_exact_kernel(const SweepArgs a) 
             const double nj = __dadd_rn(__dadd_rn(__dmul_rn(bjx, bjx), __dmul_rn(bjy, bjy)), __dmul_rn(bjz, bjz));
             const double cs = __ddiv_rn(__ddiv_rn(__dmul_rn(dot, dot), nr), nj);
             if (cs != 0.0) {
-              if (LISTS) a.nbr_idx[row + cnt] = bj;
+              if (LISTS && row + cnt < a.list_cap) a.nbr_idx[row + cnt] = bj;
               sum += cs;
               cnt += 1;
             }
@@ -658,40 +737,56 @@ __global__ void __launch_bounds__(1024) row_ptr_kernel(const int32_t *__restrict
 }
 
 // ------------------------------------------------------------------ launchers
-static int g_num_sms = 0;
-static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+// Immutable per-device facts (SM count, resident sweep CTAs per SM), looked up once per device ordinal.
+struct DevFacts {
+  int sms;
+  int per_sm[8];   // by kernel variant
+};
+static DevFacts g_dev[64];
+
+static DevFacts *dev_facts() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  DevFacts *f = &g_dev[dev];
+  if (f->sms == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    f->sms = n > 0 ? n : 148;
   }
-  return g_num_sms;
+  return f;
 }
 
-int mouse_fast_variant = 1;         // tuning / debug knob (2 = skip the fixup kernel)
-int mouse_fast_slots_override = 0;  // test / tuning hook (set through mouse_set_tuning)
-int mouse_fast_warps_override = 0;  // tuning hook: resident sweep warps per SM (0 = as many as fit)
+int mouse_num_sms() { return dev_facts()->sms; }
 
 template <int SLOTS, bool EXCL>
-static void launch_half_one(const SweepArgs &a, cudaStream_t st) {
-  static int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, p2_sweep_half_kernel<SLOTS, EXCL>, 32, 0);
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
+static void launch_half_one(const SweepArgs &a, int variant, int warps_override, cudaStream_t st) {
+  DevFacts *f = dev_facts();
+  if (f->per_sm[variant] == 0) {
+    int b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, p2_sweep_half_kernel<SLOTS, EXCL>, 32, 0);
+    f->per_sm[variant] = b < 1 ? 1 : b;
   }
   // persistent warps: every resident warp (CTA) pulls home cells from the ticket counter
-  int per_sm = blocks_per_sm;
-  if (mouse_fast_warps_override > 0 && mouse_fast_warps_override < per_sm) per_sm = mouse_fast_warps_override;
-  int blocks = num_sms() * per_sm;
+  int per_sm = f->per_sm[variant];
+  if (warps_override > 0 && warps_override < per_sm) per_sm = warps_override;
+  int blocks = f->sms * per_sm;
   if (blocks > a.g.ncell) blocks = a.g.ncell;
   p2_sweep_half_kernel<SLOTS, EXCL><<<blocks, 32, 0, st>>>(a);
 }
 
 template <int SLOTS>
-static void launch_half(const SweepArgs &a, bool excl_mol, cudaStream_t st) {
-  if (excl_mol) launch_half_one<SLOTS, true>(a, st);
-  else launch_half_one<SLOTS, false>(a, st);
+static void launch_half(const SweepArgs &a, bool excl_mol, int variant, int warps_override, cudaStream_t st) {
+  if (excl_mol) launch_half_one<SLOTS, true>(a, 2 * variant + 1, warps_override, st);
+  else launch_half_one<SLOTS, false>(a, 2 * variant, warps_override, st);
+}
+
+// The FP32-filter half-shell sweep applies when the grid allows it (>= 3 cells per axis, small guard band) and the
+// cells are not crowded: a home cell's own bonds must fit the landing zone (HS_LZ records), so frames with more than
+// HS_LZ / 2 items per cell on average go to the all-FP64 sweep directly instead of deciding most cells pair by pair.
+int mouse_p2_uses_fast(const mouse_grid_t *grid, int64_t n, uint32_t flags, bool lists) {
+  if (!grid->fast || lists || (flags & (MOUSE_FORCE_EXACT | MOUSE_NO_CUTOFF))) return 0;
+  return (flags & MOUSE_FORCE_FAST) || (double)n <= 0.5 * HS_LZ * (double)grid->ncell;
 }
 
 // frame_mode 0: stand-alone sweep (outputs zeroed here, accumulators converted by p2_finish_kernel);
@@ -699,7 +794,7 @@ static void launch_half(const SweepArgs &a, bool excl_mol, cudaStream_t st) {
 // accumulators in the fused finish + reduce kernel.  *used_fast tells the caller which path ran.
 int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const mouse_grid_t *grid, uint32_t flags,
                           const Workspace &w, double *out_sum, int32_t *out_cnt, const int64_t *row_ptr,
-                          int32_t *nbr_idx, int frame_mode, int *used_fast, cudaStream_t st) {
+                          int32_t *nbr_idx, int64_t list_cap, int frame_mode, int *used_fast, cudaStream_t st) {
   SweepArgs a;
   a.g = mouse_grid_dev(grid);
   a.R = w.rec_sorted;
@@ -718,13 +813,14 @@ int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const
   a.nbr_idx = nbr_idx;
   a.acc_fix = w.acc_fix;
   a.acc_cnt = w.acc_cnt;
-  a.fix_list = (int2 *)w.rec_tmp;    // the original-order payload is dead once the cell list is built
-  a.fix_cap = 6LL * (n > 0 ? n : 1);
   a.same_molecule = (flags & MOUSE_SAME_MOLECULE) ? 1 : 0;
   a.no_cutoff = (flags & MOUSE_NO_CUTOFF) ? 1 : 0;
+  a.list_cap = list_cap;
+  a.fix_list = (int2 *)w.rec_tmp;    // the original-order payload is dead once the cell list is built
+  a.fix_cap = 6LL * (n > 0 ? n : 1);
   a.only_if_overflow = 0;
   const bool lists = nbr_idx != nullptr;
-  const bool fast = grid->fast && !lists && !(flags & (MOUSE_FORCE_EXACT | MOUSE_NO_CUTOFF));
+  const bool fast = mouse_p2_uses_fast(grid, n, flags, lists) != 0;
   if (used_fast) *used_fast = fast ? 1 : 0;
   if (n == 0) return MOUSE_OK;
   if (!frame_mode) {
@@ -738,34 +834,33 @@ int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const
       MOUSE_CUDA_CHECK(cudaMemsetAsync(w.acc_cnt, 0, sizeof(int32_t) * (size_t)n, st));
     }
   }
-  int blocks = (int)((n + 127) / 128);
-  int maxb = num_sms() * 32;
-  if (blocks > maxb) blocks = maxb;
+  const int sms = mouse_num_sms();
   if (fast) {
-    // SLOTS * 32 register-resident candidates per pass, sized from the mean of the 14 half-shell cells
+    // SLOTS * 32 register-resident candidates per sub-pass, sized from the mean of the 14 half-shell cells (about a
+    // third of them is dropped by the bounding-box cull)
     double mean = 14.0 * (double)n / (double)grid->ncell;
-    int slots = mean <= 110.0 ? 4 : 6;
-    if (mouse_fast_slots_override) slots = mouse_fast_slots_override;
+    int slots = mean <= 150.0 ? 4 : 6;
+    const int slots_override = (int)((flags >> 8) & 0xffu), warps_override = (int)((flags >> 16) & 0xffu);
+    if (slots_override) slots = slots_override;
     const bool excl = !a.same_molecule;
     switch (slots) {
-      case 4: launch_half<4>(a, excl, st); break;
-      case 6: launch_half<6>(a, excl, st); break;
-      case 8: launch_half<8>(a, excl, st); break;
-      default: launch_half<12>(a, excl, st); break;
+      case 4: launch_half<4>(a, excl, 0, warps_override, st); break;
+      case 6: launch_half<6>(a, excl, 1, warps_override, st); break;
+      default: launch_half<8>(a, excl, 2, warps_override, st); break;
     }
     MOUSE_LAUNCH_CHECK("p2_sweep_half_kernel");
-    if (mouse_fast_variant != 2) {   // variant 2 (debug): leave the undecided pairs out
-      p2_fixup_kernel<<<num_sms(), 256, 0, st>>>(a);
-      MOUSE_LAUNCH_CHECK("p2_fixup_kernel");
-    }
+    p2_fixup_kernel<<<sms, 256, 0, st>>>(a);
+    MOUSE_LAUNCH_CHECK("p2_fixup_kernel");
     if (!frame_mode) {
-      p2_finish_kernel<<<num_sms() * 8, 256, 0, st>>>(a);
+      p2_finish_kernel<<<sms * 8, 256, 0, st>>>(a);
       MOUSE_LAUNCH_CHECK("p2_finish_kernel");
     }
     a.only_if_overflow = 1;          // pair list overflow (pathological inputs): redo the frame exactly
-    p2_sweep_exact_kernel<false><<<num_sms() * 4, 128, 0, st>>>(a);
+    p2_sweep_exact_kernel<false><<<sms * 4, 128, 0, st>>>(a);
     MOUSE_LAUNCH_CHECK("p2_sweep_exact_kernel");
   } else {
+    int blocks = (int)((n + 127) / 128);
+    if (blocks > sms * 32) blocks = sms * 32;
     if (lists)
       p2_sweep_exact_kernel<true><<<blocks, 128, 0, st>>>(a);
     else

@@ -27,10 +27,13 @@ def require_cuda():
 
 
 _ws_cache: dict = {}
+_ws_generation: dict = {}
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
-    """256-byte aligned scratch buffer, grown on demand and reused per device."""
+    """256-byte aligned scratch buffer, grown on demand and reused per device.  Every hand-out bumps the
+    device's generation counter: a result that still needs the cell list it was computed on (``p2_pair_lists``)
+    remembers the generation and refuses to run once another call has reused the buffer."""
     device = torch.device(device)
     key = device.index if device.index is not None else torch.cuda.current_device()
     buf = _ws_cache.get(key)
@@ -38,7 +41,14 @@ def workspace(nbytes: int, device) -> torch.Tensor:
         buf = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=device)
         assert buf.data_ptr() % 256 == 0
         _ws_cache[key] = buf
+    _ws_generation[key] = _ws_generation.get(key, 0) + 1
     return buf
+
+
+def workspace_generation(device) -> int:
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    return _ws_generation.get(key, 0)
 
 
 def bind_host_to_gpu(device_index: int) -> bool:
@@ -82,6 +92,8 @@ class P2Result:
     totals: torch.Tensor   # (6,) i64 view of mouse_p2_totals_t
     grid: _lib.Grid
     hist: torch.Tensor | None = None
+    ws: torch.Tensor | None = None   # the workspace holding this frame's cell list ...
+    ws_generation: int = -1          # ... and the shared buffer's generation when it was built (-1: private buffer)
 
     def totals_dict(self):
         t = self.totals.cpu()
@@ -103,10 +115,13 @@ def half_diagonal(box) -> float:
 
 
 def p2_frame(positions, bond_atoms, mol, box, rcut, same_molecule=True, nbr_mask=None, ref_mask=None,
-             exact=False, hist_args=None, device=None, out: P2Result | None = None) -> P2Result:
+             exact=False, hist_args=None, device=None, out: P2Result | None = None, slots=0, warps=0,
+             private_workspace=False, force_fast=False) -> P2Result:
     """K1 -> K4 for one frame.  ``positions`` (N_a,3) f64, ``bond_atoms`` (N_b,2) i32 (atom1 ->
     atom2 direction, 0-based), ``mol`` (N_b,) i32 molecule code of atom1 of each bond,
-    masks (N_b,) uint8/bool or None.  ``rcut < 0`` means no cutoff (reference ``:102-103``)."""
+    masks (N_b,) uint8/bool or None.  ``rcut < 0`` means no cutoff (reference ``:102-103``).
+    ``slots`` / ``warps`` / ``force_fast``: tuning fields of the C-ABI flags (tests); ``private_workspace``: the result owns its
+    workspace (needed when ``p2_pair_lists`` is not called right away)."""
     require_cuda()
     device = torch.device(device or "cuda")
     pos = as_dev(positions, torch.float64, device)
@@ -118,7 +133,11 @@ def p2_frame(positions, bond_atoms, mol, box, rcut, same_molecule=True, nbr_mask
     grid = _lib.grid_plan(box, float(rcut), n)
     L = _lib.lib()
     nbytes = L.mouse_workspace_bytes(n, C.byref(grid))
-    ws = workspace(nbytes, device)
+    if private_workspace:
+        ws, gen = torch.empty(int(nbytes) + 4096, dtype=torch.uint8, device=device), -1
+    else:
+        ws = workspace(nbytes, device)
+        gen = workspace_generation(device)
     if out is None or out.sum.shape[0] != n:
         out = P2Result(vec=torch.empty((3, n), dtype=torch.float64, device=device),
                        ctr=torch.empty((3, n), dtype=torch.float64, device=device),
@@ -126,9 +145,10 @@ def p2_frame(positions, bond_atoms, mol, box, rcut, same_molecule=True, nbr_mask
                        count=torch.empty(n, dtype=torch.int32, device=device),
                        mean=torch.empty(n, dtype=torch.float64, device=device),
                        totals=torch.zeros(6, dtype=torch.int64, device=device), grid=grid)
-    out.grid = grid
+    out.grid, out.ws, out.ws_generation = grid, ws, gen
     flags = (_lib.MOUSE_SAME_MOLECULE if same_molecule else 0) | (_lib.MOUSE_FORCE_EXACT if exact else 0) | \
-        (_lib.MOUSE_NO_CUTOFF if rcut < 0 else 0)
+        (_lib.MOUSE_NO_CUTOFF if rcut < 0 else 0) | _lib.MOUSE_SLOTS(slots) | _lib.MOUSE_WARPS(warps) | \
+        (_lib.MOUSE_FORCE_FAST if force_fast else 0)
     st = _stream()
     if hist_args is None:
         _lib.check(L.mouse_p2_frame(_ptr(pos), _ptr(bonds), _ptr(molc), _ptr(nbr), _ptr(ref), n, C.byref(grid),
@@ -142,18 +162,21 @@ def p2_frame(positions, bond_atoms, mol, box, rcut, same_molecule=True, nbr_mask
                    "mouse_bond_build")
         _lib.check(L.mouse_cell_build(_ptr(out.vec), _ptr(out.ctr), _ptr(molc), _ptr(nbr), _ptr(ref), n,
                                       C.byref(grid), _ptr(ws), ws.numel(), st), "mouse_cell_build")
-        _lib.check(L.mouse_p2_sweep(_ptr(out.vec), _ptr(out.ctr), n, C.byref(grid), flags, _ptr(ws), _ptr(out.sum),
-                                    _ptr(out.count), st), "mouse_p2_sweep")
-        _lib.check(L.mouse_p2_reduce(_ptr(out.sum), _ptr(out.count), n, C.byref(grid), _ptr(ws), _ptr(out.mean),
-                                     _ptr(out.totals), _ptr(out.hist), float(smin), float(smax), int(sbins), st),
+        _lib.check(L.mouse_p2_sweep(_ptr(out.vec), _ptr(out.ctr), n, C.byref(grid), flags, _ptr(ws), ws.numel(),
+                                    _ptr(out.sum), _ptr(out.count), st), "mouse_p2_sweep")
+        _lib.check(L.mouse_p2_reduce(_ptr(out.sum), _ptr(out.count), n, C.byref(grid), _ptr(ws), ws.numel(),
+                                     _ptr(out.mean), _ptr(out.totals), _ptr(out.hist), float(smin), float(smax),
+                                     int(sbins), st),
                    "mouse_p2_reduce")
     return out
 
 
 def p2_pair_lists(res: P2Result, same_molecule=True, exact=False, rcut=None):
-    """Counted neighbour lists of the frame last built in the workspace (call right after
-    ``p2_frame`` with the same arguments).  Returns (row_ptr int64 (N_b+1,), nbr_idx int32) with rows
-    sorted ascending (sorting is plumbing done with torch)."""
+    """Counted neighbour lists of the frame ``res`` was computed on (same ``same_molecule`` / ``rcut`` arguments).
+    The cell list lives in ``res.ws``: either a private buffer (``p2_frame(private_workspace=True)``) or the shared
+    per-device one, in which case this must be the next engine call on the device - anything in between reuses the
+    buffer and this function raises instead of reading a foreign cell list.  Returns (row_ptr int64 (N_b+1,),
+    nbr_idx int32) with rows sorted ascending (sorting is plumbing done with torch)."""
     require_cuda()
     n = int(res.sum.shape[0])
     device = res.sum.device
@@ -161,13 +184,16 @@ def p2_pair_lists(res: P2Result, same_molecule=True, exact=False, rcut=None):
     if total is None:
         raise ValueError("pair lists are undefined when zero-length bonds poison the frame")
     L = _lib.lib()
-    ws = workspace(L.mouse_workspace_bytes(n, C.byref(res.grid)), device)
+    ws = res.ws
+    if ws is None or (res.ws_generation >= 0 and res.ws_generation != workspace_generation(device)):
+        raise RuntimeError("p2_pair_lists: the shared workspace was reused after this frame was computed; "
+                           "call p2_frame(..., private_workspace=True) to keep the frame's cell list")
     row_ptr = torch.empty(n + 1, dtype=torch.int64, device=device)
     nbr = torch.empty(max(total, 1), dtype=torch.int32, device=device)
     flags = (_lib.MOUSE_SAME_MOLECULE if same_molecule else 0) | (_lib.MOUSE_FORCE_EXACT if exact else 0) | \
         (_lib.MOUSE_NO_CUTOFF if (rcut is not None and rcut < 0) else 0)
-    _lib.check(L.mouse_p2_pair_lists(_ptr(res.vec), _ptr(res.ctr), n, C.byref(res.grid), flags, _ptr(ws),
-                                     _ptr(res.count), _ptr(row_ptr), _ptr(nbr), total, _stream()),
+    _lib.check(L.mouse_p2_pair_lists(_ptr(res.vec), _ptr(res.ctr), n, C.byref(res.grid), flags, _ptr(ws), ws.numel(),
+                                     _ptr(res.count), _ptr(row_ptr), _ptr(nbr), max(total, 1), _stream()),
                "mouse_p2_pair_lists")
     nbr = nbr[:total]
     rows = torch.repeat_interleave(torch.arange(n, device=device), res.count.long())

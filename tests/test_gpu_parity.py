@@ -152,17 +152,13 @@ def test_deterministic_and_slot_variants():
     molb = melt.mol[melt.bond_atoms[:, 0]]
     base = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, 2.5)
     s0, c0 = base.sum.clone(), base.count.clone()
-    for slots in (0, 4, 8, 12, 16):
-        _lib.lib().mouse_set_tuning(b"fast_slots", slots)
-        try:
-            r = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, 2.5)
-            assert torch.equal(r.count, c0)
-            if slots == 0:
-                assert torch.equal(r.sum, s0)            # run-to-run bit-identical
-            else:
-                torch.testing.assert_close(r.sum, s0, rtol=1e-13, atol=1e-13)
-        finally:
-            _lib.lib().mouse_set_tuning(b"fast_slots", 0)
+    for slots, warps in ((0, 0), (4, 0), (6, 0), (8, 0), (6, 3)):
+        r = eng.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, 2.5, slots=slots, warps=warps)
+        assert torch.equal(r.count, c0)
+        if slots == 0:
+            assert torch.equal(r.sum, s0)            # run-to-run bit-identical
+        else:
+            torch.testing.assert_close(r.sum, s0, rtol=1e-13, atol=1e-13)
 
 
 def test_edge_cases():
@@ -410,12 +406,12 @@ def _bonds_from_midpoints(ctr, vec):
 
 
 def _sweep_counters(res, n):
-    """The workspace counters left behind by the last frame (0 zero-length, 1 exact re-decisions, 3 pair-list
+    """The workspace counters left behind by the last frame (0 zero-length bonds, 1 exact re-decisions, 3 pair-list
     length, 4 pair-list overflow flag)."""
     import ctypes as C
     from mouse_b200 import _lib, engine
     L = _lib.lib()
-    ws = engine.workspace(L.mouse_workspace_bytes(n, C.byref(res.grid)), res.sum.device)
+    ws = res.ws
     out = (C.c_int64 * 8)()
     _lib.check(L.mouse_debug_counters(C.byref(res.grid), n, engine._ptr(ws), out, engine._stream()), "debug_counters")
     return list(out)
@@ -435,12 +431,14 @@ def _check_against_c_oracle(pos, bonds, mol, box, rc, same=True, nbr=None, ref=N
     return res, ora
 
 
-def test_dense_cluster_oversize_home_cells_and_many_passes():
-    """One cell holds far more bonds than the fast sweep keeps in shared memory / registers: those home cells are
-    decided pair by pair through the pair list, their neighbours take several candidate passes."""
+@pytest.mark.parametrize("n_cl", [150, 330])
+def test_dense_cluster_oversize_home_cells_and_many_passes(n_cl):
+    """One cell holds far more bonds than the fast sweep takes as references at a time: 150 bonds are swept in
+    windows of 64 references, each against all chunks of the candidate concatenation; 330 bonds do not fit the landing
+    zone any more and the cell is decided pair by pair through the pair list (hs_oversize, p2_fixup_kernel)."""
     rng = np.random.default_rng(5)
     box = np.array([24.0, 24.0, 24.0])
-    n_bg, n_cl = 20000, 150          # 15^3 cells of edge 1.6; the cluster sits in the middle of one of them
+    n_bg = 20000                     # 15^3 cells of edge 1.6; the cluster sits in the middle of one of them
     ctr = np.concatenate([rng.uniform(-12, 12, (n_bg, 3)), rng.normal(0.8, 0.2, (n_cl, 3))])
     vec = rng.normal(size=(len(ctr), 3))
     vec *= 0.97 / np.linalg.norm(vec, axis=1)[:, None]
@@ -450,7 +448,10 @@ def test_dense_cluster_oversize_home_cells_and_many_passes():
         res, ora = _check_against_c_oracle(pos, bonds, mol, box, 1.5, same)
         assert ora["count"].max() > 140        # the cluster really is dense
         c = _sweep_counters(res, len(bonds))
-        assert c[4] == 0 and c[3] > 5000       # the oversized home cell went through the pair list, no overflow
+        if n_cl > 256:
+            assert c[4] == 0 and c[3] > 5000   # the oversized home cell went through the pair list, no overflow
+        else:
+            assert c[4] == 0 and c[3] < 500    # windows of references: only guard-band pairs are on the list
 
 
 def test_pair_list_overflow_falls_back_to_the_exact_sweep():
@@ -467,6 +468,7 @@ def test_pair_list_overflow_falls_back_to_the_exact_sweep():
     mol = np.arange(len(ctr), dtype=np.int32)
     res, ora = _check_against_c_oracle(pos, bonds, mol, box, a, True)
     assert ora["count"].min() >= 1
+    assert res.grid.fast == 1
     assert _sweep_counters(res, len(bonds))[4] == 1     # the pair list did overflow
 
 
@@ -535,7 +537,7 @@ def test_staged_sweep_after_a_fused_frame_on_the_same_cell_list():
         for flags in (_lib.MOUSE_SAME_MOLECULE, 0):
             s2 = torch.full((n,), -1.0, dtype=torch.float64, device=dev)
             c2 = torch.full((n,), -1, dtype=torch.int32, device=dev)
-            rc = L.mouse_p2_sweep(p(vec), p(ctr), n, C.byref(grid), flags, p(ws), p(s2), p(c2), st)
+            rc = L.mouse_p2_sweep(p(vec), p(ctr), n, C.byref(grid), flags, p(ws), ws.numel(), p(s2), p(c2), st)
             assert rc == 0
             torch.cuda.synchronize()
             assert torch.equal(c2, out[flags][1]) and torch.equal(s2, out[flags][0])

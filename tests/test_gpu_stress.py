@@ -38,7 +38,7 @@ def _case(seed):
 
 @pytest.mark.parametrize("seed", range(18))
 def test_random_p2_frames_match_the_c_oracle(seed):
-    from mouse_b200 import _lib, engine
+    from mouse_b200 import engine
     from oracle import c_oracle
     engine.require_cuda()
     pos, bonds, mol, box, rc, nbr, ref = _case(seed)
@@ -46,12 +46,11 @@ def test_random_p2_frames_match_the_c_oracle(seed):
     for same in (True, False):
         ora = c_oracle.p2(vec, ctr, mol, box, rc, same, ref_mask=ref, nbr_mask=nbr)
         ok = ora["count"] > 0
-        for slots in (0, 4, 8) if seed % 3 == 0 else (0,):
-            _lib.lib().mouse_set_tuning(b"fast_slots", slots)
-            try:
-                res = engine.p2_frame(pos, bonds, mol, box, rc, same_molecule=same, nbr_mask=nbr, ref_mask=ref)
-            finally:
-                _lib.lib().mouse_set_tuning(b"fast_slots", 0)
+        # slots = -1: the library's own choice (crowded frames leave the fast sweep, mouse_p2_uses_fast); the other
+        # variants force the FP32-filter sweep: several chunks / sub-passes per home cell, oversized home cells
+        for slots in (-1, 0, 4, 6, 8) if seed % 3 == 0 else (-1, 0):
+            res = engine.p2_frame(pos, bonds, mol, box, rc, same_molecule=same, nbr_mask=nbr, ref_mask=ref,
+                                  slots=max(slots, 0), force_fast=slots >= 0)
             assert res.grid.fast == 1
             assert np.array_equal(res.count.cpu().numpy().astype(np.int64), ora["count"]), (seed, same, slots)
             np.testing.assert_allclose(res.mean.cpu().numpy()[ok], ora["mean"][ok], rtol=1e-12, atol=1e-14)
