@@ -49,6 +49,15 @@ typedef struct mouse_grid {
   int32_t ncell;      /* product */
   int32_t fast;       /* 1: >= 3 cells on every axis and guard band small -> FP32-filter sweep valid */
   float guard;        /* relative half-width of the FP32 guard band around rc2 */
+  /* Triclinic boxes (LAMMPS convention a = (lx,0,0), b = (xy,ly,0), c = (xz,yz,lz)): BUILD-DEFINED semantics, the
+   * reference is orthorhombic only (lammpack_types.py:440-451 drops the tilt factors).  box[] holds lx, ly, lz; the
+   * cells are parallelepipeds of the lattice (cell_w = edge / cells per axis); the minimum image of a displacement is
+   * its representative in the brick |dx| <= lx/2, |dy| <= ly/2, |dz| <= lz/2 found axis by axis from z to x with the
+   * reference's own step dr - L*around(dr/L) (ordering_functions.py:98-100), removing the tilt components of the
+   * subtracted lattice vector from the lower axes.  tilt = 0 reproduces the orthorhombic results bit for bit. */
+  double tilt[3];     /* xy, xz, yz */
+  int32_t triclinic;  /* 1: planned by mouse_grid_plan_triclinic (the tilt-aware code paths run even for tilt = 0) */
+  int32_t reserved;
 } mouse_grid_t;
 
 /* Totals written by the fused reductions (device or host memory, see each function). */
@@ -68,6 +77,11 @@ const char *mouse_last_error(void);
 int mouse_grid_plan(const double *box /*HOST[3]*/, double rcut, double rc2, int64_t n_items,
                     mouse_grid_t *grid /*HOST out*/);
 
+/* HOST only.  The same for a triclinic box (tilt = {xy, xz, yz}); cells per axis come from the perpendicular widths
+ * of the box, `fast` additionally needs every cell plus the cutoff to fit half the box edge in Cartesian extent. */
+int mouse_grid_plan_triclinic(const double *box /*HOST[3]*/, const double *tilt /*HOST[3]*/, double rcut, double rc2,
+                              int64_t n_items, mouse_grid_t *grid /*HOST out*/);
+
 /* K1.  Replaces vector_and_center_pbc_trim method 1 (lammpack_types.py:587-599) as called per
  * bond by createNumpyBondsArrayFromConfig (ordering_functions.py:29) and again per reference
  * bond (:92).  vec/ctr are the rows 3-5 / 6-8 of the reference's (9,N_b) npBonds array:
@@ -75,6 +89,10 @@ int mouse_grid_plan(const double *box /*HOST[3]*/, double rcut, double rc2, int6
 int mouse_bond_build(const double *pos /*DEV [n_atoms][3]*/, const int32_t *bond_atoms /*DEV [n_bonds][2]*/,
                      int64_t n_bonds, const double *box /*HOST[3]*/, double *vec /*DEV [3][n_bonds]*/,
                      double *ctr /*DEV [3][n_bonds]*/, void *stream);
+
+/* K1 for a triclinic box: the np.remainder form of lammpack_types.py:587-599 axis by axis from z to x (build-defined). */
+int mouse_bond_build_triclinic(const double *pos, const int32_t *bond_atoms, int64_t n_bonds, const double *box /*HOST[3]*/,
+                               const double *tilt /*HOST[3]*/, double *vec, double *ctr, void *stream);
 
 /* Workspace for cell list + sweep on `n_items` bonds (or atoms) with `grid`. */
 size_t mouse_workspace_bytes(int64_t n_items, const mouse_grid_t *grid);
@@ -121,6 +139,19 @@ int mouse_p2_frame(const double *pos, const int32_t *bond_atoms, const int32_t *
                    const uint8_t *ref_mask, int64_t n_bonds, const mouse_grid_t *grid, uint32_t flags,
                    void *ws, size_t ws_bytes, double *vec, double *ctr, double *sum, int32_t *cnt,
                    double *mean, mouse_p2_totals_t *totals, void *stream);
+
+/* The same frame captured ONCE into a CUDA graph (trajectories: fixed topology, box, cutoff and buffers - only the
+ * contents of `pos` change): _create runs no kernel, it records mouse_p2_frame's launch train; _launch replays it on
+ * `stream` with one driver call per frame; _nodes = kernels + memsets recorded; _destroy frees the handle.  The
+ * buffers named at creation must stay alive and must not be shared with a graph launched concurrently. */
+int mouse_p2_frame_graph_create(const double *pos, const int32_t *bond_atoms, const int32_t *mol,
+                                const uint8_t *nbr_mask, const uint8_t *ref_mask, int64_t n_bonds,
+                                const mouse_grid_t *grid, uint32_t flags, void *ws, size_t ws_bytes, double *vec,
+                                double *ctr, double *sum, int32_t *cnt, double *mean, mouse_p2_totals_t *totals,
+                                void **out_graph /*HOST out*/);
+int mouse_p2_frame_graph_launch(void *graph, void *stream);
+int mouse_p2_frame_graph_nodes(void *graph);
+int mouse_p2_frame_graph_destroy(void *graph);
 
 /* mouse_p2_frame with two optional cudaEvent_t handles (NULL = none) recorded on `stream` right before and right
  * after the K3 launches: lets a caller time the pair sweep inside a frame (bench.py's roofline line). */

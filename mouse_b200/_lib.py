@@ -34,7 +34,8 @@ class Grid(C.Structure):
     """``mouse_grid_t``"""
     _fields_ = [("box", C.c_double * 3), ("rcut", C.c_double), ("rc2", C.c_double),
                 ("cell_w", C.c_double * 3), ("ncell_axis", C.c_int32 * 3), ("ncell", C.c_int32),
-                ("fast", C.c_int32), ("guard", C.c_float)]
+                ("fast", C.c_int32), ("guard", C.c_float), ("tilt", C.c_double * 3), ("triclinic", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class P2Totals(C.Structure):
@@ -44,9 +45,11 @@ class P2Totals(C.Structure):
 
 
 EXPORTS = [
-    "mouse_version", "mouse_last_error", "mouse_grid_plan", "mouse_bond_build",
+    "mouse_version", "mouse_last_error", "mouse_grid_plan", "mouse_grid_plan_triclinic", "mouse_bond_build",
+    "mouse_bond_build_triclinic",
     "mouse_workspace_bytes", "mouse_cell_build", "mouse_p2_sweep", "mouse_p2_pair_lists", "mouse_p2_reduce",
-    "mouse_p2_frame", "mouse_p2_frame_timed", "mouse_rdf_frame", "mouse_single_ref_workspace_bytes", "mouse_p2_single_ref",
+    "mouse_p2_frame", "mouse_p2_frame_timed", "mouse_p2_frame_graph_create", "mouse_p2_frame_graph_launch",
+    "mouse_p2_frame_graph_nodes", "mouse_p2_frame_graph_destroy", "mouse_rdf_frame", "mouse_single_ref_workspace_bytes", "mouse_p2_single_ref",
     "mouse_rdf_single_ref", "mouse_director_p2", "mouse_debug_counters", "mouse_parse_doubles",
 ]
 
@@ -76,7 +79,9 @@ def lib():
     L.mouse_version.restype = C.c_char_p
     L.mouse_last_error.restype = C.c_char_p
     L.mouse_grid_plan.argtypes = [C.POINTER(C.c_double), dbl, dbl, i64, gp]
+    L.mouse_grid_plan_triclinic.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), dbl, dbl, i64, gp]
     L.mouse_bond_build.argtypes = [vp, vp, i64, C.POINTER(C.c_double), vp, vp, vp]
+    L.mouse_bond_build_triclinic.argtypes = [vp, vp, i64, C.POINTER(C.c_double), C.POINTER(C.c_double), vp, vp, vp]
     L.mouse_workspace_bytes.argtypes = [i64, gp]
     L.mouse_workspace_bytes.restype = C.c_size_t
     L.mouse_cell_build.argtypes = [vp, vp, vp, vp, vp, i64, gp, vp, C.c_size_t, vp]
@@ -85,6 +90,11 @@ def lib():
     L.mouse_p2_reduce.argtypes = [vp, vp, i64, gp, vp, C.c_size_t, vp, vp, vp, dbl, dbl, i32, vp]
     L.mouse_p2_frame.argtypes = [vp, vp, vp, vp, vp, i64, gp, u32, vp, C.c_size_t, vp, vp, vp, vp, vp, vp, vp]
     L.mouse_p2_frame_timed.argtypes = [vp, vp, vp, vp, vp, i64, gp, u32, vp, C.c_size_t, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.mouse_p2_frame_graph_create.argtypes = [vp, vp, vp, vp, vp, i64, gp, u32, vp, C.c_size_t, vp, vp, vp, vp, vp, vp,
+                                              C.POINTER(C.c_void_p)]
+    L.mouse_p2_frame_graph_launch.argtypes = [vp, vp]
+    L.mouse_p2_frame_graph_nodes.argtypes = [vp]
+    L.mouse_p2_frame_graph_destroy.argtypes = [vp]
     L.mouse_rdf_frame.argtypes = [vp, vp, vp, i64, i32, gp, u32, C.POINTER(C.c_double), i32, vp, C.c_size_t, vp, vp]
     L.mouse_single_ref_workspace_bytes.restype = C.c_size_t
     L.mouse_p2_single_ref.argtypes = [vp, i64, C.POINTER(C.c_double), C.POINTER(C.c_double), dbl, dbl, u32, vp, vp, vp]
@@ -107,11 +117,17 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError("%s failed (%d): %s" % (what, rc, lib().mouse_last_error().decode()))
 
 
-def grid_plan(box, rcut: float, n_items: int, rc2: float | None = None) -> Grid:
+def grid_plan(box, rcut: float, n_items: int, rc2: float | None = None, tilt=None) -> Grid:
     """Host-side cell grid.  ``rc2`` defaults to the Python expression ``rcut**2`` so that the
-    threshold bits equal the reference's (``ordering_functions.py:102``)."""
+    threshold bits equal the reference's (``ordering_functions.py:102``).  ``tilt`` = (xy, xz, yz) plans a triclinic
+    box (build-defined semantics: the reference is orthorhombic only, ``lammpack_types.py:440-451``)."""
     g = Grid()
     b = (C.c_double * 3)(float(box[0]), float(box[1]), float(box[2]))
-    check(lib().mouse_grid_plan(b, float(rcut), float(rcut)**2 if rc2 is None else float(rc2), int(n_items),
-                                C.byref(g)), "mouse_grid_plan")
+    r2 = float(rcut)**2 if rc2 is None else float(rc2)
+    if tilt is None:
+        check(lib().mouse_grid_plan(b, float(rcut), r2, int(n_items), C.byref(g)), "mouse_grid_plan")
+    else:
+        t = (C.c_double * 3)(float(tilt[0]), float(tilt[1]), float(tilt[2]))
+        check(lib().mouse_grid_plan_triclinic(b, t, float(rcut), r2, int(n_items), C.byref(g)),
+              "mouse_grid_plan_triclinic")
     return g

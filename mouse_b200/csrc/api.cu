@@ -8,7 +8,7 @@
 
 // launchers implemented next to their kernels
 int mouse_launch_bond_build(const double *pos, const int32_t *bond_atoms, int64_t n, const double *box,
-                            double *vec, double *ctr, cudaStream_t st);
+                            const double *tilt, double *vec, double *ctr, cudaStream_t st);
 int mouse_launch_cell_build(int mode, const double *xyz, const double *vec, const int32_t *code,
                             const int32_t *code2, const uint8_t *nbr_mask, const uint8_t *ref_mask, int64_t n,
                             const mouse_grid_t *grid, const Workspace &w, cudaStream_t st);
@@ -45,22 +45,34 @@ extern "C" {
 const char *mouse_version(void) { return "mouse_b200 0.1 (sm_100a)"; }
 const char *mouse_last_error(void) { return g_err; }
 
-int mouse_grid_plan(const double *box, double rcut, double rc2, int64_t n_items, mouse_grid_t *grid) {
+static int grid_plan_impl(const char *who, const double *box, const double *tilt, double rcut, double rc2,
+                          int64_t n_items, mouse_grid_t *grid) {
   if (!box || !grid) {
-    mouse_set_error("mouse_grid_plan: NULL argument");
+    mouse_set_error("%s: NULL argument", who);
     return MOUSE_EINVAL;
   }
   memset(grid, 0, sizeof(*grid));
+  for (int a = 0; a < 3; ++a) {
+    if (!(box[a] > 0.0)) {
+      mouse_set_error("%s: box[%d]=%g must be positive", who, a, box[a]);
+      return MOUSE_EINVAL;
+    }
+  }
+  // distance between opposite faces of the box along every lattice direction (= the edge for an orthorhombic box)
+  double wid[3] = {box[0], box[1], box[2]};
+  double xy = 0.0, xz = 0.0, yz = 0.0;
+  if (tilt) {
+    xy = tilt[0], xz = tilt[1], yz = tilt[2];
+    const double bcx = box[1] * box[2], bcy = -xy * box[2], bcz = xy * yz - box[1] * xz;   // b x c
+    wid[0] = box[0] * box[1] * box[2] / sqrt(bcx * bcx + bcy * bcy + bcz * bcz);
+    wid[1] = box[1] * box[2] / sqrt(box[2] * box[2] + yz * yz);                            // V / |a x c|
+  }
   double cells = 1.0;
   int nax[3];
   for (int a = 0; a < 3; ++a) {
-    if (!(box[a] > 0.0)) {
-      mouse_set_error("mouse_grid_plan: box[%d]=%g must be positive", a, box[a]);
-      return MOUSE_EINVAL;
-    }
     int k = 1;
     if (rcut > 0.0) {
-      double q = box[a] / (rcut * (1.0 + 1e-6));
+      double q = wid[a] / (rcut * (1.0 + 1e-6));
       k = q >= 1.0 ? (q > 1024.0 ? 1024 : (int)q) : 1;
     }
     nax[a] = k;
@@ -76,8 +88,8 @@ int mouse_grid_plan(const double *box, double rcut, double rc2, int64_t n_items,
       nax[a] = k < 1 ? 1 : k;
     }
   }
-  // sparse cells: the half-shell sweeps pay a fixed cost per home cell (fetch, TMA, register load, flush), which
-  // is amortised best at ~10 items per cell (one pass of 6 slots); any cell edge >= rcut is a valid cell list.
+  // sparse cells: the half-shell sweeps pay a fixed cost per home cell (fetch, TMA, cull, register load, flush), which
+  // is amortised best at ~10 items per cell; any cell at least rcut wide is a valid cell list.
   // Small systems keep the fine grid: they need the home cells for parallelism, not for amortisation.
   {
     const double target = 9.5;
@@ -91,29 +103,52 @@ int mouse_grid_plan(const double *box, double rcut, double rc2, int64_t n_items,
       }
     }
   }
-  double ratio = 0.0;
   int fast = rcut > 0.0;
   for (int a = 0; a < 3; ++a) {
     grid->box[a] = box[a];
     grid->ncell_axis[a] = nax[a];
     grid->cell_w[a] = box[a] / nax[a];
     if (nax[a] < 3) fast = 0;
-    if (rcut > 0.0 && grid->cell_w[a] / rcut > ratio) ratio = grid->cell_w[a] / rcut;
   }
   grid->ncell = nax[0] * nax[1] * nax[2];
   grid->rcut = rcut;
   grid->rc2 = rc2;
+  grid->tilt[0] = xy, grid->tilt[1] = xz, grid->tilt[2] = yz;
+  grid->triclinic = tilt ? 1 : 0;
   // FP32 error budget of the fast sweep (DESIGN.md "guard band"): coordinates are stored as FP32 of
-  // (wrapped - L/2), one rounded periodic shift, one subtraction: |delta dx| <= 2.5 * 2^-24 * L, so the
+  // (wrapped - centre), one rounded periodic shift, one subtraction: |delta dx| <= 2.5 * 2^-24 * L, so the
   // relative error of d2 at the cutoff is <= 5.2e-7 * (Lmax / rcut) + 1.8e-7; keep a 4x margin, never below 2^-15.
-  (void)ratio;
-  double lmax = box[0] > box[1] ? (box[0] > box[2] ? box[0] : box[2]) : (box[1] > box[2] ? box[1] : box[2]);
-  double guard = rcut > 0.0 ? 4.0 * (5.2e-7 * (lmax / rcut) + 2.0e-7) : 1.0;
+  // A triclinic shift is up to three rounded steps per coordinate on a Cartesian extent lx + |xy| + |xz|: 3x.
+  double ext[3] = {box[0] + fabs(xy) + fabs(xz), box[1] + fabs(yz), box[2]};
+  double lmax = ext[0] > ext[1] ? (ext[0] > ext[2] ? ext[0] : ext[2]) : (ext[1] > ext[2] ? ext[1] : ext[2]);
+  double guard = rcut > 0.0 ? 4.0 * ((tilt ? 3.0 : 1.0) * 5.2e-7 * (lmax / rcut) + 2.0e-7) : 1.0;
   if (guard < 3.0517578125e-05) guard = 3.0517578125e-05;
   if (guard > 1.0e-2) fast = 0;
+  if (tilt && fast) {
+    // the sweep moves a candidate to the image nearest to the home cell's centre with the brick rule: that is the
+    // image a reference of the home cell needs only if half a cell plus the cutoff fits half the box edge on every
+    // Cartesian axis (for an orthorhombic box this is the ">= 3 cells" rule)
+    const double cext[3] = {box[0] / nax[0] + fabs(xy) / nax[1] + fabs(xz) / nax[2], box[1] / nax[1] + fabs(yz) / nax[2],
+                            box[2] / nax[2]};
+    for (int a = 0; a < 3; ++a)
+      if (0.5 * cext[a] + rcut * (1.0 + 2.0 * guard) > 0.5 * box[a] * (1.0 - 1e-9)) fast = 0;
+  }
   grid->guard = (float)guard;
   grid->fast = fast;
   return MOUSE_OK;
+}
+
+int mouse_grid_plan(const double *box, double rcut, double rc2, int64_t n_items, mouse_grid_t *grid) {
+  return grid_plan_impl("mouse_grid_plan", box, nullptr, rcut, rc2, n_items, grid);
+}
+
+int mouse_grid_plan_triclinic(const double *box, const double *tilt, double rcut, double rc2, int64_t n_items,
+                              mouse_grid_t *grid) {
+  if (!tilt) {
+    mouse_set_error("mouse_grid_plan_triclinic: NULL tilt");
+    return MOUSE_EINVAL;
+  }
+  return grid_plan_impl("mouse_grid_plan_triclinic", box, tilt, rcut, rc2, n_items, grid);
 }
 
 size_t mouse_workspace_bytes(int64_t n_items, const mouse_grid_t *grid) {
@@ -126,7 +161,7 @@ static int check_ws(const char *who, int64_t n, const mouse_grid_t *grid, void *
     mouse_set_error("%s: NULL grid/workspace", who);
     return MOUSE_EINVAL;
   }
-  if (n < 0 || n >= 2147483647LL) {
+  if (n < 0 || n >= (1LL << 30)) {
     mouse_set_error("%s: n=%lld out of range", who, (long long)n);
     return MOUSE_EINVAL;
   }
@@ -149,7 +184,17 @@ int mouse_bond_build(const double *pos, const int32_t *bond_atoms, int64_t n_bon
     mouse_set_error("mouse_bond_build: NULL argument");
     return MOUSE_EINVAL;
   }
-  return mouse_launch_bond_build(pos, bond_atoms, n_bonds, box, vec, ctr, (cudaStream_t)stream);
+  return mouse_launch_bond_build(pos, bond_atoms, n_bonds, box, nullptr, vec, ctr, (cudaStream_t)stream);
+}
+
+int mouse_bond_build_triclinic(const double *pos, const int32_t *bond_atoms, int64_t n_bonds, const double *box,
+                               const double *tilt, double *vec, double *ctr, void *stream) {
+  if (!pos || !bond_atoms || !box || !tilt || !vec || !ctr) {
+    if (n_bonds == 0) return MOUSE_OK;
+    mouse_set_error("mouse_bond_build_triclinic: NULL argument");
+    return MOUSE_EINVAL;
+  }
+  return mouse_launch_bond_build(pos, bond_atoms, n_bonds, box, tilt, vec, ctr, (cudaStream_t)stream);
 }
 
 int mouse_cell_build(const double *vec, const double *ctr, const int32_t *mol, const uint8_t *nbr_mask,
@@ -241,6 +286,72 @@ int mouse_p2_frame(const double *pos, const int32_t *bond_atoms, const int32_t *
                    mouse_p2_totals_t *totals, void *stream) {
   return mouse_p2_frame_timed(pos, bond_atoms, mol, nbr_mask, ref_mask, n_bonds, grid, flags, ws, ws_bytes, vec, ctr, sum,
                               cnt, mean, totals, nullptr, nullptr, stream);
+}
+
+// ---- a frame captured once into a CUDA graph: one launch per frame instead of a train of eight (the buffers, the
+// grid and the flags are baked in; new positions are copied into `pos` by the caller before every launch)
+struct FrameGraph {
+  cudaGraphExec_t exec;
+  int nodes;
+};
+
+int mouse_p2_frame_graph_create(const double *pos, const int32_t *bond_atoms, const int32_t *mol,
+                                const uint8_t *nbr_mask, const uint8_t *ref_mask, int64_t n_bonds,
+                                const mouse_grid_t *grid, uint32_t flags, void *ws, size_t ws_bytes, double *vec,
+                                double *ctr, double *sum, int32_t *cnt, double *mean, mouse_p2_totals_t *totals,
+                                void **out_graph) {
+  if (!out_graph) {
+    mouse_set_error("mouse_p2_frame_graph_create: NULL out_graph");
+    return MOUSE_EINVAL;
+  }
+  *out_graph = nullptr;
+  cudaStream_t st = nullptr;
+  MOUSE_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+  int rc = MOUSE_OK;
+  if (e == cudaSuccess) {
+    rc = mouse_p2_frame(pos, bond_atoms, mol, nbr_mask, ref_mask, n_bonds, grid, flags, ws, ws_bytes, vec, ctr, sum, cnt,
+                        mean, totals, st);
+    e = cudaStreamEndCapture(st, &g);
+  }
+  cudaGraphExec_t exec = nullptr;
+  size_t nodes = 0;
+  if (e == cudaSuccess && rc == MOUSE_OK) {
+    cudaGraphGetNodes(g, nullptr, &nodes);
+    e = cudaGraphInstantiate(&exec, g, 0);
+  }
+  if (g) cudaGraphDestroy(g);
+  cudaStreamDestroy(st);
+  if (rc != MOUSE_OK) return rc;
+  if (e != cudaSuccess) {
+    mouse_set_error("mouse_p2_frame_graph_create: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return MOUSE_ECUDA;
+  }
+  FrameGraph *fg = (FrameGraph *)malloc(sizeof(FrameGraph));
+  fg->exec = exec;
+  fg->nodes = (int)nodes;
+  *out_graph = fg;
+  return MOUSE_OK;
+}
+
+int mouse_p2_frame_graph_launch(void *graph, void *stream) {
+  if (!graph) {
+    mouse_set_error("mouse_p2_frame_graph_launch: NULL graph");
+    return MOUSE_EINVAL;
+  }
+  MOUSE_CUDA_CHECK(cudaGraphLaunch(((FrameGraph *)graph)->exec, (cudaStream_t)stream));
+  return MOUSE_OK;
+}
+
+int mouse_p2_frame_graph_nodes(void *graph) { return graph ? ((FrameGraph *)graph)->nodes : 0; }
+
+int mouse_p2_frame_graph_destroy(void *graph) {
+  if (!graph) return MOUSE_OK;
+  cudaGraphExecDestroy(((FrameGraph *)graph)->exec);
+  free(graph);
+  return MOUSE_OK;
 }
 
 int mouse_rdf_frame(const double *pos, const int32_t *type, const int32_t *mol, int64_t n_atoms, int32_t ntypes,

@@ -3,6 +3,8 @@
 //
 // K1 restates lammpack_types.py:587-599 (np.remainder form) in un-fused FP64.  K2 has no
 // reference counterpart - the reference is all-pairs (ordering_functions.py:94-115).
+#include <string.h>
+
 #include "half_shell.cuh"
 
 // np.remainder(a, b), b > 0: fmod then shift negatives by +b (NumPy npy_divmod); fmod is exact.
@@ -31,25 +33,55 @@ __device__ __forceinline__ void bond_axis(double p1, double p2, double L, double
   c = __dadd_rn(xc, __dmul_rn(__dsub_rn(xt, x), 0.5));
 }
 
+// Triclinic box (build-defined, see include/mouse_b200.h): the same np.remainder step axis by axis from z to x; a shift
+// by n lattice vectors along an axis also removes n times their tilt components from the lower axes.  tilt = {xy, xz, yz}
+__device__ __forceinline__ void bond_tri(const double *p1, const double *p2, const double *box, const double *tilt,
+                                         double (&v)[3], double (&c)[3]) {
+  double x[3], xc[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double q1 = __ldg(p1 + a), q2 = __ldg(p2 + a);
+    x[a] = __dsub_rn(q2, q1);
+    xc[a] = __dmul_rn(__dadd_rn(q2, q1), 0.5);
+  }
+  const double hz = __dmul_rn(box[2], 0.5), hy = __dmul_rn(box[1], 0.5), hx = __dmul_rn(box[0], 0.5);
+  v[2] = __dsub_rn(np_remainder_pos(__dadd_rn(x[2], hz), box[2]), hz);
+  const double nz = rint(__ddiv_rn(__dsub_rn(x[2], v[2]), box[2]));
+  const double y1 = __dsub_rn(x[1], __dmul_rn(tilt[2], nz));
+  const double x1 = __dsub_rn(x[0], __dmul_rn(tilt[1], nz));
+  v[1] = __dsub_rn(np_remainder_pos(__dadd_rn(y1, hy), box[1]), hy);
+  const double ny = rint(__ddiv_rn(__dsub_rn(y1, v[1]), box[1]));
+  const double x2 = __dsub_rn(x1, __dmul_rn(tilt[0], ny));
+  v[0] = __dsub_rn(np_remainder_pos(__dadd_rn(x2, hx), box[0]), hx);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) c[a] = __dadd_rn(xc[a], __dmul_rn(__dsub_rn(v[a], x[a]), 0.5));
+}
+
+// bond vector + midpoint of one bond for either kind of box
+__device__ __forceinline__ void bond_geom(const double *p1, const double *p2, const GridDev &g, double (&v)[3],
+                                          double (&c)[3]) {
+  if (g.tri) {
+    bond_tri(p1, p2, g.box, g.tilt, v, c);
+  } else {
+    bond_axis(__ldg(p1), __ldg(p2), g.box[0], v[0], c[0]);
+    bond_axis(__ldg(p1 + 1), __ldg(p2 + 1), g.box[1], v[1], c[1]);
+    bond_axis(__ldg(p1 + 2), __ldg(p2 + 2), g.box[2], v[2], c[2]);
+  }
+}
+
 __global__ void __launch_bounds__(256) bond_build_kernel(const double *__restrict__ pos,
-                                                         const int2 *__restrict__ bonds, int n,
-                                                         double Lx, double Ly, double Lz,
+                                                         const int2 *__restrict__ bonds, int n, GridDev g,
                                                          double *__restrict__ vec, double *__restrict__ ctr) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
   int2 ab = __ldg(bonds + b);
-  const double *p1 = pos + 3 * (size_t)ab.x;
-  const double *p2 = pos + 3 * (size_t)ab.y;
-  double v, c;
-  bond_axis(__ldg(p1), __ldg(p2), Lx, v, c);
-  vec[b] = v;
-  ctr[b] = c;
-  bond_axis(__ldg(p1 + 1), __ldg(p2 + 1), Ly, v, c);
-  vec[(size_t)n + b] = v;
-  ctr[(size_t)n + b] = c;
-  bond_axis(__ldg(p1 + 2), __ldg(p2 + 2), Lz, v, c);
-  vec[2 * (size_t)n + b] = v;
-  ctr[2 * (size_t)n + b] = c;
+  double v[3], c[3];
+  bond_geom(pos + 3 * (size_t)ab.x, pos + 3 * (size_t)ab.y, g, v, c);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    vec[a * (size_t)n + b] = v[a];
+    ctr[a * (size_t)n + b] = c[a];
+  }
 }
 
 // Wrapped copy of a coordinate into [0, L) and its cell index / in-cell offset.  The reference
@@ -68,14 +100,40 @@ __device__ __forceinline__ void cell_axis(double c, double L, double cw, int nc,
   xw = x;
 }
 
+// Cell of a point and its wrapped copy for either kind of box.  Triclinic: the point is expressed along the lattice
+// directions (fractional coordinate times edge length), wrapped and binned there, and mapped back to Cartesian; the
+// FP32 payload is the wrapped Cartesian position minus the centre of the cell H (1/2, 1/2, 1/2).  With tilt = 0 all
+// of this reduces to the orthorhombic expressions bit for bit.
+__device__ __forceinline__ int cell_of_point(double cx, double cy, double cz, const GridDev &g, double &xw, double &yw,
+                                             double &zw) {
+  int kx, ky, kz;
+  if (g.tri) {
+    const double fz = cz / g.box[2];
+    const double uy = cy - g.tilt[2] * fz;
+    const double ux = cx - g.tilt[0] * (uy / g.box[1]) - g.tilt[1] * fz;
+    double uxw, uyw, uzw;
+    cell_axis(ux, g.box[0], g.cw[0], g.nc[0], kx, uxw);
+    cell_axis(uy, g.box[1], g.cw[1], g.nc[1], ky, uyw);
+    cell_axis(cz, g.box[2], g.cw[2], g.nc[2], kz, uzw);
+    xw = uxw + g.tilt[0] * (uyw / g.box[1]) + g.tilt[1] * (uzw / g.box[2]);
+    yw = uyw + g.tilt[2] * (uzw / g.box[2]);
+    zw = uzw;
+  } else {
+    cell_axis(cx, g.box[0], g.cw[0], g.nc[0], kx, xw);
+    cell_axis(cy, g.box[1], g.cw[1], g.nc[1], ky, yw);
+    cell_axis(cz, g.box[2], g.cw[2], g.nc[2], kz, zw);
+  }
+  return (kz * g.nc[1] + ky) * g.nc[0] + kx;
+}
+
 // payload of an item, written once in ORIGINAL order (16 + 32 contiguous bytes: the canonical gather then costs two
 // sectors per item).  P = FP32 copy of the wrapped coordinate, centred on the box (|x| <= L/2 keeps one more
 // mantissa bit) + code bits; U = FP64 unit bond vector (P2) / absolute position + molecule code (RDF).
 __device__ __forceinline__ float4 payload_p(double xw, double yw, double zw, const GridDev &g, int code) {
   float4 p;
-  p.x = (float)(xw - 0.5 * g.box[0]);
-  p.y = (float)(yw - 0.5 * g.box[1]);
-  p.z = (float)(zw - 0.5 * g.box[2]);
+  p.x = (float)(xw - g.ctr_off[0]);
+  p.y = (float)(yw - g.ctr_off[1]);
+  p.z = (float)(zw - g.ctr_off[2]);
   p.w = __int_as_float(code);
   return p;
 }
@@ -123,12 +181,8 @@ __global__ void __launch_bounds__(256) cell_assign_kernel(const double *__restri
     cell_of[b] = -1;
     return;
   }
-  int kx, ky, kz;
   double xw, yw, zw;
-  cell_axis(cx, g.box[0], g.cw[0], g.nc[0], kx, xw);
-  cell_axis(cy, g.box[1], g.cw[1], g.nc[1], ky, yw);
-  cell_axis(cz, g.box[2], g.cw[2], g.nc[2], kz, zw);
-  int cid = (kz * g.nc[1] + ky) * g.nc[0] + kx;
+  const int cid = cell_of_point(cx, cy, cz, g, xw, yw, zw);
   cell_of[b] = cid;
   rank_of[b] = atomicAdd(&cell_count[cid], 1);
   Rec r;
@@ -276,6 +330,67 @@ __global__ void __launch_bounds__(256) scan_apply2_kernel(const int32_t *__restr
   }
 }
 
+// ---- exclusive scan in ONE kernel (up to MOUSE_SCAN_FUSED_TILES tiles, all co-resident): every block publishes its
+// tile total (+1, so that 0 means "not there yet"; the array is zeroed with the counters) and then sums the totals of
+// the tiles in front of it as they appear.  Blocks only ever wait for blocks with a lower index, which the hardware
+// dispatches first.
+#define MOUSE_SCAN_FUSED_TILES 592
+__global__ void __launch_bounds__(256) scan_fused_kernel(const int32_t *__restrict__ in, int nc,
+                                                         int32_t *__restrict__ tile_flags,
+                                                         int32_t *__restrict__ out) {
+  __shared__ int s_warp[8];
+  __shared__ int s_off;
+  const int base = blockIdx.x * MOUSE_SCAN_TILE + threadIdx.x * 8;
+  int v[8];
+  int tsum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = base + k;
+    v[k] = c < nc ? in[c] : 0;
+    tsum += v[k];
+  }
+  int x = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(MOUSE_FULL_MASK, x, o);
+    if ((threadIdx.x & 31) >= o) x += y;
+  }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += s_warp[w];
+    atomicExch(&tile_flags[blockIdx.x], t + 1);      // publish this tile's total
+  }
+  // totals of the tiles in front of this one
+  int part = 0;
+  for (int k = threadIdx.x; k < (int)blockIdx.x; k += 256) {
+    int f;
+    while ((f = ((volatile int32_t *)tile_flags)[k]) == 0) __nanosleep(20);
+    part += f - 1;
+  }
+  part = warp_sum(part);
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += s_warp[w];
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += s_warp[w];
+    s_off = t;
+  }
+  __syncthreads();
+  int run = s_off + woff + x - tsum;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = base + k;
+    if (c < nc) out[c] = run;
+    run += v[k];
+  }
+}
+
 // ---- scatter the item index into its cell (arrival order); the payload moves once, in cell_canon_kernel -----
 __global__ void __launch_bounds__(256) cell_scatter_idx_kernel(const uint8_t *__restrict__ ref_mask, int n,
                                                                const int32_t *__restrict__ cell_of,
@@ -298,6 +413,7 @@ __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, int n, GridD
                                                          const int32_t *__restrict__ cell_start,
                                                          const int32_t *__restrict__ idx_tmp,
                                                          const Rec *__restrict__ rec_tmp,
+                                                         int32_t *__restrict__ slot_of,
                                                          Rec *__restrict__ rec_sorted,
                                                          int32_t *__restrict__ idx_sorted,
                                                          int32_t *__restrict__ cell_sorted,
@@ -368,6 +484,9 @@ __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, int n, GridD
         // .w carries the sorted slot itself: the sweep's register-resident candidates know where they live
         if (MODE == 0) r.u.w = __hiloint2double(0, d);
         rec_sorted[d] = r;
+        // inverse permutation (the cell id of the item is dead by now): sorted slot | reference bit << 30, so that
+        // the fused finish + reduce walks the outputs in original order (coalesced stores, gathers that hit L2)
+        slot_of[mine] = d | (int)(((unsigned)raw >> 31) << 30);
         idx_sorted[d] = mine;
         cell_sorted[d] = c;
         flag_sorted[d] = (uint8_t)((unsigned)raw >> 31);
@@ -408,12 +527,9 @@ __global__ void __launch_bounds__(256) bond_assign_kernel(const double *__restri
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
   int2 ab = __ldg(bonds + b);
-  const double *p1 = pos + 3 * (size_t)ab.x;
-  const double *p2 = pos + 3 * (size_t)ab.y;
-  double vx, vy, vz, cx, cy, cz;
-  bond_axis(__ldg(p1), __ldg(p2), g.box[0], vx, cx);
-  bond_axis(__ldg(p1 + 1), __ldg(p2 + 1), g.box[1], vy, cy);
-  bond_axis(__ldg(p1 + 2), __ldg(p2 + 2), g.box[2], vz, cz);
+  double vv[3], cc[3];
+  bond_geom(pos + 3 * (size_t)ab.x, pos + 3 * (size_t)ab.y, g, vv, cc);
+  const double vx = vv[0], vy = vv[1], vz = vv[2], cx = cc[0], cy = cc[1], cz = cc[2];
   vec[b] = vx;
   vec[(size_t)n + b] = vy;
   vec[2 * (size_t)n + b] = vz;
@@ -436,12 +552,8 @@ __global__ void __launch_bounds__(256) bond_assign_kernel(const double *__restri
     cell_of[b] = -1;
     return;
   }
-  int kx, ky, kz;
   double xw, yw, zw;
-  cell_axis(cx, g.box[0], g.cw[0], g.nc[0], kx, xw);
-  cell_axis(cy, g.box[1], g.cw[1], g.nc[1], ky, yw);
-  cell_axis(cz, g.box[2], g.cw[2], g.nc[2], kz, zw);
-  int cid = (kz * g.nc[1] + ky) * g.nc[0] + kx;
+  const int cid = cell_of_point(cx, cy, cz, g, xw, yw, zw);
   cell_of[b] = cid;
   rank_of[b] = atomicAdd(&cell_count[cid], 1);
   Rec r;
@@ -452,10 +564,20 @@ __global__ void __launch_bounds__(256) bond_assign_kernel(const double *__restri
 
 // ---- host-side launchers ------------------------------------------------------------------------
 int mouse_launch_bond_build(const double *pos, const int32_t *bond_atoms, int64_t n, const double *box,
-                            double *vec, double *ctr, cudaStream_t st) {
+                            const double *tilt, double *vec, double *ctr, cudaStream_t st) {
   if (n == 0) return MOUSE_OK;
-  bond_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pos, (const int2 *)bond_atoms, (int)n, box[0],
-                                                                  box[1], box[2], vec, ctr);
+  mouse_grid_t gh;
+  memset(&gh, 0, sizeof(gh));
+  for (int a = 0; a < 3; ++a) {
+    gh.box[a] = box[a];
+    gh.cell_w[a] = box[a];
+    gh.ncell_axis[a] = 1;
+    gh.tilt[a] = tilt ? tilt[a] : 0.0;
+  }
+  gh.ncell = 1;
+  gh.triclinic = tilt ? 1 : 0;
+  bond_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pos, (const int2 *)bond_atoms, (int)n,
+                                                                  mouse_grid_dev(&gh), vec, ctr);
   MOUSE_LAUNCH_CHECK("bond_build_kernel");
   return MOUSE_OK;
 }
@@ -465,12 +587,17 @@ static int cell_build_tail(int mode, const uint8_t *ref_mask, int64_t n, const m
                            const Workspace &w, cudaStream_t st) {
   int nc = grid->ncell + 1;
   int tiles = (nc + MOUSE_SCAN_TILE - 1) / MOUSE_SCAN_TILE;
-  scan_reduce_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks);
-  MOUSE_LAUNCH_CHECK("scan_reduce_kernel");
-  if (tiles <= 4096) {   // the apply kernel sums the tile totals in front of its tile itself
+  if (tiles <= MOUSE_SCAN_FUSED_TILES) {   // one kernel; scan_blocks was zeroed together with the counters
+    scan_fused_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start);
+    MOUSE_LAUNCH_CHECK("scan_fused_kernel");
+  } else if (tiles <= 4096) {   // the apply kernel sums the tile totals in front of its tile itself
+    scan_reduce_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks);
+    MOUSE_LAUNCH_CHECK("scan_reduce_kernel");
     scan_apply2_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start);
     MOUSE_LAUNCH_CHECK("scan_apply2_kernel");
   } else {
+    scan_reduce_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks);
+    MOUSE_LAUNCH_CHECK("scan_reduce_kernel");
     scan_top_kernel<<<1, 1024, 0, st>>>(w.scan_blocks, tiles);
     MOUSE_LAUNCH_CHECK("scan_top_kernel");
     scan_apply_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start);
@@ -484,11 +611,11 @@ static int cell_build_tail(int mode, const uint8_t *ref_mask, int64_t n, const m
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
     if (mode == 0)
-      cell_canon_kernel<0><<<blocks, 256, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.rec_sorted,
+      cell_canon_kernel<0><<<blocks, 256, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.cell_of, w.rec_sorted,
                                                    w.idx_sorted, w.cell_sorted,
                                                    w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr);
     else
-      cell_canon_kernel<1><<<blocks, 256, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.rec_sorted,
+      cell_canon_kernel<1><<<blocks, 256, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.cell_of, w.rec_sorted,
                                                    w.idx_sorted, w.cell_sorted,
                                                    w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr);
     MOUSE_LAUNCH_CHECK("cell_canon_kernel");

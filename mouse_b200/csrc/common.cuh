@@ -49,7 +49,8 @@ struct Workspace {
   int32_t *scan_blocks;  // [scan_nblocks+1]
   int32_t *items;        // [ncell][40] item table of the half-shell sweeps (ranges of the 14 cells, see half_shell.cuh)
   // per item, original order
-  int32_t *cell_of;      // [n] cell id or -1 (not in the list)
+  int32_t *cell_of;      // [n] cell id or -1 (not in the list); after the build: sorted slot | reference bit << 30
+                         //     (inverse permutation, still -1 for items outside the list)
   int32_t *rank_of;      // [n] arrival rank inside the cell (atomic order, canonicalised later)
   // per item, cell-sorted (ascending original index inside a cell)
   Rec *rec_tmp;          // [n] payload in ORIGINAL order (built by the assign kernel, gathered by the canon kernel);
@@ -90,10 +91,10 @@ static inline Workspace mouse_carve(void *ws, int64_t n, int32_t ncell) {
 #define CARVE(field, type, count)                     \
   w.field = (type *)(base ? base + off : nullptr);    \
   off = mouse_align_up(off + sizeof(type) * (count), 256);
-  CARVE(counters, int64_t, 32)     // directly in front of cell_count: both are cleared by one memset
+  CARVE(counters, int64_t, 32)     // counters, scan_blocks and cell_count are adjacent: cleared by one memset
+  CARVE(scan_blocks, int32_t, nsb)
   CARVE(cell_count, int32_t, nc)
   CARVE(cell_start, int32_t, nc)
-  CARVE(scan_blocks, int32_t, nsb)
   CARVE(items, int32_t, 40 * nc)
   CARVE(cell_of, int32_t, nn)
   CARVE(rank_of, int32_t, nn)
@@ -125,6 +126,13 @@ struct GridDev {
   float boxf[3], inv_boxf[3];
   unsigned magic_x, magic_xy;   // floor(2^32 / nx), floor(2^32 / (nx * ny)): division-free cell index decoding
   float rc2_lo, rc2_hi;  // FP32 guard band: d2 < lo sure hit, d2 > hi sure miss
+  // triclinic boxes (all zero for an orthorhombic grid): tilt factors xy, xz, yz, their FP32 copies, the ratios
+  // xy/ly, xz/lz, yz/lz (fractional -> Cartesian) and the Cartesian centre of the cell H (1/2, 1/2, 1/2)
+  double tilt[3];
+  float tiltf[3];
+  float tratio[3];
+  double ctr_off[3];
+  int tri;
 };
 
 static inline GridDev mouse_grid_dev(const mouse_grid_t *g) {
@@ -144,6 +152,17 @@ static inline GridDev mouse_grid_dev(const mouse_grid_t *g) {
   double lo = g->rc2 * (1.0 - (double)g->guard), hi = g->rc2 * (1.0 + (double)g->guard);
   d.rc2_lo = nextafterf((float)lo, 0.0f);
   d.rc2_hi = nextafterf((float)hi, 3.0e38f);
+  d.tri = g->triclinic;
+  for (int a = 0; a < 3; ++a) {
+    d.tilt[a] = d.tri ? g->tilt[a] : 0.0;
+    d.tiltf[a] = (float)d.tilt[a];
+  }
+  d.tratio[0] = (float)(d.tilt[0] / g->box[1]);
+  d.tratio[1] = (float)(d.tilt[1] / g->box[2]);
+  d.tratio[2] = (float)(d.tilt[2] / g->box[2]);
+  d.ctr_off[0] = 0.5 * (g->box[0] + d.tilt[0] + d.tilt[1]);
+  d.ctr_off[1] = 0.5 * (g->box[1] + d.tilt[2]);
+  d.ctr_off[2] = 0.5 * g->box[2];
   return d;
 }
 
@@ -160,6 +179,28 @@ __device__ __forceinline__ double mouse_rsq_exact(double cix, double ciy, double
   double tx = mouse_trim(__dsub_rn(cjx, cix), box[0]);
   double ty = mouse_trim(__dsub_rn(cjy, ciy), box[1]);
   double tz = mouse_trim(__dsub_rn(cjz, ciz), box[2]);
+  return __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
+}
+
+// The same for a triclinic box (build-defined): brick representative, axis by axis from z to x; tilt = {xy, xz, yz}.
+// With tilt = 0 the three extra products vanish and the value is bit-identical to mouse_rsq_exact.
+__device__ __forceinline__ void mouse_min_image_tri(double &dx, double &dy, double &dz, const double *box,
+                                                    const double *tilt) {
+  const double nz = rint(__ddiv_rn(dz, box[2]));
+  dz = __dsub_rn(dz, __dmul_rn(box[2], nz));
+  dy = __dsub_rn(dy, __dmul_rn(tilt[2], nz));
+  dx = __dsub_rn(dx, __dmul_rn(tilt[1], nz));
+  const double ny = rint(__ddiv_rn(dy, box[1]));
+  dy = __dsub_rn(dy, __dmul_rn(box[1], ny));
+  dx = __dsub_rn(dx, __dmul_rn(tilt[0], ny));
+  const double nx = rint(__ddiv_rn(dx, box[0]));
+  dx = __dsub_rn(dx, __dmul_rn(box[0], nx));
+}
+__device__ __forceinline__ double mouse_rsq_exact_g(double cix, double ciy, double ciz, double cjx, double cjy,
+                                                    double cjz, const double *box, const double *tilt, int tri) {
+  if (!tri) return mouse_rsq_exact(cix, ciy, ciz, cjx, cjy, cjz, box);
+  double tx = __dsub_rn(cjx, cix), ty = __dsub_rn(cjy, ciy), tz = __dsub_rn(cjz, ciz);
+  mouse_min_image_tri(tx, ty, tz, box, tilt);
   return __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
 }
 

@@ -107,6 +107,21 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
 
+// Periodic image of (px, py, pz) nearest to the home cell centre h, in the brick sense (axis by axis from z to x; a
+// shift along an axis also removes the tilt components of the lattice vector from the lower axes).  FP32, un-fused.
+__device__ __forceinline__ void hs_nearest_image(float &px, float &py, float &pz, float hx, float hy, float hz,
+                                                 const GridDev &g) {
+  const float nz = rintf((pz - hz) * g.inv_boxf[2]);
+  pz -= g.boxf[2] * nz;
+  py -= g.tiltf[2] * nz;
+  px -= g.tiltf[1] * nz;
+  const float ny = rintf((py - hy) * g.inv_boxf[1]);
+  py -= g.boxf[1] * ny;
+  px -= g.tiltf[0] * ny;
+  const float nx = rintf((px - hx) * g.inv_boxf[0]);
+  px -= g.boxf[0] * nx;
+}
+
 // fetch stage 2: start the (asynchronous) copy of home cell tk's item row into s_raw
 __device__ __forceinline__ void hs_raw_issue(const int32_t *__restrict__ items, int lane, int tk, int *s_raw) {
   if (lane < HS_ITEM_INTS / 4) cp_async16(s_raw + 4 * lane, items + (size_t)tk * HS_ITEM_INTS + 4 * lane);
@@ -130,9 +145,13 @@ __device__ __forceinline__ bool hs_finalize(const GridDev &g, int lane, int tk, 
   it.rsrc = src;
   it.rlen = len;
   it.rt = rt;
-  it.hx = ((float)cx + 0.5f) * g.cwf[0] - 0.5f * g.boxf[0];
-  it.hy = ((float)cy + 0.5f) * g.cwf[1] - 0.5f * g.boxf[1];
-  it.hz = ((float)cz + 0.5f) * g.cwf[2] - 0.5f * g.boxf[2];
+  // cell centre along the lattice directions, then Cartesian (the tilt ratios are 0 for an orthorhombic box)
+  const float ux = ((float)cx + 0.5f) * g.cwf[0] - 0.5f * g.boxf[0];
+  const float uy = ((float)cy + 0.5f) * g.cwf[1] - 0.5f * g.boxf[1];
+  const float uz = ((float)cz + 0.5f) * g.cwf[2] - 0.5f * g.boxf[2];
+  it.hx = ux + g.tratio[0] * uy + g.tratio[1] * uz;
+  it.hy = uy + g.tratio[2] * uz;
+  it.hz = uz;
   it.boundary = (packed >> 30) & 1;
   return nhome > 0;
 }

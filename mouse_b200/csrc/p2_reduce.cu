@@ -123,12 +123,10 @@ __global__ void __launch_bounds__(RED_THREADS) p2_reduce_kernel(
 // sorted slot) are converted, written to out_sum / out_cnt / out_mean in original bond order (the next frame build zeroes them again),
 // and reduced to the totals in the same pass.  Deterministic: fixed slot ranges per block, fixed trees.
 struct FinishArgs {
-  long long *acc_fix;
-  int32_t *acc_cnt;
-  const int32_t *idx;
-  const uint8_t *flag;
-  const int32_t *cell_start;
-  int ncell;
+  const long long *acc_fix;
+  const int32_t *acc_cnt;
+  const int32_t *slot_of;   // [n] original index -> sorted slot | reference bit << 30, or -1 (not in the cell list)
+  int n;
   int chunk;
   double *out_sum;
   int32_t *out_cnt;
@@ -144,54 +142,56 @@ __global__ void __launch_bounds__(RED_THREADS) p2_finish_reduce_kernel(const Fin
   __shared__ bool s_last;
   const bool overflow = ((volatile int64_t *)a.counters)[4] != 0;   // the exact sweep wrote out_sum / out_cnt
   const long long nzero = a.counters[0];
-  const int n_list = a.cell_start[a.ncell];
   const int lo = blockIdx.x * a.chunk;
-  const int hi = min(n_list, lo + a.chunk);
-  long long *__restrict__ acc_fix = a.acc_fix;
-  int32_t *__restrict__ acc_cnt = a.acc_cnt;
-  const int32_t *__restrict__ idx = a.idx;
-  const uint8_t *__restrict__ flag = a.flag;
+  const int hi = min(a.n, lo + a.chunk);
+  const long long *__restrict__ acc_fix = a.acc_fix;
+  const int32_t *__restrict__ acc_cnt = a.acc_cnt;
+  const int32_t *__restrict__ slot_of = a.slot_of;
   double acc = 0.0;
   long long refs = 0, pairs = 0;
-  // four slots per thread and trip, all loads up front (memory-level parallelism)
-  for (int s0 = lo + threadIdx.x; s0 < hi; s0 += 4 * RED_THREADS) {
+  // Original bond order: the stores are coalesced, the accumulators are gathered through the inverse permutation
+  // (they were last touched by the sweep's atomics, i.e. they sit in L2).  Four bonds per thread and trip, all
+  // loads up front (memory-level parallelism).
+  for (int b0 = lo + threadIdx.x; b0 < hi; b0 += 4 * RED_THREADS) {
+    int v[4];
     long long fix[4];
-    int c[4], o[4];
-    bool isref[4];
+    int c[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int s = s0 + q * RED_THREADS;
-      const bool in = s < hi;
-      fix[q] = in ? acc_fix[s] : 0;
-      c[q] = in ? acc_cnt[s] : 0;
-      o[q] = in ? idx[s] : 0;
-      isref[q] = in && (flag[s] & 1);
+      const int b = b0 + q * RED_THREADS;
+      v[q] = b < hi ? slot_of[b] : -1;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int s = v[q] & 0x3fffffff;
+      fix[q] = v[q] >= 0 ? acc_fix[s] : 0;
+      c[q] = v[q] >= 0 ? acc_cnt[s] : 0;
     }
     // (the accumulators are NOT re-zeroed here: every frame build zeroes them in cell_canon_kernel)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int s = s0 + q * RED_THREADS;
-      if (s >= hi) continue;
+      const int b = b0 + q * RED_THREADS;
+      if (v[q] < 0) continue;              // not in the cell list: the build wrote 0 / 0 / NaN
       const double nan = __longlong_as_double(0x7ff8000000000000LL);
-      if (!isref[q]) {                     // listed, but not a reference: 0 / 0 / NaN
-        a.out_sum[o[q]] = 0.0;
-        a.out_cnt[o[q]] = 0;
-        a.out_mean[o[q]] = nan;
+      if (!((v[q] >> 30) & 1)) {           // listed, but not a reference: 0 / 0 / NaN
+        a.out_sum[b] = 0.0;
+        a.out_cnt[b] = 0;
+        a.out_mean[b] = nan;
         continue;
       }
       double sum;
       int cc = c[q];
       if (overflow) {
-        sum = a.out_sum[o[q]];
-        cc = a.out_cnt[o[q]];
+        sum = a.out_sum[b];
+        cc = a.out_cnt[b];
       } else {
         sum = (double)fix[q] * 7.105427357601002e-15;   // 2^-47
         if (nzero) {   // zero-length bonds poison every mean and add to every count (ordering_functions.py:112)
           sum = __longlong_as_double(0x7ff8000000000000LL);
           cc += (int)nzero;
         }
-        a.out_sum[o[q]] = sum;
-        a.out_cnt[o[q]] = cc;
+        a.out_sum[b] = sum;
+        a.out_cnt[b] = cc;
       }
       double m = nan;
       if (cc > 0) {
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(RED_THREADS) p2_finish_reduce_kernel(const Fin
         refs += 1;
         pairs += cc;
       }
-      a.out_mean[o[q]] = m;
+      a.out_mean[b] = m;
     }
   }
   acc = warp_sum(acc);
@@ -272,10 +272,9 @@ int mouse_launch_p2_finish_reduce(int64_t n, const mouse_grid_t *grid, const Wor
   FinishArgs a;
   a.acc_fix = w.acc_fix;
   a.acc_cnt = w.acc_cnt;
-  a.idx = w.idx_sorted;
-  a.flag = w.flag_sorted;
-  a.cell_start = w.cell_start;
-  a.ncell = grid->ncell;
+  a.slot_of = w.cell_of;
+  a.n = (int)n;
+  (void)grid;
   int blocks = (int)((n + RED_THREADS - 1) / RED_THREADS);
   if (blocks > MOUSE_REDUCE_BLOCKS) blocks = MOUSE_REDUCE_BLOCKS;
   if (blocks < 1) blocks = 1;

@@ -65,10 +65,12 @@ struct SweepArgs {
 // cos^2 exactly as ordering_functions.py:95-113 evaluates it, or 0.0 when the pair is not counted
 // (out of range, or cos^2 == 0 which the reference masks).
 __device__ __forceinline__ double exact_pair(const int32_t *__restrict__ idx, const double *__restrict__ ctr,
-                                             const double *__restrict__ vec, size_t n, const double *box, double rc2,
-                                             int si, int sj) {
+                                             const double *__restrict__ vec, size_t n, const GridDev &g, int si,
+                                             int sj) {
   const int bi = idx[si], bj = idx[sj];
-  const double rsq = mouse_rsq_exact(ctr[bi], ctr[n + bi], ctr[2 * n + bi], ctr[bj], ctr[n + bj], ctr[2 * n + bj], box);
+  const double rc2 = g.rc2;
+  const double rsq = mouse_rsq_exact_g(ctr[bi], ctr[n + bi], ctr[2 * n + bi], ctr[bj], ctr[n + bj], ctr[2 * n + bj],
+                                       g.box, g.tilt, g.tri);
   if (!(rsq <= rc2)) return 0.0;
   const double ax = vec[bi], ay = vec[n + bi], az = vec[2 * n + bi];
   const double bx = vec[bj], by = vec[n + bj], bz = vec[2 * n + bj];
@@ -325,12 +327,8 @@ __device__ __forceinline__ int hs_cull(uint32_t land, uint32_t sel, const float 
     float4 p = lds_float4(pa), q = lds_float4(pa + 32u * 48u);
     if (BND) {
       const float hx = bb[0], hy = bb[1], hz = bb[2];
-      p.x -= g.boxf[0] * rintf((p.x - hx) * g.inv_boxf[0]);
-      p.y -= g.boxf[1] * rintf((p.y - hy) * g.inv_boxf[1]);
-      p.z -= g.boxf[2] * rintf((p.z - hz) * g.inv_boxf[2]);
-      q.x -= g.boxf[0] * rintf((q.x - hx) * g.inv_boxf[0]);
-      q.y -= g.boxf[1] * rintf((q.y - hy) * g.inv_boxf[1]);
-      q.z -= g.boxf[2] * rintf((q.z - hz) * g.inv_boxf[2]);
+      hs_nearest_image(p.x, p.y, p.z, hx, hy, hz, g);
+      hs_nearest_image(q.x, q.y, q.z, hx, hy, hz, g);
       sts_float4(pa, p);
       sts_float4(pa + 32u * 48u, q);
     }
@@ -592,7 +590,7 @@ __global__ void __launch_bounds__(256) p2_fixup_kernel(const SweepArgs a) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nfix; e += (long long)gridDim.x * blockDim.x) {
     const int2 pr = a.fix_list[e];
     const int si = pr.x & 0x7fffffff, sj = pr.y, kind = (unsigned)pr.x >> 31;
-    const double cs = exact_pair(a.idx, a.ctr, a.vec, n, a.g.box, a.g.rc2, si, sj);
+    const double cs = exact_pair(a.idx, a.ctr, a.vec, n, a.g, si, sj);
     if (kind == 0) {
       if (cs != 0.0) {
         const unsigned long long f = (unsigned long long)__double2ll_rn(cs * HS_FIX_SCALE);
@@ -669,7 +667,8 @@ __global__ void __launch_bounds__(128) p2_sweep_exact_kernel(const SweepArgs a) 
             if (!a.same_molecule && __float_as_int(a.R[t].p.w) == moli) continue;
             const int bj = a.idx[t];
             if (!a.no_cutoff) {
-              double rsq = mouse_rsq_exact(cix, ciy, ciz, a.ctr[bj], a.ctr[n + bj], a.ctr[2 * n + bj], a.g.box);
+              double rsq = mouse_rsq_exact_g(cix, ciy, ciz, a.ctr[bj], a.ctr[n + bj], a.ctr[2 * n + bj], a.g.box,
+                                             a.g.tilt, a.g.tri);
               if (!(rsq <= a.g.rc2)) continue;
             }
             const double bjx = a.vec[bj], bjy = a.vec[n + bj], bjz = a.vec[2 * n + bj];

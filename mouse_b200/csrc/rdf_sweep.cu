@@ -62,9 +62,14 @@ __global__ void __launch_bounds__(128) rdf_sweep_exact_kernel(const RdfArgs a) {
             if (t == s) continue;
             const double4 pj = a.R[t].u;
             if (!a.same_molecule && pj.w == pi.w) continue;
-            const double tx = mouse_trim(__dsub_rn(pj.x, pi.x), Lx);
-            const double ty = mouse_trim(__dsub_rn(pj.y, pi.y), Ly);
-            const double tz = mouse_trim(__dsub_rn(pj.z, pi.z), Lz);
+            double tx = __dsub_rn(pj.x, pi.x), ty = __dsub_rn(pj.y, pi.y), tz = __dsub_rn(pj.z, pi.z);
+            if (a.g.tri) {
+              mouse_min_image_tri(tx, ty, tz, a.g.box, a.g.tilt);
+            } else {
+              tx = mouse_trim(tx, Lx);
+              ty = mouse_trim(ty, Ly);
+              tz = mouse_trim(tz, Lz);
+            }
             const double d = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz)));
             if (d == 0.0) continue;  // np.ma.masked_equal(d, 0.) also drops coincident atoms (:84)
             const int k = np_bin(d, first, last, a.nbin, a.edges);
@@ -244,7 +249,6 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
       phase ^= 1u;
       float2 xr2[NPAIR], yr2[NPAIR], zr2[NPAIR];
       {
-        const float Lxf = a.g.boxf[0], Lyf = a.g.boxf[1], Lzf = a.g.boxf[2];
 #pragma unroll
         for (int pp = 0; pp < NPAIR; ++pp) {
           float q[2][3];
@@ -253,11 +257,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
             const int tl = 32 * (2 * pp + h) + lane;
             const float4 p = s_land[tl].p;
             float px = p.x, py = p.y, pz = p.z;
-            if (bnd) {     // nearest periodic image to the home cell centre
-              px -= Lxf * rintf((px - cur.hx) * a.g.inv_boxf[0]);
-              py -= Lyf * rintf((py - cur.hy) * a.g.inv_boxf[1]);
-              pz -= Lzf * rintf((pz - cur.hz) * a.g.inv_boxf[2]);
-            }
+            if (bnd) hs_nearest_image(px, py, pz, cur.hx, cur.hy, cur.hz, a.g);   // nearest image to the home cell centre
             const bool valid = tl < nvalid;
             q[h][0] = valid ? px : 1.0e18f;
             q[h][1] = valid ? py : 1.0e18f;
@@ -298,9 +298,13 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
           // dr - L * around(dr / L): around() is 0 whenever |dr| <= L / 2 (ordering_functions.py:72-74); one
           // rare branch for coordinates that were not wrapped into the box
           if (!(fabs(tx) <= hLx && fabs(ty) <= hLy && fabs(tz) <= hLz)) {
-            tx = mouse_trim(tx, Lx);
-            ty = mouse_trim(ty, Ly);
-            tz = mouse_trim(tz, Lz);
+            if (a.g.tri) {      // (inside the brick the triclinic minimum image is the identity, too)
+              mouse_min_image_tri(tx, ty, tz, a.g.box, a.g.tilt);
+            } else {
+              tx = mouse_trim(tx, Lx);
+              ty = mouse_trim(ty, Ly);
+              tz = mouse_trim(tz, Lz);
+            }
           }
           const double s = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
           // np.ma.masked_equal(d, 0.) drops coincident atoms (:84); values outside [first, last] are dropped (:86)

@@ -116,10 +116,11 @@ def half_diagonal(box) -> float:
 
 def p2_frame(positions, bond_atoms, mol, box, rcut, same_molecule=True, nbr_mask=None, ref_mask=None,
              exact=False, hist_args=None, device=None, out: P2Result | None = None, slots=0, warps=0,
-             private_workspace=False, force_fast=False) -> P2Result:
+             private_workspace=False, force_fast=False, tilt=None) -> P2Result:
     """K1 -> K4 for one frame.  ``positions`` (N_a,3) f64, ``bond_atoms`` (N_b,2) i32 (atom1 ->
     atom2 direction, 0-based), ``mol`` (N_b,) i32 molecule code of atom1 of each bond,
     masks (N_b,) uint8/bool or None.  ``rcut < 0`` means no cutoff (reference ``:102-103``).
+    ``tilt`` = (xy, xz, yz): triclinic box (build-defined semantics, see ``include/mouse_b200.h``).
     ``slots`` / ``warps`` / ``force_fast``: tuning fields of the C-ABI flags (tests); ``private_workspace``: the result owns its
     workspace (needed when ``p2_pair_lists`` is not called right away)."""
     require_cuda()
@@ -130,7 +131,7 @@ def p2_frame(positions, bond_atoms, mol, box, rcut, same_molecule=True, nbr_mask
     molc = as_dev(mol, torch.int32, device) if mol is not None else torch.zeros(n, dtype=torch.int32, device=device)
     nbr = as_dev(nbr_mask, torch.uint8, device)
     ref = as_dev(ref_mask, torch.uint8, device)
-    grid = _lib.grid_plan(box, float(rcut), n)
+    grid = _lib.grid_plan(box, float(rcut), n, tilt=tilt)
     L = _lib.lib()
     nbytes = L.mouse_workspace_bytes(n, C.byref(grid))
     if private_workspace:
@@ -158,8 +159,13 @@ def p2_frame(positions, bond_atoms, mol, box, rcut, same_molecule=True, nbr_mask
         smin, smax, sbins = hist_args
         out.hist = torch.zeros(int(sbins), dtype=torch.int64, device=device)
         box3 = (C.c_double * 3)(*[float(b) for b in box])
-        _lib.check(L.mouse_bond_build(_ptr(pos), _ptr(bonds), n, box3, _ptr(out.vec), _ptr(out.ctr), st),
-                   "mouse_bond_build")
+        if tilt is None:
+            _lib.check(L.mouse_bond_build(_ptr(pos), _ptr(bonds), n, box3, _ptr(out.vec), _ptr(out.ctr), st),
+                       "mouse_bond_build")
+        else:
+            tilt3 = (C.c_double * 3)(*[float(t) for t in tilt])
+            _lib.check(L.mouse_bond_build_triclinic(_ptr(pos), _ptr(bonds), n, box3, tilt3, _ptr(out.vec),
+                                                    _ptr(out.ctr), st), "mouse_bond_build_triclinic")
         _lib.check(L.mouse_cell_build(_ptr(out.vec), _ptr(out.ctr), _ptr(molc), _ptr(nbr), _ptr(ref), n,
                                       C.byref(grid), _ptr(ws), ws.numel(), st), "mouse_cell_build")
         _lib.check(L.mouse_p2_sweep(_ptr(out.vec), _ptr(out.ctr), n, C.byref(grid), flags, _ptr(ws), ws.numel(),
@@ -202,7 +208,7 @@ def p2_pair_lists(res: P2Result, same_molecule=True, exact=False, rcut=None):
     return row_ptr, nbr
 
 
-def bond_build(positions, bond_atoms, box, device=None):
+def bond_build(positions, bond_atoms, box, device=None, tilt=None):
     """K1 alone: (vec, ctr) as (3, N_b) f64 device tensors."""
     require_cuda()
     device = torch.device(device or "cuda")
@@ -212,12 +218,18 @@ def bond_build(positions, bond_atoms, box, device=None):
     vec = torch.empty((3, n), dtype=torch.float64, device=device)
     ctr = torch.empty((3, n), dtype=torch.float64, device=device)
     box3 = (C.c_double * 3)(*[float(b) for b in box])
-    _lib.check(_lib.lib().mouse_bond_build(_ptr(pos), _ptr(bonds), n, box3, _ptr(vec), _ptr(ctr), _stream()),
-               "mouse_bond_build")
+    if tilt is None:
+        _lib.check(_lib.lib().mouse_bond_build(_ptr(pos), _ptr(bonds), n, box3, _ptr(vec), _ptr(ctr), _stream()),
+                   "mouse_bond_build")
+    else:
+        tilt3 = (C.c_double * 3)(*[float(t) for t in tilt])
+        _lib.check(_lib.lib().mouse_bond_build_triclinic(_ptr(pos), _ptr(bonds), n, box3, tilt3, _ptr(vec), _ptr(ctr),
+                                                         _stream()), "mouse_bond_build_triclinic")
     return vec, ctr
 
 
-def rdf_frame(positions, type_code, mol, ntypes, box, rmin, rmax, nbin, same_molecule=True, device=None, exact=False):
+def rdf_frame(positions, type_code, mol, ntypes, box, rmin, rmax, nbin, same_molecule=True, device=None, exact=False,
+              tilt=None):
     """K5: int64 histogram [ntypes*(ntypes+1)/2, nbin] over ordered pairs, NumPy bin edges.  ``exact`` forces the
     all-FP64 one-thread-per-atom kernel (the default picks the half-shell sweep whenever the grid allows it)."""
     require_cuda()
@@ -229,7 +241,7 @@ def rdf_frame(positions, type_code, mol, ntypes, box, rmin, rmax, nbin, same_mol
     edges = np.ascontiguousarray(np.histogram_bin_edges(np.zeros(0), bins=int(nbin), range=(rmin, rmax)),
                                  dtype=np.float64)
     rcell = float(edges[-1])
-    grid = _lib.grid_plan(box, rcell, n)
+    grid = _lib.grid_plan(box, rcell, n, tilt=tilt)
     L = _lib.lib()
     ws = workspace(L.mouse_workspace_bytes(n, C.byref(grid)), device)
     npairs = ntypes * (ntypes + 1) // 2

@@ -122,3 +122,19 @@ def write_lammps_data(melt: Melt, path: str) -> None:
         for b in range(melt.n_bonds):
             a1, a2 = melt.bond_atoms[b]
             f.write("%d %s %d %d\n" % (b + 1, melt.bond_type_names[melt.bond_type[b]], a1 + 1, a2 + 1))
+
+
+def tilt_melt(melt: Melt, tilt) -> np.ndarray:
+    """Positions of ``melt`` re-wrapped into the triclinic cell with the same edge lengths and tilt factors
+    ``tilt`` = (xy, xz, yz) (LAMMPS convention a = (lx,0,0), b = (xy,ly,0), c = (xz,yz,lz)): the chains are taken as
+    grown (unwrapped) and every atom is mapped to fractional coordinates in [0, 1), so bonds cross the tilted faces."""
+    lx, ly, lz = (float(v) for v in melt.box)
+    xy, xz, yz = (float(v) for v in tilt)
+    p = melt.positions + melt.images * melt.box
+    sz = p[:, 2] / lz
+    sy = (p[:, 1] - yz * sz) / ly
+    sx = (p[:, 0] - xy * sy - xz * sz) / lx
+    s = np.stack([sx, sy, sz], axis=1)
+    s -= np.floor(s)
+    return np.ascontiguousarray(np.stack([s[:, 0] * lx + s[:, 1] * xy + s[:, 2] * xz, s[:, 1] * ly + s[:, 2] * yz,
+                                          s[:, 2] * lz], axis=1))

@@ -78,7 +78,7 @@ class FramePipeline:
     until the slot is reused."""
 
     def __init__(self, bond_atoms, mol, box, rcut, n_atoms, same_molecule=True, nbr_mask=None, ref_mask=None,
-                 device=None, depth=3):
+                 device=None, depth=3, use_graph=True, tilt=None):
         engine.require_cuda()
         self.device = torch.device(device or "cuda")
         self.n_atoms = int(n_atoms)
@@ -90,12 +90,14 @@ class FramePipeline:
         self.ref = engine.as_dev(ref_mask, torch.uint8, self.device)
         self.box = [float(b) for b in box]
         self.rcut = float(rcut)
-        self.grid = _lib.grid_plan(self.box, self.rcut, self.n)
+        self.tilt = None if tilt is None else [float(t) for t in tilt]
+        self.grid = _lib.grid_plan(self.box, self.rcut, self.n, tilt=self.tilt)
         self.flags = (_lib.MOUSE_SAME_MOLECULE if same_molecule else 0) | (_lib.MOUSE_NO_CUTOFF if rcut < 0 else 0)
         L = _lib.lib()
         self.L = L
         nbytes = L.mouse_workspace_bytes(self.n, C.byref(self.grid))
         self.depth = depth
+        self.use_graph = bool(use_graph)     # frames with the pipeline's own box / cutoff replay a captured CUDA graph
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.slots = []
         for _ in range(depth):
@@ -116,7 +118,9 @@ class FramePipeline:
         self._pending = []
         self.h2d_bytes_per_frame = self.n_atoms * 3 * 8
         self.d2h_bytes_per_frame = 48
-        self.kernels_per_frame = 9   # bond_assign, 2 x scan, scatter_idx, canon, sweep, fixup, exact check, finish+reduce
+        self.kernels_per_frame = 8   # bond_assign, scan, scatter_idx, canon, sweep, fixup, exact check, finish+reduce
+        self.host_submit_s = 0.0     # wall time spent inside submit() (enqueue cost of the host side)
+        self.frames_submitted = 0
 
     def submit(self, positions_host, tag=None, box=None, rcut=None):
         """Enqueue one frame.  ``positions_host``: (N_a,3) f64 - a pinned CPU tensor is copied asynchronously as it
@@ -125,18 +129,26 @@ class FramePipeline:
         the ``tag`` it was submitted with) that had to be collected to free a slot.  ``box`` / ``rcut``: this
         frame's own box and cutoff (NPT dumps): the cell grid is re-planned for the frame, the slot's workspace
         grows if the new grid needs it."""
+        import time
+        t_enter = time.perf_counter()
         out = []
         s = self.slots[self._next]
         if s["busy"]:
             out.append(self._collect(s))
+            t_enter = time.perf_counter()      # waiting for the GPU is not enqueue cost
         s["tag"] = tag
         grid, flags = self.grid, self.flags
-        if box is not None or rcut is not None:
+        own_grid = box is not None or rcut is not None
+        if own_grid:
             rc = self.rcut if rcut is None else float(rcut)
-            grid = _lib.grid_plan(self.box if box is None else [float(b) for b in box], rc, self.n)
+            grid = _lib.grid_plan(self.box if box is None else [float(b) for b in box], rc, self.n, tilt=self.tilt)
             flags = (self.flags & ~_lib.MOUSE_NO_CUTOFF) | (_lib.MOUSE_NO_CUTOFF if rc < 0 else 0)
             need = self.L.mouse_workspace_bytes(self.n, C.byref(grid))
             if s["ws"].numel() < need:
+                s["done"].synchronize()
+                if s.get("graph") is not None:      # the captured graph names the old buffer
+                    self.L.mouse_p2_frame_graph_destroy(s["graph"])
+                    s["graph"] = None
                 s["ws"] = torch.empty(int(need * 1.1) + 4096, dtype=torch.uint8, device=self.device)
                 assert s["ws"].data_ptr() % 256 == 0
         s["grid"] = grid     # keeps the ctypes struct alive until the call below has returned
@@ -155,15 +167,24 @@ class FramePipeline:
         with torch.cuda.stream(s["stream"]):
             s["stream"].wait_event(s["copied"])
             st = C.c_void_p(s["stream"].cuda_stream)
-            _lib.check(self.L.mouse_p2_frame(p(s["pos"]), p(self.bonds), p(self.mol), p(self.nbr), p(self.ref), self.n,
-                                             C.byref(grid), flags, p(s["ws"]), s["ws"].numel(), p(s["vec"]),
-                                             p(s["ctr"]), p(s["sum"]), p(s["cnt"]), p(s["mean"]), p(s["totals"]), st),
-                       "mouse_p2_frame")
+            args = (p(s["pos"]), p(self.bonds), p(self.mol), p(self.nbr), p(self.ref), self.n, C.byref(grid), flags,
+                    p(s["ws"]), s["ws"].numel(), p(s["vec"]), p(s["ctr"]), p(s["sum"]), p(s["cnt"]), p(s["mean"]),
+                    p(s["totals"]))
+            if self.use_graph and not own_grid and self.n > 0:
+                if s.get("graph") is None:      # recorded once per slot: the slot's buffers never change
+                    h = C.c_void_p()
+                    _lib.check(self.L.mouse_p2_frame_graph_create(*args, C.byref(h)), "mouse_p2_frame_graph_create")
+                    s["graph"] = h
+                _lib.check(self.L.mouse_p2_frame_graph_launch(s["graph"], st), "mouse_p2_frame_graph_launch")
+            else:
+                _lib.check(self.L.mouse_p2_frame(*args, st), "mouse_p2_frame")
             s["totals_host"].copy_(s["totals"], non_blocking=True)
             s["done"].record(s["stream"])
         s["busy"] = True
         self._pending.append(s)
         self._next = (self._next + 1) % self.depth
+        self.host_submit_s += time.perf_counter() - t_enter
+        self.frames_submitted += 1
         return out
 
     def _collect(self, s):
@@ -177,6 +198,23 @@ class FramePipeline:
 
     def drain(self):
         return [self._collect(s) for s in list(self._pending)]
+
+    def close(self):
+        """Waits for the frames in flight and frees the captured graphs."""
+        self.drain()
+        for s in self.slots:
+            if s.get("graph") is not None:
+                self.L.mouse_p2_frame_graph_destroy(s["graph"])
+                s["graph"] = None
+
+    def __del__(self):
+        try:
+            for s in self.slots:
+                if s.get("graph") is not None:
+                    self.L.mouse_p2_frame_graph_destroy(s["graph"])
+                    s["graph"] = None
+        except Exception:
+            pass
 
 
 def local_ordering_trajectory(frames_positions, bond_atoms, mol, box, rcut, same_molecule=True, nbr_mask=None,

@@ -31,6 +31,52 @@ static double np_remainder(double a, double b) {
   return m;
 }
 
+/* ---- triclinic boxes: BUILD-DEFINED semantics, parity unpinned (the reference is orthorhombic only,
+ * lammpack_types.py:440-451 reads no tilt factors).  LAMMPS convention: a = (lx,0,0), b = (xy,ly,0), c = (xz,yz,lz),
+ * tilt = {xy, xz, yz}.  The minimum image of a displacement is its representative in the brick |dx| <= lx/2,
+ * |dy| <= ly/2, |dz| <= lz/2, found axis by axis from z to x with the reference's own `dr - L*around(dr/L)` step;
+ * the tilt components of the subtracted lattice vector are removed from the lower axes.  With tilt = 0 every
+ * expression below reduces bit for bit to the orthorhombic one. */
+static inline void tri_min_image(double *dx, double *dy, double *dz, const double *box, const double *tilt) {
+  double nz = rint(*dz / box[2]);
+  *dz = *dz - box[2] * nz;
+  *dy = *dy - tilt[2] * nz;
+  *dx = *dx - tilt[1] * nz;
+  double ny = rint(*dy / box[1]);
+  *dy = *dy - box[1] * ny;
+  *dx = *dx - tilt[0] * ny;
+  double nx = rint(*dx / box[0]);
+  *dx = *dx - box[0] * nx;
+}
+
+/* bond vector / midpoint, triclinic: the np.remainder form of lammpack_types.py:587-599 axis by axis from z to x */
+void mo_bond_build_tri(const double *pos, const int32_t *bonds, int64_t n_bonds, const double *box,
+                       const double *tilt, double *vec, double *ctr) {
+#pragma omp parallel for schedule(static)
+  for (int64_t b = 0; b < n_bonds; ++b) {
+    const double *p1 = pos + 3 * (int64_t)bonds[2 * b];
+    const double *p2 = pos + 3 * (int64_t)bonds[2 * b + 1];
+    double x[3], xc[3], w[3], t[3];
+    for (int a = 0; a < 3; ++a) {
+      x[a] = p2[a] - p1[a];
+      xc[a] = (p2[a] + p1[a]) / 2.;
+      w[a] = x[a];
+    }
+    t[2] = np_remainder(w[2] + box[2] / 2., box[2]) - box[2] / 2.;
+    double nz = rint((w[2] - t[2]) / box[2]);
+    w[1] = w[1] - tilt[2] * nz;
+    w[0] = w[0] - tilt[1] * nz;
+    t[1] = np_remainder(w[1] + box[1] / 2., box[1]) - box[1] / 2.;
+    double ny = rint((w[1] - t[1]) / box[1]);
+    w[0] = w[0] - tilt[0] * ny;
+    t[0] = np_remainder(w[0] + box[0] / 2., box[0]) - box[0] / 2.;
+    for (int a = 0; a < 3; ++a) {
+      vec[3 * b + a] = t[a];
+      ctr[3 * b + a] = xc[a] + (t[a] - x[a]) / 2.;
+    }
+  }
+}
+
 /* lammpack_types.py:587-599; pos (n_atoms,3), bonds (n_bonds,2) 0-based, out vec/ctr (n_bonds,3) */
 void mo_bond_build(const double *pos, const int32_t *bonds, int64_t n_bonds, const double *box,
                    double *vec, double *ctr) {
@@ -65,11 +111,22 @@ static int cell_axis(double c, double L, double w, int n) {
   return k >= n ? n - 1 : k;
 }
 
-static int cells_build(cells_t *g, const double *xyz, int64_t n, const double *box, double rc) {
+/* perpendicular widths of a triclinic box along a, b, c (distance between opposite faces) */
+static void tri_widths(const double *box, const double *tilt, double *w) {
+  double lx = box[0], ly = box[1], lz = box[2], xy = tilt[0], xz = tilt[1], yz = tilt[2];
+  double bcx = ly * lz, bcy = -xy * lz, bcz = xy * yz - ly * xz; /* b x c */
+  w[0] = lx * ly * lz / sqrt(bcx * bcx + bcy * bcy + bcz * bcz);
+  w[1] = ly * lz / sqrt(lz * lz + yz * yz);                      /* V / |a x c| */
+  w[2] = lz;
+}
+
+static int cells_build_t(cells_t *g, const double *xyz, int64_t n, const double *box, const double *tilt, double rc) {
+  double wid[3] = {box[0], box[1], box[2]};
+  if (tilt) tri_widths(box, tilt, wid);
   for (int a = 0; a < 3; ++a) {
     int k = 1;
     if (rc > 0.0) {
-      double q = box[a] / (rc * (1.0 + 1e-6));
+      double q = wid[a] / (rc * (1.0 + 1e-6));
       k = q >= 1.0 ? (q > 512.0 ? 512 : (int)q) : 1;
     }
     g->n[a] = k;
@@ -81,9 +138,16 @@ static int cells_build(cells_t *g, const double *xyz, int64_t n, const double *b
   int64_t *cid = (int64_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int64_t));
   if (!g->start || !g->items || !cid) return 1;
   for (int64_t i = 0; i < n; ++i) {
-    int cx = cell_axis(xyz[3 * i], box[0], g->w[0], g->n[0]);
-    int cy = cell_axis(xyz[3 * i + 1], box[1], g->w[1], g->n[1]);
-    int cz = cell_axis(xyz[3 * i + 2], box[2], g->w[2], g->n[2]);
+    double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    if (tilt) { /* fractional coordinates times the edge length: cells are parallelepipeds of the lattice */
+      double sz = z / box[2];
+      double sy = (y - tilt[2] * sz) / box[1];
+      double sx = (x - tilt[0] * sy - tilt[1] * sz) / box[0];
+      x = sx * box[0], y = sy * box[1], z = sz * box[2];
+    }
+    int cx = cell_axis(x, box[0], g->w[0], g->n[0]);
+    int cy = cell_axis(y, box[1], g->w[1], g->n[1]);
+    int cz = cell_axis(z, box[2], g->w[2], g->n[2]);
     cid[i] = ((int64_t)cz * g->n[1] + cy) * g->n[0] + cx;
     g->start[cid[i] + 1]++;
   }
@@ -94,6 +158,10 @@ static int cells_build(cells_t *g, const double *xyz, int64_t n, const double *b
   free(cur);
   free(cid);
   return 0;
+}
+
+static int cells_build(cells_t *g, const double *xyz, int64_t n, const double *box, double rc) {
+  return cells_build_t(g, xyz, n, box, NULL, rc);
 }
 
 static void cells_free(cells_t *g) {
@@ -127,11 +195,12 @@ static int cmp_i64(const void *a, const void *b) {
  * *nbr_idx (free with mo_free).  Zero-length reference bonds are skipped (count 0); zero-length
  * neighbour bonds poison every mean with NaN and add to every count (0/0 in the reference).
  */
-int mo_p2(const double *vec, const double *ctr, const int64_t *mol, const uint8_t *ref_mask,
-          const uint8_t *nbr_mask, int64_t n, const double *box, double rcut, double rc2,
-          int same_molecule, double *out_sum, int64_t *out_cnt, int64_t *nbr_ptr, int64_t **nbr_idx) {
+static int mo_p2_impl(const double *vec, const double *ctr, const int64_t *mol, const uint8_t *ref_mask,
+                      const uint8_t *nbr_mask, int64_t n, const double *box, const double *tilt, double rcut,
+                      double rc2, int same_molecule, double *out_sum, int64_t *out_cnt, int64_t *nbr_ptr,
+                      int64_t **nbr_idx) {
   cells_t g;
-  if (cells_build(&g, ctr, n, box, rcut)) return 1;
+  if (cells_build_t(&g, ctr, n, box, tilt, rcut)) return 1;
   int64_t n_zero_nbr = 0;
   uint8_t *zero = (uint8_t *)malloc((size_t)(n > 0 ? n : 1));
   for (int64_t i = 0; i < n; ++i) {
@@ -175,9 +244,15 @@ int mo_p2(const double *vec, const double *ctr, const int64_t *mol, const uint8_
                 if (!same_molecule && mol[j] == mol[i]) continue;
                 if (rcut >= 0.0) {
                   double drx = ctr[3 * j] - cix, dry = ctr[3 * j + 1] - ciy, drz = ctr[3 * j + 2] - ciz;
-                  double tx = drx - Lx * rint(drx / Lx);
-                  double ty = dry - Ly * rint(dry / Ly);
-                  double tz = drz - Lz * rint(drz / Lz);
+                  double tx, ty, tz;
+                  if (tilt) {
+                    tx = drx, ty = dry, tz = drz;
+                    tri_min_image(&tx, &ty, &tz, box, tilt);
+                  } else {
+                    tx = drx - Lx * rint(drx / Lx);
+                    ty = dry - Ly * rint(dry / Ly);
+                    tz = drz - Lz * rint(drz / Lz);
+                  }
                   double rsq = tx * tx + ty * ty + tz * tz;
                   if (!(rsq <= rc2)) continue;
                 }
@@ -210,6 +285,21 @@ int mo_p2(const double *vec, const double *ctr, const int64_t *mol, const uint8_
   return 0;
 }
 
+int mo_p2(const double *vec, const double *ctr, const int64_t *mol, const uint8_t *ref_mask,
+          const uint8_t *nbr_mask, int64_t n, const double *box, double rcut, double rc2,
+          int same_molecule, double *out_sum, int64_t *out_cnt, int64_t *nbr_ptr, int64_t **nbr_idx) {
+  return mo_p2_impl(vec, ctr, mol, ref_mask, nbr_mask, n, box, NULL, rcut, rc2, same_molecule, out_sum, out_cnt,
+                    nbr_ptr, nbr_idx);
+}
+
+/* triclinic variant (build-defined minimum image, see tri_min_image); tilt = {xy, xz, yz} */
+int mo_p2_tri(const double *vec, const double *ctr, const int64_t *mol, const uint8_t *ref_mask,
+              const uint8_t *nbr_mask, int64_t n, const double *box, const double *tilt, double rcut, double rc2,
+              int same_molecule, double *out_sum, int64_t *out_cnt, int64_t *nbr_ptr, int64_t **nbr_idx) {
+  return mo_p2_impl(vec, ctr, mol, ref_mask, nbr_mask, n, box, tilt, rcut, rc2, same_molecule, out_sum, out_cnt,
+                    nbr_ptr, nbr_idx);
+}
+
 void mo_free(void *p) { free(p); }
 
 /* numpy.histogram (uniform bins) index rule, NumPy 2.3 _histograms_impl.histogram */
@@ -229,11 +319,11 @@ static inline int64_t np_bin(double d, double first, double last, int64_t nbin, 
  * int64, pair slot of (a<=b) = a*ntypes - a*(a-1)/2 + (b-a).  rcell = cell edge to use (rmax).
  * Every ORDERED pair (i reference, j neighbour) adds one count (so unordered pairs count twice).
  */
-int mo_rdf(const double *pos, const int32_t *type, const int64_t *mol, int64_t n, int ntypes,
-           const double *box, double rcell, const double *edges, int64_t nbin, int same_molecule,
-           int64_t *hist) {
+static int mo_rdf_impl(const double *pos, const int32_t *type, const int64_t *mol, int64_t n, int ntypes,
+                       const double *box, const double *tilt, double rcell, const double *edges, int64_t nbin,
+                       int same_molecule, int64_t *hist) {
   cells_t g;
-  if (cells_build(&g, pos, n, box, rcell)) return 1;
+  if (cells_build_t(&g, pos, n, box, tilt, rcell)) return 1;
   const double Lx = box[0], Ly = box[1], Lz = box[2];
   const double first = edges[0], last = edges[nbin];
   int64_t npair = (int64_t)ntypes * (ntypes + 1) / 2;
@@ -259,9 +349,15 @@ int mo_rdf(const double *pos, const int32_t *type, const int64_t *mol, int64_t n
                 if (!same_molecule && mol[j] == mol[i]) continue;
                 double drx = pos[3 * j] + -1. * pos[3 * i], dry = pos[3 * j + 1] + -1. * pos[3 * i + 1],
                        drz = pos[3 * j + 2] + -1. * pos[3 * i + 2];
-                double tx = drx + -1. * Lx * rint(drx / Lx);
-                double ty = dry + -1. * Ly * rint(dry / Ly);
-                double tz = drz + -1. * Lz * rint(drz / Lz);
+                double tx, ty, tz;
+                if (tilt) {
+                  tx = drx, ty = dry, tz = drz;
+                  tri_min_image(&tx, &ty, &tz, box, tilt);
+                } else {
+                  tx = drx + -1. * Lx * rint(drx / Lx);
+                  ty = dry + -1. * Ly * rint(dry / Ly);
+                  tz = drz + -1. * Lz * rint(drz / Lz);
+                }
                 double dd = sqrt(tx * tx + ty * ty + tz * tz);
                 if (dd == 0.0) continue;
                 int64_t k = np_bin(dd, first, last, nbin, edges);
@@ -279,4 +375,16 @@ int mo_rdf(const double *pos, const int32_t *type, const int64_t *mol, int64_t n
   }
   cells_free(&g);
   return 0;
+}
+
+int mo_rdf(const double *pos, const int32_t *type, const int64_t *mol, int64_t n, int ntypes,
+           const double *box, double rcell, const double *edges, int64_t nbin, int same_molecule,
+           int64_t *hist) {
+  return mo_rdf_impl(pos, type, mol, n, ntypes, box, NULL, rcell, edges, nbin, same_molecule, hist);
+}
+
+int mo_rdf_tri(const double *pos, const int32_t *type, const int64_t *mol, int64_t n, int ntypes,
+               const double *box, const double *tilt, double rcell, const double *edges, int64_t nbin,
+               int same_molecule, int64_t *hist) {
+  return mo_rdf_impl(pos, type, mol, n, ntypes, box, tilt, rcell, edges, nbin, same_molecule, hist);
 }

@@ -35,6 +35,13 @@ def lib():
         _lib.mo_rdf.argtypes = [p, p, p, C.c_int64, C.c_int, p, C.c_double, p, C.c_int64, C.c_int, p]
         _lib.mo_rdf.restype = C.c_int
         _lib.mo_free.argtypes = [p]
+        # triclinic variants (build-defined semantics, parity unpinned: the reference is orthorhombic only)
+        _lib.mo_bond_build_tri.argtypes = [p, p, C.c_int64, p, p, p, p]
+        _lib.mo_p2_tri.argtypes = [p, p, p, p, p, C.c_int64, p, p, C.c_double, C.c_double, C.c_int, p, p, p,
+                                   C.POINTER(C.c_void_p)]
+        _lib.mo_p2_tri.restype = C.c_int
+        _lib.mo_rdf_tri.argtypes = [p, p, p, C.c_int64, C.c_int, p, p, C.c_double, p, C.c_int64, C.c_int, p]
+        _lib.mo_rdf_tri.restype = C.c_int
     return _lib
 
 
@@ -42,18 +49,23 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def bond_build(positions, bond_atoms, box):
+def bond_build(positions, bond_atoms, box, tilt=None):
+    """``tilt`` = (xy, xz, yz) selects the triclinic (build-defined) variant."""
     pos = np.ascontiguousarray(positions, np.float64)
     b = np.ascontiguousarray(bond_atoms, np.int32)
     box = np.ascontiguousarray(box, np.float64)
     vec = np.empty((len(b), 3), np.float64)
     ctr = np.empty((len(b), 3), np.float64)
-    lib().mo_bond_build(_ptr(pos), _ptr(b), len(b), _ptr(box), _ptr(vec), _ptr(ctr))
+    if tilt is None:
+        lib().mo_bond_build(_ptr(pos), _ptr(b), len(b), _ptr(box), _ptr(vec), _ptr(ctr))
+    else:
+        t = np.ascontiguousarray(tilt, np.float64)
+        lib().mo_bond_build_tri(_ptr(pos), _ptr(b), len(b), _ptr(box), _ptr(t), _ptr(vec), _ptr(ctr))
     return vec, ctr
 
 
 def p2(vec, ctr, mol, box, rcut, same_molecule=True, ref_mask=None, nbr_mask=None, want_lists=False,
-       threads=None):
+       threads=None, tilt=None):
     """Per-bond (sum cos^2, count[, neighbour lists]) with the reference's arithmetic."""
     n = len(vec)
     vec = np.ascontiguousarray(vec, np.float64)
@@ -68,9 +80,15 @@ def p2(vec, ctr, mol, box, rcut, same_molecule=True, ref_mask=None, nbr_mask=Non
     idx_p = C.c_void_p()
     if threads is not None:
         os.environ["OMP_NUM_THREADS"] = str(threads)
-    rc = lib().mo_p2(_ptr(vec), _ptr(ctr), _ptr(mol), _ptr(rm), _ptr(nm), n, _ptr(box), float(rcut),
-                     float(rcut)**2, int(bool(same_molecule)), _ptr(ssum), _ptr(cnt),
-                     _ptr(ptr) if want_lists else None, C.byref(idx_p))
+    if tilt is None:
+        rc = lib().mo_p2(_ptr(vec), _ptr(ctr), _ptr(mol), _ptr(rm), _ptr(nm), n, _ptr(box), float(rcut),
+                         float(rcut)**2, int(bool(same_molecule)), _ptr(ssum), _ptr(cnt),
+                         _ptr(ptr) if want_lists else None, C.byref(idx_p))
+    else:
+        t = np.ascontiguousarray(tilt, np.float64)
+        rc = lib().mo_p2_tri(_ptr(vec), _ptr(ctr), _ptr(mol), _ptr(rm), _ptr(nm), n, _ptr(box), _ptr(t), float(rcut),
+                             float(rcut)**2, int(bool(same_molecule)), _ptr(ssum), _ptr(cnt),
+                             _ptr(ptr) if want_lists else None, C.byref(idx_p))
     if rc:
         raise MemoryError("mo_p2 failed")
     with np.errstate(invalid="ignore", divide="ignore"):
@@ -85,7 +103,7 @@ def p2(vec, ctr, mol, box, rcut, same_molecule=True, ref_mask=None, nbr_mask=Non
     return out
 
 
-def rdf(positions, type_code, mol, ntypes, box, rmin, rmax, nbin, same_molecule=True):
+def rdf(positions, type_code, mol, ntypes, box, rmin, rmax, nbin, same_molecule=True, tilt=None):
     """int64 histogram [ntypes*(ntypes+1)/2, nbin] over ordered pairs; bin edges are NumPy's."""
     pos = np.ascontiguousarray(positions, np.float64)
     t = np.ascontiguousarray(type_code, np.int32)
@@ -93,8 +111,13 @@ def rdf(positions, type_code, mol, ntypes, box, rmin, rmax, nbin, same_molecule=
     box = np.ascontiguousarray(box, np.float64)
     edges = np.ascontiguousarray(np.histogram_bin_edges(np.zeros(0), bins=int(nbin), range=(rmin, rmax)))
     hist = np.zeros((ntypes * (ntypes + 1) // 2, int(nbin)), np.int64)
-    rc = lib().mo_rdf(_ptr(pos), _ptr(t), _ptr(mol), len(pos), int(ntypes), _ptr(box), float(edges[-1]),
-                      _ptr(edges), int(nbin), int(bool(same_molecule)), _ptr(hist))
+    if tilt is None:
+        rc = lib().mo_rdf(_ptr(pos), _ptr(t), _ptr(mol), len(pos), int(ntypes), _ptr(box), float(edges[-1]),
+                          _ptr(edges), int(nbin), int(bool(same_molecule)), _ptr(hist))
+    else:
+        tl = np.ascontiguousarray(tilt, np.float64)
+        rc = lib().mo_rdf_tri(_ptr(pos), _ptr(t), _ptr(mol), len(pos), int(ntypes), _ptr(box), _ptr(tl),
+                              float(edges[-1]), _ptr(edges), int(nbin), int(bool(same_molecule)), _ptr(hist))
     if rc:
         raise MemoryError("mo_rdf failed")
     return hist, edges

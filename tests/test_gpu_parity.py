@@ -543,6 +543,30 @@ def test_staged_sweep_after_a_fused_frame_on_the_same_cell_list():
             assert torch.equal(c2, out[flags][1]) and torch.equal(s2, out[flags][0])
 
 
+def test_captured_graph_replays_the_frame_bit_for_bit():
+    """FramePipeline replays one captured CUDA graph per slot (mouse_p2_frame_graph_*): same totals and per-bond
+    outputs as the direct launch train, frame after frame; a frame with its own box falls back to direct launches."""
+    from mouse_b200.melt import jitter, make_melt
+    from mouse_b200.trajectory import FramePipeline
+    melt = make_melt(60, 51, seed=3)
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    frames = [jitter(melt, f, 0.05) for f in range(7)]
+    out = {}
+    for use_graph in (True, False):
+        pipe = FramePipeline(melt.bond_atoms, molb, melt.box, 2.0, melt.n_atoms, same_molecule=False, depth=2,
+                             use_graph=use_graph)
+        done, means = [], []
+        for f, pos in enumerate(frames):
+            done += pipe.submit(pos, tag=f, box=melt.box * 1.01 if f == 4 else None)
+        done += pipe.drain()
+        if use_graph:
+            assert pipe.slots[0]["graph"] is not None
+            assert 8 <= pipe.L.mouse_p2_frame_graph_nodes(pipe.slots[0]["graph"]) <= 10
+        out[use_graph] = [(d["tag"], d["sum_mean"], d["n_refs"], d["n_pairs"]) for d in done]
+        pipe.close()
+    assert out[True] == out[False] and [t[0] for t in out[True]] == list(range(7))
+
+
 def test_trajectory_pipeline_matches_frame_by_frame_calls():
     """local_ordering_trajectory (several frames in flight, own stream / workspace each) gives, frame by frame
     and bit for bit, what separate p2_frame calls give; results come back in submission order."""

@@ -52,8 +52,8 @@ def main():
     stages = {
         "bond_build": lambda: L.mouse_bond_build(p(pos), p(bonds), n, box3, p(vec), p(ctr), st),
         "cell_build": lambda: L.mouse_cell_build(p(vec), p(ctr), p(mol), None, None, n, C.byref(grid), p(ws), ws.numel(), st),
-        "p2_sweep": lambda: L.mouse_p2_sweep(p(vec), p(ctr), n, C.byref(grid), flags, p(ws), p(ssum), p(cnt), st),
-        "p2_reduce": lambda: L.mouse_p2_reduce(p(ssum), p(cnt), n, C.byref(grid), p(ws), p(mean), p(tot), None, 0., 0., 0, st),
+        "p2_sweep": lambda: L.mouse_p2_sweep(p(vec), p(ctr), n, C.byref(grid), flags, p(ws), ws.numel(), p(ssum), p(cnt), st),
+        "p2_reduce": lambda: L.mouse_p2_reduce(p(ssum), p(cnt), n, C.byref(grid), p(ws), ws.numel(), p(mean), p(tot), None, 0., 0., 0, st),
         "frame": lambda: L.mouse_p2_frame(p(pos), p(bonds), p(mol), None, None, n, C.byref(grid), flags, p(ws), ws.numel(),
                                           p(vec), p(ctr), p(ssum), p(cnt), p(mean), p(tot), st),
     }
@@ -62,16 +62,12 @@ def main():
         med, mn = timeit(fn)
         print("%-12s median %.3f ms  min %.3f ms" % (name, med, mn))
     pairs = int(tot.cpu()[2])
-    for R in (1,):
-        L.mouse_set_tuning(b"fast_variant", R)
-        for slots in (4, 6, 8):
-            L.mouse_set_tuning(b"fast_slots", slots)
-            med, mn = timeit(stages["p2_sweep"])
-            print("sweep variant=%d slots=%-2d median %.3f ms  min %.3f ms  -> %.3e pairs/s" % (R, slots, med, mn, pairs / (mn * 1e-3)))
-    L.mouse_set_tuning(b"fast_slots", 0)
-    L.mouse_set_tuning(b"fast_variant", 1)
+    for slots in (4, 6, 8):
+        med, mn = timeit(lambda: L.mouse_p2_sweep(p(vec), p(ctr), n, C.byref(grid), flags | _lib.MOUSE_SLOTS(slots), p(ws),
+                                                  ws.numel(), p(ssum), p(cnt), st))
+        print("sweep slots=%-2d median %.3f ms  min %.3f ms  -> %.3e pairs/s" % (slots, med, mn, pairs / (mn * 1e-3)))
     med, mn = timeit(lambda: L.mouse_p2_sweep(p(vec), p(ctr), n, C.byref(grid), flags | _lib.MOUSE_FORCE_EXACT, p(ws),
-                                              p(ssum), p(cnt), st), reps=3, warm=1)
+                                              ws.numel(), p(ssum), p(cnt), st), reps=3, warm=1)
     print("sweep exact   median %.3f ms  min %.3f ms" % (med, mn))
     med, mn = timeit(stages["frame"])
     print("pairs=%d  frame %.3f ms -> %.3e pairs/s; n_band=%d" % (pairs, mn, pairs / (mn * 1e-3), int(tot.cpu()[5])))
