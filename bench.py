@@ -7,11 +7,14 @@ ordering, 1M-bond melt, rc = 2.5 sigma, at 1/2/4/8 B200).
 
 A "step" is one pass of the hot path (K1 bond build -> K2 cell list -> K3 pair sweep -> K4 reduction)
 over one trajectory frame of the workload on every rank (weak scaling: frames are sharded, every GPU
-processes its own frames, one NCCL all-reduce of the packed sums at the end of the timed region).
-Prints ONE JSON line on rank 0.
+processes its own frames, ONE NCCL all-reduce of the packed sums at the end of the timed region).
+Prints ONE JSON line on rank 0.  Besides the contract's keys the line carries `configs`: driver-timed
+sub-measurements of the other BASELINE.json configurations (3: 250k-bond trajectory frames, 4: RDF of 4M
+beads, 5: 8M bonds with selections, orthorhombic and triclinic).
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -29,17 +32,35 @@ WORKLOADS = {
     # the configuration BASELINE.json's metric is quoted on (default)
     "config2": dict(name="config2: single-frame 1M-bond melt (10000 chains x 101 beads), rc=2.5 sigma, "
                          "local P2 per vector + system average", chains=10000, beads=101, rcut=2.5),
-    # the frame-sharded trajectory configuration (not a bench line of the driver; `--workload config3`)
+    # the frame-sharded trajectory configuration (`--workload config3`; also measured inside `configs`)
     "config3": dict(name="config3: frames of a 250k-bond melt (2500 chains x 101 beads), rc=2.5 sigma, frames sharded "
                          "over the ranks", chains=2500, beads=101, rcut=2.5),
 }
 WORKLOAD = WORKLOADS["config2"]
 METRIC = "pairs/sec for local P2 ordering (1M bonds, rc=2.5σ)"
 UNIT = "pairs/s"
-W_LANE_INSTR_PER_PAIR = 55.2      # 6.45 x 7 FP32 + 10 FP64 lane-instructions per counted pair
+W_LANE_INSTR_PER_PAIR = 55.2      # 6.45 x 7 FP32 + 10 FP64 lane-instructions per counted pair (K3)
+W5_LANE_INSTR_PER_PAIR = 60.2     # K5: 6.45 x 7 FP32 filter + 15 per counted pair (FP64 d^2, bin, count)
 BYTES_PER_BOND = 72.0             # compulsory HBM bytes per bond per frame
 N_FRAME_VARIANTS = 4              # distinct frames cycled (working set per frame ~210 MB > 126 MB L2)
 LANES = 3                         # frames in flight in the device-resident timed region (own stream + workspace each)
+KERNELS_PER_FRAME = 8             # bond_assign, scan, scatter_idx, canon, sweep, fixup, exact check, finish+reduce
+
+
+def static_config(n_bonds):
+    """`config` is the same dict in both arms (it names the workload; measured details live in `details`)."""
+    return {"workload": WORKLOAD["name"], "bonds_per_frame": int(n_bonds), "rcut": WORKLOAD["rcut"],
+            "frames_per_step_per_gpu": 1,
+            "l2": "~%d MB touched per frame (L2 is 126 MB), %d distinct frames cycled" % (int(230e-6 * n_bonds),
+                                                                                       N_FRAME_VARIANTS)}
+
+
+def kernel_source_hash():
+    """sha256 (16 hex) of the sources of the sweep kernel: profiles/*.json measured on other sources are stale."""
+    h = hashlib.sha256()
+    for name in ("p2_sweep.cu", "half_shell.cuh", "common.cuh"):
+        h.update(open(os.path.join(ROOT, "mouse_b200", "csrc", name), "rb").read())
+    return h.hexdigest()[:16]
 
 
 # ------------------------------------------------------------------------------------------- clocks
@@ -116,12 +137,12 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "how": self.how}
 
 
-# ------------------------------------------------------------------------------------------- reference arm
-_G = {}   # arrays shared with forked workers (set before the pool is created)
+# ------------------------------------------------------------------------------------------- CPU legs
+_G = {}   # data shared with forked workers (set before the pool is created)
 
 
-def _ref_worker(refs):
-    """Literal NumPy restatement of ordering_functions.py:91-119 for a block of reference bonds."""
+def _port_worker(refs):
+    """Literal NumPy restatement (oracle port) of ordering_functions.py:91-119 for a block of reference bonds."""
     from oracle import p2_oracle as po
     np_bonds, box, vec, ctr, rcut = _G["np_bonds"], _G["box"], _G["vec"], _G["ctr"], _G["rcut"]
     t0 = time.perf_counter()
@@ -135,54 +156,88 @@ def _ref_worker(refs):
     return pairs, time.perf_counter() - t0
 
 
-def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm (all-pairs NumPy passes per reference bond,
-    ordering_functions.py:91-119, 196-214) through the oracle port, all host threads, on a bounded
-    sample of reference bonds of the SAME workload; pairs/s = counted pairs of the sample / wall time."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    import multiprocessing as mp
-    from mouse_b200.melt import make_melt
+def _literal_worker(refs):
+    """The reference's own calculateAveCosSqForReference (oracle/_ref, unmodified) for a block of reference bonds;
+    the number of counted neighbours is read off np.ma.average's argument (oracle/reference_harness._AverageSpy)."""
+    from oracle import reference_harness as rh
+    of, cfg, np_bonds, rcut = _G["of"], _G["cfg"], _G["np_bonds_ref"], _G["rcut"]
+    bonds = cfg.bonds()
+    t0 = time.perf_counter()
+    pairs = 0
+    with rh._AverageSpy() as spy:
+        for i in refs:
+            try:
+                spy.count = None
+                of.calculateAveCosSqForReference(cfg, bonds[int(i)], np_bonds, rcut, excludeSelf=True, sameMolecule=True)
+                pairs += spy.count or 0
+            except NameError:
+                pass
+    return pairs, time.perf_counter() - t0
+
+
+def _literal_frame_worker(seed):
+    """One whole frame of config 1 through the reference's CalculateOrientationOrderParameter (:180-227)."""
+    from mouse_b200.melt import jitter, make_melt
+    from oracle import reference_harness as rh
+    melt = make_melt(100, 100, seed=0)
+    cfg = rh.config_from_melt(melt, jitter(melt, seed, 0.05) if seed else None)
+    of = rh.load().of
+    t0 = time.perf_counter()
+    with rh._AverageSpy() as spy:
+        orig = spy._orig
+        pairs = [0]
+
+        def counting(a, *args, **kw):
+            pairs[0] += int(a.count())
+            return orig(a, *args, **kw)
+        np.ma.average = counting
+        s = of.CalculateOrientationOrderParameter(cfg, ['1'], 0., 1.5, mode='average', sameMolecule=True)
+    return float(s), pairs[0], time.perf_counter() - t0
+
+
+def _port_frame_worker(seed):
+    from mouse_b200.melt import jitter, make_melt
     from oracle import p2_oracle as po
-    melt = make_melt(WORKLOAD["chains"], WORKLOAD["beads"], seed=0)
-    vec, ctr = po.bond_build(melt.positions, melt.bond_atoms, melt.box)
-    n = melt.n_bonds
-    molb = melt.mol[melt.bond_atoms[:, 0]].astype(np.float64)
-    np_bonds = po.np_bonds_array(np.arange(1, n + 1), np.zeros(n), molb, vec, ctr)
-    cores = os.cpu_count() or 1
-    per_core = 4                                  # ~55 ms per reference bond at 1M bonds
-    steps, warm = max(1, args.steps), max(0, args.warmup)
-    total_pairs, total_t = 0, 0.0
-    _G.update(np_bonds=np_bonds, box=melt.box, vec=vec, ctr=ctr, rcut=WORKLOAD["rcut"])
-    with mp.get_context("fork").Pool(cores) as pool:
-        for s in range(warm + steps):
-            rng = np.random.default_rng(100 + s)
-            refs = rng.choice(n, size=cores * per_core, replace=False)
-            blocks = [refs[k::cores] for k in range(cores)]
-            t0 = time.perf_counter()
-            out = pool.map(_ref_worker, blocks)
-            dt = time.perf_counter() - t0
-            if s >= warm:
-                total_pairs += sum(o[0] for o in out)
-                total_t += dt
-    value = total_pairs / total_t
-    sample = "%d evenly drawn reference bonds per step against all %d bonds (literal all-pairs NumPy passes)" % (
-        cores * per_core, n)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": 1e3 * total_t / steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD["name"], "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    melt = make_melt(100, 100, seed=0)
+    pos = jitter(melt, seed, 0.05) if seed else melt.positions
+    t0 = time.perf_counter()
+    vec, ctr = po.bond_build(pos, melt.bond_atoms, melt.box)
+    r = po.p2_literal(vec, ctr, np.arange(1, melt.n_bonds + 1), melt.mol[melt.bond_atoms[:, 0]].astype(np.float64),
+                      melt.box, 1.5, True)
+    ok = r["count"] > 0
+    return float(1.5 * r["mean"][ok].sum() / ok.sum() - 0.5), int(r["count"].sum()), time.perf_counter() - t0
 
 
-# ------------------------------------------------------------------------------------------- CPU baseline leg
+def _reference_available():
+    try:
+        from oracle import reference_harness as rh
+        return rh.available()
+    except Exception:
+        return False
+
+
+def config1_literal_leg(cores, frames=3):
+    """SURVEY 8(d) CPU baseline item 1: the reference's CalculateOrientationOrderParameter end to end on >= 3 frames
+    of the 9 900-bond melt of config 1 (100 chains x 100 beads, rc = 1.5 sigma); one frame per process (the reference
+    is single-threaded).  Literal reference code when oracle/_ref (or /root/reference) is there, else the port."""
+    import multiprocessing as mp
+    literal = _reference_available()
+    k = max(frames, min(cores, 8))
+    with mp.get_context("fork").Pool(min(cores, k)) as pool:
+        t0 = time.perf_counter()
+        out = pool.map(_literal_frame_worker if literal else _port_frame_worker, list(range(k)))
+        wall = time.perf_counter() - t0
+    return {"kind": "reference" if literal else "port", "frames": k, "processes": min(cores, k),
+            "s_per_frame_one_core": float(np.mean([o[2] for o in out])), "pairs_per_frame": int(np.mean([o[1] for o in out])),
+            "value": float(sum(o[1] for o in out) / wall), "unit": UNIT, "S_frame0": out[0][0],
+            "sample": "calculate_local_ordering.py workload of config 1: %d frames (frame 0 + jittered copies) of 100 x 100 "
+                      "beads, 9 900 bonds, rc=1.5, CalculateOrientationOrderParameter (ordering_functions.py:180-227)" % k}
+
+
 def cpu_baseline(melt):
-    """Oracle timed on the host cores (rank 0, N=1): (a) the literal reference algorithm on a bounded
-    sample of reference bonds; (b) the strong cell-list C oracle on the whole frame."""
+    """Timed on the host cores (rank 0, N=1): (a) the reference algorithm on a bounded sample of reference bonds of
+    config 2 (oracle port of ordering_functions.py:91-119; the literal code needs a 1M-object Config: that is what
+    `--impl reference` times); (b) the strong cell-list C oracle on the whole frame; (c) config 1 end to end."""
     import multiprocessing as mp
     from oracle import c_oracle, p2_oracle as po
     vec, ctr = po.bond_build(melt.positions, melt.bond_atoms, melt.box)
@@ -194,9 +249,9 @@ def cpu_baseline(melt):
     blocks = [refs[k::cores] for k in range(cores)]
     _G.update(np_bonds=np_bonds, box=melt.box, vec=vec, ctr=ctr, rcut=WORKLOAD["rcut"])
     with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_ref_worker, [refs[:1]] * cores)          # warm the workers
+        pool.map(_port_worker, [refs[:1]] * cores)          # warm the workers
         t0 = time.perf_counter()
-        out = pool.map(_ref_worker, blocks)
+        out = pool.map(_port_worker, blocks)
         dt = time.perf_counter() - t0
     lit = sum(o[0] for o in out) / dt
     t0 = time.perf_counter()
@@ -206,14 +261,260 @@ def cpu_baseline(melt):
             "sample": "%d evenly spaced reference bonds against all %d bonds, literal all-pairs NumPy passes "
                       "(ordering_functions.py:91-119)" % (len(refs), n),
             "strong_cell_list_c": {"value": float(r["count"].sum()) / dt_c, "unit": UNIT, "cores": cores,
-                                   "sample": "whole frame, OpenMP cell-list C oracle (not the reference's algorithm)"}}
+                                   "sample": "whole frame, OpenMP cell-list C oracle (not the reference's algorithm)"},
+            "config1_literal": config1_literal_leg(cores)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on all host cores, on a bounded sample
+    of reference bonds of the SAME workload per step.  When the unmodified reference modules are staged
+    (oracle/_ref, see oracle/make_ref.py) the timed code IS the reference: its Config, its
+    createNumpyBondsArrayFromConfig and its calculateAveCosSqForReference (kind "reference"); otherwise the
+    oracle's literal NumPy port of the same lines (kind "port").  pairs/s = counted pairs of the sample / wall."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import gc
+    import multiprocessing as mp
+    from mouse_b200.melt import make_melt
+    from oracle import p2_oracle as po
+    melt = make_melt(WORKLOAD["chains"], WORKLOAD["beads"], seed=0)
+    n = melt.n_bonds
+    cores = os.cpu_count() or 1
+    per_core = 4                                  # ~55 ms per reference bond at 1M bonds
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    literal = _reference_available() and not os.environ.get("MOUSE_BENCH_PORT")
+    if literal:
+        from oracle import reference_harness as rh
+        of = rh.load().of
+        cfg = rh.config_from_melt(melt)                                     # the reference's own object model
+        np_bonds_ref = of.createNumpyBondsArrayFromConfig(cfg, allowedBondTypes=['1'])
+        _G.update(of=of, cfg=cfg, np_bonds_ref=np_bonds_ref, rcut=WORKLOAD["rcut"])
+        worker = _literal_worker
+        gc.freeze()                                # keep the forked workers from copying the 1M-object heap
+    else:
+        vec, ctr = po.bond_build(melt.positions, melt.bond_atoms, melt.box)
+        molb = melt.mol[melt.bond_atoms[:, 0]].astype(np.float64)
+        np_bonds = po.np_bonds_array(np.arange(1, n + 1), np.zeros(n), molb, vec, ctr)
+        _G.update(np_bonds=np_bonds, box=melt.box, vec=vec, ctr=ctr, rcut=WORKLOAD["rcut"])
+        worker = _port_worker
+    total_pairs, total_t = 0, 0.0
+    with mp.get_context("fork").Pool(cores) as pool:
+        for s in range(warm + steps):
+            rng = np.random.default_rng(100 + s)
+            refs = rng.choice(n, size=cores * per_core, replace=False)
+            blocks = [refs[k::cores] for k in range(cores)]
+            t0 = time.perf_counter()
+            out = pool.map(worker, blocks)
+            dt = time.perf_counter() - t0
+            if s >= warm:
+                total_pairs += sum(o[0] for o in out)
+                total_t += dt
+    value = total_pairs / total_t
+    sample = "%d randomly drawn reference bonds per step against all %d bonds: %s" % (
+        cores * per_core, n,
+        "the reference's own calculateAveCosSqForReference on its own Config / npBonds (oracle/_ref, unmodified)"
+        if literal else "literal all-pairs NumPy passes (oracle port of ordering_functions.py:91-119)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total_t / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": static_config(n),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference" if literal else "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------- our arm
+class P2Bench:
+    """Device-resident frames of one topology: LANES frames in flight (own stream, workspace and outputs each)."""
+
+    def __init__(self, dev, positions_list, bond_atoms, molb, box, rcut, same_molecule=True, nbr_mask=None, ref_mask=None,
+                 tilt=None, lanes=LANES):
+        import torch
+        from mouse_b200 import _lib, engine
+        self.torch, self._lib, self.engine = torch, _lib, engine
+        self.dev = dev
+        self.frames_dev = [torch.as_tensor(np.ascontiguousarray(p)).to(dev) for p in positions_list]
+        self.bonds = torch.as_tensor(np.ascontiguousarray(bond_atoms)).to(dev)
+        self.mol = torch.as_tensor(np.ascontiguousarray(molb).astype(np.int32)).to(dev)
+        self.nbr = None if nbr_mask is None else torch.as_tensor(np.ascontiguousarray(nbr_mask).astype(np.uint8)).to(dev)
+        self.ref = None if ref_mask is None else torch.as_tensor(np.ascontiguousarray(ref_mask).astype(np.uint8)).to(dev)
+        self.n = int(self.bonds.shape[0])
+        self.L = _lib.lib()
+        self.grid = _lib.grid_plan(box, rcut, self.n, tilt=tilt)
+        self.flags = _lib.MOUSE_SAME_MOLECULE if same_molecule else 0
+        nbytes = self.L.mouse_workspace_bytes(self.n, C.byref(self.grid))
+        n = self.n
+        self.lanes = []
+        for _ in range(lanes):
+            self.lanes.append(dict(ws=torch.empty(int(nbytes) + 4096, dtype=torch.uint8, device=dev),
+                                   vec=torch.empty((3, n), dtype=torch.float64, device=dev),
+                                   ctr=torch.empty((3, n), dtype=torch.float64, device=dev),
+                                   ssum=torch.empty(n, dtype=torch.float64, device=dev),
+                                   cnt=torch.empty(n, dtype=torch.int32, device=dev),
+                                   mean=torch.empty(n, dtype=torch.float64, device=dev),
+                                   stream=torch.cuda.Stream(device=dev), done=torch.cuda.Event()))
+
+    def ev(self):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record(self.torch.cuda.current_stream())        # torch creates the CUDA event lazily at the first record
+        return e
+
+    def frame(self, k, tot_row, timed=None, lane=None):
+        # one C-ABI call per frame: K1+K2 (fused build), K3 (half-shell sweep + exact fixup), K4 (fused finish + reduce);
+        # the two events bracket the K3 launches on the frame's stream
+        p = self.engine._ptr
+        ln = self.lanes[k % len(self.lanes) if lane is None else lane]
+        pos = self.frames_dev[k % len(self.frames_dev)]
+        ev0 = C.c_void_p(timed[0].cuda_event) if timed is not None else None
+        ev1 = C.c_void_p(timed[1].cuda_event) if timed is not None else None
+        self._lib.check(self.L.mouse_p2_frame_timed(p(pos), p(self.bonds), p(self.mol), p(self.nbr), p(self.ref), self.n,
+                                                    C.byref(self.grid), self.flags, p(ln["ws"]), ln["ws"].numel(),
+                                                    p(ln["vec"]), p(ln["ctr"]), p(ln["ssum"]), p(ln["cnt"]), p(ln["mean"]),
+                                                    p(tot_row), ev0, ev1, C.c_void_p(ln["stream"].cuda_stream)),
+                        "p2_frame")
+
+    def overlapped(self, steps, tot, first=0, timed=None):
+        """Records `steps` frames over the lanes between two events on the current stream; returns the events."""
+        torch = self.torch
+        stream = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for ln in self.lanes:
+            ln["stream"].wait_event(e0)
+        for k in range(steps):
+            self.frame(first + k, tot[first + k], None if timed is None else timed[k])
+        for ln in self.lanes:
+            ln["done"].record(ln["stream"])
+            stream.wait_event(ln["done"])
+        return e0, e1
+
+    def serial(self, count, tot):
+        """`count` frames serialised on lane 0 with the K3 events: (ms per frame, ms per sweep, pairs per frame)."""
+        torch = self.torch
+        evs = [(self.ev(), self.ev()) for _ in range(count)]
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ln0 = self.lanes[0]["stream"]
+        ln0.wait_stream(torch.cuda.current_stream())
+        s0.record(ln0)
+        for k, tev in enumerate(evs):
+            self.frame(k, tot[k], tev, lane=0)
+        s1.record(ln0)
+        torch.cuda.synchronize()
+        return (s0.elapsed_time(s1) / count, float(np.mean([a.elapsed_time(b) for a, b in evs])),
+                float(tot[:count, 2].sum().item()) / count)
+
+
+def measure_small_config(dev, positions_list, bond_atoms, molb, box, rcut, steps, warm, **kw):
+    """ms per frame (LANES in flight, device resident), serial frame / sweep times and pairs per frame."""
+    import torch
+    b = P2Bench(dev, positions_list, bond_atoms, molb, box, rcut, **kw)
+    tot = torch.zeros((warm + steps, 6), dtype=torch.int64, device=dev)
+    for k in range(warm):
+        b.frame(k, tot[k])
+    torch.cuda.synchronize()
+    e0, e1 = b.overlapped(steps, tot, first=warm)
+    e1.record(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    tot_s = torch.zeros((min(steps, 20), 6), dtype=torch.int64, device=dev)
+    serial_ms, sweep_ms, pairs = b.serial(min(steps, 20), tot_s)
+    t = tot_s[0].cpu()
+    s = 1.5 * float(t.view(torch.float64)[0]) / max(int(t[1]), 1) - 0.5
+    return dict(ms_per_frame=ms, serial_frame_ms=serial_ms, sweep_ms=sweep_ms, pairs_per_frame=pairs,
+                pairs_per_s=pairs / (ms * 1e-3), frames_per_s=1e3 / ms, n_refs=int(t[1]), S=s,
+                cell_grid=list(b.grid.ncell_axis), fast=int(b.grid.fast), triclinic=int(b.grid.triclinic))
+
+
+def bench_other_configs(dev, world, rank, sms, f_clk, dist):
+    """Driver-timed sub-measurements of BASELINE configs 3, 4 and 5 (inputs resident in HBM, CUDA events)."""
+    import torch
+    from mouse_b200 import _lib, engine
+    from mouse_b200.melt import jitter, make_melt
+    from mouse_b200.workloads import CONFIG3, CONFIG4, config5
+    out = {}
+    peak_issue = sms * 128 * f_clk * 1e6
+    # ---- config 3: frames of the 250k-bond melt, every rank its own frames (weak scaling over the frame shards)
+    melt = make_melt(CONFIG3["chains"], CONFIG3["beads"], seed=0)
+    frames = [jitter(melt, rank * 8 + f, 0.02) for f in range(8)]
+    r = measure_small_config(dev, frames, melt.bond_atoms, melt.mol[melt.bond_atoms[:, 0]], melt.box, CONFIG3["rcut"],
+                             steps=200, warm=20)
+    t = torch.tensor([r["ms_per_frame"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    out["config3"] = dict(workload="250k-bond melt frames (2500 x 101 beads), rc=2.5, frames sharded over %d rank(s), %d in "
+                                   "flight per GPU" % (world, LANES), bonds_per_frame=melt.n_bonds, ms_per_frame=ms,
+                          frames_per_s=world * 1e3 / ms, pairs_per_s=world * r["pairs_per_frame"] / (ms * 1e-3),
+                          serial_frame_ms=r["serial_frame_ms"], sweep_ms=r["sweep_ms"], pairs_per_frame=r["pairs_per_frame"],
+                          trajectory_10k_frames_s=10000 * ms * 1e-3 / world, cell_grid=r["cell_grid"], S=r["S"],
+                          roofline_frac_sweep=r["pairs_per_frame"] / (r["sweep_ms"] * 1e-3) * W_LANE_INSTR_PER_PAIR / peak_issue)
+    if world > 1:
+        out["note"] = "configs 4 and 5 are single-frame workloads (replicas only): measured at N=1"
+        return out
+    del frames
+    # ---- config 5: 8M bonds, rc = 3 sigma, bond-type neighbour set, residue-type references, other-molecule pairs
+    for key, tri in (("config5_orthorhombic", False), ("config5_triclinic", True)):
+        cfg = config5(tri)
+        r = measure_small_config(dev, [cfg["positions"]], cfg["bond_atoms"], cfg["molb"], cfg["box"], cfg["rcut"],
+                                 steps=6, warm=2, same_molecule=False, nbr_mask=cfg["nbr_mask"], ref_mask=cfg["ref_mask"],
+                                 tilt=cfg["tilt"], lanes=1)
+        out[key] = dict(workload="8M bonds (80000 x 101 beads), rc=3.0, neighbour set = bond type 1 (4M bonds), references = "
+                                 "residue types R0/R1, other-molecule pairs only%s" % (
+                                     "; triclinic cell (build-defined minimum image, parity unpinned)" if tri else ""),
+                        bonds=len(cfg["bond_atoms"]), tilt=cfg["tilt"], ms_per_frame=r["ms_per_frame"],
+                        sweep_ms=r["sweep_ms"], pairs_per_frame=r["pairs_per_frame"], pairs_per_s=r["pairs_per_s"],
+                        n_refs=r["n_refs"], cell_grid=r["cell_grid"], fast=r["fast"], S=r["S"],
+                        roofline_frac_sweep=r["pairs_per_frame"] / (r["sweep_ms"] * 1e-3) * W_LANE_INSTR_PER_PAIR / peak_issue)
+        del cfg
+        torch.cuda.empty_cache()
+    # ---- config 4: RDF pair histogram of 4M beads, 0-5 sigma, 1000 bins (K5)
+    melt = make_melt(CONFIG4["chains"], CONFIG4["beads"], seed=0)
+    L = _lib.lib()
+    n = melt.n_atoms
+    edges = np.ascontiguousarray(np.histogram_bin_edges(np.zeros(0), bins=CONFIG4["nbin"], range=(CONFIG4["rmin"],
+                                                                                               CONFIG4["rmax"])))
+    grid = _lib.grid_plan(melt.box, float(edges[-1]), n)
+    ws = torch.empty(L.mouse_workspace_bytes(n, C.byref(grid)) + 4096, dtype=torch.uint8, device=dev)
+    pos = torch.as_tensor(melt.positions).to(dev)
+    typ = torch.zeros(n, dtype=torch.int32, device=dev)
+    mol = torch.as_tensor(melt.mol.astype(np.int32)).to(dev)
+    hist = torch.empty((1, CONFIG4["nbin"]), dtype=torch.int64, device=dev)
+    p, st = engine._ptr, engine._stream()
+    reps = 5
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(reps + 1)]
+    for row in ev:
+        for e in row:
+            e.record()
+    for k in range(reps + 1):
+        ev[k][0].record()
+        _lib.check(L.mouse_rdf_frame_timed(p(pos), p(typ), p(mol), n, 1, C.byref(grid), _lib.MOUSE_SAME_MOLECULE,
+                                           edges.ctypes.data_as(C.POINTER(C.c_double)), CONFIG4["nbin"], p(ws), ws.numel(),
+                                           p(hist), C.c_void_p(ev[k][1].cuda_event), C.c_void_p(ev[k][2].cuda_event), st),
+                   "mouse_rdf_frame")
+        ev[k][3].record()
+        torch.cuda.synchronize()
+    frame_ms = float(np.mean([ev[k][0].elapsed_time(ev[k][3]) for k in range(1, reps + 1)]))
+    sweep_ms = float(np.mean([ev[k][1].elapsed_time(ev[k][2]) for k in range(1, reps + 1)]))
+    pairs = int(hist.sum().item())
+    ach = pairs / (sweep_ms * 1e-3) * W5_LANE_INSTR_PER_PAIR
+    out["config4"] = dict(workload="RDF pair histogram, 4 000 000 beads (40000 x 100), 0-5 sigma, 1000 bins, one type, "
+                                   "sameMolecule=True", atoms=n, ms_per_frame=frame_ms, sweep_ms=sweep_ms,
+                          pairs_per_frame=pairs, pairs_per_s=pairs / (frame_ms * 1e-3), cell_grid=list(grid.ncell_axis),
+                          roofline={"bound": "fp_issue", "kernel": "rdf_sweep_half_kernel", "achieved": ach / 1e12,
+                                    "peak": peak_issue / 1e12, "unit": "Tlane-instr/s", "frac": ach / peak_issue,
+                                    "traffic": None,
+                                    "how": "ordered pairs in range / K5 launch time x 60.2 lane-instr per pair (6.45 "
+                                           "candidates x 7 FP32 filter + 15 per counted pair: FP64 d^2, bin, count) over "
+                                           "SMs x 128 lanes x f_clk"})
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from mouse_b200 import _lib, engine
+    from mouse_b200 import engine
     from mouse_b200.melt import jitter, make_melt
     from mouse_b200.trajectory import FramePipeline, TrajectoryTotals, all_reduce_totals
 
@@ -232,51 +533,18 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     n, n_atoms, rcut = melt.n_bonds, melt.n_atoms, WORKLOAD["rcut"]
+    molb = melt.mol[melt.bond_atoms[:, 0]].astype(np.int32)
     # frames of the trajectory: base melt + per-frame jitter; every rank owns different frames
-    frames_host = [torch.from_numpy(np.ascontiguousarray(jitter(melt, rank * N_FRAME_VARIANTS + f, 0.02))).pin_memory()
-                   for f in range(N_FRAME_VARIANTS)]
-    frames_dev = [f.to(dev) for f in frames_host]
-    bonds = torch.as_tensor(melt.bond_atoms).to(dev)
-    mol = torch.as_tensor(melt.mol[melt.bond_atoms[:, 0]].astype(np.int32)).to(dev)
-    L = _lib.lib()
-    grid = _lib.grid_plan(melt.box, rcut, n)
+    frames_np = [np.ascontiguousarray(jitter(melt, rank * N_FRAME_VARIANTS + f, 0.02)) for f in range(N_FRAME_VARIANTS)]
+    frames_host = [torch.from_numpy(f).pin_memory() for f in frames_np]
     # LANES frames in flight, each on its own stream with its own workspace and per-bond outputs (frames are
     # independent): the HBM-side kernels and the tail of the persistent sweep of one frame overlap the sweep of
     # the next.  Lane 0 alone (serialised frames) gives the per-kernel durations of the roofline object.
-    nbytes = L.mouse_workspace_bytes(n, C.byref(grid))
-    lanes = []
-    for _ in range(LANES):
-        lanes.append(dict(ws=torch.empty(int(nbytes) + 4096, dtype=torch.uint8, device=dev),
-                          vec=torch.empty((3, n), dtype=torch.float64, device=dev),
-                          ctr=torch.empty((3, n), dtype=torch.float64, device=dev),
-                          ssum=torch.empty(n, dtype=torch.float64, device=dev),
-                          cnt=torch.empty(n, dtype=torch.int32, device=dev),
-                          mean=torch.empty(n, dtype=torch.float64, device=dev),
-                          stream=torch.cuda.Stream(device=dev), done=torch.cuda.Event()))
+    b = P2Bench(dev, frames_np, melt.bond_atoms, molb, melt.box, rcut)
+    grid = b.grid
     tot = torch.zeros((warm + steps, 6), dtype=torch.int64, device=dev)
     tot_serial = torch.zeros((100, 6), dtype=torch.int64, device=dev)
-    p, flags = engine._ptr, _lib.MOUSE_SAME_MOLECULE
-    stream = torch.cuda.current_stream()
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    sweep_ev = [(ev(), ev()) for _ in range(steps)]
-    serial_ev = [(ev(), ev()) for _ in range(min(steps, 100))]
-
-    for e0_, e1_ in sweep_ev + serial_ev:   # create the CUDA events (torch creates them lazily at the first record)
-        e0_.record(stream)
-        e1_.record(stream)
-
-    def frame(k, timed=None, lane=None, out=None):
-        # one C-ABI call per frame: K1+K2 (fused build), K3 (half-shell sweep + exact fixup), K4 (fused finish + reduce);
-        # the two events bracket the K3 launches on the frame's stream
-        ln = lanes[k % LANES if lane is None else lane]
-        pos = frames_dev[k % N_FRAME_VARIANTS]
-        ev0 = C.c_void_p(timed[0].cuda_event) if timed is not None else None
-        ev1 = C.c_void_p(timed[1].cuda_event) if timed is not None else None
-        _lib.check(L.mouse_p2_frame_timed(p(pos), p(bonds), p(mol), None, None, n, C.byref(grid), flags, p(ln["ws"]),
-                                          ln["ws"].numel(), p(ln["vec"]), p(ln["ctr"]), p(ln["ssum"]), p(ln["cnt"]),
-                                          p(ln["mean"]), p(tot[k] if out is None else out[k]), ev0, ev1,
-                                          C.c_void_p(ln["stream"].cuda_stream)),
-                   "p2_frame")
+    sweep_ev = [(b.ev(), b.ev()) for _ in range(steps)]
 
     def barrier():
         if world > 1:
@@ -293,36 +561,28 @@ def run_ours(args):
     t_spin = time.perf_counter() + 0.3
     k = 0
     while k < warm or time.perf_counter() < t_spin:
-        frame(k % warm)
+        b.frame(k % warm, tot[k % warm])
         k += 1
         if k % 16 == 0:
             torch.cuda.synchronize()
     warm_done = k
     # the tail of the timed region (sum of the per-frame totals + the path's only collective) is warmed up too:
     # the first call of a torch kernel / NCCL collective pays one-off module loading and communicator set-up
+    packed = torch.zeros(6, dtype=torch.float64, device=dev)
     _w = tot[:warm].sum(dim=0)
     if world > 1:
-        _wf = tot[:warm, 0].view(torch.float64).sum().reshape(1)
-        dist.all_reduce(_wf)
-        dist.all_reduce(_w)
+        dist.all_reduce(packed)
     barrier()
     n_before = len(sampler.samples)
-    e0, e1 = ev(), ev()
-    e0.record(stream)
-    for ln in lanes:
-        ln["stream"].wait_event(e0)
-    for k in range(steps):
-        frame(warm + k, sweep_ev[k])
-    for ln in lanes:
-        ln["done"].record(ln["stream"])
-        stream.wait_event(ln["done"])
-    totals = TrajectoryTotals()
-    # the path's only collective: all-reduce of the packed order-parameter sums (device tensors)
+    stream = torch.cuda.current_stream()
+    e0, e1 = b.overlapped(steps, tot, first=warm, timed=sweep_ev)
+    # the path's only collective: ONE all-reduce of the packed order-parameter sums and counts (device tensor; the
+    # integer counts ride as float64, exact below 2^53 - trajectory.TrajectoryTotals.pack)
     tsum = tot[warm:].sum(dim=0)
+    packed[0] = tot[warm:, 0].view(torch.float64).sum()
+    packed[1:] = tsum[1:].to(torch.float64)
     if world > 1:
-        fsum = tot[warm:, 0].view(torch.float64).sum().reshape(1)
-        dist.all_reduce(fsum)
-        dist.all_reduce(tsum)
+        dist.all_reduce(packed)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -330,32 +590,24 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
-    sweep_ms_overlapped = float(np.mean([a.elapsed_time(b) for a, b in sweep_ev]))
+    sweep_ms_overlapped = float(np.mean([a.elapsed_time(bb) for a, bb in sweep_ev]))
     # per-kernel durations: the same frames once more, serialised on one lane (in the overlapped region above the
     # kernels of up to LANES frames share the SMs, so an in-stream duration there is not a kernel time)
-    s0, s1 = ev(), ev()
-    ln0 = lanes[0]["stream"]
-    s0.record(ln0)
-    for k, tev in enumerate(serial_ev):
-        frame(k, tev, lane=0, out=tot_serial)
-    s1.record(ln0)
-    torch.cuda.synchronize()
-    serial_ms = s0.elapsed_time(s1) / len(serial_ev)
-    sweep_ms = float(np.mean([a.elapsed_time(b) for a, b in serial_ev]))
+    n_serial = min(steps, 100)
+    serial_ms, sweep_ms, pairs_serial = b.serial(n_serial, tot_serial)
     if os.environ.get("MOUSE_BENCH_DIAG"):
         sys.stderr.write("overlapped frame %.4f ms; serial frame %.4f ms, sweep %.4f ms (in-stream, overlapped: %.4f ms)\n" % (
             ms / steps, serial_ms, sweep_ms, sweep_ms_overlapped))
-    tl = tot[warm:].cpu()
-    pairs_local = int(tl[:, 2].sum())
-    pairs_all = int(tsum[2].item()) if world > 1 else pairs_local
+    pairs_local = int(tot[warm:, 2].sum().item())
+    pairs_all = int(round(float(packed[2].item())))
     value = pairs_all / (ms * 1e-3)
 
     # ---- end-to-end through the host-buffer API (pinned host positions in, totals out, every step)
-    pipe = FramePipeline(melt.bond_atoms, melt.mol[melt.bond_atoms[:, 0]].astype(np.int32), melt.box, rcut, n_atoms,
-                         same_molecule=True, device=dev)
+    pipe = FramePipeline(melt.bond_atoms, molb, melt.box, rcut, n_atoms, same_molecule=True, device=dev)
     for k in range(warm):
         pipe.submit(frames_host[k % N_FRAME_VARIANTS])
     pipe.drain()
+    pipe.host_submit_s, pipe.frames_submitted = 0.0, 0
     barrier()
     t0 = time.perf_counter()
     done = []
@@ -364,79 +616,115 @@ def run_ours(args):
     done += pipe.drain()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    host_submit_us = 1e6 * pipe.host_submit_s / max(pipe.frames_submitted, 1)
+    graph_nodes = pipe.L.mouse_p2_frame_graph_nodes(pipe.slots[0]["graph"]) if pipe.slots[0].get("graph") else 0
     e2e_pairs = sum(d["n_pairs"] for d in done)
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     e2e_p = torch.tensor([e2e_pairs], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_p)
+    # ---- the ceiling of that path on this box: the same pinned buffers copied to the same device buffers, no kernels,
+    # on every rank at once (what the host side of the box delivers to N GPUs streaming 24 MB frames)
+    barrier()
+    c0 = torch.cuda.Event(enable_timing=True)
+    c1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(pipe.copy_stream):
+        c0.record(pipe.copy_stream)
+        for k in range(steps):
+            pipe.slots[k % pipe.depth]["pos"].copy_(frames_host[k % N_FRAME_VARIANTS], non_blocking=True)
+        c1.record(pipe.copy_stream)
+    barrier()
+    copy_t = torch.tensor([c0.elapsed_time(c1) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(copy_t, op=dist.ReduceOp.MAX)
+    h2d_ceiling = world * steps * pipe.h2d_bytes_per_frame / float(copy_t.item()) / 1e9
+    pipe.close()
     if rank == 0 and len(sampler.samples) - n_before < 3:
         # very short runs: keep the kernels busy a little longer so that the clocks are sampled under load
         t_end = time.perf_counter() + 0.5
         while time.perf_counter() < t_end:
-            frame(0)
+            b.frame(0, tot[0])
         torch.cuda.synchronize()
     if rank == 0:
         sampler.samples = sampler.samples[n_before:]
     clocks = sampler.stop() if rank == 0 else None
+    totals = TrajectoryTotals()
     for d in done:
         totals.add_frame(d["sum_mean"], d["n_refs"], d["n_pairs"])
     totals = all_reduce_totals(totals, dev)
 
+    props = torch.cuda.get_device_properties(dev)
+    sms = props.multi_processor_count
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    f_clk = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    if world > 1:      # every rank needs the same clock figure for the sub-measurements' fractions
+        fc = torch.tensor([f_clk if rank == 0 else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(fc)
+        f_clk = float(fc.item())
+    configs = None
+    if not args.no_configs:
+        del b
+        torch.cuda.empty_cache()
+        configs = bench_other_configs(dev, world, rank, sms, f_clk, dist)
+
     if rank == 0:
-        props = torch.cuda.get_device_properties(dev)
-        sms = props.multi_processor_count
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        f_clk = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
         traffic, traffic_src = None, None
-        try:   # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the sweep kernel (ncu --set full capture)
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_sweep_half_v6.json")))
-            traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
-            traffic_src = prof["source"]
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the sweep kernel (ncu --set full capture),
+            # valid only for the kernel sources it was measured on
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r2_sweep_half.json")))
+            if prof.get("kernel_source_sha16") == kernel_source_hash():
+                traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
+                traffic_src = prof["source"]
+            else:
+                traffic_src = "profiles/r2_sweep_half.json is stale (kernel sources changed since the capture)"
         except (OSError, KeyError, ValueError):
             pass
         peak_issue = sms * 128 * f_clk * 1e6                       # lane-instructions / s
-        pairs_serial = float(tot_serial[:len(serial_ev), 2].sum().item()) / len(serial_ev)
         sweep_pairs_s = pairs_serial / (sweep_ms * 1e-3)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         build_ms = serial_ms - sweep_ms
+        e2e_ms = 1e3 * float(e2e_t.item()) / steps
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm_done,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64 (packed FP32 cutoff filter with exact FP64 re-check, FP64 cos^2, 2^-47 fixed-point sums)", "data": "synthetic",
-            "config": {"workload": WORKLOAD["name"], "bonds_per_frame": n, "frames_per_step_per_gpu": 1,
-                       "pairs_per_frame": pairs_local // steps, "cell_grid": list(grid.ncell_axis),
-                       "l2": "~%d MB touched per frame (L2 is 126 MB), %d distinct frames cycled"
-                             % (int(230e-6 * n), N_FRAME_VARIANTS),
-                       "frames_per_s": world * steps / (ms * 1e-3),
-                       "parallelism": "frames sharded, %d rank(s), one NCCL all-reduce of packed sums; %d frames in "
-                                      "flight per GPU (own stream / workspace each)" % (world, LANES),
-                       "S_mean": totals.mean_s},
+            "dtype": "f64 (packed FP32 cutoff filter with exact FP64 re-check, FP64 cos^2, 2^-47 fixed-point sums)",
+            "data": "synthetic", "config": static_config(n),
+            "details": {"warmup_frames_actual": warm_done, "steps_timed": steps, "pairs_per_frame": pairs_local // steps,
+                        "cell_grid": list(grid.ncell_axis), "frames_per_s": world * steps / (ms * 1e-3),
+                        "parallelism": "frames sharded, %d rank(s), ONE NCCL all-reduce of the packed sums and counts; %d "
+                                       "frames in flight per GPU (own stream / workspace each)" % (world, LANES),
+                        "S_mean": totals.mean_s},
             "e2e": {"value": float(e2e_p.item()) / float(e2e_t.item()), "unit": UNIT,
                     "h2d_bytes_per_step": pipe.h2d_bytes_per_frame, "d2h_bytes_per_step": pipe.d2h_bytes_per_frame,
-                    "ms_per_step": 1e3 * float(e2e_t.item()) / steps,
-                    "note": "FramePipeline.submit(): pinned host positions -> H2D -> K1-K4 -> 48-byte totals -> D2H, "
-                            "%d frames in flight (copy of frame k+1 and its HBM-side kernels overlap the sweep of frame k); "
-                            "topology resident%s" % (pipe.depth, "; host process bound to the GPU's CPU set" if numa_bound else "")},
-            "gpu_launches": steps * 9 + (2 if world > 1 else 0),
+                    "ms_per_step": e2e_ms, "host_submit_us": host_submit_us, "graph_nodes_per_frame": graph_nodes,
+                    "h2d_achieved_gbs": world * pipe.h2d_bytes_per_frame / (e2e_ms * 1e-3) / 1e9,
+                    "h2d_ceiling_gbs": h2d_ceiling,
+                    "h2d_ceiling_how": "the same pinned frame buffers copied to the same device buffers on every rank "
+                                       "at once, no kernels (CUDA events, max over ranks)",
+                    "note": "FramePipeline.submit(): pinned host positions -> ONE H2D copy -> K1-K4 replayed from a "
+                            "captured CUDA graph -> 48-byte totals -> D2H, %d frames in flight (copy of frame k+1 and its "
+                            "HBM-side kernels overlap the sweep of frame k); topology resident%s" % (
+                                pipe.depth, "; host process bound to the GPU's CPU set" if numa_bound else "")},
+            "gpu_launches": steps * KERNELS_PER_FRAME + (1 if world > 1 else 0),
             "clocks": clocks,
             "roofline": {
                 "bound": "fp_issue", "kernel": "p2_sweep_half_kernel (+ p2_fixup_kernel)",
                 "achieved": sweep_pairs_s * W_LANE_INSTR_PER_PAIR / 1e12,
                 "peak": peak_issue / 1e12, "unit": "Tlane-instr/s",
                 "frac": sweep_pairs_s * W_LANE_INSTR_PER_PAIR / peak_issue,
-                "traffic": traffic, "traffic_source": traffic_src,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel_source_sha16": kernel_source_hash(),
                 "how": "SURVEY 8(d): ordered pairs/s x 55.2 lane-instr/pair (full-shell bound; the kernel is half-shell: "
                        "every unordered pair is decided once and counted for both partners) over SMs x 128 lanes x f_clk "
                        "(%d SMs, %.0f MHz %s); sweep %.3f ms/launch: CUDA events around the K3 launches of %d frames "
                        "serialised on one stream right after the timed region (in the timed region up to %d frames "
                        "share the SMs; the in-stream duration there is %.3f ms)"
                        % (sms, f_clk, "sampled under load" if clocks and clocks.get("sm_mhz") else "max clock", sweep_ms,
-                          len(serial_ev), LANES, sweep_ms_overlapped),
+                          n_serial, LANES, sweep_ms_overlapped),
                 "sweep_ms": sweep_ms, "sweep_ms_in_timed_region": sweep_ms_overlapped, "serial_frame_ms": serial_ms,
                 "sweep_pairs_per_s": sweep_pairs_s,
                 "hbm": {"bound": "hbm", "stage": "K1+K2+K4 build/reduce stages", "achieved": BYTES_PER_BOND * n /
@@ -445,6 +733,8 @@ def run_ours(args):
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                         "ms": build_ms, "algorithmic_bytes": BYTES_PER_BOND * n}},
         }
+        if configs is not None:
+            line["configs"] = configs
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line
         print(json.dumps(line), flush=True)
@@ -459,6 +749,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the sub-measurements of configs 3, 4 and 5")
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     global WORKLOAD

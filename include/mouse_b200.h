@@ -170,6 +170,11 @@ int mouse_rdf_frame(const double *pos /*DEV [n][3]*/, const int32_t *type /*DEV 
                     const double *edges /*HOST [nbin+1]*/, int32_t nbin, void *ws, size_t ws_bytes,
                     int64_t *hist /*DEV*/, void *stream);
 
+/* mouse_rdf_frame with two optional cudaEvent_t handles recorded right before / after the K5 launches (bench.py). */
+int mouse_rdf_frame_timed(const double *pos, const int32_t *type, const int32_t *mol, int64_t n_atoms, int32_t ntypes,
+                          const mouse_grid_t *grid, uint32_t flags, const double *edges, int32_t nbin, void *ws,
+                          size_t ws_bytes, int64_t *hist, void *ev_sweep_begin, void *ev_sweep_end, void *stream);
+
 /* One reference against a caller-built array: the reference's per-call granularity.
  * mouse_p2_single_ref replaces calculateAveCosSqForReference (ordering_functions.py:91-119):
  *   np_bonds DEV (9,n) f64 row-major = createNumpyBondsArrayFromConfig's array (:41);
@@ -194,6 +199,14 @@ int mouse_rdf_single_ref(const double *np_atoms, int64_t n, const double *ref, c
  * updateHistogram (lammpack_misc.py:185-189), hist[nbins] = values the reference would raise IndexError on. */
 int mouse_director_p2(const double *vec, const uint8_t *mask, int64_t n_bonds, const double *director, double *out_s,
                       int64_t *hist, double smin, double smax, int32_t nbins, void *stream);
+
+/* Per-atom colouring of --out-pdb (storeAsAtomtypes, ordering_functions.py:207-220): for every atom the mean of
+ * 1.5*m-0.5 over its incident bonds with cnt > 0 (CSR adjacency row_ptr[n_atoms+1] / bond_of[], bonds ascending),
+ * as the integer of the type string: code >= 0 -> "C%02d" % code; code < 0 -> "Cm%02d" % (-code - 1); INT32_MIN -> the
+ * atom has no bond with a value and keeps its type.  direct != 0: `mean` already holds the per-bond value (director
+ * P2 of CalculateCrystallinityParameter, :263-281) and cnt is a 0/1 selection.  All pointers DEV. */
+int mouse_atom_colour(const double *mean, const int32_t *cnt, const int64_t *row_ptr, const int32_t *bond_of,
+                      int64_t n_atoms, int32_t direct, int32_t *code, void *stream);
 
 /* Debug: the 8 int64 workspace counters (0 zero-length, 1 guard-band redos, 4-7 phase cycle timers when built
  * with -DMOUSE_PHASE_TIMERS); synchronises `stream`. */

@@ -49,8 +49,8 @@ EXPORTS = [
     "mouse_bond_build_triclinic",
     "mouse_workspace_bytes", "mouse_cell_build", "mouse_p2_sweep", "mouse_p2_pair_lists", "mouse_p2_reduce",
     "mouse_p2_frame", "mouse_p2_frame_timed", "mouse_p2_frame_graph_create", "mouse_p2_frame_graph_launch",
-    "mouse_p2_frame_graph_nodes", "mouse_p2_frame_graph_destroy", "mouse_rdf_frame", "mouse_single_ref_workspace_bytes", "mouse_p2_single_ref",
-    "mouse_rdf_single_ref", "mouse_director_p2", "mouse_debug_counters", "mouse_parse_doubles",
+    "mouse_p2_frame_graph_nodes", "mouse_p2_frame_graph_destroy", "mouse_rdf_frame_timed", "mouse_rdf_frame", "mouse_single_ref_workspace_bytes", "mouse_p2_single_ref",
+    "mouse_rdf_single_ref", "mouse_director_p2", "mouse_atom_colour", "mouse_debug_counters", "mouse_parse_doubles",
 ]
 
 
@@ -96,11 +96,14 @@ def lib():
     L.mouse_p2_frame_graph_nodes.argtypes = [vp]
     L.mouse_p2_frame_graph_destroy.argtypes = [vp]
     L.mouse_rdf_frame.argtypes = [vp, vp, vp, i64, i32, gp, u32, C.POINTER(C.c_double), i32, vp, C.c_size_t, vp, vp]
+    L.mouse_rdf_frame_timed.argtypes = [vp, vp, vp, i64, i32, gp, u32, C.POINTER(C.c_double), i32, vp, C.c_size_t, vp, vp,
+                                        vp, vp]
     L.mouse_single_ref_workspace_bytes.restype = C.c_size_t
     L.mouse_p2_single_ref.argtypes = [vp, i64, C.POINTER(C.c_double), C.POINTER(C.c_double), dbl, dbl, u32, vp, vp, vp]
     L.mouse_rdf_single_ref.argtypes = [vp, i64, C.POINTER(C.c_double), C.POINTER(C.c_double), u32,
                                        C.POINTER(C.c_double), i32, vp, vp, vp]
     L.mouse_director_p2.argtypes = [vp, vp, i64, C.POINTER(C.c_double), vp, vp, dbl, dbl, i32, vp]
+    L.mouse_atom_colour.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp]
     L.mouse_debug_counters.argtypes = [gp, i64, vp, vp, vp]
     L.mouse_parse_doubles.argtypes = [C.c_char_p, i64, vp, i64]
     L.mouse_parse_doubles.restype = i64

@@ -29,6 +29,8 @@ int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, 
                            int32_t nbin, const Workspace &w, int64_t *hist, cudaStream_t st);
 int mouse_launch_director_p2(const double *vec, const uint8_t *mask, int64_t n, const double *director, double *out_s,
                              int64_t *hist, double smin, double smax, int32_t nbins, cudaStream_t st);
+int mouse_launch_atom_colour(const double *mean, const int32_t *cnt, const int64_t *row_ptr, const int32_t *bond_of,
+                             int64_t n_atoms, int32_t direct, int32_t *code, cudaStream_t st);
 int mouse_p2_uses_fast(const mouse_grid_t *grid, int64_t n, uint32_t flags, bool lists);
 
 static thread_local char g_err[512] = "";
@@ -354,9 +356,9 @@ int mouse_p2_frame_graph_destroy(void *graph) {
   return MOUSE_OK;
 }
 
-int mouse_rdf_frame(const double *pos, const int32_t *type, const int32_t *mol, int64_t n_atoms, int32_t ntypes,
-                    const mouse_grid_t *grid, uint32_t flags, const double *edges, int32_t nbin, void *ws,
-                    size_t ws_bytes, int64_t *hist, void *stream) {
+int mouse_rdf_frame_timed(const double *pos, const int32_t *type, const int32_t *mol, int64_t n_atoms, int32_t ntypes,
+                          const mouse_grid_t *grid, uint32_t flags, const double *edges, int32_t nbin, void *ws,
+                          size_t ws_bytes, int64_t *hist, void *ev_sweep_begin, void *ev_sweep_end, void *stream) {
   Workspace w;
   int rc = check_ws("mouse_rdf_frame", n_atoms, grid, ws, ws_bytes, &w);
   if (rc) return rc;
@@ -370,7 +372,17 @@ int mouse_rdf_frame(const double *pos, const int32_t *type, const int32_t *mol, 
   w.rdf_first = edges[0];
   // the fast sweep's cutoff is the last edge: it needs a grid planned for exactly that cutoff
   if (!(grid->rcut == edges[nbin]) || !(edges[nbin] > edges[0])) flags |= MOUSE_FORCE_EXACT;
-  return mouse_launch_rdf_sweep(grid, flags, n_atoms, ntypes, w.edges, nbin, w, hist, st);
+  if (ev_sweep_begin) MOUSE_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev_sweep_begin, st));
+  rc = mouse_launch_rdf_sweep(grid, flags, n_atoms, ntypes, w.edges, nbin, w, hist, st);
+  if (ev_sweep_end) MOUSE_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev_sweep_end, st));
+  return rc;
+}
+
+int mouse_rdf_frame(const double *pos, const int32_t *type, const int32_t *mol, int64_t n_atoms, int32_t ntypes,
+                    const mouse_grid_t *grid, uint32_t flags, const double *edges, int32_t nbin, void *ws,
+                    size_t ws_bytes, int64_t *hist, void *stream) {
+  return mouse_rdf_frame_timed(pos, type, mol, n_atoms, ntypes, grid, flags, edges, nbin, ws, ws_bytes, hist, nullptr,
+                               nullptr, stream);
 }
 
 int mouse_director_p2(const double *vec, const uint8_t *mask, int64_t n_bonds, const double *director, double *out_s,
@@ -382,6 +394,15 @@ int mouse_director_p2(const double *vec, const uint8_t *mask, int64_t n_bonds, c
     return MOUSE_EINVAL;
   }
   return mouse_launch_director_p2(vec, mask, n_bonds, director, out_s, hist, smin, smax, nbins, (cudaStream_t)stream);
+}
+
+int mouse_atom_colour(const double *mean, const int32_t *cnt, const int64_t *row_ptr, const int32_t *bond_of,
+                      int64_t n_atoms, int32_t direct, int32_t *code, void *stream) {
+  if (n_atoms < 0 || (n_atoms > 0 && (!mean || !cnt || !row_ptr || !bond_of || !code))) {
+    mouse_set_error("mouse_atom_colour: bad argument");
+    return MOUSE_EINVAL;
+  }
+  return mouse_launch_atom_colour(mean, cnt, row_ptr, bond_of, n_atoms, direct, code, (cudaStream_t)stream);
 }
 
 // Debug / tuning: copies the 8 workspace counters to host (synchronises the stream).

@@ -318,3 +318,39 @@ int mouse_launch_p2_reduce(const double *sum, const int32_t *cnt, int64_t n, con
   MOUSE_LAUNCH_CHECK("p2_reduce_kernel");
   return MOUSE_OK;
 }
+
+// ---- per-atom colouring (--out-pdb): ordering_functions.py:207-220.  Per atom, the mean of 1.5 * m - 0.5 over its
+// incident bonds that produced a value, summed in ascending bond order (a per-atom list gathered through a CSR
+// adjacency: the reference appends in bond order and np.mean of fewer than 8 values adds them sequentially), then
+// the integer of the type string: code = int(mean * 100) >= 0 -> "C%02d", or -(int(mean * -100)) - 1 < 0 -> "Cm%02d";
+// INT_MIN = no bond with a value (the atom keeps its type).
+__global__ void __launch_bounds__(256) atom_colour_kernel(const double *__restrict__ mean, const int32_t *__restrict__ cnt,
+                                                          const int64_t *__restrict__ row_ptr,
+                                                          const int32_t *__restrict__ bond_of, int64_t n_atoms, int direct,
+                                                          int32_t *__restrict__ code) {
+  const int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (a >= n_atoms) return;
+  double sum = 0.0;
+  int k = 0;
+  for (int64_t e = row_ptr[a]; e < row_ptr[a + 1]; ++e) {
+    const int b = bond_of[e];
+    if (cnt[b] > 0) {
+      sum = __dadd_rn(sum, direct ? mean[b] : __dsub_rn(__dmul_rn(1.5, mean[b]), 0.5));
+      k += 1;
+    }
+  }
+  int c = (int)0x80000000;
+  if (k > 0) {
+    const double m = __ddiv_rn(sum, (double)k);
+    c = m >= 0.0 ? (int)__dmul_rn(m, 100.0) : -(int)__dmul_rn(m, -100.0) - 1;
+  }
+  code[a] = c;
+}
+
+int mouse_launch_atom_colour(const double *mean, const int32_t *cnt, const int64_t *row_ptr, const int32_t *bond_of,
+                             int64_t n_atoms, int32_t direct, int32_t *code, cudaStream_t st) {
+  if (n_atoms == 0) return MOUSE_OK;
+  atom_colour_kernel<<<(unsigned)((n_atoms + 255) / 256), 256, 0, st>>>(mean, cnt, row_ptr, bond_of, n_atoms, direct, code);
+  MOUSE_LAUNCH_CHECK("atom_colour_kernel");
+  return MOUSE_OK;
+}

@@ -85,51 +85,59 @@ def select_rectangular(config, cutx=False, xrelmin=0., xrelmax=1., cuty=False, y
     return new
 
 
+class Histogram(dict):
+    """The reference's histogram record (``lammpack_misc.py:177-212``) - a plain dict with the keys ``min, max,
+    nbins, step, values, norm`` that callers index directly - plus the operations on it as methods.  Two quirks of
+    the reference are part of the contract: the bin of a value is ``int(nbins * (v - min) / (max - min))`` used as a
+    Python list index (negative wraps around, ``v == max`` raises ``IndexError``), while the printed abscissa is
+    ``min + step * i`` with ``step = (max - min) / (nbins - 1)``."""
+
+    def __init__(self, lo, hi, nbins):
+        if not isinstance(nbins, int):
+            raise NameError("Number of bins (" + str(nbins) + ") in the histogram must be integer")
+        if nbins < 1:
+            raise NameError("Invalid number of bins in the histogram (" + str(nbins) + ")")
+        span = hi - lo
+        super().__init__(min=lo, max=hi, nbins=nbins, step=span / (nbins - 1) if nbins > 1 else span,
+                         values=[0.] * nbins, norm=[0.] * nbins)
+
+    def bin_of(self, value):
+        return int(len(self["values"]) * (value - self["min"]) / (self["max"] - self["min"]))
+
+    def add(self, value, weight=1):
+        self["values"][self.bin_of(value)] += weight
+
+    def normalise(self, norm_too=False):
+        for key in ("values", "norm") if norm_too else ("values",):
+            total = sum(self[key], 0.)          # left to right, like the reference's running sum
+            if total > 0.:
+                self[key] = [v / total for v in self[key]]
+
+    def lines(self, norm=False):
+        weights = self["norm"] if norm else [1] * self["nbins"]
+        rows = ((self["min"] + self["step"] * i, self["values"][i] / w if norm else self["values"][i])
+                for i, w in zip(range(self["nbins"]), weights))
+        return "".join(str(x) + "\t" + str(v) + "\n" for x, v in rows)
+
+
 def createHistogram(minvalue, maxvalue, nbins):
-    """Reference ``lammpack_misc.py:177-183``: labels use step = (max-min)/(nbins-1)."""
-    if not isinstance(nbins, int):
-        raise NameError("Number of bins (" + str(nbins) + ") in the histogram must be integer")
-    if nbins > 1:
-        step = (maxvalue - minvalue) / (nbins - 1)
-    elif nbins == 1:
-        step = maxvalue - minvalue
-    else:
-        raise NameError("Invalid number of bins in the histogram (" + str(nbins) + ")")
-    return {"min": minvalue, "max": maxvalue, "nbins": nbins, "step": step,
-            "values": [0.] * nbins, "norm": [0.] * nbins}
+    """Reference ``lammpack_misc.py:177-183``."""
+    return Histogram(minvalue, maxvalue, nbins)
 
 
 def updateHistogram(value, histogram, weight=1):
-    """Reference ``lammpack_misc.py:185-189`` (Python list indexing: negative wraps, too large raises)."""
-    ibin = int(len(histogram["values"]) * (value - histogram["min"]) / (histogram["max"] - histogram["min"]))
-    histogram["values"][ibin] += weight
+    """Reference ``lammpack_misc.py:185-189``."""
+    Histogram.add(histogram, value, weight)
 
 
 def normHistogram(histogram, normInternalNorm=False):
     """Reference ``lammpack_misc.py:191-203``."""
-    histsum = 0.
-    for v in histogram["values"]:
-        histsum += v
-    if histsum > 0.:
-        histogram["values"] = [v / histsum for v in histogram["values"]]
-    if normInternalNorm:
-        nsum = 0.
-        for v in histogram["norm"]:
-            nsum += v
-        if nsum > 0:
-            histogram["norm"] = [v / nsum for v in histogram["norm"]]
+    Histogram.normalise(histogram, normInternalNorm)
 
 
 def printHistogram(histogram, norm=False):
-    """Reference ``lammpack_misc.py:205-212``: ``"<x>\\t<value>\\n"`` per bin, x = min + step*i."""
-    s = ''
-    for i in range(histogram["nbins"]):
-        x = histogram["min"] + histogram["step"] * i
-        value = histogram["values"][i]
-        if norm:
-            value /= histogram["norm"][i]
-        s += str(x) + "\t" + str(value) + "\n"
-    return s
+    """Reference ``lammpack_misc.py:205-212``: ``"<x>\\t<value>\\n"`` per bin."""
+    return Histogram.lines(histogram, norm)
 
 
 def printRdfs(rdfs, norm=True, out=None):

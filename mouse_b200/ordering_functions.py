@@ -284,20 +284,48 @@ def CalculateOrientationOrderParameter(config, bondtypes, rmin=0., rmax=0., stor
         return s_hist
 
 
-def _store_as_atomtypes(config, fa, res):
-    """``ordering_functions.py:207-220``: per atom, mean P2 of its reference bonds that produced
-    a value; the per-bond values come from the device, the (tiny) per-atom mean is host logic."""
-    mean = res.mean.cpu().numpy()
-    count = res.count.cpu().numpy()
-    per_atom = {}
-    for b in np.flatnonzero(count > 0):
-        p2 = 1.5 * mean[b] - 0.5
-        for a in fa.bond_atoms[b]:
-            per_atom.setdefault(int(a), []).append(p2)
+def atom_colour_codes(fa, res=None, values=None, selected=None):
+    """Per-atom colour codes of ``storeAsAtomtypes`` (``ordering_functions.py:207-220``) computed on the device: a CSR
+    adjacency atom -> incident bonds (built once per topology with vectorised NumPy, bonds ascending) feeds a
+    segmented reduction of the per-bond P2 (``mouse_atom_colour``).  Returns an int32 array: code >= 0 -> ``C%02d``,
+    code < 0 -> ``Cm%02d`` of ``-code - 1``, INT32_MIN -> atom without a value.  Either ``res`` (a ``P2Result``: value
+    = 1.5 * mean - 0.5 of the bonds with a count) or ``values`` / ``selected`` (device tensors: per-bond value and
+    int32 0/1 selection, the director P2 of ``CalculateCrystallinityParameter``)."""
+    key = "_csr"
+    if key not in fa._cache:
+        ends = fa.bond_atoms.astype(np.int64).ravel()                    # (b0.a1, b0.a2, b1.a1, ...)
+        order = np.argsort(ends, kind="stable")                          # per atom: ascending bond index
+        row_ptr = np.zeros(fa.n_atoms + 1, np.int64)
+        np.cumsum(np.bincount(ends, minlength=fa.n_atoms), out=row_ptr[1:])
+        fa._cache[key] = (row_ptr, (order // 2).astype(np.int32))
+    row_ptr, bond_of = fa._cache[key]
+    val, sel, direct = (res.mean, res.count, 0) if res is not None else (values, selected, 1)
+    dev = val.device
+    code = torch.empty(fa.n_atoms, dtype=torch.int32, device=dev)
+    rp, bo = torch.as_tensor(row_ptr).to(dev), torch.as_tensor(bond_of).to(dev)
+    _lib.check(_lib.lib().mouse_atom_colour(C.c_void_p(val.data_ptr()), C.c_void_p(sel.data_ptr()),
+                                            C.c_void_p(rp.data_ptr()), C.c_void_p(bo.data_ptr()), fa.n_atoms, direct,
+                                            C.c_void_p(code.data_ptr()),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mouse_atom_colour")
+    return code.cpu().numpy()
+
+
+_COLOUR_NAMES = None
+
+
+def _store_as_atomtypes(config, fa, res=None, values=None, selected=None):
+    """``ordering_functions.py:207-220``: per atom, mean P2 of its reference bonds that produced a value ->
+    ``atom.type = "C%02d"`` / ``"Cm%02d"``.  The reduction runs on the device (``atom_colour_codes``); the host only
+    turns the integer codes into strings (one table look-up per atom)."""
+    global _COLOUR_NAMES
+    if _COLOUR_NAMES is None:
+        _COLOUR_NAMES = {c: "C%02d" % c for c in range(0, 201)}
+        _COLOUR_NAMES.update({-c - 1: "Cm%02d" % c for c in range(0, 201)})
+    code = atom_colour_codes(fa, res, values, selected)
     atoms = config.atoms()
-    for a, vals in per_atom.items():
-        m = np.mean(vals)
-        atoms[a].type = ("C" + "%02d" % int(m * 100)) if m >= 0. else ("Cm" + "%02d" % int(m * -100))
+    for a in np.flatnonzero(code != np.iinfo(np.int32).min):
+        c = int(code[a])
+        atoms[a].type = _COLOUR_NAMES.get(c) or (("C%02d" % c) if c >= 0 else ("Cm%02d" % (-c - 1)))
 
 
 # --------------------------------------------------------------------------------------- next rows (SURVEY 8(f) rank 4)
@@ -344,15 +372,7 @@ def CalculateCrystallinityParameter(config, bondtypes, reference_vector=None, st
             raise IndexError("list index out of range")
         s_hist["values"] = [float(v) for v in h[:int(sbins)]]
         if storeAsAtomtypes and not isinstance(config, FrameArrays):
-            s = out_s.cpu().numpy()
-            per_atom = {}
-            for b in np.flatnonzero(mask):
-                for a in fa.bond_atoms[b]:
-                    per_atom.setdefault(int(a), []).append(s[b])
-            atoms = config.atoms()
-            for a, vals in per_atom.items():
-                mval = np.mean(vals)
-                atoms[a].type = ("C" + "%02d" % int(mval * 100)) if mval >= 0. else ("Cm" + "%02d" % int(mval * -100))
+            _store_as_atomtypes(config, fa, values=out_s, selected=m.to(torch.int32))      # (:274-281)
         normHistogram(s_hist, normInternalNorm=True)
         return s_hist
 

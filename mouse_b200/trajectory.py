@@ -21,27 +21,51 @@ def shard_range(n_frames: int, rank: int, world: int):
 
 @dataclass
 class TrajectoryTotals:
-    """What the final all-reduce carries (exactly reducible integers + f64 sums)."""
+    """What the final all-reduce carries: the order-parameter sums, the counts and the histograms of a trajectory
+    (reference semantics being reduced: ``ordering_functions.py:203-206, 221-227`` for S and the P2 histogram,
+    ``:162-176`` for the RDF counts)."""
     sum_s: float = 0.0        # sum over frames of S_frame
     n_frames: int = 0         # frames that produced an S
     sum_mean: float = 0.0     # sum over frames of sum_i m_i
     n_refs: int = 0           # sum over frames of i_s
     n_pairs: int = 0          # ordered in-cutoff pairs counted
     n_skipped_frames: int = 0  # frames without any reference that has neighbours
+    n_hist_over: int = 0      # P2 values the reference's updateHistogram would raise IndexError on
+    p2_hist: np.ndarray | None = None    # int64 [sbins]: per-vector P2 histogram counts summed over frames
+    rdf_hist: np.ndarray | None = None   # int64 [npairs, nbin]: RDF pair counts summed over frames
+
+    # Everything rides in ONE float64 buffer: [sum_s, sum_mean | n_frames, n_refs, n_pairs, n_skipped, n_hist_over |
+    # p2_hist... | rdf_hist...].  The integer fields are stored as float64, which adds integers exactly (and in any
+    # order) as long as every partial sum stays below 2^53 - checked when packing.
+    _N_SCALARS = 7
 
     def pack(self, device):
-        f = torch.tensor([self.sum_s, self.sum_mean], dtype=torch.float64, device=device)
-        i = torch.tensor([self.n_frames, self.n_refs, self.n_pairs, self.n_skipped_frames], dtype=torch.int64,
-                         device=device)
-        return f, i
+        ints = [self.n_frames, self.n_refs, self.n_pairs, self.n_skipped_frames, self.n_hist_over]
+        parts = [np.array([self.sum_s, self.sum_mean], np.float64), np.array(ints, np.float64)]
+        for h in (self.p2_hist, self.rdf_hist):
+            if h is not None:
+                parts.append(np.asarray(h, np.int64).ravel().astype(np.float64))
+        buf = np.concatenate(parts)
+        if np.abs(buf[2:]).max() >= 2.0**53 / 64:      # every field keeps head-room for up to 64 ranks
+            raise OverflowError("TrajectoryTotals: integer totals too large for an exact float64 all-reduce")
+        return torch.from_numpy(buf).to(device)
 
-    @classmethod
-    def unpack(cls, f, i):
-        f, i = f.cpu().tolist(), i.cpu().tolist()
-        return cls(sum_s=f[0], sum_mean=f[1], n_frames=int(i[0]), n_refs=int(i[1]), n_pairs=int(i[2]),
-                   n_skipped_frames=int(i[3]))
+    def unpack_into(self, buf):
+        b = buf.cpu().numpy()
+        self.sum_s, self.sum_mean = float(b[0]), float(b[1])
+        (self.n_frames, self.n_refs, self.n_pairs, self.n_skipped_frames,
+         self.n_hist_over) = (int(round(v)) for v in b[2:self._N_SCALARS])
+        off = self._N_SCALARS
+        if self.p2_hist is not None:
+            k = self.p2_hist.size
+            self.p2_hist = np.rint(b[off:off + k]).astype(np.int64).reshape(self.p2_hist.shape)
+            off += k
+        if self.rdf_hist is not None:
+            k = self.rdf_hist.size
+            self.rdf_hist = np.rint(b[off:off + k]).astype(np.int64).reshape(self.rdf_hist.shape)
+        return self
 
-    def add_frame(self, sum_mean, n_refs, n_pairs):
+    def add_frame(self, sum_mean, n_refs, n_pairs, hist=None, n_hist_over=0):
         if n_refs > 0:
             self.sum_s += 1.5 * sum_mean / n_refs - 0.5
             self.n_frames += 1
@@ -50,22 +74,75 @@ class TrajectoryTotals:
         self.sum_mean += sum_mean
         self.n_refs += int(n_refs)
         self.n_pairs += int(n_pairs)
+        self.n_hist_over += int(n_hist_over)
+        if hist is not None:
+            h = np.asarray(hist, np.int64)
+            self.p2_hist = h.copy() if self.p2_hist is None else self.p2_hist + h
+
+    def add_rdf_frame(self, hist):
+        h = np.asarray(hist, np.int64)
+        self.rdf_hist = h.copy() if self.rdf_hist is None else self.rdf_hist + h
+        self.n_frames += 1
 
     @property
     def mean_s(self):
         return self.sum_s / self.n_frames if self.n_frames else float("nan")
 
+    def p2_histogram(self, smin, smax, sbins):
+        """The reference's histogram dict (``ordering_functions.py:187-193, 225-227``) of the whole trajectory:
+        counts summed over frames (and ranks), then ``normHistogram``; raises ``IndexError`` if any frame did."""
+        from .lammpack_misc import createHistogram, normHistogram
+        if self.n_hist_over > 0:
+            raise IndexError("list index out of range")
+        h = createHistogram(smin, smax, sbins)
+        for i in range(sbins):
+            sleft, sright = smin + i * h["step"], smin + (i + 1) * h["step"]
+            h["norm"][i] = 1. / ((2. / 3. * (sleft + 0.5))**0.5 + (2. / 3. * (sright + 0.5))**0.5)
+        h["values"] = [float(v) for v in (self.p2_hist if self.p2_hist is not None else np.zeros(sbins))]
+        normHistogram(h)
+        return h
+
+
+def _dist_state():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
 
 def all_reduce_totals(t: TrajectoryTotals, device) -> TrajectoryTotals:
-    """The single collective of the path: sum-all-reduce of the packed totals (two tiny tensors:
-    f64 sums and i64 counts; the integers reduce exactly)."""
-    import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    """The single collective of the path: ONE sum-all-reduce of the packed totals (sums, counts and histogram
+    bins in one float64 buffer; the integer fields reduce exactly).  Every rank must carry histograms of the same
+    shape (or none)."""
+    dist, _, world = _dist_state()
+    if world == 1:
         return t
-    f, i = t.pack(device)
-    dist.all_reduce(f, op=dist.ReduceOp.SUM)
-    dist.all_reduce(i, op=dist.ReduceOp.SUM)
-    return TrajectoryTotals.unpack(f, i)
+    buf = t.pack(device)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    return t.unpack_into(buf)
+
+
+def gather_per_frame(per_frame, n_frames, device):
+    """The reference prints one S per frame in input order (``calculate_local_ordering.py:39-76``): every rank's
+    (frame index, S) block is all-gathered (F x 8 bytes) and put back in frame order.  Returns a float64 array of
+    ``n_frames`` values (NaN = the frame produced no S) on every rank."""
+    dist, rank, world = _dist_state()
+    out = np.full(n_frames, np.nan)
+    if world == 1:
+        for f, s in per_frame:
+            out[f] = s
+        return out
+    width = max(((r + 1) * n_frames) // world - (r * n_frames) // world for r in range(world))
+    mine = torch.full((max(width, 1),), float("nan"), dtype=torch.float64, device=device)
+    lo, _ = shard_range(n_frames, rank, world)
+    for f, s in per_frame:
+        mine[f - lo] = float(s)
+    blocks = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(blocks, mine)
+    for r, blk in enumerate(blocks):
+        a, b = shard_range(n_frames, r, world)
+        out[a:b] = blk.cpu().numpy()[:b - a]
+    return out
 
 
 class FramePipeline:
@@ -78,7 +155,7 @@ class FramePipeline:
     until the slot is reused."""
 
     def __init__(self, bond_atoms, mol, box, rcut, n_atoms, same_molecule=True, nbr_mask=None, ref_mask=None,
-                 device=None, depth=3, use_graph=True, tilt=None):
+                 device=None, depth=3, use_graph=True, tilt=None, hist_args=None):
         engine.require_cuda()
         self.device = torch.device(device or "cuda")
         self.n_atoms = int(n_atoms)
@@ -98,6 +175,7 @@ class FramePipeline:
         nbytes = L.mouse_workspace_bytes(self.n, C.byref(self.grid))
         self.depth = depth
         self.use_graph = bool(use_graph)     # frames with the pipeline's own box / cutoff replay a captured CUDA graph
+        self.hist_args = None if hist_args is None else (float(hist_args[0]), float(hist_args[1]), int(hist_args[2]))
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.slots = []
         for _ in range(depth):
@@ -114,6 +192,9 @@ class FramePipeline:
                 cnt=torch.empty(self.n, dtype=torch.int32, device=self.device),
                 mean=torch.empty(self.n, dtype=torch.float64, device=self.device)))
             assert self.slots[-1]["ws"].data_ptr() % 256 == 0
+            if self.hist_args is not None:       # per-vector P2 histogram of the frame (mode='histo', :187-193, 203)
+                self.slots[-1]["hist"] = torch.zeros(self.hist_args[2], dtype=torch.int64, device=self.device)
+                self.slots[-1]["hist_host"] = torch.zeros(self.hist_args[2], dtype=torch.int64).pin_memory()
         self._next = 0
         self._pending = []
         self.h2d_bytes_per_frame = self.n_atoms * 3 * 8
@@ -178,6 +259,12 @@ class FramePipeline:
                 _lib.check(self.L.mouse_p2_frame_graph_launch(s["graph"], st), "mouse_p2_frame_graph_launch")
             else:
                 _lib.check(self.L.mouse_p2_frame(*args, st), "mouse_p2_frame")
+            if self.hist_args is not None:
+                smin, smax, sbins = self.hist_args
+                _lib.check(self.L.mouse_p2_reduce(p(s["sum"]), p(s["cnt"]), self.n, C.byref(grid), p(s["ws"]),
+                                                  s["ws"].numel(), p(s["mean"]), p(s["totals"]), p(s["hist"]), smin, smax,
+                                                  sbins, st), "mouse_p2_reduce")
+                s["hist_host"].copy_(s["hist"], non_blocking=True)
             s["totals_host"].copy_(s["totals"], non_blocking=True)
             s["done"].record(s["stream"])
         s["busy"] = True
@@ -193,8 +280,11 @@ class FramePipeline:
         if s in self._pending:
             self._pending.remove(s)
         t = s["totals_host"]
-        return dict(sum_mean=float(t.view(torch.float64)[0]), n_refs=int(t[1]), n_pairs=int(t[2]),
-                    n_zero_len=int(t[3]), tag=s.get("tag"))
+        out = dict(sum_mean=float(t.view(torch.float64)[0]), n_refs=int(t[1]), n_pairs=int(t[2]),
+                   n_zero_len=int(t[3]), n_hist_over=int(t[4]), tag=s.get("tag"))
+        if self.hist_args is not None:
+            out["hist"] = s["hist_host"].numpy().copy()
+        return out
 
     def drain(self):
         return [self._collect(s) for s in list(self._pending)]
@@ -217,33 +307,69 @@ class FramePipeline:
             pass
 
 
+def _frame_s(t):
+    return np.float64(1.5 * t["sum_mean"] / t["n_refs"] - 0.5) if t["n_refs"] else np.float64("nan")
+
+
 def local_ordering_trajectory(frames_positions, bond_atoms, mol, box, rcut, same_molecule=True, nbr_mask=None,
-                              ref_mask=None, device=None):
+                              ref_mask=None, device=None, hist_args=None, tilt=None, gather=False):
     """Per-frame S of this rank's shard plus the trajectory totals reduced over all ranks.
     ``frames_positions``: sequence of (N_a,3) float64 arrays / tensors (the WHOLE trajectory, every
-    rank indexes its own block).  Returns (list of (frame_index, S) for this rank, TrajectoryTotals)."""
-    import torch.distributed as dist
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank() if world > 1 else 0
+    rank indexes its own block).  ``hist_args`` = (smin, smax, sbins) also accumulates the per-vector P2 histogram of
+    every frame (``mode='histo'``), reduced with the sums in the same all-reduce.  Returns (list of (frame_index, S)
+    for this rank, TrajectoryTotals); with ``gather=True`` the first item is instead the float64 array of ALL frames'
+    S in frame order on every rank (the order the reference's CLI prints them in)."""
+    dist, rank, world = _dist_state()
     lo, hi = shard_range(len(frames_positions), rank, world)
     device = torch.device(device or "cuda")
     totals = TrajectoryTotals()
+    if hist_args is not None:
+        totals.p2_hist = np.zeros(int(hist_args[2]), np.int64)
     per_frame = []
     if hi > lo:
         # fixed topology and box: the frames go through the pipeline (several frames in flight, no per-frame sync)
         n_atoms = int(np.asarray(frames_positions[lo].shape)[0]) if hasattr(frames_positions[lo], "shape") \
             else len(frames_positions[lo])
         pipe = FramePipeline(bond_atoms, mol, box, rcut, n_atoms, same_molecule=same_molecule, nbr_mask=nbr_mask,
-                             ref_mask=ref_mask, device=device)
+                             ref_mask=ref_mask, device=device, hist_args=hist_args, tilt=tilt)
         done = []
         for f in range(lo, hi):
             done += pipe.submit(frames_positions[f], tag=f)
         done += pipe.drain()
+        pipe.close()
         for t in done:
-            totals.add_frame(t["sum_mean"], t["n_refs"], t["n_pairs"])
-            per_frame.append((t["tag"], np.float64(1.5 * t["sum_mean"] / t["n_refs"] - 0.5) if t["n_refs"]
-                              else np.float64("nan")))
-    return per_frame, all_reduce_totals(totals, device)
+            totals.add_frame(t["sum_mean"], t["n_refs"], t["n_pairs"], t.get("hist"), t.get("n_hist_over", 0))
+            per_frame.append((t["tag"], _frame_s(t)))
+    totals = all_reduce_totals(totals, device)
+    if gather:
+        return gather_per_frame(per_frame, len(frames_positions), device), totals
+    return per_frame, totals
+
+
+def pair_correlation_trajectory(frames_positions, type_code, mol, ntypes, box, rmin, rmax, nbin, same_molecule=True,
+                                device=None, tilt=None):
+    """RDF pair histograms of a trajectory (``CalculatePairCorrelationFunctions`` per frame,
+    ``ordering_functions.py:122-177``): the frames are block-sharded over the ranks like
+    ``local_ordering_trajectory``, each rank sums the int64 ``[npairs, nbin]`` counts of its frames on the device, and
+    the single all-reduce adds them over the ranks (integers: exact, identical to a one-rank run bit for bit).
+    Returns (hist int64 [npairs, nbin] of ALL frames, edges, TrajectoryTotals with ``n_frames``)."""
+    dist, rank, world = _dist_state()
+    lo, hi = shard_range(len(frames_positions), rank, world)
+    device = torch.device(device or "cuda")
+    npairs = int(ntypes) * (int(ntypes) + 1) // 2
+    acc = torch.zeros((npairs, int(nbin)), dtype=torch.int64, device=device)
+    edges = np.ascontiguousarray(np.histogram_bin_edges(np.zeros(0), bins=int(nbin), range=(rmin, rmax)), np.float64)
+    totals = TrajectoryTotals()
+    tc = engine.as_dev(type_code, torch.int32, device)
+    mc = engine.as_dev(mol, torch.int32, device) if mol is not None else None
+    for f in range(lo, hi):
+        h, _ = engine.rdf_frame(frames_positions[f], tc, mc, ntypes, box, rmin, rmax, nbin,
+                                same_molecule=same_molecule, device=device, tilt=tilt)
+        acc += h
+        totals.n_frames += 1
+    totals.rdf_hist = acc.cpu().numpy()
+    totals = all_reduce_totals(totals, device)
+    return totals.rdf_hist, edges, totals
 
 
 def local_ordering_from_dump(topology, dump_path, bondtypes=None, rcut=0., coords_type="scaled",
@@ -275,8 +401,8 @@ def local_ordering_from_dump(topology, dump_path, bondtypes=None, rcut=0., coord
             rc = float(rcut) if rcut != 0. else engine.half_diagonal(boxes[f])
             done += pipe.submit(positions[f], tag=int(timesteps[f]), box=boxes[f], rcut=rc)
         done += pipe.drain()
+        pipe.close()
         for t in done:
             totals.add_frame(t["sum_mean"], t["n_refs"], t["n_pairs"])
-            per_frame.append((t["tag"], np.float64(1.5 * t["sum_mean"] / t["n_refs"] - 0.5) if t["n_refs"]
-                              else np.float64("nan")))
+            per_frame.append((t["tag"], _frame_s(t)))
     return per_frame, all_reduce_totals(totals, device)

@@ -1,10 +1,11 @@
 """TEST INFRASTRUCTURE ONLY - runs the UNMODIFIED reference (mglagolev/mouse) in-process.
 
-Works only where ``/root/reference`` exists (the build container); the GPU box does
-not have it, so nothing under ``tests -m gpu``, ``smoke()`` or ``bench.py`` imports
-this module.  It is used by ``tests/golden/make_golden.py`` to produce the committed
-golden vectors and by the CPU test-suite (skipped when the reference is absent) to
-re-pin the NumPy restatement in ``oracle/p2_oracle.py`` against the real thing.
+Works where ``/root/reference`` exists (the build container) or where ``oracle/make_ref.py`` has staged the
+eight unmodified modules of the path under ``oracle/_ref/`` (git-ignored, travels to the GPU box).  Nothing under
+``tests -m gpu`` or ``smoke()`` imports this module; ``bench.py`` uses it only for the CPU legs that time the
+literal reference (``--impl reference``, ``cpu_baseline``).  It is used by ``tests/golden/make_golden.py`` to
+produce the committed golden vectors and by the CPU test-suite (skipped when the reference is absent) to re-pin the
+NumPy restatement in ``oracle/p2_oracle.py`` against the real thing.
 
 Shims, none of which touches reference source:
   * a stub ``natsort`` module (``natsorted = sorted``): ``lammpack_pdb_functions.py:3``
@@ -25,7 +26,9 @@ import types
 
 import numpy as np
 
-REFERENCE_DIR = os.environ.get("MOUSE_REFERENCE_DIR", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_DIR = os.environ.get("MOUSE_REFERENCE_DIR") or (
+    "/root/reference" if os.path.isfile("/root/reference/ordering_functions.py") else _STAGED)
 
 
 def available() -> bool:

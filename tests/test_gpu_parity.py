@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C-ABI) against the golden vectors of the real reference
 and against the oracle.  Bit-exact: bond vectors/midpoints, neighbour counts, pair lists, RDF
 histograms.  Tolerance 1e-5 relative (north_star) on P2 / S - in practice ~1e-13."""
+import os
+
 import numpy as np
 import pytest
 
@@ -541,6 +543,81 @@ def test_staged_sweep_after_a_fused_frame_on_the_same_cell_list():
             assert rc == 0
             torch.cuda.synchronize()
             assert torch.equal(c2, out[flags][1]) and torch.equal(s2, out[flags][0])
+
+
+def test_trajectory_histograms_and_rdf_trajectory_single_rank():
+    """mode='histo' over a trajectory: the per-frame P2 histograms accumulated by the pipeline equal the staged
+    single-frame histograms summed up; the RDF trajectory driver equals the per-frame RDF histograms summed up."""
+    from mouse_b200.melt import jitter, make_melt
+    from mouse_b200.trajectory import local_ordering_trajectory, pair_correlation_trajectory
+    melt = make_melt(40, 51, seed=12)
+    eng = _engine()
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    frames = [jitter(melt, f, 0.05) for f in range(6)]
+    hargs = (-0.5, 1.0, 30)
+    s_all, totals = local_ordering_trajectory(frames, melt.bond_atoms, molb, melt.box, 1.8, same_molecule=True,
+                                              hist_args=hargs, gather=True)
+    exp = np.zeros(30, np.int64)
+    for f, pos in enumerate(frames):
+        r = eng.p2_frame(pos, melt.bond_atoms, molb, melt.box, 1.8, hist_args=hargs)
+        exp += r.hist.cpu().numpy()
+        assert s_all[f] == r.order_parameter()
+    assert np.array_equal(totals.p2_hist, exp) and exp.sum() == totals.n_refs and totals.n_hist_over == 0
+    h = totals.p2_histogram(*hargs)
+    assert abs(sum(h["values"]) - 1.0) < 1e-12
+    typ = (np.arange(melt.n_atoms) % 2).astype(np.int32)
+    hist, edges, t2 = pair_correlation_trajectory(frames, typ, melt.mol, 2, melt.box, 0.0, 2.0, 50,
+                                                  same_molecule=False)
+    exp = sum(eng.rdf_frame(pos, typ, melt.mol, 2, melt.box, 0.0, 2.0, 50, same_molecule=False)[0].cpu().numpy()
+              for pos in frames)
+    assert np.array_equal(hist, exp) and t2.n_frames == 6 and len(edges) == 51
+
+
+def _two_rank_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from mouse_b200.melt import jitter, make_melt
+    from mouse_b200.trajectory import local_ordering_trajectory, pair_correlation_trajectory
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    melt = make_melt(40, 51, seed=12)
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    frames = [jitter(melt, f, 0.05) for f in range(7)]
+    s_all, tot = local_ordering_trajectory(frames, melt.bond_atoms, molb, melt.box, 1.8, hist_args=(-0.5, 1.0, 30),
+                                           gather=True, device=torch.device("cuda", rank))
+    typ = (np.arange(melt.n_atoms) % 2).astype(np.int32)
+    hist, _, t2 = pair_correlation_trajectory(frames, typ, melt.mol, 2, melt.box, 0.0, 2.0, 50,
+                                              device=torch.device("cuda", rank))
+    out[rank] = (s_all.tolist(), tot.p2_hist.tolist(), tot.n_pairs, tot.n_refs, hist.tolist(), t2.n_frames)
+    dist.destroy_process_group()
+
+
+def test_two_ranks_over_nccl_give_the_one_rank_histograms_bit_for_bit():
+    """Frames sharded over two GPUs, one NCCL all-reduce of the packed sums + histograms, all-gather of the
+    per-frame S: identical (integers: bit for bit) to the single-rank run."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    from mouse_b200.melt import jitter, make_melt
+    from mouse_b200.trajectory import local_ordering_trajectory, pair_correlation_trajectory
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_two_rank_worker, args=(r, 2, port, out)) for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(300) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    melt = make_melt(40, 51, seed=12)
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    frames = [jitter(melt, f, 0.05) for f in range(7)]
+    s_all, tot = local_ordering_trajectory(frames, melt.bond_atoms, molb, melt.box, 1.8, hist_args=(-0.5, 1.0, 30),
+                                           gather=True)
+    typ = (np.arange(melt.n_atoms) % 2).astype(np.int32)
+    hist, _, _ = pair_correlation_trajectory(frames, typ, melt.mol, 2, melt.box, 0.0, 2.0, 50)
+    for r in range(2):
+        s_r, p2h, npairs, nrefs, rdfh, nfr = out[r]
+        assert s_r == s_all.tolist() and p2h == tot.p2_hist.tolist() and (npairs, nrefs) == (tot.n_pairs, tot.n_refs)
+        assert rdfh == hist.tolist() and nfr == 7
 
 
 def test_captured_graph_replays_the_frame_bit_for_bit():
