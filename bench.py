@@ -569,20 +569,22 @@ def run_ours(args):
     # the tail of the timed region (sum of the per-frame totals + the path's only collective) is warmed up too:
     # the first call of a torch kernel / NCCL collective pays one-off module loading and communicator set-up
     packed = torch.zeros(6, dtype=torch.float64, device=dev)
-    _w = tot[:warm].sum(dim=0)
-    if world > 1:
-        dist.all_reduce(packed)
+
+    def pack_totals(rows):
+        # ONE buffer for the path's only collective: the f64 sum of the per-frame sums and the integer counts as
+        # float64 (exact below 2^53, trajectory.TrajectoryTotals.pack)
+        tsum = rows.sum(dim=0)
+        packed[0] = rows[:, 0].view(torch.float64).sum()
+        packed[1:] = tsum[1:].to(torch.float64)
+        if world > 1:
+            dist.all_reduce(packed)
+
+    pack_totals(tot[:warm])      # exactly the ops of the timed region's tail, run once before it
     barrier()
     n_before = len(sampler.samples)
     stream = torch.cuda.current_stream()
     e0, e1 = b.overlapped(steps, tot, first=warm, timed=sweep_ev)
-    # the path's only collective: ONE all-reduce of the packed order-parameter sums and counts (device tensor; the
-    # integer counts ride as float64, exact below 2^53 - trajectory.TrajectoryTotals.pack)
-    tsum = tot[warm:].sum(dim=0)
-    packed[0] = tot[warm:, 0].view(torch.float64).sum()
-    packed[1:] = tsum[1:].to(torch.float64)
-    if world > 1:
-        dist.all_reduce(packed)
+    pack_totals(tot[warm:])      # the path's only collective: ONE all-reduce of the packed sums and counts
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)

@@ -7,6 +7,13 @@
 
 #include "half_shell.cuh"
 
+// Threads per block of the per-item HBM-side kernels.  Small blocks fit into the registers the persistent sweep of
+// ANOTHER frame leaves free on an SM (10 CTAs x 32 threads x 168 registers = 53 760 of 65 536), so the build of frame
+// k+1 really runs next to the sweep of frame k; alone on the GPU they reach the same occupancy as large blocks.
+#ifndef MOUSE_ITEM_BLOCK
+#define MOUSE_ITEM_BLOCK 128
+#endif
+
 // np.remainder(a, b), b > 0: fmod then shift negatives by +b (NumPy npy_divmod); fmod is exact.
 // For |a| < 2 b (every bond of a wrapped or mildly unwrapped configuration) fmod needs no library call:
 // fmod(a, b) = a for |a| < b, and a -+ b for b <= |a| < 2 b, where the subtraction is exact (Sterbenz).
@@ -334,7 +341,12 @@ __global__ void __launch_bounds__(256) scan_apply2_kernel(const int32_t *__restr
 // tile total (+1, so that 0 means "not there yet"; the array is zeroed with the counters) and then sums the totals of
 // the tiles in front of it as they appear.  Blocks only ever wait for blocks with a lower index, which the hardware
 // dispatches first.
-#define MOUSE_SCAN_FUSED_TILES 592
+// (Measured: with three frames in flight the waiting blocks of this kernel sit on SM slots that the other frames'
+// sweeps want - 0.463 ms per 1M-bond frame against 0.420 ms with the two-kernel scan - so it is only used when a
+// build sets MOUSE_SCAN_FUSED_TILES > 0.)
+#ifndef MOUSE_SCAN_FUSED_TILES
+#define MOUSE_SCAN_FUSED_TILES 0
+#endif
 __global__ void __launch_bounds__(256) scan_fused_kernel(const int32_t *__restrict__ in, int nc,
                                                          int32_t *__restrict__ tile_flags,
                                                          int32_t *__restrict__ out) {
@@ -392,7 +404,7 @@ __global__ void __launch_bounds__(256) scan_fused_kernel(const int32_t *__restri
 }
 
 // ---- scatter the item index into its cell (arrival order); the payload moves once, in cell_canon_kernel -----
-__global__ void __launch_bounds__(256) cell_scatter_idx_kernel(const uint8_t *__restrict__ ref_mask, int n,
+__global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_scatter_idx_kernel(const uint8_t *__restrict__ ref_mask, int n,
                                                                const int32_t *__restrict__ cell_of,
                                                                const int32_t *__restrict__ rank_of,
                                                                const int32_t *__restrict__ cell_start,
@@ -409,7 +421,7 @@ __global__ void __launch_bounds__(256) cell_scatter_idx_kernel(const uint8_t *__
 // The items of a cell arrive in atomic order; ranking them by original index makes the sorted arrays - and with
 // them every floating-point sum of the sweeps - a deterministic function of the input.
 template <int MODE>
-__global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, int n, GridDev g,
+__global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_canon_kernel(int ncell, int n, GridDev g,
                                                          const int32_t *__restrict__ cell_start,
                                                          const int32_t *__restrict__ idx_tmp,
                                                          const Rec *__restrict__ rec_tmp,
@@ -514,7 +526,7 @@ __global__ void __launch_bounds__(256) cell_canon_kernel(int ncell, int n, GridD
 }
 
 // ---- K1 + cell assignment + output initialisation in one pass (mouse_p2_frame) -------------------------------
-__global__ void __launch_bounds__(256) bond_assign_kernel(const double *__restrict__ pos, const int2 *__restrict__ bonds,
+__global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) bond_assign_kernel(const double *__restrict__ pos, const int2 *__restrict__ bonds,
                                                           const int32_t *__restrict__ mol,
                                                           const uint8_t *__restrict__ nbr_mask, int n, GridDev g,
                                                           double *__restrict__ vec, double *__restrict__ ctr,
@@ -604,18 +616,18 @@ static int cell_build_tail(int mode, const uint8_t *ref_mask, int64_t n, const m
     MOUSE_LAUNCH_CHECK("scan_apply_kernel");
   }
   if (n > 0) {
-    unsigned nb = (unsigned)((n + 255) / 256);
-    cell_scatter_idx_kernel<<<nb, 256, 0, st>>>(ref_mask, (int)n, w.cell_of, w.rank_of, w.cell_start, w.idx_tmp);
+    unsigned nb = (unsigned)((n + MOUSE_ITEM_BLOCK - 1) / MOUSE_ITEM_BLOCK);
+    cell_scatter_idx_kernel<<<nb, MOUSE_ITEM_BLOCK, 0, st>>>(ref_mask, (int)n, w.cell_of, w.rank_of, w.cell_start, w.idx_tmp);
     MOUSE_LAUNCH_CHECK("cell_scatter_idx_kernel");
-    int blocks = (int)((((int64_t)grid->ncell * 32) + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    int blocks = (int)((((int64_t)grid->ncell * 32) + MOUSE_ITEM_BLOCK - 1) / MOUSE_ITEM_BLOCK);
+    if (blocks > 148 * 16 * (256 / MOUSE_ITEM_BLOCK)) blocks = 148 * 16 * (256 / MOUSE_ITEM_BLOCK);
     if (blocks < 1) blocks = 1;
     if (mode == 0)
-      cell_canon_kernel<0><<<blocks, 256, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.cell_of, w.rec_sorted,
+      cell_canon_kernel<0><<<blocks, MOUSE_ITEM_BLOCK, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.cell_of, w.rec_sorted,
                                                    w.idx_sorted, w.cell_sorted,
                                                    w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr);
     else
-      cell_canon_kernel<1><<<blocks, 256, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.cell_of, w.rec_sorted,
+      cell_canon_kernel<1><<<blocks, MOUSE_ITEM_BLOCK, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.cell_of, w.rec_sorted,
                                                    w.idx_sorted, w.cell_sorted,
                                                    w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr);
     MOUSE_LAUNCH_CHECK("cell_canon_kernel");
@@ -651,7 +663,7 @@ int mouse_launch_frame_build(const double *pos, const int32_t *bond_atoms, const
   GridDev g = mouse_grid_dev(grid);
   MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, (size_t)((char *)(w.cell_count + grid->ncell + 1) - (char *)w.counters), st));
   if (n > 0) {
-    bond_assign_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pos, (const int2 *)bond_atoms, mol, nbr_mask, (int)n,
+    bond_assign_kernel<<<(unsigned)((n + MOUSE_ITEM_BLOCK - 1) / MOUSE_ITEM_BLOCK), MOUSE_ITEM_BLOCK, 0, st>>>(pos, (const int2 *)bond_atoms, mol, nbr_mask, (int)n,
                                                                      g, vec, ctr, w.cell_of, w.rank_of, w.cell_count,
                                                                      w.counters, w.rec_tmp, out_sum, out_cnt,
                                                                      out_mean, init_listed);

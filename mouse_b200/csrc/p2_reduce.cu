@@ -4,6 +4,9 @@
 #include "common.cuh"
 
 #define RED_THREADS 256
+#ifndef FIN_THREADS
+#define FIN_THREADS 128    // fused finish + reduce: small blocks fit next to another frame's sweep (see cell_build.cu)
+#endif
 
 __global__ void __launch_bounds__(RED_THREADS) p2_reduce_kernel(
     const double *__restrict__ sum, const int32_t *__restrict__ cnt, int n, int chunk,
@@ -136,9 +139,9 @@ struct FinishArgs {
   mouse_p2_totals_t *totals;
 };
 
-__global__ void __launch_bounds__(RED_THREADS) p2_finish_reduce_kernel(const FinishArgs a) {
-  __shared__ double s_sum[RED_THREADS / 32];
-  __shared__ long long s_refs[RED_THREADS / 32], s_pairs[RED_THREADS / 32];
+__global__ void __launch_bounds__(FIN_THREADS) p2_finish_reduce_kernel(const FinishArgs a) {
+  __shared__ double s_sum[FIN_THREADS / 32];
+  __shared__ long long s_refs[FIN_THREADS / 32], s_pairs[FIN_THREADS / 32];
   __shared__ bool s_last;
   const bool overflow = ((volatile int64_t *)a.counters)[4] != 0;   // the exact sweep wrote out_sum / out_cnt
   const long long nzero = a.counters[0];
@@ -152,13 +155,13 @@ __global__ void __launch_bounds__(RED_THREADS) p2_finish_reduce_kernel(const Fin
   // Original bond order: the stores are coalesced, the accumulators are gathered through the inverse permutation
   // (they were last touched by the sweep's atomics, i.e. they sit in L2).  Four bonds per thread and trip, all
   // loads up front (memory-level parallelism).
-  for (int b0 = lo + threadIdx.x; b0 < hi; b0 += 4 * RED_THREADS) {
+  for (int b0 = lo + threadIdx.x; b0 < hi; b0 += 4 * FIN_THREADS) {
     int v[4];
     long long fix[4];
     int c[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int b = b0 + q * RED_THREADS;
+      const int b = b0 + q * FIN_THREADS;
       v[q] = b < hi ? slot_of[b] : -1;
     }
 #pragma unroll
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(RED_THREADS) p2_finish_reduce_kernel(const Fin
     // (the accumulators are NOT re-zeroed here: every frame build zeroes them in cell_canon_kernel)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int b = b0 + q * RED_THREADS;
+      const int b = b0 + q * FIN_THREADS;
       if (v[q] < 0) continue;              // not in the cell list: the build wrote 0 / 0 / NaN
       const double nan = __longlong_as_double(0x7ff8000000000000LL);
       if (!((v[q] >> 30) & 1)) {           // listed, but not a reference: 0 / 0 / NaN
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(RED_THREADS) p2_finish_reduce_kernel(const Fin
   if (threadIdx.x == 0) {
     double t = 0.0;
     long long r = 0, p = 0;
-    for (int w = 0; w < RED_THREADS / 32; ++w) {
+    for (int w = 0; w < FIN_THREADS / 32; ++w) {
       t += s_sum[w];
       r += s_refs[w];
       p += s_pairs[w];
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(RED_THREADS) p2_finish_reduce_kernel(const Fin
   if (s_last) {
     __threadfence();
     double t = 0.0, r = 0.0, p = 0.0;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += RED_THREADS) {
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += FIN_THREADS) {
       t += ((volatile double *)a.partials)[3 * b];
       r += ((volatile double *)a.partials)[3 * b + 1];
       p += ((volatile double *)a.partials)[3 * b + 2];
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(RED_THREADS) p2_finish_reduce_kernel(const Fin
     if (threadIdx.x == 0) {
       double tt = 0.0;
       long long rr = 0, pp = 0;
-      for (int w = 0; w < RED_THREADS / 32; ++w) {
+      for (int w = 0; w < FIN_THREADS / 32; ++w) {
         tt += s_sum[w];
         rr += s_refs[w];
         pp += s_pairs[w];
@@ -275,12 +278,12 @@ int mouse_launch_p2_finish_reduce(int64_t n, const mouse_grid_t *grid, const Wor
   a.slot_of = w.cell_of;
   a.n = (int)n;
   (void)grid;
-  int blocks = (int)((n + RED_THREADS - 1) / RED_THREADS);
+  int blocks = (int)((n + FIN_THREADS - 1) / FIN_THREADS);
   if (blocks > MOUSE_REDUCE_BLOCKS) blocks = MOUSE_REDUCE_BLOCKS;
   if (blocks < 1) blocks = 1;
   int chunk = (int)((n + blocks - 1) / blocks);
-  chunk = (chunk + RED_THREADS - 1) / RED_THREADS * RED_THREADS;
-  if (chunk < RED_THREADS) chunk = RED_THREADS;
+  chunk = (chunk + FIN_THREADS - 1) / FIN_THREADS * FIN_THREADS;
+  if (chunk < FIN_THREADS) chunk = FIN_THREADS;
   a.chunk = chunk;
   a.out_sum = out_sum;
   a.out_cnt = out_cnt;
@@ -288,7 +291,7 @@ int mouse_launch_p2_finish_reduce(int64_t n, const mouse_grid_t *grid, const Wor
   a.partials = w.partials;
   a.counters = w.counters;
   a.totals = totals;
-  p2_finish_reduce_kernel<<<blocks, RED_THREADS, 0, st>>>(a);
+  p2_finish_reduce_kernel<<<blocks, FIN_THREADS, 0, st>>>(a);
   MOUSE_LAUNCH_CHECK("p2_finish_reduce_kernel");
   return MOUSE_OK;
 }
