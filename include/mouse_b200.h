@@ -219,6 +219,18 @@ int mouse_debug_counters(const mouse_grid_t *grid, int64_t n_items, const void *
  * others go through strtod.  Returns the number of values written, or -(offset + 1) of the first token that is not a
  * number or does not fit. */
 int64_t mouse_parse_doubles(const char *text /*HOST*/, int64_t len, double *out /*HOST*/, int64_t cap);
+/* The same on `nthreads` host threads (the text is cut at whitespace, tokens are counted, then parsed in place):
+ * identical values and error position. */
+int64_t mouse_parse_doubles_mt(const char *text /*HOST*/, int64_t len, double *out /*HOST*/, int64_t cap,
+                               int32_t nthreads);
+
+/* The ATOMS block of one LAMMPS dump frame straight into arrays (lammpack_types.py:377-395: one float() per token, then
+ * `lo + (hi - lo) * xs` for scaled coordinates): nrows lines of ncol numbers; col_id -> ids, col_xyz[3] -> xyz[row][3]
+ * with the reference's coordinate transform (mode 0 scaled, 1 cut: lo + x, 2 uncut: x; un-fused), col_img[3] (or NULL)
+ * -> img[row][3].  Lines are split over nthreads host threads.  Returns nrows or a negative error (see api.cu). */
+int64_t mouse_parse_dump_atoms(const char *text /*HOST*/, int64_t len, int64_t nrows, int32_t ncol, int32_t col_id,
+                               const int32_t *col_xyz, const int32_t *col_img, int32_t mode, const double *lo,
+                               const double *hi, int64_t *ids, double *xyz, int32_t *img, int32_t nthreads);
 
 #ifdef __cplusplus
 }

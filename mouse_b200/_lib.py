@@ -50,7 +50,7 @@ EXPORTS = [
     "mouse_workspace_bytes", "mouse_cell_build", "mouse_p2_sweep", "mouse_p2_pair_lists", "mouse_p2_reduce",
     "mouse_p2_frame", "mouse_p2_frame_timed", "mouse_p2_frame_graph_create", "mouse_p2_frame_graph_launch",
     "mouse_p2_frame_graph_nodes", "mouse_p2_frame_graph_destroy", "mouse_rdf_frame_timed", "mouse_rdf_frame", "mouse_single_ref_workspace_bytes", "mouse_p2_single_ref",
-    "mouse_rdf_single_ref", "mouse_director_p2", "mouse_atom_colour", "mouse_debug_counters", "mouse_parse_doubles",
+    "mouse_rdf_single_ref", "mouse_director_p2", "mouse_atom_colour", "mouse_debug_counters", "mouse_parse_doubles", "mouse_parse_doubles_mt", "mouse_parse_dump_atoms",
 ]
 
 
@@ -107,6 +107,10 @@ def lib():
     L.mouse_debug_counters.argtypes = [gp, i64, vp, vp, vp]
     L.mouse_parse_doubles.argtypes = [C.c_char_p, i64, vp, i64]
     L.mouse_parse_doubles.restype = i64
+    L.mouse_parse_doubles_mt.argtypes = [C.c_char_p, i64, vp, i64, i32]
+    L.mouse_parse_doubles_mt.restype = i64
+    L.mouse_parse_dump_atoms.argtypes = [vp, i64, i64, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32]
+    L.mouse_parse_dump_atoms.restype = i64
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:

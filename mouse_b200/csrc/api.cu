@@ -4,6 +4,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 // launchers implemented next to their kernels
@@ -415,22 +418,33 @@ int mouse_debug_counters(const mouse_grid_t *grid, int64_t n_items, const void *
 
 }  // extern "C"
 
-// ------------------------------------------------------------------ host-side ingestion helper
-int64_t mouse_parse_doubles(const char *text, int64_t len, double *out, int64_t cap) {
+// ------------------------------------------------------------------ host-side ingestion helpers
+static inline bool mouse_is_ws(char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r'; }
+
+// One decimal number starting at s (no leading whitespace), token ends at whitespace or `end`.  Correctly rounded:
+// numbers with <= 15 significant digits and a decimal exponent within +-22 take the exact fast path (integer
+// mantissa times / divided by an exactly representable power of ten: one rounding), all others go through strtod.
+// Returns the end of the token, or NULL when the token is not a number.
+static inline const char *mouse_parse_token(const char *s, const char *end, double *value) {
   static const double p10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
                                  1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
-  const char *s = text, *end = text + len;
-  int64_t n = 0;
-  for (;;) {
-    while (s < end && (*s == ' ' || *s == '\n' || *s == '\t' || *s == '\r')) ++s;
-    if (s >= end) break;
-    const char *tok = s;
-    if (n >= cap) return -((int64_t)(tok - text) + 1);
-    bool neg = false;
-    if (*s == '-' || *s == '+') neg = (*s++ == '-');
-    uint64_t m = 0;
-    int digits = 0, frac = 0;
-    bool any = false, lead = true;
+  const char *tok = s;
+  bool neg = false;
+  if (s < end && (*s == '-' || *s == '+')) neg = (*s++ == '-');
+  uint64_t m = 0;
+  int digits = 0, frac = 0;
+  bool any = false, lead = true;
+  while (s < end && *s >= '0' && *s <= '9') {
+    any = true;
+    if (!(lead && *s == '0')) {
+      lead = false;
+      if (digits < 19) m = m * 10 + (uint64_t)(*s - '0');
+      ++digits;
+    }
+    ++s;
+  }
+  if (s < end && *s == '.') {
+    ++s;
     while (s < end && *s >= '0' && *s <= '9') {
       any = true;
       if (!(lead && *s == '0')) {
@@ -438,60 +452,216 @@ int64_t mouse_parse_doubles(const char *text, int64_t len, double *out, int64_t 
         if (digits < 19) m = m * 10 + (uint64_t)(*s - '0');
         ++digits;
       }
+      ++frac;
       ++s;
     }
-    if (s < end && *s == '.') {
-      ++s;
+  }
+  int e10 = 0;
+  bool fast = any;
+  if (any && s < end && (*s == 'e' || *s == 'E')) {
+    const char *save = s++;
+    bool eneg = false;
+    if (s < end && (*s == '-' || *s == '+')) eneg = (*s++ == '-');
+    if (s < end && *s >= '0' && *s <= '9') {
+      int e = 0;
       while (s < end && *s >= '0' && *s <= '9') {
-        any = true;
-        if (!(lead && *s == '0')) {
-          lead = false;
-          if (digits < 19) m = m * 10 + (uint64_t)(*s - '0');
-          ++digits;
-        }
-        ++frac;
+        if (e < 10000) e = e * 10 + (*s - '0');
         ++s;
       }
+      e10 = eneg ? -e : e;
+    } else {
+      s = save;      // "1e" / "1ex": not an exponent
+      fast = false;
     }
-    int e10 = 0;
-    bool fast = any;
-    if (any && s < end && (*s == 'e' || *s == 'E')) {
-      const char *save = s++;
-      bool eneg = false;
-      if (s < end && (*s == '-' || *s == '+')) eneg = (*s++ == '-');
-      if (s < end && *s >= '0' && *s <= '9') {
-        int e = 0;
-        while (s < end && *s >= '0' && *s <= '9') {
-          if (e < 10000) e = e * 10 + (*s - '0');
-          ++s;
-        }
-        e10 = eneg ? -e : e;
-      } else {
-        s = save;      // "1e" / "1ex": not an exponent
-        fast = false;
-      }
-    }
-    const bool token_ends = s >= end || *s == ' ' || *s == '\n' || *s == '\t' || *s == '\r';
-    const int e = e10 - frac;
-    if (fast && token_ends && digits <= 15 && e >= -22 && e <= 22) {
-      double v = (double)m;                       // exact: m < 10^15 < 2^53
-      v = e >= 0 ? v * p10[e] : v / p10[-e];      // one correctly rounded operation with an exact power of ten
-      out[n++] = neg ? -v : v;
-      continue;
-    }
-    // everything else (long mantissas, large exponents, nan / inf, malformed tokens): the C library
-    const char *t = tok;
-    while (t < end && !(*t == ' ' || *t == '\n' || *t == '\t' || *t == '\r')) ++t;
-    char buf[128];
-    const size_t tl = (size_t)(t - tok);
-    if (tl == 0 || tl >= sizeof(buf)) return -((int64_t)(tok - text) + 1);
-    memcpy(buf, tok, tl);
-    buf[tl] = 0;
-    char *stop = nullptr;
-    const double v = strtod(buf, &stop);
-    if (stop != buf + tl) return -((int64_t)(tok - text) + 1);
+  }
+  const bool token_ends = s >= end || mouse_is_ws(*s);
+  const int e = e10 - frac;
+  if (fast && token_ends && digits <= 15 && e >= -22 && e <= 22) {
+    double v = (double)m;                       // exact: m < 10^15 < 2^53
+    v = e >= 0 ? v * p10[e] : v / p10[-e];      // one correctly rounded operation with an exact power of ten
+    *value = neg ? -v : v;
+    return s;
+  }
+  // everything else (long mantissas, large exponents, nan / inf, malformed tokens): the C library
+  const char *t = tok;
+  while (t < end && !mouse_is_ws(*t)) ++t;
+  char buf[128];
+  const size_t tl = (size_t)(t - tok);
+  if (tl == 0 || tl >= sizeof(buf)) return nullptr;
+  memcpy(buf, tok, tl);
+  buf[tl] = 0;
+  char *stop = nullptr;
+  const double v = strtod(buf, &stop);
+  if (stop != buf + tl) return nullptr;
+  *value = v;
+  return t;
+}
+
+extern "C" int64_t mouse_parse_doubles(const char *text, int64_t len, double *out, int64_t cap) {
+  const char *s = text, *end = text + len;
+  int64_t n = 0;
+  for (;;) {
+    while (s < end && mouse_is_ws(*s)) ++s;
+    if (s >= end) break;
+    if (n >= cap) return -((int64_t)(s - text) + 1);
+    double v;
+    const char *next = mouse_parse_token(s, end, &v);
+    if (!next) return -((int64_t)(s - text) + 1);
     out[n++] = v;
-    s = t;
+    s = next;
   }
   return n;
+}
+
+// The same over several host threads: the text is cut at whitespace into one chunk per thread, a first pass counts the
+// tokens of every chunk (so that every chunk knows where its values go), a second pass parses the chunks in place.
+// Token boundaries do not depend on the cut, every token is converted by the same code as above: the values (and the
+// error position) are those of the single-threaded call.
+extern "C" int64_t mouse_parse_doubles_mt(const char *text, int64_t len, double *out, int64_t cap, int32_t nthreads) {
+  if (nthreads > 64) nthreads = 64;
+  if (nthreads <= 1 || len < (int64_t)1 << 16) return mouse_parse_doubles(text, len, out, cap);
+  std::vector<int64_t> cut(nthreads + 1), count(nthreads, 0), result(nthreads, 0);
+  cut[0] = 0;
+  cut[nthreads] = len;
+  for (int t = 1; t < nthreads; ++t) {
+    int64_t c = len * t / nthreads;
+    if (c < cut[t - 1]) c = cut[t - 1];
+    while (c < len && !mouse_is_ws(text[c])) ++c;     // never inside a token
+    cut[t] = c;
+  }
+  {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t)
+      pool.emplace_back([&, t]() {
+        int64_t n = 0;
+        bool in_tok = false;
+        for (int64_t k = cut[t]; k < cut[t + 1]; ++k) {
+          const bool w = mouse_is_ws(text[k]);
+          n += (!w && !in_tok);
+          in_tok = !w;
+        }
+        count[t] = n;
+      });
+    for (auto &th : pool) th.join();
+  }
+  std::vector<int64_t> first(nthreads + 1, 0);
+  for (int t = 0; t < nthreads; ++t) first[t + 1] = first[t] + count[t];
+  if (first[nthreads] > cap) {
+    // the single-threaded call reports the first token that does not fit
+    return mouse_parse_doubles(text, len, out, cap);
+  }
+  {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t)
+      pool.emplace_back([&, t]() {
+        result[t] = mouse_parse_doubles(text + cut[t], cut[t + 1] - cut[t], out + first[t], count[t]);
+      });
+    for (auto &th : pool) th.join();
+  }
+  for (int t = 0; t < nthreads; ++t)
+    if (result[t] < 0) return -((-result[t] - 1) + cut[t] + 1);     // offset of the bad token in the whole text
+  return first[nthreads];
+}
+
+// The ATOMS block of a LAMMPS dump frame (lammpack_types.py:377-395) straight into the arrays the pipeline needs:
+// `nrows` lines of `ncol` whitespace-separated numbers; column col_id -> ids (int64), columns col_xyz[0..2] ->
+// xyz[row][3] with the coordinate transform of the reference applied (mode 0 "scaled": lo + (hi - lo) * x, mode 1
+// "cut": lo + x, mode 2 "uncut": x - un-fused, like the NumPy expressions), optional columns col_img[0..2] ->
+// img[row][3] (int32).  Lines are distributed over `nthreads` host threads (cut at newlines).  Returns nrows, or
+// -(byte offset + 1) of the first line that is short, long or holds a token that is not a number; -1 - len when the
+// block does not hold exactly nrows lines.
+extern "C" int64_t mouse_parse_dump_atoms(const char *text, int64_t len, int64_t nrows, int32_t ncol, int32_t col_id,
+                                          const int32_t *col_xyz, const int32_t *col_img, int32_t mode,
+                                          const double *lo, const double *hi, int64_t *ids, double *xyz, int32_t *img,
+                                          int32_t nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 64) nthreads = 64;
+  if (len < (int64_t)1 << 16) nthreads = 1;
+  std::vector<int64_t> cut(nthreads + 1), lines(nthreads, 0), result(nthreads, 0);
+  cut[0] = 0;
+  cut[nthreads] = len;
+  for (int t = 1; t < nthreads; ++t) {
+    int64_t c = len * t / nthreads;
+    if (c < cut[t - 1]) c = cut[t - 1];
+    while (c < len && text[c] != '\n') ++c;
+    if (c < len) ++c;                                  // a chunk starts right behind a newline
+    cut[t] = c;
+  }
+  auto blank = [&](int64_t a, int64_t b) {
+    for (int64_t k = a; k < b; ++k)
+      if (!mouse_is_ws(text[k])) return false;
+    return true;
+  };
+  auto count_lines = [&](int t) {
+    int64_t n = 0, a = cut[t];
+    for (int64_t k = cut[t]; k < cut[t + 1]; ++k)
+      if (text[k] == '\n') {
+        n += !blank(a, k);
+        a = k + 1;
+      }
+    if (a < cut[t + 1]) n += !blank(a, cut[t + 1]);
+    lines[t] = n;
+  };
+  const double span[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+  auto parse_chunk = [&](int t, int64_t row) {
+    const char *s = text + cut[t], *end = text + cut[t + 1];
+    while (s < end) {
+      const char *eol = (const char *)memchr(s, '\n', (size_t)(end - s));
+      if (!eol) eol = end;
+      const char *q = s;
+      int col = 0;
+      bool any = false;
+      for (;;) {
+        while (q < eol && mouse_is_ws(*q)) ++q;
+        if (q >= eol) break;
+        any = true;
+        double v;
+        const char *next = mouse_parse_token(q, eol, &v);
+        if (!next || col >= ncol) {
+          result[t] = -((int64_t)(q - text) + 1);
+          return;
+        }
+        if (col == col_id) ids[row] = (int64_t)v;
+        for (int a = 0; a < 3; ++a) {
+          if (col == col_xyz[a]) {
+            volatile double p = mode == 0 ? span[a] * v : v;      // (hi - lo) * x, rounded, then lo + ...
+            xyz[3 * row + a] = mode == 2 ? v : lo[a] + p;
+          }
+          if (img && col == col_img[a]) img[3 * row + a] = (int32_t)v;
+        }
+        ++col;
+        q = next;
+      }
+      if (any) {
+        if (col != ncol) {
+          result[t] = -((int64_t)(s - text) + 1);
+          return;
+        }
+        ++row;
+      }
+      s = eol < end ? eol + 1 : end;
+    }
+  };
+  if (nthreads == 1) {
+    count_lines(0);
+    if (lines[0] != nrows) return -1 - len;
+    parse_chunk(0, 0);
+    return result[0] < 0 ? result[0] : nrows;
+  }
+  {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) pool.emplace_back(count_lines, t);
+    for (auto &th : pool) th.join();
+  }
+  std::vector<int64_t> first(nthreads + 1, 0);
+  for (int t = 0; t < nthreads; ++t) first[t + 1] = first[t] + lines[t];
+  if (first[nthreads] != nrows) return -1 - len;
+  {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) pool.emplace_back(parse_chunk, t, first[t]);
+    for (auto &th : pool) th.join();
+  }
+  for (int t = 0; t < nthreads; ++t)
+    if (result[t] < 0) return result[t];
+  return nrows;
 }

@@ -100,6 +100,26 @@ class FrameArrays:
         """hash8(bond.atom1.mol_id) per bond (``ordering_functions.py:31,39``)."""
         return self.atom_mol_hash()[self.bond_atoms[:, 0]]
 
+    def atom_mol_code(self):
+        """Dense, collision-free molecule codes (0 = the empty mol_id, then 1.. in order of first appearance): what
+        the kernels compare for ``sameMolecule=False``.  Unlike ``hash8`` (kept for the reference's (9,N)/(6,N)
+        array layout, whose collisions and per-process salt are part of that layout) these are identical on every
+        rank and in every run."""
+        if "molc" not in self._cache:
+            table = {"": 0}
+            out = np.empty(len(self.atom_mol), np.int32)
+            for k, s in enumerate(self.atom_mol):
+                c = table.get(s)
+                if c is None:
+                    c = table[s] = len(table)
+                out[k] = c
+            self._cache["molc"] = out
+        return self._cache["molc"]
+
+    def bond_mol_code(self):
+        """``atom_mol_code`` of atom1 of every bond (the molecule the reference attributes the bond to, ``:31,39``)."""
+        return self.atom_mol_code()[self.bond_atoms[:, 0]] if self.n_bonds else np.zeros(0, np.int32)
+
     def bond_res_hash(self):
         return self.atom_res_hash()[self.bond_atoms[:, 0]]
 

@@ -131,81 +131,203 @@ def read_lmp_data_arrays(path, bonds=True) -> FrameArrays:
 _COORD_KEYS = {"scaled": ("xs", "ys", "zs"), "cut": ("xc", "yc", "zc"), "uncut": ("xu", "yu", "zu")}
 
 
-def _parse_numbers(block: bytes, count: int):
+def _parse_numbers(block: bytes, count: int, threads: int = 1):
     """``count`` whitespace-separated numbers of a text block as float64 (correctly rounded, the same values
-    ``float()`` gives): the C parser of ``libmouse_b200.so`` (``mouse_parse_doubles``), NumPy's text parser when the
-    library is not built.  ``None`` when the block does not hold exactly ``count`` numbers."""
+    ``float()`` gives): the C parser of ``libmouse_b200.so`` (``mouse_parse_doubles`` / ``_mt`` on ``threads`` host
+    threads - ctypes releases the GIL for the call), NumPy's text parser when the library is not built.  ``None``
+    when the block does not hold exactly ``count`` numbers."""
     try:
         import ctypes as C
         from . import _lib
         out = np.empty(max(count, 1), np.float64)
-        got = _lib.lib().mouse_parse_doubles(block, len(block), C.c_void_p(out.ctypes.data), count)
+        if threads > 1:
+            got = _lib.lib().mouse_parse_doubles_mt(block, len(block), C.c_void_p(out.ctypes.data), count, int(threads))
+        else:
+            got = _lib.lib().mouse_parse_doubles(block, len(block), C.c_void_p(out.ctypes.data), count)
         return out[:count] if got == count else None
     except (ImportError, OSError):
         data = np.fromstring(block.decode(), dtype=np.float64, sep=" ") if block.strip() else np.zeros(0)
         return data if data.size == count else None
 
 
-def iter_lmp_dump_frames(path, atom_num, coords_type="scaled"):
+def index_lmp_dump(path):
+    """Byte offset of every ``ITEM: TIMESTEP`` line of a LAMMPS dump, plus the file size as the last entry
+    (int64 array of F + 1 values): built with one sequential scan of the memory-mapped file, it lets every rank
+    seek straight to its own frames instead of parsing the whole trajectory."""
+    import mmap
+    import os
+    size = os.path.getsize(path)
+    offs = []
+    if size:
+        with open(path, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            k = mm.find(b"ITEM: TIMESTEP")
+            while k >= 0:
+                if k == 0 or mm[k - 1] == 0x0a:
+                    offs.append(k)
+                k = mm.find(b"ITEM: TIMESTEP", k + 14)
+    return np.array(offs + [size], np.int64)
+
+
+class _RowMap:
+    """atom id -> row of the topology, cached between frames: dumps normally list the atoms in the same order in
+    every frame, and most often in the topology's own order (then no permutation is applied at all)."""
+
+    def __init__(self, atom_num):
+        self.atom_num = np.asarray(atom_num, np.int64)
+        self.order = np.argsort(self.atom_num, kind="stable")
+        self.sorted_num = self.atom_num[self.order]
+        self.last_ids, self.row, self.identity = None, None, False
+
+    def rows(self, ids):
+        if self.last_ids is not None and np.array_equal(ids, self.last_ids):
+            return self.row, self.identity
+        n = len(self.atom_num)
+        where = np.searchsorted(self.sorted_num, ids)
+        if np.any(where >= n) or np.any(self.sorted_num[np.minimum(where, n - 1)] != ids):
+            raise KeyError("dump refers to an unknown atom number")
+        self.row = self.order[where]
+        self.identity = bool(np.array_equal(self.row, np.arange(n)))
+        self.last_ids = ids.copy()
+        return self.row, self.identity
+
+
+def _parse_dump_header(head: str, n: int):
+    lines = head.split("\n")
+    timestep, natom, lo, hi = 0, n, np.zeros(3), np.zeros(3)
+    j = 0
+    while j < len(lines):
+        item = lines[j][6:].strip() if lines[j].startswith("ITEM:") else ""
+        if item == "TIMESTEP":
+            timestep = int(lines[j + 1])
+            j += 1
+        elif item == "NUMBER OF ATOMS":
+            natom = int(lines[j + 1])
+            j += 1
+            if natom != n:
+                raise NameError("Error reading extra frame for a configuration with %d from a dump file with %d "
+                                "atoms\n" % (n, natom))
+        elif item[:10] == "BOX BOUNDS":
+            for a in range(3):
+                w = lines[j + 1 + a].split()
+                lo[a], hi[a] = float(w[0]), float(w[1])
+            j += 3
+        j += 1
+    return timestep, natom, lo, hi
+
+
+def _parse_dump_frame(buf, start: int, stop: int, rowmap: _RowMap, coords_type: str, threads: int):
+    """One frame = the bytes [start, stop) of ``buf`` (the memory-mapped dump as a uint8 array), from its ``ITEM:
+    TIMESTEP`` line up to the next one -> (timestep, box, centre, pos, img).  The ATOMS block goes to
+    ``mouse_parse_dump_atoms`` in place (no copy of the text, ids / coordinates / image flags written directly,
+    the reference's coordinate transform applied in C); blocks that function cannot take (non-numeric columns,
+    library not built) go through the token-by-token path."""
+    n = len(rowmap.atom_num)
+    head_end = min(stop, start + 4096)
+    head_bytes = bytes(buf[start:head_end])
+    k = head_bytes.find(b"ITEM: ATOMS")
+    while k < 0 and head_end < stop:                  # (a header longer than 4 KiB: keep looking)
+        head_end = min(stop, head_end + 65536)
+        head_bytes = bytes(buf[start:head_end])
+        k = head_bytes.find(b"ITEM: ATOMS")
+    if k < 0:
+        raise ValueError("dump frame without an ATOMS section")
+    eol = head_bytes.find(b"\n", k)
+    if eol < 0:
+        raise ValueError("dump frame with a truncated ATOMS header")
+    keys = head_bytes[k:eol].decode().split()[2:]
+    timestep, natom, lo, hi = _parse_dump_header(head_bytes[:k].decode(), n)
+    b0 = start + eol + 1
+    ci = [keys.index(kk) for kk in _COORD_KEYS[coords_type]]
+    has_img = all(kk in keys for kk in ("ix", "iy", "iz"))
+    ids = xyz = iv = None
+    try:
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        ids = np.empty(natom, np.int64)
+        xyz = np.empty((natom, 3), np.float64)
+        iv = np.empty((natom, 3), np.int32) if has_img else None
+        cxyz = (C.c_int32 * 3)(*ci)
+        cimg = (C.c_int32 * 3)(*[keys.index(kk) for kk in ("ix", "iy", "iz")]) if has_img else None
+        mode = {"scaled": 0, "cut": 1, "uncut": 2}[coords_type]
+        got = L.mouse_parse_dump_atoms(C.c_void_p(buf.ctypes.data + b0), stop - b0, natom, len(keys), keys.index("id"),
+                                       cxyz, cimg, mode, C.c_void_p(lo.ctypes.data), C.c_void_p(hi.ctypes.data),
+                                       C.c_void_p(ids.ctypes.data), C.c_void_p(xyz.ctypes.data),
+                                       C.c_void_p(iv.ctypes.data) if has_img else None, int(threads))
+        if got != natom:
+            ids = None
+    except (ImportError, OSError):
+        ids = None
+    if ids is None:                         # token by token (what the reference does, one float() per token)
+        block = bytes(buf[b0:stop])
+        data = _parse_numbers(block, natom * len(keys), threads)
+        if data is None:
+            rows = [ln.split() for ln in block.decode().split("\n") if ln.strip()][:natom]
+            data = np.array(rows, dtype=np.float64)
+        data = data.reshape(natom, len(keys))
+        ids = data[:, keys.index("id")].astype(np.int64)
+        c = data[:, ci]
+        if coords_type == "scaled":
+            xyz = lo + (hi - lo) * c
+        elif coords_type == "cut":
+            xyz = lo + c
+        else:
+            xyz = np.array(c)
+        iv = data[:, [keys.index("ix"), keys.index("iy"), keys.index("iz")]].astype(np.int32) if has_img else None
+    row, identity = rowmap.rows(ids)
+    if identity:
+        pos, img = np.ascontiguousarray(xyz), iv
+    else:
+        pos = np.empty((n, 3), np.float64)
+        pos[row] = xyz
+        img = None
+        if has_img:
+            img = np.zeros((n, 3), np.int32)
+            img[row] = iv
+    return timestep, hi - lo, (lo + hi) / 2., pos, img
+
+
+def iter_lmp_dump_frames(path, atom_num, coords_type="scaled", frames=None, index=None, threads=1):
     """Yield ``(timestep, box[3], box_center[3], positions[N,3], images[N,3] or None)`` per frame of a LAMMPS dump,
-    with the rows ordered like ``atom_num`` (the topology's atom numbers)."""
+    with the rows ordered like ``atom_num`` (the topology's atom numbers).  ``frames`` = (lo, hi) restricts the
+    iteration to that range of frames: with the byte-offset ``index`` (``index_lmp_dump``; built here when not
+    given) the reader seeks to frame ``lo`` and never touches the others - this is how the ranks of a sharded
+    trajectory each read their own block.  ``threads``: host threads of the number parser.  One frame is in memory
+    at a time."""
     if coords_type not in _COORD_KEYS:
         raise ValueError("coords_type must be scaled, cut or uncut")
-    atom_num = np.asarray(atom_num, np.int64)
-    order = np.argsort(atom_num, kind="stable")
-    sorted_num = atom_num[order]
-    n = len(atom_num)
+    if index is None:
+        index = index_lmp_dump(path)
+    nframes = len(index) - 1
+    lo_f, hi_f = (0, nframes) if frames is None else (max(0, int(frames[0])), min(nframes, int(frames[1])))
+    rowmap = _RowMap(atom_num)
+    if hi_f <= lo_f:
+        return
+    import mmap
     with open(path, "rb") as f:
-        timestep, natom, lo, hi = 0, n, np.zeros(3), np.zeros(3)
-        while True:
-            head = f.readline().decode()
-            item = head[6:-1]
-            if len(item) == 0:
-                break
-            if item == "TIMESTEP":
-                timestep = int(f.readline())
-            elif item == "NUMBER OF ATOMS":
-                natom = int(f.readline())
-                if natom != n:
-                    raise NameError("Error reading extra frame for a configuration with %d from a dump file with %d "
-                                    "atoms\n" % (n, natom))
-            elif item[:10] == "BOX BOUNDS":
-                for a in range(3):
-                    w = f.readline().split()
-                    lo[a], hi[a] = float(w[0]), float(w[1])
-            elif item.split()[0] == "ATOMS":
-                keys = item.split()[1:]
-                block = b"".join(itertools.islice(f, natom))
-                data = _parse_numbers(block, natom * len(keys))
-                if data is None:                        # non-numeric columns or a short block: token by token
-                    data = np.array([ln.split() for ln in block.decode().split("\n") if ln.strip()], dtype=np.float64)
-                data = data.reshape(natom, len(keys))
-                ids = data[:, keys.index("id")].astype(np.int64)
-                where = np.searchsorted(sorted_num, ids)
-                if np.any(where >= n) or np.any(sorted_num[np.minimum(where, n - 1)] != ids):
-                    raise KeyError("dump refers to an unknown atom number")
-                row = order[where]
-                c = data[:, [keys.index(kk) for kk in _COORD_KEYS[coords_type]]]
-                if coords_type == "scaled":
-                    xyz = lo + (hi - lo) * c
-                elif coords_type == "cut":
-                    xyz = lo + c
-                else:
-                    xyz = c
-                pos = np.empty((n, 3), np.float64)
-                pos[row] = xyz
-                img = None
-                if all(kk in keys for kk in ("ix", "iy", "iz")):
-                    img = np.zeros((n, 3), np.int32)
-                    img[row] = data[:, [keys.index("ix"), keys.index("iy"), keys.index("iz")]].astype(np.int32)
-                yield timestep, hi - lo, (lo + hi) / 2., pos, img
+        mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        buf = np.frombuffer(mm, dtype=np.uint8)       # the parser reads the mapped text in place
+        try:
+            for k in range(lo_f, hi_f):
+                yield _parse_dump_frame(buf, int(index[k]), int(index[k + 1]), rowmap, coords_type, threads)
+        finally:
+            del buf
+            try:
+                mm.close()
+            except BufferError:      # a traceback still holds a view of the mapping: the collector unmaps it later
+                pass
 
 
-def read_lmp_dump_arrays(path, atom_num, coords_type="scaled"):
-    """All frames of a dump: ``(timesteps[F], boxes[F,3], positions[F,N,3])`` - the trajectory tensors of
-    ``mouse_b200.trajectory``."""
+def count_lmp_dump_frames(path, index=None):
+    return len(index_lmp_dump(path) if index is None else index) - 1
+
+
+def read_lmp_dump_arrays(path, atom_num, coords_type="scaled", frames=None, index=None, threads=1):
+    """Frames of a dump (all, or the range ``frames``): ``(timesteps[F], boxes[F,3], positions[F,N,3])`` - the
+    trajectory tensors of ``mouse_b200.trajectory``.  Materialises the frames: use ``iter_lmp_dump_frames`` to
+    stream."""
     ts, boxes, pos = [], [], []
-    for t, box, _, p, _ in iter_lmp_dump_frames(path, atom_num, coords_type):
+    for t, box, _, p, _ in iter_lmp_dump_frames(path, atom_num, coords_type, frames, index, threads):
         ts.append(t)
         boxes.append(box.copy())
         pos.append(p)

@@ -219,10 +219,12 @@ def CalculatePairCorrelationFunctions(config, atomtypes=[], rmin=0., rmax=0., nb
     rdfs['v'] = volumes
     code_of = {t: k for k, t in enumerate(types)}
     tcode = np.fromiter((code_of.get(t, -1) for t in fa.atom_type), np.int32, fa.n_atoms)
-    if not sameMolecule and bool(np.any((fa.atom_mol_hash() == hash8('')) & (tcode >= 0))):
+    # molecule codes: dense and collision-free (0 = empty mol_id); the reference compares hash8(mol_id), whose
+    # collisions (and per-process salt) would silently drop inter-molecular pairs - not reproduced
+    if not sameMolecule and bool(np.any((fa.atom_mol_code() == 0) & (tcode >= 0))):
         hist = np.zeros((len(types) * (len(types) + 1) // 2, nbin), np.int64)   # every reference raises NameError
     else:
-        h, _ = engine.rdf_frame(fa.positions, tcode, fa.atom_mol_hash().astype(np.int32), len(types), box, rmin,
+        h, _ = engine.rdf_frame(fa.positions, tcode, fa.atom_mol_code(), len(types), box, rmin,
                                 rmax, nbin, same_molecule=sameMolecule)
         hist = h.cpu().numpy()
     rdfdata, norm = {}, {}
@@ -263,9 +265,11 @@ def CalculateOrientationOrderParameter(config, bondtypes, rmin=0., rmax=0., stor
             s_hist["norm"][i] = 1. / (costhetaleft + costhetaright)
     nbr_mask = fa.bond_mask(bond_types=bondtypes)
     ref_mask = fa.bond_mask(bond_types=bondtypes, res_types=referenceResTypes)
-    mol = fa.bond_mol_hash().astype(np.int32)
+    # molecule codes: dense and collision-free (0 = empty mol_id); the reference compares hash8(mol_id), whose
+    # collisions (and per-process salt) would silently drop inter-molecular pairs - not reproduced
+    mol = fa.bond_mol_code()
     all_skipped = False
-    if not sameMolecule and bool(np.any(nbr_mask & (fa.bond_mol_hash() == hash8('')))):
+    if not sameMolecule and bool(np.any(nbr_mask & (mol == 0))):
         all_skipped = True   # every reference raises NameError (:107-109) and is skipped (:214)
         ref_mask = np.zeros_like(ref_mask)
     res = engine.p2_frame(fa.positions, fa.bond_atoms, mol, box, rmax, same_molecule=sameMolecule,

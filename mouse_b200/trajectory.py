@@ -373,36 +373,73 @@ def pair_correlation_trajectory(frames_positions, type_code, mol, ntypes, box, r
 
 
 def local_ordering_from_dump(topology, dump_path, bondtypes=None, rcut=0., coords_type="scaled",
-                             reference_res_types=None, same_molecule=True, device=None):
+                             reference_res_types=None, same_molecule=True, device=None, gather=False,
+                             parse_threads=None, hist_args=None):
     """Trajectory driver over files: ``topology`` is a ``FrameArrays`` (e.g.
     ``ingest.read_lmp_data_arrays(data_file)``), the frames come from a LAMMPS dump.  Every frame carries its own
     box, so the cell grid is re-planned per frame; frames are block-sharded over the ranks exactly like
     ``local_ordering_trajectory`` and reduced with the same single all-reduce.  Selections follow the reference:
     neighbour set = bonds passing ``bondtypes``, reference set = those also passing ``reference_res_types``
-    (``ordering_functions.py:196-199``); ``rcut == 0`` means half the box diagonal (``:185-186``)."""
-    import torch.distributed as dist
+    (``ordering_functions.py:196-199``); ``rcut == 0`` means half the box diagonal (``:185-186``).
+
+    Ingestion keeps up with the GPU: the dump is indexed once (byte offset of every ``ITEM: TIMESTEP``), every rank
+    seeks to its own block of frames and parses nothing else, a producer thread parses frame k+1 (multi-threaded C
+    number parser, GIL released) while frame k is on the GPU, and frames are handed to the pipeline one at a time -
+    the host never holds more than a few frames whatever the length of the trajectory."""
+    import os
+    import queue
+    import threading
     from . import ingest
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank() if world > 1 else 0
+    dist, rank, world = _dist_state()
     device = torch.device(device or "cuda")
-    timesteps, boxes, positions = ingest.read_lmp_dump_arrays(dump_path, topology.atom_num, coords_type)
-    lo, hi = shard_range(len(timesteps), rank, world)
+    index = ingest.index_lmp_dump(dump_path)
+    n_frames = len(index) - 1
+    lo, hi = shard_range(n_frames, rank, world)
     nbr_mask = topology.bond_mask(bond_types=bondtypes)
     ref_mask = topology.bond_mask(bond_types=bondtypes, res_types=reference_res_types)
-    mol = topology.bond_mol_hash().astype(np.int32)
+    mol = topology.bond_mol_code()
+    if parse_threads is None:
+        parse_threads = max(1, min(16, (os.cpu_count() or 1) // max(world, 1)))
     totals = TrajectoryTotals()
+    if hist_args is not None:
+        totals.p2_hist = np.zeros(int(hist_args[2]), np.int64)
     per_frame = []
     if hi > lo:
-        rc0 = float(rcut) if rcut != 0. else engine.half_diagonal(boxes[lo])
-        pipe = FramePipeline(topology.bond_atoms, mol, boxes[lo], rc0, positions[lo].shape[0],
-                             same_molecule=same_molecule, nbr_mask=nbr_mask, ref_mask=ref_mask, device=device)
-        done = []
-        for f in range(lo, hi):
-            rc = float(rcut) if rcut != 0. else engine.half_diagonal(boxes[f])
-            done += pipe.submit(positions[f], tag=int(timesteps[f]), box=boxes[f], rcut=rc)
-        done += pipe.drain()
-        pipe.close()
+        q = queue.Queue(maxsize=3)
+
+        def produce():
+            try:
+                for item in ingest.iter_lmp_dump_frames(dump_path, topology.atom_num, coords_type, frames=(lo, hi),
+                                                        index=index, threads=parse_threads):
+                    q.put(item)
+                q.put(None)
+            except BaseException as e:      # hand the error to the consumer
+                q.put(e)
+
+        threading.Thread(target=produce, daemon=True).start()
+        pipe, done, f = None, [], lo
+        while True:
+            item = q.get()
+            if item is None:
+                break
+            if isinstance(item, BaseException):
+                raise item
+            timestep, box, _, pos, _ = item
+            rc = float(rcut) if rcut != 0. else engine.half_diagonal(box)
+            if pipe is None:
+                pipe = FramePipeline(topology.bond_atoms, mol, box, rc, pos.shape[0], same_molecule=same_molecule,
+                                     nbr_mask=nbr_mask, ref_mask=ref_mask, device=device, hist_args=hist_args)
+            same_grid = np.array_equal(box, pipe.box) and rc == pipe.rcut      # NVT dumps replay the captured graph
+            done += pipe.submit(pos, tag=(f, int(timestep)), box=None if same_grid else box,
+                                rcut=None if same_grid else rc)
+            f += 1
+        if pipe is not None:
+            done += pipe.drain()
+            pipe.close()
         for t in done:
-            totals.add_frame(t["sum_mean"], t["n_refs"], t["n_pairs"])
+            totals.add_frame(t["sum_mean"], t["n_refs"], t["n_pairs"], t.get("hist"), t.get("n_hist_over", 0))
             per_frame.append((t["tag"], _frame_s(t)))
-    return per_frame, all_reduce_totals(totals, device)
+    totals = all_reduce_totals(totals, device)
+    if gather:
+        return gather_per_frame([(tag[0], s) for tag, s in per_frame], n_frames, device), totals
+    return [(tag[1], s) for tag, s in per_frame], totals

@@ -693,6 +693,43 @@ def test_dump_trajectory_matches_the_oracle_frame_by_frame():
         assert abs(per_frame[f][1] - s_ref) <= RTOL * abs(s_ref)
 
 
+def test_cli_over_several_files_and_over_two_ranks(tmp_path, capsys):
+    """calculate_local_ordering.py over several frame files: one S per file in command-line order (files are read
+    on a host thread while the previous one is on the GPU); under torchrun with two ranks the files are sharded and
+    rank 0 prints the same stdout."""
+    import subprocess
+    import sys
+    import calculate_local_ordering as cli
+    from mouse_b200.melt import jitter, make_melt, write_lammps_data
+    from tests.util import GOLDEN_DIR
+    melt = make_melt(12, 30, seed=3)
+    files = []
+    for f in range(5):
+        m2 = make_melt(12, 30, seed=3)
+        m2.positions[:] = jitter(melt, f, 0.05) if f else melt.positions
+        path = str(tmp_path / ("frame%d.data" % f))
+        write_lammps_data(m2, path)
+        files.append(path)
+    argv = files + ["--bondtypes", "1", "--max", "1.5", "--same-molecule"]
+    cli.main(argv)
+    out = capsys.readouterr().out
+    lines = out.strip().split("\n")
+    assert len(lines) == 5
+    single = []
+    for path in files:
+        cli.main([path] + argv[5:])
+        single.append(capsys.readouterr().out.strip())
+    assert lines == single
+    if torch.cuda.device_count() >= 2:
+        root = os.path.dirname(GOLDEN_DIR.rstrip("/").rsplit("/tests", 1)[0] + "/x")
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(29700 + os.getpid() % 200),
+                            os.path.join(root, "calculate_local_ordering.py")] + argv, capture_output=True, text=True,
+                           timeout=600, cwd=root)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert [ln for ln in r.stdout.strip().split("\n") if ln and not ln.startswith("W")] == lines
+
+
 # ------------------------------------------------------------------------------- next rows: director P2, COM RDF
 def test_crystallinity_parameter_against_the_reference():
     """CalculateCrystallinityParameter (ordering_functions.py:230-282): histogram, labels and recoloured atom types

@@ -48,6 +48,62 @@ def test_dump_frames_match_the_reference_reader(golden, coords):
     assert frames[0][4] is not None and frames[0][4].shape == (300, 3)              # image flags are carried along
 
 
+def test_dump_index_frame_ranges_and_threaded_parser(tmp_path):
+    """The byte-offset index lets a rank read only its own block of frames; the threaded number parser gives the
+    single-threaded values; a shuffled atom order is mapped back through the id column (cached per frame order)."""
+    import ctypes as C
+    from mouse_b200 import _lib
+    fa = ingest.read_lmp_data_arrays(DATA)
+    index = ingest.index_lmp_dump(DUMP)
+    assert len(index) == 4 and index[0] == 0 and ingest.count_lmp_dump_frames(DUMP, index) == 3
+    full = ingest.read_lmp_dump_arrays(DUMP, fa.atom_num, "scaled")
+    for lo, hi in ((0, 1), (1, 3), (2, 3), (0, 3)):
+        ts, boxes, pos = ingest.read_lmp_dump_arrays(DUMP, fa.atom_num, "scaled", frames=(lo, hi), index=index, threads=4)
+        assert np.array_equal(ts, full[0][lo:hi]) and np.array_equal(boxes, full[1][lo:hi])
+        assert np.array_equal(pos, full[2][lo:hi])
+    # a bigger synthetic dump with the atoms in a different order in every frame, parsed on several threads
+    rng = np.random.default_rng(7)
+    n, nf = 20000, 3
+    num = np.arange(1, n + 1)
+    path = tmp_path / "big.dump"
+    want = []
+    with open(path, "w") as f:
+        for k in range(nf):
+            xs = rng.random((n, 3))
+            want.append(-5.0 + 10.0 * xs)
+            order = rng.permutation(n) if k != 1 else np.arange(n)
+            f.write("ITEM: TIMESTEP\n%d\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n" % (100 * k, n))
+            f.write("-5.0 5.0\n-5.0 5.0\n-5.0 5.0\nITEM: ATOMS id type xs ys zs\n")
+            f.write("".join("%d 1 %r %r %r\n" % (num[i], float(xs[i, 0]), float(xs[i, 1]), float(xs[i, 2])) for i in order))
+    for threads in (1, 3, 8):
+        ts, boxes, pos = ingest.read_lmp_dump_arrays(str(path), num, "scaled", threads=threads)
+        assert ts.tolist() == [0, 100, 200] and np.array_equal(boxes, np.full((3, 3), 10.0))
+        for k in range(nf):
+            assert np.array_equal(pos[k], want[k])
+    text = open(path, "rb").read()
+    blk = text[text.index(b"ITEM: ATOMS"):]
+    blk = blk[blk.index(b"\n") + 1:blk.index(b"ITEM: TIMESTEP")]
+    a, b = np.empty(5 * n + 9), np.empty(5 * n + 9)
+    L = _lib.lib()
+    assert L.mouse_parse_doubles(blk, len(blk), C.c_void_p(a.ctypes.data), 5 * n) == 5 * n
+    assert L.mouse_parse_doubles_mt(blk, len(blk), C.c_void_p(b.ctypes.data), 5 * n, 7) == 5 * n
+    assert np.array_equal(a[:5 * n], b[:5 * n])
+    bad = blk[:300000] + b" nope " + blk[300000:]
+    assert L.mouse_parse_doubles(bad, len(bad), C.c_void_p(a.ctypes.data), 5 * n + 9) == \
+        L.mouse_parse_doubles_mt(bad, len(bad), C.c_void_p(b.ctypes.data), 5 * n + 9, 7) < 0
+
+
+def test_dense_molecule_codes_are_collision_free_and_stable():
+    fa = ingest.read_lmp_data_arrays(DATA)
+    code = fa.atom_mol_code()
+    assert code.dtype == np.int32 and code.min() >= 1          # no empty mol_id in this file
+    assert len(set(code.tolist())) == len(set(fa.atom_mol))    # one code per molecule id, no collisions
+    first = {}
+    for m, c in zip(fa.atom_mol, code):
+        assert first.setdefault(m, c) == c
+    assert np.array_equal(fa.bond_mol_code(), code[fa.bond_atoms[:, 0]])
+
+
 def test_dump_atom_count_mismatch_raises_like_the_reference():
     with pytest.raises(NameError):
         list(ingest.iter_lmp_dump_frames(DUMP, np.arange(1, 10), "scaled"))
