@@ -198,16 +198,68 @@ __global__ void __launch_bounds__(256) cell_assign_kernel(const double *__restri
   rec_tmp[b] = r;
 }
 
+// ---- heaviest cells first -------------------------------------------------------------------
+// The half-shell sweeps hand out home cells through a ticket counter; a crowded cell (cost ~ occupancy^2) taken late
+// leaves the other warps idle at the end of the kernel.  The item rows are therefore written in eight occupancy
+// classes, heaviest first (longest-processing-time-first scheduling): class of a cell = its occupancy relative to the
+// mean, in steps of half the mean; empty cells last.  counters[16 + k] = cells of class k (histogram taken by the scan),
+// counters[24 + k] = rows of class k handed out so far; the scan leaves every cell's row in place of its occupancy.
+#define MOUSE_NCLASS 8
+__device__ __forceinline__ int cell_class(int count, float inv_half_mean) {
+  if (count <= 0) return MOUSE_NCLASS - 1;
+  const int q = (int)((float)count * inv_half_mean);       // occupancy in units of half the mean
+  return q >= 6 ? 0 : 6 - q;
+}
+
+// Rows of the 8 consecutive cells a thread of the scan owns (v = their occupancies, first cell `base`): the block
+// reserves one contiguous range per class (one global atomic per class and tile), its cells take consecutive rows
+// inside it.  The row overwrites the cell's occupancy in place (dead after the scan).  All threads of the block call.
+__device__ __forceinline__ void lpt_rows(const int (&v)[8], int base, int ncells, int32_t *__restrict__ rows,
+                                         int64_t *counters, float inv_half_mean) {
+  __shared__ int s_n[MOUSE_NCLASS], s_first[MOUSE_NCLASS];
+  if (threadIdx.x < MOUSE_NCLASS) s_n[threadIdx.x] = 0;
+  __syncthreads();
+  int cls[8], rk[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    cls[k] = cell_class(v[k], inv_half_mean);
+    rk[k] = base + k < ncells ? atomicAdd(&s_n[cls[k]], 1) : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x < MOUSE_NCLASS) {
+    int first = 0;      // rows of the heavier classes come first
+    for (int j = 0; j < (int)threadIdx.x; ++j) first += (int)counters[16 + j];
+    const int mine = s_n[threadIdx.x];
+    const int tile = mine ? (int)atomicAdd((unsigned long long *)&counters[24 + threadIdx.x], (unsigned long long)mine) : 0;
+    s_first[threadIdx.x] = first + tile;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (base + k < ncells) rows[base + k] = s_first[cls[k]] + rk[k];
+}
+
 // ---- exclusive scan of cell_count[0..nc) -> cell_start, three small kernels ----------------
 __global__ void __launch_bounds__(256) scan_reduce_kernel(const int32_t *__restrict__ in, int nc,
-                                                          int32_t *__restrict__ block_sums) {
+                                                          int32_t *__restrict__ block_sums, int64_t *counters,
+                                                          float inv_half_mean) {
   __shared__ int s_warp[8];
+  __shared__ int s_hist[MOUSE_NCLASS];
+  if (threadIdx.x < MOUSE_NCLASS) s_hist[threadIdx.x] = 0;
+  __syncthreads();
   int base = blockIdx.x * MOUSE_SCAN_TILE;
   int sum = 0;
   for (int k = threadIdx.x; k < MOUSE_SCAN_TILE; k += 256) {
     int c = base + k;
-    if (c < nc) sum += in[c];
+    if (c < nc - 1) {      // (the last entry of the array is the unused total slot, not a cell)
+      const int v = in[c];
+      sum += v;
+      atomicAdd(&s_hist[cell_class(v, inv_half_mean)], 1);
+    }
   }
+  __syncthreads();
+  if (counters && threadIdx.x < MOUSE_NCLASS && s_hist[threadIdx.x])
+    atomicAdd((unsigned long long *)&counters[16 + threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
   sum = warp_sum(sum);
   if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
   __syncthreads();
@@ -255,9 +307,10 @@ __global__ void __launch_bounds__(1024) scan_top_kernel(int32_t *__restrict__ bl
   }
 }
 
-__global__ void __launch_bounds__(256) scan_apply_kernel(const int32_t *__restrict__ in, int nc,
+__global__ void __launch_bounds__(256) scan_apply_kernel(int32_t *in, int nc,
                                                          const int32_t *__restrict__ block_offs,
-                                                         int32_t *__restrict__ out) {
+                                                         int32_t *__restrict__ out, int64_t *counters,
+                                                         float inv_half_mean) {
   // each thread owns 8 consecutive entries of the tile
   __shared__ int s_warp[8];
   int base = blockIdx.x * MOUSE_SCAN_TILE + threadIdx.x * 8;
@@ -286,13 +339,15 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(const int32_t *__restri
     if (c < nc) out[c] = run;
     run += v[k];
   }
+  lpt_rows(v, base, nc - 1, in, counters, inv_half_mean);    // in[c] becomes the cell's row in the item table
 }
 
 // ---- exclusive scan, second kernel of two: every block sums the tile totals in front of it (a few dozen values)
 // and scans its own tile
-__global__ void __launch_bounds__(256) scan_apply2_kernel(const int32_t *__restrict__ in, int nc,
+__global__ void __launch_bounds__(256) scan_apply2_kernel(int32_t *in, int nc,
                                                           const int32_t *__restrict__ tile_sums,
-                                                          int32_t *__restrict__ out) {
+                                                          int32_t *__restrict__ out, int64_t *counters,
+                                                          float inv_half_mean) {
   __shared__ int s_warp[8];
   __shared__ int s_off;
   // offset of this tile = sum of the totals of all tiles before it
@@ -335,72 +390,7 @@ __global__ void __launch_bounds__(256) scan_apply2_kernel(const int32_t *__restr
     if (c < nc) out[c] = run;
     run += v[k];
   }
-}
-
-// ---- exclusive scan in ONE kernel (up to MOUSE_SCAN_FUSED_TILES tiles, all co-resident): every block publishes its
-// tile total (+1, so that 0 means "not there yet"; the array is zeroed with the counters) and then sums the totals of
-// the tiles in front of it as they appear.  Blocks only ever wait for blocks with a lower index, which the hardware
-// dispatches first.
-// (Measured: with three frames in flight the waiting blocks of this kernel sit on SM slots that the other frames'
-// sweeps want - 0.463 ms per 1M-bond frame against 0.420 ms with the two-kernel scan - so it is only used when a
-// build sets MOUSE_SCAN_FUSED_TILES > 0.)
-#ifndef MOUSE_SCAN_FUSED_TILES
-#define MOUSE_SCAN_FUSED_TILES 0
-#endif
-__global__ void __launch_bounds__(256) scan_fused_kernel(const int32_t *__restrict__ in, int nc,
-                                                         int32_t *__restrict__ tile_flags,
-                                                         int32_t *__restrict__ out) {
-  __shared__ int s_warp[8];
-  __shared__ int s_off;
-  const int base = blockIdx.x * MOUSE_SCAN_TILE + threadIdx.x * 8;
-  int v[8];
-  int tsum = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c = base + k;
-    v[k] = c < nc ? in[c] : 0;
-    tsum += v[k];
-  }
-  int x = tsum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int y = __shfl_up_sync(MOUSE_FULL_MASK, x, o);
-    if ((threadIdx.x & 31) >= o) x += y;
-  }
-  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int w = 0; w < 8; ++w) t += s_warp[w];
-    atomicExch(&tile_flags[blockIdx.x], t + 1);      // publish this tile's total
-  }
-  // totals of the tiles in front of this one
-  int part = 0;
-  for (int k = threadIdx.x; k < (int)blockIdx.x; k += 256) {
-    int f;
-    while ((f = ((volatile int32_t *)tile_flags)[k]) == 0) __nanosleep(20);
-    part += f - 1;
-  }
-  part = warp_sum(part);
-  __syncthreads();
-  int woff = 0;
-  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += s_warp[w];
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = part;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int w = 0; w < 8; ++w) t += s_warp[w];
-    s_off = t;
-  }
-  __syncthreads();
-  int run = s_off + woff + x - tsum;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c = base + k;
-    if (c < nc) out[c] = run;
-    run += v[k];
-  }
+  lpt_rows(v, base, nc - 1, in, counters, inv_half_mean);    // in[c] becomes the cell's row in the item table
 }
 
 // ---- scatter the item index into its cell (arrival order); the payload moves once, in cell_canon_kernel -----
@@ -432,12 +422,14 @@ __global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_canon_kernel(int ncell,
                                                          uint8_t *__restrict__ flag_sorted,
                                                          long long *__restrict__ acc_fix,
                                                          int32_t *__restrict__ acc_cnt,
-                                                         int32_t *__restrict__ items) {
+                                                         int32_t *__restrict__ items,
+                                                         const int32_t *__restrict__ cell_row) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < ncell; c += warps) {
     const int s = cell_start[c], e = cell_start[c + 1];
     const int nc = e - s;
+    const size_t row = items ? (size_t)cell_row[c] : 0;     // the cell's row in the item table: heaviest classes first
     if (items) {
       // the cell's item row for the half-shell sweeps (half_shell.cuh): lane L < 10 owns range L; an empty cell
       // only needs its size (the sweeps skip it)
@@ -470,8 +462,8 @@ __global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_canon_kernel(int ncell,
         val = lane < 10 ? src_k : lane < 20 ? len_k : lane < 30 ? off_k : lane == 30 ? nc
                                                                    : (cx | (cy << 10) | (cz << 20) | (boundary << 30));
       }
-      items[(size_t)c * HS_ITEM_INTS + lane] = val;
-      if (nc <= 0 && lane < 8) items[(size_t)c * HS_ITEM_INTS + 32 + lane] = 0;
+      items[row * HS_ITEM_INTS + lane] = val;
+      if (nc <= 0 && lane < 8) items[row * HS_ITEM_INTS + 32 + lane] = 0;
     }
     if (nc <= 0) continue;
     float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
@@ -519,7 +511,7 @@ __global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_canon_kernel(int ncell,
       if (lane < 8) {
         const float v = lane == 0 ? blo[0] : lane == 1 ? blo[1] : lane == 2 ? blo[2] : lane == 3 ? bhi[0]
                         : lane == 4 ? bhi[1] : lane == 5 ? bhi[2] : 0.0f;
-        items[(size_t)c * HS_ITEM_INTS + 32 + lane] = __float_as_int(v);
+        items[row * HS_ITEM_INTS + 32 + lane] = __float_as_int(v);
       }
     }
   }
@@ -599,20 +591,19 @@ static int cell_build_tail(int mode, const uint8_t *ref_mask, int64_t n, const m
                            const Workspace &w, cudaStream_t st) {
   int nc = grid->ncell + 1;
   int tiles = (nc + MOUSE_SCAN_TILE - 1) / MOUSE_SCAN_TILE;
-  if (tiles <= MOUSE_SCAN_FUSED_TILES) {   // one kernel; scan_blocks was zeroed together with the counters
-    scan_fused_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start);
-    MOUSE_LAUNCH_CHECK("scan_fused_kernel");
-  } else if (tiles <= 4096) {   // the apply kernel sums the tile totals in front of its tile itself
-    scan_reduce_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks);
+  // occupancy classes of the item rows (heaviest cells first): in units of half the mean occupancy
+  const float inv_half_mean = (float)(2.0 * (double)grid->ncell / (double)(n > 0 ? n : 1));
+  if (tiles <= 4096) {   // the apply kernel sums the tile totals in front of its tile itself
+    scan_reduce_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.counters, inv_half_mean);
     MOUSE_LAUNCH_CHECK("scan_reduce_kernel");
-    scan_apply2_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start);
+    scan_apply2_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start, w.counters, inv_half_mean);
     MOUSE_LAUNCH_CHECK("scan_apply2_kernel");
   } else {
-    scan_reduce_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks);
+    scan_reduce_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.counters, inv_half_mean);
     MOUSE_LAUNCH_CHECK("scan_reduce_kernel");
     scan_top_kernel<<<1, 1024, 0, st>>>(w.scan_blocks, tiles);
     MOUSE_LAUNCH_CHECK("scan_top_kernel");
-    scan_apply_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start);
+    scan_apply_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start, w.counters, inv_half_mean);
     MOUSE_LAUNCH_CHECK("scan_apply_kernel");
   }
   if (n > 0) {
@@ -625,11 +616,11 @@ static int cell_build_tail(int mode, const uint8_t *ref_mask, int64_t n, const m
     if (mode == 0)
       cell_canon_kernel<0><<<blocks, MOUSE_ITEM_BLOCK, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.cell_of, w.rec_sorted,
                                                    w.idx_sorted, w.cell_sorted,
-                                                   w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr);
+                                                   w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr, w.cell_count);
     else
       cell_canon_kernel<1><<<blocks, MOUSE_ITEM_BLOCK, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.cell_of, w.rec_sorted,
                                                    w.idx_sorted, w.cell_sorted,
-                                                   w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr);
+                                                   w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr, w.cell_count);
     MOUSE_LAUNCH_CHECK("cell_canon_kernel");
   }
   return MOUSE_OK;

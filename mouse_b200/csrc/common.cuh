@@ -44,7 +44,7 @@ static_assert(sizeof(Rec) == 48, "Rec must be 48 bytes");
 // Everything the cell list and the sweeps need, carved out of one caller-provided buffer.
 struct Workspace {
   // per cell
-  int32_t *cell_count;   // [ncell+1]   items per cell (atomic histogram), last entry unused
+  int32_t *cell_count;   // [ncell+1]   items per cell (atomic histogram), last entry unused; after the scan: the cell's row in `items`
   int32_t *cell_start;   // [ncell+1]   exclusive scan; cell_start[ncell] = items in the list
   int32_t *scan_blocks;  // [scan_nblocks+1]
   int32_t *items;        // [ncell][40] item table of the half-shell sweeps (ranges of the 14 cells, see half_shell.cuh)

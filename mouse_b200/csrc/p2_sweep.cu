@@ -82,7 +82,7 @@ __device__ __forceinline__ double exact_pair(const int32_t *__restrict__ idx, co
 
 // ------------------------------------------------------------------ half-shell fast sweep
 #ifndef HS_MAXHOME
-#define HS_MAXHOME 64      // home cells with more bonds are decided pair by pair, exactly (hs_oversize)
+#define HS_MAXHOME 32      // home cells with more bonds are decided pair by pair, exactly (hs_oversize)
 #endif
 #ifndef HS_GRP
 #define HS_GRP 8           // references reduced together (transposed reduction through shared memory)
@@ -138,61 +138,141 @@ __device__ __forceinline__ void hs_flush(long long *acc_fix, int32_t *acc_cnt, i
                : "memory");
 }
 
+// explicit shared-memory accesses with a 32-bit address held in a register
+__device__ __forceinline__ float4 lds_float4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_float4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ double2 lds_double2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return (uint32_t)v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, int v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+
 struct HsConst {
-  float rc2_c, rc2_w, negw, nearz_thr;
+  float nlo;            // -rc2_lo: t = d2 - rc2_lo is negative for a sure hit
+  unsigned band_bits;   // bit pattern of the guard band width: 0 <= t <= width (compared as unsigned) is undecided
+  float nearz_thr;
 };
+
+// One reference of the current window as the loop reads it (64 bytes, four 128-bit broadcast loads): the negated FP32
+// coordinates duplicated for the packed f32x2 subtraction, the molecule code and the FP64 unit vector.
+struct __align__(16) HsRef {
+  float4 a;    // -x, -x, -y, -y
+  float4 b;    // -z, -z, molecule code bits, unused
+  double2 u;   // ux, uy
+  double2 v;   // uz, unused
+};
+
+__device__ __forceinline__ unsigned hs_umin3(unsigned a, unsigned b, unsigned c) { return __vimin3_u32(a, b, c); }
+
+// Two packed floats in ONE 64-bit register (an aligned register pair by construction: the packed f32x2 instructions
+// then take their operands as they are, the compiler never has to re-pair two scalar registers inside the loop).
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pk2_make(float lo, float hi) {
+  pk2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void pk2_bits(pk2 v, int &lo, int &hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ void pk2_floats(pk2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ pk2 pk2_add(pk2 a, pk2 b) {
+  pk2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ pk2 pk2_mul(pk2 a, pk2 b) {
+  pk2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ pk2 pk2_fma(pk2 a, pk2 b, pk2 c) {
+  pk2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// 16 bytes of shared memory as two packed pairs / as two doubles
+__device__ __forceinline__ void lds_pk2x2(uint32_t addr, pk2 &a, pk2 &b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+// @(m < 0): accj += d * d; acci += d * d   (the hit mask m predicates the FP64 accumulation: no select, no copy of d)
+__device__ __forceinline__ void hs_acc_if(double &accj, double &acci, double d, int m) {
+  asm("{\n.reg .pred p;\nsetp.lt.s32 p, %3, 0;\n@p fma.rn.f64 %0, %2, %2, %0;\n@p fma.rn.f64 %1, %2, %2, %1;\n}"
+      : "+d"(accj), "+d"(acci)
+      : "d"(d), "r"(m));
+}
 
 // The references of one home cell against NPP register-resident slot pairs (specialised on NPP: no guards inside the
 // reference loop, the slot pairs interleave freely).
 template <int SLOTS, int NPP, bool EXCL_MOL>
 __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k, const int lane, const bool pass0,
-                                            const int hs, const int nhome, const float2 (&xr2)[SLOTS / 2],
-                                            const float2 (&yr2)[SLOTS / 2], const float2 (&zr2)[SLOTS / 2],
+                                            const int hs, const int nhome, const pk2 (&xr2)[SLOTS / 2],
+                                            const pk2 (&yr2)[SLOTS / 2], const pk2 (&zr2)[SLOTS / 2],
                                             const double (&ux)[SLOTS], const double (&uy)[SLOTS],
                                             const double (&uz)[SLOTS], double (&accj)[SLOTS], int (&cntj)[SLOTS],
-                                            const int (&molr)[SLOTS], const float4 *s_homeP,
-                                            const double (*s_homeU)[HS_MAXHOME], double (*s_acc)[33],
+                                            const int (&molr)[SLOTS], const uint32_t s_ref, double (*s_acc)[33],
                                             int (*s_cnt)[33], const int (*s_gid)[32]) {
   static_assert(HS_GRP == 8 || HS_GRP == 4, "reference groups of 4 or 8");
   static_assert(HS_MAXHOME % 2 == 0, "references are processed two at a time");
   constexpr int HSL = HS_MAXHOME / 32;   // slots of pass 0 that may hold home-cell bonds
-  const float2 nrc = make_float2(-k.rc2_c, -k.rc2_c);
+  const pk2 nlo = pk2_make(k.nlo, k.nlo);
+  // home-home pairs are decided once: candidate t = 32 c + lane of pass 0 counts for reference il only if t > il.
+  // (il - t) >> 31 is the all-ones mask of that rule; jl[c] = t (pass 0) or a large number (every il passes)
+  int jl[HSL];
+#pragma unroll
+  for (int c = 0; c < HSL; ++c) jl[c] = pass0 ? 32 * c + lane : 0x3fffffff;
   // References are processed in groups of HS_GRP.  The inner loop is one basic block: the rare-candidate
-  // decision is only recorded (one bit per reference) and the reference-side partial of reference il is
+  // decision is only recorded (two bits per pair of references) and the reference-side partial of reference il is
   // stored while reference il + 1 is computed, so no iteration ends by draining its own FP64 chain.
   for (int base = 0; base < nhome; base += HS_GRP) {
     const int nref = min(HS_GRP, nhome - base);
     unsigned rare = 0u;
     // two references per iteration: two independent dependency chains per warp.  The second one of an odd
-    // tail is switched off through its threshold
+    // tail is the sentinel record behind the window (far away: no hits, never in the band)
+    uint32_t rp = s_ref + 64u * (uint32_t)base;
+    uint32_t ap = smem_addr(&s_acc[0][lane]), cp = smem_addr(&s_cnt[0][lane]);
 #pragma unroll 1
-    for (int r = 0; r < nref; r += 2) {
+    for (int r = 0; r < nref; r += 2, rp += 128u, ap += 2u * 33u * 8u, cp += 2u * 33u * 4u) {
       const int il = base + r;
-      const float4 pa = s_homeP[il], pb = s_homeP[il + 1];
-      const double uax = s_homeU[0][il], uay = s_homeU[1][il], uaz = s_homeU[2][il];
-      const double ubx = s_homeU[0][il + 1], uby = s_homeU[1][il + 1], ubz = s_homeU[2][il + 1];
-      const float negwb = r + 1 < nref ? k.negw : -3.0e38f;
-      const int mola = __float_as_int(pa.w), molb = __float_as_int(pb.w);
-      const float2 nax = make_float2(-pa.x, -pa.x), nay = make_float2(-pa.y, -pa.y), naz = make_float2(-pa.z, -pa.z);
-      const float2 nbx = make_float2(-pb.x, -pb.x), nby = make_float2(-pb.y, -pb.y), nbz = make_float2(-pb.z, -pb.z);
-      // home-home pairs are decided once: candidate t > il (pass 0: slot c < HSL holds t = 32 c + lane)
-      const int ea = pass0 ? il : -1, eb = pass0 ? il + 1 : -1;
+      pk2 nax, nay, naz, nbx, nby, nbz, mola2, molb2;
+      lds_pk2x2(rp, nax, nay);
+      lds_pk2x2(rp + 16u, naz, mola2);
+      lds_pk2x2(rp + 64u, nbx, nby);
+      lds_pk2x2(rp + 80u, nbz, molb2);
+      const double2 ua = lds_double2(rp + 32u), va = lds_double2(rp + 48u);
+      const double2 ub = lds_double2(rp + 96u), vb = lds_double2(rp + 112u);
+      const double uax = ua.x, uay = ua.y, uaz = va.x, ubx = ub.x, uby = ub.y, ubz = vb.x;
+      int mola, molb, unused;
+      pk2_bits(mola2, mola, unused);
+      pk2_bits(molb2, molb, unused);
       double acca0 = 0.0, acca1 = 0.0, accb0 = 0.0, accb1 = 0.0;
       int cnta = 0, cntb = 0;
-      float banda = 3.0e38f, nza = 3.0e38f, bandb = 3.0e38f, nzb = 3.0e38f;
+      unsigned banda = 0xffffffffu, bandb = 0xffffffffu;
+      float nza = 3.0e38f, nzb = 3.0e38f;
 #pragma unroll
       for (int pp = 0; pp < NPP; ++pp) {
-        const float2 dxa = __fadd2_rn(xr2[pp], nax), dya = __fadd2_rn(yr2[pp], nay), dza = __fadd2_rn(zr2[pp], naz);
-        const float2 dxb = __fadd2_rn(xr2[pp], nbx), dyb = __fadd2_rn(yr2[pp], nby), dzb = __fadd2_rn(zr2[pp], nbz);
-#ifdef HS_FOLD_RC
-        const float2 ta = __ffma2_rn(dza, dza, __ffma2_rn(dya, dya, __ffma2_rn(dxa, dxa, nrc)));   // d2 - rc2
-        const float2 tb = __ffma2_rn(dzb, dzb, __ffma2_rn(dyb, dyb, __ffma2_rn(dxb, dxb, nrc)));
-#else
-        const float2 ta = __fadd2_rn(__ffma2_rn(dza, dza, __ffma2_rn(dya, dya, __fmul2_rn(dxa, dxa))), nrc);   // d2 - rc2
-        const float2 tb = __fadd2_rn(__ffma2_rn(dzb, dzb, __ffma2_rn(dyb, dyb, __fmul2_rn(dxb, dxb))), nrc);
-#endif
-        banda = fminf(banda, fminf(fabsf(ta.x), fabsf(ta.y)));
-        bandb = fminf(bandb, fminf(fabsf(tb.x), fabsf(tb.y)));
+        const pk2 dxa = pk2_add(xr2[pp], nax), dya = pk2_add(yr2[pp], nay), dza = pk2_add(zr2[pp], naz);
+        const pk2 dxb = pk2_add(xr2[pp], nbx), dyb = pk2_add(yr2[pp], nby), dzb = pk2_add(zr2[pp], nbz);
+        const pk2 ta = pk2_add(pk2_fma(dza, dza, pk2_fma(dya, dya, pk2_mul(dxa, dxa))), nlo);   // d2 - rc2_lo
+        const pk2 tb = pk2_add(pk2_fma(dzb, dzb, pk2_fma(dyb, dyb, pk2_mul(dxb, dxb))), nlo);
+        int ta0, ta1, tb0, tb1;
+        pk2_bits(ta, ta0, ta1);
+        pk2_bits(tb, tb0, tb1);
+        // smallest non-negative t (negative values are huge as unsigned): in the guard band if <= its width
+        banda = hs_umin3(banda, (unsigned)ta0, (unsigned)ta1);
+        bandb = hs_umin3(bandb, (unsigned)tb0, (unsigned)tb1);
         const double da0 = fma(uax, ux[2 * pp], fma(uay, uy[2 * pp], uaz * uz[2 * pp]));
         const double da1 = fma(uax, ux[2 * pp + 1], fma(uay, uy[2 * pp + 1], uaz * uz[2 * pp + 1]));
         const double db0 = fma(ubx, ux[2 * pp], fma(uby, uy[2 * pp], ubz * uz[2 * pp]));
@@ -200,54 +280,56 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
         // smallest |d| over ALL slots (as the high word, compared as a float): a false alarm only costs time
         nza = fminf(nza, fminf(fabsf(__int_as_float(__double2hiint(da0))), fabsf(__int_as_float(__double2hiint(da1)))));
         nzb = fminf(nzb, fminf(fabsf(__int_as_float(__double2hiint(db0))), fabsf(__int_as_float(__double2hiint(db1)))));
-        // Branch-free: the weight w is d with its high word cleared on a miss (|w| < 1e-300, w * w vanishes
-        // in the sums), so the FP64 FMAs are unconditional
-        bool pa0 = ta.x < k.negw, pa1 = ta.y < k.negw, pb0 = tb.x < negwb, pb1 = tb.y < negwb;
-        // (bitwise & on purpose: && makes ptxas emit divergent branches here)
+        // Branch-free: the hit mask is the sign of t spread over the word (combined with the home-cell j > i rule and
+        // the molecule test); it predicates the FP64 accumulation and is subtracted from the counts
+        int ma0 = ta0 >> 31, ma1 = ta1 >> 31, mb0 = tb0 >> 31, mb1 = tb1 >> 31;
         if (2 * pp < HSL) {
-          pa0 = pa0 & (lane > ea - 64 * pp);
-          pb0 = pb0 & (lane > eb - 64 * pp);
+          ma0 &= (il - jl[2 * pp]) >> 31;
+          mb0 &= (il + 1 - jl[2 * pp]) >> 31;
         }
         if (2 * pp + 1 < HSL) {
-          pa1 = pa1 & (lane > ea - 64 * pp - 32);
-          pb1 = pb1 & (lane > eb - 64 * pp - 32);
+          ma1 &= (il - jl[2 * pp + 1]) >> 31;
+          mb1 &= (il + 1 - jl[2 * pp + 1]) >> 31;
         }
         if (EXCL_MOL) {
-          pa0 = pa0 & (molr[2 * pp] != mola);
-          pa1 = pa1 & (molr[2 * pp + 1] != mola);
-          pb0 = pb0 & (molr[2 * pp] != molb);
-          pb1 = pb1 & (molr[2 * pp + 1] != molb);
+          ma0 &= molr[2 * pp] != mola ? -1 : 0;
+          ma1 &= molr[2 * pp + 1] != mola ? -1 : 0;
+          mb0 &= molr[2 * pp] != molb ? -1 : 0;
+          mb1 &= molr[2 * pp + 1] != molb ? -1 : 0;
         }
-        const double wa0 = __hiloint2double(pa0 ? __double2hiint(da0) : 0, __double2loint(da0));
-        const double wa1 = __hiloint2double(pa1 ? __double2hiint(da1) : 0, __double2loint(da1));
-        const double wb0 = __hiloint2double(pb0 ? __double2hiint(db0) : 0, __double2loint(db0));
-        const double wb1 = __hiloint2double(pb1 ? __double2hiint(db1) : 0, __double2loint(db1));
+        const double wa0 = __hiloint2double(__double2hiint(da0) & ma0, __double2loint(da0));
+        const double wa1 = __hiloint2double(__double2hiint(da1) & ma1, __double2loint(da1));
+        const double wb0 = __hiloint2double(__double2hiint(db0) & mb0, __double2loint(db0));
+        const double wb1 = __hiloint2double(__double2hiint(db1) & mb1, __double2loint(db1));
         accj[2 * pp] = fma(wb0, wb0, fma(wa0, wa0, accj[2 * pp]));
         accj[2 * pp + 1] = fma(wb1, wb1, fma(wa1, wa1, accj[2 * pp + 1]));
         acca0 = fma(wa0, wa0, acca0);
         acca1 = fma(wa1, wa1, acca1);
         accb0 = fma(wb0, wb0, accb0);
         accb1 = fma(wb1, wb1, accb1);
-        cntj[2 * pp] += (pa0 ? 1 : 0) + (pb0 ? 1 : 0);
-        cntj[2 * pp + 1] += (pa1 ? 1 : 0) + (pb1 ? 1 : 0);
-        cnta += (pa0 ? 1 : 0) + (pa1 ? 1 : 0);
-        cntb += (pb0 ? 1 : 0) + (pb1 ? 1 : 0);
+        cntj[2 * pp] = cntj[2 * pp] - ma0 - mb0;
+        cntj[2 * pp + 1] = cntj[2 * pp + 1] - ma1 - mb1;
+        cnta = cnta - ma0 - ma1;
+        cntb = cntb - mb0 - mb1;
       }
-      rare |= (unsigned)(banda <= k.rc2_w || nza <= k.nearz_thr) << r;
-      rare |= (unsigned)(r + 1 < nref && (bandb <= k.rc2_w || nzb <= k.nearz_thr)) << (r + 1);
-      s_acc[r][lane] = acca0 + acca1;
-      s_cnt[r][lane] = cnta;
-      s_acc[r + 1][lane] = accb0 + accb1;
-      s_cnt[r + 1][lane] = cntb;
+      // either reference of the pair has a candidate in the band or a near-zero dot: both are re-tested below
+      if ((min(banda, bandb) <= k.band_bits) | (fminf(nza, nzb) <= k.nearz_thr)) rare |= 3u << r;
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(ap), "d"(acca0 + acca1) : "memory");
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(ap + 33u * 8u), "d"(accb0 + accb1) : "memory");
+      asm volatile("st.shared.s32 [%0], %1;" ::"r"(cp), "r"(cnta) : "memory");
+      asm volatile("st.shared.s32 [%0], %1;" ::"r"(cp + 33u * 4u), "r"(cntb) : "memory");
     }
+    rare &= (1u << nref) - 1u;     // the sentinel of an odd tail is not a reference
     // ---- rare: candidates inside the guard band / near-zero dots are handed to p2_fixup_kernel
     while (rare) {
       const int r = __ffs(rare) - 1;
       rare &= rare - 1;
       const int il = base + r;
-      const float4 pi = s_homeP[il];
-      const double uix = s_homeU[0][il], uiy = s_homeU[1][il], uiz = s_homeU[2][il];
-      const int moli = __float_as_int(pi.w);
+      const uint32_t rq = s_ref + 64u * (uint32_t)il;
+      const float4 ria = lds_float4(rq), rib = lds_float4(rq + 16u);
+      const double2 ui = lds_double2(rq + 32u), vi = lds_double2(rq + 48u);
+      const double uix = ui.x, uiy = ui.y, uiz = vi.x;
+      const int moli = __float_as_int(rib.z);
       const int il_eff = pass0 ? il : -1;
 #pragma unroll
       for (int c = 0; c < 2 * NPP; ++c) {
@@ -256,18 +338,16 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
         if (c < HSL) pc = pc && 32 * c + lane > il_eff;
         if (EXCL_MOL) pc = pc && molr[c] != moli;
         if (pc) {
-          const float px = (c & 1) ? xr2[c >> 1].y : xr2[c >> 1].x;
-          const float py = (c & 1) ? yr2[c >> 1].y : yr2[c >> 1].x;
-          const float pz = (c & 1) ? zr2[c >> 1].y : zr2[c >> 1].x;
-          const float dx = __fadd_rn(px, -pi.x), dy = __fadd_rn(py, -pi.y), dz = __fadd_rn(pz, -pi.z);
-#ifdef HS_FOLD_RC
-          const float t = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, -k.rc2_c)));
-#else
-          const float t = __fadd_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))), -k.rc2_c);
-#endif
-          if (fabsf(t) <= k.rc2_w) {
+          float px0, px1, py0, py1, pz0, pz1;
+          pk2_floats(xr2[c >> 1], px0, px1);
+          pk2_floats(yr2[c >> 1], py0, py1);
+          pk2_floats(zr2[c >> 1], pz0, pz1);
+          const float px = (c & 1) ? px1 : px0, py = (c & 1) ? py1 : py0, pz = (c & 1) ? pz1 : pz0;
+          const float dx = __fadd_rn(px, ria.x), dy = __fadd_rn(py, ria.z), dz = __fadd_rn(pz, rib.x);
+          const float t = __fadd_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))), k.nlo);
+          if (__float_as_uint(t) <= k.band_bits) {
             fix_append(a.counters, a.fix_list, a.fix_cap, hs + il, g, 0);          // undecided: nothing was added
-          } else if (t < k.negw) {
+          } else if (t < 0.0f) {
             const double d = fma(uix, ux[c], fma(uiy, uy[c], uiz * uz[c]));
             if (fabs(d) < HS_NEARZ) fix_append(a.counters, a.fix_list, a.fix_cap, hs + il, g, 1);   // counted; cos^2 == 0 ?
           }
@@ -298,22 +378,9 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
   }
 }
 
-// explicit shared-memory accesses with a 32-bit address held in a register
-__device__ __forceinline__ float4 lds_float4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts_float4(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts_u16(uint32_t addr, int v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
-}
-
 // Drops the candidates of the landing zone that are farther than the cutoff from the bounding box of the home cell's
 // bonds (no reference of the home cell can reach them): s_sel[0..M) = landing-zone index of the candidates kept, in
-// order; returns M.  bb (shared memory) = home cell centre, box lower corner, box upper corner.  BND: the home cell
+// order, as BYTE offsets (48 * index); returns M.  bb (shared memory) = home cell centre, box lower corner, box upper corner.  BND: the home cell
 // sits on the periodic boundary; the candidates are first moved to their image nearest to the home cell centre
 // (written back to the landing zone).  Two candidates per lane and trip (two independent chains).
 template <bool BND>
@@ -344,8 +411,8 @@ __device__ __forceinline__ int hs_cull(uint32_t land, uint32_t sel, const float 
     const bool ka = (ta < nland) & (d2 <= thr), kb = (tb < nland) & (e2 <= thr);
     const unsigned ba = __ballot_sync(MOUSE_FULL_MASK, ka), bq = __ballot_sync(MOUSE_FULL_MASK, kb);
     const int na = __popc(ba);
-    if (ka) sts_u16(sel + 2u * (uint32_t)(M + __popc(ba & lt)), ta);
-    if (kb) sts_u16(sel + 2u * (uint32_t)(M + na + __popc(bq & lt)), tb);
+    if (ka) sts_u16(sel + 2u * (uint32_t)(M + __popc(ba & lt)), 48 * ta);
+    if (kb) sts_u16(sel + 2u * (uint32_t)(M + na + __popc(bq & lt)), 48 * tb);
     M += na + __popc(bq);
   }
   __syncwarp();
@@ -360,10 +427,11 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
   constexpr int LZ = HS_LZ;
   static_assert(SLOTS % 2 == 0 && NC >= HS_MAXHOME && LZ >= HS_MAXHOME && LZ % 64 == 0 && NPAIR <= 6,
                 "slots come in pairs; the home cell lives in the first sub-pass of the first chunk");
-  __shared__ __align__(128) Rec s_land[LZ];         // TMA landing zone (one chunk of the candidate concatenation)
-  __shared__ uint16_t s_sel[LZ];                    // landing-zone index of the candidates that survived the cull
-  __shared__ float4 s_homeP[HS_MAXHOME];            // the home cell's bonds: the references of this item
-  __shared__ double s_homeU[3][HS_MAXHOME];
+  __shared__ __align__(128) Rec s_land[LZ + 1];     // TMA landing zone (one chunk of the candidate concatenation);
+                                                    // record LZ is the filler of the empty register slots
+  __shared__ uint16_t s_sel[LZ + NC];               // byte offset in the landing zone of the candidates that survived
+                                                    // the cull, then NC times the filler
+  __shared__ HsRef s_ref[HS_MAXHOME + 2];           // the references of this window (+ the far-away sentinel)
   __shared__ double s_acc[HS_GRP][33];              // per-lane partial sums of 8 references (transposed reduce)
   __shared__ int s_cnt[HS_GRP][33];                 // ... and partial counts
   __shared__ int s_gid[SLOTS][32];                  // sorted slot of every register-resident candidate (-1: empty)
@@ -374,9 +442,8 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
   __shared__ __align__(8) uint64_t s_bar;
   const int lane = threadIdx.x;
   HsConst k;
-  k.rc2_c = 0.5f * (a.g.rc2_lo + a.g.rc2_hi);             // guard band [c - w, c + w] around rc^2
-  k.rc2_w = 0.5f * (a.g.rc2_hi - a.g.rc2_lo) * 1.0001f;
-  k.negw = -k.rc2_w;
+  k.nlo = -a.g.rc2_lo;                                    // guard band [rc2_lo, rc2_hi] around rc^2
+  k.band_bits = __float_as_uint((a.g.rc2_hi - a.g.rc2_lo) * 1.0001f);
   k.nearz_thr = __int_as_float(HS_NEARZ_HI);
   const float cull_thr = a.g.rc2_hi * 1.001f;             // box distance test: well outside the guard band
 
@@ -384,8 +451,11 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     mbar_init(&s_bar, 1);
     fence_mbar_init();
   }
-#pragma unroll
-  for (int q = 0; q < LZ / 32; ++q) s_sel[32 * q + lane] = 0;
+  for (int q = lane; q < LZ + NC; q += 32) s_sel[q] = (uint16_t)(48 * LZ);
+  if (lane == 0) {
+    s_land[LZ].p = make_float4(HS_PAD, HS_PAD, HS_PAD, __int_as_float(-1));
+    s_land[LZ].u = make_double4(1.0, 1.0, 1.0, __hiloint2double(0, -1));
+  }
   __syncwarp();
   uint32_t phase = 0;
 
@@ -460,6 +530,10 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
       phase ^= 1u;
       M = cur.boundary ? hs_cull<true>(smem_addr(s_land), smem_addr(s_sel), s_bb, a.g, lane, nland, cull_thr)
                        : hs_cull<false>(smem_addr(s_land), smem_addr(s_sel), s_bb, a.g, lane, nland, cull_thr);
+      // the NC entries behind the survivors point at the filler record
+#pragma unroll
+      for (int c = 0; c < SLOTS; ++c) s_sel[M + 32 * c + lane] = (uint16_t)(48 * LZ);
+      __syncwarp();
       sp = 0;
     }
     // ---- landing zone -> registers: candidates [k0, k0 + NC) of the survivors (first chunk: behind the window start)
@@ -469,41 +543,54 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     const bool last = k0 + NC >= M;                 // last sub-pass of this chunk
     const bool pass0 = (ch == 0) & (sp == 0);       // the home cell leads the concatenation and is never dropped
     const int hs = cur.hs + rb, nhome = min(cur.nhome - rb, HS_MAXHOME);   // this window's references
-    float2 xr2[NPAIR], yr2[NPAIR], zr2[NPAIR];
+    pk2 xr2[NPAIR], yr2[NPAIR], zr2[NPAIR];
     double ux[SLOTS], uy[SLOTS], uz[SLOTS];
     double accj[SLOTS];
     int cntj[SLOTS], molr[SLOTS];
+    {
+      const uint32_t land = smem_addr(s_land), selp = smem_addr(s_sel) + 2u * (uint32_t)(k0 + lane);
+      uint32_t off[SLOTS];
 #pragma unroll
-    for (int pp = 0; pp < NPAIR; ++pp) {
-      float q[2][3];
+      for (int c = 0; c < SLOTS; ++c) off[c] = land + lds_u16(selp + 64u * c);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = 2 * pp + h;
-        const int tl = 32 * c + lane;
-        const bool valid = tl < nvalid;
-        const int t = s_sel[min(k0 + tl, LZ - 1)];
-        const float4 p = s_land[t].p;
-        const double4 u = s_land[t].u;
-        q[h][0] = valid ? p.x : HS_PAD;
-        q[h][1] = valid ? p.y : HS_PAD;
-        q[h][2] = valid ? p.z : HS_PAD;
-        ux[c] = valid ? u.x : 1.0;
-        uy[c] = valid ? u.y : 1.0;
-        uz[c] = valid ? u.z : 1.0;
-        s_gid[c][lane] = valid ? __double2loint(u.w) : -1;
-        molr[c] = __float_as_int(p.w);
-        accj[c] = 0.0;
-        cntj[c] = 0;
-        if (c < HSL && pass0 && tl < nhome) {   // survivors [0, nhome) of the cell are its own bonds, in order
-          s_homeP[tl] = make_float4(p.x, p.y, p.z, p.w);
-          s_homeU[0][tl] = u.x;
-          s_homeU[1][tl] = u.y;
-          s_homeU[2][tl] = u.z;
+      for (int pp = 0; pp < NPAIR; ++pp) {
+        float4 p[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = 2 * pp + h;
+          p[h] = lds_float4(off[c]);
+          const double2 u01 = lds_double2(off[c] + 16u), u2w = lds_double2(off[c] + 32u);
+          ux[c] = u01.x;
+          uy[c] = u01.y;
+          uz[c] = u2w.x;
+          s_gid[c][lane] = __double2loint(u2w.y);      // the filler record carries -1
+          molr[c] = __float_as_int(p[h].w);
+          accj[c] = 0.0;
+          cntj[c] = 0;
+          if (c < HSL && pass0 && 32 * c + lane < nhome) {   // survivors [0, nhome) of the cell are its own bonds, in order
+            HsRef rr;
+            rr.a = make_float4(-p[h].x, -p[h].x, -p[h].y, -p[h].y);
+            rr.b = make_float4(-p[h].z, -p[h].z, p[h].w, 0.0f);
+            rr.u = u01;
+            rr.v = make_double2(u2w.x, 0.0);
+            s_ref[32 * c + lane] = rr;
+          }
         }
+        // (the packed add of -0.0 makes each pair the RESULT of an instruction: the compiler then keeps the pair in
+        // an aligned register pair instead of re-pairing two scalar registers inside the reference loop)
+        const pk2 nz2 = pk2_make(-0.0f, -0.0f);
+        xr2[pp] = pk2_add(pk2_make(p[0].x, p[1].x), nz2);
+        yr2[pp] = pk2_add(pk2_make(p[0].y, p[1].y), nz2);
+        zr2[pp] = pk2_add(pk2_make(p[0].z, p[1].z), nz2);
       }
-      xr2[pp] = make_float2(q[0][0], q[1][0]);
-      yr2[pp] = make_float2(q[0][1], q[1][1]);
-      zr2[pp] = make_float2(q[0][2], q[1][2]);
+      if (pass0 && lane == 0) {      // sentinel behind the window: the partner of the last reference of an odd tail
+        HsRef rr;
+        rr.a = make_float4(HS_PAD, HS_PAD, HS_PAD, HS_PAD);       // at -HS_PAD: far from the bonds AND from the filler
+        rr.b = make_float4(HS_PAD, HS_PAD, __int_as_float(-1), 0.0f);
+        rr.u = make_double2(1.0, 0.0);
+        rr.v = make_double2(0.0, 0.0);
+        s_ref[nhome] = rr;
+      }
     }
     __syncwarp();
 
@@ -538,7 +625,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     // ---- the references of the home cell against the register-resident candidates
 #define HS_RUN(N)                                                                                                  \
   hs_ref_loop<SLOTS, (N <= NPAIR ? N : NPAIR), EXCL_MOL>(a, k, lane, pass0, hs, nhome, xr2, yr2, zr2, ux, uy, uz, accj, cntj, \
-                                                          molr, s_homeP, s_homeU, s_acc, s_cnt, s_gid)
+                                                          molr, smem_addr(s_ref), s_acc, s_cnt, s_gid)
     switch (npp) {      // npp <= NPAIR: the other cases are not instantiated
       case 0: break;    // a later chunk without survivors
       case 1: HS_RUN(1); break;

@@ -33,9 +33,14 @@ def one(chains, beads, rc):
     tot = torch.zeros(6, dtype=torch.int64, device=dev)
     p, st = engine._ptr, engine._stream()
     name = os.path.basename(os.path.dirname(os.environ.get("MOUSE_B200_LIB", "default/x")))
-    for same in (True, False):
-        for slots in (4, 6, 8):
-            flags = (_lib.MOUSE_SAME_MOLECULE if same else 0) | _lib.MOUSE_SLOTS(slots)
+    combos = [(same, slots, 0) for same in (True, False) for slots in (4, 6, 8)]
+    if os.environ.get("SWEEP_WARPS"):      # occupancy scan of the default slot count: SWEEP_WARPS=4,6,8,10
+        combos = [(True, int(os.environ.get("SWEEP_SLOTS", "6")), int(w)) for w in os.environ["SWEEP_WARPS"].split(",")]
+    if os.environ.get("SWEEP_QUICK"):
+        combos = [(True, int(s), 0) for s in os.environ["SWEEP_QUICK"].split(",")]
+    for same, slots, warps in combos:
+        if True:
+            flags = (_lib.MOUSE_SAME_MOLECULE if same else 0) | _lib.MOUSE_SLOTS(slots) | _lib.MOUSE_WARPS(warps)
             e0 = [torch.cuda.Event(enable_timing=True) for _ in range(24)]
             e1 = [torch.cuda.Event(enable_timing=True) for _ in range(24)]
             f0 = [torch.cuda.Event(enable_timing=True) for _ in range(24)]
@@ -53,8 +58,8 @@ def one(chains, beads, rc):
             ts = sorted(a.elapsed_time(b) for a, b in zip(e0[4:], e1[4:]))
             tf = sorted(a.elapsed_time(b) for a, b in zip(f0[4:], f1[4:]))
             t = tot.cpu()
-            print("%-12s same=%d slots=%d sweep median %.4f min %.4f ms | frame median %.4f ms | pairs=%d band=%d S=%.15g" % (
-                name, same, slots, ts[len(ts) // 2], ts[0], tf[len(tf) // 2], int(t[2]), int(t[5]),
+            print("%-12s same=%d slots=%d warps=%d sweep median %.4f min %.4f ms | frame median %.4f ms | pairs=%d band=%d S=%.15g" % (
+                name, same, slots, warps, ts[len(ts) // 2], ts[0], tf[len(tf) // 2], int(t[2]), int(t[5]),
                 1.5 * float(t.view(torch.float64)[0]) / max(int(t[1]), 1) - 0.5), flush=True)
 
 
