@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_canon_kernel(int ncell,
     const int s = cell_start[c], e = cell_start[c + 1];
     const int nc = e - s;
     const size_t row = items ? (size_t)cell_row[c] : 0;     // the cell's row in the item table: heaviest classes first
+    float ctr_x = 0.0f, ctr_y = 0.0f;
     if (items) {
       // the cell's item row for the half-shell sweeps (half_shell.cuh): lane L < 10 owns range L; an empty cell
       // only needs its size (the sweeps skip it)
@@ -452,15 +453,21 @@ __global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_canon_kernel(int ncell,
           const int y = __shfl_up_sync(MOUSE_FULL_MASK, incl, o);
           if (lane >= o) incl += y;
         }
-        // row layout: [0..9] src, [10..19] len, [20..29] offset, [30] size, [31] packed coordinates + boundary bit,
-        // [32..37] bounding box of the cell's items (written below)
+        // row layout: [0..9] src, [10..19] len, [20..29] offset, [30] size | boundary << 30, [31] centre z,
+        // [32..37] bounding box of the cell's items, [38..39] centre x, y (written below)
         const int src_k = __shfl_sync(MOUSE_FULL_MASK, src, lane % 10);
         const int len_k = __shfl_sync(MOUSE_FULL_MASK, len, lane % 10);
         const int off_k = __shfl_sync(MOUSE_FULL_MASK, incl - len, lane % 10);
         const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
         const int boundary = (cx == 0) | (cx == nx - 1) | (cy == 0) | (cy == ny - 1) | (cz == nz - 1);
-        val = lane < 10 ? src_k : lane < 20 ? len_k : lane < 30 ? off_k : lane == 30 ? nc
-                                                                   : (cx | (cy << 10) | (cz << 20) | (boundary << 30));
+        // cell centre along the lattice directions, then Cartesian (the tilt ratios are 0 for an orthorhombic box)
+        const float ux = ((float)cx + 0.5f) * g.cwf[0] - 0.5f * g.boxf[0];
+        const float uy = ((float)cy + 0.5f) * g.cwf[1] - 0.5f * g.boxf[1];
+        const float uz = ((float)cz + 0.5f) * g.cwf[2] - 0.5f * g.boxf[2];
+        ctr_x = ux + g.tratio[0] * uy + g.tratio[1] * uz;
+        ctr_y = uy + g.tratio[2] * uz;
+        val = lane < 10 ? src_k : lane < 20 ? len_k : lane < 30 ? off_k : lane == 30 ? (nc | (boundary << 30))
+                                                                   : __float_as_int(uz);
       }
       items[row * HS_ITEM_INTS + lane] = val;
       if (nc <= 0 && lane < 8) items[row * HS_ITEM_INTS + 32 + lane] = 0;
@@ -510,7 +517,7 @@ __global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_canon_kernel(int ncell,
       }
       if (lane < 8) {
         const float v = lane == 0 ? blo[0] : lane == 1 ? blo[1] : lane == 2 ? blo[2] : lane == 3 ? bhi[0]
-                        : lane == 4 ? bhi[1] : lane == 5 ? bhi[2] : 0.0f;
+                        : lane == 4 ? bhi[1] : lane == 5 ? bhi[2] : lane == 6 ? ctr_x : ctr_y;
         items[row * HS_ITEM_INTS + 32 + lane] = __float_as_int(v);
       }
     }

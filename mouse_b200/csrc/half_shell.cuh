@@ -98,9 +98,9 @@ __device__ __forceinline__ void hs_range_cells(const GridDev &g, int cx, int cy,
 
 // Per-cell item table (40 ints per cell, written by cell_canon_kernel, one warp per cell, read by the sweeps):
 //   [0..9] first sorted slot of range L, [10..19] its length, [20..29] its offset t in the candidate concatenation,
-//   [30] bonds / atoms in the home cell, [31] cx | cy << 10 | cz << 20 | boundary << 30,
+//   [30] bonds / atoms in the home cell | boundary << 30 (some neighbour cell is a periodic image),
 //   [32..34] / [35..37] lower / upper corner of the bounding box of the cell's own items (FP32 bit patterns, frame of
-//   the stored coordinates: wrapped - L/2), [38..39] unused.
+//   the stored coordinates: wrapped - L/2), [38], [39], [31] the cell centre x, y, z in the same frame.
 #define HS_ITEM_INTS 40
 
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
@@ -135,9 +135,10 @@ __device__ __forceinline__ bool hs_finalize(const GridDev &g, int lane, int tk, 
   const int l = lane < 10 ? lane : 0;
   const int src = s_raw[l], len = lane < 10 ? s_raw[10 + l] : 0, rt = s_raw[20 + l];
   const int T = s_raw[29] + s_raw[19];
-  const int nhome = s_raw[30], packed = s_raw[31];
+  const int size = s_raw[30];
+  const float hx = __int_as_float(s_raw[38]), hy = __int_as_float(s_raw[39]), hz = __int_as_float(s_raw[31]);
   __syncwarp();
-  const int cx = packed & 1023, cy = (packed >> 10) & 1023, cz = (packed >> 20) & 1023;
+  const int nhome = size & 0x3fffffff;
   it.home = tk;
   it.hs = __shfl_sync(MOUSE_FULL_MASK, src, 0);      // range 0 starts with the home cell
   it.nhome = nhome;
@@ -145,13 +146,9 @@ __device__ __forceinline__ bool hs_finalize(const GridDev &g, int lane, int tk, 
   it.rsrc = src;
   it.rlen = len;
   it.rt = rt;
-  // cell centre along the lattice directions, then Cartesian (the tilt ratios are 0 for an orthorhombic box)
-  const float ux = ((float)cx + 0.5f) * g.cwf[0] - 0.5f * g.boxf[0];
-  const float uy = ((float)cy + 0.5f) * g.cwf[1] - 0.5f * g.boxf[1];
-  const float uz = ((float)cz + 0.5f) * g.cwf[2] - 0.5f * g.boxf[2];
-  it.hx = ux + g.tratio[0] * uy + g.tratio[1] * uz;
-  it.hy = uy + g.tratio[2] * uz;
-  it.hz = uz;
-  it.boundary = (packed >> 30) & 1;
+  it.hx = hx;          // cell centre, Cartesian, frame of the stored coordinates (written by the canon kernel)
+  it.hy = hy;
+  it.hz = hz;
+  it.boundary = (size >> 30) & 1;
   return nhome > 0;
 }

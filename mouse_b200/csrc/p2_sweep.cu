@@ -167,14 +167,15 @@ struct HsConst {
   float nearz_thr;
 };
 
-// One reference of the current window as the loop reads it (64 bytes, four 128-bit broadcast loads): the negated FP32
-// coordinates duplicated for the packed f32x2 subtraction, the molecule code and the FP64 unit vector.
+// One reference of the current window as the loop reads it (48 bytes, three 128-bit broadcast loads): the negated FP32
+// coordinates duplicated for the packed f32x2 subtraction and the FP64 unit vector (the molecule codes live in s_mol).
 struct __align__(16) HsRef {
   float4 a;    // -x, -x, -y, -y
-  float4 b;    // -z, -z, molecule code bits, unused
+  float2 b;    // -z, -z
+  double uz;
   double2 u;   // ux, uy
-  double2 v;   // uz, unused
 };
+#define HS_REF_BYTES 48u
 
 __device__ __forceinline__ unsigned hs_umin3(unsigned a, unsigned b, unsigned c) { return __vimin3_u32(a, b, c); }
 
@@ -222,7 +223,7 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
                                             const pk2 (&yr2)[SLOTS / 2], const pk2 (&zr2)[SLOTS / 2],
                                             const double (&ux)[SLOTS], const double (&uy)[SLOTS],
                                             const double (&uz)[SLOTS], double (&accj)[SLOTS], int (&cntj)[SLOTS],
-                                            const int (&molr)[SLOTS], const uint32_t s_ref, double (*s_acc)[33],
+                                            const int (&molr)[SLOTS], const uint32_t s_ref, const int *s_mol, double (*s_acc)[33],
                                             int (*s_cnt)[33], const int (*s_gid)[32]) {
   static_assert(HS_GRP == 8 || HS_GRP == 4, "reference groups of 4 or 8");
   static_assert(HS_MAXHOME % 2 == 0, "references are processed two at a time");
@@ -241,22 +242,24 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
     unsigned rare = 0u;
     // two references per iteration: two independent dependency chains per warp.  The second one of an odd
     // tail is the sentinel record behind the window (far away: no hits, never in the band)
-    uint32_t rp = s_ref + 64u * (uint32_t)base;
+    uint32_t rp = s_ref + HS_REF_BYTES * (uint32_t)base;
     uint32_t ap = smem_addr(&s_acc[0][lane]), cp = smem_addr(&s_cnt[0][lane]);
 #pragma unroll 1
-    for (int r = 0; r < nref; r += 2, rp += 128u, ap += 2u * 33u * 8u, cp += 2u * 33u * 4u) {
+    for (int r = 0; r < nref; r += 2, rp += 2u * HS_REF_BYTES, ap += 2u * 33u * 8u, cp += 2u * 33u * 4u) {
       const int il = base + r;
-      pk2 nax, nay, naz, nbx, nby, nbz, mola2, molb2;
+      pk2 nax, nay, naz, nbx, nby, nbz, uaz2, ubz2;
       lds_pk2x2(rp, nax, nay);
-      lds_pk2x2(rp + 16u, naz, mola2);
-      lds_pk2x2(rp + 64u, nbx, nby);
-      lds_pk2x2(rp + 80u, nbz, molb2);
-      const double2 ua = lds_double2(rp + 32u), va = lds_double2(rp + 48u);
-      const double2 ub = lds_double2(rp + 96u), vb = lds_double2(rp + 112u);
-      const double uax = ua.x, uay = ua.y, uaz = va.x, ubx = ub.x, uby = ub.y, ubz = vb.x;
-      int mola, molb, unused;
-      pk2_bits(mola2, mola, unused);
-      pk2_bits(molb2, molb, unused);
+      lds_pk2x2(rp + 16u, naz, uaz2);
+      lds_pk2x2(rp + HS_REF_BYTES, nbx, nby);
+      lds_pk2x2(rp + HS_REF_BYTES + 16u, nbz, ubz2);
+      const double2 ua = lds_double2(rp + 32u), ub = lds_double2(rp + HS_REF_BYTES + 32u);
+      const double uax = ua.x, uay = ua.y, uaz = __longlong_as_double((long long)uaz2);
+      const double ubx = ub.x, uby = ub.y, ubz = __longlong_as_double((long long)ubz2);
+      int mola = 0, molb = 0;
+      if (EXCL_MOL) {
+        mola = s_mol[il];
+        molb = s_mol[il + 1];
+      }
       double acca0 = 0.0, acca1 = 0.0, accb0 = 0.0, accb1 = 0.0;
       int cnta = 0, cntb = 0;
       unsigned banda = 0xffffffffu, bandb = 0xffffffffu;
@@ -325,11 +328,15 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
       const int r = __ffs(rare) - 1;
       rare &= rare - 1;
       const int il = base + r;
-      const uint32_t rq = s_ref + 64u * (uint32_t)il;
-      const float4 ria = lds_float4(rq), rib = lds_float4(rq + 16u);
-      const double2 ui = lds_double2(rq + 32u), vi = lds_double2(rq + 48u);
-      const double uix = ui.x, uiy = ui.y, uiz = vi.x;
-      const int moli = __float_as_int(rib.z);
+      const uint32_t rq = s_ref + HS_REF_BYTES * (uint32_t)il;
+      const float4 ria = lds_float4(rq);
+      pk2 riz2, uiz2;
+      lds_pk2x2(rq + 16u, riz2, uiz2);
+      float riz, riz_dup;
+      pk2_floats(riz2, riz, riz_dup);
+      const double2 ui = lds_double2(rq + 32u);
+      const double uix = ui.x, uiy = ui.y, uiz = __longlong_as_double((long long)uiz2);
+      const int moli = EXCL_MOL ? s_mol[il] : 0;
       const int il_eff = pass0 ? il : -1;
 #pragma unroll
       for (int c = 0; c < 2 * NPP; ++c) {
@@ -343,7 +350,7 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
           pk2_floats(yr2[c >> 1], py0, py1);
           pk2_floats(zr2[c >> 1], pz0, pz1);
           const float px = (c & 1) ? px1 : px0, py = (c & 1) ? py1 : py0, pz = (c & 1) ? pz1 : pz0;
-          const float dx = __fadd_rn(px, ria.x), dy = __fadd_rn(py, ria.z), dz = __fadd_rn(pz, rib.x);
+          const float dx = __fadd_rn(px, ria.x), dy = __fadd_rn(py, ria.z), dz = __fadd_rn(pz, riz);
           const float t = __fadd_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))), k.nlo);
           if (__float_as_uint(t) <= k.band_bits) {
             fix_append(a.counters, a.fix_list, a.fix_cap, hs + il, g, 0);          // undecided: nothing was added
@@ -432,6 +439,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
   __shared__ uint16_t s_sel[LZ + NC];               // byte offset in the landing zone of the candidates that survived
                                                     // the cull, then NC times the filler
   __shared__ HsRef s_ref[HS_MAXHOME + 2];           // the references of this window (+ the far-away sentinel)
+  __shared__ int s_mol[EXCL_MOL ? HS_MAXHOME + 2 : 1];   // their molecule codes (only read when pairs inside a molecule are excluded)
   __shared__ double s_acc[HS_GRP][33];              // per-lane partial sums of 8 references (transposed reduce)
   __shared__ int s_cnt[HS_GRP][33];                 // ... and partial counts
   __shared__ int s_gid[SLOTS][32];                  // sorted slot of every register-resident candidate (-1: empty)
@@ -570,10 +578,11 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
           if (c < HSL && pass0 && 32 * c + lane < nhome) {   // survivors [0, nhome) of the cell are its own bonds, in order
             HsRef rr;
             rr.a = make_float4(-p[h].x, -p[h].x, -p[h].y, -p[h].y);
-            rr.b = make_float4(-p[h].z, -p[h].z, p[h].w, 0.0f);
+            rr.b = make_float2(-p[h].z, -p[h].z);
+            rr.uz = u2w.x;
             rr.u = u01;
-            rr.v = make_double2(u2w.x, 0.0);
             s_ref[32 * c + lane] = rr;
+            if (EXCL_MOL) s_mol[32 * c + lane] = __float_as_int(p[h].w);
           }
         }
         // (the packed add of -0.0 makes each pair the RESULT of an instruction: the compiler then keeps the pair in
@@ -586,10 +595,11 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
       if (pass0 && lane == 0) {      // sentinel behind the window: the partner of the last reference of an odd tail
         HsRef rr;
         rr.a = make_float4(HS_PAD, HS_PAD, HS_PAD, HS_PAD);       // at -HS_PAD: far from the bonds AND from the filler
-        rr.b = make_float4(HS_PAD, HS_PAD, __int_as_float(-1), 0.0f);
+        rr.b = make_float2(HS_PAD, HS_PAD);
+        rr.uz = 0.0;
         rr.u = make_double2(1.0, 0.0);
-        rr.v = make_double2(0.0, 0.0);
         s_ref[nhome] = rr;
+        if (EXCL_MOL) s_mol[nhome] = -1;
       }
     }
     __syncwarp();
@@ -625,7 +635,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     // ---- the references of the home cell against the register-resident candidates
 #define HS_RUN(N)                                                                                                  \
   hs_ref_loop<SLOTS, (N <= NPAIR ? N : NPAIR), EXCL_MOL>(a, k, lane, pass0, hs, nhome, xr2, yr2, zr2, ux, uy, uz, accj, cntj, \
-                                                          molr, smem_addr(s_ref), s_acc, s_cnt, s_gid)
+                                                          molr, smem_addr(s_ref), s_mol, s_acc, s_cnt, s_gid)
     switch (npp) {      // npp <= NPAIR: the other cases are not instantiated
       case 0: break;    // a later chunk without survivors
       case 1: HS_RUN(1); break;
@@ -638,11 +648,9 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
 #undef HS_RUN
     // ---- candidate side: one pair of integer atomics per candidate that was hit
 #pragma unroll
-    for (int c = 0; c < SLOTS; ++c) {
-      if (c < 2 * npp) {
-        const int g = s_gid[c][lane];
-        hs_flush(a.acc_fix, a.acc_cnt, g < 0 ? 0 : g, accj[c], cntj[c]);
-      }
+    for (int c = 0; c < SLOTS; ++c) {      // (slots that were not in use and fillers have a zero count: predicated off)
+      const int g = s_gid[c][lane];
+      hs_flush(a.acc_fix, a.acc_cnt, g < 0 ? 0 : g, accj[c], cntj[c]);
     }
     if (!last) {
       sp += 1;
