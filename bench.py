@@ -43,7 +43,7 @@ W_LANE_INSTR_PER_PAIR = 55.2      # 6.45 x 7 FP32 + 10 FP64 la
 W5_LANE_INSTR_PER_PAIR = 60.2     # K5: 6.45 x 7 FP32 filter + 15 per counted pair (FP64 d^2, bin, count)
 BYTES_PER_BOND = 72.0             # compulsory HBM bytes per bond per frame
 N_FRAME_VARIANTS = 4              # distinct frames cycled (working set per frame ~210 MB > 126 MB L2)
-LANES = 3                         # frames in flight in the device-resident timed region (own stream + workspace each)
+LANES = int(os.environ.get("MOUSE_BENCH_LANES", "3"))                         # frames in flight in the device-resident timed region (own stream + workspace each)
 KERNELS_PER_FRAME = 8             # bond_assign, scan, scatter_idx, canon, sweep, fixup, exact check, finish+reduce
 
 
@@ -343,7 +343,7 @@ class P2Bench:
         self.n = int(self.bonds.shape[0])
         self.L = _lib.lib()
         self.grid = _lib.grid_plan(box, rcut, self.n, tilt=tilt)
-        self.flags = _lib.MOUSE_SAME_MOLECULE if same_molecule else 0
+        self.flags = (_lib.MOUSE_SAME_MOLECULE if same_molecule else 0) | int(os.environ.get("MOUSE_BENCH_FLAGS", "0"), 0)
         nbytes = self.L.mouse_workspace_bytes(self.n, C.byref(self.grid))
         n = self.n
         self.lanes = []

@@ -47,7 +47,6 @@ struct SweepArgs {
   int64_t list_cap;        // lists only: entries of nbr_idx the caller allocated
   int2 *fix_list;          // pairs of sorted slots left to p2_fixup_kernel: x = i | kind << 31, y = j
   long long fix_cap;
-  int only_if_overflow;    // exact kernel: run only when the pair list overflowed
   long long *acc_fix;      // [n] per sorted slot: sum of cos^2 as 2^-47 fixed point
   int32_t *acc_cnt;        // [n] per sorted slot: counted neighbours
   int same_molecule;
@@ -215,11 +214,125 @@ __device__ __forceinline__ void hs_acc_if(double &accj, double &acci, double d, 
       : "d"(d), "r"(m));
 }
 
-// The references of one home cell against NPP register-resident slot pairs (specialised on NPP: no guards inside the
-// reference loop, the slot pairs interleave freely).
-template <int SLOTS, int NPP, bool EXCL_MOL>
+// One group of references (nref <= HS_GRP, two per iteration) against NS register-resident slots = NPP slot pairs
+// (specialised on NS: no guards inside the loop, the slot pairs interleave freely; with an odd NS the FP64 work of the
+// last pair's empty second slot is left out).  Returns the rare mask: two bits per pair of references.  Only this loop
+// is instantiated per slot count - the code around it exists once (the kernel's instruction footprint matters: with
+// every slot count inlining its own copy of the rare path and of the reduction the kernel ran 20 % slower).
+template <int SLOTS, int NS, bool EXCL_MOL>
+__device__ __forceinline__ unsigned hs_ref_pairs(const HsConst k, const int lane, const int base, const int nref,
+                                                 const int (&jl)[HS_MAXHOME / 32], const pk2 (&xr2)[SLOTS / 2],
+                                                 const pk2 (&yr2)[SLOTS / 2], const pk2 (&zr2)[SLOTS / 2],
+                                                 const double (&ux)[SLOTS], const double (&uy)[SLOTS],
+                                                 const double (&uz)[SLOTS], double (&accj)[SLOTS], int (&cntj)[SLOTS],
+                                                 const int (&molr)[SLOTS], const uint32_t s_ref, const int *s_mol,
+                                                 double (*s_acc)[33], int (*s_cnt)[33]) {
+  constexpr int NPP = (NS + 1) / 2;
+  constexpr int HSL = HS_MAXHOME / 32;   // slots of pass 0 that may hold home-cell bonds
+  const pk2 nlo = pk2_make(k.nlo, k.nlo);
+  unsigned rare = 0u;
+  // two references per iteration: two independent dependency chains per warp.  The second one of an odd
+  // tail is the sentinel record behind the window (far away: no hits, never in the band)
+  uint32_t rp = s_ref + HS_REF_BYTES * (uint32_t)base;
+  uint32_t ap = smem_addr(&s_acc[0][lane]), cp = smem_addr(&s_cnt[0][lane]);
+#pragma unroll 1
+  for (int r = 0; r < nref; r += 2, rp += 2u * HS_REF_BYTES, ap += 2u * 33u * 8u, cp += 2u * 33u * 4u) {
+    const int il = base + r;
+    pk2 nax, nay, naz, nbx, nby, nbz, uaz2, ubz2;
+    lds_pk2x2(rp, nax, nay);
+    lds_pk2x2(rp + 16u, naz, uaz2);
+    lds_pk2x2(rp + HS_REF_BYTES, nbx, nby);
+    lds_pk2x2(rp + HS_REF_BYTES + 16u, nbz, ubz2);
+    const double2 ua = lds_double2(rp + 32u), ub = lds_double2(rp + HS_REF_BYTES + 32u);
+    const double uax = ua.x, uay = ua.y, uaz = __longlong_as_double((long long)uaz2);
+    const double ubx = ub.x, uby = ub.y, ubz = __longlong_as_double((long long)ubz2);
+    int mola = 0, molb = 0;
+    if (EXCL_MOL) {
+      mola = s_mol[il];
+      molb = s_mol[il + 1];
+    }
+    double acca0 = 0.0, acca1 = 0.0, accb0 = 0.0, accb1 = 0.0;
+    int cnta = 0, cntb = 0;
+    unsigned banda = 0xffffffffu, bandb = 0xffffffffu;
+    float nza = 3.0e38f, nzb = 3.0e38f;
+#pragma unroll
+    for (int pp = 0; pp < NPP; ++pp) {
+      const pk2 dxa = pk2_add(xr2[pp], nax), dya = pk2_add(yr2[pp], nay), dza = pk2_add(zr2[pp], naz);
+      const pk2 dxb = pk2_add(xr2[pp], nbx), dyb = pk2_add(yr2[pp], nby), dzb = pk2_add(zr2[pp], nbz);
+      const pk2 ta = pk2_add(pk2_fma(dza, dza, pk2_fma(dya, dya, pk2_mul(dxa, dxa))), nlo);   // d2 - rc2_lo
+      const pk2 tb = pk2_add(pk2_fma(dzb, dzb, pk2_fma(dyb, dyb, pk2_mul(dxb, dxb))), nlo);
+      int ta0, ta1, tb0, tb1;
+      pk2_bits(ta, ta0, ta1);
+      pk2_bits(tb, tb0, tb1);
+      // smallest non-negative t (negative values are huge as unsigned): in the guard band if <= its width
+      banda = hs_umin3(banda, (unsigned)ta0, (unsigned)ta1);
+      bandb = hs_umin3(bandb, (unsigned)tb0, (unsigned)tb1);
+      const bool two = 2 * pp + 1 < NS;     // (compile time) the pair's second slot is in use
+      const double da0 = fma(uax, ux[2 * pp], fma(uay, uy[2 * pp], uaz * uz[2 * pp]));
+      const double db0 = fma(ubx, ux[2 * pp], fma(uby, uy[2 * pp], ubz * uz[2 * pp]));
+      // Branch-free: the hit mask is the sign of t spread over the word (combined with the home-cell j > i rule and
+      // the molecule test); the weight w is d with its high word cleared on a miss (|w| < 1e-300, w * w vanishes in
+      // the sums), so the FP64 FMAs are unconditional, and the counts subtract the masks
+      int ma0 = ta0 >> 31, mb0 = tb0 >> 31;
+      if (2 * pp < HSL) {
+        ma0 &= (il - jl[2 * pp]) >> 31;
+        mb0 &= (il + 1 - jl[2 * pp]) >> 31;
+      }
+      if (EXCL_MOL) {
+        ma0 &= molr[2 * pp] != mola ? -1 : 0;
+        mb0 &= molr[2 * pp] != molb ? -1 : 0;
+      }
+      const double wa0 = __hiloint2double(__double2hiint(da0) & ma0, __double2loint(da0));
+      const double wb0 = __hiloint2double(__double2hiint(db0) & mb0, __double2loint(db0));
+      accj[2 * pp] = fma(wb0, wb0, fma(wa0, wa0, accj[2 * pp]));
+      acca0 = fma(wa0, wa0, acca0);
+      accb0 = fma(wb0, wb0, accb0);
+      cntj[2 * pp] = cntj[2 * pp] - ma0 - mb0;
+      if (two) {
+        const double da1 = fma(uax, ux[2 * pp + 1], fma(uay, uy[2 * pp + 1], uaz * uz[2 * pp + 1]));
+        const double db1 = fma(ubx, ux[2 * pp + 1], fma(uby, uy[2 * pp + 1], ubz * uz[2 * pp + 1]));
+        // smallest |d| over ALL slots (as the high word, compared as a float): a false alarm only costs time
+        nza = fminf(nza, fminf(fabsf(__int_as_float(__double2hiint(da0))), fabsf(__int_as_float(__double2hiint(da1)))));
+        nzb = fminf(nzb, fminf(fabsf(__int_as_float(__double2hiint(db0))), fabsf(__int_as_float(__double2hiint(db1)))));
+        int ma1 = ta1 >> 31, mb1 = tb1 >> 31;
+        if (2 * pp + 1 < HSL) {
+          ma1 &= (il - jl[2 * pp + 1]) >> 31;
+          mb1 &= (il + 1 - jl[2 * pp + 1]) >> 31;
+        }
+        if (EXCL_MOL) {
+          ma1 &= molr[2 * pp + 1] != mola ? -1 : 0;
+          mb1 &= molr[2 * pp + 1] != molb ? -1 : 0;
+        }
+        const double wa1 = __hiloint2double(__double2hiint(da1) & ma1, __double2loint(da1));
+        const double wb1 = __hiloint2double(__double2hiint(db1) & mb1, __double2loint(db1));
+        accj[2 * pp + 1] = fma(wb1, wb1, fma(wa1, wa1, accj[2 * pp + 1]));
+        acca1 = fma(wa1, wa1, acca1);
+        accb1 = fma(wb1, wb1, accb1);
+        cntj[2 * pp + 1] = cntj[2 * pp + 1] - ma1 - mb1;
+        cnta = cnta - ma0 - ma1;
+        cntb = cntb - mb0 - mb1;
+      } else {
+        nza = fminf(nza, fabsf(__int_as_float(__double2hiint(da0))));
+        nzb = fminf(nzb, fabsf(__int_as_float(__double2hiint(db0))));
+        cnta -= ma0;
+        cntb -= mb0;
+      }
+    }
+    // either reference of the pair has a candidate in the band or a near-zero dot: both are re-tested below
+    if ((min(banda, bandb) <= k.band_bits) | (fminf(nza, nzb) <= k.nearz_thr)) rare |= 3u << r;
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(ap), "d"(acca0 + acca1) : "memory");
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(ap + 33u * 8u), "d"(accb0 + accb1) : "memory");
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(cp), "r"(cnta) : "memory");
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(cp + 33u * 4u), "r"(cntb) : "memory");
+  }
+  return rare;
+}
+
+// The references of one home cell (window) against the register-resident candidates: groups of HS_GRP references
+// through hs_ref_pairs, then - once per group - the rare path and the reduction of the reference-side partials.
+template <int SLOTS, bool EXCL_MOL>
 __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k, const int lane, const bool pass0,
-                                            const int hs, const int nhome, const pk2 (&xr2)[SLOTS / 2],
+                                            const int ns, const int hs, const int nhome, const pk2 (&xr2)[SLOTS / 2],
                                             const pk2 (&yr2)[SLOTS / 2], const pk2 (&zr2)[SLOTS / 2],
                                             const double (&ux)[SLOTS], const double (&uy)[SLOTS],
                                             const double (&uz)[SLOTS], double (&accj)[SLOTS], int (&cntj)[SLOTS],
@@ -228,7 +341,6 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
   static_assert(HS_GRP == 8 || HS_GRP == 4, "reference groups of 4 or 8");
   static_assert(HS_MAXHOME % 2 == 0, "references are processed two at a time");
   constexpr int HSL = HS_MAXHOME / 32;   // slots of pass 0 that may hold home-cell bonds
-  const pk2 nlo = pk2_make(k.nlo, k.nlo);
   // home-home pairs are decided once: candidate t = 32 c + lane of pass 0 counts for reference il only if t > il.
   // (il - t) >> 31 is the all-ones mask of that rule; jl[c] = t (pass 0) or a large number (every il passes)
   int jl[HSL];
@@ -239,89 +351,25 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
   // stored while reference il + 1 is computed, so no iteration ends by draining its own FP64 chain.
   for (int base = 0; base < nhome; base += HS_GRP) {
     const int nref = min(HS_GRP, nhome - base);
-    unsigned rare = 0u;
-    // two references per iteration: two independent dependency chains per warp.  The second one of an odd
-    // tail is the sentinel record behind the window (far away: no hits, never in the band)
-    uint32_t rp = s_ref + HS_REF_BYTES * (uint32_t)base;
-    uint32_t ap = smem_addr(&s_acc[0][lane]), cp = smem_addr(&s_cnt[0][lane]);
-#pragma unroll 1
-    for (int r = 0; r < nref; r += 2, rp += 2u * HS_REF_BYTES, ap += 2u * 33u * 8u, cp += 2u * 33u * 4u) {
-      const int il = base + r;
-      pk2 nax, nay, naz, nbx, nby, nbz, uaz2, ubz2;
-      lds_pk2x2(rp, nax, nay);
-      lds_pk2x2(rp + 16u, naz, uaz2);
-      lds_pk2x2(rp + HS_REF_BYTES, nbx, nby);
-      lds_pk2x2(rp + HS_REF_BYTES + 16u, nbz, ubz2);
-      const double2 ua = lds_double2(rp + 32u), ub = lds_double2(rp + HS_REF_BYTES + 32u);
-      const double uax = ua.x, uay = ua.y, uaz = __longlong_as_double((long long)uaz2);
-      const double ubx = ub.x, uby = ub.y, ubz = __longlong_as_double((long long)ubz2);
-      int mola = 0, molb = 0;
-      if (EXCL_MOL) {
-        mola = s_mol[il];
-        molb = s_mol[il + 1];
-      }
-      double acca0 = 0.0, acca1 = 0.0, accb0 = 0.0, accb1 = 0.0;
-      int cnta = 0, cntb = 0;
-      unsigned banda = 0xffffffffu, bandb = 0xffffffffu;
-      float nza = 3.0e38f, nzb = 3.0e38f;
-#pragma unroll
-      for (int pp = 0; pp < NPP; ++pp) {
-        const pk2 dxa = pk2_add(xr2[pp], nax), dya = pk2_add(yr2[pp], nay), dza = pk2_add(zr2[pp], naz);
-        const pk2 dxb = pk2_add(xr2[pp], nbx), dyb = pk2_add(yr2[pp], nby), dzb = pk2_add(zr2[pp], nbz);
-        const pk2 ta = pk2_add(pk2_fma(dza, dza, pk2_fma(dya, dya, pk2_mul(dxa, dxa))), nlo);   // d2 - rc2_lo
-        const pk2 tb = pk2_add(pk2_fma(dzb, dzb, pk2_fma(dyb, dyb, pk2_mul(dxb, dxb))), nlo);
-        int ta0, ta1, tb0, tb1;
-        pk2_bits(ta, ta0, ta1);
-        pk2_bits(tb, tb0, tb1);
-        // smallest non-negative t (negative values are huge as unsigned): in the guard band if <= its width
-        banda = hs_umin3(banda, (unsigned)ta0, (unsigned)ta1);
-        bandb = hs_umin3(bandb, (unsigned)tb0, (unsigned)tb1);
-        const double da0 = fma(uax, ux[2 * pp], fma(uay, uy[2 * pp], uaz * uz[2 * pp]));
-        const double da1 = fma(uax, ux[2 * pp + 1], fma(uay, uy[2 * pp + 1], uaz * uz[2 * pp + 1]));
-        const double db0 = fma(ubx, ux[2 * pp], fma(uby, uy[2 * pp], ubz * uz[2 * pp]));
-        const double db1 = fma(ubx, ux[2 * pp + 1], fma(uby, uy[2 * pp + 1], ubz * uz[2 * pp + 1]));
-        // smallest |d| over ALL slots (as the high word, compared as a float): a false alarm only costs time
-        nza = fminf(nza, fminf(fabsf(__int_as_float(__double2hiint(da0))), fabsf(__int_as_float(__double2hiint(da1)))));
-        nzb = fminf(nzb, fminf(fabsf(__int_as_float(__double2hiint(db0))), fabsf(__int_as_float(__double2hiint(db1)))));
-        // Branch-free: the hit mask is the sign of t spread over the word (combined with the home-cell j > i rule and
-        // the molecule test); it predicates the FP64 accumulation and is subtracted from the counts
-        int ma0 = ta0 >> 31, ma1 = ta1 >> 31, mb0 = tb0 >> 31, mb1 = tb1 >> 31;
-        if (2 * pp < HSL) {
-          ma0 &= (il - jl[2 * pp]) >> 31;
-          mb0 &= (il + 1 - jl[2 * pp]) >> 31;
-        }
-        if (2 * pp + 1 < HSL) {
-          ma1 &= (il - jl[2 * pp + 1]) >> 31;
-          mb1 &= (il + 1 - jl[2 * pp + 1]) >> 31;
-        }
-        if (EXCL_MOL) {
-          ma0 &= molr[2 * pp] != mola ? -1 : 0;
-          ma1 &= molr[2 * pp + 1] != mola ? -1 : 0;
-          mb0 &= molr[2 * pp] != molb ? -1 : 0;
-          mb1 &= molr[2 * pp + 1] != molb ? -1 : 0;
-        }
-        const double wa0 = __hiloint2double(__double2hiint(da0) & ma0, __double2loint(da0));
-        const double wa1 = __hiloint2double(__double2hiint(da1) & ma1, __double2loint(da1));
-        const double wb0 = __hiloint2double(__double2hiint(db0) & mb0, __double2loint(db0));
-        const double wb1 = __hiloint2double(__double2hiint(db1) & mb1, __double2loint(db1));
-        accj[2 * pp] = fma(wb0, wb0, fma(wa0, wa0, accj[2 * pp]));
-        accj[2 * pp + 1] = fma(wb1, wb1, fma(wa1, wa1, accj[2 * pp + 1]));
-        acca0 = fma(wa0, wa0, acca0);
-        acca1 = fma(wa1, wa1, acca1);
-        accb0 = fma(wb0, wb0, accb0);
-        accb1 = fma(wb1, wb1, accb1);
-        cntj[2 * pp] = cntj[2 * pp] - ma0 - mb0;
-        cntj[2 * pp + 1] = cntj[2 * pp + 1] - ma1 - mb1;
-        cnta = cnta - ma0 - ma1;
-        cntb = cntb - mb0 - mb1;
-      }
-      // either reference of the pair has a candidate in the band or a near-zero dot: both are re-tested below
-      if ((min(banda, bandb) <= k.band_bits) | (fminf(nza, nzb) <= k.nearz_thr)) rare |= 3u << r;
-      asm volatile("st.shared.f64 [%0], %1;" ::"r"(ap), "d"(acca0 + acca1) : "memory");
-      asm volatile("st.shared.f64 [%0], %1;" ::"r"(ap + 33u * 8u), "d"(accb0 + accb1) : "memory");
-      asm volatile("st.shared.s32 [%0], %1;" ::"r"(cp), "r"(cnta) : "memory");
-      asm volatile("st.shared.s32 [%0], %1;" ::"r"(cp + 33u * 4u), "r"(cntb) : "memory");
+    unsigned rare;
+#define HS_PAIRS(N)                                                                                                   \
+  rare = hs_ref_pairs<SLOTS, (N <= SLOTS ? N : SLOTS), EXCL_MOL>(k, lane, base, nref, jl, xr2, yr2, zr2, ux, uy, uz, accj, cntj, \
+                                                                  molr, s_ref, s_mol, s_acc, s_cnt)
+#ifdef HS_EVEN_ONLY
+    switch ((ns + 1) & ~1) {
+#else
+    switch (ns) {      // slots in use (1 <= ns <= SLOTS: the other cases are not instantiated)
+#endif
+      case 1: HS_PAIRS(1); break;
+      case 2: HS_PAIRS(2); break;
+      case 3: if constexpr (SLOTS >= 3) HS_PAIRS(3); break;
+      case 4: if constexpr (SLOTS >= 4) HS_PAIRS(4); break;
+      case 5: if constexpr (SLOTS >= 5) HS_PAIRS(5); break;
+      case 6: if constexpr (SLOTS >= 6) HS_PAIRS(6); break;
+      case 7: if constexpr (SLOTS >= 7) HS_PAIRS(7); break;
+      default: if constexpr (SLOTS >= 8) HS_PAIRS(8); break;
     }
+#undef HS_PAIRS
     rare &= (1u << nref) - 1u;     // the sentinel of an odd tail is not a reference
     // ---- rare: candidates inside the guard band / near-zero dots are handed to p2_fixup_kernel
     while (rare) {
@@ -339,8 +387,8 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
       const int moli = EXCL_MOL ? s_mol[il] : 0;
       const int il_eff = pass0 ? il : -1;
 #pragma unroll
-      for (int c = 0; c < 2 * NPP; ++c) {
-        const int g = s_gid[c][lane];
+      for (int c = 0; c < SLOTS; ++c) {
+        const int g = c < ns ? s_gid[c][lane] : -1;
         bool pc = g >= 0;
         if (c < HSL) pc = pc && 32 * c + lane > il_eff;
         if (EXCL_MOL) pc = pc && molr[c] != moli;
@@ -633,19 +681,9 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     }
 
     // ---- the references of the home cell against the register-resident candidates
-#define HS_RUN(N)                                                                                                  \
-  hs_ref_loop<SLOTS, (N <= NPAIR ? N : NPAIR), EXCL_MOL>(a, k, lane, pass0, hs, nhome, xr2, yr2, zr2, ux, uy, uz, accj, cntj, \
-                                                          molr, smem_addr(s_ref), s_mol, s_acc, s_cnt, s_gid)
-    switch (npp) {      // npp <= NPAIR: the other cases are not instantiated
-      case 0: break;    // a later chunk without survivors
-      case 1: HS_RUN(1); break;
-      case 2: if constexpr (NPAIR >= 2) HS_RUN(2); break;
-      case 3: if constexpr (NPAIR >= 3) HS_RUN(3); break;
-      case 4: if constexpr (NPAIR >= 4) HS_RUN(4); break;
-      case 5: if constexpr (NPAIR >= 5) HS_RUN(5); break;
-      default: if constexpr (NPAIR >= 6) HS_RUN(6); break;
-    }
-#undef HS_RUN
+    if (nvalid > 0)      // (a later chunk may have no survivors)
+      hs_ref_loop<SLOTS, EXCL_MOL>(a, k, lane, pass0, (nvalid + 31) >> 5, hs, nhome, xr2, yr2, zr2, ux, uy, uz, accj, cntj, molr,
+                                   smem_addr(s_ref), s_mol, s_acc, s_cnt, s_gid);
     // ---- candidate side: one pair of integer atomics per candidate that was hit
 #pragma unroll
     for (int c = 0; c < SLOTS; ++c) {      // (slots that were not in use and fillers have a zero count: predicated off)
@@ -675,62 +713,9 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
   }
 }
 
-// Exact decision of the listed pairs (one thread per pair): kind 0 = nothing was added by the fast sweep, add the
-// reference's cos^2 to both partners if the pair is counted; kind 1 = added as a hit with a near-zero dot product,
-// remove it from both counts if the reference's cos^2 is exactly 0.0 (masked, :113).
-__global__ void __launch_bounds__(256) p2_fixup_kernel(const SweepArgs a) {
-  if (((volatile int64_t *)a.counters)[C_OVERFLOW]) return;
-  const long long nfix = ((volatile int64_t *)a.counters)[C_NFIX];
-  const size_t n = (size_t)a.n;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nfix; e += (long long)gridDim.x * blockDim.x) {
-    const int2 pr = a.fix_list[e];
-    const int si = pr.x & 0x7fffffff, sj = pr.y, kind = (unsigned)pr.x >> 31;
-    const double cs = exact_pair(a.idx, a.ctr, a.vec, n, a.g, si, sj);
-    if (kind == 0) {
-      if (cs != 0.0) {
-        const unsigned long long f = (unsigned long long)__double2ll_rn(cs * HS_FIX_SCALE);
-        atomicAdd((unsigned long long *)&a.acc_fix[si], f);
-        atomicAdd((unsigned long long *)&a.acc_fix[sj], f);
-        atomicAdd(&a.acc_cnt[si], 1);
-        atomicAdd(&a.acc_cnt[sj], 1);
-      }
-    } else if (cs == 0.0) {
-      atomicAdd(&a.acc_cnt[si], -1);
-      atomicAdd(&a.acc_cnt[sj], -1);
-    }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.counters[C_NFIX_DONE] = nfix;
-}
-
-// accumulators (sorted slots, fixed point) -> out_sum / out_cnt (original bond order).  The accumulators are
-// handed back zeroed: the cell build zeroes them once, every sweep leaves them as it found them.
-__global__ void __launch_bounds__(256) p2_finish_kernel(const SweepArgs a) {
-  const bool overflow = ((volatile int64_t *)a.counters)[C_OVERFLOW] != 0;   // the exact sweep writes the outputs
-  const int n_list = a.cell_start[a.g.ncell];
-  const long long nzero = a.counters[C_NZERO];
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_list; s += gridDim.x * blockDim.x) {
-    const long long fix = a.acc_fix[s];
-    int cnt = a.acc_cnt[s];
-    a.acc_fix[s] = 0;
-    a.acc_cnt[s] = 0;
-    if (overflow || !(a.flag[s] & 1)) continue;     // not a reference: out stays 0 / 0
-    const int o = a.idx[s];
-    double sum = (double)fix * HS_FIX_INV;
-    // zero-length bonds in the neighbour set turn every mean into NaN and add to every count
-    // (0/0 in ordering_functions.py:112, SURVEY.md 8(a) a4)
-    if (nzero) {
-      sum = __longlong_as_double(0x7ff8000000000000LL);
-      cnt += (int)nzero;
-    }
-    a.out_sum[o] = sum;
-    a.out_cnt[o] = cnt;
-  }
-}
-
 // ------------------------------------------------------------------ exact all-FP64 sweep
 template <bool LISTS>
-__global__ void __launch_bounds__(128) p2_sweep_exact_kernel(const SweepArgs a) {
-  if (a.only_if_overflow && !((volatile int64_t *)a.counters)[C_OVERFLOW]) return;
+__device__ __forceinline__ void p2_sweep_exact_body(const SweepArgs &a) {
   const int n_list = a.cell_start[a.g.ncell];
   const size_t n = (size_t)a.n;
   const int nx = a.g.nc[0], ny = a.g.nc[1], nz = a.g.nc[2];
@@ -788,6 +773,70 @@ __global__ void __launch_bounds__(128) p2_sweep_exact_kernel(const SweepArgs a) 
       a.out_sum[bi] = sum;
       a.out_cnt[bi] = cnt;
     }
+  }
+}
+
+template <bool LISTS>
+__global__ void __launch_bounds__(128) p2_sweep_exact_kernel(const SweepArgs a) {
+  p2_sweep_exact_body<LISTS>(a);
+}
+
+// Exact decision of the listed pairs (one thread per pair): kind 0 = nothing was added by the fast sweep, add the
+// reference's cos^2 to both partners if the pair is counted; kind 1 = added as a hit with a near-zero dot product,
+// remove it from both counts if the reference's cos^2 is exactly 0.0 (masked, :113).
+// If the pair list overflowed (pathological inputs: e.g. a lattice with most pairs exactly at the cutoff) the same
+// launch recomputes the whole frame with the all-FP64 sweep instead: results stay exact, only slower.
+// (64-thread blocks: they fit next to the persistent sweep of another frame in flight.)
+#define HS_FIXUP_THREADS 64
+__global__ void __launch_bounds__(HS_FIXUP_THREADS) p2_fixup_kernel(const SweepArgs a) {
+  if (((volatile int64_t *)a.counters)[C_OVERFLOW]) {
+    p2_sweep_exact_body<false>(a);
+    return;
+  }
+  const long long nfix = ((volatile int64_t *)a.counters)[C_NFIX];
+  const size_t n = (size_t)a.n;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nfix; e += (long long)gridDim.x * blockDim.x) {
+    const int2 pr = a.fix_list[e];
+    const int si = pr.x & 0x7fffffff, sj = pr.y, kind = (unsigned)pr.x >> 31;
+    const double cs = exact_pair(a.idx, a.ctr, a.vec, n, a.g, si, sj);
+    if (kind == 0) {
+      if (cs != 0.0) {
+        const unsigned long long f = (unsigned long long)__double2ll_rn(cs * HS_FIX_SCALE);
+        atomicAdd((unsigned long long *)&a.acc_fix[si], f);
+        atomicAdd((unsigned long long *)&a.acc_fix[sj], f);
+        atomicAdd(&a.acc_cnt[si], 1);
+        atomicAdd(&a.acc_cnt[sj], 1);
+      }
+    } else if (cs == 0.0) {
+      atomicAdd(&a.acc_cnt[si], -1);
+      atomicAdd(&a.acc_cnt[sj], -1);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.counters[C_NFIX_DONE] = nfix;
+}
+
+// accumulators (sorted slots, fixed point) -> out_sum / out_cnt (original bond order).  The accumulators are
+// handed back zeroed: the cell build zeroes them once, every sweep leaves them as it found them.
+__global__ void __launch_bounds__(256) p2_finish_kernel(const SweepArgs a) {
+  const bool overflow = ((volatile int64_t *)a.counters)[C_OVERFLOW] != 0;   // the exact sweep writes the outputs
+  const int n_list = a.cell_start[a.g.ncell];
+  const long long nzero = a.counters[C_NZERO];
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_list; s += gridDim.x * blockDim.x) {
+    const long long fix = a.acc_fix[s];
+    int cnt = a.acc_cnt[s];
+    a.acc_fix[s] = 0;
+    a.acc_cnt[s] = 0;
+    if (overflow || !(a.flag[s] & 1)) continue;     // not a reference: out stays 0 / 0
+    const int o = a.idx[s];
+    double sum = (double)fix * HS_FIX_INV;
+    // zero-length bonds in the neighbour set turn every mean into NaN and add to every count
+    // (0/0 in ordering_functions.py:112, SURVEY.md 8(a) a4)
+    if (nzero) {
+      sum = __longlong_as_double(0x7ff8000000000000LL);
+      cnt += (int)nzero;
+    }
+    a.out_sum[o] = sum;
+    a.out_cnt[o] = cnt;
   }
 }
 
@@ -912,7 +961,6 @@ int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const
   a.list_cap = list_cap;
   a.fix_list = (int2 *)w.rec_tmp;    // the original-order payload is dead once the cell list is built
   a.fix_cap = 6LL * (n > 0 ? n : 1);
-  a.only_if_overflow = 0;
   const bool lists = nbr_idx != nullptr;
   const bool fast = mouse_p2_uses_fast(grid, n, flags, lists) != 0;
   if (used_fast) *used_fast = fast ? 1 : 0;
@@ -943,15 +991,12 @@ int mouse_launch_p2_sweep(const double *vec, const double *ctr, int64_t n, const
       default: launch_half<8>(a, excl, 2, warps_override, st); break;
     }
     MOUSE_LAUNCH_CHECK("p2_sweep_half_kernel");
-    p2_fixup_kernel<<<sms, 256, 0, st>>>(a);
+    p2_fixup_kernel<<<sms * 8, HS_FIXUP_THREADS, 0, st>>>(a);     // (or the exact redo of the frame after an overflow)
     MOUSE_LAUNCH_CHECK("p2_fixup_kernel");
     if (!frame_mode) {
       p2_finish_kernel<<<sms * 8, 256, 0, st>>>(a);
       MOUSE_LAUNCH_CHECK("p2_finish_kernel");
     }
-    a.only_if_overflow = 1;          // pair list overflow (pathological inputs): redo the frame exactly
-    p2_sweep_exact_kernel<false><<<sms * 4, 128, 0, st>>>(a);
-    MOUSE_LAUNCH_CHECK("p2_sweep_exact_kernel");
   } else {
     int blocks = (int)((n + 127) / 128);
     if (blocks > sms * 32) blocks = sms * 32;
