@@ -407,6 +407,28 @@ __global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_scatter_idx_kernel(cons
   idx_tmp[cell_start[cid] + rank_of[b]] = b | (is_ref ? (int32_t)0x80000000 : 0);
 }
 
+// ---- crowded grids (more than 32 items per cell on average, down to ONE cell for rmax == 0 / no cutoff): the rank of
+// an item inside its cell (= items of the cell with a smaller original index) is computed here, one thread per item, so
+// that the canon kernel's single warp per cell does not rank a huge cell serially (O(nc^2 / 32) on one warp: seconds
+// for one cell of 100 000 bonds).  The arrival rank is dead after the scatter: its array takes the canonical rank.
+__global__ void __launch_bounds__(256) cell_rank_kernel(int ncell, const int32_t *__restrict__ cell_of,
+                                                        const int32_t *__restrict__ cell_start,
+                                                        const int32_t *__restrict__ idx_tmp,
+                                                        int32_t *__restrict__ rank_of) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= cell_start[ncell]) return;        // items in the list
+  const int mine = idx_tmp[p] & 0x7fffffff;
+  const int c = cell_of[mine];
+#ifdef MOUSE_DEBUG_RANK
+  if (c < 0 || c >= ncell) { printf("rank: p %d mine %d c %d ncell %d nlist %d\n", p, mine, c, ncell, cell_start[ncell]); return; }
+#endif
+  const int s = cell_start[c], nc = cell_start[c + 1] - s;
+  if (nc <= 32) return;        // ranked with shuffles by the canon kernel
+  int rank = 0;
+  for (int k = 0; k < nc; ++k) rank += (idx_tmp[s + k] & 0x7fffffff) < mine;
+  rank_of[mine] = rank;
+}
+
 // ---- canonical order inside each cell (ascending original index, one warp per cell) + payload gather ---------
 // The items of a cell arrive in atomic order; ranking them by original index makes the sorted arrays - and with
 // them every floating-point sum of the sweeps - a deterministic function of the input.
@@ -423,7 +445,8 @@ __global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_canon_kernel(int ncell,
                                                          long long *__restrict__ acc_fix,
                                                          int32_t *__restrict__ acc_cnt,
                                                          int32_t *__restrict__ items,
-                                                         const int32_t *__restrict__ cell_row) {
+                                                         const int32_t *__restrict__ cell_row,
+                                                         const int32_t *__restrict__ big_rank) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < ncell; c += warps) {
@@ -484,6 +507,8 @@ __global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_canon_kernel(int ncell,
           const int other = __shfl_sync(MOUSE_FULL_MASK, mine, k);
           rank += other < mine;
         }
+      } else if (big_rank) {
+        rank = m < nc ? big_rank[mine] : 0;       // cell_rank_kernel
       } else {
         for (int k = 0; k < nc; ++k) rank += (idx_tmp[s + k] & 0x7fffffff) < mine;
       }
@@ -617,17 +642,24 @@ static int cell_build_tail(int mode, const uint8_t *ref_mask, int64_t n, const m
     unsigned nb = (unsigned)((n + MOUSE_ITEM_BLOCK - 1) / MOUSE_ITEM_BLOCK);
     cell_scatter_idx_kernel<<<nb, MOUSE_ITEM_BLOCK, 0, st>>>(ref_mask, (int)n, w.cell_of, w.rank_of, w.cell_start, w.idx_tmp);
     MOUSE_LAUNCH_CHECK("cell_scatter_idx_kernel");
+    // crowded grid: rank the items of the large cells with one thread per item first
+    const int32_t *big_rank = nullptr;
+    if ((double)n > 32.0 * (double)grid->ncell) {
+      cell_rank_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(grid->ncell, w.cell_of, w.cell_start, w.idx_tmp, w.rank_of);
+      MOUSE_LAUNCH_CHECK("cell_rank_kernel");
+      big_rank = w.rank_of;
+    }
     int blocks = (int)((((int64_t)grid->ncell * 32) + MOUSE_ITEM_BLOCK - 1) / MOUSE_ITEM_BLOCK);
     if (blocks > 148 * 16 * (256 / MOUSE_ITEM_BLOCK)) blocks = 148 * 16 * (256 / MOUSE_ITEM_BLOCK);
     if (blocks < 1) blocks = 1;
     if (mode == 0)
       cell_canon_kernel<0><<<blocks, MOUSE_ITEM_BLOCK, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.cell_of, w.rec_sorted,
                                                    w.idx_sorted, w.cell_sorted,
-                                                   w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr, w.cell_count);
+                                                   w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr, w.cell_count, big_rank);
     else
       cell_canon_kernel<1><<<blocks, MOUSE_ITEM_BLOCK, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.cell_of, w.rec_sorted,
                                                    w.idx_sorted, w.cell_sorted,
-                                                   w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr, w.cell_count);
+                                                   w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr, w.cell_count, big_rank);
     MOUSE_LAUNCH_CHECK("cell_canon_kernel");
   }
   return MOUSE_OK;

@@ -103,20 +103,26 @@ __device__ __forceinline__ double exact_pair(const int32_t *__restrict__ idx, co
 // (no function call and no extra state inside the sweep: its register budget is spent on the candidates).
 __device__ __forceinline__ void fix_append(int64_t *counters, int2 *fix_list, long long fix_cap, int si, int sj,
                                            int kind) {
+#ifdef HS_DEBUG_COUNT
+  atomicAdd((unsigned long long *)&counters[5 + (kind & 3)], 1ULL);   // (debug build only: 5..7 belong to the reduce)
+#endif
   const unsigned long long pos = atomicAdd((unsigned long long *)&counters[C_NFIX], 1ULL);
-  if (pos < (unsigned long long)fix_cap) fix_list[pos] = make_int2(si | (kind << 31), sj);
+  if (pos < (unsigned long long)fix_cap) fix_list[pos] = make_int2(si | ((kind & 1) << 31), sj);
   else counters[C_OVERFLOW] = 1;   // the exact sweep recomputes the whole frame
 }
 
-// every pair of an oversized home cell (more bonds than the landing zone holds) goes to the pair list
+// every pair of a home cell with more candidates than the fixed-point accumulators are sized for goes to the pair list
+// (never reached through mouse_p2_uses_fast: such frames take the all-FP64 sweep; kept as a safety net)
 __device__ __noinline__ void hs_oversize(const Rec *__restrict__ R, int64_t *counters, int2 *fix_list,
                                          long long fix_cap, int same_molecule, int lane, int hs, int nhome, int rsrc,
                                          int rlen, int rt0) {
   for (int r = 0; r < 10; ++r) {
     const int src = __shfl_sync(MOUSE_FULL_MASK, rsrc, r), len = __shfl_sync(MOUSE_FULL_MASK, rlen, r);
     const int rt = __shfl_sync(MOUSE_FULL_MASK, rt0, r);
+    // the frame is being redone exactly anyway once the list has overflowed (warp-uniform decision: the lanes must
+    // stay together for the shuffles above and in the caller)
+    if (__any_sync(MOUSE_FULL_MASK, ((volatile int64_t *)counters)[C_OVERFLOW] != 0)) return;
     for (int k = lane; k < len; k += 32) {
-      if (((volatile int64_t *)counters)[C_OVERFLOW]) return;     // the frame is being redone exactly anyway
       const int sj = src + k, tj = rt + k;
       const int molj = __float_as_int(R[sj].p.w);
       for (int il = 0; il < nhome; ++il) {
@@ -480,6 +486,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
   constexpr int NPAIR = SLOTS / 2;
   constexpr int HSL = HS_MAXHOME / 32;
   constexpr int LZ = HS_LZ;
+  static_assert(LZ % HS_MAXHOME == 0, "a window of references never straddles two chunks");
   static_assert(SLOTS % 2 == 0 && NC >= HS_MAXHOME && LZ >= HS_MAXHOME && LZ % 64 == 0 && NPAIR <= 6,
                 "slots come in pairs; the home cell lives in the first sub-pass of the first chunk");
   __shared__ __align__(128) Rec s_land[LZ + 1];     // TMA landing zone (one chunk of the candidate concatenation);
@@ -555,7 +562,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
       if (lane == 0) tkP = (int)atomicAdd((unsigned int *)&a.counters[C_TICKET], 1u);
       if (tkA < a.g.ncell) hs_raw_issue(a.items, lane, tkA, s_raw);
       if (!nonempty) continue;
-      if (it.nhome > LZ || it.T > HS_MAXT) {
+      if (it.T > HS_MAXT) {
         hs_oversize(a.R, a.counters, a.fix_list, a.fix_cap, a.same_molecule, lane, it.hs, it.nhome, it.rsrc, it.rlen, it.rt);
         continue;
       }
@@ -593,11 +600,11 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
       sp = 0;
     }
     // ---- landing zone -> registers: candidates [k0, k0 + NC) of the survivors (first chunk: behind the window start)
-    const int k0 = sp * NC + (ch == 0 ? rb : 0);
+    const int k0 = sp * NC + (ch == rb / LZ ? rb % LZ : 0);
     const int nvalid = max(min(M - k0, NC), 0);
     const int npp = (nvalid + 63) >> 6;             // slot pairs in use
     const bool last = k0 + NC >= M;                 // last sub-pass of this chunk
-    const bool pass0 = (ch == 0) & (sp == 0);       // the home cell leads the concatenation and is never dropped
+    const bool pass0 = (ch == rb / LZ) & (sp == 0);   // the home cell leads the concatenation and is never dropped
     const int hs = cur.hs + rb, nhome = min(cur.nhome - rb, HS_MAXHOME);   // this window's references
     pk2 xr2[NPAIR], yr2[NPAIR], zr2[NPAIR];
     double ux[SLOTS], uy[SLOTS], uz[SLOTS];
@@ -658,7 +665,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     if (last) {
       HsItem nxt = cur;
       if (nch * LZ >= cur.T) {
-        nch = 0;
+        nch = (rb + HS_MAXHOME < cur.nhome) ? (rb + HS_MAXHOME) / LZ : 0;   // the chunk the next window starts in
         nrb = rb + HS_MAXHOME;               // next window of this home cell, or the next home cell
         if (nrb >= cur.nhome) {
           nrb = 0;

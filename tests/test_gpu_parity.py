@@ -433,11 +433,12 @@ def _check_against_c_oracle(pos, bonds, mol, box, rc, same=True, nbr=None, ref=N
     return res, ora
 
 
-@pytest.mark.parametrize("n_cl", [150, 330])
+@pytest.mark.parametrize("n_cl", [150, 330, 700])
 def test_dense_cluster_oversize_home_cells_and_many_passes(n_cl):
-    """One cell holds far more bonds than the fast sweep takes as references at a time: 150 bonds are swept in
-    windows of 64 references, each against all chunks of the candidate concatenation; 330 bonds do not fit the landing
-    zone any more and the cell is decided pair by pair through the pair list (hs_oversize, p2_fixup_kernel)."""
+    """One cell holds far more bonds than the fast sweep takes as references at a time: the cell is swept in windows of
+    HS_MAXHOME references, each against all chunks of the candidate concatenation; with 330 bonds the home cell itself
+    spans two chunks of the landing zone (a window then starts in the chunk that holds its references).  Only
+    guard-band pairs may reach the pair list."""
     rng = np.random.default_rng(5)
     box = np.array([24.0, 24.0, 24.0])
     n_bg = 20000                     # 15^3 cells of edge 1.6; the cluster sits in the middle of one of them
@@ -450,10 +451,7 @@ def test_dense_cluster_oversize_home_cells_and_many_passes(n_cl):
         res, ora = _check_against_c_oracle(pos, bonds, mol, box, 1.5, same)
         assert ora["count"].max() > 140        # the cluster really is dense
         c = _sweep_counters(res, len(bonds))
-        if n_cl > 256:
-            assert c[4] == 0 and c[3] > 5000   # the oversized home cell went through the pair list, no overflow
-        else:
-            assert c[4] == 0 and c[3] < 500    # windows of references: only guard-band pairs are on the list
+        assert c[4] == 0 and c[3] < 500
 
 
 def test_pair_list_overflow_falls_back_to_the_exact_sweep():
