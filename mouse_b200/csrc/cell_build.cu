@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(256) scan_apply2_kernel(int32_t *in, int nc,
   lpt_rows(v, base, nc - 1, in, counters, inv_half_mean);    // in[c] becomes the cell's row in the item table
 }
 
-// ---- scatter the item index into its cell (arrival order); the payload moves once, in cell_canon_kernel -----
+// ---- scatter the item index into its cell (arrival order); the payload moves once, in cell_place_kernel -----
 __global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_scatter_idx_kernel(const uint8_t *__restrict__ ref_mask, int n,
                                                                const int32_t *__restrict__ cell_of,
                                                                const int32_t *__restrict__ rank_of,
@@ -407,146 +407,116 @@ __global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_scatter_idx_kernel(cons
   idx_tmp[cell_start[cid] + rank_of[b]] = b | (is_ref ? (int32_t)0x80000000 : 0);
 }
 
-// ---- crowded grids (more than 32 items per cell on average, down to ONE cell for rmax == 0 / no cutoff): the rank of
-// an item inside its cell (= items of the cell with a smaller original index) is computed here, one thread per item, so
-// that the canon kernel's single warp per cell does not rank a huge cell serially (O(nc^2 / 32) on one warp: seconds
-// for one cell of 100 000 bonds).  The arrival rank is dead after the scatter: its array takes the canonical rank.
-__global__ void __launch_bounds__(256) cell_rank_kernel(int ncell, const int32_t *__restrict__ cell_of,
-                                                        const int32_t *__restrict__ cell_start,
-                                                        const int32_t *__restrict__ idx_tmp,
-                                                        int32_t *__restrict__ rank_of) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= cell_start[ncell]) return;        // items in the list
-  const int mine = idx_tmp[p] & 0x7fffffff;
-  const int c = cell_of[mine];
-#ifdef MOUSE_DEBUG_RANK
-  if (c < 0 || c >= ncell) { printf("rank: p %d mine %d c %d ncell %d nlist %d\n", p, mine, c, ncell, cell_start[ncell]); return; }
-#endif
-  const int s = cell_start[c], nc = cell_start[c + 1] - s;
-  if (nc <= 32) return;        // ranked with shuffles by the canon kernel
-  int rank = 0;
-  for (int k = 0; k < nc; ++k) rank += (idx_tmp[s + k] & 0x7fffffff) < mine;
-  rank_of[mine] = rank;
-}
-
-// ---- canonical order inside each cell (ascending original index, one warp per cell) + payload gather ---------
-// The items of a cell arrive in atomic order; ranking them by original index makes the sorted arrays - and with
-// them every floating-point sum of the sweeps - a deterministic function of the input.
+// ---- canonical order inside each cell (ascending original index) + payload gather: ONE THREAD PER ITEM -----------
+// The items of a cell arrive in atomic order; ranking them by original index makes the sorted arrays - and with them
+// every floating-point sum of the sweeps - a deterministic function of the input.  Thread p owns the item at arrival
+// position p: its rank = items of its cell with a smaller original index (the cell's arrival list is read by all the
+// threads of the cell: broadcast loads), then it gathers its 48-byte record (2 sectors) and writes the sorted arrays.
+// Every lane works whatever the occupancy of the cells (a warp per cell keeps 14 of 32 lanes busy at 1M bonds and
+// ranks one huge cell - rmax == 0, no cutoff - serially: seconds for 100 000 bonds).
 template <int MODE>
-__global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_canon_kernel(int ncell, int n, GridDev g,
-                                                         const int32_t *__restrict__ cell_start,
-                                                         const int32_t *__restrict__ idx_tmp,
-                                                         const Rec *__restrict__ rec_tmp,
-                                                         int32_t *__restrict__ slot_of,
-                                                         Rec *__restrict__ rec_sorted,
-                                                         int32_t *__restrict__ idx_sorted,
-                                                         int32_t *__restrict__ cell_sorted,
-                                                         uint8_t *__restrict__ flag_sorted,
-                                                         long long *__restrict__ acc_fix,
-                                                         int32_t *__restrict__ acc_cnt,
-                                                         int32_t *__restrict__ items,
-                                                         const int32_t *__restrict__ cell_row,
-                                                         const int32_t *__restrict__ big_rank) {
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < ncell; c += warps) {
-    const int s = cell_start[c], e = cell_start[c + 1];
-    const int nc = e - s;
-    const size_t row = items ? (size_t)cell_row[c] : 0;     // the cell's row in the item table: heaviest classes first
-    float ctr_x = 0.0f, ctr_y = 0.0f;
-    if (items) {
-      // the cell's item row for the half-shell sweeps (half_shell.cuh): lane L < 10 owns range L; an empty cell
-      // only needs its size (the sweeps skip it)
-      int32_t val = 0;
-      if (nc > 0) {
-        int cx, cy, cz;
-        hs_cell_coords(g, c, cx, cy, cz);
-        int src = 0, len = 0;
-        if (lane < 10) {
-          int rb, lo, hi;
-          hs_range_cells(g, cx, cy, cz, lane, rb, lo, hi);
-          if (lo <= hi) {
-            src = cell_start[rb + lo];
-            len = cell_start[rb + hi + 1] - src;
-          }
-        }
-        int incl = len;
+__global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_place_kernel(int ncell, const int32_t *__restrict__ cell_start,
+                                                                      const int32_t *__restrict__ idx_tmp,
+                                                                      const Rec *__restrict__ rec_tmp, int32_t *slot_of,
+                                                                      Rec *__restrict__ rec_sorted,
+                                                                      int32_t *__restrict__ idx_sorted,
+                                                                      int32_t *__restrict__ cell_sorted,
+                                                                      uint8_t *__restrict__ flag_sorted,
+                                                                      long long *__restrict__ acc_fix,
+                                                                      int32_t *__restrict__ acc_cnt,
+                                                                      uint32_t *__restrict__ cell_bbox) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = p < cell_start[ncell];   // items in the list
+  const unsigned act = __ballot_sync(MOUSE_FULL_MASK, live);     // the lanes that meet again at the box reduction
+  if (!live) return;
+  const int raw = idx_tmp[p];
+  const int mine = raw & 0x7fffffff;
+  const int c = slot_of[mine];               // still the item's cell id (this thread replaces it below)
+  const int s = cell_start[c], e = cell_start[c + 1];
+  int rank = 0;
+  for (int k = s; k < e; ++k) rank += (idx_tmp[k] & 0x7fffffff) < mine;
+  const int d = s + rank;
+  Rec r = rec_tmp[mine];
+  // .w carries the sorted slot itself: the sweep's register-resident candidates know where they live
+  if (MODE == 0) r.u.w = __hiloint2double(0, d);
+  rec_sorted[d] = r;
+  // inverse permutation (the cell id of the item is dead by now): sorted slot | reference bit << 30, so that
+  // the fused finish + reduce walks the outputs in original order (coalesced stores, gathers that hit L2)
+  slot_of[mine] = d | (int)(((unsigned)raw >> 31) << 30);
+  idx_sorted[d] = mine;
+  cell_sorted[d] = c;
+  flag_sorted[d] = (uint8_t)((unsigned)raw >> 31);
+  acc_fix[d] = 0;      // the half-shell sweep's accumulators start (and are left) at zero
+  acc_cnt[d] = 0;
+  if (MODE == 0 && cell_bbox) {
+    // bounding box of the cell's items (the P2 sweep drops candidates farther than the cutoff from it): the threads of
+    // a cell are neighbours, so the lanes of the warp that share a cell reduce their keys (REDUX) and one of them
+    // folds the result into the cell's box with six integer atomics
+    const unsigned peers = __match_any_sync(act, c);
+    uint32_t k[6];
+    k[0] = mouse_float_key(r.p.x), k[1] = mouse_float_key(r.p.y), k[2] = mouse_float_key(r.p.z);
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-          const int y = __shfl_up_sync(MOUSE_FULL_MASK, incl, o);
-          if (lane >= o) incl += y;
-        }
-        // row layout: [0..9] src, [10..19] len, [20..29] offset, [30] size | boundary << 30, [31] centre z,
-        // [32..37] bounding box of the cell's items, [38..39] centre x, y (written below)
-        const int src_k = __shfl_sync(MOUSE_FULL_MASK, src, lane % 10);
-        const int len_k = __shfl_sync(MOUSE_FULL_MASK, len, lane % 10);
-        const int off_k = __shfl_sync(MOUSE_FULL_MASK, incl - len, lane % 10);
-        const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
-        const int boundary = (cx == 0) | (cx == nx - 1) | (cy == 0) | (cy == ny - 1) | (cz == nz - 1);
-        // cell centre along the lattice directions, then Cartesian (the tilt ratios are 0 for an orthorhombic box)
-        const float ux = ((float)cx + 0.5f) * g.cwf[0] - 0.5f * g.boxf[0];
-        const float uy = ((float)cy + 0.5f) * g.cwf[1] - 0.5f * g.boxf[1];
-        const float uz = ((float)cz + 0.5f) * g.cwf[2] - 0.5f * g.boxf[2];
-        ctr_x = ux + g.tratio[0] * uy + g.tratio[1] * uz;
-        ctr_y = uy + g.tratio[2] * uz;
-        val = lane < 10 ? src_k : lane < 20 ? len_k : lane < 30 ? off_k : lane == 30 ? (nc | (boundary << 30))
-                                                                   : __float_as_int(uz);
-      }
-      items[row * HS_ITEM_INTS + lane] = val;
-      if (nc <= 0 && lane < 8) items[row * HS_ITEM_INTS + 32 + lane] = 0;
-    }
-    if (nc <= 0) continue;
-    float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    for (int m0 = 0; m0 < nc; m0 += 32) {
-      const int m = m0 + lane;
-      const int raw = m < nc ? idx_tmp[s + m] : 0x7fffffff;
-      const int mine = raw & 0x7fffffff;
-      int rank = 0;
-      if (nc <= 32) {
-        for (int k = 0; k < nc; ++k) {
-          const int other = __shfl_sync(MOUSE_FULL_MASK, mine, k);
-          rank += other < mine;
-        }
-      } else if (big_rank) {
-        rank = m < nc ? big_rank[mine] : 0;       // cell_rank_kernel
-      } else {
-        for (int k = 0; k < nc; ++k) rank += (idx_tmp[s + k] & 0x7fffffff) < mine;
-      }
-      if (m < nc) {
-        const int d = s + rank;
-        Rec r = rec_tmp[mine];
-        blo[0] = fminf(blo[0], r.p.x), blo[1] = fminf(blo[1], r.p.y), blo[2] = fminf(blo[2], r.p.z);
-        bhi[0] = fmaxf(bhi[0], r.p.x), bhi[1] = fmaxf(bhi[1], r.p.y), bhi[2] = fmaxf(bhi[2], r.p.z);
-        // .w carries the sorted slot itself: the sweep's register-resident candidates know where they live
-        if (MODE == 0) r.u.w = __hiloint2double(0, d);
-        rec_sorted[d] = r;
-        // inverse permutation (the cell id of the item is dead by now): sorted slot | reference bit << 30, so that
-        // the fused finish + reduce walks the outputs in original order (coalesced stores, gathers that hit L2)
-        slot_of[mine] = d | (int)(((unsigned)raw >> 31) << 30);
-        idx_sorted[d] = mine;
-        cell_sorted[d] = c;
-        flag_sorted[d] = (uint8_t)((unsigned)raw >> 31);
-        acc_fix[d] = 0;      // the half-shell sweep's accumulators start (and are left) at zero
-        acc_cnt[d] = 0;
-      }
-    }
-    if (items) {
-      // bounding box of the cell's items: the P2 sweep drops candidates farther than the cutoff from it
+    for (int a = 0; a < 3; ++a) k[3 + a] = ~k[a];
 #pragma unroll
-      for (int ax = 0; ax < 3; ++ax) {
+    for (int a = 0; a < 6; ++a) k[a] = __reduce_max_sync(peers, k[a]);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          blo[ax] = fminf(blo[ax], __shfl_xor_sync(MOUSE_FULL_MASK, blo[ax], o));
-          bhi[ax] = fmaxf(bhi[ax], __shfl_xor_sync(MOUSE_FULL_MASK, bhi[ax], o));
-        }
-      }
-      if (lane < 8) {
-        const float v = lane == 0 ? blo[0] : lane == 1 ? blo[1] : lane == 2 ? blo[2] : lane == 3 ? bhi[0]
-                        : lane == 4 ? bhi[1] : lane == 5 ? bhi[2] : lane == 6 ? ctr_x : ctr_y;
-        items[row * HS_ITEM_INTS + 32 + lane] = __float_as_int(v);
-      }
+      for (int a = 0; a < 6; ++a) atomicMax(&cell_bbox[(size_t)c * 6 + a], k[a]);
     }
   }
+}
+
+// ---- the item rows of the half-shell sweeps (half_shell.cuh): ONE THREAD PER CELL ------------------------------
+// [0..9] first sorted slot of range L, [10..19] its length, [20..29] its offset in the candidate concatenation,
+// [30] size | boundary << 30, [31] centre z, [32..37] bounding box of the cell's items (P2: the sweep drops candidates
+// farther than the cutoff from it), [38..39] centre x, y.  The row index comes from the scan (heaviest cells first).
+template <int MODE>
+__global__ void __launch_bounds__(128) cell_items_kernel(int ncell, GridDev g, const int32_t *__restrict__ cell_start,
+                                                         const uint32_t *__restrict__ cell_bbox,
+                                                         const int32_t *__restrict__ cell_row,
+                                                         int32_t *__restrict__ items) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  const int s = cell_start[c], nc = cell_start[c + 1] - s;
+  int4 *row = (int4 *)(items + (size_t)cell_row[c] * HS_ITEM_INTS);
+  if (nc <= 0) {       // an empty cell only needs its size (the sweeps skip it)
+    row[7] = make_int4(0, 0, 0, 0);
+    return;
+  }
+  int cx, cy, cz;
+  hs_cell_coords(g, c, cx, cy, cz);
+  int v[HS_ITEM_INTS];
+  int off = 0;
+#pragma unroll
+  for (int L = 0; L < 10; ++L) {
+    int rb, lo, hi, src = 0, len = 0;
+    hs_range_cells(g, cx, cy, cz, L, rb, lo, hi);
+    if (lo <= hi) {
+      src = cell_start[rb + lo];
+      len = cell_start[rb + hi + 1] - src;
+    }
+    v[L] = src;
+    v[10 + L] = len;
+    v[20 + L] = off;
+    off += len;
+  }
+  const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
+  const int boundary = (cx == 0) | (cx == nx - 1) | (cy == 0) | (cy == ny - 1) | (cz == nz - 1);
+  // cell centre along the lattice directions, then Cartesian (the tilt ratios are 0 for an orthorhombic box)
+  const float ux = ((float)cx + 0.5f) * g.cwf[0] - 0.5f * g.boxf[0];
+  const float uy = ((float)cy + 0.5f) * g.cwf[1] - 0.5f * g.boxf[1];
+  const float uz = ((float)cz + 0.5f) * g.cwf[2] - 0.5f * g.boxf[2];
+  v[30] = nc | (boundary << 30);
+  v[31] = __float_as_int(uz);
+  v[38] = __float_as_int(ux + g.tratio[0] * uy + g.tratio[1] * uz);
+  v[39] = __float_as_int(uy + g.tratio[2] * uz);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {      // upper corner: max of the keys; lower corner: max of the complemented keys
+    v[35 + a] = MODE == 0 ? __float_as_int(mouse_key_float(cell_bbox[(size_t)c * 6 + a])) : 0;
+    v[32 + a] = MODE == 0 ? __float_as_int(mouse_key_float(~cell_bbox[(size_t)c * 6 + 3 + a])) : 0;
+  }
+#pragma unroll
+  for (int q = 0; q < HS_ITEM_INTS / 4; ++q) row[q] = make_int4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
 // ---- K1 + cell assignment + output initialisation in one pass (mouse_p2_frame) -------------------------------
@@ -642,25 +612,21 @@ static int cell_build_tail(int mode, const uint8_t *ref_mask, int64_t n, const m
     unsigned nb = (unsigned)((n + MOUSE_ITEM_BLOCK - 1) / MOUSE_ITEM_BLOCK);
     cell_scatter_idx_kernel<<<nb, MOUSE_ITEM_BLOCK, 0, st>>>(ref_mask, (int)n, w.cell_of, w.rank_of, w.cell_start, w.idx_tmp);
     MOUSE_LAUNCH_CHECK("cell_scatter_idx_kernel");
-    // crowded grid: rank the items of the large cells with one thread per item first
-    const int32_t *big_rank = nullptr;
-    if ((double)n > 32.0 * (double)grid->ncell) {
-      cell_rank_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(grid->ncell, w.cell_of, w.cell_start, w.idx_tmp, w.rank_of);
-      MOUSE_LAUNCH_CHECK("cell_rank_kernel");
-      big_rank = w.rank_of;
-    }
-    int blocks = (int)((((int64_t)grid->ncell * 32) + MOUSE_ITEM_BLOCK - 1) / MOUSE_ITEM_BLOCK);
-    if (blocks > 148 * 16 * (256 / MOUSE_ITEM_BLOCK)) blocks = 148 * 16 * (256 / MOUSE_ITEM_BLOCK);
-    if (blocks < 1) blocks = 1;
     if (mode == 0)
-      cell_canon_kernel<0><<<blocks, MOUSE_ITEM_BLOCK, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.cell_of, w.rec_sorted,
-                                                   w.idx_sorted, w.cell_sorted,
-                                                   w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr, w.cell_count, big_rank);
+      cell_place_kernel<0><<<nb, MOUSE_ITEM_BLOCK, 0, st>>>(grid->ncell, w.cell_start, w.idx_tmp, w.rec_tmp, w.cell_of, w.rec_sorted,
+                                                            w.idx_sorted, w.cell_sorted, w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.cell_bbox : nullptr);
     else
-      cell_canon_kernel<1><<<blocks, MOUSE_ITEM_BLOCK, 0, st>>>(grid->ncell, (int)n, g, w.cell_start, w.idx_tmp, w.rec_tmp, w.cell_of, w.rec_sorted,
-                                                   w.idx_sorted, w.cell_sorted,
-                                                   w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.items : nullptr, w.cell_count, big_rank);
-    MOUSE_LAUNCH_CHECK("cell_canon_kernel");
+      cell_place_kernel<1><<<nb, MOUSE_ITEM_BLOCK, 0, st>>>(grid->ncell, w.cell_start, w.idx_tmp, w.rec_tmp, w.cell_of, w.rec_sorted,
+                                                            w.idx_sorted, w.cell_sorted, w.flag_sorted, w.acc_fix, w.acc_cnt, grid->fast ? w.cell_bbox : nullptr);
+    MOUSE_LAUNCH_CHECK("cell_place_kernel");
+  }
+  if (grid->fast) {      // (also for an empty list: the sweeps read every cell's row)
+    const unsigned cb = (unsigned)((grid->ncell + 127) / 128);
+    if (mode == 0)
+      cell_items_kernel<0><<<cb, 128, 0, st>>>(grid->ncell, g, w.cell_start, w.cell_bbox, w.cell_count, w.items);
+    else
+      cell_items_kernel<1><<<cb, 128, 0, st>>>(grid->ncell, g, w.cell_start, w.cell_bbox, w.cell_count, w.items);
+    MOUSE_LAUNCH_CHECK("cell_items_kernel");
   }
   return MOUSE_OK;
 }
@@ -671,7 +637,7 @@ int mouse_launch_cell_build(int mode, const double *xyz, const double *vec, cons
                             const Workspace &w, cudaStream_t st) {
   GridDev g = mouse_grid_dev(grid);
   // counters sit right in front of cell_count: one memset clears both
-  MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, (size_t)((char *)(w.cell_count + grid->ncell + 1) - (char *)w.counters), st));
+  MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, mouse_clear_bytes(w, grid->ncell), st));
   unsigned nb = (unsigned)((n + 255) / 256);
   if (n > 0) {
     if (mode == 0)
@@ -691,7 +657,7 @@ int mouse_launch_frame_build(const double *pos, const int32_t *bond_atoms, const
                              double *vec, double *ctr, double *out_sum, int32_t *out_cnt, double *out_mean,
                              int init_listed, cudaStream_t st) {
   GridDev g = mouse_grid_dev(grid);
-  MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, (size_t)((char *)(w.cell_count + grid->ncell + 1) - (char *)w.counters), st));
+  MOUSE_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, mouse_clear_bytes(w, grid->ncell), st));
   if (n > 0) {
     bond_assign_kernel<<<(unsigned)((n + MOUSE_ITEM_BLOCK - 1) / MOUSE_ITEM_BLOCK), MOUSE_ITEM_BLOCK, 0, st>>>(pos, (const int2 *)bond_atoms, mol, nbr_mask, (int)n,
                                                                      g, vec, ctr, w.cell_of, w.rank_of, w.cell_count,

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/mouse_b200.h"
 
@@ -45,6 +46,8 @@ static_assert(sizeof(Rec) == 48, "Rec must be 48 bytes");
 struct Workspace {
   // per cell
   int32_t *cell_count;   // [ncell+1]   items per cell (atomic histogram), last entry unused; after the scan: the cell's row in `items`
+  uint32_t *cell_bbox;   // [ncell][6]  bounding box of the cell's items as order-preserving integer keys, reduced with
+                         //             atomicMax: [0..2] upper corner, [3..5] lower corner (complemented keys); 0 = empty
   int32_t *cell_start;   // [ncell+1]   exclusive scan; cell_start[ncell] = items in the list
   int32_t *scan_blocks;  // [scan_nblocks+1]
   int32_t *items;        // [ncell][40] item table of the half-shell sweeps (ranges of the 14 cells, see half_shell.cuh)
@@ -91,9 +94,10 @@ static inline Workspace mouse_carve(void *ws, int64_t n, int32_t ncell) {
 #define CARVE(field, type, count)                     \
   w.field = (type *)(base ? base + off : nullptr);    \
   off = mouse_align_up(off + sizeof(type) * (count), 256);
-  CARVE(counters, int64_t, 32)     // counters, scan_blocks and cell_count are adjacent: cleared by one memset
+  CARVE(counters, int64_t, 32)     // counters, scan_blocks, cell_count and cell_bbox are adjacent: cleared by one memset
   CARVE(scan_blocks, int32_t, nsb)
   CARVE(cell_count, int32_t, nc)
+  CARVE(cell_bbox, uint32_t, 6 * nc)
   CARVE(cell_start, int32_t, nc)
   CARVE(items, int32_t, 40 * nc)
   CARVE(cell_of, int32_t, nn)
@@ -113,6 +117,25 @@ static inline Workspace mouse_carve(void *ws, int64_t n, int32_t ncell) {
 #undef CARVE
   w.bytes = off;
   return w;
+}
+
+// bytes from the start of the counters to the end of cell_bbox: what a cell build clears before it starts
+static inline size_t mouse_clear_bytes(const Workspace &w, int32_t ncell) {
+  return (size_t)((const char *)(w.cell_bbox + 6 * ((size_t)ncell + 1)) - (const char *)w.counters);
+}
+
+// order-preserving map float -> uint32 (a < b  <=>  key(a) < key(b)) and back
+__host__ __device__ __forceinline__ uint32_t mouse_float_key(float x) {
+#ifdef __CUDA_ARCH__
+  const uint32_t b = __float_as_uint(x);
+#else
+  uint32_t b;
+  memcpy(&b, &x, 4);
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float mouse_key_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
 // ------------------------------------------------------------------ grid passed by value to kernels

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(FIN_THREADS) p2_finish_reduce_kernel(const Fin
       fix[q] = v[q] >= 0 ? acc_fix[s] : 0;
       c[q] = v[q] >= 0 ? acc_cnt[s] : 0;
     }
-    // (the accumulators are NOT re-zeroed here: every frame build zeroes them in cell_canon_kernel)
+    // (the accumulators are NOT re-zeroed here: every frame build zeroes them in cell_place_kernel)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int b = b0 + q * FIN_THREADS;
