@@ -11,6 +11,7 @@
 
 // ------------------------------------------------------------------ error plumbing
 void mouse_set_error(const char *fmt, ...);
+int mouse_num_sms();      // SMs of the current device (p2_sweep.cu: per-device table of immutable facts)
 
 #define MOUSE_CUDA_CHECK(expr)                                                            \
   do {                                                                                    \

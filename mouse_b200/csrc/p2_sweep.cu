@@ -444,6 +444,7 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
 // order, as BYTE offsets (48 * index); returns M.  bb (shared memory) = home cell centre, box lower corner, box upper corner.  BND: the home cell
 // sits on the periodic boundary; the candidates are first moved to their image nearest to the home cell centre
 // (written back to the landing zone).  Two candidates per lane and trip (two independent chains).
+#define HS_CULL_W 2        // candidates per lane and trip of the cull (independent chains: the trip is latency-bound)
 template <bool BND>
 __device__ __forceinline__ int hs_cull(uint32_t land, uint32_t sel, const float *bb, const GridDev &g, int lane,
                                        int nland, float thr) {
@@ -451,30 +452,34 @@ __device__ __forceinline__ int hs_cull(uint32_t land, uint32_t sel, const float 
   const unsigned lt = (1u << lane) - 1u;
   int M = 0;
   uint32_t pa = land + 48u * (uint32_t)lane;
-  for (int t0 = 0; t0 < nland; t0 += 64, pa += 64u * 48u) {
-    float4 p = lds_float4(pa), q = lds_float4(pa + 32u * 48u);
+  for (int t0 = 0; t0 < nland; t0 += 32 * HS_CULL_W, pa += 32u * HS_CULL_W * 48u) {
+    float4 p[HS_CULL_W];
+#pragma unroll
+    for (int j = 0; j < HS_CULL_W; ++j) p[j] = lds_float4(pa + 32u * 48u * j);
     if (BND) {
       const float hx = bb[0], hy = bb[1], hz = bb[2];
-      hs_nearest_image(p.x, p.y, p.z, hx, hy, hz, g);
-      hs_nearest_image(q.x, q.y, q.z, hx, hy, hz, g);
-      sts_float4(pa, p);
-      sts_float4(pa + 32u * 48u, q);
+#pragma unroll
+      for (int j = 0; j < HS_CULL_W; ++j) {
+        hs_nearest_image(p[j].x, p[j].y, p[j].z, hx, hy, hz, g);
+        sts_float4(pa + 32u * 48u * j, p[j]);
+      }
     }
-    const float ex = fmaxf(fmaxf(__fadd_rn(blx, -p.x), __fadd_rn(p.x, -bhx)), 0.0f);
-    const float ey = fmaxf(fmaxf(__fadd_rn(bly, -p.y), __fadd_rn(p.y, -bhy)), 0.0f);
-    const float ez = fmaxf(fmaxf(__fadd_rn(blz, -p.z), __fadd_rn(p.z, -bhz)), 0.0f);
-    const float fx = fmaxf(fmaxf(__fadd_rn(blx, -q.x), __fadd_rn(q.x, -bhx)), 0.0f);
-    const float fy = fmaxf(fmaxf(__fadd_rn(bly, -q.y), __fadd_rn(q.y, -bhy)), 0.0f);
-    const float fz = fmaxf(fmaxf(__fadd_rn(blz, -q.z), __fadd_rn(q.z, -bhz)), 0.0f);
-    const float d2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
-    const float e2 = __fmaf_rn(fz, fz, __fmaf_rn(fy, fy, __fmul_rn(fx, fx)));
-    const int ta = t0 + lane, tb = ta + 32;
-    const bool ka = (ta < nland) & (d2 <= thr), kb = (tb < nland) & (e2 <= thr);
-    const unsigned ba = __ballot_sync(MOUSE_FULL_MASK, ka), bq = __ballot_sync(MOUSE_FULL_MASK, kb);
-    const int na = __popc(ba);
-    if (ka) sts_u16(sel + 2u * (uint32_t)(M + __popc(ba & lt)), 48 * ta);
-    if (kb) sts_u16(sel + 2u * (uint32_t)(M + na + __popc(bq & lt)), 48 * tb);
-    M += na + __popc(bq);
+    unsigned bal[HS_CULL_W];
+    bool keep[HS_CULL_W];
+#pragma unroll
+    for (int j = 0; j < HS_CULL_W; ++j) {
+      const float ex = fmaxf(fmaxf(__fadd_rn(blx, -p[j].x), __fadd_rn(p[j].x, -bhx)), 0.0f);
+      const float ey = fmaxf(fmaxf(__fadd_rn(bly, -p[j].y), __fadd_rn(p[j].y, -bhy)), 0.0f);
+      const float ez = fmaxf(fmaxf(__fadd_rn(blz, -p[j].z), __fadd_rn(p[j].z, -bhz)), 0.0f);
+      const float d2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
+      keep[j] = (t0 + 32 * j + lane < nland) & (d2 <= thr);
+      bal[j] = __ballot_sync(MOUSE_FULL_MASK, keep[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < HS_CULL_W; ++j) {
+      if (keep[j]) sts_u16(sel + 2u * (uint32_t)(M + __popc(bal[j] & lt)), 48 * (t0 + 32 * j + lane));
+      M += __popc(bal[j]);
+    }
   }
   __syncwarp();
   return M;
@@ -487,7 +492,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
   constexpr int HSL = HS_MAXHOME / 32;
   constexpr int LZ = HS_LZ;
   static_assert(LZ % HS_MAXHOME == 0, "a window of references never straddles two chunks");
-  static_assert(SLOTS % 2 == 0 && NC >= HS_MAXHOME && LZ >= HS_MAXHOME && LZ % 64 == 0 && NPAIR <= 6,
+  static_assert(SLOTS % 2 == 0 && NC >= HS_MAXHOME && LZ >= HS_MAXHOME && LZ % (32 * HS_CULL_W) == 0 && NPAIR <= 6,
                 "slots come in pairs; the home cell lives in the first sub-pass of the first chunk");
   __shared__ __align__(128) Rec s_land[LZ + 1];     // TMA landing zone (one chunk of the candidate concatenation);
                                                     // record LZ is the filler of the empty register slots

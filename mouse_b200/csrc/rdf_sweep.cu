@@ -444,15 +444,12 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
 
 template <bool SAME_MOL, bool ONE_TYPE, bool SMEM_HIST>
 static void launch_rdf_half(const RdfHalfArgs &h, int ncell, size_t smem, cudaStream_t st) {
-  static int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rdf_sweep_half_kernel<8, SAME_MOL, ONE_TYPE, SMEM_HIST>,
-                                                  32, SMEM_HIST ? 4096 : 0);
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // (no cached state: the library holds nothing per process; the query costs microseconds next to a 10 ms sweep)
+  int blocks_per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rdf_sweep_half_kernel<8, SAME_MOL, ONE_TYPE, SMEM_HIST>, 32,
+                                                smem);
+  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  const int sms = mouse_num_sms();
   int blocks = sms * blocks_per_sm;
   if (blocks > ncell) blocks = ncell;
   rdf_sweep_half_kernel<8, SAME_MOL, ONE_TYPE, SMEM_HIST><<<blocks, 32, smem, st>>>(h);
