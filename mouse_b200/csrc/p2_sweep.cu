@@ -232,7 +232,7 @@ __device__ __forceinline__ unsigned hs_ref_pairs(const HsConst k, const int lane
                                                  const double (&ux)[SLOTS], const double (&uy)[SLOTS],
                                                  const double (&uz)[SLOTS], double (&accj)[SLOTS], int (&cntj)[SLOTS],
                                                  const int (&molr)[SLOTS], const uint32_t s_ref, const int *s_mol,
-                                                 double (*s_acc)[33], int (*s_cnt)[33]) {
+                                                 double (*s_acc)[33], uint8_t (*s_cnt)[36]) {
   constexpr int NPP = (NS + 1) / 2;
   constexpr int HSL = HS_MAXHOME / 32;   // slots of pass 0 that may hold home-cell bonds
   const pk2 nlo = pk2_make(k.nlo, k.nlo);
@@ -240,9 +240,9 @@ __device__ __forceinline__ unsigned hs_ref_pairs(const HsConst k, const int lane
   // two references per iteration: two independent dependency chains per warp.  The second one of an odd
   // tail is the sentinel record behind the window (far away: no hits, never in the band)
   uint32_t rp = s_ref + HS_REF_BYTES * (uint32_t)base;
-  uint32_t ap = smem_addr(&s_acc[0][lane]), cp = smem_addr(&s_cnt[0][lane]);
+  uint32_t ap = smem_addr(&s_acc[0][lane]), cp = smem_addr(&s_cnt[0][lane]);      // (counts: one byte per lane, <= SLOTS)
 #pragma unroll 1
-  for (int r = 0; r < nref; r += 2, rp += 2u * HS_REF_BYTES, ap += 2u * 33u * 8u, cp += 2u * 33u * 4u) {
+  for (int r = 0; r < nref; r += 2, rp += 2u * HS_REF_BYTES, ap += 2u * 33u * 8u, cp += 2u * 36u) {
     const int il = base + r;
     pk2 nax, nay, naz, nbx, nby, nbz, uaz2, ubz2;
     lds_pk2x2(rp, nax, nay);
@@ -328,8 +328,8 @@ __device__ __forceinline__ unsigned hs_ref_pairs(const HsConst k, const int lane
     if ((min(banda, bandb) <= k.band_bits) | (fminf(nza, nzb) <= k.nearz_thr)) rare |= 3u << r;
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(ap), "d"(acca0 + acca1) : "memory");
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(ap + 33u * 8u), "d"(accb0 + accb1) : "memory");
-    asm volatile("st.shared.s32 [%0], %1;" ::"r"(cp), "r"(cnta) : "memory");
-    asm volatile("st.shared.s32 [%0], %1;" ::"r"(cp + 33u * 4u), "r"(cntb) : "memory");
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(cp), "r"(cnta) : "memory");
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(cp + 36u), "r"(cntb) : "memory");
   }
   return rare;
 }
@@ -343,7 +343,7 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
                                             const double (&ux)[SLOTS], const double (&uy)[SLOTS],
                                             const double (&uz)[SLOTS], double (&accj)[SLOTS], int (&cntj)[SLOTS],
                                             const int (&molr)[SLOTS], const uint32_t s_ref, const int *s_mol, double (*s_acc)[33],
-                                            int (*s_cnt)[33], const int (*s_gid)[32]) {
+                                            uint8_t (*s_cnt)[36], const int (*s_gid)[32]) {
   static_assert(HS_GRP == 8 || HS_GRP == 4, "reference groups of 4 or 8");
   static_assert(HS_MAXHOME % 2 == 0, "references are processed two at a time");
   constexpr int HSL = HS_MAXHOME / 32;   // slots of pass 0 that may hold home-cell bonds
@@ -425,7 +425,7 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
 #pragma unroll
       for (int q = 0; q < HS_GRP; ++q) {
         pv[q] = s_acc[row][part * HS_GRP + q];
-        nv += s_cnt[row][part * HS_GRP + q];
+        nv += (int)s_cnt[row][part * HS_GRP + q];
       }
 #pragma unroll
       for (int w = 1; w < HS_GRP; w <<= 1)
@@ -498,13 +498,13 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
                                                     // record LZ is the filler of the empty register slots
   __shared__ uint16_t s_sel[LZ + NC];               // byte offset in the landing zone of the candidates that survived
                                                     // the cull, then NC times the filler
-  __shared__ HsRef s_ref[HS_MAXHOME + 2];           // the references of this window (+ the far-away sentinel)
+  __shared__ HsRef s_ref[HS_MAXHOME + 1];           // the references of this window (+ the far-away sentinel)
   __shared__ int s_mol[EXCL_MOL ? HS_MAXHOME + 2 : 1];   // their molecule codes (only read when pairs inside a molecule are excluded)
   __shared__ double s_acc[HS_GRP][33];              // per-lane partial sums of 8 references (transposed reduce)
-  __shared__ int s_cnt[HS_GRP][33];                 // ... and partial counts
+  __shared__ uint8_t s_cnt[HS_GRP][36];             // ... and partial counts (<= SLOTS per lane and reference: a byte each)
   __shared__ int s_gid[SLOTS][32];                  // sorted slot of every register-resident candidate (-1: empty)
   __shared__ __align__(16) int s_raw[HS_ITEM_INTS]; // item row in flight (fetch stage 2 -> 3)
-  __shared__ int s_next[3][32];                     // range table of the prefetched item (kept out of the registers)
+  __shared__ int s_next[3][10];                     // range table of the prefetched item (kept out of the registers)
   __shared__ float s_bb[9];                         // home cell centre + bounding box of the prefetched / current item
   __shared__ int s_nexti[6];
   __shared__ __align__(8) uint64_t s_bar;
@@ -679,9 +679,11 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
       }
       if (have) {
         issue(nxt, nch);
-        s_next[0][lane] = nxt.rsrc;
-        s_next[1][lane] = nxt.rlen;
-        s_next[2][lane] = nxt.rt;
+        if (lane < 10) {
+          s_next[0][lane] = nxt.rsrc;
+          s_next[1][lane] = nxt.rlen;
+          s_next[2][lane] = nxt.rt;
+        }
         if (lane == 0) {
           s_nexti[0] = nxt.home;
           s_nexti[1] = nxt.hs;
@@ -710,9 +712,9 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     }
     if (!have) break;
     __syncwarp();
-    cur.rsrc = s_next[0][lane];
-    cur.rlen = s_next[1][lane];
-    cur.rt = s_next[2][lane];
+    cur.rsrc = s_next[0][lane < 10 ? lane : 0];
+    cur.rlen = lane < 10 ? s_next[1][lane] : 0;
+    cur.rt = s_next[2][lane < 10 ? lane : 0];
     cur.home = s_nexti[0];
     cur.hs = s_nexti[1];
     cur.nhome = s_nexti[2];
