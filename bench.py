@@ -44,7 +44,7 @@ W5_LANE_INSTR_PER_PAIR = 60.2     # K5: 6.45 x 7 FP32 filter + 1
 BYTES_PER_BOND = 72.0             # compulsory HBM bytes per bond per frame
 N_FRAME_VARIANTS = 4              # distinct frames cycled (working set per frame ~210 MB > 126 MB L2)
 LANES = int(os.environ.get("MOUSE_BENCH_LANES", "3"))                         # frames in flight in the device-resident timed region (own stream + workspace each)
-KERNELS_PER_FRAME = 8             # bond_assign, scan, scatter_idx, canon, sweep, fixup, exact check, finish+reduce
+KERNELS_PER_FRAME = 9             # bond_assign, scan_reduce, scan_apply2, scatter_idx, place, items, sweep, fixup, finish+reduce
 
 
 def static_config(n_bonds):
