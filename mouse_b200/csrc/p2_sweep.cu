@@ -361,19 +361,29 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
 #define HS_PAIRS(N)                                                                                                   \
   rare = hs_ref_pairs<SLOTS, (N <= SLOTS ? N : SLOTS), EXCL_MOL>(k, lane, base, nref, jl, xr2, yr2, zr2, ux, uy, uz, accj, cntj, \
                                                                   molr, s_ref, s_mol, s_acc, s_cnt)
-#ifdef HS_EVEN_ONLY
-    switch ((ns + 1) & ~1) {
-#else
-    switch (ns) {      // slots in use (1 <= ns <= SLOTS: the other cases are not instantiated)
-#endif
-      case 1: HS_PAIRS(1); break;
-      case 2: HS_PAIRS(2); break;
-      case 3: if constexpr (SLOTS >= 3) HS_PAIRS(3); break;
-      case 4: if constexpr (SLOTS >= 4) HS_PAIRS(4); break;
-      case 5: if constexpr (SLOTS >= 5) HS_PAIRS(5); break;
-      case 6: if constexpr (SLOTS >= 6) HS_PAIRS(6); break;
-      case 7: if constexpr (SLOTS >= 7) HS_PAIRS(7); break;
-      default: if constexpr (SLOTS >= 8) HS_PAIRS(8); break;
+    // (a tree of warp-uniform compares: the jump table of a switch costs an indirect branch per group)
+    if (SLOTS > 6 && ns > 6) {
+      if (ns > 7) {
+        if constexpr (SLOTS >= 8) HS_PAIRS(8);
+      } else {
+        if constexpr (SLOTS >= 7) HS_PAIRS(7);
+      }
+    } else if (ns > 3) {
+      if (ns > 5) {
+        if constexpr (SLOTS >= 6) HS_PAIRS(6);
+      } else if (ns > 4) {
+        if constexpr (SLOTS >= 5) HS_PAIRS(5);
+      } else {
+        if constexpr (SLOTS >= 4) HS_PAIRS(4);
+      }
+    } else if (ns > 1) {
+      if (ns > 2) {
+        if constexpr (SLOTS >= 3) HS_PAIRS(3);
+      } else {
+        HS_PAIRS(2);
+      }
+    } else {
+      HS_PAIRS(1);
     }
 #undef HS_PAIRS
     rare &= (1u << nref) - 1u;     // the sentinel of an odd tail is not a reference
