@@ -166,6 +166,11 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, int v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
 }
 
+#ifndef HS_REF_UNROLL
+#define HS_REF_UNROLL 1       // trips of the reference-pair loop unrolled together
+#endif
+constexpr int hs_ref_unroll = HS_REF_UNROLL;
+
 struct HsConst {
   float nlo;            // -rc2_lo: t = d2 - rc2_lo is negative for a sure hit
   unsigned band_bits;   // bit pattern of the guard band width: 0 <= t <= width (compared as unsigned) is undecided
@@ -241,7 +246,7 @@ __device__ __forceinline__ unsigned hs_ref_pairs(const HsConst k, const int lane
   // tail is the sentinel record behind the window (far away: no hits, never in the band)
   uint32_t rp = s_ref + HS_REF_BYTES * (uint32_t)base;
   uint32_t ap = smem_addr(&s_acc[0][lane]), cp = smem_addr(&s_cnt[0][lane]);      // (counts: one byte per lane, <= SLOTS)
-#pragma unroll 1
+#pragma unroll hs_ref_unroll
   for (int r = 0; r < nref; r += 2, rp += 2u * HS_REF_BYTES, ap += 2u * 33u * 8u, cp += 2u * 36u) {
     const int il = base + r;
     pk2 nax, nay, naz, nbx, nby, nbz, uaz2, ubz2;
