@@ -71,7 +71,8 @@ def process_frame(frame, args, write_pdb):
 
 def main(argv=None):
     """The reference loops over the frame files one after the other (``calculate_local_ordering.py:39-76``).  Here
-    the files are block-sharded over the ranks when the script runs under ``torchrun`` (one process per GPU), every
+    the files are block-sharded over the ranks when the script runs under ``torchrun`` (one process per GPU; put ``--``
+    between the script path and its arguments: the launcher rejects ``--max`` as an abbreviation of its own options), every
     rank reads file k+1 on a host thread while file k is on its GPU, and rank 0 prints the per-frame results in the
     order of the command line - the reference's stdout, byte for byte, whatever the number of ranks."""
     import os
