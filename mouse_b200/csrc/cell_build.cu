@@ -202,9 +202,13 @@ __global__ void __launch_bounds__(256) cell_assign_kernel(const double *__restri
 // The half-shell sweeps hand out home cells through a ticket counter; a crowded cell (cost ~ occupancy^2) taken late
 // leaves the other warps idle at the end of the kernel.  The item rows are therefore written in eight occupancy
 // classes, heaviest first (longest-processing-time-first scheduling): class of a cell = its occupancy relative to the
-// mean, in steps of half the mean; empty cells last.  counters[16 + k] = cells of class k (histogram taken by the scan),
+// mean, in steps of half the mean; empty cells last.  counters[16 + k] = item rows of class k (histogram taken by the scan),
 // counters[24 + k] = rows of class k handed out so far; the scan leaves every cell's row in place of its occupancy.
 #define MOUSE_NCLASS 8
+// item rows of a cell: one, or one per window of `window` items (P2 sweep); window == 0: always one
+__device__ __forceinline__ int cell_rows(int count, int window) {
+  return (window > 0 && count > window) ? (count + window - 1) / window : 1;
+}
 __device__ __forceinline__ int cell_class(int count, float inv_half_mean) {
   if (count <= 0) return MOUSE_NCLASS - 1;
   const int q = (int)((float)count * inv_half_mean);       // occupancy in units of half the mean
@@ -213,9 +217,10 @@ __device__ __forceinline__ int cell_class(int count, float inv_half_mean) {
 
 // Rows of the 8 consecutive cells a thread of the scan owns (v = their occupancies, first cell `base`): the block
 // reserves one contiguous range per class (one global atomic per class and tile), its cells take consecutive rows
-// inside it.  The row overwrites the cell's occupancy in place (dead after the scan).  All threads of the block call.
+// inside it (a crowded cell takes one row per window).  The FIRST row overwrites the cell's occupancy in place (dead
+// after the scan).  All threads of the block call.
 __device__ __forceinline__ void lpt_rows(const int (&v)[8], int base, int ncells, int32_t *__restrict__ rows,
-                                         int64_t *counters, float inv_half_mean) {
+                                         int64_t *counters, float inv_half_mean, int window) {
   __shared__ int s_n[MOUSE_NCLASS], s_first[MOUSE_NCLASS];
   if (threadIdx.x < MOUSE_NCLASS) s_n[threadIdx.x] = 0;
   __syncthreads();
@@ -223,7 +228,7 @@ __device__ __forceinline__ void lpt_rows(const int (&v)[8], int base, int ncells
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     cls[k] = cell_class(v[k], inv_half_mean);
-    rk[k] = base + k < ncells ? atomicAdd(&s_n[cls[k]], 1) : 0;
+    rk[k] = base + k < ncells ? atomicAdd(&s_n[cls[k]], cell_rows(v[k], window)) : 0;
   }
   __syncthreads();
   if (threadIdx.x < MOUSE_NCLASS) {
@@ -242,7 +247,7 @@ __device__ __forceinline__ void lpt_rows(const int (&v)[8], int base, int ncells
 // ---- exclusive scan of cell_count[0..nc) -> cell_start, three small kernels ----------------
 __global__ void __launch_bounds__(256) scan_reduce_kernel(const int32_t *__restrict__ in, int nc,
                                                           int32_t *__restrict__ block_sums, int64_t *counters,
-                                                          float inv_half_mean) {
+                                                          float inv_half_mean, int window) {
   __shared__ int s_warp[8];
   __shared__ int s_hist[MOUSE_NCLASS];
   if (threadIdx.x < MOUSE_NCLASS) s_hist[threadIdx.x] = 0;
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(256) scan_reduce_kernel(const int32_t *__restr
     if (c < nc - 1) {      // (the last entry of the array is the unused total slot, not a cell)
       const int v = in[c];
       sum += v;
-      atomicAdd(&s_hist[cell_class(v, inv_half_mean)], 1);
+      atomicAdd(&s_hist[cell_class(v, inv_half_mean)], cell_rows(v, window));
     }
   }
   __syncthreads();
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(1024) scan_top_kernel(int32_t *__restrict__ bl
 __global__ void __launch_bounds__(256) scan_apply_kernel(int32_t *in, int nc,
                                                          const int32_t *__restrict__ block_offs,
                                                          int32_t *__restrict__ out, int64_t *counters,
-                                                         float inv_half_mean) {
+                                                         float inv_half_mean, int window) {
   // each thread owns 8 consecutive entries of the tile
   __shared__ int s_warp[8];
   int base = blockIdx.x * MOUSE_SCAN_TILE + threadIdx.x * 8;
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(int32_t *in, int nc,
     if (c < nc) out[c] = run;
     run += v[k];
   }
-  lpt_rows(v, base, nc - 1, in, counters, inv_half_mean);    // in[c] becomes the cell's row in the item table
+  lpt_rows(v, base, nc - 1, in, counters, inv_half_mean, window);    // in[c] becomes the cell's first row in the item table
 }
 
 // ---- exclusive scan, second kernel of two: every block sums the tile totals in front of it (a few dozen values)
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(int32_t *in, int nc,
 __global__ void __launch_bounds__(256) scan_apply2_kernel(int32_t *in, int nc,
                                                           const int32_t *__restrict__ tile_sums,
                                                           int32_t *__restrict__ out, int64_t *counters,
-                                                          float inv_half_mean) {
+                                                          float inv_half_mean, int window) {
   __shared__ int s_warp[8];
   __shared__ int s_off;
   // offset of this tile = sum of the totals of all tiles before it
@@ -390,7 +395,7 @@ __global__ void __launch_bounds__(256) scan_apply2_kernel(int32_t *in, int nc,
     if (c < nc) out[c] = run;
     run += v[k];
   }
-  lpt_rows(v, base, nc - 1, in, counters, inv_half_mean);    // in[c] becomes the cell's row in the item table
+  lpt_rows(v, base, nc - 1, in, counters, inv_half_mean, window);    // in[c] becomes the cell's first row in the item table
 }
 
 // ---- scatter the item index into its cell (arrival order); the payload moves once, in cell_place_kernel -----
@@ -474,18 +479,19 @@ template <int MODE>
 __global__ void __launch_bounds__(128) cell_items_kernel(int ncell, GridDev g, const int32_t *__restrict__ cell_start,
                                                          const uint32_t *__restrict__ cell_bbox,
                                                          const int32_t *__restrict__ cell_row,
-                                                         int32_t *__restrict__ items) {
+                                                         int32_t *__restrict__ items, int window) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncell) return;
   const int s = cell_start[c], nc = cell_start[c + 1] - s;
   int4 *row = (int4 *)(items + (size_t)cell_row[c] * HS_ITEM_INTS);
   if (nc <= 0) {       // an empty cell only needs its size (the sweeps skip it)
     row[7] = make_int4(0, 0, 0, 0);
+    row[10] = make_int4(0, 0, 0, 0);
     return;
   }
   int cx, cy, cz;
   hs_cell_coords(g, c, cx, cy, cz);
-  int v[HS_ITEM_INTS];
+  int v[40];
   int off = 0;
 #pragma unroll
   for (int L = 0; L < 10; ++L) {
@@ -516,7 +522,17 @@ __global__ void __launch_bounds__(128) cell_items_kernel(int ncell, GridDev g, c
     v[32 + a] = MODE == 0 ? __float_as_int(mouse_key_float(~cell_bbox[(size_t)c * 6 + 3 + a])) : 0;
   }
 #pragma unroll
-  for (int q = 0; q < HS_ITEM_INTS / 4; ++q) row[q] = make_int4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  for (int q = 0; q < 10; ++q) row[q] = make_int4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  row[10] = make_int4(0, 0, 0, 0);
+  // a crowded cell has one row per window of references (consecutive rows: the same ranges, their own window index), so
+  // that its windows are separate work items - several warps share the cell instead of one warp sweeping it alone
+  const int nw = cell_rows(nc, window);
+  for (int w = 1; w < nw; ++w) {
+    int4 *rw = row + (size_t)w * (HS_ITEM_INTS / 4);
+#pragma unroll
+    for (int q = 0; q < 10; ++q) rw[q] = make_int4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    rw[10] = make_int4(w, 0, 0, 0);
+  }
 }
 
 // ---- K1 + cell assignment + output initialisation in one pass (mouse_p2_frame) -------------------------------
@@ -595,17 +611,18 @@ static int cell_build_tail(int mode, const uint8_t *ref_mask, int64_t n, const m
   int tiles = (nc + MOUSE_SCAN_TILE - 1) / MOUSE_SCAN_TILE;
   // occupancy classes of the item rows (heaviest cells first): in units of half the mean occupancy
   const float inv_half_mean = (float)(2.0 * (double)grid->ncell / (double)(n > 0 ? n : 1));
+  const int window = mode == 0 ? MOUSE_WINDOW : 0;      // P2: one item row per window of references; RDF: one per cell
   if (tiles <= 4096) {   // the apply kernel sums the tile totals in front of its tile itself
-    scan_reduce_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.counters, inv_half_mean);
+    scan_reduce_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.counters, inv_half_mean, window);
     MOUSE_LAUNCH_CHECK("scan_reduce_kernel");
-    scan_apply2_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start, w.counters, inv_half_mean);
+    scan_apply2_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start, w.counters, inv_half_mean, window);
     MOUSE_LAUNCH_CHECK("scan_apply2_kernel");
   } else {
-    scan_reduce_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.counters, inv_half_mean);
+    scan_reduce_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.counters, inv_half_mean, window);
     MOUSE_LAUNCH_CHECK("scan_reduce_kernel");
     scan_top_kernel<<<1, 1024, 0, st>>>(w.scan_blocks, tiles);
     MOUSE_LAUNCH_CHECK("scan_top_kernel");
-    scan_apply_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start, w.counters, inv_half_mean);
+    scan_apply_kernel<<<tiles, 256, 0, st>>>(w.cell_count, nc, w.scan_blocks, w.cell_start, w.counters, inv_half_mean, window);
     MOUSE_LAUNCH_CHECK("scan_apply_kernel");
   }
   if (n > 0) {
@@ -623,9 +640,9 @@ static int cell_build_tail(int mode, const uint8_t *ref_mask, int64_t n, const m
   if (grid->fast) {      // (also for an empty list: the sweeps read every cell's row)
     const unsigned cb = (unsigned)((grid->ncell + 127) / 128);
     if (mode == 0)
-      cell_items_kernel<0><<<cb, 128, 0, st>>>(grid->ncell, g, w.cell_start, w.cell_bbox, w.cell_count, w.items);
+      cell_items_kernel<0><<<cb, 128, 0, st>>>(grid->ncell, g, w.cell_start, w.cell_bbox, w.cell_count, w.items, window);
     else
-      cell_items_kernel<1><<<cb, 128, 0, st>>>(grid->ncell, g, w.cell_start, w.cell_bbox, w.cell_count, w.items);
+      cell_items_kernel<1><<<cb, 128, 0, st>>>(grid->ncell, g, w.cell_start, w.cell_bbox, w.cell_count, w.items, window);
     MOUSE_LAUNCH_CHECK("cell_items_kernel");
   }
   return MOUSE_OK;

@@ -51,7 +51,8 @@ struct Workspace {
                          //             atomicMax: [0..2] upper corner, [3..5] lower corner (complemented keys); 0 = empty
   int32_t *cell_start;   // [ncell+1]   exclusive scan; cell_start[ncell] = items in the list
   int32_t *scan_blocks;  // [scan_nblocks+1]
-  int32_t *items;        // [ncell][40] item table of the half-shell sweeps (ranges of the 14 cells, see half_shell.cuh)
+  int32_t *items;        // [ncell + n / 32 + 1][44] item rows of the half-shell sweeps (ranges of the 14 cells, see half_shell.cuh):
+                         //               one row per cell (RDF) or per window of MOUSE_WINDOW references of a cell (P2)
   // per item, original order
   int32_t *cell_of;      // [n] cell id or -1 (not in the list); after the build: sorted slot | reference bit << 30
                          //     (inverse permutation, still -1 for items outside the list)
@@ -79,6 +80,7 @@ struct Workspace {
 };
 
 #define MOUSE_REDUCE_BLOCKS 1024
+#define MOUSE_WINDOW 32      // references of a home cell one work item of the P2 sweep takes (one item row per window)
 #define MOUSE_SCAN_TILE 2048
 #define MOUSE_MAX_BINS 8192
 
@@ -100,7 +102,7 @@ static inline Workspace mouse_carve(void *ws, int64_t n, int32_t ncell) {
   CARVE(cell_count, int32_t, nc)
   CARVE(cell_bbox, uint32_t, 6 * nc)
   CARVE(cell_start, int32_t, nc)
-  CARVE(items, int32_t, 40 * nc)
+  CARVE(items, int32_t, 44 * (nc + nn / MOUSE_WINDOW + 1))
   CARVE(cell_of, int32_t, nn)
   CARVE(rank_of, int32_t, nn)
   CARVE(rec_tmp, Rec, nn)

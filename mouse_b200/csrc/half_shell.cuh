@@ -39,6 +39,7 @@ struct HsItem {
   int home, hs, nhome, T;   // home cell, its first sorted slot, its bonds, candidates of the 14 cells
   int rsrc, rlen, rt;       // lane L < 10: range L of the candidate concatenation (first slot, length, offset t)
   float hx, hy, hz;         // home cell centre (frame of the stored FP32 coordinates)
+  int win;                  // window of references this item covers: [win * MOUSE_WINDOW, ...) of the home cell (P2)
   int boundary;             // some neighbour cell is a periodic image
 };
 
@@ -100,8 +101,9 @@ __device__ __forceinline__ void hs_range_cells(const GridDev &g, int cx, int cy,
 //   [0..9] first sorted slot of range L, [10..19] its length, [20..29] its offset t in the candidate concatenation,
 //   [30] bonds / atoms in the home cell | boundary << 30 (some neighbour cell is a periodic image),
 //   [32..34] / [35..37] lower / upper corner of the bounding box of the cell's own items (FP32 bit patterns, frame of
-//   the stored coordinates: wrapped - L/2), [38], [39], [31] the cell centre x, y, z in the same frame.
-#define HS_ITEM_INTS 40
+//   the stored coordinates: wrapped - L/2), [38], [39], [31] the cell centre x, y, z in the same frame,
+//   [40] window index of the row (P2: a cell with more than MOUSE_WINDOW items has one row per window), [41..43] unused.
+#define HS_ITEM_INTS 44
 
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
@@ -137,6 +139,7 @@ __device__ __forceinline__ bool hs_finalize(const GridDev &g, int lane, int tk, 
   const int T = s_raw[29] + s_raw[19];
   const int size = s_raw[30];
   const float hx = __int_as_float(s_raw[38]), hy = __int_as_float(s_raw[39]), hz = __int_as_float(s_raw[31]);
+  const int win = s_raw[40];
   __syncwarp();
   const int nhome = size & 0x3fffffff;
   it.home = tk;
@@ -150,5 +153,6 @@ __device__ __forceinline__ bool hs_finalize(const GridDev &g, int lane, int tk, 
   it.hy = hy;
   it.hz = hz;
   it.boundary = (size >> 30) & 1;
+  it.win = win;
   return nhome > 0;
 }

@@ -81,7 +81,7 @@ __device__ __forceinline__ double exact_pair(const int32_t *__restrict__ idx, co
 
 // ------------------------------------------------------------------ half-shell fast sweep
 #ifndef HS_MAXHOME
-#define HS_MAXHOME 32      // home cells with more bonds are decided pair by pair, exactly (hs_oversize)
+#define HS_MAXHOME MOUSE_WINDOW   // references per work item: a home cell with more bonds has one item row per window
 #endif
 #ifndef HS_GRP
 #define HS_GRP 8           // references reduced together (transposed reduction through shared memory)
@@ -561,6 +561,8 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
   //   stage 1  ticket  = atomicAdd(home-cell counter)           (tkP: issued one iteration before it is used)
   //   stage 2  item row of the ticket's home cell -> s_raw      (tkA: cp.async issued one iteration before stage 3)
   //   stage 3  finalize the row, arm the landing zone (TMA)     (one iteration before the data is consumed)
+  // item rows of the frame: the sum of the class histogram the scan left in counters[16..23]
+  const int nrows = warp_sum(lane < 8 ? (int)a.counters[16 + lane] : 0);
   int tkA, tkP = 0;
   {
     int t0 = 0;
@@ -569,21 +571,22 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
       tkP = (int)atomicAdd((unsigned int *)&a.counters[C_TICKET], 1u);
     }
     tkA = __shfl_sync(MOUSE_FULL_MASK, t0, 0);
-    if (tkA < a.g.ncell) hs_raw_issue(a.items, lane, tkA, s_raw);
+    if (tkA < nrows) hs_raw_issue(a.items, lane, tkA, s_raw);
   }
   // next non-empty, regular home cell (its centre and bounding box go to s_bb); false when the grid is exhausted
   auto advance = [&](HsItem &it) -> bool {
     for (;;) {
-      if (tkA >= a.g.ncell) return false;
+      if (tkA >= nrows) return false;
       const bool nonempty = hs_finalize(a.g, lane, tkA, s_raw, it);
       const float bbv = lane < 6 ? __int_as_float(s_raw[32 + lane]) : 0.0f;
       __syncwarp();
       tkA = __shfl_sync(MOUSE_FULL_MASK, tkP, 0);
       if (lane == 0) tkP = (int)atomicAdd((unsigned int *)&a.counters[C_TICKET], 1u);
-      if (tkA < a.g.ncell) hs_raw_issue(a.items, lane, tkA, s_raw);
+      if (tkA < nrows) hs_raw_issue(a.items, lane, tkA, s_raw);
       if (!nonempty) continue;
       if (it.T > HS_MAXT) {
-        hs_oversize(a.R, a.counters, a.fix_list, a.fix_cap, a.same_molecule, lane, it.hs, it.nhome, it.rsrc, it.rlen, it.rt);
+        if (it.win == 0)       // (once per cell, not once per window row)
+          hs_oversize(a.R, a.counters, a.fix_list, a.fix_cap, a.same_molecule, lane, it.hs, it.nhome, it.rsrc, it.rlen, it.rt);
         continue;
       }
       if (lane < 6) s_bb[3 + lane] = bbv;
@@ -596,14 +599,16 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     }
   };
 
-  // A home cell with more than HS_MAXHOME bonds is taken in windows of HS_MAXHOME references [rb, rb + HS_MAXHOME):
-  // each window is a pass over the whole candidate concatenation of its own, in which the survivors in front of the
-  // window (home-cell bonds j < rb <= i: those pairs belong to the earlier windows) are skipped.
+  // A home cell with more than HS_MAXHOME bonds is taken in windows of HS_MAXHOME references [rb, rb + HS_MAXHOME),
+  // one ITEM ROW per window (cell_items_kernel): each window is a pass over the candidate concatenation of its own
+  // that starts in the chunk holding its references and skips the survivors in front of the window (home-cell bonds
+  // j < rb <= i: those pairs belong to the earlier windows).  The windows of a crowded cell are separate tickets, so
+  // several warps share the cell (one warp sweeping a 65-bond cell alone takes as long as a whole 250k-bond frame).
   HsItem cur;
   bool have = advance(cur);
-  int ch = 0, sp = 0, M = 0, rb = 0;
+  int ch = have ? (cur.win * HS_MAXHOME) / LZ : 0, sp = 0, M = 0, rb = have ? cur.win * HS_MAXHOME : 0;
   bool fresh = true;
-  if (have) issue(cur, 0);
+  if (have) issue(cur, ch);
 
   while (have) {
     if (fresh) {
@@ -684,13 +689,10 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     int nch = ch + 1, nrb = rb;
     if (last) {
       HsItem nxt = cur;
-      if (nch * LZ >= cur.T) {
-        nch = (rb + HS_MAXHOME < cur.nhome) ? (rb + HS_MAXHOME) / LZ : 0;   // the chunk the next window starts in
-        nrb = rb + HS_MAXHOME;               // next window of this home cell, or the next home cell
-        if (nrb >= cur.nhome) {
-          nrb = 0;
-          have = advance(nxt);
-        }
+      if (nch * LZ >= cur.T) {               // this window is complete: next item row
+        have = advance(nxt);
+        nrb = have ? nxt.win * HS_MAXHOME : 0;
+        nch = nrb / LZ;                      // the chunk the window starts in
       }
       if (have) {
         issue(nxt, nch);
@@ -700,7 +702,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
           s_next[2][lane] = nxt.rt;
         }
         if (lane == 0) {
-          s_nexti[0] = nxt.home;
+          s_nexti[0] = nxt.win;
           s_nexti[1] = nxt.hs;
           s_nexti[2] = nxt.nhome;
           s_nexti[3] = nxt.T;
@@ -730,7 +732,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     cur.rsrc = s_next[0][lane < 10 ? lane : 0];
     cur.rlen = lane < 10 ? s_next[1][lane] : 0;
     cur.rt = s_next[2][lane < 10 ? lane : 0];
-    cur.home = s_nexti[0];
+    cur.win = s_nexti[0];
     cur.hs = s_nexti[1];
     cur.nhome = s_nexti[2];
     cur.T = s_nexti[3];
@@ -943,7 +945,7 @@ static void launch_half_one(const SweepArgs &a, int variant, int warps_override,
   int per_sm = f->per_sm[variant];
   if (warps_override > 0 && warps_override < per_sm) per_sm = warps_override;
   int blocks = f->sms * per_sm;
-  if (blocks > a.g.ncell) blocks = a.g.ncell;
+  if (blocks > a.g.ncell) blocks = a.g.ncell;     // (at least one row per cell)
   p2_sweep_half_kernel<SLOTS, EXCL><<<blocks, 32, 0, st>>>(a);
 }
 
