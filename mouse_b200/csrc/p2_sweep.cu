@@ -955,12 +955,14 @@ static void launch_half(const SweepArgs &a, bool excl_mol, int variant, int warp
   else launch_half_one<SLOTS, false>(a, 2 * variant, warps_override, st);
 }
 
-// The FP32-filter half-shell sweep applies when the grid allows it (>= 3 cells per axis, small guard band) and the
-// cells are not crowded: a home cell's own bonds must fit the landing zone (HS_LZ records), so frames with more than
-// HS_LZ / 2 items per cell on average go to the all-FP64 sweep directly instead of deciding most cells pair by pair.
+// The FP32-filter half-shell sweep applies when the grid allows it (>= 3 cells per axis, small guard band).  Crowded
+// cells are taken in windows of references, one item row each, so the fast path stays ahead of the all-FP64 sweep far
+// beyond the landing zone (250k bonds at rc = 7 sigma, 343 per cell: 2.4 ms against 15.4 ms; rc = 9 sigma, 729 per
+// cell: 6.8 against 28.9 ms); the limit is the candidate count a cell's fixed-point accumulators are sized for
+// (HS_MAXT = 16 384 per home cell): frames with more than 512 items per cell on average go to the all-FP64 sweep.
 int mouse_p2_uses_fast(const mouse_grid_t *grid, int64_t n, uint32_t flags, bool lists) {
   if (!grid->fast || lists || (flags & (MOUSE_FORCE_EXACT | MOUSE_NO_CUTOFF))) return 0;
-  return (flags & MOUSE_FORCE_FAST) || (double)n <= 0.5 * HS_LZ * (double)grid->ncell;
+  return (flags & MOUSE_FORCE_FAST) || (double)n <= 512.0 * (double)grid->ncell;
 }
 
 // frame_mode 0: stand-alone sweep (outputs zeroed here, accumulators converted by p2_finish_kernel);

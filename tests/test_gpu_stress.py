@@ -119,3 +119,19 @@ def test_single_cell_frame_is_ranked_in_parallel():
     t = res.totals_dict()
     assert t["n_pairs"] == melt.n_bonds * (melt.n_bonds - 1)
     assert int(res.count.min().item()) == melt.n_bonds - 1 and int(res.count.max().item()) == melt.n_bonds - 1
+
+
+@pytest.mark.gpu
+def test_very_crowded_grid_takes_the_fast_path_by_itself():
+    """343 bonds per cell (rc = 7 sigma on a 60k-bond melt): the library picks the fast sweep (window rows), the result
+    equals the all-FP64 sweep."""
+    import torch
+    from mouse_b200 import engine
+    from mouse_b200.melt import make_melt
+    melt = make_melt(600, 101, seed=5)
+    molb = melt.mol[melt.bond_atoms[:, 0]]
+    res = engine.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, 7.0, same_molecule=False)
+    ex = engine.p2_frame(melt.positions, melt.bond_atoms, molb, melt.box, 7.0, same_molecule=False, exact=True)
+    assert res.grid.fast == 1 and res.totals_dict()["n_band"] > 0          # the fast path ran (it has a guard band)
+    assert torch.equal(res.count, ex.count)
+    assert float((res.mean - ex.mean).abs().max().item()) < 1e-13
