@@ -160,9 +160,6 @@ static int cells_build_t(cells_t *g, const double *xyz, int64_t n, const double 
   return 0;
 }
 
-static int cells_build(cells_t *g, const double *xyz, int64_t n, const double *box, double rc) {
-  return cells_build_t(g, xyz, n, box, NULL, rc);
-}
 
 static void cells_free(cells_t *g) {
   free(g->start);
