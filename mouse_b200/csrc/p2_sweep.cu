@@ -103,11 +103,8 @@ __device__ __forceinline__ double exact_pair(const int32_t *__restrict__ idx, co
 // (no function call and no extra state inside the sweep: its register budget is spent on the candidates).
 __device__ __forceinline__ void fix_append(int64_t *counters, int2 *fix_list, long long fix_cap, int si, int sj,
                                            int kind) {
-#ifdef HS_DEBUG_COUNT
-  atomicAdd((unsigned long long *)&counters[5 + (kind & 3)], 1ULL);   // (debug build only: 5..7 belong to the reduce)
-#endif
   const unsigned long long pos = atomicAdd((unsigned long long *)&counters[C_NFIX], 1ULL);
-  if (pos < (unsigned long long)fix_cap) fix_list[pos] = make_int2(si | ((kind & 1) << 31), sj);
+  if (pos < (unsigned long long)fix_cap) fix_list[pos] = make_int2(si | (kind << 31), sj);
   else counters[C_OVERFLOW] = 1;   // the exact sweep recomputes the whole frame
 }
 
