@@ -433,7 +433,7 @@ def _check_against_c_oracle(pos, bonds, mol, box, rc, same=True, nbr=None, ref=N
     return res, ora
 
 
-@pytest.mark.parametrize("n_cl", [150, 330, 700])
+@pytest.mark.parametrize("n_cl", [33, 64, 65, 150, 330, 700])
 def test_dense_cluster_oversize_home_cells_and_many_passes(n_cl):
     """One cell holds far more bonds than the fast sweep takes as references at a time: the cell is swept in windows of
     HS_MAXHOME references, each against all chunks of the candidate concatenation; with 330 bonds the home cell itself
@@ -449,7 +449,7 @@ def test_dense_cluster_oversize_home_cells_and_many_passes(n_cl):
     mol = (np.arange(len(ctr)) // 7).astype(np.int32)
     for same in (True, False):
         res, ora = _check_against_c_oracle(pos, bonds, mol, box, 1.5, same)
-        assert ora["count"].max() > 140        # the cluster really is dense
+        assert ora["count"].max() > min(140, n_cl - 10)        # the cluster really is dense
         c = _sweep_counters(res, len(bonds))
         assert c[4] == 0 and c[3] < 500
 
