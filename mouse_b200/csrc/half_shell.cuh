@@ -97,7 +97,8 @@ __device__ __forceinline__ void hs_range_cells(const GridDev &g, int cx, int cy,
   }
 }
 
-// Per-cell item table (40 ints per cell, written by cell_items_kernel, one thread per cell, read by the sweeps):
+// Item rows (44 ints each, written by cell_items_kernel - one thread per cell - in the order the scan assigned:
+// heaviest cells first; read by the sweeps through a ticket counter):
 //   [0..9] first sorted slot of range L, [10..19] its length, [20..29] its offset t in the candidate concatenation,
 //   [30] bonds / atoms in the home cell | boundary << 30 (some neighbour cell is a periodic image),
 //   [32..34] / [35..37] lower / upper corner of the bounding box of the cell's own items (FP32 bit patterns, frame of

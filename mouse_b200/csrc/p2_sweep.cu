@@ -3,25 +3,26 @@
 //
 //  * p2_sweep_half_kernel - the fast path.  Half shell (Newton's third law): every unordered pair of
 //    bonds is decided ONCE - home cell against itself (j > i) and against its 13 "forward" neighbour
-//    cells - and its cos^2 is added to both partners.  One warp per home cell, persistent warps with a
-//    ticket counter.  The candidates of the 14 cells are up to 10 contiguous ranges of the cell-sorted
-//    arrays: they are fetched with 1-D TMA bulk copies (cp.async.bulk + mbarrier) into a shared-memory
-//    landing zone, moved into REGISTERS (lane t % 32, slot t / 32: FP32 wrapped coordinates as packed
-//    pairs, FP64 unit vectors) and the landing zone is immediately re-armed with the NEXT home cell's
-//    copies, which then overlap the arithmetic.  The references are taken in groups of eight, two per
-//    loop iteration (warp-uniform loop, broadcast LDS): packed f32x2 distance test against the guard
-//    band, dense FP64 cos^2 = (u_i . u_j)^2 for every slot, branch-free accumulation into the
-//    reference's and the candidate's registers (the hit predicate clears the weight).  Candidates
-//    inside the FP32 guard band around rc^2, and sure hits with |u_i . u_j| < 1e-9 (the reference masks
-//    cos^2 == 0, :113), are NOT decided in FP32: they are appended to a pair list and decided with the
-//    reference's exact un-fused FP64 expressions by p2_fixup_kernel.  Before the reference
-//    loop the candidates farther than the cutoff from the bounding box of the home cell's bonds are dropped
-//    (hs_cull): 220 -> 148 candidates per reference on the 1M-bond melt.  Sums are merged across home cells
-//    as 2^-47 fixed point with integer atomics: exact, order independent -> run-to-run bit-identical.
+//    cells - and its cos^2 is added to both partners.  A work item is one ITEM ROW (half_shell.cuh): a home cell, or
+//    one window of 32 references of a crowded home cell; one warp per item, persistent warps with a ticket counter,
+//    rows ordered heaviest cells first.  The candidates of the 14 cells are up to 10 contiguous ranges of the
+//    cell-sorted arrays: they are fetched with 1-D TMA bulk copies (cp.async.bulk + mbarrier) into a shared-memory
+//    landing zone (a chunk of 256 records), culled (hs_cull: candidates farther than the cutoff from the bounding box
+//    of the home cell's bonds are dropped, 220 -> 148 per reference on the 1M-bond melt), moved into REGISTERS (lane
+//    t % 32, slot t / 32: FP32 wrapped coordinates as packed pairs, FP64 unit vectors), and the landing zone is
+//    immediately re-armed with the NEXT chunk / item, whose copies then overlap the arithmetic.  The references are
+//    taken in groups of eight, two per loop iteration (warp-uniform loop, broadcast LDS, one loop body per number of
+//    slots in use): packed f32x2 distance test against the guard band, dense FP64 cos^2 = (u_i . u_j)^2 for every
+//    slot, branch-free accumulation into the reference's and the candidate's registers (the hit mask - the sign of
+//    d2 - rc2_lo - clears the weight and is subtracted from the counts).  Candidates inside the FP32 guard band around
+//    rc^2, and sure hits with |u_i . u_j| < 1e-9 (the reference masks cos^2 == 0, :113), are NOT decided in FP32:
+//    they are appended to a pair list and decided with the reference's exact un-fused FP64 expressions by
+//    p2_fixup_kernel.  Sums are merged across items as 2^-47 fixed point with integer atomics: exact, order
+//    independent -> run-to-run bit-identical.
 //  * p2_sweep_exact_kernel - one thread per reference, all FP64, literally the reference's
 //    expression per candidate.  Valid for ANY grid (fewer than 3 cells on an axis, rcut < 0,
-//    rmax == 0 -> half diagonal, crowded cells); it also extracts the pair lists and is the automatic
-//    fallback when the pair list of the fast path overflows.
+//    rmax == 0 -> half diagonal, more than 512 items per cell); it also extracts the pair lists, and its body is the
+//    automatic fallback (inside the fixup launch) when the pair list of the fast path overflows.
 #include <type_traits>
 
 #include "half_shell.cuh"
