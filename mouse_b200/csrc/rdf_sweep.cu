@@ -101,6 +101,10 @@ __global__ void __launch_bounds__(128) rdf_sweep_exact_kernel(const RdfArgs a) {
 // sqrt(s) is >= edges[k] (rdf_thresholds_kernel), so "edges[k] <= sqrt(s) < edges[k+1]" is decided by comparing s
 // itself - bit-exact with numpy.histogram's rule, including range ends and the closed last bin.
 #define RH_WARPS 12
+#ifndef RH_SLOTS
+#define RH_SLOTS 6          // register-resident candidate slots per lane (candidates per landing-zone pass = 32 * RH_SLOTS):
+                            // 6 -> 12 warps per SM (4M beads: 11.6 ms; 8 slots, 11 warps: 11.9 ms; 4 slots: 12.2 ms)
+#endif
 #ifndef RH_WALK
 #define RH_WALK 2          // queued hits per lane and walk round
 #endif
@@ -456,13 +460,13 @@ template <bool SAME_MOL, bool ONE_TYPE, bool SMEM_HIST>
 static void launch_rdf_half(const RdfHalfArgs &h, int ncell, size_t smem, cudaStream_t st) {
   // (no cached state: the library holds nothing per process; the query costs microseconds next to a 10 ms sweep)
   int blocks_per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rdf_sweep_half_kernel<8, SAME_MOL, ONE_TYPE, SMEM_HIST>, 32,
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rdf_sweep_half_kernel<RH_SLOTS, SAME_MOL, ONE_TYPE, SMEM_HIST>, 32,
                                                 smem);
   if (blocks_per_sm < 1) blocks_per_sm = 1;
   const int sms = mouse_num_sms();
   int blocks = sms * blocks_per_sm;
   if (blocks > ncell) blocks = ncell;
-  rdf_sweep_half_kernel<8, SAME_MOL, ONE_TYPE, SMEM_HIST><<<blocks, 32, smem, st>>>(h);
+  rdf_sweep_half_kernel<RH_SLOTS, SAME_MOL, ONE_TYPE, SMEM_HIST><<<blocks, 32, smem, st>>>(h);
 }
 
 int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, int32_t ntypes,
