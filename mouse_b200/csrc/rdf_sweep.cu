@@ -302,11 +302,18 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
           double tx = __dsub_rn(uj[r].x, ui[r].x), ty = __dsub_rn(uj[r].y, ui[r].y), tz = __dsub_rn(uj[r].z, ui[r].z);
           // dr - L * around(dr / L): around() is 0 whenever |dr| <= L / 2 (ordering_functions.py:72-74); one
           // rare branch for coordinates that were not wrapped into the box
-          // (measured: the branch-free form dr - L * n, n in {-1, 0, 1}, costs nine more FP64-pipe operations per hit
-          // and makes the sweep 22 % slower than this branch, which boundary cells do take)
+          // (measured: a branch-free dr - L * n for EVERY hit costs nine more FP64-pipe operations per hit and makes the
+          // sweep 22 % slower; inside the branch, which boundary cells do take, it replaces three divisions)
           if (!(fabs(tx) <= hLx && fabs(ty) <= hLy && fabs(tz) <= hLz)) {
             if (a.g.tri) {      // (inside the brick the triclinic minimum image is the identity, too)
               mouse_min_image_tri(tx, ty, tz, a.g.box, a.g.tilt);
+            } else if (fabs(tx) < 2.5 * hLx && fabs(ty) < 2.5 * hLy && fabs(tz) < 2.5 * hLz) {
+              // around(dr / L) is +-1 for L / 2 < |dr| < 5 L / 4 (dr > L/2 means dr >= L/2 (1 + 2^-52): the rounded
+              // quotient is >= 0.5 + 2^-53 > 0.5; exactly L / 2 rounds half-to-even to 0) and 0 below: dr - L * n with
+              // an exact L * n and one rounded subtraction, no division (pairs across the periodic boundary)
+              tx = __dsub_rn(tx, tx > hLx ? Lx : (tx < -hLx ? -Lx : 0.0));
+              ty = __dsub_rn(ty, ty > hLy ? Ly : (ty < -hLy ? -Ly : 0.0));
+              tz = __dsub_rn(tz, tz > hLz ? Lz : (tz < -hLz ? -Lz : 0.0));
             } else {
               tx = mouse_trim(tx, Lx);
               ty = mouse_trim(ty, Ly);
@@ -494,10 +501,11 @@ int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, 
     h.scale = (float)((double)nbin / (grid->rcut - w.rdf_first));
     h.r2hi = nextafterf((float)(grid->rc2 * (1.0 + (double)grid->guard)), 3.0e38f);
     // error of the FP32 bin estimate in bins: sqrt through (float)s * rsqrt.approx (relative < 4e-7 of a value <= last),
-    // the subtraction and the scaling (a few ulps of a value <= nbin); delta = 8 x that bound, at least 1e-3
+    // the subtraction and the scaling (a few ulps of a value <= nbin); delta = 3 x that (already generous) bound, at
+    // least 1e-3
     {
       const double width = (grid->rcut - w.rdf_first) / (double)nbin;
-      double d = 8.0 * (4.0e-7 * grid->rcut / width + 3.0e-7 * (double)nbin);
+      double d = 3.0 * (4.0e-7 * grid->rcut / width + 3.0e-7 * (double)nbin);
       if (d < 1.0e-3) d = 1.0e-3;
       h.bin_delta = (float)d;      // (>= 0.5: every hit takes the exact check)
     }
