@@ -108,7 +108,10 @@ __global__ void __launch_bounds__(128) rdf_sweep_exact_kernel(const RdfArgs a) {
 #ifndef RH_WALK
 #define RH_WALK 2          // queued hits per lane and walk round
 #endif
-#define RH_QUEUE 256      // ring capacity (power of two); one reference adds at most SLOTS * 32 = 256 entries
+#ifndef RH_QUEUE
+#define RH_QUEUE 512      // ring capacity (power of two): the < 64 entries a walk leaves behind plus the 2 * SLOTS * 32 = 384 a
+                          // pair of reference atoms can add always fit - no capacity check in front of the push
+#endif
 
 struct RdfHalfArgs {
   GridDev g;
@@ -421,21 +424,27 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
             }
             __syncwarp();
           };
-          int tot = __reduce_add_sync(MOUSE_FULL_MASK, __popc(maska) + __popc(maskb));
-          if (qn + tot > RH_QUEUE) {      // cannot happen below ~3 hits per lane and reference
-            drain();
-            if (tot > RH_QUEUE) {         // more than 4 per lane and reference: one reference at a time
-              const int ta = __reduce_add_sync(MOUSE_FULL_MASK, __popc(maska));
-              push(maska, 0u);
-              qn = ta;
+          if (RH_QUEUE >= 64 + 2 * NC) {        // (compile time) the ring cannot overflow: the new length is read back
+            push(maska, maskb);
+            __syncwarp();
+            qn = (int)(*(volatile unsigned *)&s_qt - qh);
+          } else {
+            int tot = __reduce_add_sync(MOUSE_FULL_MASK, __popc(maska) + __popc(maskb));
+            if (qn + tot > RH_QUEUE) {      // cannot happen below ~3 hits per lane and reference
               drain();
-              maska = 0u;
-              tot -= ta;
+              if (tot > RH_QUEUE) {         // more than 4 per lane and reference: one reference at a time
+                const int ta = __reduce_add_sync(MOUSE_FULL_MASK, __popc(maska));
+                push(maska, 0u);
+                qn = ta;
+                drain();
+                maska = 0u;
+                tot -= ta;
+              }
             }
+            push(maska, maskb);
+            qn += tot;
+            __syncwarp();
           }
-          push(maska, maskb);
-          qn += tot;
-          __syncwarp();
           // ---- full rounds of 64 queued hits: exact FP64 distance, exact bin, two hits per lane
           while (qn >= 32 * RH_WALK) {
             walk(32 * RH_WALK, buf);
