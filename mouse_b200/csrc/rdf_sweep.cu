@@ -100,13 +100,16 @@ __global__ void __launch_bounds__(128) rdf_sweep_exact_kernel(const RdfArgs a) {
 // The bin is found WITHOUT sqrt / division in FP64: thr[k] is the smallest double s whose correctly rounded
 // sqrt(s) is >= edges[k] (rdf_thresholds_kernel), so "edges[k] <= sqrt(s) < edges[k+1]" is decided by comparing s
 // itself - bit-exact with numpy.histogram's rule, including range ends and the closed last bin.
-#define RH_WARPS 12
+#define RH_WARPS 13
 #ifndef RH_SLOTS
 #define RH_SLOTS 6          // register-resident candidate slots per lane (candidates per landing-zone pass = 32 * RH_SLOTS):
                             // 6 -> 12 warps per SM (4M beads: 11.6 ms; 8 slots, 11 warps: 11.9 ms; 4 slots: 12.2 ms)
 #endif
 #ifndef RH_WALK
 #define RH_WALK 2          // queued hits per lane and walk round
+#endif
+#ifndef RH_HOMEBUF
+#define RH_HOMEBUF 1        // buffers of reference atoms in shared memory (1: 13 warps per SM fit; 2: double buffered)
 #endif
 #ifndef RH_QUEUE
 #define RH_QUEUE 512      // ring capacity (power of two): the < 64 entries a walk leaves behind plus the 2 * SLOTS * 32 = 384 a
@@ -178,8 +181,8 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
   constexpr int NPAIR = SLOTS / 2;
   extern __shared__ unsigned int s_hist[];            // [npairs * nbin] when use_smem
   __shared__ __align__(128) Rec s_land[NC];           // TMA landing zone; stays valid for the whole pass
-  __shared__ float4 s_homeP[2][32];                   // reference atoms of the home cell, 32 at a time, double buffered
-  __shared__ double4 s_homeU[2][32];
+  __shared__ float4 s_homeP[RH_HOMEBUF][32];          // reference atoms of the home cell, 32 at a time (the next 32 wait
+  __shared__ double4 s_homeU[RH_HOMEBUF][32];         // in registers until the queue of the current ones is drained)
   __shared__ __align__(16) int s_raw[HS_ITEM_INTS];
   __shared__ unsigned short s_q[RH_QUEUE];            // hit queue: reference (5 bits) | slot << 5 | lane << 9
   __shared__ unsigned s_qt;                           // ... its tail (running counter, advanced with one atomic per lane)
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
           }
         }
       };
-      for (int chunk0 = 0, buf = 0; chunk0 < nhome; chunk0 += 32, buf ^= 1) {
+      for (int chunk0 = 0, buf = 0; chunk0 < nhome; chunk0 += 32, buf ^= (RH_HOMEBUF - 1)) {
         const int nchunk = min(32, nhome - chunk0);
         // next chunk of reference atoms: loaded now, stored after this chunk has been processed
         if (chunk0 + 32 + lane < nhome) {
@@ -459,8 +462,8 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
           qn = 0;
         }
         __syncwarp();
-        s_homeP[buf ^ 1][lane] = hp;
-        s_homeU[buf ^ 1][lane] = hu;
+        s_homeP[buf ^ (RH_HOMEBUF - 1)][lane] = hp;
+        s_homeU[buf ^ (RH_HOMEBUF - 1)][lane] = hu;
         __syncwarp();
       }
     }
