@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(128) rdf_sweep_exact_kernel(const RdfArgs a) {
 // The bin is found WITHOUT sqrt / division in FP64: thr[k] is the smallest double s whose correctly rounded
 // sqrt(s) is >= edges[k] (rdf_thresholds_kernel), so "edges[k] <= sqrt(s) < edges[k+1]" is decided by comparing s
 // itself - bit-exact with numpy.histogram's rule, including range ends and the closed last bin.
-#define RH_WARPS 13
+#define RH_WARPS 16        // resident warps per SM the register allocation is sized for
+#ifndef RH_CTA_WARPS
+#define RH_CTA_WARPS 2      // warps per CTA: they share one privatised histogram
+#endif
 #ifndef RH_SLOTS
 #define RH_SLOTS 6          // register-resident candidate slots per lane (candidates per landing-zone pass = 32 * RH_SLOTS):
                             // 6 -> 12 warps per SM (4M beads: 11.6 ms; 8 slots, 11 warps: 11.9 ms; 4 slots: 12.2 ms)
@@ -175,29 +178,46 @@ __device__ __forceinline__ void reds_add(uint32_t addr, unsigned v) {
 
 // SAME_MOL: pairs inside one molecule count (reference sameMolecule=True); ONE_TYPE: a single type-pair key;
 // SMEM_HIST: the histogram fits the per-warp shared-memory copy
+// Everything one warp owns in shared memory.  The warps of a CTA work independently, each on its own home cells; they
+// only share the privatised histogram - 4 KB for 1000 bins, which limits single-warp CTAs to 13 per SM; one histogram
+// per two warps gives 16.  (Measured on config 4: 10.1 -> 9.3 ms; a multi-warp CTA pays ~5 % for real WARPSYNCs, which
+// the compiler drops when the CTA is one warp, so four warps per CTA gain nothing over two.)
+template <int NC>
+struct __align__(128) RhWarp {
+  Rec land[NC];                       // TMA landing zone; stays valid for the whole pass
+  double4 homeU[RH_HOMEBUF][32];      // reference atoms of the home cell, 32 at a time (the next 32 wait in registers
+  float4 homeP[RH_HOMEBUF][32];       // until the queue of the current ones is drained)
+  int raw[HS_ITEM_INTS];
+  unsigned short q[RH_QUEUE];         // hit queue: reference (5 bits) | slot << 5 | lane << 9
+  uint64_t bar;
+  unsigned qt;                        // ... its tail (running counter, advanced with one atomic per lane)
+};
+
 template <int SLOTS, bool SAME_MOL, bool ONE_TYPE, bool SMEM_HIST>
-__global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfHalfArgs a) {
+__global__ void __launch_bounds__(32 * RH_CTA_WARPS, RH_WARPS / RH_CTA_WARPS) rdf_sweep_half_kernel(const RdfHalfArgs a) {
   constexpr int NC = SLOTS * 32;
   constexpr int NPAIR = SLOTS / 2;
-  extern __shared__ unsigned int s_hist[];            // [npairs * nbin] when use_smem
-  __shared__ __align__(128) Rec s_land[NC];           // TMA landing zone; stays valid for the whole pass
-  __shared__ float4 s_homeP[RH_HOMEBUF][32];          // reference atoms of the home cell, 32 at a time (the next 32 wait
-  __shared__ double4 s_homeU[RH_HOMEBUF][32];         // in registers until the queue of the current ones is drained)
-  __shared__ __align__(16) int s_raw[HS_ITEM_INTS];
-  __shared__ unsigned short s_q[RH_QUEUE];            // hit queue: reference (5 bits) | slot << 5 | lane << 9
-  __shared__ unsigned s_qt;                           // ... its tail (running counter, advanced with one atomic per lane)
-  __shared__ __align__(8) uint64_t s_bar;
-  const int lane = threadIdx.x;
+  extern __shared__ unsigned int s_hist[];            // [npairs * nbin] when use_smem: one copy per CTA
+  __shared__ RhWarp<NC> s_warp[RH_CTA_WARPS];
+  RhWarp<NC> &W = s_warp[threadIdx.x >> 5];
+  Rec(&s_land)[NC] = W.land;
+  float4(&s_homeP)[RH_HOMEBUF][32] = W.homeP;
+  double4(&s_homeU)[RH_HOMEBUF][32] = W.homeU;
+  int(&s_raw)[HS_ITEM_INTS] = W.raw;
+  unsigned short(&s_q)[RH_QUEUE] = W.q;
+  unsigned &s_qt = W.qt;
+  uint64_t &s_bar = W.bar;
+  const int lane = threadIdx.x & 31;
   const int nbin = a.nbin;
   const int hsize = a.ntypes * (a.ntypes + 1) / 2 * nbin;
   if (SMEM_HIST)
-    for (int k = lane; k < hsize; k += 32) s_hist[k] = 0;
+    for (int k = threadIdx.x; k < hsize; k += 32 * RH_CTA_WARPS) s_hist[k] = 0;
   if (lane == 0) {
     mbar_init(&s_bar, 1);
     fence_mbar_init();
     s_qt = 0u;
   }
-  __syncwarp();
+  __syncthreads();
   uint32_t phase = 0;
   const double thr0 = a.thr[0], shi = a.thr[nbin + 1];
   const double Lx = a.g.box[0], Ly = a.g.box[1], Lz = a.g.box[2];
@@ -469,8 +489,8 @@ __global__ void __launch_bounds__(32, RH_WARPS) rdf_sweep_half_kernel(const RdfH
     }
   }
   if (SMEM_HIST) {
-    __syncwarp();
-    for (int k = lane; k < hsize; k += 32)
+    __syncthreads();        // every warp of the CTA has run out of home cells
+    for (int k = threadIdx.x; k < hsize; k += 32 * RH_CTA_WARPS)
       if (s_hist[k]) atomicAdd(&a.hist[k], (unsigned long long)s_hist[k]);
   }
 }
@@ -479,13 +499,16 @@ template <bool SAME_MOL, bool ONE_TYPE, bool SMEM_HIST>
 static void launch_rdf_half(const RdfHalfArgs &h, int ncell, size_t smem, cudaStream_t st) {
   // (no cached state: the library holds nothing per process; the query costs microseconds next to a 10 ms sweep)
   int blocks_per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rdf_sweep_half_kernel<RH_SLOTS, SAME_MOL, ONE_TYPE, SMEM_HIST>, 32,
-                                                smem);
+  // static + dynamic shared memory passes 48 KB with the histogram: opt in (per device and function, cheap)
+  cudaFuncSetAttribute(rdf_sweep_half_kernel<RH_SLOTS, SAME_MOL, ONE_TYPE, SMEM_HIST>,
+                       cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rdf_sweep_half_kernel<RH_SLOTS, SAME_MOL, ONE_TYPE, SMEM_HIST>,
+                                                32 * RH_CTA_WARPS, smem);
   if (blocks_per_sm < 1) blocks_per_sm = 1;
   const int sms = mouse_num_sms();
   int blocks = sms * blocks_per_sm;
-  if (blocks > ncell) blocks = ncell;
-  rdf_sweep_half_kernel<RH_SLOTS, SAME_MOL, ONE_TYPE, SMEM_HIST><<<blocks, 32, smem, st>>>(h);
+  if (blocks > (ncell + RH_CTA_WARPS - 1) / RH_CTA_WARPS) blocks = (ncell + RH_CTA_WARPS - 1) / RH_CTA_WARPS;
+  rdf_sweep_half_kernel<RH_SLOTS, SAME_MOL, ONE_TYPE, SMEM_HIST><<<blocks, 32 * RH_CTA_WARPS, smem, st>>>(h);
 }
 
 int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, int32_t ntypes,

@@ -9,6 +9,6 @@ pos = torch.as_tensor(melt.positions).cuda(); t = torch.as_tensor(melt.atom_type
 for same in (True, False):
     for rep in range(2):
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        h, e = engine.rdf_frame(pos, t, mol, 1, melt.box, 0., 5., 1000, same_molecule=same)
+        h, e = engine.rdf_frame(pos, t, mol, 1, melt.box, 0., 5., int(os.environ.get("NBIN", "1000")), same_molecule=same)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print("rdf n=%d same=%s: %.2f ms, pairs %d -> %.3e pairs/s" % (melt.n_atoms, same, dt * 1e3, int(h.sum()), int(h.sum()) / dt))
