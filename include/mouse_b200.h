@@ -232,6 +232,24 @@ int64_t mouse_parse_dump_atoms(const char *text /*HOST*/, int64_t len, int64_t n
                                const int32_t *col_xyz, const int32_t *col_img, int32_t mode, const double *lo,
                                const double *hi, int64_t *ids, double *xyz, int32_t *img, int32_t nthreads);
 
+/* The same block parsed ON THE DEVICE: `text` (DEV, 16-byte aligned, len < 2^31) holds the raw bytes of the ATOMS block
+ * as they lie in the file; ids / xyz / img (DEV) receive what mouse_parse_dump_atoms would write, bit for bit (the exact
+ * fast path of the number parser: <= 15 significant digits, decimal exponent within +-22, one IEEE rounding; the
+ * reference's coordinate transform un-fused).  row_of_line (DEV int32[nrows] or NULL): xyz / img of line k go to row
+ * row_of_line[k] (the id -> topology row permutation of a previous frame); ids are always written in line order.
+ * expect_ids (DEV or NULL): ids of the previous frame, mismatches are counted.  lo / hi / col_*: HOST.
+ * status (DEV int64[4], written by the call): [0] non-blank lines found (must equal nrows), [1] byte offset of the
+ * first line with a wrong number of columns (INT64_MAX: none), [2] tokens that need the host parser (long mantissas,
+ * nan / inf, malformed), [3] lines whose id differs from expect_ids.  Unless [0] == nrows, [1] == INT64_MAX and
+ * [2] == 0 the outputs are incomplete and the caller parses the frame with mouse_parse_dump_atoms, which is
+ * authoritative for errors.  ws: mouse_parse_dump_ws_bytes(len, nrows) bytes (DEV).  Asynchronous on `stream`. */
+size_t mouse_parse_dump_ws_bytes(int64_t len, int64_t nrows);
+int mouse_parse_dump_atoms_dev(const char *text /*DEV*/, int64_t len, int64_t nrows, int32_t ncol, int32_t col_id,
+                               const int32_t *col_xyz /*HOST*/, const int32_t *col_img /*HOST or NULL*/, int32_t mode,
+                               const double *lo /*HOST*/, const double *hi /*HOST*/, const int32_t *row_of_line,
+                               const int64_t *expect_ids, int64_t *ids, double *xyz, int32_t *img, void *ws,
+                               size_t ws_bytes, int64_t *status, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -191,6 +191,103 @@ class _RowMap:
         return self.row, self.identity
 
 
+class DeviceDumpParser:
+    """The ATOMS block of a dump frame parsed ON THE GPU (``mouse_parse_dump_atoms_dev``, ``csrc/dump_parse.cu``):
+    the raw text goes from the page cache into one pinned staging buffer and over PCIe as it is, four small kernels
+    turn it into ids / positions / image flags with the host parser's arithmetic (bit-identical values), and the
+    positions come back as a CUDA tensor that ``FramePipeline.submit`` takes without another host round trip.  The
+    id -> topology-row permutation of the previous frame stays on the device; the ids of a frame are compared with
+    the previous frame's there, and only a frame that lists the atoms in a different order costs a host lookup.
+    ``parse`` returns None for a frame the device parser does not take (tokens outside the exact fast path of the
+    number parser, wrong line or column counts): the caller then uses the host parser, which is authoritative."""
+
+    def __init__(self, rowmap: "_RowMap", device):
+        import torch
+        from . import _lib
+        self.torch, self.L = torch, _lib.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("DeviceDumpParser needs a CUDA device")
+        self.rowmap = rowmap
+        self.n = len(rowmap.atom_num)
+        with torch.cuda.device(self.device):
+            self.stream = torch.cuda.Stream(device=self.device)
+            self.status = torch.zeros(4, dtype=torch.int64, device=self.device)
+            self.status_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+        self.stage = self.text = self.ws = None
+        self.ids = [torch.empty(self.n, dtype=torch.int64, device=self.device) for _ in range(2)]
+        self.have_ids = False          # ids[0] holds the previous frame's ids (line order)
+        self.row_dev = None            # int32 permutation line -> topology row (None: identity)
+        self.frames_device = self.frames_host = 0
+        self.declined_in_a_row = 0     # a dump written with 17 digits per number never takes the device path: stop
+                                       # shipping its text after three frames
+
+    def _room(self, nbytes):
+        torch = self.torch
+        if self.stage is None or self.stage.numel() < nbytes:
+            cap = int(nbytes * 1.25) + 4096
+            self.stage = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            self.stage_np = self.stage.numpy()
+            self.text = torch.empty(cap, dtype=torch.uint8, device=self.device)
+        need = int(self.L.mouse_parse_dump_ws_bytes(nbytes, self.n))
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, device=self.device)
+
+    def _run(self, nbytes, ncol, col_id, cxyz, cimg, mode, lo, hi, pos, img, expect):
+        import ctypes as C
+        from . import _lib
+        vp = C.c_void_p
+        rc = self.L.mouse_parse_dump_atoms_dev(
+            vp(self.text.data_ptr()), nbytes, self.n, ncol, col_id, cxyz, cimg, mode, vp(lo.ctypes.data),
+            vp(hi.ctypes.data), vp(self.row_dev.data_ptr()) if self.row_dev is not None else None,
+            vp(self.ids[0].data_ptr()) if expect else None, vp(self.ids[1].data_ptr()), vp(pos.data_ptr()),
+            vp(img.data_ptr()) if img is not None else None, vp(self.ws.data_ptr()), self.ws.numel(),
+            vp(self.status.data_ptr()), vp(self.stream.cuda_stream))
+        _lib.check(rc, "mouse_parse_dump_atoms_dev")
+        self.status_host.copy_(self.status, non_blocking=True)
+        self.stream.synchronize()
+        return [int(v) for v in self.status_host]
+
+    def parse(self, buf, b0, stop, keys, ci, coords_type, lo, hi):
+        import ctypes as C
+        torch = self.torch
+        nbytes = int(stop - b0)
+        if nbytes <= 0 or nbytes >= 2 ** 31 or self.declined_in_a_row >= 3:
+            self.frames_host += 1
+            return None
+        has_img = all(kk in keys for kk in ("ix", "iy", "iz"))
+        cxyz = (C.c_int32 * 3)(*ci)
+        cimg = (C.c_int32 * 3)(*[keys.index(kk) for kk in ("ix", "iy", "iz")]) if has_img else None
+        mode = {"scaled": 0, "cut": 1, "uncut": 2}[coords_type]
+        lo = np.ascontiguousarray(lo, np.float64)
+        hi = np.ascontiguousarray(hi, np.float64)
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self._room(nbytes)
+            np.copyto(self.stage_np[:nbytes], buf[b0:stop])          # page cache -> pinned, the only host pass
+            self.text[:nbytes].copy_(self.stage[:nbytes], non_blocking=True)
+            pos = torch.empty((self.n, 3), dtype=torch.float64, device=self.device)
+            img = torch.empty((self.n, 3), dtype=torch.int32, device=self.device) if has_img else None
+            args = (nbytes, len(keys), keys.index("id"), cxyz, cimg, mode, lo, hi, pos, img)
+            rows, bad, slow, changed = self._run(*args, expect=self.have_ids)
+            if rows != self.n or bad != 2 ** 63 - 1 or slow:
+                self.frames_host += 1
+                self.declined_in_a_row += 1
+                return None
+            self.declined_in_a_row = 0
+            if changed or not self.have_ids:
+                # first frame, or the atoms are listed in another order than in the previous frame: look the ids up
+                # on the host once, keep the permutation on the device
+                row, identity = self.rowmap.rows(self.ids[1].cpu().numpy())
+                old = self.row_dev
+                self.row_dev = None if identity else torch.from_numpy(row.astype(np.int32)).to(self.device)
+                if not (identity and old is None):                     # the first pass scattered with the old map
+                    rows, bad, slow, _ = self._run(*args, expect=False)
+            self.ids.reverse()          # this frame's ids become "the previous frame's"
+            self.have_ids = True
+        self.frames_device += 1
+        return pos, img
+
+
 def _parse_dump_header(head: str, n: int):
     lines = head.split("\n")
     timestep, natom, lo, hi = 0, n, np.zeros(3), np.zeros(3)
@@ -215,12 +312,13 @@ def _parse_dump_header(head: str, n: int):
     return timestep, natom, lo, hi
 
 
-def _parse_dump_frame(buf, start: int, stop: int, rowmap: _RowMap, coords_type: str, threads: int):
+def _parse_dump_frame(buf, start: int, stop: int, rowmap: _RowMap, coords_type: str, threads: int, device_parser=None):
     """One frame = the bytes [start, stop) of ``buf`` (the memory-mapped dump as a uint8 array), from its ``ITEM:
     TIMESTEP`` line up to the next one -> (timestep, box, centre, pos, img).  The ATOMS block goes to
     ``mouse_parse_dump_atoms`` in place (no copy of the text, ids / coordinates / image flags written directly,
     the reference's coordinate transform applied in C); blocks that function cannot take (non-numeric columns,
-    library not built) go through the token-by-token path."""
+    library not built) go through the token-by-token path.  With a ``device_parser`` the block is parsed on the GPU
+    and ``pos`` / ``img`` are CUDA tensors; frames it declines take the host path (NumPy arrays)."""
     n = len(rowmap.atom_num)
     head_end = min(stop, start + 4096)
     head_bytes = bytes(buf[start:head_end])
@@ -239,6 +337,10 @@ def _parse_dump_frame(buf, start: int, stop: int, rowmap: _RowMap, coords_type: 
     b0 = start + eol + 1
     ci = [keys.index(kk) for kk in _COORD_KEYS[coords_type]]
     has_img = all(kk in keys for kk in ("ix", "iy", "iz"))
+    if device_parser is not None and natom == n:
+        got = device_parser.parse(buf, b0, stop, keys, ci, coords_type, lo, hi)
+        if got is not None:
+            return timestep, hi - lo, (lo + hi) / 2., got[0], got[1]
     ids = xyz = iv = None
     try:
         import ctypes as C
@@ -287,13 +389,16 @@ def _parse_dump_frame(buf, start: int, stop: int, rowmap: _RowMap, coords_type: 
     return timestep, hi - lo, (lo + hi) / 2., pos, img
 
 
-def iter_lmp_dump_frames(path, atom_num, coords_type="scaled", frames=None, index=None, threads=1):
+def iter_lmp_dump_frames(path, atom_num, coords_type="scaled", frames=None, index=None, threads=1, device=None,
+                         stats=None):
     """Yield ``(timestep, box[3], box_center[3], positions[N,3], images[N,3] or None)`` per frame of a LAMMPS dump,
     with the rows ordered like ``atom_num`` (the topology's atom numbers).  ``frames`` = (lo, hi) restricts the
     iteration to that range of frames: with the byte-offset ``index`` (``index_lmp_dump``; built here when not
     given) the reader seeks to frame ``lo`` and never touches the others - this is how the ranks of a sharded
     trajectory each read their own block.  ``threads``: host threads of the number parser.  One frame is in memory
-    at a time."""
+    at a time.  ``device`` (a CUDA device): the ATOMS blocks are parsed on the GPU (``DeviceDumpParser``) and
+    positions / images are CUDA tensors there - except for frames the device parser declines, which come from the host
+    parser as NumPy arrays with the same values; ``stats`` (a dict) receives the count of each kind."""
     if coords_type not in _COORD_KEYS:
         raise ValueError("coords_type must be scaled, cut or uncut")
     if index is None:
@@ -303,14 +408,18 @@ def iter_lmp_dump_frames(path, atom_num, coords_type="scaled", frames=None, inde
     rowmap = _RowMap(atom_num)
     if hi_f <= lo_f:
         return
+    dev_parser = DeviceDumpParser(rowmap, device) if device is not None else None
     import mmap
     with open(path, "rb") as f:
         mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
         buf = np.frombuffer(mm, dtype=np.uint8)       # the parser reads the mapped text in place
         try:
             for k in range(lo_f, hi_f):
-                yield _parse_dump_frame(buf, int(index[k]), int(index[k + 1]), rowmap, coords_type, threads)
+                yield _parse_dump_frame(buf, int(index[k]), int(index[k + 1]), rowmap, coords_type, threads, dev_parser)
         finally:
+            if stats is not None and dev_parser is not None:
+                stats["frames_device"] = dev_parser.frames_device
+                stats["frames_host"] = dev_parser.frames_host
             del buf
             try:
                 mm.close()

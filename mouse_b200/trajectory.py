@@ -243,6 +243,8 @@ class FramePipeline:
             s["stage"].copy_(src.reshape(self.n_atoms, 3))
             src = s["stage"]
         with torch.cuda.stream(self.copy_stream):
+            if src.device.type == "cuda":       # (the allocator must not hand the block out again before the copy ran)
+                src.record_stream(self.copy_stream)
             s["pos"].copy_(src.reshape(self.n_atoms, 3), non_blocking=True)
             s["copied"].record(self.copy_stream)
         with torch.cuda.stream(s["stream"]):
@@ -374,7 +376,7 @@ def pair_correlation_trajectory(frames_positions, type_code, mol, ntypes, box, r
 
 def local_ordering_from_dump(topology, dump_path, bondtypes=None, rcut=0., coords_type="scaled",
                              reference_res_types=None, same_molecule=True, device=None, gather=False,
-                             parse_threads=None, hist_args=None):
+                             parse_threads=None, hist_args=None, parse_on="device", stats=None):
     """Trajectory driver over files: ``topology`` is a ``FrameArrays`` (e.g.
     ``ingest.read_lmp_data_arrays(data_file)``), the frames come from a LAMMPS dump.  Every frame carries its own
     box, so the cell grid is re-planned per frame; frames are block-sharded over the ranks exactly like
@@ -385,7 +387,10 @@ def local_ordering_from_dump(topology, dump_path, bondtypes=None, rcut=0., coord
     Ingestion keeps up with the GPU: the dump is indexed once (byte offset of every ``ITEM: TIMESTEP``), every rank
     seeks to its own block of frames and parses nothing else, a producer thread parses frame k+1 (multi-threaded C
     number parser, GIL released) while frame k is on the GPU, and frames are handed to the pipeline one at a time -
-    the host never holds more than a few frames whatever the length of the trajectory."""
+    the host never holds more than a few frames whatever the length of the trajectory.  ``parse_on="device"`` (default)
+    ships the raw text of the ATOMS block to the GPU and parses it there (``ingest.DeviceDumpParser``: same values bit
+    for bit; frames with tokens outside the number parser's exact fast path fall to the host parser one by one);
+    ``"host"`` keeps the parsing on ``parse_threads`` host threads.  ``stats`` (dict) receives the frame counts."""
     import os
     import queue
     import threading
@@ -410,7 +415,8 @@ def local_ordering_from_dump(topology, dump_path, bondtypes=None, rcut=0., coord
         def produce():
             try:
                 for item in ingest.iter_lmp_dump_frames(dump_path, topology.atom_num, coords_type, frames=(lo, hi),
-                                                        index=index, threads=parse_threads):
+                                                        index=index, threads=parse_threads,
+                                                        device=device if parse_on == "device" else None, stats=stats):
                     q.put(item)
                 q.put(None)
             except BaseException as e:      # hand the error to the consumer

@@ -1,0 +1,151 @@
+"""Device-side parser of LAMMPS dump frames (mouse_parse_dump_atoms_dev, csrc/dump_parse.cu) against the host parser
+(mouse_parse_dump_atoms, pinned to the reference's readers in tests/test_ingest_cpu.py): the same ids, coordinates and
+image flags BIT FOR BIT, whatever the number format, the order of the atoms and the white space; frames the device
+parser declines come from the host parser."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from mouse_b200 import ingest  # noqa: E402
+
+
+def _write_dump(path, frames, keys="id type xs ys zs ix iy iz", lo=(-5.0, -4.0, -3.0), hi=(5.0, 6.0, 7.0)):
+    """frames: list of (timestep, list of text lines)"""
+    with open(path, "wb") as f:
+        for ts, n, lines, eol in frames:
+            head = "ITEM: TIMESTEP\n%d\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n" % (ts, n)
+            head += "".join("%r %r\n" % (float(a), float(b)) for a, b in zip(lo, hi)) + "ITEM: ATOMS " + keys + "\n"
+            f.write(head.encode())
+            f.write(eol.join(lines).encode() + eol.encode())
+
+
+def _frames(path, num, coords, device=None, stats=None):
+    out = []
+    for ts, box, ctr, pos, img in ingest.iter_lmp_dump_frames(str(path), num, coords, threads=1, device=device,
+                                                              stats=stats):
+        if isinstance(pos, torch.Tensor):
+            pos = pos.cpu().numpy()
+            img = None if img is None else img.cpu().numpy()
+        out.append((ts, box, pos.copy(), None if img is None else np.array(img)))
+    return out
+
+
+def _same(a, b):
+    assert len(a) == len(b)
+    for (ta, ba, pa, ia), (tb, bb, pb, ib) in zip(a, b):
+        assert ta == tb and np.array_equal(ba, bb)
+        assert pa.dtype == pb.dtype == np.float64
+        assert np.array_equal(pa.view(np.int64), pb.view(np.int64))          # bit for bit, signed zeros included
+        assert (ia is None) == (ib is None) and (ia is None or np.array_equal(ia, ib))
+
+
+@pytest.mark.parametrize("coords", ["scaled", "cut", "uncut"])
+def test_device_parser_is_bit_identical_to_the_host_parser(tmp_path, coords):
+    rng = np.random.default_rng(11)
+    n = 20000
+    num = np.arange(1, n + 1) * 3 - 1            # atom numbers with gaps
+    key = {"scaled": "xs ys zs", "cut": "xc yc zc", "uncut": "xu yu zu"}[coords]
+    perm1, perm2 = rng.permutation(n), rng.permutation(n)
+
+    def lines(order, fmt, x, img, decorate=False):
+        out = []
+        for k, i in enumerate(order):
+            ln = ("%d 1 " + fmt + " %d %d %d") % (num[i], x[i, 0], x[i, 1], x[i, 2], img[i, 0], img[i, 1], img[i, 2])
+            if decorate:
+                ln = ["  " + ln, ln + "  ", "\t" + ln.replace(" ", "   "), ln][k % 4]
+                if k % 97 == 0:
+                    ln += "\n   "                 # a blank line in the middle of the block
+            out.append(ln)
+        return out
+
+    frames = []
+    xs = [rng.random((n, 3)) * (30.0 if coords != "scaled" else 1.0) - (10.0 if coords != "scaled" else 0.0)
+          for _ in range(6)]
+    xs[2][::7] = 0.0
+    xs[2][1::7] *= 1e-7                           # leading zeros behind the point, tiny exponents
+    im = rng.integers(-3, 4, (n, 3))
+    frames.append((0, n, lines(np.arange(n), "%.8g %.8g %.8g", xs[0], im), "\n"))
+    frames.append((10, n, lines(perm1, "%.15g %.15g %.15g", xs[1], im), "\n"))
+    frames.append((20, n, lines(perm1, "%.6e %.6e %+.6e", xs[2], im), "\n"))          # same order: cached permutation
+    frames.append((30, n, lines(perm2, "%+.10f %.10f %.10f", xs[3], im, decorate=True), "\r\n"))
+    frames.append((40, n, lines(perm2, "%r %r %r", xs[4].astype(object), im), "\n"))  # 17 digits: host parser
+    xs[5][:, 1] = np.abs(xs[5][:, 1])            # (written behind an explicit minus sign)
+    frames.append((50, n, lines(np.arange(n), "%.12g -%.12g %.3f", xs[5], im), "\n"))
+    path = tmp_path / "mixed.dump"
+    _write_dump(path, frames, keys="id type " + key + " ix iy iz")
+    host = _frames(path, num, coords)
+    stats = {}
+    dev = _frames(path, num, coords, device="cuda", stats=stats)
+    _same(host, dev)
+    assert stats == {"frames_device": 5, "frames_host": 1}
+    assert [f[0] for f in dev] == [0, 10, 20, 30, 40, 50]
+    # the scaled transform really is lo + (hi - lo) * x, un-fused (spot check against NumPy)
+    if coords == "scaled":
+        lo, hi = np.array([-5.0, -4.0, -3.0]), np.array([5.0, 6.0, 7.0])
+        x0 = np.array([[float("%.8g" % v) for v in row] for row in xs[0][:50]])
+        assert np.array_equal(dev[0][2][:50], lo + (hi - lo) * x0)
+
+
+def test_device_parser_without_image_columns_and_with_extra_columns(tmp_path):
+    rng = np.random.default_rng(3)
+    n = 5000
+    num = np.arange(1, n + 1)
+    x = rng.random((n, 3))
+    order = rng.permutation(n)
+    lines = ["%d %d %.9g %.7g %.9g %.9g %d" % (2, num[i], x[i, 2], 1.5e-3 * i, x[i, 0], x[i, 1], i % 5) for i in order]
+    path = tmp_path / "cols.dump"
+    _write_dump(path, [(5, n, lines, "\n"), (6, n, lines[::-1], "\n")], keys="type id zs q xs ys c_extra")
+    stats = {}
+    _same(_frames(path, num, "scaled"), _frames(path, num, "scaled", device="cuda", stats=stats))
+    assert stats == {"frames_device": 2, "frames_host": 0}
+
+
+def test_frames_the_device_parser_declines_raise_what_the_host_parser_raises(tmp_path):
+    n = 300
+    num = np.arange(1, n + 1)
+    good = ["%d 1 0.5 0.25 0.125" % i for i in num]
+    short = list(good)
+    short[177] = "178 1 0.5 0.25"                     # a column is missing
+    word = list(good)
+    word[12] = "13 1 0.5 abc 0.125"                   # not a number
+    unknown = list(good)
+    unknown[5] = "9999 1 0.5 0.25 0.125"              # an atom number the topology does not have
+    for bad in (short, word, unknown, good[:-1]):
+        path = tmp_path / "bad.dump"
+        _write_dump(path, [(0, n, good, "\n"), (1, n, bad, "\n")], keys="id type xs ys zs")
+        errs = []
+        for device in (None, "cuda"):
+            with pytest.raises(Exception) as e:
+                _frames(path, num, "scaled", device=device)
+            errs.append(type(e.value))
+        assert errs[0] is errs[1]
+
+
+def test_trajectory_from_a_dump_gives_the_same_S_with_either_parser(tmp_path):
+    """local_ordering_from_dump with parse_on='device' (CUDA positions straight into FramePipeline) and 'host'."""
+    from mouse_b200.frames import FrameArrays
+    from mouse_b200.melt import jitter, make_melt
+    from mouse_b200.trajectory import local_ordering_from_dump
+    melt = make_melt(40, 51, seed=5)
+    top = FrameArrays.from_melt(melt)
+    half = melt.box / 2
+    rng = np.random.default_rng(0)
+    frames = []
+    for k in range(7):
+        pos = jitter(melt, k, 0.03)
+        xs = (pos + half) / melt.box
+        order = rng.permutation(melt.n_atoms) if k in (2, 3, 5) else np.arange(melt.n_atoms)
+        frames.append((100 * k, melt.n_atoms, ["%d 1 %.8g %.8g %.8g" % (i + 1, xs[i, 0], xs[i, 1], xs[i, 2])
+                                              for i in order], "\n"))
+    path = tmp_path / "traj.dump"
+    _write_dump(path, frames, keys="id type xs ys zs", lo=tuple(-half), hi=tuple(half))
+    sd, sh = {}, {}
+    dev, tot_d = local_ordering_from_dump(top, str(path), ["1"], 2.0, "scaled", parse_on="device", stats=sd)
+    host, tot_h = local_ordering_from_dump(top, str(path), ["1"], 2.0, "scaled", parse_on="host", stats=sh)
+    assert sd == {"frames_device": 7, "frames_host": 0} and sh == {}
+    assert dev == host and len(dev) == 7
+    assert tot_d.n_pairs == tot_h.n_pairs and tot_d.mean_s == tot_h.mean_s
