@@ -232,6 +232,11 @@ int64_t mouse_parse_dump_atoms(const char *text /*HOST*/, int64_t len, int64_t n
                                const int32_t *col_xyz, const int32_t *col_img, int32_t mode, const double *lo,
                                const double *hi, int64_t *ids, double *xyz, int32_t *img, int32_t nthreads);
 
+/* HOST only.  Frame index of a LAMMPS dump (lammpack_types.py:344-398 walks the file line by line looking for
+ * `ITEM: TIMESTEP`): byte offset of every line that starts with it, ascending, found with nthreads host threads.
+ * Returns the number of frames; only the first `cap` offsets are written to out (call again with a larger array). */
+int64_t mouse_index_dump(const char *text /*HOST*/, int64_t len, int64_t *out /*HOST*/, int64_t cap, int32_t nthreads);
+
 /* The same block parsed ON THE DEVICE: `text` (DEV, 16-byte aligned, len < 2^31) holds the raw bytes of the ATOMS block
  * as they lie in the file; ids / xyz / img (DEV) receive what mouse_parse_dump_atoms would write, bit for bit (the exact
  * fast path of the number parser: <= 15 significant digits, decimal exponent within +-22, one IEEE rounding; the

@@ -563,6 +563,45 @@ extern "C" int64_t mouse_parse_doubles_mt(const char *text, int64_t len, double 
   return first[nthreads];
 }
 
+// Byte offset of every `ITEM: TIMESTEP` line of a dump (the frame index of ingest.index_lmp_dump): memmem over
+// nthreads chunks of the (memory-mapped) file, matches kept when they open a line.  Returns the number of frames found;
+// only the first `cap` offsets are written.
+extern "C" int64_t mouse_index_dump(const char *text, int64_t len, int64_t *out, int64_t cap, int32_t nthreads) {
+  static const char pat[] = "ITEM: TIMESTEP";
+  const int64_t plen = (int64_t)sizeof(pat) - 1;
+  if (!text || len < plen) return 0;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 64) nthreads = 64;
+  if (len < (int64_t)1 << 22) nthreads = 1;
+  std::vector<std::vector<int64_t>> found(nthreads);
+  auto scan = [&](int t) {
+    // matches that START in [a, b): the window runs plen - 1 bytes past b
+    const int64_t a = len * t / nthreads, b = len * (t + 1) / nthreads;
+    const int64_t wend = b + plen - 1 < len ? b + plen - 1 : len;
+    const char *p = text + a, *end = text + wend;
+    while (p < end) {
+      const char *q = (const char *)memmem(p, (size_t)(end - p), pat, (size_t)plen);
+      if (!q) break;
+      if (q == text || q[-1] == '\n') found[t].push_back((int64_t)(q - text));
+      p = q + plen;
+    }
+  };
+  if (nthreads == 1) {
+    scan(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) pool.emplace_back(scan, t);
+    for (auto &th : pool) th.join();
+  }
+  int64_t n = 0;
+  for (int t = 0; t < nthreads; ++t)
+    for (int64_t v : found[t]) {
+      if (n < cap && out) out[n] = v;
+      ++n;
+    }
+  return n;
+}
+
 // The ATOMS block of a LAMMPS dump frame (lammpack_types.py:377-395) straight into the arrays the pipeline needs:
 // `nrows` lines of `ncol` whitespace-separated numbers; column col_id -> ids (int64), columns col_xyz[0..2] ->
 // xyz[row][3] with the coordinate transform of the reference applied (mode 0 "scaled": lo + (hi - lo) * x, mode 1

@@ -160,6 +160,25 @@ def index_lmp_dump(path):
     offs = []
     if size:
         with open(path, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            try:                        # the library's threaded memmem scan (GIL released)
+                import ctypes as C
+                from . import _lib
+                L = _lib.lib()
+                buf = np.frombuffer(mm, dtype=np.uint8)
+                try:
+                    threads = max(1, min(16, os.cpu_count() or 1))
+                    out = np.empty(max(16, size // 4096), np.int64)
+                    got = L.mouse_index_dump(C.c_void_p(buf.ctypes.data), size, C.c_void_p(out.ctypes.data), len(out),
+                                             threads)
+                    if got > len(out):
+                        out = np.empty(got, np.int64)
+                        got = L.mouse_index_dump(C.c_void_p(buf.ctypes.data), size, C.c_void_p(out.ctypes.data),
+                                                 len(out), threads)
+                finally:
+                    del buf
+                return np.concatenate([out[:got], np.array([size], np.int64)])
+            except (ImportError, OSError, AttributeError):
+                pass
             k = mm.find(b"ITEM: TIMESTEP")
             while k >= 0:
                 if k == 0 or mm[k - 1] == 0x0a:
@@ -201,7 +220,7 @@ class DeviceDumpParser:
     ``parse`` returns None for a frame the device parser does not take (tokens outside the exact fast path of the
     number parser, wrong line or column counts): the caller then uses the host parser, which is authoritative."""
 
-    def __init__(self, rowmap: "_RowMap", device):
+    def __init__(self, rowmap: "_RowMap", device, fd=None, read_threads=4):
         import torch
         from . import _lib
         self.torch, self.L = torch, _lib.lib()
@@ -210,11 +229,22 @@ class DeviceDumpParser:
             raise ValueError("DeviceDumpParser needs a CUDA device")
         self.rowmap = rowmap
         self.n = len(rowmap.atom_num)
+        # with the file descriptor the text is read straight into the pinned buffer (pread on a few threads: no page
+        # faults of a mapping, the GIL is released); without it the block is copied from the caller's mapping
+        self.fd, self.pool = fd, None
+        if fd is not None and read_threads > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            self.pool = ThreadPoolExecutor(read_threads)
+        self.read_threads = max(1, int(read_threads))
         with torch.cuda.device(self.device):
             self.stream = torch.cuda.Stream(device=self.device)
             self.status = torch.zeros(4, dtype=torch.int64, device=self.device)
             self.status_host = torch.zeros(4, dtype=torch.int64).pin_memory()
-        self.stage = self.text = self.ws = None
+        self.text = self.ws = None
+        # two pinned staging buffers: while the GPU works on the frame in one of them, the read threads fill the other
+        # with the next frame (``next_range``, set by the iterator: the byte range of the frame after this one)
+        self.stages, self.cur = [None, None], 0
+        self.next_range, self.ahead = None, None
         self.ids = [torch.empty(self.n, dtype=torch.int64, device=self.device) for _ in range(2)]
         self.have_ids = False          # ids[0] holds the previous frame's ids (line order)
         self.row_dev = None            # int32 permutation line -> topology row (None: identity)
@@ -224,14 +254,60 @@ class DeviceDumpParser:
 
     def _room(self, nbytes):
         torch = self.torch
-        if self.stage is None or self.stage.numel() < nbytes:
-            cap = int(nbytes * 1.25) + 4096
-            self.stage = torch.empty(cap, dtype=torch.uint8).pin_memory()
-            self.stage_np = self.stage.numpy()
-            self.text = torch.empty(cap, dtype=torch.uint8, device=self.device)
+        if self.text is None or self.text.numel() < nbytes:
+            self.text = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=self.device)
         need = int(self.L.mouse_parse_dump_ws_bytes(nbytes, self.n))
         if self.ws is None or self.ws.numel() < need:
             self.ws = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, device=self.device)
+
+    def _stage(self, i, nbytes):
+        st = self.stages[i]
+        if st is None or st[0].numel() < nbytes:
+            t = self.torch.empty(int(nbytes * 1.25) + 4096, dtype=self.torch.uint8).pin_memory()
+            st = self.stages[i] = (t, t.numpy())
+        return st
+
+    def _read(self, i, buf, b0, nbytes, wait=True):
+        """File bytes [b0, b0 + nbytes) -> staging buffer i; wait=False returns the futures of the read threads."""
+        import os
+        view_np = self._stage(i, nbytes)[1]
+        if self.fd is None:
+            np.copyto(view_np[:nbytes], buf[b0:b0 + nbytes])
+            return []
+        view = memoryview(view_np)
+
+        def chunk(a, b):
+            while a < b:
+                got = os.preadv(self.fd, [view[a:b]], b0 + a)
+                if got <= 0:
+                    raise IOError("short read of the dump file")
+                a += got
+
+        parts = self.read_threads if self.pool is not None and nbytes >= (1 << 20) else 1
+        if self.pool is None:
+            chunk(0, nbytes)
+            return []
+        cuts = [nbytes * k // parts for k in range(parts + 1)]
+        futs = [self.pool.submit(chunk, cuts[k], cuts[k + 1]) for k in range(parts)]
+        if wait:
+            for fut in futs:
+                fut.result()
+            return []
+        return futs
+
+    def _prefetch(self):
+        if self.next_range is None or self.pool is None or self.ahead is not None:
+            return
+        start, stop = self.next_range
+        self.next_range = None
+        if stop > start:
+            i = 1 - self.cur
+            self.ahead = (int(start), int(stop), i, self._read(i, None, int(start), int(stop - start), wait=False))
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.shutdown(wait=True)
+            self.pool = None
 
     def _run(self, nbytes, ncol, col_id, cxyz, cimg, mode, lo, hi, pos, img, expect):
         import ctypes as C
@@ -254,6 +330,7 @@ class DeviceDumpParser:
         nbytes = int(stop - b0)
         if nbytes <= 0 or nbytes >= 2 ** 31 or self.declined_in_a_row >= 3:
             self.frames_host += 1
+            self.next_range = None
             return None
         has_img = all(kk in keys for kk in ("ix", "iy", "iz"))
         cxyz = (C.c_int32 * 3)(*ci)
@@ -263,8 +340,21 @@ class DeviceDumpParser:
         hi = np.ascontiguousarray(hi, np.float64)
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self._room(nbytes)
-            np.copyto(self.stage_np[:nbytes], buf[b0:stop])          # page cache -> pinned, the only host pass
-            self.text[:nbytes].copy_(self.stage[:nbytes], non_blocking=True)
+            off = 0
+            if self.ahead is not None and self.ahead[0] <= b0 and self.ahead[1] == stop:
+                start, _, self.cur, futs = self.ahead        # read while the previous frame was on the GPU
+                self.ahead = None
+                for fut in futs:
+                    fut.result()
+                off = int(b0 - start)
+            else:
+                if self.ahead is not None:                   # (a range nobody asked for: let it finish, drop it)
+                    for fut in self.ahead[3]:
+                        fut.result()
+                    self.ahead = None
+                self._read(self.cur, buf, b0, nbytes)         # page cache -> pinned, the only host pass
+            self.text[:nbytes].copy_(self.stages[self.cur][0][off:off + nbytes], non_blocking=True)
+            self._prefetch()
             pos = torch.empty((self.n, 3), dtype=torch.float64, device=self.device)
             img = torch.empty((self.n, 3), dtype=torch.int32, device=self.device) if has_img else None
             args = (nbytes, len(keys), keys.index("id"), cxyz, cimg, mode, lo, hi, pos, img)
@@ -408,18 +498,24 @@ def iter_lmp_dump_frames(path, atom_num, coords_type="scaled", frames=None, inde
     rowmap = _RowMap(atom_num)
     if hi_f <= lo_f:
         return
-    dev_parser = DeviceDumpParser(rowmap, device) if device is not None else None
+    dev_parser = None
     import mmap
     with open(path, "rb") as f:
+        if device is not None:
+            dev_parser = DeviceDumpParser(rowmap, device, fd=f.fileno())
         mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
         buf = np.frombuffer(mm, dtype=np.uint8)       # the parser reads the mapped text in place
         try:
             for k in range(lo_f, hi_f):
+                if dev_parser is not None:
+                    dev_parser.next_range = (int(index[k + 1]), int(index[k + 2])) if k + 1 < hi_f else None
                 yield _parse_dump_frame(buf, int(index[k]), int(index[k + 1]), rowmap, coords_type, threads, dev_parser)
         finally:
-            if stats is not None and dev_parser is not None:
-                stats["frames_device"] = dev_parser.frames_device
-                stats["frames_host"] = dev_parser.frames_host
+            if dev_parser is not None:
+                dev_parser.close()
+                if stats is not None:
+                    stats["frames_device"] = dev_parser.frames_device
+                    stats["frames_host"] = dev_parser.frames_host
             del buf
             try:
                 mm.close()

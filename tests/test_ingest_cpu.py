@@ -177,3 +177,31 @@ def test_parse_doubles_is_correctly_rounded():
     assert L.mouse_parse_doubles(bad, len(bad), C.c_void_p(out.ctypes.data), out.size) == -(bad.index(b"abc") + 1)
     assert L.mouse_parse_doubles(b"1 2 3", 5, C.c_void_p(out.ctypes.data), 2) == -(4 + 1)     # does not fit
     assert L.mouse_parse_doubles(b"  \n", 3, C.c_void_p(out.ctypes.data), 2) == 0
+
+
+def test_threaded_frame_index_finds_exactly_the_line_starts(tmp_path):
+    """mouse_index_dump (memmem over several chunks) against a plain scan: matches inside a line do not count, matches
+    that straddle a chunk border are found once, the file size closes the index."""
+    rng = np.random.default_rng(5)
+    path = tmp_path / "idx.dump"
+    want, pos = [], 0
+    with open(path, "wb") as f:
+        for k in range(400):
+            head = b"ITEM: TIMESTEP\n%d\n" % k
+            want.append(pos)
+            body = b"".join(rng.choice([b"1 2 3\n", b"x ITEM: TIMESTEP\n", b"ITEM: TIMESTE\n", b"0.5 ITEM: ATOMS\n"],
+                                       size=int(rng.integers(500, 4000))))
+            f.write(head + body)
+            pos += len(head) + len(body)
+    index = ingest.index_lmp_dump(str(path))
+    assert index.dtype == np.int64 and index[-1] == pos and index[:-1].tolist() == want
+    import ctypes as C
+    from mouse_b200 import _lib
+    text = open(path, "rb").read()
+    L = _lib.lib()
+    for threads in (1, 2, 7, 16):
+        out = np.empty(len(want) + 5, np.int64)
+        assert L.mouse_index_dump(text, len(text), C.c_void_p(out.ctypes.data), len(out), threads) == len(want)
+        assert out[:len(want)].tolist() == want
+    out = np.empty(3, np.int64)          # a short array: the count is still complete
+    assert L.mouse_index_dump(text, len(text), C.c_void_p(out.ctypes.data), 3, 4) == len(want) and out.tolist() == want[:3]
