@@ -1,8 +1,8 @@
 // Device-side parser of the ATOMS block of a LAMMPS dump frame (file ingestion row).
 // The reference reads the block with one float() per token (lammpack_types.py:377-395) and applies
 // `lo + (hi - lo) * xs`; the host parser of api.cu (mouse_parse_dump_atoms) does the same in C.  Here the raw text of
-// the block is shipped to the GPU as it lies in the file (about half the bytes of the doubles it encodes per used
-// column, and no host parsing at all) and turned into ids / coordinates / image flags by four small kernels:
+// the block is shipped to the GPU as it lies in the file (no host parsing at all: the host only moves bytes from the
+// page cache into a pinned buffer) and turned into ids / coordinates / image flags by four small kernels:
 //   dump_count_lines_kernel   non-blank lines per 4 KB tile
 //   dump_scan_tiles_kernel    exclusive scan of the tile counts (one block), total -> status[0]
 //   dump_fill_lines_kernel    byte offset of every non-blank line, in file order
