@@ -397,6 +397,8 @@ def local_ordering_from_dump(topology, dump_path, bondtypes=None, rcut=0., coord
     from . import ingest
     dist, rank, world = _dist_state()
     device = torch.device(device or "cuda")
+    if device.type == "cuda" and device.index is None:      # resolved HERE: the producer thread has its own current device
+        device = torch.device("cuda", torch.cuda.current_device())
     index = ingest.index_lmp_dump(dump_path)
     n_frames = len(index) - 1
     lo, hi = shard_range(n_frames, rank, world)

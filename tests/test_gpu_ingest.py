@@ -149,3 +149,59 @@ def test_trajectory_from_a_dump_gives_the_same_S_with_either_parser(tmp_path):
     assert sd == {"frames_device": 7, "frames_host": 0} and sh == {}
     assert dev == host and len(dev) == 7
     assert tot_d.n_pairs == tot_h.n_pairs and tot_d.mean_s == tot_h.mean_s
+
+
+def _melt_dump(tmp_path, nframes=9):
+    from mouse_b200.frames import FrameArrays
+    from mouse_b200.melt import jitter, make_melt
+    melt = make_melt(40, 51, seed=8)
+    half = melt.box / 2
+    rng = np.random.default_rng(1)
+    frames = []
+    for k in range(nframes):
+        xs = (jitter(melt, k, 0.03) + half) / melt.box
+        order = rng.permutation(melt.n_atoms) if k % 3 == 1 else np.arange(melt.n_atoms)
+        frames.append((10 * k, melt.n_atoms, ["%d 1 %.9g %.9g %.9g" % (i + 1, xs[i, 0], xs[i, 1], xs[i, 2])
+                                             for i in order], "\n"))
+    path = str(tmp_path / "ranks.dump")
+    _write_dump(path, frames, keys="id type xs ys zs", lo=tuple(-half), hi=tuple(half))
+    return FrameArrays.from_melt(melt), path
+
+
+def _two_rank_dump_worker(rank, world, port, path, out):
+    import torch.distributed as dist
+    from mouse_b200.frames import FrameArrays
+    from mouse_b200.melt import make_melt
+    from mouse_b200.trajectory import local_ordering_from_dump
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    top = FrameArrays.from_melt(make_melt(40, 51, seed=8))
+    stats = {}
+    s_all, tot = local_ordering_from_dump(top, path, ["1"], 2.0, "scaled", gather=True, stats=stats)   # device=None
+    out[rank] = (s_all.tolist(), tot.n_pairs, tot.n_refs, tot.n_frames, dict(stats))
+    dist.destroy_process_group()
+
+
+def test_two_ranks_parse_their_own_frames_on_their_own_gpu(tmp_path):
+    """A dump sharded over two ranks: every rank seeks to its block of frames, parses it on ITS device (the parser runs
+    on a producer thread, whose current device is not the caller's) and the gathered per-frame S is the one-rank list."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    from mouse_b200.trajectory import local_ordering_from_dump
+    top, path = _melt_dump(tmp_path)
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    port = 29700 + os.getpid() % 90
+    procs = [ctx.Process(target=_two_rank_dump_worker, args=(r, 2, port, path, out)) for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(300) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    per_frame, tot = local_ordering_from_dump(top, path, ["1"], 2.0, "scaled", parse_on="host")
+    want = [s for _, s in per_frame]
+    assert len(want) == 9
+    for r in range(2):
+        s_r, npairs, nrefs, nfr, stats = out[r]
+        assert s_r == want and (npairs, nrefs, nfr) == (tot.n_pairs, tot.n_refs, 9)
+        assert stats["frames_host"] == 0 and stats["frames_device"] in (4, 5)
