@@ -427,6 +427,71 @@ def measure_small_config(dev, positions_list, bond_atoms, molb, box, rcut, steps
                 cell_grid=list(b.grid.ncell_axis), fast=int(b.grid.fast), triclinic=int(b.grid.triclinic))
 
 
+def measure_dump_ingest(dev, melt, rcut, nframes=48):
+    """File ingestion row on config 3's frame size: a LAMMPS dump (scaled coordinates, %.8g - LAMMPS' own default is
+    %g) of `nframes` frames is written to the temp directory, then read back (a) by the device-side parser - raw text
+    over PCIe, positions born on the GPU -, (b) by the host parser on one and on all usable threads, and (c) end to
+    end through local_ordering_from_dump (index + parse + K1-K4 + totals).  Host wall clock: this leg is host-bound."""
+    import io
+    import tempfile
+    import time
+    import torch
+    from mouse_b200 import ingest
+    from mouse_b200.frames import FrameArrays
+    from mouse_b200.trajectory import local_ordering_from_dump
+    top = FrameArrays.from_melt(melt)
+    half = melt.box / 2
+    xs = (melt.positions + half) / melt.box
+    body = io.BytesIO()
+    np.savetxt(body, np.column_stack([np.arange(1, melt.n_atoms + 1), np.ones(melt.n_atoms), xs, melt.images]),
+               fmt="%d %d %.8g %.8g %.8g %d %d %d")
+    body = body.getvalue()
+    path = os.path.join(tempfile.gettempdir(), "mouse_b200_bench_%d.dump" % os.getpid())
+    try:
+        with open(path, "wb") as f:
+            for k in range(nframes):
+                f.write(("ITEM: TIMESTEP\n%d\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n" % (1000 * k, melt.n_atoms)).encode())
+                f.write("".join("%.10g %.10g\n" % (-half[a], half[a]) for a in range(3)).encode())
+                f.write(b"ITEM: ATOMS id type xs ys zs ix iy iz\n")
+                f.write(body)
+        t0 = time.perf_counter()
+        index = ingest.index_lmp_dump(path)
+        index_ms = 1e3 * (time.perf_counter() - t0)
+        cores = max(1, min(16, os.cpu_count() or 1))
+
+        def sweep(**kw):
+            t0 = time.perf_counter()
+            n = sum(1 for _ in ingest.iter_lmp_dump_frames(path, top.atom_num, "scaled", index=index, **kw))
+            torch.cuda.synchronize()
+            return 1e3 * (time.perf_counter() - t0) / n
+
+        stats = {}
+        sweep(device=dev)                                    # warms the pinned buffers and the allocator
+        dev_ms = sweep(device=dev, stats=stats)
+        host1_ms = sweep(frames=(0, 3), threads=1)
+        hostn_ms = sweep(threads=cores)
+        e2e = {}
+        for parse_on in ("device", "host"):
+            local_ordering_from_dump(top, path, ["1"], rcut, "scaled", device=dev, parse_on=parse_on)
+            t0 = time.perf_counter()
+            per_frame, tot = local_ordering_from_dump(top, path, ["1"], rcut, "scaled", device=dev, parse_on=parse_on)
+            e2e[parse_on] = (1e3 * (time.perf_counter() - t0) / tot.n_frames, per_frame[0][1], tot.n_pairs)
+        assert e2e["device"][1:] == e2e["host"][1:]          # same S, same pair count whichever parser fed the frames
+        return dict(workload="LAMMPS dump of %d frames x %d atoms (%.1f MB of text per frame), scaled coordinates, image "
+                             "flags; host wall clock" % (nframes, melt.n_atoms, len(body) / 1e6),
+                    text_mb_per_frame=len(body) / 1e6, index_ms_per_frame=index_ms / nframes,
+                    device_parse_ms_per_frame=dev_ms, device_parser_frames=stats,
+                    host_parse_ms_per_frame_1_thread=host1_ms, host_parse_ms_per_frame_all_threads=hostn_ms,
+                    host_threads=cores, trajectory_ms_per_frame_device_parser=e2e["device"][0],
+                    trajectory_ms_per_frame_host_parser=e2e["host"][0], S_frame0=e2e["device"][1],
+                    how="device parser: page cache -> pinned buffer (pread threads, next frame prefetched) -> H2D of the "
+                        "raw text -> 4 kernels (dump_parse.cu) -> CUDA positions -> FramePipeline; bit-identical to the "
+                        "host parser (tests/test_gpu_ingest.py)")
+    finally:
+        if os.path.exists(path):
+            os.remove(path)
+
+
 def bench_other_configs(dev, world, rank, sms, f_clk, dist):
     """Driver-timed sub-measurements of BASELINE configs 3, 4 and 5 (inputs resident in HBM, CUDA events)."""
     import torch
@@ -454,6 +519,7 @@ def bench_other_configs(dev, world, rank, sms, f_clk, dist):
         out["note"] = "configs 4 and 5 are single-frame workloads (replicas only): measured at N=1"
         return out
     del frames
+    out["config3_from_dump"] = measure_dump_ingest(dev, melt, CONFIG3["rcut"])
     # ---- config 5: 8M bonds, rc = 3 sigma, bond-type neighbour set, residue-type references, other-molecule pairs
     for key, tri in (("config5_orthorhombic", False), ("config5_triclinic", True)):
         cfg = config5(tri)
