@@ -232,6 +232,15 @@ int64_t mouse_parse_dump_atoms(const char *text /*HOST*/, int64_t len, int64_t n
                                const int32_t *col_xyz, const int32_t *col_img, int32_t mode, const double *lo,
                                const double *hi, int64_t *ids, double *xyz, int32_t *img, int32_t nthreads);
 
+/* HOST only.  One section of a LAMMPS data file (the per-line readers AtomFromLmpDataLine / BondFromLmpDataLine,
+ * lammpack_lmp_functions.py:3-33, called from lammpack_types.py:400-464): nrows lines of exactly ncol tokens; column
+ * cols[w] -> outs[w][row] as double (kinds[w] == 0, correctly rounded) or as int64 (kinds[w] == 1, canonical integers
+ * only, so that the token can be printed back: types and molecule ids are strings in the reference).  *consumed = bytes
+ * of the block.  Returns nrows, or < 0 when the block has another shape (the caller takes its line-by-line path). */
+int64_t mouse_parse_table(const char *text /*HOST*/, int64_t len, int64_t nrows, int32_t ncol, int32_t nwant,
+                          const int32_t *cols, const int32_t *kinds, void *const *outs, int64_t *consumed,
+                          int32_t nthreads);
+
 /* HOST only.  Frame index of a LAMMPS dump (lammpack_types.py:344-398 walks the file line by line looking for
  * `ITEM: TIMESTEP`): byte offset of every line that starts with it, ascending, found with nthreads host threads.
  * Returns the number of frames; only the first `cap` offsets are written to out (call again with a larger array). */

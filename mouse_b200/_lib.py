@@ -51,7 +51,7 @@ EXPORTS = [
     "mouse_p2_frame", "mouse_p2_frame_timed", "mouse_p2_frame_graph_create", "mouse_p2_frame_graph_launch",
     "mouse_p2_frame_graph_nodes", "mouse_p2_frame_graph_destroy", "mouse_rdf_frame_timed", "mouse_rdf_frame", "mouse_single_ref_workspace_bytes", "mouse_p2_single_ref",
     "mouse_rdf_single_ref", "mouse_director_p2", "mouse_atom_colour", "mouse_debug_counters", "mouse_parse_doubles", "mouse_parse_doubles_mt", "mouse_parse_dump_atoms",
-    "mouse_parse_dump_ws_bytes", "mouse_parse_dump_atoms_dev", "mouse_index_dump",
+    "mouse_parse_dump_ws_bytes", "mouse_parse_dump_atoms_dev", "mouse_index_dump", "mouse_parse_table",
 ]
 
 
@@ -112,6 +112,8 @@ def lib():
     L.mouse_parse_doubles_mt.restype = i64
     L.mouse_parse_dump_atoms.argtypes = [vp, i64, i64, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32]
     L.mouse_parse_dump_atoms.restype = i64
+    L.mouse_parse_table.argtypes = [vp, i64, i64, i32, i32, vp, vp, vp, vp, i32]
+    L.mouse_parse_table.restype = i64
     L.mouse_index_dump.argtypes = [vp, i64, vp, i64, i32]
     L.mouse_index_dump.restype = i64
     L.mouse_parse_dump_ws_bytes.argtypes = [i64, i64]

@@ -563,6 +563,112 @@ extern "C" int64_t mouse_parse_doubles_mt(const char *text, int64_t len, double 
   return first[nthreads];
 }
 
+// A section of a LAMMPS data file (Atoms, Bonds: lammpack_types.py:400-464 reads them line by line with
+// AtomFromLmpDataLine / BondFromLmpDataLine, lammpack_lmp_functions.py:3-33): `nrows` consecutive lines of exactly
+// `ncol` whitespace-separated tokens; the `nwant` columns cols[] go to the arrays outs[] - kind 0: a decimal number as a
+// correctly rounded double (mouse_parse_token), kind 1: an integer in CANONICAL form ([-]digits, no plus sign, no
+// leading zeros, at most 18 digits) as int64, so that printing the value gives the token back (types and molecule ids
+// are strings in the reference).  Tokens of the other columns are skipped unread.  *consumed = bytes up to and including
+// the newline of the last line.  Returns nrows, or a negative number when the block is not of that shape (blank or
+// ragged line, a wanted token of another form, fewer lines): the caller then takes the general line-by-line path.
+extern "C" int64_t mouse_parse_table(const char *text, int64_t len, int64_t nrows, int32_t ncol, int32_t nwant,
+                                     const int32_t *cols, const int32_t *kinds, void *const *outs, int64_t *consumed,
+                                     int32_t nthreads) {
+  if (!text || len < 0 || nrows < 0 || ncol < 1 || nwant < 0 || nwant > 16 || (nwant && (!cols || !kinds || !outs)))
+    return -1;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 64) nthreads = 64;
+  if (nrows < 4096) nthreads = 1;
+  std::vector<int> want(ncol, -1);
+  for (int w = 0; w < nwant; ++w) {
+    if (cols[w] < 0 || cols[w] >= ncol || want[cols[w]] >= 0 || (kinds[w] != 0 && kinds[w] != 1)) return -1;
+    want[cols[w]] = w;
+  }
+  // extent of the block and the first byte of every thread's share of the lines
+  std::vector<int64_t> cut(nthreads + 1, 0), row0(nthreads + 1, 0);
+  {
+    const char *p = text, *end = text + len;
+    int t = 1;
+    for (int64_t r = 0; r < nrows; ++r) {
+      if (p >= end) return -1 - len;
+      while (t < nthreads && r == nrows * t / nthreads) {
+        cut[t] = p - text;
+        row0[t] = r;
+        ++t;
+      }
+      const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+      p = nl ? nl + 1 : end;
+    }
+    for (; t <= nthreads; ++t) {
+      cut[t] = p - text;
+      row0[t] = nrows;
+    }
+  }
+  if (consumed) *consumed = cut[nthreads];
+  std::vector<int64_t> result(nthreads, 0);
+  auto parse_chunk = [&](int t) {
+    const char *s = text + cut[t], *end = text + cut[t + 1];
+    for (int64_t row = row0[t]; row < row0[t + 1]; ++row) {
+      const char *eol = (const char *)memchr(s, '\n', (size_t)(end - s));
+      if (!eol) eol = end;
+      const char *q = s;
+      int col = 0;
+      for (;;) {
+        while (q < eol && mouse_is_ws(*q)) ++q;
+        if (q >= eol) break;
+        if (col >= ncol) {
+          result[t] = -((int64_t)(s - text) + 2);
+          return;
+        }
+        const int w = want[col];
+        if (w < 0) {
+          while (q < eol && !mouse_is_ws(*q)) ++q;
+        } else if (kinds[w] == 0) {
+          double v;
+          const char *next = mouse_parse_token(q, eol, &v);
+          if (!next) {
+            result[t] = -((int64_t)(s - text) + 2);
+            return;
+          }
+          ((double *)outs[w])[row] = v;
+          q = next;
+        } else {
+          const char *d = q;
+          const bool neg = *d == '-';
+          if (neg) ++d;
+          const char *first = d;
+          int64_t v = 0;
+          while (d < eol && *d >= '0' && *d <= '9') v = v * 10 + (*d++ - '0');
+          const int nd = (int)(d - first);
+          if (nd < 1 || nd > 18 || (nd > 1 && *first == '0') || (neg && nd == 1 && *first == '0') ||
+              (d < eol && !mouse_is_ws(*d))) {
+            result[t] = -((int64_t)(s - text) + 2);      // "+1", "01", "-0", "1.0", "C3": not canonical
+            return;
+          }
+          ((int64_t *)outs[w])[row] = neg ? -v : v;
+          q = d;
+        }
+        ++col;
+      }
+      if (col != ncol) {                                  // blank or ragged line
+        result[t] = -((int64_t)(s - text) + 2);
+        return;
+      }
+      s = eol < end ? eol + 1 : end;
+    }
+  };
+  if (nthreads == 1) {
+    parse_chunk(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) pool.emplace_back(parse_chunk, t);
+    for (auto &th : pool) th.join();
+  }
+  for (int t = 0; t < nthreads; ++t)
+    if (result[t] < 0) return result[t];
+  return nrows;
+}
+
 // Byte offset of every `ITEM: TIMESTEP` line of a dump (the frame index of ingest.index_lmp_dump): memmem over
 // nthreads chunks of the (memory-mapped) file, matches kept when they open a line.  Returns the number of frames found;
 // only the first `cap` offsets are written.

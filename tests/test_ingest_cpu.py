@@ -205,3 +205,63 @@ def test_threaded_frame_index_finds_exactly_the_line_starts(tmp_path):
         assert out[:len(want)].tolist() == want
     out = np.empty(3, np.int64)          # a short array: the count is still complete
     assert L.mouse_index_dump(text, len(text), C.c_void_p(out.ctypes.data), 3, 4) == len(want) and out.tolist() == want[:3]
+
+
+def _same_frame_arrays(a, b):
+    for k in ("positions", "box", "atom_num", "bond_atoms", "bond_num"):
+        x, y = getattr(a, k), getattr(b, k)
+        assert x.dtype == y.dtype and x.shape == y.shape and np.array_equal(x, y), k
+    for k in ("atom_type", "atom_mol", "atom_res", "bond_type"):
+        assert list(getattr(a, k)) == list(getattr(b, k)), k
+
+
+def test_table_reader_of_data_files_equals_the_line_reader(tmp_path):
+    """read_lmp_data_arrays takes files of the plain LAMMPS shape through mouse_parse_table (threaded, in place) and
+    everything else through the line-by-line reader: same arrays, same token strings either way."""
+    import glob
+    from mouse_b200.melt import make_melt, write_lammps_data
+    for path in sorted(glob.glob(os.path.join(os.path.dirname(DATA), "*.data"))):
+        _same_frame_arrays(ingest.read_lmp_data_arrays(path), ingest.read_lmp_data_arrays(path, fast=False))
+    melt = make_melt(60, 80, seed=4)                       # 4800 atoms: the threaded branch of the table parser
+    plain = str(tmp_path / "plain.data")
+    write_lammps_data(melt, plain)
+    assert ingest._read_lmp_data_fast(plain, True, 5) is not None
+    for threads in (1, 3, 8):
+        _same_frame_arrays(ingest.read_lmp_data_arrays(plain, threads=threads), ingest.read_lmp_data_arrays(plain, fast=False))
+    text = open(plain).read()
+    head, rest = text.split("Atoms", 1)
+    atoms, bonds = rest.split("Bonds", 1)
+    atom_lines = atoms.split("\n")[2:]
+    atom_lines = atom_lines[:melt.n_atoms]
+    bond_lines = bonds.split("\n")[2:][:melt.n_bonds]
+
+    def build(alines, blines, between="", after="", atoms_head="Atoms # molecular"):
+        return head + atoms_head + "\n\n" + "\n".join(alines) + "\n" + between + "\nBonds\n\n" + "\n".join(blines) + "\n" + after
+
+    variants = {
+        # shapes the table parser takes
+        "velocities": (build(atom_lines, bond_lines, between="\nVelocities\n\n" + "\n".join(
+            "%d 0.1 -0.2 0.3" % (i + 1) for i in range(melt.n_atoms)) + "\n"), True),
+        "charge": (build([" ".join(ln.split()[:3] + ["-0.5"] + ln.split()[3:]) for ln in atom_lines], bond_lines), True),
+        "angles_after": (build(atom_lines, bond_lines, after="\nAngles\n\n1 1 1 2 3\n"), True),
+        "negative_mol": (build([" ".join([ln.split()[0], "-7"] + ln.split()[2:]) for ln in atom_lines], bond_lines), True),
+        # shapes it declines: the line reader decides (same result, or the same exception)
+        "type_label": (build([" ".join(ln.split()[:2] + ["CA"] + ln.split()[3:]) for ln in atom_lines], bond_lines), False),
+        "leading_zero": (build([" ".join(ln.split()[:2] + ["01"] + ln.split()[3:]) for ln in atom_lines], bond_lines), False),
+        "plus_sign": (build(atom_lines, [" ".join([w[0], "+1"] + w[2:]) for w in (ln.split() for ln in bond_lines)]), False),
+        "ragged": (build([ln + (" 9" if k == 17 else "") for k, ln in enumerate(atom_lines)], bond_lines), False),
+        "bonds_first": (head + "Bonds\n\n" + "\n".join(bond_lines) + "\n\nAtoms\n\n" + "\n".join(atom_lines) + "\n", False),
+        "header_word_later": (build(atom_lines, bond_lines, after="\n5 atoms\n"), False),
+    }
+    for name, (body, takes) in variants.items():
+        path = str(tmp_path / (name + ".data"))
+        with open(path, "w") as f:
+            f.write(body)
+        assert (ingest._read_lmp_data_fast(path, True, 4) is not None) == takes, name
+        try:
+            want = ingest.read_lmp_data_arrays(path, fast=False)
+        except Exception as e:      # noqa: BLE001 - whatever the line reader raises, the default entry raises too
+            with pytest.raises(type(e)):
+                ingest.read_lmp_data_arrays(path)
+            continue
+        _same_frame_arrays(ingest.read_lmp_data_arrays(path), want)
