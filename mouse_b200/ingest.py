@@ -350,6 +350,8 @@ class DeviceDumpParser:
     ``parse`` returns None for a frame the device parser does not take (tokens outside the exact fast path of the
     number parser, wrong line or column counts): the caller then uses the host parser, which is authoritative."""
 
+    max_declines = 3       # frames declined in a row after which the text is no longer shipped (17-digit dumps)
+
     def __init__(self, rowmap: "_RowMap", device, fd=None, read_threads=4):
         import torch
         from . import _lib
@@ -458,7 +460,7 @@ class DeviceDumpParser:
         import ctypes as C
         torch = self.torch
         nbytes = int(stop - b0)
-        if nbytes <= 0 or nbytes >= 2 ** 31 or self.declined_in_a_row >= 3:
+        if nbytes <= 0 or nbytes >= 2 ** 31 or self.declined_in_a_row >= self.max_declines:
             self.frames_host += 1
             self.next_range = None
             return None

@@ -205,3 +205,81 @@ def test_two_ranks_parse_their_own_frames_on_their_own_gpu(tmp_path):
         s_r, npairs, nrefs, nfr, stats = out[r]
         assert s_r == want and (npairs, nrefs, nfr) == (tot.n_pairs, tot.n_refs, 9)
         assert stats["frames_host"] == 0 and stats["frames_device"] in (4, 5)
+
+
+def test_token_grammar_fuzz_device_equals_host_or_declines(tmp_path, monkeypatch):
+    """Every spelling of a number the host parser accepts: the device parser gives the same bits or declines the frame
+    (then the host parser's values are what the caller sees).  One small frame per spelling mix."""
+    monkeypatch.setattr(ingest.DeviceDumpParser, "max_declines", 10 ** 9)
+    rng = np.random.default_rng(2024)
+    n = 96
+    num = np.arange(1, n + 1)
+
+    def spell(v, kind):
+        if kind == 0:
+            return "%.*g" % (int(rng.integers(1, 16)), v)
+        if kind == 1:
+            return "%.*e" % (int(rng.integers(0, 15)), v)
+        if kind == 2:
+            return "%.*f" % (int(rng.integers(0, 20)), v)
+        if kind == 3:
+            return ("%.*E" % (int(rng.integers(0, 12)), v)).replace("E+", "E").replace("E0", "E")
+        if kind == 4:                                   # bare point forms: "5.", ".5", "-.25"
+            t = "%.6f" % v
+            t = t.rstrip("0")
+            return t.replace("0.", ".", 1) if abs(v) < 1 and rng.random() < 0.7 else t
+        if kind == 5:
+            return "%+.*g" % (int(rng.integers(1, 16)), v)
+        if kind == 6:                                   # zeros in many shapes
+            return str(rng.choice(["0", "-0", "0.0", "-0.0", "+0", "0e0", "0.000e-5", "-.0", "00", "000.5", "0e30"]))
+        if kind == 7:                                   # limits of the exact path and just beyond
+            return str(rng.choice(["1e22", "1e23", "1e-22", "1e-23", "123456789012345", "1234567890123456",
+                                   "0.123456789012345", "0.1234567890123456", "999999999999999e7", "999999999999999e8",
+                                   "1e-300", "4.9e-324", "1.7976931348623157e308", "1e400", "0." + "0" * 25 + "1",
+                                   "9007199254740993", "1" + "0" * 22, "0.3e-22"]))
+        if kind == 8:
+            return repr(float(v))                       # 16-17 digits
+        return str(rng.choice(["nan", "inf", "-inf", "1e", "1e+", "--1", "1.2.3", "0x10", "1_0", "1d5", "NaN"]))
+
+    frames, expect_decline = [], []
+    for k in range(120):
+        if k % 10 == 0:
+            kinds = [9, 0, 0]
+        elif k % 2:
+            kinds = rng.choice([0, 1, 3, 4, 5, 6], size=3)          # spellings inside the exact path: device frames
+        else:
+            kinds = rng.choice(9, size=3, p=[.2, .15, .15, .1, .1, .1, .08, .07, .05])
+        # (15 digits at 1e-9 need 10^-23: outside the exact path - the odd frames stay at magnitudes LAMMPS dumps have)
+        x = rng.standard_normal((n, 3)) * 10.0 ** (rng.integers(-2, 4) if k % 2 else rng.integers(-8, 8))
+        lines = []
+        for i in range(n):
+            tok = [spell(x[i, a], int(kinds[a])) for a in range(3)]
+            if k % 10 == 0 and i != n // 2:
+                tok[0] = "0.5"                          # ONE malformed token in the frame
+            lines.append("%d 1 %s %s %s" % (num[i], tok[0], tok[1], tok[2]))
+        frames.append((k, n, lines, "\n"))
+    path = tmp_path / "fuzz.dump"
+    _write_dump(path, frames, keys="id type xu yu zu")
+    index = ingest.index_lmp_dump(str(path))
+    ndev = nhost = nraise = 0
+    for k in range(len(frames)):
+        got = []
+        for device in (None, "cuda"):
+            st = {}
+            try:
+                fr = [(ts, pos.cpu().numpy() if isinstance(pos, torch.Tensor) else pos)
+                      for ts, _, _, pos, _ in ingest.iter_lmp_dump_frames(str(path), num, "uncut", frames=(k, k + 1),
+                                                                         index=index, device=device, stats=st)]
+                got.append((fr, st))
+            except Exception as e:      # noqa: BLE001
+                got.append(type(e))
+        if isinstance(got[0], type):
+            assert got[1] is got[0]
+            nraise += 1
+            continue
+        (host, _), (dev, st) = got
+        assert host[0][0] == dev[0][0] == k
+        assert np.array_equal(host[0][1].view(np.int64), dev[0][1].view(np.int64)), frames[k][2][:3]
+        ndev += st["frames_device"]
+        nhost += st["frames_host"]
+    assert nraise >= 6 and ndev >= 30 and nhost >= 20, (nraise, ndev, nhost)
