@@ -43,7 +43,8 @@ W_LANE_INSTR_PER_PAIR = 55.2      # 6.45 x 7 FP32 + 10 FP64 la
 W5_LANE_INSTR_PER_PAIR = 60.2     # K5: 6.45 x 7 FP32 filter + 15 per counted pair (FP64 d^2, bin, count)
 BYTES_PER_BOND = 72.0             # compulsory HBM bytes per bond per frame
 N_FRAME_VARIANTS = 4              # distinct frames cycled (working set per frame ~210 MB > 126 MB L2)
-LANES = int(os.environ.get("MOUSE_BENCH_LANES", "3"))                         # frames in flight in the device-resident timed region (own stream + workspace each)
+LANES_SMALL = int(os.environ.get("MOUSE_BENCH_LANES_SMALL", "6"))             # ... for config 3's 250k-bond frames (the tail of a short sweep is a larger share)
+LANES = int(os.environ.get("MOUSE_BENCH_LANES", "4"))                         # frames in flight in the device-resident timed region (own stream + workspace each)
 KERNELS_PER_FRAME = 9             # bond_assign, scan_reduce, scan_apply2, scatter_idx, place, items, sweep, fixup, finish+reduce
 
 
@@ -504,13 +505,13 @@ def bench_other_configs(dev, world, rank, sms, f_clk, dist):
     melt = make_melt(CONFIG3["chains"], CONFIG3["beads"], seed=0)
     frames = [jitter(melt, rank * 8 + f, 0.02) for f in range(8)]
     r = measure_small_config(dev, frames, melt.bond_atoms, melt.mol[melt.bond_atoms[:, 0]], melt.box, CONFIG3["rcut"],
-                             steps=200, warm=20)
+                             steps=200, warm=20, lanes=LANES_SMALL)
     t = torch.tensor([r["ms_per_frame"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     out["config3"] = dict(workload="250k-bond melt frames (2500 x 101 beads), rc=2.5, frames sharded over %d rank(s), %d in "
-                                   "flight per GPU" % (world, LANES), bonds_per_frame=melt.n_bonds, ms_per_frame=ms,
+                                   "flight per GPU" % (world, LANES_SMALL), bonds_per_frame=melt.n_bonds, ms_per_frame=ms,
                           frames_per_s=world * 1e3 / ms, pairs_per_s=world * r["pairs_per_frame"] / (ms * 1e-3),
                           serial_frame_ms=r["serial_frame_ms"], sweep_ms=r["sweep_ms"], pairs_per_frame=r["pairs_per_frame"],
                           trajectory_10k_frames_s=10000 * ms * 1e-3 / world, cell_grid=r["cell_grid"], S=r["S"],
