@@ -374,6 +374,56 @@ def pair_correlation_trajectory(frames_positions, type_code, mol, ntypes, box, r
     return totals.rdf_hist, edges, totals
 
 
+def pair_correlation_from_dump(topology, dump_path, rmin, rmax, nbin, atomtypes=None, coords_type="scaled",
+                               same_molecule=True, device=None, parse_on="device", parse_threads=None, stats=None):
+    """RDF pair histograms summed over the frames of a LAMMPS dump (``CalculatePairCorrelationFunctions`` per frame,
+    ``ordering_functions.py:122-177``, fed by ``return_extra_frames_from_lmp_dump``, ``lammpack_types.py:344-398``).
+    ``topology``: ``FrameArrays`` of the data file; ``atomtypes``: the atom types taken into account (None / empty:
+    all, ``:134-139``) - they get the type codes 0.. in sorted order, and the histogram rows are the reference's
+    ``"ti_tj"`` pairs in that order.  Every frame carries its own box: the grid is planned per frame for the last bin
+    edge.  Frames are block-sharded over the ranks by the dump's byte-offset index, parsed on the rank's GPU
+    (``parse_on="device"``) or by the host parser, histograms are summed on the device and all-reduced once.
+    Returns (hist int64 [npairs, nbin], edges, type names, TrajectoryTotals with ``n_frames``)."""
+    import os
+    from . import ingest
+    dist, rank, world = _dist_state()
+    device = torch.device(device or "cuda")
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    index = ingest.index_lmp_dump(dump_path)
+    lo, hi = shard_range(len(index) - 1, rank, world)
+    types = np.asarray([str(t) for t in topology.atom_type], dtype=object)
+    wanted = sorted(set(types.tolist()) if not atomtypes else set(str(t) for t in atomtypes) & set(types.tolist()))
+    code_of = {t: k for k, t in enumerate(wanted)}
+    keep = np.array([t in code_of for t in types.tolist()], bool)
+    rows = np.nonzero(keep)[0]
+    ntypes = max(len(wanted), 1)
+    tcode = torch.as_tensor(np.array([code_of[t] for t in types[rows].tolist()], np.int32)).to(device)
+    mcode = torch.as_tensor(np.ascontiguousarray(topology.atom_mol_code()[rows], np.int32)).to(device)
+    rows_dev = None if keep.all() else torch.as_tensor(rows).to(device)
+    npairs = ntypes * (ntypes + 1) // 2
+    acc = torch.zeros((npairs, int(nbin)), dtype=torch.int64, device=device)
+    edges = np.ascontiguousarray(np.histogram_bin_edges(np.zeros(0), bins=int(nbin), range=(rmin, rmax)), np.float64)
+    totals = TrajectoryTotals()
+    if parse_threads is None:
+        parse_threads = max(1, min(16, (os.cpu_count() or 1) // max(world, 1)))
+    if hi > lo and len(rows):
+        for _, box, _, pos, _ in ingest.iter_lmp_dump_frames(dump_path, topology.atom_num, coords_type, frames=(lo, hi),
+                                                             index=index, threads=parse_threads,
+                                                             device=device if parse_on == "device" else None,
+                                                             stats=stats):
+            pos = engine.as_dev(pos, torch.float64, device)
+            if rows_dev is not None:
+                pos = pos.index_select(0, rows_dev)
+            h, _ = engine.rdf_frame(pos, tcode, mcode, ntypes, box, rmin, rmax, nbin, same_molecule=same_molecule,
+                                    device=device)
+            acc += h
+            totals.n_frames += 1
+    totals.rdf_hist = acc.cpu().numpy()
+    totals = all_reduce_totals(totals, device)
+    return totals.rdf_hist, edges, wanted, totals
+
+
 def local_ordering_from_dump(topology, dump_path, bondtypes=None, rcut=0., coords_type="scaled",
                              reference_res_types=None, same_molecule=True, device=None, gather=False,
                              parse_threads=None, hist_args=None, parse_on="device", stats=None):

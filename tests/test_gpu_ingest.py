@@ -283,3 +283,43 @@ def test_token_grammar_fuzz_device_equals_host_or_declines(tmp_path, monkeypatch
         ndev += st["frames_device"]
         nhost += st["frames_host"]
     assert nraise >= 6 and ndev >= 30 and nhost >= 20, (nraise, ndev, nhost)
+
+
+def test_rdf_trajectory_from_a_dump_against_the_oracle(tmp_path):
+    """pair_correlation_from_dump: histograms summed over the frames of a dump, device parser and host parser, all
+    types and a type selection, against the C oracle on the host-parsed frames (integers: bit for bit)."""
+    from mouse_b200.frames import FrameArrays
+    from mouse_b200.melt import jitter, make_melt
+    from mouse_b200.trajectory import pair_correlation_from_dump
+    from oracle import c_oracle
+    melt = make_melt(30, 40, seed=9)
+    top = FrameArrays.from_melt(melt)
+    types = [str(1 + (i % 3)) for i in range(melt.n_atoms)]
+    top.atom_type = types
+    half = melt.box / 2
+    frames = []
+    for k in range(5):
+        xs = (jitter(melt, k, 0.04) + half) / melt.box
+        frames.append((k, melt.n_atoms, ["%d %s %.9g %.9g %.9g" % (i + 1, types[i], xs[i, 0], xs[i, 1], xs[i, 2])
+                                         for i in range(melt.n_atoms)], "\n"))
+    path = str(tmp_path / "rdf.dump")
+    _write_dump(path, frames, keys="id type xs ys zs", lo=tuple(-half), hi=tuple(half))
+    host_frames = list(ingest.iter_lmp_dump_frames(path, top.atom_num, "scaled"))
+    molc = top.atom_mol_code()
+    for sel, same in ((None, True), (["1", "3"], False)):
+        names = sorted(set(types)) if sel is None else sorted(sel)
+        code = {t: k for k, t in enumerate(names)}
+        rows = np.array([i for i, t in enumerate(types) if t in code])
+        tc = np.array([code[types[i]] for i in rows], np.int32)
+        want = 0
+        for _, box, _, pos, _ in host_frames:
+            h, edges = c_oracle.rdf(pos[rows], tc, molc[rows].astype(np.int64), len(names), box, 0.0, 2.5, 60,
+                                    same_molecule=same)
+            want = want + h
+        for parse_on in ("device", "host"):
+            st = {}
+            hist, e2, got_names, tot = pair_correlation_from_dump(top, path, 0.0, 2.5, 60, atomtypes=sel,
+                                                                  same_molecule=same, parse_on=parse_on, stats=st)
+            assert got_names == names and tot.n_frames == 5 and np.array_equal(e2, edges)
+            assert hist.dtype == np.int64 and np.array_equal(hist, want)
+            assert st == ({"frames_device": 5, "frames_host": 0} if parse_on == "device" else {})
