@@ -672,7 +672,8 @@ def run_ours(args):
     value = pairs_all / (ms * 1e-3)
 
     # ---- end-to-end through the host-buffer API (pinned host positions in, totals out, every step)
-    pipe = FramePipeline(melt.bond_atoms, molb, melt.box, rcut, n_atoms, same_molecule=True, device=dev)
+    pipe = FramePipeline(melt.bond_atoms, molb, melt.box, rcut, n_atoms, same_molecule=True, device=dev,
+                         depth=int(os.environ.get("MOUSE_PIPE_DEPTH", "3")))
     for k in range(warm):
         pipe.submit(frames_host[k % N_FRAME_VARIANTS])
     pipe.drain()
