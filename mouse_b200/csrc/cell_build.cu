@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(256) cell_assign_kernel(const double *__restri
   double xw, yw, zw;
   const int cid = cell_of_point(cx, cy, cz, g, xw, yw, zw);
   cell_of[b] = cid;
+  MOUSE_ASSERT(cid >= 0 && cid < g.ncell);
   rank_of[b] = atomicAdd(&cell_count[cid], 1);
   Rec r;
   r.p = payload_p(xw, yw, zw, g, type ? type[b] : 0);
@@ -409,6 +410,7 @@ __global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_scatter_idx_kernel(cons
   int cid = cell_of[b];
   if (cid < 0) return;
   bool is_ref = ref_mask ? (ref_mask[b] != 0) : true;
+  MOUSE_ASSERT(rank_of[b] >= 0 && cell_start[cid] + rank_of[b] < cell_start[cid + 1] && cell_start[cid + 1] <= n);
   idx_tmp[cell_start[cid] + rank_of[b]] = b | (is_ref ? (int32_t)0x80000000 : 0);
 }
 
@@ -441,6 +443,7 @@ __global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) cell_place_kernel(int ncell,
   int rank = 0;
   for (int k = s; k < e; ++k) rank += (idx_tmp[k] & 0x7fffffff) < mine;
   const int d = s + rank;
+  MOUSE_ASSERT(c >= 0 && c < ncell && s <= p && p < e && d >= s && d < e);
   Rec r = rec_tmp[mine];
   // .w carries the sorted slot itself: the sweep's register-resident candidates know where they live
   if (MODE == 0) r.u.w = __hiloint2double(0, d);
@@ -577,6 +580,7 @@ __global__ void __launch_bounds__(MOUSE_ITEM_BLOCK) bond_assign_kernel(const dou
   double xw, yw, zw;
   const int cid = cell_of_point(cx, cy, cz, g, xw, yw, zw);
   cell_of[b] = cid;
+  MOUSE_ASSERT(cid >= 0 && cid < g.ncell);
   rank_of[b] = atomicAdd(&cell_count[cid], 1);
   Rec r;
   r.p = payload_p(xw, yw, zw, g, mol ? mol[b] : 0);

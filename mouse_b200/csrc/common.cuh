@@ -9,6 +9,17 @@
 
 #define MOUSE_FULL_MASK 0xffffffffu
 
+// Checked build (make EXTRA=-DMOUSE_CHECKED): device-side assertions on the indices the kernels compute themselves
+// (landing-zone and queue slots, sorted-slot and cell indices, histogram bins, item rows).  compute-sanitizer is not
+// available on the GPU pool this was developed on; the GPU test suite run against the checked library is the bounds
+// evidence kept under profiles/.  In the normal build the macro expands to nothing.
+#ifdef MOUSE_CHECKED
+#include <assert.h>
+#define MOUSE_ASSERT(cond) assert(cond)
+#else
+#define MOUSE_ASSERT(cond) ((void)0)
+#endif
+
 // ------------------------------------------------------------------ error plumbing
 void mouse_set_error(const char *fmt, ...);
 int mouse_num_sms();      // SMs of the current device (p2_sweep.cu: per-device table of immutable facts)

@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(128) dump_parse_rows_kernel(const unsigned cha
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nrows || r >= status[0]) return;      // (fewer lines than expected: the caller sees status[0] != nrows)
   const int64_t start = line_off[r];
+  MOUSE_ASSERT(start >= 0 && start < len);
   int64_t s = start, end = start;
   while (end < len && t[end] != '\n') ++end;      // tokens never cross the end of the line
   int col = 0, slow = 0;
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(128) dump_parse_rows_kernel(const unsigned cha
   ids[r] = id;
   if (expect_ids && expect_ids[r] != id) atomicAdd((unsigned long long *)&status[3], 1ull);
   const int64_t d = row_of_line ? (int64_t)row_of_line[r] : r;
+  MOUSE_ASSERT(d >= 0 && d < nrows);
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     xyz[3 * d + a] = px[a];

@@ -446,6 +446,7 @@ __device__ __forceinline__ void hs_ref_loop(const SweepArgs &a, const HsConst k,
         for (int q = 0; q + w < HS_GRP; q += 2 * w) pv[q] += pv[q + w];
       // the 32 / HS_GRP partials of a reference go straight to the integer accumulators (no shuffle stages:
       // their latency would be exposed here, the extra atomics are not)
+      MOUSE_ASSERT(row >= nref || (hs + base + row >= 0 && hs + base + row < a.n));
       if (row < nref) hs_flush(a.acc_fix, a.acc_cnt, hs + base + row, pv[0], nv);
       __syncwarp();
     }
@@ -543,6 +544,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
   // arm the landing zone with chunk `ch` of item `it`: candidates [ch * LZ, min(T, ch * LZ + LZ))
   auto issue = [&](const HsItem &it, int ch) {
     const int w0 = ch * LZ, w1 = min(it.T, w0 + LZ);
+    MOUSE_ASSERT(ch >= 0 && w1 > w0 && w1 - w0 <= LZ);
     // WAR on the landing zone: every lane's shared-memory accesses to the previous contents were issued before the
     // __syncwarp() that precedes this call; the proxy fence orders them against the async-proxy writes
     fence_proxy_async();
@@ -551,6 +553,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     const int a0 = max(it.rt, w0), b0 = min(it.rt + it.rlen, w1);
     if (b0 > a0) {
       const int src = it.rsrc + (a0 - it.rt), cnt = b0 - a0, dst = a0 - w0;
+      MOUSE_ASSERT(dst >= 0 && dst + cnt <= LZ && src >= 0 && src + cnt <= a.n);
       tma_load_1d(&s_land[dst], a.R + src, (uint32_t)cnt * 48u, &s_bar);
     }
   };
@@ -612,10 +615,12 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
     if (fresh) {
       // ---- a new chunk has landed: drop the candidates no reference of the home cell can reach
       const int nland = min(cur.T - ch * LZ, LZ);
+      MOUSE_ASSERT(nland > 0 && cur.hs >= 0 && cur.nhome > 0 && rb >= 0 && rb < cur.nhome && cur.hs + cur.nhome <= a.n);
       mbar_wait(&s_bar, phase);
       phase ^= 1u;
       M = cur.boundary ? hs_cull<true>(smem_addr(s_land), smem_addr(s_sel), s_bb, a.g, lane, nland, cull_thr)
                        : hs_cull<false>(smem_addr(s_land), smem_addr(s_sel), s_bb, a.g, lane, nland, cull_thr);
+      MOUSE_ASSERT(M >= 0 && M <= nland);
       // the NC entries behind the survivors point at the filler record
 #pragma unroll
       for (int c = 0; c < SLOTS; ++c) s_sel[M + 32 * c + lane] = (uint16_t)(48 * LZ);
@@ -717,6 +722,7 @@ __global__ void __launch_bounds__(32, HS_WARPS) p2_sweep_half_kernel(const Sweep
 #pragma unroll
     for (int c = 0; c < SLOTS; ++c) {      // (slots that were not in use and fillers have a zero count: predicated off)
       const int g = s_gid[c][lane];
+      MOUSE_ASSERT(g < a.n && (g >= 0 || cntj[c] == 0));
       hs_flush(a.acc_fix, a.acc_cnt, g < 0 ? 0 : g, accj[c], cntj[c]);
     }
     if (!last) {
@@ -827,6 +833,7 @@ __global__ void __launch_bounds__(HS_FIXUP_THREADS) p2_fixup_kernel(const SweepA
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nfix; e += (long long)gridDim.x * blockDim.x) {
     const int2 pr = a.fix_list[e];
     const int si = pr.x & 0x7fffffff, sj = pr.y, kind = (unsigned)pr.x >> 31;
+    MOUSE_ASSERT(si < a.n && sj >= 0 && sj < a.n && si != sj);
     const double cs = exact_pair(a.idx, a.ctr, a.vec, n, a.g, si, sj);
     if (kind == 0) {
       if (cs != 0.0) {

@@ -131,6 +131,7 @@ struct RdfHalfArgs {
   float r2hi;            // loose FP32 filter: d2 < r2hi may be in range
   unsigned long long *hist;
   int64_t *counters;
+  int n;                 // items (checked build: bounds of the sorted array)
 };
 
 __global__ void rdf_thresholds_kernel(const double *__restrict__ edges, int nbin, double *__restrict__ thr) {
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(32 * RH_CTA_WARPS, RH_WARPS / RH_CTA_WARPS) rd
         const int a0 = max(cur.rt, w0), b0 = min(cur.rt + cur.rlen, w1);
         if (b0 > a0) {
           const int src = cur.rsrc + (a0 - cur.rt), cnt = b0 - a0, dst = a0 - w0;
+          MOUSE_ASSERT(dst >= 0 && dst + cnt <= NC && src >= 0 && src + cnt <= a.n);
           tma_load_1d(&s_land[dst], a.R + src, (uint32_t)cnt * 48u, &s_bar);
         }
       }
@@ -318,6 +320,7 @@ __global__ void __launch_bounds__(32 * RH_CTA_WARPS, RH_WARPS / RH_CTA_WARPS) rd
           act[r] = lane + 32 * r < navail;
           const unsigned e = act[r] ? (unsigned)s_q[(qh + (unsigned)(lane + 32 * r)) & (RH_QUEUE - 1)] : 0u;
           const int c = (e >> 5) & 15u, lj = e >> 9;
+          MOUSE_ASSERT(c < SLOTS && lj < 32 && (int)(e & 31u) < 32);
           ilr[r] = e & 31u;
           ui[r] = s_homeU[buf][ilr[r]];
           cand[r] = land_base + (uint32_t)(c * 32 + lj) * 48u;
@@ -374,6 +377,7 @@ __global__ void __launch_bounds__(32 * RH_CTA_WARPS, RH_WARPS / RH_CTA_WARPS) rd
             slot = (ta * a.ntypes - ta * (ta - 1) / 2 + (tb - ta)) * nbin;
           }
           if (keep) {
+            MOUSE_ASSERT(k >= 0 && k < nbin && slot >= 0 && slot + k < hsize);
             if (SMEM_HIST) reds_add(hist_base + 4u * (uint32_t)(slot + k), 2u);
             else atomicAdd(&a.hist[(size_t)(slot + k)], 2ULL);
           }
@@ -530,6 +534,7 @@ int mouse_launch_rdf_sweep(const mouse_grid_t *grid, uint32_t flags, int64_t n, 
     h.same_molecule = (flags & MOUSE_SAME_MOLECULE) ? 1 : 0;
     h.hist = (unsigned long long *)hist;
     h.counters = w.counters;
+    h.n = (int)n;
     // bin estimate and loose filter need the range on the host: grid->rcut is the last edge (engine.rdf_frame),
     // the first edge rides in through rdf_first
     h.first = (float)w.rdf_first;
