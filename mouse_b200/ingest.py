@@ -342,7 +342,8 @@ class _RowMap:
 
 class DeviceDumpParser:
     """The ATOMS block of a dump frame parsed ON THE GPU (``mouse_parse_dump_atoms_dev``, ``csrc/dump_parse.cu``):
-    the raw text goes from the page cache into one pinned staging buffer and over PCIe as it is, four small kernels
+    the raw text goes from the page cache into a pinned staging buffer (two of them: the next frame is read by a few
+    ``pread`` threads while this one is on the GPU) and over PCIe as it is, four small kernels
     turn it into ids / positions / image flags with the host parser's arithmetic (bit-identical values), and the
     positions come back as a CUDA tensor that ``FramePipeline.submit`` takes without another host round trip.  The
     id -> topology-row permutation of the previous frame stays on the device; the ids of a frame are compared with
