@@ -525,7 +525,18 @@ def bench_other_configs(dev, world, rank, sms, f_clk, dist):
         out["note"] = "configs 4 and 5 are single-frame workloads (replicas only): measured at N=1"
         return out
     del frames
-    out["config3_from_dump"] = measure_dump_ingest(dev, melt, CONFIG3["rcut"])
+    try:        # (a host-side leg with a 0.6 GB temporary file: never the reason for a bench run to fail)
+        import shutil
+        import tempfile
+        free = shutil.disk_usage(tempfile.gettempdir()).free
+        if free > (4 << 30):
+            out["config3_from_dump"] = measure_dump_ingest(dev, melt, CONFIG3["rcut"], nframes=48)
+        elif free > (1 << 30):
+            out["config3_from_dump"] = measure_dump_ingest(dev, melt, CONFIG3["rcut"], nframes=12)
+        else:
+            out["config3_from_dump"] = {"skipped": "less than 1 GB free in the temp directory"}
+    except Exception as e:      # noqa: BLE001
+        out["config3_from_dump"] = {"error": "%s: %s" % (type(e).__name__, e)}
     # ---- config 5: 8M bonds, rc = 3 sigma, bond-type neighbour set, residue-type references, other-molecule pairs
     for key, tri in (("config5_orthorhombic", False), ("config5_triclinic", True)):
         cfg = config5(tri)
